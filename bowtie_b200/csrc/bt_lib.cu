@@ -1,0 +1,476 @@
+/*
+ * bt_lib.cu — kernels and C ABI of libbowtie_b200.so (sm_100a).
+ *
+ *   bt_relayout_kernel   .ebwt sides -> 32-byte rank blocks (once per index load)
+ *   bt_search_kernel     persistent lanes, one read per thread, dynamic work queue
+ *   bt_collect_kernel    device-side list of reads whose scratch overflowed (for the retry pass)
+ *
+ * There is no host search path in this library: without a CUDA device every entry point fails.
+ */
+#include <cuda_runtime.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+#include <string>
+#include <vector>
+#include <mutex>
+
+#include "bt_native.cuh"
+#include "../../include/bowtie_b200.h"
+
+static_assert(sizeof(bt_policy_t) == sizeof(BtPolicy), "bt_policy_t and BtPolicy must share a layout");
+static_assert(BT_HIT_HDR_WORDS == BT_HIT_HDR, "hit header size");
+static_assert(sizeof(BtFrame) == 64, "BtFrame layout");
+
+/* ------------------------------------------------------------------------------------------- */
+/* kernels                                                                                      */
+/* ------------------------------------------------------------------------------------------- */
+
+__global__ void bt_relayout_kernel(BtNativeIndex n, uint32_t nblocks, uint4 *out) {
+	uint32_t k = blockIdx.x * blockDim.x + threadIdx.x;
+	if (k >= nblocks) return;
+	uint4 b[2];
+	bt_relayout_block(n, k, b);
+	out[2 * (size_t)k] = b[0];
+	out[2 * (size_t)k + 1] = b[1];
+}
+
+__global__ void bt_debug_lf_kernel(BtDevIndex ix, const uint32_t *rows, uint32_t n, uint32_t *out) {
+	uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+	if (i >= n) return;
+	uint32_t row = rows[i], ex[4];
+	BtBlock b = bt_load_block(ix, row);
+	bt_lf_ex(ix, b, row, ex);
+	for (int c = 0; c < 4; c++) {
+		out[5 * (size_t)i + c] = ex[c];
+		/* the single-character path must agree with the quartet */
+		if (bt_lf(ix, b, row, c) != ex[c]) out[5 * (size_t)i + c] = 0xdeadbeefu;
+	}
+	out[5 * (size_t)i + 4] = bt_row_l(b, row);
+}
+
+#define BT_THREADS 128
+
+struct BtWorkCtl { unsigned long long next; unsigned long long nwork; };
+
+/* Persistent search kernel: every thread is a lane that pulls read ids from a global cursor until
+ * the batch is exhausted.  `ctl->nwork` is read from device memory so that the retry pass can be
+ * enqueued before its size is known on the host. */
+__global__ void __launch_bounds__(BT_THREADS)
+bt_search_kernel(BtKParams P, BtWorkCtl *ctl) {
+	const uint32_t tid = blockIdx.x * blockDim.x + threadIdx.x;
+	const uint32_t lane = threadIdx.x & 31;
+	BtScratch S;
+	S.rows = P.rows + (size_t)tid * P.R * 2;
+	S.elims = P.elims + (size_t)tid * P.R;
+	S.frames = P.frames + (size_t)tid * P.FCAP;
+	S.partials = P.partials + (size_t)tid * P.PCAP;
+	BtLane L;
+	L.pc = PC_NEXT_READ;
+	L.s_lfex = L.s_lf = L.s_chase = L.s_ftab = L.s_offs = L.s_bt = L.s_iter = L.s_blk = 0;
+	L.nmuts = 0; L.ebwtSel = 0; L.lfk = 0; L.ltop = L.lbot = L.crow = 0;
+	const unsigned long long nwork = ctl->nwork;
+	for (;;) {
+		/* work distribution: warp-aggregated grab from the global cursor */
+		const bool want = (L.pc == PC_NEXT_READ);
+		const unsigned wmask = __ballot_sync(0xffffffffu, want);
+		if (wmask) {
+			const int leader = __ffs(wmask) - 1;
+			unsigned long long base = 0;
+			if ((int)lane == leader) base = atomicAdd(&ctl->next, (unsigned long long)__popc(wmask));
+			base = __shfl_sync(0xffffffffu, base, leader);
+			if (want) {
+				unsigned long long w = base + (unsigned long long)__popc(wmask & ((1u << lane) - 1u));
+				if (w < nwork) {
+					uint32_t rid = P.sel ? P.sel[w] : (uint32_t)w;
+					bt_begin_read(L, P, rid);
+				} else L.pc = PC_EXIT;
+			}
+		}
+		if (__all_sync(0xffffffffu, L.pc == PC_EXIT)) break;
+		if (L.pc == PC_FINISH_READ) { bt_finish_read(L, P); L.pc = PC_NEXT_READ; }
+		else if (L.pc != PC_EXIT && L.pc != PC_NEXT_READ) bt_iter(L, P, S);
+	}
+	/* statistics: warp-reduce, one atomic per warp and counter */
+	unsigned long long v[8] = { L.s_lfex, L.s_lf, L.s_chase, L.s_ftab, L.s_offs, L.s_bt, L.s_iter, L.s_blk };
+#pragma unroll
+	for (int k = 0; k < 8; k++) {
+		unsigned long long x = v[k];
+		for (int o = 16; o > 0; o >>= 1) x += __shfl_down_sync(0xffffffffu, x, o);
+		if (lane == 0 && x) atomicAdd(&P.stats[k], x);
+	}
+}
+
+/* Builds the list of reads whose scratch overflowed and resets the work control for the retry pass. */
+__global__ void bt_collect_kernel(const uint32_t *flags, const uint32_t *sel_in, uint32_t n, uint32_t mask, uint32_t *sel_out, BtWorkCtl *ctl) {
+	uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+	if (i >= n) return;
+	uint32_t rid = sel_in ? sel_in[i] : i;
+	if (flags[rid] & mask) {
+		unsigned long long p = atomicAdd(&ctl->nwork, 1ull);
+		sel_out[p] = rid;
+	}
+}
+__global__ void bt_ctl_set_kernel(BtWorkCtl *ctl, unsigned long long nwork) { ctl->next = 0; ctl->nwork = nwork; }
+
+/* ------------------------------------------------------------------------------------------- */
+/* host side                                                                                    */
+/* ------------------------------------------------------------------------------------------- */
+
+static thread_local std::string g_err;
+static int fail(const std::string &m) { g_err = m; return 1; }
+#define CUDA_TRY(x) do { cudaError_t e_ = (x); if (e_ != cudaSuccess) return fail(std::string(#x) + ": " + cudaGetErrorString(e_)); } while (0)
+
+struct HostEbwt {     /* the parsed contents of X.1.ebwt / X.2.ebwt */
+	uint32_t len = 0; int32_t lineRate = 0, linesPerSide = 0, offRate = 0, ftabChars = 0, flags = 0;
+	uint32_t nPat = 0, nFrag = 0, zOff = 0; uint32_t fchr[5] = {0,0,0,0,0};
+	std::vector<uint32_t> plen, rstarts, ftab, eftab, offs;
+	std::vector<uint8_t> ebwt;
+	std::vector<std::string> refnames;
+};
+
+struct DevEbwt {
+	uint4 *blocks = nullptr; uint32_t *offs = nullptr, *ftab = nullptr, *eftab = nullptr, *rstarts = nullptr, *plen = nullptr;
+	uint32_t nblocks = 0;
+	BtDevIndex dev;
+	uint64_t bytes = 0;
+};
+
+struct Workspace {
+	uint32_t nthreads = 0, R = 0, FCAP = 0, PCAP = 0;
+	uint4 *rows = nullptr; uint8_t *elims = nullptr; BtFrame *frames = nullptr; uint64_t *partials = nullptr;
+	void release() { cudaFree(rows); cudaFree(elims); cudaFree(frames); cudaFree(partials); rows = nullptr; elims = nullptr; frames = nullptr; partials = nullptr; nthreads = 0; }
+};
+
+struct bt_index {
+	int device = 0;
+	bool has_mirror = false;
+	HostEbwt host[2];            /* small arrays + names kept; ebwt bytes dropped after upload */
+	DevEbwt dev[2];
+	Workspace ws1, ws2;          /* first pass / retry pass scratch */
+	BtWorkCtl *ctl = nullptr;    /* [2] */
+	unsigned long long *stats = nullptr;
+	uint32_t *retry_sel = nullptr; uint32_t retry_cap = 0;
+	int sms = 0, blocks_per_sm = 0;
+	/* staging for the host-buffer entry point */
+	uint8_t *d_seq = nullptr, *d_qual = nullptr; uint64_t *d_offs = nullptr; uint32_t *d_seeds = nullptr, *d_sel = nullptr;
+	uint32_t *d_found = nullptr, *d_flags = nullptr, *d_hits = nullptr;
+	size_t cap_seq = 0, cap_qual = 0, cap_offs = 0, cap_seeds = 0, cap_found = 0, cap_flags = 0, cap_hitwords = 0, cap_sel = 0;
+	std::mutex mu;
+};
+
+static bool read_exact(FILE *f, void *p, size_t n) { return fread(p, 1, n, f) == n; }
+
+/* Ebwt::readIntoMemory (ebwt.h:2835-3445), small-index format */
+static int parse_ebwt(const std::string &base, bool mirror, HostEbwt &h) {
+	std::string p1 = base + (mirror ? ".rev" : "") + ".1.ebwt", p2 = base + (mirror ? ".rev" : "") + ".2.ebwt";
+	FILE *f1 = fopen(p1.c_str(), "rb");
+	if (!f1) return fail("cannot open " + p1);
+	FILE *f2 = fopen(p2.c_str(), "rb");
+	if (!f2) { fclose(f1); return fail("cannot open " + p2); }
+	int rc = 1;
+	do {
+		uint32_t one = 0, hdr[6];
+		if (!read_exact(f1, &one, 4) || one != 1) { fail(p1 + ": bad endianness sentinel (big-endian indexes are not supported)"); break; }
+		if (!read_exact(f2, &one, 4) || one != 1) { fail(p2 + ": bad endianness sentinel"); break; }
+		if (!read_exact(f1, hdr, sizeof hdr)) { fail(p1 + ": truncated header"); break; }
+		h.len = hdr[0]; h.lineRate = (int32_t)hdr[1]; h.linesPerSide = (int32_t)hdr[2]; h.offRate = (int32_t)hdr[3];
+		h.ftabChars = (int32_t)hdr[4]; h.flags = (int32_t)hdr[5];
+		if (h.lineRate != 6 || h.linesPerSide != 1) { fail(p1 + ": unsupported side geometry (need lineRate 6, linesPerSide 1)"); break; }
+		if (h.ftabChars < 1 || h.ftabChars > 16 || h.offRate < 0 || h.offRate > 31) { fail(p1 + ": implausible header"); break; }
+		if (!read_exact(f1, &h.nPat, 4)) { fail(p1 + ": truncated"); break; }
+		h.plen.resize(h.nPat);
+		if (!read_exact(f1, h.plen.data(), 4 * (size_t)h.nPat)) { fail(p1 + ": truncated plen"); break; }
+		if (!read_exact(f1, &h.nFrag, 4)) { fail(p1 + ": truncated"); break; }
+		h.rstarts.resize(3 * (size_t)h.nFrag);
+		if (!read_exact(f1, h.rstarts.data(), 12 * (size_t)h.nFrag)) { fail(p1 + ": truncated rstarts"); break; }
+		uint32_t bwtSz = h.len / 4 + 1;
+		size_t ebwtTotLen = (size_t)((bwtSz + 111) / 112) * 128;          /* EbwtParams::init ebwt.h:168-171 */
+		h.ebwt.resize(ebwtTotLen + 128);                                  /* + slack: bw side reads side+120 */
+		if (!read_exact(f1, h.ebwt.data(), ebwtTotLen)) { fail(p1 + ": truncated ebwt[]"); break; }
+		if (!read_exact(f1, &h.zOff, 4) || !read_exact(f1, h.fchr, 20)) { fail(p1 + ": truncated"); break; }
+		size_t ftabLen = ((size_t)1 << (2 * h.ftabChars)) + 1, eftabLen = 2 * (size_t)h.ftabChars;
+		h.ftab.resize(ftabLen); h.eftab.resize(eftabLen);
+		if (!read_exact(f1, h.ftab.data(), 4 * ftabLen) || !read_exact(f1, h.eftab.data(), 4 * eftabLen)) { fail(p1 + ": truncated ftab"); break; }
+		int c;
+		while ((c = fgetc(f1)) != EOF) {                                   /* ebwt.h:3258-3272 */
+			if (c == '\0') break;
+			if (c == '\n') h.refnames.push_back("");
+			else { if (h.refnames.empty()) h.refnames.push_back(""); h.refnames.back().push_back((char)c); }
+		}
+		size_t offsLen = ((size_t)h.len + 1 + ((size_t)1 << h.offRate) - 1) >> h.offRate;
+		h.offs.resize(offsLen);
+		if (!read_exact(f2, h.offs.data(), 4 * offsLen)) { fail(p2 + ": truncated offs[]"); break; }
+		rc = 0;
+	} while (0);
+	fclose(f1); fclose(f2);
+	return rc;
+}
+
+template <typename T> static int upload(const std::vector<T> &v, T **d, uint64_t &bytes) {
+	size_t n = v.size() ? v.size() : 1;
+	CUDA_TRY(cudaMalloc((void **)d, n * sizeof(T)));
+	if (v.size()) CUDA_TRY(cudaMemcpy(*d, v.data(), v.size() * sizeof(T), cudaMemcpyHostToDevice));
+	bytes += n * sizeof(T);
+	return 0;
+}
+
+static int upload_index(HostEbwt &h, bool fw, DevEbwt &d) {
+	uint8_t *d_raw = nullptr;
+	CUDA_TRY(cudaMalloc((void **)&d_raw, h.ebwt.size()));
+	CUDA_TRY(cudaMemcpy(d_raw, h.ebwt.data(), h.ebwt.size(), cudaMemcpyHostToDevice));
+	BtNativeIndex n;
+	n.ebwt = d_raw; n.len = h.len; n.zOff = h.zOff;
+	{   /* Ebwt::postReadInit (ebwt.h:1043-1059) */
+		uint32_t sideNum = h.zOff / 224, sideCharOff = h.zOff % 224, by = sideCharOff >> 2, bp = sideCharOff & 3;
+		if ((sideNum & 1) == 0) { by = 56 - by - 1; bp = 3 - bp; }
+		n.zEbwtByteOff = by + sideNum * 64; n.zEbwtBpOff = bp;
+	}
+	memcpy(n.fchr, h.fchr, sizeof n.fchr);
+	d.nblocks = (h.len >> 6) + 1;
+	CUDA_TRY(cudaMalloc((void **)&d.blocks, (size_t)d.nblocks * 32));
+	d.bytes += (uint64_t)d.nblocks * 32;
+	bt_relayout_kernel<<<(d.nblocks + 127) / 128, 128>>>(n, d.nblocks, d.blocks);
+	CUDA_TRY(cudaGetLastError());
+	CUDA_TRY(cudaDeviceSynchronize());
+	CUDA_TRY(cudaFree(d_raw));
+	if (upload(h.offs, &d.offs, d.bytes) || upload(h.ftab, &d.ftab, d.bytes) || upload(h.eftab, &d.eftab, d.bytes) ||
+	    upload(h.rstarts, &d.rstarts, d.bytes) || upload(h.plen, &d.plen, d.bytes)) return 1;
+	BtDevIndex &x = d.dev;
+	x.blocks = d.blocks; x.offs = d.offs; x.ftab = d.ftab; x.eftab = d.eftab; x.rstarts = d.rstarts; x.plen = d.plen;
+	x.len = h.len; x.zOff = h.zOff; x.nFrag = h.nFrag; x.nPat = h.nPat; x.offMask = 0xffffffffu << h.offRate;
+	x.offRate = h.offRate; x.ftabChars = h.ftabChars; memcpy(x.fchr, h.fchr, sizeof x.fchr); x.fw = fw ? 1u : 0u;
+	std::vector<uint8_t>().swap(h.ebwt);   /* the native image is not needed after the re-layout */
+	std::vector<uint32_t>().swap(h.offs);
+	std::vector<uint32_t>().swap(h.ftab);
+	return 0;
+}
+
+extern "C" int bt_abi_version(void) { return BT_ABI_VERSION; }
+extern "C" const char *bt_last_error(void) { return g_err.c_str(); }
+
+extern "C" void bt_policy_init(bt_policy_t *p) {
+	memset(p, 0, sizeof *p);
+	p->mode = 1; p->mms = 2; p->seed_len = 28; p->qual_thresh = 70; p->max_bts = 125; p->khits = 1; p->mhits = 0xffffffffu; p->maq_round = 1;
+}
+
+extern "C" void bt_index_free(bt_index_t *ix) {
+	if (!ix) return;
+	cudaSetDevice(ix->device);
+	for (int k = 0; k < 2; k++) {
+		DevEbwt &d = ix->dev[k];
+		cudaFree(d.blocks); cudaFree(d.offs); cudaFree(d.ftab); cudaFree(d.eftab); cudaFree(d.rstarts); cudaFree(d.plen);
+	}
+	ix->ws1.release(); ix->ws2.release();
+	cudaFree(ix->ctl); cudaFree(ix->stats); cudaFree(ix->retry_sel);
+	cudaFree(ix->d_seq); cudaFree(ix->d_qual); cudaFree(ix->d_offs); cudaFree(ix->d_seeds); cudaFree(ix->d_sel);
+	cudaFree(ix->d_found); cudaFree(ix->d_flags); cudaFree(ix->d_hits);
+	delete ix;
+}
+
+extern "C" int bt_index_load(const char *basename, int need_mirror, int device, bt_index_t **out) {
+	if (!basename || !out) return fail("bt_index_load: null argument");
+	*out = nullptr;
+	int ndev = 0;
+	if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0)
+		return fail("bt_index_load: no CUDA device available (this library has no CPU search path)");
+	if (device < 0 || device >= ndev) return fail("bt_index_load: bad device ordinal");
+	CUDA_TRY(cudaSetDevice(device));
+	bt_index *ix = new bt_index();
+	ix->device = device;
+	ix->has_mirror = need_mirror != 0;
+	int rc = parse_ebwt(basename, false, ix->host[0]);
+	if (!rc) rc = upload_index(ix->host[0], true, ix->dev[0]);
+	if (!rc && need_mirror) {
+		rc = parse_ebwt(basename, true, ix->host[1]);
+		if (!rc) rc = upload_index(ix->host[1], false, ix->dev[1]);
+	}
+	if (!rc) {
+		cudaDeviceProp prop;
+		if (cudaGetDeviceProperties(&prop, device) != cudaSuccess) rc = fail("cudaGetDeviceProperties failed");
+		else {
+			ix->sms = prop.multiProcessorCount;
+			int bps = 0;
+			if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bps, bt_search_kernel, BT_THREADS, 0) != cudaSuccess || bps < 1) bps = 1;
+			ix->blocks_per_sm = bps;
+		}
+	}
+	if (!rc && (cudaMalloc((void **)&ix->ctl, 2 * sizeof(BtWorkCtl)) != cudaSuccess ||
+	            cudaMalloc((void **)&ix->stats, 8 * sizeof(unsigned long long)) != cudaSuccess ||
+	            cudaMemset(ix->stats, 0, 8 * sizeof(unsigned long long)) != cudaSuccess)) rc = fail("cudaMalloc failed");
+	if (rc) { std::string keep = g_err; bt_index_free(ix); g_err = keep; return rc; }
+	*out = ix;
+	return 0;
+}
+
+extern "C" int bt_index_info(const bt_index_t *ix, bt_index_info_t *info) {
+	if (!ix || !info) return fail("bt_index_info: null argument");
+	info->len = ix->host[0].len; info->n_refs = ix->host[0].nPat; info->off_rate = ix->host[0].offRate; info->ftab_chars = ix->host[0].ftabChars;
+	info->has_mirror = ix->has_mirror; info->device_bytes = ix->dev[0].bytes + ix->dev[1].bytes;
+	return 0;
+}
+extern "C" const char *bt_index_refname(const bt_index_t *ix, uint32_t i) {
+	if (!ix || i >= ix->host[0].refnames.size()) return nullptr;
+	return ix->host[0].refnames[i].c_str();
+}
+extern "C" uint32_t bt_index_reflen(const bt_index_t *ix, uint32_t i) {
+	if (!ix || i >= ix->host[0].plen.size()) return 0;
+	return ix->host[0].plen[i];
+}
+
+static int ensure_ws(Workspace &w, uint32_t nthreads, uint32_t R, uint32_t FCAP, uint32_t PCAP) {
+	if (w.nthreads >= nthreads && w.R >= R && w.FCAP >= FCAP && w.PCAP >= PCAP) return 0;
+	w.release();
+	CUDA_TRY(cudaMalloc((void **)&w.rows, (size_t)nthreads * R * 32));
+	CUDA_TRY(cudaMalloc((void **)&w.elims, (size_t)nthreads * R));
+	CUDA_TRY(cudaMalloc((void **)&w.frames, (size_t)nthreads * FCAP * sizeof(BtFrame)));
+	CUDA_TRY(cudaMalloc((void **)&w.partials, (size_t)nthreads * PCAP * 8));
+	w.nthreads = nthreads; w.R = R; w.FCAP = FCAP; w.PCAP = PCAP;
+	return 0;
+}
+
+static int check_policy(const bt_index_t *ix, const bt_policy_t *pol) {
+	if (pol->mode == 0) { if (pol->mms < 0 || pol->mms > 2) return fail("bt_align: -v 3 is the reference's stateful (best-first) path; not provided by this ABI version"); }
+	else if (pol->mode == 1) { if (pol->mms < 0 || pol->mms > 3) return fail("bt_align: -n must be 0..3"); if (pol->seed_len < 5) return fail("bt_align: -l must be >= 5"); }
+	else return fail("bt_align: bad mode");
+	if ((pol->mode == 1 || pol->mms > 0) && !ix->has_mirror) return fail("bt_align: this policy needs the mirror index (load with need_mirror=1)");
+	if (!pol->all_hits && pol->khits == 0) return fail("bt_align: -k must be >= 1");
+	return 0;
+}
+
+/* Enqueue first pass + collect + retry pass.  All pointers are device pointers. `maxlen` bounds the read length. */
+static int enqueue_align(bt_index_t *ix, const bt_policy_t *pol, const bt_read_batch_t *in, bt_hit_batch_t *out, uint32_t maxlen, cudaStream_t st) {
+	const uint32_t nwork = in->sel ? in->nsel : in->nreads;
+	if (nwork == 0) return 0;
+	if (maxlen < 1) maxlen = 1;
+	if (maxlen > 1023) return fail("bt_align: reads longer than 1023 bases are not supported (the reference's Hit::mms is a FixedBitset<1024>)");
+	/* first-pass workspace: enough for the common case; rare deep searches go to the retry pass */
+	uint32_t nthreads = (uint32_t)ix->sms * (uint32_t)ix->blocks_per_sm * BT_THREADS;
+	if (ensure_ws(ix->ws1, nthreads, 6 * maxlen + 8, 8, 64)) return 1;
+	const uint32_t nthreads2 = (uint32_t)ix->sms * 32;
+	uint32_t R2 = maxlen * maxlen + 8; if (R2 > 65000) R2 = 65000;   /* BtFrame::rowbase is 16 bits */
+	if (ensure_ws(ix->ws2, nthreads2, R2, maxlen + 2, 4096)) return 1;
+	if (ix->retry_cap < nwork) {
+		cudaFree(ix->retry_sel); ix->retry_sel = nullptr; ix->retry_cap = 0;
+		CUDA_TRY(cudaMalloc((void **)&ix->retry_sel, (size_t)nwork * 4));
+		ix->retry_cap = nwork;
+	}
+	BtKParams P; memset(&P, 0, sizeof P);
+	P.ix[0] = ix->dev[0].dev; P.ix[1] = ix->dev[1].dev;
+	memcpy(&P.pol, pol, sizeof(BtPolicy));
+	P.seq = in->seq; P.qual = in->qual; P.roff = in->offs; P.seeds = in->seeds; P.sel = in->sel; P.nwork = nwork;
+	P.found = out->found; P.flags = out->flags; P.hits = out->hits; P.slots = out->slots; P.mm_cap = out->mm_cap; P.rec_words = BT_HIT_HDR + out->mm_cap;
+	P.stats = ix->stats;
+	/* pass 1 */
+	P.rows = ix->ws1.rows; P.elims = ix->ws1.elims; P.frames = ix->ws1.frames; P.partials = ix->ws1.partials;
+	P.R = ix->ws1.R; P.FCAP = ix->ws1.FCAP; P.PCAP = ix->ws1.PCAP;
+	bt_ctl_set_kernel<<<1, 1, 0, st>>>(ix->ctl, nwork);
+	uint32_t grid = (uint32_t)ix->sms * (uint32_t)ix->blocks_per_sm;
+	uint32_t need = (nwork + BT_THREADS - 1) / BT_THREADS;
+	if (grid > need) grid = need;
+	bt_search_kernel<<<grid, BT_THREADS, 0, st>>>(P, ix->ctl);
+	/* retry pass for reads whose scratch overflowed (sized on the device) */
+	bt_ctl_set_kernel<<<1, 1, 0, st>>>(ix->ctl + 1, 0);
+	bt_collect_kernel<<<(nwork + 255) / 256, 256, 0, st>>>(out->flags, in->sel, nwork, BT_FLAG_STACK_OVF | BT_FLAG_FRAME_OVF | BT_FLAG_PART_OVF, ix->retry_sel, ix->ctl + 1);
+	P.sel = ix->retry_sel;
+	P.rows = ix->ws2.rows; P.elims = ix->ws2.elims; P.frames = ix->ws2.frames; P.partials = ix->ws2.partials;
+	P.R = ix->ws2.R; P.FCAP = ix->ws2.FCAP; P.PCAP = ix->ws2.PCAP;
+	bt_search_kernel<<<ix->sms, 32, 0, st>>>(P, ix->ctl + 1);
+	CUDA_TRY(cudaGetLastError());
+	return 0;
+}
+
+extern "C" int bt_align_batch_device(bt_index_t *ix, const bt_policy_t *pol, const bt_read_batch_t *in, bt_hit_batch_t *out, void *stream) {
+	if (!ix || !pol || !in || !out) return fail("bt_align_batch_device: null argument");
+	if (check_policy(ix, pol)) return 1;
+	std::lock_guard<std::mutex> g(ix->mu);
+	CUDA_TRY(cudaSetDevice(ix->device));
+	if (in->max_len == 0) return fail("bt_align_batch_device: max_len must be set (the offsets live on the device)");
+	return enqueue_align(ix, pol, in, out, in->max_len, (cudaStream_t)stream);
+}
+
+template <typename T> static int grow(T **p, size_t &cap, size_t need) {
+	if (cap >= need) return 0;
+	cudaFree(*p); *p = nullptr; cap = 0;
+	size_t n = need + need / 4 + 16;
+	CUDA_TRY(cudaMalloc((void **)p, n * sizeof(T)));
+	cap = n;
+	return 0;
+}
+
+extern "C" int bt_align_batch(bt_index_t *ix, const bt_policy_t *pol, const bt_read_batch_t *in, bt_hit_batch_t *out, void *stream) {
+	if (!ix || !pol || !in || !out) return fail("bt_align_batch: null argument");
+	if (check_policy(ix, pol)) return 1;
+	if (in->nreads == 0) return 0;
+	if (!in->seq || !in->qual || !in->offs || !in->seeds || !out->found || !out->flags || !out->hits) return fail("bt_align_batch: null buffer");
+	if (out->slots == 0) return fail("bt_align_batch: slots must be >= 1");
+	cudaStream_t st = (cudaStream_t)stream;
+	uint32_t maxlen = 0;
+	{
+		std::lock_guard<std::mutex> g(ix->mu);
+		CUDA_TRY(cudaSetDevice(ix->device));
+		const uint32_t n = in->nreads;
+		const size_t nb = (size_t)in->offs[n];
+		for (uint32_t i = 0; i < n; i++) { uint64_t l = in->offs[i + 1] - in->offs[i]; if (l > maxlen) maxlen = (uint32_t)l; }
+		const size_t rec_words = BT_HIT_HDR + out->mm_cap;
+		const size_t hitwords = (size_t)n * out->slots * rec_words;
+		if (grow(&ix->d_seq, ix->cap_seq, nb + 1) || grow(&ix->d_qual, ix->cap_qual, nb + 1)) return 1;
+		if (grow(&ix->d_offs, ix->cap_offs, (size_t)n + 1) || grow(&ix->d_seeds, ix->cap_seeds, n) ||
+		    grow(&ix->d_found, ix->cap_found, n) || grow(&ix->d_flags, ix->cap_flags, n)) return 1;
+		if (grow(&ix->d_hits, ix->cap_hitwords, hitwords)) return 1;
+		if (in->sel && grow(&ix->d_sel, ix->cap_sel, in->nsel)) return 1;
+		CUDA_TRY(cudaMemcpyAsync(ix->d_seq, in->seq, nb, cudaMemcpyHostToDevice, st));
+		CUDA_TRY(cudaMemcpyAsync(ix->d_qual, in->qual, nb, cudaMemcpyHostToDevice, st));
+		CUDA_TRY(cudaMemcpyAsync(ix->d_offs, in->offs, ((size_t)n + 1) * 8, cudaMemcpyHostToDevice, st));
+		CUDA_TRY(cudaMemcpyAsync(ix->d_seeds, in->seeds, (size_t)n * 4, cudaMemcpyHostToDevice, st));
+		if (in->sel) CUDA_TRY(cudaMemcpyAsync(ix->d_sel, in->sel, (size_t)in->nsel * 4, cudaMemcpyHostToDevice, st));
+		else { CUDA_TRY(cudaMemsetAsync(ix->d_found, 0, (size_t)n * 4, st)); CUDA_TRY(cudaMemsetAsync(ix->d_flags, 0, (size_t)n * 4, st)); }
+		bt_read_batch_t din = *in; bt_hit_batch_t dout = *out;
+		din.seq = ix->d_seq; din.qual = ix->d_qual; din.offs = ix->d_offs; din.seeds = ix->d_seeds; din.sel = in->sel ? ix->d_sel : nullptr;
+		dout.found = ix->d_found; dout.flags = ix->d_flags; dout.hits = ix->d_hits;
+		if (enqueue_align(ix, pol, &din, &dout, maxlen, st)) return 1;
+		if (!in->sel) {
+			CUDA_TRY(cudaMemcpyAsync(out->found, ix->d_found, (size_t)n * 4, cudaMemcpyDeviceToHost, st));
+			CUDA_TRY(cudaMemcpyAsync(out->flags, ix->d_flags, (size_t)n * 4, cudaMemcpyDeviceToHost, st));
+			CUDA_TRY(cudaMemcpyAsync(out->hits, ix->d_hits, hitwords * 4, cudaMemcpyDeviceToHost, st));
+			CUDA_TRY(cudaStreamSynchronize(st));
+		} else {
+			/* selection call: only the selected reads' entries are defined; copy them back one by one */
+			CUDA_TRY(cudaStreamSynchronize(st));
+			for (uint32_t k = 0; k < in->nsel; k++) {
+				uint32_t r = in->sel[k];
+				CUDA_TRY(cudaMemcpy(out->found + r, ix->d_found + r, 4, cudaMemcpyDeviceToHost));
+				CUDA_TRY(cudaMemcpy(out->flags + r, ix->d_flags + r, 4, cudaMemcpyDeviceToHost));
+				CUDA_TRY(cudaMemcpy(out->hits + (size_t)r * out->slots * rec_words, ix->d_hits + (size_t)r * out->slots * rec_words, out->slots * rec_words * 4, cudaMemcpyDeviceToHost));
+			}
+		}
+	}
+	return 0;
+}
+
+extern "C" int bt_stats_get(bt_index_t *ix, bt_stats_t *out, int reset) {
+	if (!ix || !out) return fail("bt_stats_get: null argument");
+	CUDA_TRY(cudaSetDevice(ix->device));
+	CUDA_TRY(cudaDeviceSynchronize());
+	unsigned long long v[8];
+	CUDA_TRY(cudaMemcpy(v, ix->stats, sizeof v, cudaMemcpyDeviceToHost));
+	out->lfex = v[0]; out->lf = v[1]; out->chase = v[2]; out->ftab = v[3]; out->offs = v[4]; out->backtracks = v[5]; out->iters = v[6]; out->block_loads = v[7];
+	if (reset) CUDA_TRY(cudaMemset(ix->stats, 0, sizeof v));
+	return 0;
+}
+
+extern "C" int bt_debug_lf(bt_index_t *ix, int mirror, const uint32_t *rows, uint32_t n, uint32_t *out) {
+	if (!ix || !rows || !out) return fail("bt_debug_lf: null argument");
+	if (mirror && !ix->has_mirror) return fail("bt_debug_lf: mirror index not loaded");
+	if (n == 0) return 0;
+	CUDA_TRY(cudaSetDevice(ix->device));
+	uint32_t *d_rows = nullptr, *d_out = nullptr;
+	CUDA_TRY(cudaMalloc((void **)&d_rows, (size_t)n * 4));
+	CUDA_TRY(cudaMalloc((void **)&d_out, (size_t)n * 20));
+	CUDA_TRY(cudaMemcpy(d_rows, rows, (size_t)n * 4, cudaMemcpyHostToDevice));
+	bt_debug_lf_kernel<<<(n + 127) / 128, 128>>>(ix->dev[mirror ? 1 : 0].dev, d_rows, n, d_out);
+	CUDA_TRY(cudaGetLastError());
+	CUDA_TRY(cudaMemcpy(out, d_out, (size_t)n * 20, cudaMemcpyDeviceToHost));
+	cudaFree(d_rows); cudaFree(d_out);
+	return 0;
+}

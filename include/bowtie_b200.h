@@ -1,0 +1,135 @@
+/*
+ * bowtie_b200.h — C ABI of the B200-native FM-index backward-search path.
+ *
+ * This is the drop-in boundary for the hot path of Bowtie 1.3.1.  The reference has no plugin
+ * API; its hot path sits between PatternSourcePerThread::nextReadPair() (reads in) and
+ * HitSinkPerThread::reportHit()/finishRead() (hits out), inside the per-thread worker functions
+ *     exactSearchWorker                    ebwt_search.cpp:1130
+ *     mismatchSearchWorkerFull             ebwt_search.cpp:1606
+ *     twoOrThreeMismatchSearchWorkerFull   ebwt_search.cpp:2056
+ *     seededQualSearchWorkerFull           ebwt_search.cpp:2378
+ * operating on two immutable Ebwt objects (ebwt.h:335-1263).  The entry points below replace
+ * exactly that: load the same .ebwt files, take a batch of Read records (sequence, qualities,
+ * per-read seed), and return for every read what the worker would have handed to its
+ * HitSinkPerThread.  Plain pointers and sizes only; no exceptions cross the boundary; every
+ * function returns 0 on success and a nonzero code otherwise (bt_last_error() has the message).
+ *
+ * INTEGRATION.md shows the reference-side binding.
+ */
+#ifndef BOWTIE_B200_H_
+#define BOWTIE_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define BT_ABI_VERSION 1
+
+typedef struct bt_index bt_index_t;
+
+/* Search policy = the option globals of ebwt_search.cpp:153-253 that reach the workers.
+ * Layout is shared with the kernels (BtPolicy in bt_core.cuh). */
+typedef struct bt_policy {
+	int32_t  mode;        /* 0: -v <mms> end-to-end mismatches ; 1: -n <mms> seeded, quality-aware ("maqLike") */
+	int32_t  mms;         /* -v: 0..2 ; -n: 0..3   (-v 3, --best, -M, paired-end are the reference's stateful path: not this ABI yet) */
+	int32_t  seed_len;    /* -l, default 28                                  */
+	uint32_t qual_thresh; /* -e, default 70                                  */
+	uint32_t max_bts;     /* --maxbts, default 125 (maxBtsBetter)            */
+	uint32_t khits;       /* -k, default 1                                   */
+	uint32_t mhits;       /* -m, default 0xffffffff                          */
+	int32_t  all_hits;    /* -a                                              */
+	int32_t  nofw, norc;  /* --nofw / --norc                                 */
+	int32_t  maq_round;   /* 1 unless --nomaqround                           */
+} bt_policy_t;
+
+/* Per-read overflow flags (bt_hit_batch_t::flags).  Scratch-related overflows are retried inside the
+ * library with a larger workspace; HITS/MM overflows mean the caller's record array was too small
+ * for this read (call again for those reads with more slots / mm_cap via bt_read_batch_t::sel). */
+#define BT_OVF_STACK 1u
+#define BT_OVF_FRAME 2u
+#define BT_OVF_PART  4u
+#define BT_OVF_HITS  8u
+#define BT_OVF_MM   16u
+
+/* A batch of reads = the fields of Read (read.h:42-277) the search consumes.
+ * seq: base codes 0=A 1=C 2=G 3=T 4=N (asc2dna), qual: Phred+33 characters, both concatenated;
+ * offs[i]..offs[i+1] delimits read i; seeds[i] = Read::seed (genRandSeed, pat.cpp:21-57). */
+typedef struct bt_read_batch {
+	uint32_t        nreads;
+	const uint8_t  *seq;
+	const uint8_t  *qual;
+	const uint64_t *offs;     /* nreads + 1 */
+	const uint32_t *seeds;    /* nreads     */
+	const uint32_t *sel;      /* optional: process only these read ids (length nsel), else NULL */
+	uint32_t        nsel;
+	uint32_t        max_len;  /* longest read in the batch; required by bt_align_batch_device, else 0 = compute */
+} bt_read_batch_t;
+
+/* Hit record: BT_HIT_HDR_WORDS header words + mm_cap mismatch words.
+ *   w0 tidx (Hit::h.first)     w1 toff (Hit::h.second)     w2 oms (Hit::oms)
+ *   w3 cost[15:0] | stratum[23:16] | fw[24]                w4 number of mismatches
+ *   w5.. mismatch k: pos[15:0] (offset from the 5' end, Hit::mms) | refc[23:16] (0..3, Hit::refcs)          */
+#define BT_HIT_HDR_WORDS 5
+
+/* Per-read results, caller-allocated:
+ *   found[i]  = hitsForThisRead_ when the worker called finishRead (hit.h:741-786); the caller applies
+ *               "found > mhits => suppressed by -m" and "report min(found, khits)" exactly as finishRead does.
+ *   hits      = nreads x slots x (BT_HIT_HDR_WORDS + mm_cap) words; the first min(found, n, slots) records
+ *               of read i are valid, in the order the reference's sink would have buffered them. */
+typedef struct bt_hit_batch {
+	uint32_t *found;      /* nreads */
+	uint32_t *flags;      /* nreads */
+	uint32_t *hits;
+	uint32_t  slots;
+	uint32_t  mm_cap;
+} bt_hit_batch_t;
+
+typedef struct bt_index_info {
+	uint32_t len;         /* joined reference length               */
+	uint32_t n_refs;      /* number of reference sequences (nPat)  */
+	int32_t  off_rate, ftab_chars;
+	int32_t  has_mirror;
+	uint64_t device_bytes;
+} bt_index_info_t;
+
+/* Operation counters accumulated over all bt_align_* calls on this index since the last reset;
+ * units of SURVEY.md §8(d): side fetches = 2*lfex + lf. */
+typedef struct bt_stats {
+	uint64_t lfex, lf, chase, ftab, offs, backtracks, iters, block_loads;
+} bt_stats_t;
+
+int  bt_abi_version(void);
+const char *bt_last_error(void);
+
+/* Replaces Ebwt::Ebwt + Ebwt::loadIntoMemory (ebwt.h:402-448, 2835-3445) for X.1.ebwt/X.2.ebwt and,
+ * if need_mirror, X.rev.1.ebwt/X.rev.2.ebwt; uploads to `device` and re-lays-out the BWT for the kernels. */
+int  bt_index_load(const char *basename, int need_mirror, int device, bt_index_t **out);
+void bt_index_free(bt_index_t *ix);
+int  bt_index_info(const bt_index_t *ix, bt_index_info_t *info);
+const char *bt_index_refname(const bt_index_t *ix, uint32_t i);   /* Ebwt::_refnames */
+uint32_t    bt_index_reflen(const bt_index_t *ix, uint32_t i);    /* Ebwt::_plen     */
+
+void bt_policy_init(bt_policy_t *p);                              /* resetOptions defaults (ebwt_search.cpp:153-253) */
+
+/* Replaces one pass of the worker loop over a batch (GET_READ ... search_*.c ... FINISH_READ).
+ * Host buffers in, host buffers out; the call returns when the results are in `out`.
+ * `stream` is a cudaStream_t (NULL = default stream). */
+int  bt_align_batch(bt_index_t *ix, const bt_policy_t *pol, const bt_read_batch_t *in, bt_hit_batch_t *out, void *stream);
+
+/* Same, with every pointer of `in` and `out` already resident on the index's device; enqueues on
+ * `stream` and returns without synchronising (scratch overflows are retried by a second enqueued pass). */
+int  bt_align_batch_device(bt_index_t *ix, const bt_policy_t *pol, const bt_read_batch_t *in, bt_hit_batch_t *out, void *stream);
+
+int  bt_stats_get(bt_index_t *ix, bt_stats_t *out, int reset);    /* synchronises the device */
+
+/* LF primitives on the device layout, for parity tests: computes, for each row, mapLFEx-style
+ * (fchr[c] + occ(c,row)) for c = 0..3 and rowL.  rows/out are host arrays; out has 5 words per row. */
+int  bt_debug_lf(bt_index_t *ix, int mirror, const uint32_t *rows, uint32_t n, uint32_t *out);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

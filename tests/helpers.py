@@ -337,3 +337,131 @@ def run_reference(args: list[str], index, reads, extra_env=None) -> tuple[bytes,
             return f.read(), p.stderr
     finally:
         os.unlink(outp)
+
+
+# ----------------------------------------------------------------------------------------
+# decoding of the kernel's raw output (found / flags / hit records) — mirrors the host-side
+# finishRead logic of bowtie_b200 (HitSinkPerThread::finishRead, hit.h:741-786)
+# ----------------------------------------------------------------------------------------
+
+BT_HIT_HDR = 5
+
+
+def decode_device_result(found: np.ndarray, hits: np.ndarray, slots: int, mm_cap: int, pol: Policy) -> AlignResult:
+    n = len(found)
+    rec_words = BT_HIT_HDR + mm_cap
+    hits = hits.reshape(n, slots, rec_words) if n else hits.reshape(0, slots, rec_words)
+    nlim = 0xFFFFFFFF if pol.all_hits else pol.khits
+    maxed = found > pol.mhits
+    nrep = np.where(maxed, 0, np.minimum(found, nlim)).astype(np.uint32)
+    out_hits, out_mms = [], []
+    for i in np.nonzero(nrep)[0].tolist():
+        for s in range(int(nrep[i])):
+            rec = hits[i, s]
+            w3 = int(rec[3])
+            nmm = int(rec[4])
+            mm_off = len(out_mms)
+            for k in range(min(nmm, mm_cap)):   # reads flagged BT_OVF_MM carry a truncated list
+                w = int(rec[BT_HIT_HDR + k])
+                out_mms.append((w & 0xFFFF, (w >> 16) & 0xFF, 0))
+            out_hits.append((i, int(rec[0]), int(rec[1]), int(rec[2]), w3 & 0xFFFF, (w3 >> 24) & 0xFF, (w3 >> 16) & 0xFF, min(nmm, mm_cap), mm_off))
+    h = np.array(out_hits, dtype=HIT_DTYPE) if out_hits else np.zeros(0, HIT_DTYPE)
+    m = np.array(out_mms, dtype=MM_DTYPE) if out_mms else np.zeros(0, MM_DTYPE)
+    aligned = int(np.count_nonzero(nrep))
+    nmaxed = int(np.count_nonzero(maxed))
+    ctr = np.array([aligned, n - aligned - nmaxed, nmaxed, int(nrep.sum()), 0], dtype=np.uint64)
+    return AlignResult(h, m, nrep, maxed.astype(np.uint8), ctr, None)
+
+
+def results_equal(a: AlignResult, b: AlignResult) -> tuple[bool, str]:
+    if not np.array_equal(a.nhits_per_read, b.nhits_per_read):
+        bad = np.nonzero(a.nhits_per_read != b.nhits_per_read)[0]
+        return False, f"nhits_per_read differ at reads {bad[:10].tolist()}"
+    if not np.array_equal(a.maxed, b.maxed):
+        return False, "maxed flags differ"
+    if len(a.hits) != len(b.hits):
+        return False, f"hit counts differ {len(a.hits)} vs {len(b.hits)}"
+    for f in ("read", "tidx", "toff", "oms", "cost", "fw", "stratum", "nmm"):
+        if not np.array_equal(a.hits[f], b.hits[f]):
+            bad = np.nonzero(a.hits[f] != b.hits[f])[0]
+            return False, f"hit field {f} differs at hits {bad[:10].tolist()} (reads {a.hits['read'][bad[:10]].tolist()})"
+    for i in range(len(a.hits)):
+        ma = a.mms[int(a.hits["mm_off"][i]): int(a.hits["mm_off"][i]) + int(a.hits["nmm"][i])]
+        mb = b.mms[int(b.hits["mm_off"][i]): int(b.hits["mm_off"][i]) + int(b.hits["nmm"][i])]
+        if not (np.array_equal(ma["pos"], mb["pos"]) and np.array_equal(ma["refc"], mb["refc"])):
+            return False, f"mismatch list differs at hit {i} (read {int(a.hits['read'][i])})"
+    if not np.array_equal(a.counters, b.counters):
+        return False, f"counters differ {a.counters} vs {b.counters}"
+    return True, ""
+
+
+class _DevPolicy(C.Structure):
+    _fields_ = [("mode", C.c_int32), ("mms", C.c_int32), ("seedLen", C.c_int32), ("qualThresh", C.c_uint32),
+                ("maxBts", C.c_uint32), ("khits", C.c_uint32), ("mhits", C.c_uint32), ("allHits", C.c_int32),
+                ("nofw", C.c_int32), ("norc", C.c_int32), ("maqRound", C.c_int32)]
+
+
+def dev_policy(pol: Policy) -> _DevPolicy:
+    return _DevPolicy(pol.mode, pol.mms, pol.seed_len, pol.qual_thresh, pol.max_bts, pol.khits, pol.mhits,
+                      int(pol.all_hits), int(pol.nofw), int(pol.norc), int(pol.maq_round))
+
+
+class HostEmu:
+    """Test-only host build of the device state machine (tests/host_emu/emu.cpp)."""
+
+    def __init__(self) -> None:
+        ensure_oracle_built()
+        d = ROOT / "tests" / "host_emu"
+        so = d / "libbtemu.so"
+        srcs = [d / "emu.cpp", ROOT / "bowtie_b200" / "csrc" / "bt_core.cuh", ROOT / "bowtie_b200" / "csrc" / "bt_native.cuh",
+                ORACLE_DIR / "bt_oracle.c"]
+        if not so.exists() or so.stat().st_mtime < max(s.stat().st_mtime for s in srcs):
+            subprocess.run(["g++", "-O2", "-g", "-std=c++17", "-fPIC", "-shared", "-o", str(so), str(d / "emu.cpp"),
+                            str(ORACLE_DIR / "bt_oracle.c")], check=True, capture_output=True)
+        L = C.CDLL(str(so))
+        L.emu_index_load.restype = C.c_void_p
+        L.emu_index_load.argtypes = [C.c_char_p, C.c_int]
+        L.emu_index_free.argtypes = [C.c_void_p]
+        L.emu_lf.restype = C.c_uint32
+        L.emu_lf.argtypes = [C.c_void_p, C.c_uint32, C.c_int]
+        L.emu_lf_ex.argtypes = [C.c_void_p, C.c_uint32, C.POINTER(C.c_uint32)]
+        L.emu_row_l.restype = C.c_int
+        L.emu_row_l.argtypes = [C.c_void_p, C.c_uint32]
+        L.emu_align.restype = C.c_int
+        L.emu_align.argtypes = [C.c_void_p, C.c_void_p, C.POINTER(_DevPolicy), C.c_uint32, C.c_void_p, C.c_void_p, C.c_void_p,
+                                C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint32, C.c_uint32, C.c_uint32,
+                                C.c_uint32, C.c_uint32, C.c_void_p]
+        self.L = L
+        self._idx = {}
+
+    def index(self, base, mirror: bool):
+        key = (str(base), int(mirror))
+        if key not in self._idx:
+            h = self.L.emu_index_load(str(base).encode(), int(mirror))
+            if not h:
+                raise RuntimeError("emu index load failed")
+            self._idx[key] = h
+        return self._idx[key]
+
+    def align(self, base, batch: ReadBatch, pol: Policy, slots=None, mm_cap=8, R=None, FCAP=16, PCAP=256):
+        fw = self.index(base, False)
+        bw = self.index(base, True) if (pol.mode == 1 or pol.mms > 0) else None
+        n = len(batch)
+        if slots is None:
+            slots = 64 if pol.all_hits else pol.khits
+        maxlen = int((batch.offs[1:] - batch.offs[:-1]).max()) if n else 1
+        if R is None:
+            R = 8 * maxlen
+        found = np.zeros(n, np.uint32)
+        flags = np.zeros(n, np.uint32)
+        hits = np.zeros(n * slots * (BT_HIT_HDR + mm_cap), np.uint32)
+        stats = np.zeros(8, np.uint64)
+        cp = dev_policy(pol)
+        rc = self.L.emu_align(fw, bw, C.byref(cp), n, batch.seq_codes.ctypes.data, batch.qual_cat.ctypes.data,
+                              batch.offs.ctypes.data, batch.seeds.ctypes.data, found.ctypes.data, flags.ctypes.data,
+                              hits.ctypes.data, slots, mm_cap, R, FCAP, PCAP, stats.ctypes.data)
+        if rc:
+            raise RuntimeError(f"emu_align rc={rc}")
+        res = decode_device_result(found, hits, slots, mm_cap, pol)
+        res.stats = dict(zip(["lfex", "lf", "chase", "ftab", "offs", "backtracks", "iters", "blockloads"], stats.tolist()))
+        return res, flags

@@ -1,0 +1,72 @@
+/*
+ * tests/host_emu/emu.cpp — TEST-ONLY logic emulation of the device state machine.
+ *
+ * Compiles bowtie_b200/csrc/bt_core.cuh + bt_native.cuh for the host (one lane at a time) so that
+ * the kernel's control logic can be checked against the oracle on a machine without a GPU
+ * (pytest -m "not gpu").  It is never linked into the product library and is not a fallback:
+ * libbowtie_b200.so has no host search path at all.
+ */
+#define BT_HOST_EMU 1
+#include <stdlib.h>
+#include <string.h>
+#include <vector>
+#include "../../bowtie_b200/csrc/bt_native.cuh"
+extern "C" {
+#include "../../oracle/bt_oracle.h"
+}
+
+struct EmuIndex { std::vector<uint4> blocks; bto_index *raw; BtDevIndex dev; };
+
+static EmuIndex *emu_load(const char *base, int mirror) {
+	char err[256];
+	bto_index *ix = bto_index_load(base, mirror, err, sizeof err);
+	if (!ix) return NULL;
+	EmuIndex *e = new EmuIndex();
+	e->raw = ix;
+	BtNativeIndex n;
+	n.ebwt = ix->ebwt; n.len = ix->len; n.zOff = ix->zOff; n.zEbwtByteOff = ix->zEbwtByteOff; n.zEbwtBpOff = (uint32_t)ix->zEbwtBpOff;
+	memcpy(n.fchr, ix->fchr, sizeof n.fchr);
+	uint32_t nblocks = (ix->len >> 6) + 1;
+	e->blocks.resize(2 * (size_t)nblocks);
+	for (uint32_t k = 0; k < nblocks; k++) bt_relayout_block(n, k, &e->blocks[2 * (size_t)k]);
+	BtDevIndex &d = e->dev;
+	d.blocks = e->blocks.data(); d.offs = ix->offs; d.ftab = ix->ftab; d.eftab = ix->eftab; d.rstarts = ix->rstarts; d.plen = ix->plen;
+	d.len = ix->len; d.zOff = ix->zOff; d.nFrag = ix->nFrag; d.nPat = ix->nPat; d.offMask = ix->offMask;
+	d.offRate = ix->offRate; d.ftabChars = ix->ftabChars; memcpy(d.fchr, ix->fchr, sizeof d.fchr); d.fw = (uint32_t)ix->fw;
+	return e;
+}
+
+extern "C" {
+
+void *emu_index_load(const char *base, int mirror) { return emu_load(base, mirror); }
+void emu_index_free(void *p) { EmuIndex *e = (EmuIndex *)p; if (!e) return; bto_index_free(e->raw); delete e; }
+
+/* LF via the re-laid-out blocks, for unit tests against the oracle's side arithmetic */
+uint32_t emu_lf(void *p, uint32_t row, int c) { EmuIndex *e = (EmuIndex *)p; BtBlock b = bt_load_block(e->dev, row); return bt_lf(e->dev, b, row, (uint32_t)c); }
+void emu_lf_ex(void *p, uint32_t row, uint32_t out[4]) { EmuIndex *e = (EmuIndex *)p; BtBlock b = bt_load_block(e->dev, row); bt_lf_ex(e->dev, b, row, out); }
+int emu_row_l(void *p, uint32_t row) { EmuIndex *e = (EmuIndex *)p; BtBlock b = bt_load_block(e->dev, row); return (int)bt_row_l(b, row); }
+
+int emu_align(void *fwp, void *bwp, const BtPolicy *pol, uint32_t nreads, const uint8_t *seq, const uint8_t *qual,
+              const uint64_t *roff, const uint32_t *seeds, uint32_t *found, uint32_t *flags, uint32_t *hits,
+              uint32_t slots, uint32_t mm_cap, uint32_t R, uint32_t FCAP, uint32_t PCAP, unsigned long long *stats) {
+	BtKParams P; memset(&P, 0, sizeof P);
+	P.ix[0] = ((EmuIndex *)fwp)->dev;
+	if (bwp) P.ix[1] = ((EmuIndex *)bwp)->dev;
+	P.pol = *pol;
+	P.seq = seq; P.qual = qual; P.roff = roff; P.seeds = seeds; P.nwork = nreads;
+	P.found = found; P.flags = flags; P.hits = hits; P.slots = slots; P.mm_cap = mm_cap; P.rec_words = BT_HIT_HDR + mm_cap;
+	std::vector<uint4> rows(2 * (size_t)R); std::vector<uint8_t> elims(R); std::vector<BtFrame> frames(FCAP); std::vector<uint64_t> parts(PCAP);
+	P.R = R; P.FCAP = FCAP; P.PCAP = PCAP;
+	BtScratch S = { rows.data(), elims.data(), frames.data(), parts.data() };
+	BtLane L; memset(&L, 0, sizeof L);
+	for (uint32_t r = 0; r < nreads; r++) {
+		bt_begin_read(L, P, r);
+		unsigned long long guard = 0;
+		while (L.pc != PC_FINISH_READ) { bt_iter(L, P, S); if (++guard > (1ull << 34)) return 1; }
+		bt_finish_read(L, P);
+	}
+	stats[0] = L.s_lfex; stats[1] = L.s_lf; stats[2] = L.s_chase; stats[3] = L.s_ftab; stats[4] = L.s_offs; stats[5] = L.s_bt; stats[6] = L.s_iter; stats[7] = L.s_blk;
+	return 0;
+}
+
+}

@@ -1,0 +1,108 @@
+"""Deterministic synthetic genomes / reads for the tests and the bench (numpy PCG64 streams)."""
+from __future__ import annotations
+
+import subprocess
+from pathlib import Path
+
+import numpy as np
+
+from helpers import REF_BUILD, REF_DIR, ReadBatch, finalize_batch
+
+CACHE = REF_DIR / "cache"
+
+
+def synth_genome(n_seqs: int, total_len: int, seed: int, with_gaps: bool = False, repeats: bool = True) -> list[tuple[str, bytes]]:
+    rng = np.random.default_rng(seed)
+    sizes = rng.dirichlet(np.ones(n_seqs) * 3) * total_len
+    out = []
+    fam = rng.choice(np.frombuffer(b"ACGT", np.uint8), size=300, p=[0.295, 0.205, 0.205, 0.295])
+    for s in range(n_seqs):
+        L = max(2000, int(sizes[s]))
+        g = rng.choice(np.frombuffer(b"ACGT", np.uint8), size=L, p=[0.295, 0.205, 0.205, 0.295]).copy()
+        if repeats:
+            for _ in range(max(1, L // 5000)):
+                p = int(rng.integers(0, L - 300))
+                cp = fam.copy()
+                mut = rng.random(300) < 0.03
+                cp[mut] = rng.choice(np.frombuffer(b"ACGT", np.uint8), size=int(mut.sum()))
+                g[p:p + 300] = cp
+        if with_gaps:
+            for _ in range(2):
+                p = int(rng.integers(100, L - 200))
+                g[p:p + int(rng.integers(1, 60))] = ord("N")
+        out.append((f"seq{s} synthetic len={L}", g.tobytes()))
+    return out
+
+
+def write_fasta(path: Path, seqs: list[tuple[str, bytes]]) -> None:
+    with open(path, "wb") as f:
+        for name, s in seqs:
+            f.write(b">" + name.encode() + b"\n")
+            for i in range(0, len(s), 60):
+                f.write(s[i:i + 60] + b"\n")
+
+
+def build_synth_index(tag: str, n_seqs: int, total_len: int, seed: int, ftab_chars: int = 10, off_rate: int = 5,
+                      with_gaps: bool = False, threads: int = 8):
+    """Build (once; cached under oracle/_ref/cache) an index with the reference's bowtie-build.
+    Returns (basename, genome)."""
+    CACHE.mkdir(parents=True, exist_ok=True)
+    base = CACHE / f"{tag}_{n_seqs}_{total_len}_{seed}_{ftab_chars}_{off_rate}_{int(with_gaps)}"
+    genome = synth_genome(n_seqs, total_len, seed, with_gaps)
+    if not Path(str(base) + ".rev.2.ebwt").exists():
+        fa = Path(str(base) + ".fa")
+        write_fasta(fa, genome)
+        p = subprocess.run([str(REF_BUILD), "-q", "-t", str(ftab_chars), "-o", str(off_rate), "--threads", str(threads), str(fa), str(base)],
+                           capture_output=True, text=True)
+        if p.returncode != 0:
+            raise RuntimeError("bowtie-build failed: " + p.stderr)
+    return base, genome
+
+
+_COMP = bytes.maketrans(b"ACGTN", b"TGCAN")
+
+
+def synth_reads(genome: list[tuple[str, bytes]], n: int, length: int | tuple[int, int], seed: int, sub_rate: float = 0.01,
+                n_rate: float = 0.0, random_frac: float = 0.02, qual_profile: str = "mixed", global_seed: int = 0) -> ReadBatch:
+    """Reads sampled uniformly from the genome (both strands) with substitutions, optional Ns and
+    a fraction of random (unalignable) reads.  qual_profile: 'high' | 'mixed' | 'low'."""
+    rng = np.random.default_rng(seed)
+    seqs = [np.frombuffer(s, np.uint8) for _, s in genome]
+    w = np.array([len(s) for s in seqs], float)
+    w /= w.sum()
+    acgt = np.frombuffer(b"ACGT", np.uint8)
+    if qual_profile == "high":
+        qchoices, qp = np.array([40, 40, 40, 35, 30]), None
+    elif qual_profile == "low":
+        qchoices, qp = np.array([40, 30, 20, 12, 8, 3, 2]), None
+    else:
+        qchoices, qp = np.array([40, 40, 40, 35, 30, 20, 10]), None
+    names, rs, qs = [], [], []
+    for i in range(n):
+        L = length if isinstance(length, int) else int(rng.integers(length[0], length[1] + 1))
+        if rng.random() < random_frac:
+            r = rng.choice(acgt, size=L).copy()
+        else:
+            while True:
+                si = int(rng.choice(len(seqs), p=w))
+                if len(seqs[si]) > L:
+                    break
+            p = int(rng.integers(0, len(seqs[si]) - L))
+            r = seqs[si][p:p + L].copy()
+            mut = rng.random(L) < sub_rate
+            r[mut] = rng.choice(acgt, size=int(mut.sum()))
+            if rng.random() < 0.5:
+                r = np.frombuffer(r.tobytes().translate(_COMP)[::-1], np.uint8).copy()
+        if n_rate > 0:
+            r[rng.random(L) < n_rate] = ord("N")
+        q = (rng.choice(qchoices, size=L, p=qp) + 33).astype(np.uint8)
+        names.append(f"s{i}".encode())
+        rs.append(r.tobytes())
+        qs.append(q.tobytes())
+    return finalize_batch(names, rs, qs, global_seed)
+
+
+def write_fastq(path: Path, batch: ReadBatch) -> None:
+    with open(path, "wb") as f:
+        for n, s, q in zip(batch.names, batch.seqs, batch.quals):
+            f.write(b"@" + n + b"\n" + s + b"\n+\n" + q + b"\n")
