@@ -1,0 +1,359 @@
+#!/usr/bin/env python
+"""bench.py — aligned reads/s of the B200 FM-index backward-search path (100 bp, -n 2).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W]            our arm
+    python bench.py --impl reference [--gpus N] ...               the reference's CPU path (oracle/_ref)
+
+A "step" is one pass of the hot path (bt_align_batch*, all phases of `-n 2 -k 1`) over one batch of
+synthetic 100-bp reads.  `value` = whole-job reads/s with the batch already resident in HBM; `e2e` = the
+same through the C ABI with pinned HOST buffers (H2D + D2H inside the timed region).  `roofline` is the
+search kernel's algorithmic bytes (64 B per side fetch + 4 B per offs[] read + 8 B per ftab
+jump, counted by the kernel itself) over its device time.  Under torchrun every rank owns one GPU, holds the
+whole index and a disjoint shard of reads (weak scaling); the only collective is the all-reduce of the five
+hit counters.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import tempfile
+import threading
+import time
+from pathlib import Path
+
+import numpy as np
+
+ROOT = Path(__file__).resolve().parent
+sys.path.insert(0, str(ROOT))
+REF_DIR = ROOT / "oracle" / "_ref"
+READ_LEN = 100
+
+
+# ------------------------------------------------------------------------------------------------
+# workload
+# ------------------------------------------------------------------------------------------------
+
+def pick_index() -> tuple[Path, str]:
+    """Largest prebuilt synthetic index under oracle/_ref/cache (built once with the reference's
+    bowtie-build; see tests/synth.py), else the reference's shipped e_coli index."""
+    env = os.environ.get("BT_BENCH_INDEX")
+    if env:
+        return Path(env), Path(env).name
+    best = None
+    for p in sorted((REF_DIR / "cache").glob("bench_*.rev.2.ebwt")):
+        base = Path(str(p)[: -len(".rev.2.ebwt")])
+        if Path(str(base) + ".4.ebwt").exists():
+            sz = Path(str(base) + ".1.ebwt").stat().st_size
+            if best is None or sz > best[0]:
+                best = (sz, base)
+    if best:
+        return best[1], best[1].name
+    base = REF_DIR / "fixtures" / "e_coli"
+    if Path(str(base) + ".1.ebwt").exists():
+        return base, "e_coli (reference fixture)"
+    raise SystemExit("bench.py: no index available (expected oracle/_ref/cache/bench_* or oracle/_ref/fixtures/e_coli)")
+
+
+def load_genome(base: Path) -> np.ndarray:
+    """Base codes 0..3 of the joined reference from X.4.ebwt (2-bit packed, base i in bits 2*(i&3) of byte i>>2;
+    reference.h:58-330).  Reads are sampled from this text, so no FASTA has to travel with the index."""
+    raw = np.frombuffer(Path(str(base) + ".4.ebwt").read_bytes(), np.uint8)
+    out = np.empty(len(raw) * 4, np.uint8)
+    for k in range(4):
+        out[k::4] = (raw >> (2 * k)) & 3
+    return out
+
+
+def make_reads(genome: np.ndarray, n: int, seed: int):
+    """n x 100 bp: uniform positions, both strands, 1 % substitutions, 0.1 % random reads, Phred33 quals from
+    {40,40,40,35,30,20,10}.  Returns (codes[n*100], quals[n*100], offs[n+1], seeds[n], names)."""
+    rng = np.random.default_rng(seed)
+    L = READ_LEN
+    pos = rng.integers(0, len(genome) - L, n)
+    codes = genome[pos[:, None] + np.arange(L)[None, :]]
+    mut = rng.random((n, L)) < 0.01
+    codes[mut] = (codes[mut] + rng.integers(1, 4, int(mut.sum()))) & 3
+    rnd = rng.random(n) < 0.001
+    codes[rnd] = rng.integers(0, 4, (int(rnd.sum()), L))
+    rc = rng.random(n) < 0.5
+    flipped = codes[rc, ::-1]
+    codes[rc] = np.where(flipped < 4, 3 - flipped, 4)
+    codes = np.ascontiguousarray(codes, np.uint8)
+    quals = (rng.choice(np.array([40, 40, 40, 35, 30, 20, 10], np.uint8), (n, L)) + 33).astype(np.uint8)
+    # names "r%09d" (fixed width so genRandSeed vectorises); Read::seed per pat.cpp:21-57 with global seed 0
+    ids = np.arange(n, dtype=np.uint32)
+    name = np.zeros((n, 10), np.uint8)
+    name[:, 0] = ord("r")
+    for d in range(9):
+        name[:, 9 - d] = (ids // 10 ** d) % 10 + 48
+    seeds = np.full(n, ((0 + 101) * 59 * 61 * 67 * 71 * 73 * 79 * 83) & 0xFFFFFFFF, np.uint32)
+    i = np.arange(L)
+    seeds ^= np.bitwise_xor.reduce(codes.astype(np.uint32) << ((i & 15) << 1).astype(np.uint32), axis=1)
+    seeds ^= np.bitwise_xor.reduce(quals.astype(np.uint32) << ((i & 3) << 3).astype(np.uint32), axis=1)
+    j = np.arange(10)
+    seeds ^= np.bitwise_xor.reduce(name.astype(np.uint32) << ((j & 3) << 3).astype(np.uint32), axis=1)
+    offs = (np.arange(n + 1, dtype=np.uint64) * L)
+    return codes.reshape(-1), quals.reshape(-1), offs, seeds.astype(np.uint32), name
+
+
+def write_fastq(path: Path, codes, quals, name, n: int) -> None:
+    L = READ_LEN
+    lut = np.frombuffer(b"ACGTN", np.uint8)
+    seq = lut[codes[: n * L]].reshape(n, L)
+    q = quals[: n * L].reshape(n, L)
+    rec = np.empty((n, 1 + 10 + 1 + L + 3 + L + 1), np.uint8)
+    rec[:, 0] = ord("@"); rec[:, 1:11] = name[:n]; rec[:, 11] = 10
+    rec[:, 12:12 + L] = seq; rec[:, 12 + L] = 10; rec[:, 13 + L] = ord("+"); rec[:, 14 + L] = 10
+    rec[:, 15 + L:15 + 2 * L] = q; rec[:, 15 + 2 * L] = 10
+    path.write_bytes(rec.tobytes())
+
+
+# ------------------------------------------------------------------------------------------------
+# clocks (recipe of /opt/skills/guides/B200_PROFILING.md)
+# ------------------------------------------------------------------------------------------------
+
+class ClockSampler:
+    Q = "clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+
+    def __init__(self, gpu: int) -> None:
+        self.gpu, self.samples, self.stop = gpu, [], threading.Event()
+        self.t = threading.Thread(target=self.run, daemon=True)
+
+    def run(self) -> None:
+        while not self.stop.is_set():
+            try:
+                o = subprocess.run(["nvidia-smi", "-i", str(self.gpu), f"--query-gpu={self.Q}", "--format=csv,noheader,nounits"],
+                                   capture_output=True, text=True, timeout=5).stdout.strip()
+                if o:
+                    self.samples.append([x.strip() for x in o.split(",")])
+            except Exception:
+                pass
+            self.stop.wait(0.2)
+
+    def __enter__(self):
+        self.t.start()
+        return self
+
+    def __exit__(self, *a):
+        self.stop.set()
+        self.t.join(timeout=6)
+
+    def summary(self) -> dict:
+        if not self.samples:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["unsampled"]}
+        sm = sorted(int(s[0]) for s in self.samples if s[0].isdigit())
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = [n for k, n in enumerate(names) if any(len(s) > 2 + k and s[2 + k].startswith("Active") for s in self.samples)]
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": int(self.samples[0][1]) if self.samples[0][1].isdigit() else None,
+                "reasons": reasons, "samples": len(self.samples)}
+
+
+# ------------------------------------------------------------------------------------------------
+# reference arm / cpu baseline: the UNMODIFIED reference binary on the host cores
+# ------------------------------------------------------------------------------------------------
+
+def run_reference_sample(base: Path, fq: Path, n: int, threads: int) -> tuple[float, float]:
+    """bowtie-align-s -n 2 -k 1 -t -p <threads>; returns (search seconds from -t, wall seconds)."""
+    exe = REF_DIR / "bowtie-align-s"
+    if not exe.exists():
+        raise RuntimeError("oracle/_ref/bowtie-align-s missing (built by oracle/Makefile from /root/reference)")
+    t0 = time.time()
+    p = subprocess.run([str(exe), "-n", "2", "-k", "1", "-t", "-p", str(threads), "-x", str(base), str(fq), "/dev/null"],
+                       capture_output=True, text=True)
+    wall = time.time() - t0
+    if p.returncode != 0:
+        raise RuntimeError("reference run failed: " + p.stderr[-500:])
+    search = None
+    for line in (p.stdout + p.stderr).splitlines():
+        if line.startswith("Time searching:"):
+            h, m, s = line.split(":", 1)[1].strip().split(":")
+            search = int(h) * 3600 + int(m) * 60 + int(s)
+    return (float(search) if search else wall), wall
+
+
+def main() -> None:
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--reads-per-step", type=int, default=int(os.environ.get("BT_BENCH_READS", 2_000_000)))
+    ap.add_argument("--cpu-sample", type=int, default=int(os.environ.get("BT_BENCH_CPU_SAMPLE", 1_000_000)))
+    args = ap.parse_args()
+    rank, world, local = int(os.environ.get("RANK", 0)), int(os.environ.get("WORLD_SIZE", 1)), int(os.environ.get("LOCAL_RANK", 0))
+    base, idx_name = pick_index()
+    cfg_workload = f"-n 2 -k 1, {READ_LEN} bp synthetic reads (1% subs, both strands), index {idx_name}"
+    cores = os.cpu_count() or 1
+
+    if args.impl == "reference":
+        if rank != 0:
+            return
+        genome = load_genome(base)
+        n = min(args.cpu_sample, args.reads_per_step)
+        codes, quals, offs, seeds, name = make_reads(genome, n, seed=12345)
+        with tempfile.TemporaryDirectory() as td:
+            fq = Path(td) / "s.fq"
+            write_fastq(fq, codes, quals, name, n)
+            times = []
+            for it in range(args.warmup + args.steps):
+                search, wall = run_reference_sample(base, fq, n, cores)
+                if it >= args.warmup:
+                    times.append(wall)
+        tot = sum(times)
+        val = n * args.steps / tot
+        line = {"impl": "reference", "metric": "aligned reads/sec (100 bp, -n 2)", "value": val, "unit": "reads/s", "n_gpus": args.gpus,
+                "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * tot / args.steps, "higher_is_better": True,
+                "scaling": "weak", "vs_baseline": None, "dtype": "u32", "data": "synthetic",
+                "config": {"workload": cfg_workload, "reads_per_step": n, "parallelism": f"{cores} host threads (bowtie -p)"},
+                "cpu_baseline": {"value": val, "unit": "reads/s", "cores": cores, "kind": "reference",
+                                 "sample": f"{n} reads per step, wall clock of bowtie-align-s -n 2 -k 1 -p {cores} incl. index load"},
+                "e2e": {"value": val, "unit": "reads/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+        print(json.dumps(line))
+        return
+
+    import torch
+    import torch.distributed as dist
+    import bowtie_b200
+
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device (the product has no CPU path)")
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    bowtie_b200.build_library()
+    ix = bowtie_b200.Index(str(base), need_mirror=True, device=local)
+    pol = bowtie_b200.Policy(mode=1, mms=2, khits=1)
+    B, L, slots, mm_cap = args.reads_per_step, READ_LEN, 1, 7
+    rw = bowtie_b200.BT_HIT_HDR_WORDS + mm_cap
+    genome = load_genome(base)
+    # two distinct batches per rank, alternated, each larger than L2 (2M reads x 200 B = 400 MB)
+    host = [make_reads(genome, B, seed=12345 + 1000 * rank + k) for k in range(2)]
+    dev = [tuple(torch.from_numpy(np.ascontiguousarray(a)).cuda() for a in (h[0], h[1], h[2].view(np.int64), h[3].view(np.int32))) for h in host]
+    d_found = torch.zeros(B, dtype=torch.int32, device="cuda")
+    d_flags = torch.zeros(B, dtype=torch.int32, device="cuda")
+    d_hits = torch.zeros(B * slots * rw, dtype=torch.int32, device="cuda")
+    stream = torch.cuda.current_stream().cuda_stream
+
+    def step_dev(k: int) -> None:
+        s, q, o, sd = dev[k & 1]
+        ix.align_device(s.data_ptr(), q.data_ptr(), o.data_ptr(), sd.data_ptr(), B, L, pol, d_found.data_ptr(), d_flags.data_ptr(),
+                        d_hits.data_ptr(), slots, mm_cap, stream)
+
+    def barrier() -> None:
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for k in range(args.warmup):
+        step_dev(k)
+    barrier()
+    ix.stats(reset=True)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    with ClockSampler(local) as clk:
+        barrier()
+        e0.record()
+        for k in range(args.steps):
+            step_dev(k)
+        e1.record()
+        barrier()
+    ms = e0.elapsed_time(e1)
+    st = ix.stats(reset=True)
+    flags_bad = int((d_flags != 0).sum().item())
+    aligned = int((d_found > 0).sum().item())
+    t = torch.tensor([ms], dtype=torch.float64, device="cuda")
+    ctr = torch.tensor([aligned, B - aligned, 0, aligned, 0], dtype=torch.int64, device="cuda")   # counters of the last step (hit.h:169-175)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        dist.all_reduce(ctr, op=dist.ReduceOp.SUM)                                                  # the path's only collective
+    ms_max = float(t.item())
+    value = B * args.steps * world / (ms_max / 1e3)
+
+    # end to end through the host-buffer entry point: pinned host inputs, H2D + kernels + D2H every step
+    pin = []
+    for h in host:
+        ts = [torch.from_numpy(np.ascontiguousarray(a)).pin_memory() for a in (h[0], h[1], h[2].view(np.int64), h[3].view(np.int32))]
+        pin.append(ts)
+    o_found = torch.zeros(B, dtype=torch.int32).pin_memory()
+    o_flags = torch.zeros(B, dtype=torch.int32).pin_memory()
+    o_hits = torch.zeros(B * slots * rw, dtype=torch.int32).pin_memory()
+    outs = (o_found.numpy().view(np.uint32), o_flags.numpy().view(np.uint32), o_hits.numpy().view(np.uint32).reshape(B, slots, rw))
+
+    def step_e2e(k: int) -> None:
+        s, q, o, sd = pin[k & 1]
+        ix.align(s.numpy(), q.numpy(), o.numpy().view(np.uint64), sd.numpy().view(np.uint32), pol, slots=slots, mm_cap=mm_cap, out=outs, stream=stream)
+
+    for k in range(max(1, args.warmup - 1)):
+        step_e2e(k)
+    barrier()
+    t0 = time.perf_counter()
+    for k in range(args.steps):
+        step_e2e(k)
+    barrier()
+    e2e_s = time.perf_counter() - t0
+    t = torch.tensor([e2e_s], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    e2e_val = B * args.steps * world / float(t.item())
+    h2d = 2 * B * L + 8 * (B + 1) + 4 * B
+    d2h = 4 * B + 4 * B + 4 * B * slots * rw
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    peaks = {}
+    try:
+        peaks = json.loads((ROOT / "MEASURED_PEAKS.json").read_text())
+    except Exception:
+        pass
+    peak = float(peaks.get("hbm_gbs", 6650.0))
+    alg_bytes = st.algorithmic_bytes / args.steps
+    achieved = alg_bytes / (ms / args.steps / 1e3) / 1e9
+    traffic = None
+    tp = ROOT / "profiles" / "traffic_per_launch.json"
+    if tp.exists():
+        try:
+            traffic = json.loads(tp.read_text()).get("dram_bytes_per_launch")
+        except Exception:
+            pass
+    cpu = None
+    if world == 1:
+        try:
+            n = min(args.cpu_sample, B)
+            with tempfile.TemporaryDirectory() as td:
+                fq = Path(td) / "s.fq"
+                write_fastq(fq, host[0][0], host[0][1], host[0][4], n)
+                search, wall = run_reference_sample(base, fq, n, cores)
+            cpu = {"value": n / wall, "unit": "reads/s", "cores": cores, "kind": "reference",
+                   "sample": f"first {n} reads of step 0, bowtie-align-s -n 2 -k 1 -p {cores}, wall clock {wall:.1f}s incl. index load ('Time searching' {search:.0f}s)"}
+        except Exception as ex:  # the reference binary did not travel: report why instead of a number
+            cpu = {"value": None, "unit": "reads/s", "cores": cores, "kind": "reference", "sample": f"unavailable: {ex}"}
+    line = {
+        "metric": "aligned reads/sec (100 bp, -n 2)", "value": value, "unit": "reads/s", "n_gpus": world, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": ms_max / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "u32", "data": "synthetic",
+        "config": {"workload": cfg_workload, "reads_per_step_per_gpu": B, "index_len_bp": ix.len, "index_device_bytes": ix.device_bytes,
+                   "parallelism": f"reads sharded over {world} GPU(s), full index per GPU",
+                   "l2": "two alternating read batches of 400 MB each (> 126 MB L2); index smaller than L2 stays partly resident",
+                   "aligned_frac_last_step": aligned / B, "overflow_flags": flags_bad,
+                   "counters_allreduced": [int(x) for x in ctr.tolist()]},
+        "clocks": clk.summary(),
+        "e2e": {"value": e2e_val, "unit": "reads/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
+        "gpu_launches": 5 * args.steps,
+        "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
+                     "peak_source": "MEASURED_PEAKS.json hbm_gbs" if peaks else "fallback 6650 GB/s",
+                     "side_fetches_per_read": st.side_fetches / (B * args.steps), "block_loads_per_read": st.block_loads / (B * args.steps),
+                     "algorithmic_bytes_per_read": alg_bytes / B},
+        "cpu_baseline": cpu,
+    }
+    print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

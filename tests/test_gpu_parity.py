@@ -31,7 +31,7 @@ def gpu_align(ix, batch, pol, slots=None, mm_cap=8):
     assert not (flags & 7).any(), "scratch overflows must be resolved inside the library"
     if len(need):
         lim = 0xFFFFFFFF if pol.all_hits else pol.khits
-        slots2 = int(min(int(found[need].max()), lim))
+        slots2 = int(min(int(found.max()), lim))
         maxlen = int((batch.offs[1:] - batch.offs[:-1]).max())
         f2 = found.copy(); g2 = flags.copy(); h2 = np.zeros((len(found), slots2, 5 + maxlen), np.uint32)
         ix.align(batch.seq_codes, batch.qual_cat, batch.offs, batch.seeds, to_dev(pol), slots=slots2, mm_cap=maxlen,
