@@ -125,7 +125,7 @@ enum {
 	PC_REPORT_RET, PC_BT_END, PC_FINISH_READ, PC_EXIT
 };
 enum { SITE_MAIN = 0, SITE_BT, SITE_END, SITE_FTABFULL };
-enum { LFK_EX = 0, LFK_ONE, LFK_PAIR };
+enum { LFK_EX = 0, LFK_ONE, LFK_PAIR, LFK_FCHR, LFK_NONE };
 
 struct BtLane {
 	/* read */
@@ -137,7 +137,7 @@ struct BtLane {
 	uint32_t ebwtSel, fw, considerQuals, halfAndHalf, reportPartials, reportExacts, maqPenalty;
 	uint32_t qualThresh, maxBts;
 	uint32_t qlen, depth5, depth3, unrev0, rev1_0, rev2_0, rev3_0, iham;
-	uint32_t nmuts, mut[3];        /* pos | newBase << 16 | oldBase << 24                      */
+	uint32_t nmuts, mut0, mut1, mut2;   /* pos | newBase << 16 | oldBase << 24                 */
 	uint32_t rnd, numBts, bailed, viewRev, viewComp;
 	/* current frame */
 	uint32_t stackDepth, depth, d, unrevOff, oneRevOff, twoRevOff, threeRevOff, ham;
@@ -176,7 +176,11 @@ BT_FN uint32_t bt_qry_raw(const BtKParams &P, const BtLane &L, uint32_t cur) {
 }
 BT_FN uint32_t bt_qry(const BtKParams &P, const BtLane &L, uint32_t cur) {
 	uint32_t c = bt_qry_raw(P, L, cur);
-	for (uint32_t k = 0; k < L.nmuts; k++) if ((L.mut[k] & 0xffffu) == cur) c = (L.mut[k] >> 16) & 0xff;
+	if (L.nmuts > 0) {
+		if ((L.mut0 & 0xffffu) == cur) c = (L.mut0 >> 16) & 0xff;
+		if (L.nmuts > 1 && (L.mut1 & 0xffffu) == cur) c = (L.mut1 >> 16) & 0xff;
+		if (L.nmuts > 2 && (L.mut2 & 0xffffu) == cur) c = (L.mut2 >> 16) & 0xff;
+	}
 	return c;
 }
 BT_FN uint32_t bt_qual_at(const BtKParams &P, const BtLane &L, uint32_t cur) {
@@ -288,7 +292,9 @@ BT_FN void bt_set_muts(BtLane &L, const BtKParams &P, uint64_t pal) {
 		uint32_t tpos = (L.rlen - 1 - pos) & 0xffffu;
 		oldQuals = (oldQuals + bt_mm_penalty(L.maqPenalty, bt_qual_at(P, L, tpos))) & 0xff;
 		uint32_t oldc = bt_qry_raw(P, L, tpos);
-		L.mut[L.nmuts++] = tpos | (chr << 16) | (oldc << 24);
+		uint32_t mv = tpos | (chr << 16) | (oldc << 24);
+		if (k == 0) L.mut0 = mv; else if (k == 1) L.mut1 = mv; else L.mut2 = mv;
+		L.nmuts = k + 1;
 	}
 	L.iham = oldQuals;
 	L.pc = PC_BT_BEGIN;
@@ -482,7 +488,7 @@ BT_FN bool bt_sink_report(BtLane &L, const BtKParams &P, const BtScratch &S, uin
 			for (uint32_t i = 0; i < nmm; i++) {
 				uint32_t pos, refc;
 				if (i < nsearch) { pos = S.frames[i].mm_pos; refc = S.frames[i].mm_refc; }
-				else { uint32_t mu = L.mut[i - nsearch]; pos = mu & 0xffffu; refc = (mu >> 16) & 0xff; }
+				else { uint32_t km = i - nsearch; uint32_t mu = km == 0 ? L.mut0 : km == 1 ? L.mut1 : L.mut2; pos = mu & 0xffffu; refc = (mu >> 16) & 0xff; }
 				if (flip) pos = L.qlen - pos - 1;
 				if (i < P.mm_cap) rec[BT_HIT_HDR + i] = pos | (refc << 16); else L.flags |= BT_FLAG_MM_OVF;
 			}
@@ -531,9 +537,28 @@ BT_FN void bt_report_begin(BtLane &L, const BtKParams &P, const BtScratch &S, ui
 	L.pc = PC_REPORT_ROW;
 }
 
+/* Position prologue: the part of the while-loop body before the LF step (ebwt_search_backtrack.h:472-529),
+ * given the query character and quality of position L.d.  Leaves L.pc = PC_LF when rank blocks are needed. */
+BT_FN void bt_prologue(BtLane &L, uint32_t c, uint32_t q) {
+	L.c = c; L.q = q;
+	L.curIsElig = 0; L.curOverrides = 0;
+	L.curIsAlt = (L.d >= L.unrevOff) && (!L.considerQuals || (L.ham + bt_mm_penalty(L.maqPenalty, q) <= L.qualThresh));
+	if (L.curIsAlt) {
+		if (L.considerQuals) {
+			if (q < L.lowAltQual) { L.curIsElig = 1; L.curOverrides = 1; }
+			else if (q == L.lowAltQual) L.curIsElig = 1;
+		} else L.curIsElig = 1;
+	}
+	if (c == 4 && L.d > 0) L.top = L.bot = 1;
+	if (L.top == 0 && L.bot == 0) { L.lfk = LFK_FCHR; L.pc = PC_POS2; }
+	else if (L.curIsAlt) { L.lfk = LFK_EX; L.pc = PC_LF; }
+	else if (c < 4) { L.lfk = (L.top + 1 == L.bot) ? LFK_ONE : LFK_PAIR; L.pc = PC_LF; }
+	else { L.lfk = LFK_NONE; L.pc = PC_POS2; }
+}
+
 /* One transition of the lane's state machine.  bA/bB are the rank blocks of (top, bot) resp. the
  * chase row, valid when the lane was in PC_LF / PC_CHASE at the fetch stage. */
-BT_FN void bt_step(BtLane &L, const BtKParams &P, const BtScratch &S, const BtBlock &bA, const BtBlock &bB) {
+BT_FN void bt_step(BtLane &L, const BtKParams &P, const BtScratch &S, const BtBlock &bA, const BtBlock &bB, uint32_t nc, uint32_t nq) {
 	const BtDevIndex &ix = P.ix[L.ebwtSel];
 	switch (L.pc) {
 	case PC_PHASE:
@@ -575,7 +600,8 @@ BT_FN void bt_step(BtLane &L, const BtKParams &P, const BtScratch &S, const BtBl
 		break; }
 
 	case PC_POS: {
-		/* top of while(cur < _qlen) (ebwt_search_backtrack.h:456-568) */
+		/* top of while(cur < _qlen) (ebwt_search_backtrack.h:456-568), entered with its own query loads
+		 * (frame entry and rare paths; the common path chains positions inside PC_LF below) */
 		if (L.d >= L.qlen) {
 			if (L.stackDepth >= L.reportPartials) bt_report_begin(L, P, S, L.stackDepth, L.top, L.bot, L.ham, SITE_END);
 			else { L.ret = 0; L.pc = PC_FRAME_RET; }
@@ -583,43 +609,19 @@ BT_FN void bt_step(BtLane &L, const BtKParams &P, const BtScratch &S, const BtBl
 		}
 		if (L.halfAndHalf && !bt_hh_check_top(L, S)) { L.ret = 0; L.pc = PC_FRAME_RET; break; }
 		const uint32_t cur = L.qlen - L.d - 1;
-		const uint32_t c = bt_qry(P, L, cur), q = bt_qual_at(P, L, cur);
-		L.c = c; L.q = q;
-		L.curIsElig = 0; L.curOverrides = 0;
-		L.curIsAlt = (L.d >= L.unrevOff) && (!L.considerQuals || (L.ham + bt_mm_penalty(L.maqPenalty, q) <= L.qualThresh));
-		if (L.curIsAlt) {
-			if (L.considerQuals) {
-				if (q < L.lowAltQual) { L.curIsElig = 1; L.curOverrides = 1; }
-				else if (q == L.lowAltQual) L.curIsElig = 1;
-			} else L.curIsElig = 1;
-		}
-		if (c == 4 && L.d > 0) L.top = L.bot = 1;
-		if (L.top == 0 && L.bot == 0) {
-			/* first quartet from fchr[] */
-			if (L.curIsAlt) {
-				uint32_t ri = bt_row_idx(L, L.d);
-				uint4 t = { ix.fchr[0], ix.fchr[1], ix.fchr[2], ix.fchr[3] }, b = { ix.fchr[1], ix.fchr[2], ix.fchr[3], ix.fchr[4] };
-				S.rows[2 * (size_t)ri] = t; S.rows[2 * (size_t)ri + 1] = b;
-			}
-			if (c < 4) { L.top = ix.fchr[c]; L.bot = ix.fchr[c + 1]; }
-			L.pc = PC_POS2;
-		} else if (L.curIsAlt) {
-			L.lfk = LFK_EX; L.pc = PC_LF;
-		} else if (c < 4) {
-			L.lfk = (L.top + 1 == L.bot) ? LFK_ONE : LFK_PAIR; L.pc = PC_LF;
-		} else L.pc = PC_POS2;
+		bt_prologue(L, bt_qry(P, L, cur), bt_qual_at(P, L, cur));
 		break; }
 
-	case PC_LF: {
-		const uint32_t c = L.c;
+	case PC_LF:
+	case PC_POS2: {
+		/* the LF step (ebwt_search_backtrack.h:530-568) and what follows it (569-739) */
+		const uint32_t c = L.c, q = L.q, d = L.d;
+		const uint32_t cur = L.qlen - d - 1;
+		uint32_t tops[4] = { 0, 0, 0, 0 }, bots[4] = { 0, 0, 0, 0 };
 		if (L.lfk == LFK_EX) {
 			/* mapLFEx(ltop, lbot, tops, bots) (ebwt.h:2334-2380) */
-			uint32_t tops[4], bots[4];
 			bt_lf_ex(ix, bA, L.ltop, tops);
 			bt_lf_ex(ix, bB, L.lbot, bots);
-			uint32_t ri = bt_row_idx(L, L.d);
-			uint4 t = { tops[0], tops[1], tops[2], tops[3] }, b = { bots[0], bots[1], bots[2], bots[3] };
-			S.rows[2 * (size_t)ri] = t; S.rows[2 * (size_t)ri + 1] = b;
 			L.s_lfex++;
 			if (c < 4) { L.top = tops[c]; L.bot = bots[c]; }
 		} else if (L.lfk == LFK_ONE) {
@@ -630,27 +632,28 @@ BT_FN void bt_step(BtLane &L, const BtKParams &P, const BtScratch &S, const BtBl
 			L.top = t; L.bot = t;
 			if (t != BT_OFF_MASK) L.bot++;
 			L.s_lf++;
-		} else {
+		} else if (L.lfk == LFK_PAIR) {
 			uint32_t t = bt_lf(ix, bA, L.ltop, c), b = bt_lf(ix, bB, L.lbot, c);
 			L.top = t; L.bot = b;
 			L.s_lf += 2;
+		} else if (L.lfk == LFK_FCHR) {
+			/* first quartet from fchr[] (ebwt_search_backtrack.h:531-543) */
+			tops[0] = ix.fchr[0]; tops[1] = ix.fchr[1]; tops[2] = ix.fchr[2]; tops[3] = ix.fchr[3];
+			bots[0] = ix.fchr[1]; bots[1] = ix.fchr[2]; bots[2] = ix.fchr[3]; bots[3] = ix.fchr[4];
+			if (c < 4) { L.top = tops[c]; L.bot = bots[c]; }
 		}
-		L.pc = PC_POS2;
-	} /* fallthrough */
-
-	case PC_POS2: {
-		/* after the LF step (ebwt_search_backtrack.h:569-739) */
-		const uint32_t c = L.c, q = L.q, d = L.d;
-		const uint32_t cur = L.qlen - d - 1;
 		if (L.top != L.bot) { L.ltop = L.top; L.lbot = L.bot; }   /* SideLocus::initFromTopBot */
 		if (d >= L.rowd0) {
-			uint32_t ri = bt_row_idx(L, d);
+			const uint32_t ri = bt_row_idx(L, d);
 			uint32_t el = (c < 4) ? (1u << c) : 0u;                   /* eliminate() */
 			if (L.curIsAlt) {
+				uint4 tv = { tops[0], tops[1], tops[2], tops[3] }, bv = { bots[0], bots[1], bots[2], bots[3] };
+				S.rows[2 * (size_t)ri] = tv; S.rows[2 * (size_t)ri + 1] = bv;
+#pragma unroll
 				for (uint32_t i = 0; i < 4; i++) {
 					if (i == c) continue;
-					uint32_t ptop = bt_pair_top(S, ri, i), pbot = bt_pair_bot(S, ri, i);
-					uint32_t spread = pbot - ptop;
+					const uint32_t ptop = tops[i], pbot = bots[i];
+					const uint32_t spread = pbot - ptop;
 					if (spread == 0) el |= (1u << i);
 					else {
 						if (L.curIsElig) {
@@ -694,8 +697,16 @@ BT_FN void bt_step(BtLane &L, const BtKParams &P, const BtScratch &S, const BtBl
 			bt_report_begin(L, P, S, L.stackDepth, L.top, L.bot, L.ham, SITE_MAIN);
 			break;
 		}
-		L.pc = PC_BTLOOP;
-	} /* fallthrough */
+		if ((L.top == L.bot || L.f_bdm) && L.altNum > 0) { L.pc = PC_BTLOOP; break; }   /* mismatch with alternatives: next transition */
+		/* match (or dead end): the tail of the loop body (1066-1078) and, on a match, the next position's
+		 * prologue with the query character prefetched in the fetch stage — one transition per position */
+		if (L.f_must || L.f_invHH || L.f_invExact) { L.ret = 0; L.pc = PC_FRAME_RET; break; }
+		if (L.top == L.bot) { L.ret = 0; L.pc = PC_FRAME_RET; break; }
+		L.d = d + 1;
+		if (L.d >= L.qlen) { L.pc = PC_POS; break; }
+		if (L.halfAndHalf && !bt_hh_check_top(L, S)) { L.ret = 0; L.pc = PC_FRAME_RET; break; }
+		bt_prologue(L, nc, nq);
+		break; }
 
 	case PC_BTLOOP: {
 		/* while((top == bot || backtrackDespiteMatch) && altNum > 0) (ebwt_search_backtrack.h:743-971) */
@@ -911,11 +922,15 @@ BT_FN void bt_finish_read(BtLane &L, const BtKParams &P) {
 	P.flags[L.rid] = L.flags;
 }
 
-/* One iteration of the lane loop: the (warp-converged) fetch stage followed by one transition. */
+/* One iteration of the lane loop: the (warp-converged) fetch stage followed by one transition.
+ * Fetch stage = the rank block(s) of the pending LF / chase step plus the NEXT position's query
+ * character and quality, all independent loads in flight together. */
 BT_FN void bt_iter(BtLane &L, const BtKParams &P, const BtScratch &S) {
+	if (L.flags & BT_FLAG_PART_OVF) { L.found = 0; L.pc = PC_FINISH_READ; return; }   /* retried with a larger workspace */
 	BtBlock bA, bB;
 	bA.occ.x = bA.occ.y = bA.occ.z = bA.occ.w = 0; bA.hi = bA.lo = 0;
 	const bool isLF = (L.pc == PC_LF), isChase = (L.pc == PC_CHASE);
+	uint32_t nc = 4, nq = 0;
 	if (isLF || isChase) {
 		const BtDevIndex &ix = P.ix[L.ebwtSel];
 		const uint32_t rowA = isChase ? L.crow : L.ltop;
@@ -927,6 +942,10 @@ BT_FN void bt_iter(BtLane &L, const BtKParams &P, const BtScratch &S) {
 		bB = bt_load_block(P.ix[L.ebwtSel], L.lbot);
 		L.s_blk++;
 	}
+	if ((isLF || L.pc == PC_POS2) && L.d + 1 < L.qlen) {
+		const uint32_t ncur = L.qlen - L.d - 2;
+		nc = bt_qry(P, L, ncur); nq = bt_qual_at(P, L, ncur);
+	}
 	L.s_iter++;
-	bt_step(L, P, S, bA, bB);
+	bt_step(L, P, S, bA, bB, nc, nq);
 }

@@ -68,7 +68,7 @@ bt_search_kernel(BtKParams P, BtWorkCtl *ctl) {
 	BtLane L;
 	L.pc = PC_NEXT_READ;
 	L.s_lfex = L.s_lf = L.s_chase = L.s_ftab = L.s_offs = L.s_bt = L.s_iter = L.s_blk = 0;
-	L.nmuts = 0; L.ebwtSel = 0; L.lfk = 0; L.ltop = L.lbot = L.crow = 0;
+	L.nmuts = 0; L.mut0 = L.mut1 = L.mut2 = 0; L.ebwtSel = 0; L.lfk = 0; L.ltop = L.lbot = L.crow = 0; L.flags = 0; L.d = 0; L.qlen = 0;
 	const unsigned long long nwork = ctl->nwork;
 	for (;;) {
 		/* work distribution: warp-aggregated grab from the global cursor */

@@ -430,7 +430,7 @@ class HostEmu:
         L.emu_align.restype = C.c_int
         L.emu_align.argtypes = [C.c_void_p, C.c_void_p, C.POINTER(_DevPolicy), C.c_uint32, C.c_void_p, C.c_void_p, C.c_void_p,
                                 C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint32, C.c_uint32, C.c_uint32,
-                                C.c_uint32, C.c_uint32, C.c_void_p]
+                                C.c_uint32, C.c_uint32, C.c_void_p, C.c_void_p]
         self.L = L
         self._idx = {}
 
@@ -456,10 +456,11 @@ class HostEmu:
         flags = np.zeros(n, np.uint32)
         hits = np.zeros(n * slots * (BT_HIT_HDR + mm_cap), np.uint32)
         stats = np.zeros(8, np.uint64)
+        self.iters_per_read = np.zeros(n, np.uint32)
         cp = dev_policy(pol)
         rc = self.L.emu_align(fw, bw, C.byref(cp), n, batch.seq_codes.ctypes.data, batch.qual_cat.ctypes.data,
                               batch.offs.ctypes.data, batch.seeds.ctypes.data, found.ctypes.data, flags.ctypes.data,
-                              hits.ctypes.data, slots, mm_cap, R, FCAP, PCAP, stats.ctypes.data)
+                              hits.ctypes.data, slots, mm_cap, R, FCAP, PCAP, stats.ctypes.data, self.iters_per_read.ctypes.data)
         if rc:
             raise RuntimeError(f"emu_align rc={rc}")
         res = decode_device_result(found, hits, slots, mm_cap, pol)

@@ -48,7 +48,7 @@ int emu_row_l(void *p, uint32_t row) { EmuIndex *e = (EmuIndex *)p; BtBlock b = 
 
 int emu_align(void *fwp, void *bwp, const BtPolicy *pol, uint32_t nreads, const uint8_t *seq, const uint8_t *qual,
               const uint64_t *roff, const uint32_t *seeds, uint32_t *found, uint32_t *flags, uint32_t *hits,
-              uint32_t slots, uint32_t mm_cap, uint32_t R, uint32_t FCAP, uint32_t PCAP, unsigned long long *stats) {
+              uint32_t slots, uint32_t mm_cap, uint32_t R, uint32_t FCAP, uint32_t PCAP, unsigned long long *stats, uint32_t *iters_per_read) {
 	BtKParams P; memset(&P, 0, sizeof P);
 	P.ix[0] = ((EmuIndex *)fwp)->dev;
 	if (bwp) P.ix[1] = ((EmuIndex *)bwp)->dev;
@@ -61,9 +61,10 @@ int emu_align(void *fwp, void *bwp, const BtPolicy *pol, uint32_t nreads, const 
 	BtLane L; memset(&L, 0, sizeof L);
 	for (uint32_t r = 0; r < nreads; r++) {
 		bt_begin_read(L, P, r);
-		unsigned long long guard = 0;
+		unsigned long long guard = 0; uint32_t it0 = L.s_iter;
 		while (L.pc != PC_FINISH_READ) { bt_iter(L, P, S); if (++guard > (1ull << 34)) return 1; }
 		bt_finish_read(L, P);
+		if (iters_per_read) iters_per_read[r] = L.s_iter - it0;
 	}
 	stats[0] = L.s_lfex; stats[1] = L.s_lf; stats[2] = L.s_chase; stats[3] = L.s_ftab; stats[4] = L.s_offs; stats[5] = L.s_bt; stats[6] = L.s_iter; stats[7] = L.s_blk;
 	return 0;
