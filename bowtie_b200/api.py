@@ -14,7 +14,10 @@ OVF_STACK, OVF_FRAME, OVF_PART, OVF_HITS, OVF_MM = 1, 2, 4, 8, 16
 
 
 def lib_path() -> Path:
-    return _PKG / "libbowtie_b200.so"
+    """The in-tree CUDA library; BOWTIE_B200_LIB selects a tuning variant built by `make variants` (development only)."""
+    import os
+    v = os.environ.get("BOWTIE_B200_LIB")
+    return Path(v) if v else _PKG / "libbowtie_b200.so"
 
 
 def build_library(force: bool = False) -> Path:

@@ -129,8 +129,9 @@ enum { LFK_EX = 0, LFK_ONE, LFK_PAIR, LFK_FCHR, LFK_NONE };
 
 struct BtLane {
 	/* read */
-	uint32_t rid, rlen, seed, found, flags;
+	uint32_t rid, rlen, seed, found, flags, hasN;
 	uint64_t roff;
+	const uint8_t *rseq, *rqual;     /* this read's bases / qualities (shared-memory staging copy, or global) */
 	/* control */
 	uint32_t pc, ph, done, ret, lfk;
 	/* backtracker object state */
@@ -170,7 +171,7 @@ BT_FN uint32_t bt_rand_next(uint32_t &last) {                                   
  * GreedyDFSRangeSource::setQuery, ebwt_search_backtrack.h:90-99), with seedling mutations applied */
 BT_FN uint32_t bt_qry_raw(const BtKParams &P, const BtLane &L, uint32_t cur) {
 	uint32_t idx = L.viewRev ? (L.rlen - 1 - cur) : cur;
-	uint32_t c = BT_LDG(P.seq + L.roff + idx);
+	uint32_t c = L.rseq[idx];
 	if (L.viewComp && c < 4) c ^= 3;
 	return c;
 }
@@ -185,7 +186,7 @@ BT_FN uint32_t bt_qry(const BtKParams &P, const BtLane &L, uint32_t cur) {
 }
 BT_FN uint32_t bt_qual_at(const BtKParams &P, const BtLane &L, uint32_t cur) {
 	uint32_t idx = L.viewRev ? (L.rlen - 1 - cur) : cur;
-	uint32_t ch = BT_LDG(P.qual + L.roff + idx);
+	uint32_t ch = L.rqual[idx];
 	return ch >= 33 ? ch - 33 : 0;                     /* phredCharToPhredQual qual.h:15-17 */
 }
 
@@ -360,7 +361,7 @@ BT_FN void bt_phase(BtLane &L, const BtKParams &P, const BtScratch &S) {
 				if (len < 4) skip = true;
 				else {
 					uint32_t ns = 0;
-					for (uint32_t i = 0; i < qs; i++) if (BT_LDG(P.seq + L.roff + i) == 4) { if (++ns > m) { skip = true; break; } }
+					if (L.hasN) for (uint32_t i = 0; i < qs; i++) if (L.rseq[i] == 4) { if (++ns > m) { skip = true; break; } }
 				}
 				if (skip) { L.pc = PC_FINISH_READ; return; }
 				if (!nofw) { bt_cfg(L, P, 0, 1, 0, 0, 0, 1, len, 0, len, len, len, len, len); return; }
@@ -571,7 +572,7 @@ BT_FN void bt_step(BtLane &L, const BtKParams &P, const BtScratch &S, const BtBl
 		L.numBts = 0; L.bailed = 0;
 		/* tallyNs (1308-1341) */
 		uint32_t nsInSeed = 0, nsInFtab = 0; bool ok = true;
-		for (uint32_t i = 0; i < L.rev3_0 && ok; i++) {
+		for (uint32_t i = 0; L.hasN && i < L.rev3_0 && ok; i++) {
 			if (bt_qry(P, L, L.qlen - i - 1) == 4) {
 				nsInSeed++;
 				if (nsInSeed == 1) { if (i < L.unrev0) ok = false; }
@@ -581,7 +582,7 @@ BT_FN void bt_step(BtLane &L, const BtKParams &P, const BtScratch &S, const BtBl
 			}
 		}
 		if (!ok) { L.done = 0; L.pc = PC_PHASE; break; }
-		for (uint32_t i = 0; i < ftabChars && i < L.qlen; i++) if (bt_qry(P, L, L.qlen - i - 1) == 4) nsInFtab++;
+		for (uint32_t i = 0; L.hasN && i < ftabChars && i < L.qlen; i++) if (bt_qry(P, L, L.qlen - i - 1) == 4) nsInFtab++;
 		uint32_t mlim = L.unrev0 < L.qlen ? L.unrev0 : L.qlen;
 		if (nsInFtab == 0 && mlim >= ftabChars) {
 			uint32_t ftabOff = bt_qry(P, L, L.qlen - ftabChars);                 /* calcFtabOff (1348-1362) */
@@ -908,6 +909,7 @@ BT_FN void bt_begin_read(BtLane &L, const BtKParams &P, uint32_t rid) {
 	L.roff = P.roff[rid];
 	L.rlen = (uint32_t)(P.roff[rid + 1] - L.roff);
 	L.seed = P.seeds[rid];
+	L.rseq = P.seq + L.roff; L.rqual = P.qual + L.roff; L.hasN = 1;   /* the kernel may re-point these at its staging copy */
 	L.found = 0; L.flags = 0; L.ph = 0; L.done = 0; L.npart = 0; L.nmuts = 0; L.pal_i = 0;
 	L.qualThresh = P.pol.mode == 0 ? 0xffffffffu : P.pol.qualThresh;
 	L.maxBts = P.pol.mode == 0 ? 0xffffffffu : P.pol.maxBts;

@@ -50,16 +50,34 @@ __global__ void bt_debug_lf_kernel(BtDevIndex ix, const uint32_t *rows, uint32_t
 }
 
 #define BT_THREADS 128
+#ifndef BT_MIN_BLOCKS
+#define BT_MIN_BLOCKS 4            /* register cap = 65536 / (128 * BT_MIN_BLOCKS) */
+#endif
+#ifndef BT_RARE_PERIOD
+#define BT_RARE_PERIOD 4           /* rare transitions run at least every BT_RARE_PERIOD-th iteration ... */
+#endif
+#ifndef BT_RARE_THRESH
+#define BT_RARE_THRESH 12          /* ... or as soon as this many lanes of the warp wait for one          */
+#endif
+#define BT_SMEM_LEN 128            /* reads up to this length are staged in shared memory                   */
+#define BT_SMEM_STRIDE (2 * BT_SMEM_LEN + 4)   /* +4: lanes' equal offsets fall in different banks          */
 
 struct BtWorkCtl { unsigned long long next; unsigned long long nwork; };
 
 /* Persistent search kernel: every thread is a lane that pulls read ids from a global cursor until
  * the batch is exhausted.  `ctl->nwork` is read from device memory so that the retry pass can be
- * enqueued before its size is known on the host. */
-__global__ void __launch_bounds__(BT_THREADS)
+ * enqueued before its size is known on the host.
+ *
+ * Divergence control: the LF step and the row-chase step ("fast" transitions, > 85 % of all transitions)
+ * run every iteration; every other transition ("rare": phase changes, backtrack selection, frame push/pop,
+ * hit resolution, fetching the next read) is deferred until enough lanes of the warp wait for one, so that
+ * their long, serialised code paths are paid once for many lanes instead of once per iteration. */
+__global__ void __launch_bounds__(BT_THREADS, BT_MIN_BLOCKS)
 bt_search_kernel(BtKParams P, BtWorkCtl *ctl) {
+	extern __shared__ __align__(16) uint8_t bt_smem[];
 	const uint32_t tid = blockIdx.x * blockDim.x + threadIdx.x;
 	const uint32_t lane = threadIdx.x & 31;
+	uint8_t *const my_stage = bt_smem + (size_t)threadIdx.x * BT_SMEM_STRIDE;
 	BtScratch S;
 	S.rows = P.rows + (size_t)tid * P.R * 2;
 	S.elims = P.elims + (size_t)tid * P.R;
@@ -69,27 +87,61 @@ bt_search_kernel(BtKParams P, BtWorkCtl *ctl) {
 	L.pc = PC_NEXT_READ;
 	L.s_lfex = L.s_lf = L.s_chase = L.s_ftab = L.s_offs = L.s_bt = L.s_iter = L.s_blk = 0;
 	L.nmuts = 0; L.mut0 = L.mut1 = L.mut2 = 0; L.ebwtSel = 0; L.lfk = 0; L.ltop = L.lbot = L.crow = 0; L.flags = 0; L.d = 0; L.qlen = 0;
+	L.rlen = 0; L.roff = 0; L.rseq = P.seq; L.rqual = P.qual; L.hasN = 1;
 	const unsigned long long nwork = ctl->nwork;
-	for (;;) {
-		/* work distribution: warp-aggregated grab from the global cursor */
-		const bool want = (L.pc == PC_NEXT_READ);
-		const unsigned wmask = __ballot_sync(0xffffffffu, want);
-		if (wmask) {
-			const int leader = __ffs(wmask) - 1;
-			unsigned long long base = 0;
-			if ((int)lane == leader) base = atomicAdd(&ctl->next, (unsigned long long)__popc(wmask));
-			base = __shfl_sync(0xffffffffu, base, leader);
-			if (want) {
-				unsigned long long w = base + (unsigned long long)__popc(wmask & ((1u << lane) - 1u));
-				if (w < nwork) {
-					uint32_t rid = P.sel ? P.sel[w] : (uint32_t)w;
-					bt_begin_read(L, P, rid);
-				} else L.pc = PC_EXIT;
+	uint32_t it = 0;
+	for (;; it++) {
+		const bool fast = (L.pc == PC_LF || L.pc == PC_POS2 || L.pc == PC_CHASE);
+		const bool rare = !fast && L.pc != PC_EXIT;
+		const unsigned fmask = __ballot_sync(0xffffffffu, fast);
+		const unsigned rmask = __ballot_sync(0xffffffffu, rare);
+		if ((fmask | rmask) == 0) break;                                  /* every lane has exited */
+		const bool run_rare = (fmask == 0) || (__popc(rmask) >= BT_RARE_THRESH) || ((it % BT_RARE_PERIOD) == 0);
+		if (run_rare) {
+			/* work distribution: warp-aggregated grab from the global cursor, then the warp copies each new
+			 * read into the owning lane's shared-memory stage with coalesced loads */
+			const bool want = (L.pc == PC_NEXT_READ);
+			const unsigned wmask = __ballot_sync(0xffffffffu, want);
+			if (wmask) {
+				const int leader = __ffs(wmask) - 1;
+				unsigned long long base = 0;
+				if ((int)lane == leader) base = atomicAdd(&ctl->next, (unsigned long long)__popc(wmask));
+				base = __shfl_sync(0xffffffffu, base, leader);
+				bool got = false;
+				if (want) {
+					unsigned long long w = base + (unsigned long long)__popc(wmask & ((1u << lane) - 1u));
+					if (w < nwork) {
+						uint32_t rid = P.sel ? P.sel[w] : (uint32_t)w;
+						bt_begin_read(L, P, rid);
+						got = true;
+					} else L.pc = PC_EXIT;
+				}
+				unsigned gmask = __ballot_sync(0xffffffffu, got && L.rlen <= BT_SMEM_LEN);
+				while (gmask) {
+					const int j = __ffs(gmask) - 1;
+					gmask &= gmask - 1;
+					const uint32_t rl = __shfl_sync(0xffffffffu, L.rlen, j);
+					const unsigned long long ro = __shfl_sync(0xffffffffu, (unsigned long long)L.roff, j);
+					uint8_t *dst = bt_smem + (size_t)((threadIdx.x & ~31u) + j) * BT_SMEM_STRIDE;
+					bool sawN = false;
+#pragma unroll
+					for (uint32_t k = 0; k < BT_SMEM_LEN; k += 32) {
+						const uint32_t idx = k + lane;
+						if (idx < rl) {
+							const uint8_t b = __ldg(P.seq + ro + idx);
+							dst[idx] = b;
+							dst[BT_SMEM_LEN + idx] = __ldg(P.qual + ro + idx);
+							sawN |= (b == 4);
+						}
+					}
+					const unsigned nm = __ballot_sync(0xffffffffu, sawN);
+					if ((int)lane == j) { L.rseq = my_stage; L.rqual = my_stage + BT_SMEM_LEN; L.hasN = (nm != 0); }
+				}
+				__syncwarp();
 			}
+			if (L.pc == PC_FINISH_READ) { bt_finish_read(L, P); L.pc = PC_NEXT_READ; }
 		}
-		if (__all_sync(0xffffffffu, L.pc == PC_EXIT)) break;
-		if (L.pc == PC_FINISH_READ) { bt_finish_read(L, P); L.pc = PC_NEXT_READ; }
-		else if (L.pc != PC_EXIT && L.pc != PC_NEXT_READ) bt_iter(L, P, S);
+		if (fast || (run_rare && L.pc != PC_EXIT && L.pc != PC_NEXT_READ && L.pc != PC_FINISH_READ)) bt_iter(L, P, S);
 	}
 	/* statistics: warp-reduce, one atomic per warp and counter */
 	unsigned long long v[8] = { L.s_lfex, L.s_lf, L.s_chase, L.s_ftab, L.s_offs, L.s_bt, L.s_iter, L.s_blk };
@@ -291,7 +343,7 @@ extern "C" int bt_index_load(const char *basename, int need_mirror, int device, 
 		else {
 			ix->sms = prop.multiProcessorCount;
 			int bps = 0;
-			if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bps, bt_search_kernel, BT_THREADS, 0) != cudaSuccess || bps < 1) bps = 1;
+			if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bps, bt_search_kernel, BT_THREADS, BT_THREADS * BT_SMEM_STRIDE) != cudaSuccess || bps < 1) bps = 1;
 			ix->blocks_per_sm = bps;
 		}
 	}
@@ -368,14 +420,14 @@ static int enqueue_align(bt_index_t *ix, const bt_policy_t *pol, const bt_read_b
 	uint32_t grid = (uint32_t)ix->sms * (uint32_t)ix->blocks_per_sm;
 	uint32_t need = (nwork + BT_THREADS - 1) / BT_THREADS;
 	if (grid > need) grid = need;
-	bt_search_kernel<<<grid, BT_THREADS, 0, st>>>(P, ix->ctl);
+	bt_search_kernel<<<grid, BT_THREADS, BT_THREADS * BT_SMEM_STRIDE, st>>>(P, ix->ctl);
 	/* retry pass for reads whose scratch overflowed (sized on the device) */
 	bt_ctl_set_kernel<<<1, 1, 0, st>>>(ix->ctl + 1, 0);
 	bt_collect_kernel<<<(nwork + 255) / 256, 256, 0, st>>>(out->flags, in->sel, nwork, BT_FLAG_STACK_OVF | BT_FLAG_FRAME_OVF | BT_FLAG_PART_OVF, ix->retry_sel, ix->ctl + 1);
 	P.sel = ix->retry_sel;
 	P.rows = ix->ws2.rows; P.elims = ix->ws2.elims; P.frames = ix->ws2.frames; P.partials = ix->ws2.partials;
 	P.R = ix->ws2.R; P.FCAP = ix->ws2.FCAP; P.PCAP = ix->ws2.PCAP;
-	bt_search_kernel<<<ix->sms, 32, 0, st>>>(P, ix->ctl + 1);
+	bt_search_kernel<<<ix->sms, 32, 32 * BT_SMEM_STRIDE, st>>>(P, ix->ctl + 1);
 	CUDA_TRY(cudaGetLastError());
 	return 0;
 }
