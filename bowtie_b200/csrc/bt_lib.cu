@@ -87,17 +87,18 @@ bt_search_kernel(BtKParams P, BtWorkCtl *ctl) {
 	L.pc = PC_NEXT_READ;
 	L.s_lfex = L.s_lf = L.s_chase = L.s_ftab = L.s_offs = L.s_bt = L.s_iter = L.s_blk = 0;
 	L.nmuts = 0; L.mut0 = L.mut1 = L.mut2 = 0; L.ebwtSel = 0; L.lfk = 0; L.ltop = L.lbot = L.crow = 0; L.flags = 0; L.d = 0; L.qlen = 0;
-	L.rlen = 0; L.roff = 0; L.rseq = P.seq; L.rqual = P.qual; L.hasN = 1;
+	L.rlen = 0; L.rseq = my_stage; L.rqual = my_stage + BT_SMEM_LEN; L.hasN = 1; L.step = 0;
 	const unsigned long long nwork = ctl->nwork;
 	uint32_t it = 0;
 	for (;; it++) {
-		const bool fast = (L.pc == PC_LF || L.pc == PC_POS2 || L.pc == PC_CHASE);
+		const bool fast = BT_IS_FAST(L.pc);
 		const bool rare = !fast && L.pc != PC_EXIT;
 		const unsigned fmask = __ballot_sync(0xffffffffu, fast);
 		const unsigned rmask = __ballot_sync(0xffffffffu, rare);
 		if ((fmask | rmask) == 0) break;                                  /* every lane has exited */
 		const bool run_rare = (fmask == 0) || (__popc(rmask) >= BT_RARE_THRESH) || ((it % BT_RARE_PERIOD) == 0);
 		if (run_rare) {
+			if (L.pc == PC_FINISH_READ) { bt_finish_read(L, P); L.pc = PC_NEXT_READ; }
 			/* work distribution: warp-aggregated grab from the global cursor, then the warp copies each new
 			 * read into the owning lane's shared-memory stage with coalesced loads */
 			const bool want = (L.pc == PC_NEXT_READ);
@@ -108,11 +109,13 @@ bt_search_kernel(BtKParams P, BtWorkCtl *ctl) {
 				if ((int)lane == leader) base = atomicAdd(&ctl->next, (unsigned long long)__popc(wmask));
 				base = __shfl_sync(0xffffffffu, base, leader);
 				bool got = false;
+				unsigned long long ro = 0;
 				if (want) {
 					unsigned long long w = base + (unsigned long long)__popc(wmask & ((1u << lane) - 1u));
 					if (w < nwork) {
-						uint32_t rid = P.sel ? P.sel[w] : (uint32_t)w;
+						const uint32_t rid = P.sel ? P.sel[w] : (uint32_t)w;
 						bt_begin_read(L, P, rid);
+						ro = P.roff[rid];
 						got = true;
 					} else L.pc = PC_EXIT;
 				}
@@ -121,27 +124,37 @@ bt_search_kernel(BtKParams P, BtWorkCtl *ctl) {
 					const int j = __ffs(gmask) - 1;
 					gmask &= gmask - 1;
 					const uint32_t rl = __shfl_sync(0xffffffffu, L.rlen, j);
-					const unsigned long long ro = __shfl_sync(0xffffffffu, (unsigned long long)L.roff, j);
+					const unsigned long long rj = __shfl_sync(0xffffffffu, ro, j);
 					uint8_t *dst = bt_smem + (size_t)((threadIdx.x & ~31u) + j) * BT_SMEM_STRIDE;
 					bool sawN = false;
-#pragma unroll
-					for (uint32_t k = 0; k < BT_SMEM_LEN; k += 32) {
+					for (uint32_t k = 0; k < rl; k += 32) {
 						const uint32_t idx = k + lane;
 						if (idx < rl) {
-							const uint8_t b = __ldg(P.seq + ro + idx);
+							const uint8_t b = __ldg(P.seq + rj + idx);
 							dst[idx] = b;
-							dst[BT_SMEM_LEN + idx] = __ldg(P.qual + ro + idx);
+							dst[BT_SMEM_LEN + idx] = __ldg(P.qual + rj + idx);
 							sawN |= (b == 4);
 						}
 					}
 					const unsigned nm = __ballot_sync(0xffffffffu, sawN);
 					if ((int)lane == j) { L.rseq = my_stage; L.rqual = my_stage + BT_SMEM_LEN; L.hasN = (nm != 0); }
 				}
+				if (got && L.rlen > BT_SMEM_LEN) {
+					/* long read: private copy in global scratch */
+					uint8_t *dst = P.stage + (size_t)tid * 2 * P.stage_len;
+					bool sawN = false;
+					for (uint32_t k = 0; k < L.rlen; k++) {
+						const uint8_t b = __ldg(P.seq + ro + k);
+						dst[k] = b; dst[P.stage_len + k] = __ldg(P.qual + ro + k);
+						sawN |= (b == 4);
+					}
+					L.rseq = dst; L.rqual = dst + P.stage_len; L.hasN = sawN;
+				}
 				__syncwarp();
 			}
-			if (L.pc == PC_FINISH_READ) { bt_finish_read(L, P); L.pc = PC_NEXT_READ; }
+			if (BT_IS_RARE_STEP(L.pc)) bt_rare_iter(L, P, S);
 		}
-		if (fast || (run_rare && L.pc != PC_EXIT && L.pc != PC_NEXT_READ && L.pc != PC_FINISH_READ)) bt_iter(L, P, S);
+		if (fast) bt_fast_iter(L, P, S);
 	}
 	/* statistics: warp-reduce, one atomic per warp and counter */
 	unsigned long long v[8] = { L.s_lfex, L.s_lf, L.s_chase, L.s_ftab, L.s_offs, L.s_bt, L.s_iter, L.s_blk };
@@ -190,8 +203,9 @@ struct DevEbwt {
 
 struct Workspace {
 	uint32_t nthreads = 0, R = 0, FCAP = 0, PCAP = 0;
-	uint4 *rows = nullptr; uint8_t *elims = nullptr; BtFrame *frames = nullptr; uint64_t *partials = nullptr;
-	void release() { cudaFree(rows); cudaFree(elims); cudaFree(frames); cudaFree(partials); rows = nullptr; elims = nullptr; frames = nullptr; partials = nullptr; nthreads = 0; }
+	uint32_t stage_len = 0;
+	uint4 *rows = nullptr; uint8_t *elims = nullptr; BtFrame *frames = nullptr; uint64_t *partials = nullptr; uint8_t *stage = nullptr;
+	void release() { cudaFree(rows); cudaFree(elims); cudaFree(frames); cudaFree(partials); cudaFree(stage); rows = nullptr; elims = nullptr; frames = nullptr; partials = nullptr; stage = nullptr; nthreads = 0; }
 };
 
 struct bt_index {
@@ -370,14 +384,15 @@ extern "C" uint32_t bt_index_reflen(const bt_index_t *ix, uint32_t i) {
 	return ix->host[0].plen[i];
 }
 
-static int ensure_ws(Workspace &w, uint32_t nthreads, uint32_t R, uint32_t FCAP, uint32_t PCAP) {
-	if (w.nthreads >= nthreads && w.R >= R && w.FCAP >= FCAP && w.PCAP >= PCAP) return 0;
+static int ensure_ws(Workspace &w, uint32_t nthreads, uint32_t R, uint32_t FCAP, uint32_t PCAP, uint32_t stage_len) {
+	if (w.nthreads >= nthreads && w.R >= R && w.FCAP >= FCAP && w.PCAP >= PCAP && w.stage_len >= stage_len) return 0;
 	w.release();
 	CUDA_TRY(cudaMalloc((void **)&w.rows, (size_t)nthreads * R * 32));
 	CUDA_TRY(cudaMalloc((void **)&w.elims, (size_t)nthreads * R));
 	CUDA_TRY(cudaMalloc((void **)&w.frames, (size_t)nthreads * FCAP * sizeof(BtFrame)));
 	CUDA_TRY(cudaMalloc((void **)&w.partials, (size_t)nthreads * PCAP * 8));
-	w.nthreads = nthreads; w.R = R; w.FCAP = FCAP; w.PCAP = PCAP;
+	CUDA_TRY(cudaMalloc((void **)&w.stage, (size_t)nthreads * 2 * (stage_len ? stage_len : 1)));
+	w.nthreads = nthreads; w.R = R; w.FCAP = FCAP; w.PCAP = PCAP; w.stage_len = stage_len;
 	return 0;
 }
 
@@ -398,10 +413,11 @@ static int enqueue_align(bt_index_t *ix, const bt_policy_t *pol, const bt_read_b
 	if (maxlen > 1023) return fail("bt_align: reads longer than 1023 bases are not supported (the reference's Hit::mms is a FixedBitset<1024>)");
 	/* first-pass workspace: enough for the common case; rare deep searches go to the retry pass */
 	uint32_t nthreads = (uint32_t)ix->sms * (uint32_t)ix->blocks_per_sm * BT_THREADS;
-	if (ensure_ws(ix->ws1, nthreads, 6 * maxlen + 8, 8, 64)) return 1;
+	const uint32_t stage_len = maxlen > BT_SMEM_LEN ? maxlen : 0;
+	if (ensure_ws(ix->ws1, nthreads, 6 * maxlen + 8, 8, 64, stage_len)) return 1;
 	const uint32_t nthreads2 = (uint32_t)ix->sms * 32;
 	uint32_t R2 = maxlen * maxlen + 8; if (R2 > 65000) R2 = 65000;   /* BtFrame::rowbase is 16 bits */
-	if (ensure_ws(ix->ws2, nthreads2, R2, maxlen + 2, 4096)) return 1;
+	if (ensure_ws(ix->ws2, nthreads2, R2, maxlen + 2, 4096, stage_len)) return 1;
 	if (ix->retry_cap < nwork) {
 		cudaFree(ix->retry_sel); ix->retry_sel = nullptr; ix->retry_cap = 0;
 		CUDA_TRY(cudaMalloc((void **)&ix->retry_sel, (size_t)nwork * 4));
@@ -410,12 +426,13 @@ static int enqueue_align(bt_index_t *ix, const bt_policy_t *pol, const bt_read_b
 	BtKParams P; memset(&P, 0, sizeof P);
 	P.ix[0] = ix->dev[0].dev; P.ix[1] = ix->dev[1].dev;
 	memcpy(&P.pol, pol, sizeof(BtPolicy));
+	bt_build_prog(pol->mode, pol->mms, pol->nofw, pol->norc, P.prog);
 	P.seq = in->seq; P.qual = in->qual; P.roff = in->offs; P.seeds = in->seeds; P.sel = in->sel; P.nwork = nwork;
 	P.found = out->found; P.flags = out->flags; P.hits = out->hits; P.slots = out->slots; P.mm_cap = out->mm_cap; P.rec_words = BT_HIT_HDR + out->mm_cap;
 	P.stats = ix->stats;
 	/* pass 1 */
 	P.rows = ix->ws1.rows; P.elims = ix->ws1.elims; P.frames = ix->ws1.frames; P.partials = ix->ws1.partials;
-	P.R = ix->ws1.R; P.FCAP = ix->ws1.FCAP; P.PCAP = ix->ws1.PCAP;
+	P.R = ix->ws1.R; P.FCAP = ix->ws1.FCAP; P.PCAP = ix->ws1.PCAP; P.stage = ix->ws1.stage; P.stage_len = ix->ws1.stage_len;
 	bt_ctl_set_kernel<<<1, 1, 0, st>>>(ix->ctl, nwork);
 	uint32_t grid = (uint32_t)ix->sms * (uint32_t)ix->blocks_per_sm;
 	uint32_t need = (nwork + BT_THREADS - 1) / BT_THREADS;
@@ -426,7 +443,7 @@ static int enqueue_align(bt_index_t *ix, const bt_policy_t *pol, const bt_read_b
 	bt_collect_kernel<<<(nwork + 255) / 256, 256, 0, st>>>(out->flags, in->sel, nwork, BT_FLAG_STACK_OVF | BT_FLAG_FRAME_OVF | BT_FLAG_PART_OVF, ix->retry_sel, ix->ctl + 1);
 	P.sel = ix->retry_sel;
 	P.rows = ix->ws2.rows; P.elims = ix->ws2.elims; P.frames = ix->ws2.frames; P.partials = ix->ws2.partials;
-	P.R = ix->ws2.R; P.FCAP = ix->ws2.FCAP; P.PCAP = ix->ws2.PCAP;
+	P.R = ix->ws2.R; P.FCAP = ix->ws2.FCAP; P.PCAP = ix->ws2.PCAP; P.stage = ix->ws2.stage; P.stage_len = ix->ws2.stage_len;
 	bt_search_kernel<<<ix->sms, 32, 32 * BT_SMEM_STRIDE, st>>>(P, ix->ctl + 1);
 	CUDA_TRY(cudaGetLastError());
 	return 0;

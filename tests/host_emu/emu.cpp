@@ -58,11 +58,22 @@ int emu_align(void *fwp, void *bwp, const BtPolicy *pol, uint32_t nreads, const 
 	std::vector<uint4> rows(2 * (size_t)R); std::vector<uint8_t> elims(R); std::vector<BtFrame> frames(FCAP); std::vector<uint64_t> parts(PCAP);
 	P.R = R; P.FCAP = FCAP; P.PCAP = PCAP;
 	BtScratch S = { rows.data(), elims.data(), frames.data(), parts.data() };
+	bt_build_prog(pol->mode, pol->mms, pol->nofw, pol->norc, P.prog);
 	BtLane L; memset(&L, 0, sizeof L);
+	std::vector<uint8_t> stage;
 	for (uint32_t r = 0; r < nreads; r++) {
 		bt_begin_read(L, P, r);
+		/* the lane's writable copy of the read (shared memory on the device) */
+		stage.assign(2 * (size_t)L.rlen + 2, 0);
+		memcpy(stage.data(), seq + roff[r], L.rlen);
+		memcpy(stage.data() + L.rlen, qual + roff[r], L.rlen);
+		L.rseq = stage.data(); L.rqual = stage.data() + L.rlen;
+		L.hasN = memchr(stage.data(), 4, L.rlen) != NULL;
 		unsigned long long guard = 0; uint32_t it0 = L.s_iter;
-		while (L.pc != PC_FINISH_READ) { bt_iter(L, P, S); if (++guard > (1ull << 34)) return 1; }
+		while (L.pc != PC_FINISH_READ) {
+			if (BT_IS_FAST(L.pc)) bt_fast_iter(L, P, S); else bt_rare_iter(L, P, S);
+			if (++guard > (1ull << 34)) return 1;
+		}
 		bt_finish_read(L, P);
 		if (iters_per_read) iters_per_read[r] = L.s_iter - it0;
 	}
