@@ -43,7 +43,7 @@ def pick_index() -> tuple[Path, str]:
     if env:
         return Path(env), Path(env).name
     best = None
-    for p in sorted((REF_DIR / "cache").glob("bench_*.rev.2.ebwt")):
+    for p in sorted((REF_DIR / "cache").glob("bench*.rev.2.ebwt")):
         base = Path(str(p)[: -len(".rev.2.ebwt")])
         if Path(str(base) + ".4.ebwt").exists():
             sz = Path(str(base) + ".1.ebwt").stat().st_size
@@ -181,6 +181,8 @@ def main() -> None:
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--reads-per-step", type=int, default=int(os.environ.get("BT_BENCH_READS", 2_000_000)))
+    ap.add_argument("--streams", type=int, default=int(os.environ.get("BT_BENCH_STREAMS", 4)),
+                    help="batches kept in flight (one bt_context_t + CUDA stream each), like the reference's -p worker threads")
     ap.add_argument("--cpu-sample", type=int, default=int(os.environ.get("BT_BENCH_CPU_SAMPLE", 1_000_000)))
     args = ap.parse_args()
     rank, world, local = int(os.environ.get("RANK", 0)), int(os.environ.get("WORLD_SIZE", 1)), int(os.environ.get("LOCAL_RANK", 0))
@@ -232,35 +234,49 @@ def main() -> None:
     # two distinct batches per rank, alternated, each larger than L2 (2M reads x 200 B = 400 MB)
     host = [make_reads(genome, B, seed=12345 + 1000 * rank + k) for k in range(2)]
     dev = [tuple(torch.from_numpy(np.ascontiguousarray(a)).cuda() for a in (h[0], h[1], h[2].view(np.int64), h[3].view(np.int32))) for h in host]
-    d_found = torch.zeros(B, dtype=torch.int32, device="cuda")
-    d_flags = torch.zeros(B, dtype=torch.int32, device="cuda")
-    d_hits = torch.zeros(B * slots * rw, dtype=torch.int32, device="cuda")
-    stream = torch.cuda.current_stream().cuda_stream
+    NS = max(1, min(args.streams, args.steps))
+    ctxs = [bowtie_b200.Context(ix) for _ in range(NS)]
+    streams = [torch.cuda.Stream() for _ in range(NS)]
+    d_out = [(torch.zeros(B, dtype=torch.int32, device="cuda"), torch.zeros(B, dtype=torch.int32, device="cuda"),
+              torch.zeros(B * slots * rw, dtype=torch.int32, device="cuda")) for _ in range(NS)]
+    main = torch.cuda.current_stream()
 
     def step_dev(k: int) -> None:
         s, q, o, sd = dev[k & 1]
-        ix.align_device(s.data_ptr(), q.data_ptr(), o.data_ptr(), sd.data_ptr(), B, L, pol, d_found.data_ptr(), d_flags.data_ptr(),
-                        d_hits.data_ptr(), slots, mm_cap, stream)
+        f, g, h = d_out[k % NS]
+        ctxs[k % NS].align_device(s.data_ptr(), q.data_ptr(), o.data_ptr(), sd.data_ptr(), B, L, pol, f.data_ptr(), g.data_ptr(),
+                                  h.data_ptr(), slots, mm_cap, streams[k % NS].cuda_stream)
 
     def barrier() -> None:
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
 
-    for k in range(args.warmup):
-        step_dev(k)
+    def run_steps(fn, nsteps: int):
+        """K steps round-robin over NS streams, bracketed by events on the main stream."""
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(main)
+        for st in streams:
+            st.wait_event(e0)
+        for k in range(nsteps):
+            fn(k)
+        for st in streams:
+            ev = torch.cuda.Event()
+            ev.record(st)
+            main.wait_event(ev)
+        e1.record(main)
+        return e0, e1
+
+    run_steps(step_dev, args.warmup)
     barrier()
     ix.stats(reset=True)
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     with ClockSampler(local) as clk:
         barrier()
-        e0.record()
-        for k in range(args.steps):
-            step_dev(k)
-        e1.record()
+        e0, e1 = run_steps(step_dev, args.steps)
         barrier()
     ms = e0.elapsed_time(e1)
     st = ix.stats(reset=True)
+    d_found, d_flags = d_out[(args.steps - 1) % NS][0], d_out[(args.steps - 1) % NS][1]
     flags_bad = int((d_flags != 0).sum().item())
     aligned = int((d_found > 0).sum().item())
     t = torch.tensor([ms], dtype=torch.float64, device="cuda")
@@ -276,23 +292,25 @@ def main() -> None:
     for h in host:
         ts = [torch.from_numpy(np.ascontiguousarray(a)).pin_memory() for a in (h[0], h[1], h[2].view(np.int64), h[3].view(np.int32))]
         pin.append(ts)
-    o_found = torch.zeros(B, dtype=torch.int32).pin_memory()
-    o_flags = torch.zeros(B, dtype=torch.int32).pin_memory()
-    o_hits = torch.zeros(B * slots * rw, dtype=torch.int32).pin_memory()
-    outs = (o_found.numpy().view(np.uint32), o_flags.numpy().view(np.uint32), o_hits.numpy().view(np.uint32).reshape(B, slots, rw))
+    outs = []
+    for _ in range(NS):
+        o_found = torch.zeros(B, dtype=torch.int32).pin_memory()
+        o_flags = torch.zeros(B, dtype=torch.int32).pin_memory()
+        o_hits = torch.zeros(B * slots * rw, dtype=torch.int32).pin_memory()
+        outs.append((o_found.numpy().view(np.uint32), o_flags.numpy().view(np.uint32), o_hits.numpy().view(np.uint32).reshape(B, slots, rw)))
 
     def step_e2e(k: int) -> None:
         s, q, o, sd = pin[k & 1]
-        ix.align(s.numpy(), q.numpy(), o.numpy().view(np.uint64), sd.numpy().view(np.uint32), pol, slots=slots, mm_cap=mm_cap, out=outs, stream=stream)
+        ctxs[k % NS].align_async(s.numpy(), q.numpy(), o.numpy().view(np.uint64), sd.numpy().view(np.uint32), pol, outs[k % NS],
+                                 slots, mm_cap, streams[k % NS].cuda_stream)
 
-    for k in range(max(1, args.warmup - 1)):
-        step_e2e(k)
+    run_steps(step_e2e, max(1, args.warmup - 1))
     barrier()
     t0 = time.perf_counter()
-    for k in range(args.steps):
-        step_e2e(k)
+    run_steps(step_e2e, args.steps)
     barrier()
     e2e_s = time.perf_counter() - t0
+    e2e_aligned = int((outs[(args.steps - 1) % NS][0] > 0).sum())
     t = torch.tensor([e2e_s], dtype=torch.float64, device="cuda")
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
@@ -337,13 +355,13 @@ def main() -> None:
         "warmup": args.warmup, "ms_per_step": ms_max / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "u32", "data": "synthetic",
         "config": {"workload": cfg_workload, "reads_per_step_per_gpu": B, "index_len_bp": ix.len, "index_device_bytes": ix.device_bytes,
-                   "parallelism": f"reads sharded over {world} GPU(s), full index per GPU",
+                   "parallelism": f"reads sharded over {world} GPU(s), full index per GPU; {NS} batches in flight per GPU (contexts/streams)",
                    "l2": "two alternating read batches of 400 MB each (> 126 MB L2); index smaller than L2 stays partly resident",
-                   "aligned_frac_last_step": aligned / B, "overflow_flags": flags_bad,
+                   "aligned_frac_last_step": aligned / B, "aligned_frac_last_e2e_step": e2e_aligned / B, "overflow_flags": flags_bad,
                    "counters_allreduced": [int(x) for x in ctr.tolist()]},
         "clocks": clk.summary(),
         "e2e": {"value": e2e_val, "unit": "reads/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
-        "gpu_launches": 5 * args.steps,
+        "gpu_launches": 5 * args.steps,   # ctl_set, search, ctl_set, collect, search(retry) per step
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
                      "peak_source": "MEASURED_PEAKS.json hbm_gbs" if peaks else "fallback 6650 GB/s",
                      "side_fetches_per_read": st.side_fetches / (B * args.steps), "block_loads_per_read": st.block_loads / (B * args.steps),

@@ -80,9 +80,14 @@ def load_library() -> C.CDLL:
     L.bt_index_reflen.restype = C.c_uint32
     L.bt_index_reflen.argtypes = [C.c_void_p, C.c_uint32]
     L.bt_policy_init.argtypes = [C.POINTER(_Policy)]
-    for fn in (L.bt_align_batch, L.bt_align_batch_device):
+    for fn in (L.bt_align_batch, L.bt_align_batch_device, L.bt_context_align, L.bt_context_align_async, L.bt_context_align_device):
         fn.restype = C.c_int
         fn.argtypes = [C.c_void_p, C.POINTER(_Policy), C.POINTER(_ReadBatch), C.POINTER(_HitBatch), C.c_void_p]
+    L.bt_context_create.restype = C.c_int
+    L.bt_context_create.argtypes = [C.c_void_p, C.POINTER(C.c_void_p)]
+    L.bt_context_free.argtypes = [C.c_void_p]
+    L.bt_context_sync.restype = C.c_int
+    L.bt_context_sync.argtypes = [C.c_void_p, C.c_void_p]
     L.bt_stats_get.argtypes = [C.c_void_p, C.POINTER(_Stats), C.c_int]
     L.bt_debug_lf.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_uint32, C.c_void_p]
     _LIB = L
@@ -220,6 +225,40 @@ class Index:
         out = np.zeros((len(rows), 5), np.uint32)
         self._check(self.L.bt_debug_lf(self.h, int(mirror), rows.ctypes.data, len(rows), out.ctypes.data), "bt_debug_lf")
         return out
+
+
+class Context:
+    """One in-flight batch over a shared Index (bt_context_t): scratch + staging.  Use one per CUDA stream
+    to keep several batches in flight (the reference's equivalent: one worker thread per `-p`)."""
+
+    def __init__(self, index: Index) -> None:
+        self.ix, self.L = index, index.L
+        h = C.c_void_p()
+        index._check(self.L.bt_context_create(index.h, C.byref(h)), "bt_context_create")
+        self.h = h
+
+    def close(self) -> None:
+        if getattr(self, "h", None):
+            self.L.bt_context_free(self.h)
+            self.h = None
+
+    def align_device(self, seq_ptr, qual_ptr, offs_ptr, seeds_ptr, n, max_len, pol: Policy, found_ptr, flags_ptr, hits_ptr,
+                     slots, mm_cap, stream=0) -> None:
+        rb = _ReadBatch(n, seq_ptr, qual_ptr, offs_ptr, seeds_ptr, None, 0, max_len)
+        hb = _HitBatch(found_ptr, flags_ptr, hits_ptr, slots, mm_cap)
+        cp = pol.to_c()
+        self.ix._check(self.L.bt_context_align_device(self.h, C.byref(cp), C.byref(rb), C.byref(hb), C.c_void_p(stream)), "bt_context_align_device")
+
+    def align_async(self, seq, qual, offs, seeds, pol: Policy, out, slots, mm_cap, stream=0) -> None:
+        """Pinned host arrays in/out; enqueue H2D + kernels + D2H on `stream` and return (bt_context_align_async)."""
+        found, flags, hits = out
+        rb = _ReadBatch(len(seeds), seq.ctypes.data, qual.ctypes.data, offs.ctypes.data, seeds.ctypes.data, None, 0, 0)
+        hb = _HitBatch(found.ctypes.data, flags.ctypes.data, hits.ctypes.data, slots, mm_cap)
+        cp = pol.to_c()
+        self.ix._check(self.L.bt_context_align_async(self.h, C.byref(cp), C.byref(rb), C.byref(hb), C.c_void_p(stream)), "bt_context_align_async")
+
+    def sync(self, stream=0) -> None:
+        self.ix._check(self.L.bt_context_sync(self.h, C.c_void_p(stream)), "bt_context_sync")
 
 
 def decode_hits(found: np.ndarray, hits: np.ndarray, pol: Policy):

@@ -51,13 +51,13 @@ __global__ void bt_debug_lf_kernel(BtDevIndex ix, const uint32_t *rows, uint32_t
 
 #define BT_THREADS 128
 #ifndef BT_MIN_BLOCKS
-#define BT_MIN_BLOCKS 4            /* register cap = 65536 / (128 * BT_MIN_BLOCKS) */
+#define BT_MIN_BLOCKS 3            /* register cap = 65536 / (128 * BT_MIN_BLOCKS) */
 #endif
 #ifndef BT_RARE_PERIOD
-#define BT_RARE_PERIOD 4           /* rare transitions run at least every BT_RARE_PERIOD-th iteration ... */
+#define BT_RARE_PERIOD 16          /* rare transitions run at least every BT_RARE_PERIOD-th iteration ... */
 #endif
 #ifndef BT_RARE_THRESH
-#define BT_RARE_THRESH 12          /* ... or as soon as this many lanes of the warp wait for one          */
+#define BT_RARE_THRESH 24          /* ... or as soon as this many lanes of the warp wait for one          */
 #endif
 #define BT_SMEM_LEN 128            /* reads up to this length are staged in shared memory                   */
 #define BT_SMEM_STRIDE (2 * BT_SMEM_LEN + 4)   /* +4: lanes' equal offsets fall in different banks          */
@@ -208,17 +208,26 @@ struct Workspace {
 	void release() { cudaFree(rows); cudaFree(elims); cudaFree(frames); cudaFree(partials); cudaFree(stage); rows = nullptr; elims = nullptr; frames = nullptr; partials = nullptr; stage = nullptr; nthreads = 0; }
 };
 
+struct bt_context;
 struct bt_index {
 	int device = 0;
 	bool has_mirror = false;
 	HostEbwt host[2];            /* small arrays + names kept; ebwt bytes dropped after upload */
 	DevEbwt dev[2];
+	unsigned long long *stats = nullptr;
+	int sms = 0, blocks_per_sm = 0;
+	bt_context *def = nullptr;   /* context behind bt_align_batch / bt_align_batch_device */
+	std::mutex mu;
+};
+
+/* Everything one in-flight batch needs besides the (shared, immutable) index: scratch for both passes,
+ * the work-queue words and the device staging of the host-buffer entry points.  One call at a time per
+ * context; different contexts may be in flight concurrently on different streams. */
+struct bt_context {
+	bt_index *ix = nullptr;
 	Workspace ws1, ws2;          /* first pass / retry pass scratch */
 	BtWorkCtl *ctl = nullptr;    /* [2] */
-	unsigned long long *stats = nullptr;
 	uint32_t *retry_sel = nullptr; uint32_t retry_cap = 0;
-	int sms = 0, blocks_per_sm = 0;
-	/* staging for the host-buffer entry point */
 	uint8_t *d_seq = nullptr, *d_qual = nullptr; uint64_t *d_offs = nullptr; uint32_t *d_seeds = nullptr, *d_sel = nullptr;
 	uint32_t *d_found = nullptr, *d_flags = nullptr, *d_hits = nullptr;
 	size_t cap_seq = 0, cap_qual = 0, cap_offs = 0, cap_seeds = 0, cap_found = 0, cap_flags = 0, cap_hitwords = 0, cap_sel = 0;
@@ -320,6 +329,33 @@ extern "C" void bt_policy_init(bt_policy_t *p) {
 	p->mode = 1; p->mms = 2; p->seed_len = 28; p->qual_thresh = 70; p->max_bts = 125; p->khits = 1; p->mhits = 0xffffffffu; p->maq_round = 1;
 }
 
+extern "C" void bt_context_free(bt_context_t *cx) {
+	if (!cx) return;
+	cudaSetDevice(cx->ix->device);
+	cx->ws1.release(); cx->ws2.release();
+	cudaFree(cx->ctl); cudaFree(cx->retry_sel);
+	cudaFree(cx->d_seq); cudaFree(cx->d_qual); cudaFree(cx->d_offs); cudaFree(cx->d_seeds); cudaFree(cx->d_sel);
+	cudaFree(cx->d_found); cudaFree(cx->d_flags); cudaFree(cx->d_hits);
+	delete cx;
+}
+
+extern "C" int bt_context_create(bt_index_t *ix, bt_context_t **out) {
+	if (!ix || !out) return fail("bt_context_create: null argument");
+	*out = nullptr;
+	CUDA_TRY(cudaSetDevice(ix->device));
+	bt_context *cx = new bt_context();
+	cx->ix = ix;
+	if (cudaMalloc((void **)&cx->ctl, 2 * sizeof(BtWorkCtl)) != cudaSuccess) { delete cx; return fail("bt_context_create: cudaMalloc failed"); }
+	*out = cx;
+	return 0;
+}
+
+static bt_context *default_ctx(bt_index_t *ix) {
+	std::lock_guard<std::mutex> g(ix->mu);
+	if (!ix->def) { bt_context *cx = nullptr; if (bt_context_create(ix, &cx)) return nullptr; ix->def = cx; }
+	return ix->def;
+}
+
 extern "C" void bt_index_free(bt_index_t *ix) {
 	if (!ix) return;
 	cudaSetDevice(ix->device);
@@ -327,10 +363,8 @@ extern "C" void bt_index_free(bt_index_t *ix) {
 		DevEbwt &d = ix->dev[k];
 		cudaFree(d.blocks); cudaFree(d.offs); cudaFree(d.ftab); cudaFree(d.eftab); cudaFree(d.rstarts); cudaFree(d.plen);
 	}
-	ix->ws1.release(); ix->ws2.release();
-	cudaFree(ix->ctl); cudaFree(ix->stats); cudaFree(ix->retry_sel);
-	cudaFree(ix->d_seq); cudaFree(ix->d_qual); cudaFree(ix->d_offs); cudaFree(ix->d_seeds); cudaFree(ix->d_sel);
-	cudaFree(ix->d_found); cudaFree(ix->d_flags); cudaFree(ix->d_hits);
+	if (ix->def) bt_context_free(ix->def);
+	cudaFree(ix->stats);
 	delete ix;
 }
 
@@ -361,8 +395,7 @@ extern "C" int bt_index_load(const char *basename, int need_mirror, int device, 
 			ix->blocks_per_sm = bps;
 		}
 	}
-	if (!rc && (cudaMalloc((void **)&ix->ctl, 2 * sizeof(BtWorkCtl)) != cudaSuccess ||
-	            cudaMalloc((void **)&ix->stats, 8 * sizeof(unsigned long long)) != cudaSuccess ||
+	if (!rc && (cudaMalloc((void **)&ix->stats, 8 * sizeof(unsigned long long)) != cudaSuccess ||
 	            cudaMemset(ix->stats, 0, 8 * sizeof(unsigned long long)) != cudaSuccess)) rc = fail("cudaMalloc failed");
 	if (rc) { std::string keep = g_err; bt_index_free(ix); g_err = keep; return rc; }
 	*out = ix;
@@ -406,7 +439,8 @@ static int check_policy(const bt_index_t *ix, const bt_policy_t *pol) {
 }
 
 /* Enqueue first pass + collect + retry pass.  All pointers are device pointers. `maxlen` bounds the read length. */
-static int enqueue_align(bt_index_t *ix, const bt_policy_t *pol, const bt_read_batch_t *in, bt_hit_batch_t *out, uint32_t maxlen, cudaStream_t st) {
+static int enqueue_align(bt_context *cx, const bt_policy_t *pol, const bt_read_batch_t *in, bt_hit_batch_t *out, uint32_t maxlen, cudaStream_t st) {
+	bt_index_t *ix = cx->ix;
 	const uint32_t nwork = in->sel ? in->nsel : in->nreads;
 	if (nwork == 0) return 0;
 	if (maxlen < 1) maxlen = 1;
@@ -414,14 +448,14 @@ static int enqueue_align(bt_index_t *ix, const bt_policy_t *pol, const bt_read_b
 	/* first-pass workspace: enough for the common case; rare deep searches go to the retry pass */
 	uint32_t nthreads = (uint32_t)ix->sms * (uint32_t)ix->blocks_per_sm * BT_THREADS;
 	const uint32_t stage_len = maxlen > BT_SMEM_LEN ? maxlen : 0;
-	if (ensure_ws(ix->ws1, nthreads, 6 * maxlen + 8, 8, 64, stage_len)) return 1;
+	if (ensure_ws(cx->ws1, nthreads, 6 * maxlen + 8, 8, 64, stage_len)) return 1;
 	const uint32_t nthreads2 = (uint32_t)ix->sms * 32;
 	uint32_t R2 = maxlen * maxlen + 8; if (R2 > 65000) R2 = 65000;   /* BtFrame::rowbase is 16 bits */
-	if (ensure_ws(ix->ws2, nthreads2, R2, maxlen + 2, 4096, stage_len)) return 1;
-	if (ix->retry_cap < nwork) {
-		cudaFree(ix->retry_sel); ix->retry_sel = nullptr; ix->retry_cap = 0;
-		CUDA_TRY(cudaMalloc((void **)&ix->retry_sel, (size_t)nwork * 4));
-		ix->retry_cap = nwork;
+	if (ensure_ws(cx->ws2, nthreads2, R2, maxlen + 2, 4096, stage_len)) return 1;
+	if (cx->retry_cap < nwork) {
+		cudaFree(cx->retry_sel); cx->retry_sel = nullptr; cx->retry_cap = 0;
+		CUDA_TRY(cudaMalloc((void **)&cx->retry_sel, (size_t)nwork * 4));
+		cx->retry_cap = nwork;
 	}
 	BtKParams P; memset(&P, 0, sizeof P);
 	P.ix[0] = ix->dev[0].dev; P.ix[1] = ix->dev[1].dev;
@@ -431,31 +465,38 @@ static int enqueue_align(bt_index_t *ix, const bt_policy_t *pol, const bt_read_b
 	P.found = out->found; P.flags = out->flags; P.hits = out->hits; P.slots = out->slots; P.mm_cap = out->mm_cap; P.rec_words = BT_HIT_HDR + out->mm_cap;
 	P.stats = ix->stats;
 	/* pass 1 */
-	P.rows = ix->ws1.rows; P.elims = ix->ws1.elims; P.frames = ix->ws1.frames; P.partials = ix->ws1.partials;
-	P.R = ix->ws1.R; P.FCAP = ix->ws1.FCAP; P.PCAP = ix->ws1.PCAP; P.stage = ix->ws1.stage; P.stage_len = ix->ws1.stage_len;
-	bt_ctl_set_kernel<<<1, 1, 0, st>>>(ix->ctl, nwork);
+	P.rows = cx->ws1.rows; P.elims = cx->ws1.elims; P.frames = cx->ws1.frames; P.partials = cx->ws1.partials;
+	P.R = cx->ws1.R; P.FCAP = cx->ws1.FCAP; P.PCAP = cx->ws1.PCAP; P.stage = cx->ws1.stage; P.stage_len = cx->ws1.stage_len;
+	bt_ctl_set_kernel<<<1, 1, 0, st>>>(cx->ctl, nwork);
 	uint32_t grid = (uint32_t)ix->sms * (uint32_t)ix->blocks_per_sm;
 	uint32_t need = (nwork + BT_THREADS - 1) / BT_THREADS;
 	if (grid > need) grid = need;
-	bt_search_kernel<<<grid, BT_THREADS, BT_THREADS * BT_SMEM_STRIDE, st>>>(P, ix->ctl);
+	bt_search_kernel<<<grid, BT_THREADS, BT_THREADS * BT_SMEM_STRIDE, st>>>(P, cx->ctl);
 	/* retry pass for reads whose scratch overflowed (sized on the device) */
-	bt_ctl_set_kernel<<<1, 1, 0, st>>>(ix->ctl + 1, 0);
-	bt_collect_kernel<<<(nwork + 255) / 256, 256, 0, st>>>(out->flags, in->sel, nwork, BT_FLAG_STACK_OVF | BT_FLAG_FRAME_OVF | BT_FLAG_PART_OVF, ix->retry_sel, ix->ctl + 1);
-	P.sel = ix->retry_sel;
-	P.rows = ix->ws2.rows; P.elims = ix->ws2.elims; P.frames = ix->ws2.frames; P.partials = ix->ws2.partials;
-	P.R = ix->ws2.R; P.FCAP = ix->ws2.FCAP; P.PCAP = ix->ws2.PCAP; P.stage = ix->ws2.stage; P.stage_len = ix->ws2.stage_len;
-	bt_search_kernel<<<ix->sms, 32, 32 * BT_SMEM_STRIDE, st>>>(P, ix->ctl + 1);
+	bt_ctl_set_kernel<<<1, 1, 0, st>>>(cx->ctl + 1, 0);
+	bt_collect_kernel<<<(nwork + 255) / 256, 256, 0, st>>>(out->flags, in->sel, nwork, BT_FLAG_STACK_OVF | BT_FLAG_FRAME_OVF | BT_FLAG_PART_OVF, cx->retry_sel, cx->ctl + 1);
+	P.sel = cx->retry_sel;
+	P.rows = cx->ws2.rows; P.elims = cx->ws2.elims; P.frames = cx->ws2.frames; P.partials = cx->ws2.partials;
+	P.R = cx->ws2.R; P.FCAP = cx->ws2.FCAP; P.PCAP = cx->ws2.PCAP; P.stage = cx->ws2.stage; P.stage_len = cx->ws2.stage_len;
+	bt_search_kernel<<<ix->sms, 32, 32 * BT_SMEM_STRIDE, st>>>(P, cx->ctl + 1);
 	CUDA_TRY(cudaGetLastError());
 	return 0;
 }
 
+extern "C" int bt_context_align_device(bt_context_t *cx, const bt_policy_t *pol, const bt_read_batch_t *in, bt_hit_batch_t *out, void *stream) {
+	if (!cx || !pol || !in || !out) return fail("bt_context_align_device: null argument");
+	if (check_policy(cx->ix, pol)) return 1;
+	if (in->max_len == 0) return fail("bt_context_align_device: max_len must be set (the offsets live on the device)");
+	std::lock_guard<std::mutex> g(cx->mu);
+	CUDA_TRY(cudaSetDevice(cx->ix->device));
+	return enqueue_align(cx, pol, in, out, in->max_len, (cudaStream_t)stream);
+}
+
 extern "C" int bt_align_batch_device(bt_index_t *ix, const bt_policy_t *pol, const bt_read_batch_t *in, bt_hit_batch_t *out, void *stream) {
-	if (!ix || !pol || !in || !out) return fail("bt_align_batch_device: null argument");
-	if (check_policy(ix, pol)) return 1;
-	std::lock_guard<std::mutex> g(ix->mu);
-	CUDA_TRY(cudaSetDevice(ix->device));
-	if (in->max_len == 0) return fail("bt_align_batch_device: max_len must be set (the offsets live on the device)");
-	return enqueue_align(ix, pol, in, out, in->max_len, (cudaStream_t)stream);
+	if (!ix) return fail("bt_align_batch_device: null argument");
+	bt_context *cx = default_ctx(ix);
+	if (!cx) return 1;
+	return bt_context_align_device(cx, pol, in, out, stream);
 }
 
 template <typename T> static int grow(T **p, size_t &cap, size_t need) {
@@ -467,8 +508,9 @@ template <typename T> static int grow(T **p, size_t &cap, size_t need) {
 	return 0;
 }
 
-extern "C" int bt_align_batch(bt_index_t *ix, const bt_policy_t *pol, const bt_read_batch_t *in, bt_hit_batch_t *out, void *stream) {
-	if (!ix || !pol || !in || !out) return fail("bt_align_batch: null argument");
+static int align_host(bt_context *cx, const bt_policy_t *pol, const bt_read_batch_t *in, bt_hit_batch_t *out, void *stream, bool sync) {
+	if (!cx || !pol || !in || !out) return fail("bt_align_batch: null argument");
+	bt_index_t *ix = cx->ix;
 	if (check_policy(ix, pol)) return 1;
 	if (in->nreads == 0) return 0;
 	if (!in->seq || !in->qual || !in->offs || !in->seeds || !out->found || !out->flags || !out->hits) return fail("bt_align_batch: null buffer");
@@ -476,45 +518,66 @@ extern "C" int bt_align_batch(bt_index_t *ix, const bt_policy_t *pol, const bt_r
 	cudaStream_t st = (cudaStream_t)stream;
 	uint32_t maxlen = 0;
 	{
-		std::lock_guard<std::mutex> g(ix->mu);
+		std::lock_guard<std::mutex> g(cx->mu);
 		CUDA_TRY(cudaSetDevice(ix->device));
 		const uint32_t n = in->nreads;
 		const size_t nb = (size_t)in->offs[n];
 		for (uint32_t i = 0; i < n; i++) { uint64_t l = in->offs[i + 1] - in->offs[i]; if (l > maxlen) maxlen = (uint32_t)l; }
 		const size_t rec_words = BT_HIT_HDR + out->mm_cap;
 		const size_t hitwords = (size_t)n * out->slots * rec_words;
-		if (grow(&ix->d_seq, ix->cap_seq, nb + 1) || grow(&ix->d_qual, ix->cap_qual, nb + 1)) return 1;
-		if (grow(&ix->d_offs, ix->cap_offs, (size_t)n + 1) || grow(&ix->d_seeds, ix->cap_seeds, n) ||
-		    grow(&ix->d_found, ix->cap_found, n) || grow(&ix->d_flags, ix->cap_flags, n)) return 1;
-		if (grow(&ix->d_hits, ix->cap_hitwords, hitwords)) return 1;
-		if (in->sel && grow(&ix->d_sel, ix->cap_sel, in->nsel)) return 1;
-		CUDA_TRY(cudaMemcpyAsync(ix->d_seq, in->seq, nb, cudaMemcpyHostToDevice, st));
-		CUDA_TRY(cudaMemcpyAsync(ix->d_qual, in->qual, nb, cudaMemcpyHostToDevice, st));
-		CUDA_TRY(cudaMemcpyAsync(ix->d_offs, in->offs, ((size_t)n + 1) * 8, cudaMemcpyHostToDevice, st));
-		CUDA_TRY(cudaMemcpyAsync(ix->d_seeds, in->seeds, (size_t)n * 4, cudaMemcpyHostToDevice, st));
-		if (in->sel) CUDA_TRY(cudaMemcpyAsync(ix->d_sel, in->sel, (size_t)in->nsel * 4, cudaMemcpyHostToDevice, st));
-		else { CUDA_TRY(cudaMemsetAsync(ix->d_found, 0, (size_t)n * 4, st)); CUDA_TRY(cudaMemsetAsync(ix->d_flags, 0, (size_t)n * 4, st)); }
+		if (grow(&cx->d_seq, cx->cap_seq, nb + 1) || grow(&cx->d_qual, cx->cap_qual, nb + 1)) return 1;
+		if (grow(&cx->d_offs, cx->cap_offs, (size_t)n + 1) || grow(&cx->d_seeds, cx->cap_seeds, n) ||
+		    grow(&cx->d_found, cx->cap_found, n) || grow(&cx->d_flags, cx->cap_flags, n)) return 1;
+		if (grow(&cx->d_hits, cx->cap_hitwords, hitwords)) return 1;
+		if (in->sel && grow(&cx->d_sel, cx->cap_sel, in->nsel)) return 1;
+		CUDA_TRY(cudaMemcpyAsync(cx->d_seq, in->seq, nb, cudaMemcpyHostToDevice, st));
+		CUDA_TRY(cudaMemcpyAsync(cx->d_qual, in->qual, nb, cudaMemcpyHostToDevice, st));
+		CUDA_TRY(cudaMemcpyAsync(cx->d_offs, in->offs, ((size_t)n + 1) * 8, cudaMemcpyHostToDevice, st));
+		CUDA_TRY(cudaMemcpyAsync(cx->d_seeds, in->seeds, (size_t)n * 4, cudaMemcpyHostToDevice, st));
+		if (in->sel) CUDA_TRY(cudaMemcpyAsync(cx->d_sel, in->sel, (size_t)in->nsel * 4, cudaMemcpyHostToDevice, st));
+		else { CUDA_TRY(cudaMemsetAsync(cx->d_found, 0, (size_t)n * 4, st)); CUDA_TRY(cudaMemsetAsync(cx->d_flags, 0, (size_t)n * 4, st)); }
 		bt_read_batch_t din = *in; bt_hit_batch_t dout = *out;
-		din.seq = ix->d_seq; din.qual = ix->d_qual; din.offs = ix->d_offs; din.seeds = ix->d_seeds; din.sel = in->sel ? ix->d_sel : nullptr;
-		dout.found = ix->d_found; dout.flags = ix->d_flags; dout.hits = ix->d_hits;
-		if (enqueue_align(ix, pol, &din, &dout, maxlen, st)) return 1;
+		din.seq = cx->d_seq; din.qual = cx->d_qual; din.offs = cx->d_offs; din.seeds = cx->d_seeds; din.sel = in->sel ? cx->d_sel : nullptr;
+		dout.found = cx->d_found; dout.flags = cx->d_flags; dout.hits = cx->d_hits;
+		if (enqueue_align(cx, pol, &din, &dout, maxlen, st)) return 1;
 		if (!in->sel) {
-			CUDA_TRY(cudaMemcpyAsync(out->found, ix->d_found, (size_t)n * 4, cudaMemcpyDeviceToHost, st));
-			CUDA_TRY(cudaMemcpyAsync(out->flags, ix->d_flags, (size_t)n * 4, cudaMemcpyDeviceToHost, st));
-			CUDA_TRY(cudaMemcpyAsync(out->hits, ix->d_hits, hitwords * 4, cudaMemcpyDeviceToHost, st));
-			CUDA_TRY(cudaStreamSynchronize(st));
+			CUDA_TRY(cudaMemcpyAsync(out->found, cx->d_found, (size_t)n * 4, cudaMemcpyDeviceToHost, st));
+			CUDA_TRY(cudaMemcpyAsync(out->flags, cx->d_flags, (size_t)n * 4, cudaMemcpyDeviceToHost, st));
+			CUDA_TRY(cudaMemcpyAsync(out->hits, cx->d_hits, hitwords * 4, cudaMemcpyDeviceToHost, st));
+			if (sync) CUDA_TRY(cudaStreamSynchronize(st));
 		} else {
 			/* selection call: only the selected reads' entries are defined; copy them back one by one */
 			CUDA_TRY(cudaStreamSynchronize(st));
 			for (uint32_t k = 0; k < in->nsel; k++) {
 				uint32_t r = in->sel[k];
-				CUDA_TRY(cudaMemcpy(out->found + r, ix->d_found + r, 4, cudaMemcpyDeviceToHost));
-				CUDA_TRY(cudaMemcpy(out->flags + r, ix->d_flags + r, 4, cudaMemcpyDeviceToHost));
-				CUDA_TRY(cudaMemcpy(out->hits + (size_t)r * out->slots * rec_words, ix->d_hits + (size_t)r * out->slots * rec_words, out->slots * rec_words * 4, cudaMemcpyDeviceToHost));
+				CUDA_TRY(cudaMemcpy(out->found + r, cx->d_found + r, 4, cudaMemcpyDeviceToHost));
+				CUDA_TRY(cudaMemcpy(out->flags + r, cx->d_flags + r, 4, cudaMemcpyDeviceToHost));
+				CUDA_TRY(cudaMemcpy(out->hits + (size_t)r * out->slots * rec_words, cx->d_hits + (size_t)r * out->slots * rec_words, out->slots * rec_words * 4, cudaMemcpyDeviceToHost));
 			}
 		}
 	}
 	return 0;
+}
+
+extern "C" int bt_context_align(bt_context_t *cx, const bt_policy_t *pol, const bt_read_batch_t *in, bt_hit_batch_t *out, void *stream) {
+	return align_host(cx, pol, in, out, stream, true);
+}
+/* Enqueue-only variant: host buffers must be pinned and stay untouched until bt_context_sync(). Not for `sel` calls. */
+extern "C" int bt_context_align_async(bt_context_t *cx, const bt_policy_t *pol, const bt_read_batch_t *in, bt_hit_batch_t *out, void *stream) {
+	if (in && in->sel) return fail("bt_context_align_async: selection calls are synchronous (use bt_context_align)");
+	return align_host(cx, pol, in, out, stream, false);
+}
+extern "C" int bt_context_sync(bt_context_t *cx, void *stream) {
+	if (!cx) return fail("bt_context_sync: null argument");
+	CUDA_TRY(cudaSetDevice(cx->ix->device));
+	CUDA_TRY(cudaStreamSynchronize((cudaStream_t)stream));
+	return 0;
+}
+extern "C" int bt_align_batch(bt_index_t *ix, const bt_policy_t *pol, const bt_read_batch_t *in, bt_hit_batch_t *out, void *stream) {
+	if (!ix) return fail("bt_align_batch: null argument");
+	bt_context *cx = default_ctx(ix);
+	if (!cx) return 1;
+	return align_host(cx, pol, in, out, stream, true);
 }
 
 extern "C" int bt_stats_get(bt_index_t *ix, bt_stats_t *out, int reset) {

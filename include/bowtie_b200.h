@@ -29,6 +29,7 @@ extern "C" {
 #define BT_ABI_VERSION 1
 
 typedef struct bt_index bt_index_t;
+typedef struct bt_context bt_context_t;
 
 /* Search policy = the option globals of ebwt_search.cpp:153-253 that reach the workers.
  * Layout is shared with the kernels (BtPolicy in bt_core.cuh). */
@@ -122,6 +123,18 @@ int  bt_align_batch(bt_index_t *ix, const bt_policy_t *pol, const bt_read_batch_
 /* Same, with every pointer of `in` and `out` already resident on the index's device; enqueues on
  * `stream` and returns without synchronising (scratch overflows are retried by a second enqueued pass). */
 int  bt_align_batch_device(bt_index_t *ix, const bt_policy_t *pol, const bt_read_batch_t *in, bt_hit_batch_t *out, void *stream);
+
+/* Contexts: everything one in-flight batch needs besides the shared immutable index (scratch, work queue,
+ * device staging).  The reference runs N worker threads over one Ebwt (ebwt_search.cpp:1385-1405); the
+ * equivalent here is N contexts on N CUDA streams over one bt_index_t.  One call at a time per context.
+ * bt_align_batch / bt_align_batch_device use an internal default context. */
+int  bt_context_create(bt_index_t *ix, bt_context_t **out);
+void bt_context_free(bt_context_t *cx);
+int  bt_context_align(bt_context_t *cx, const bt_policy_t *pol, const bt_read_batch_t *in, bt_hit_batch_t *out, void *stream);
+/* enqueue only (pinned host buffers, no `sel`); results are valid after bt_context_sync on the same stream */
+int  bt_context_align_async(bt_context_t *cx, const bt_policy_t *pol, const bt_read_batch_t *in, bt_hit_batch_t *out, void *stream);
+int  bt_context_align_device(bt_context_t *cx, const bt_policy_t *pol, const bt_read_batch_t *in, bt_hit_batch_t *out, void *stream);
+int  bt_context_sync(bt_context_t *cx, void *stream);
 
 int  bt_stats_get(bt_index_t *ix, bt_stats_t *out, int reset);    /* synchronises the device */
 

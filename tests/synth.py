@@ -11,6 +11,33 @@ from helpers import REF_BUILD, REF_DIR, ReadBatch, finalize_batch
 CACHE = REF_DIR / "cache"
 
 
+def synth_genome_survey(n_seqs: int, total_len: int, seed: int) -> list[tuple[str, bytes]]:
+    """Benchmark genome in the style of SURVEY.md §8(d) config 3: i.i.d. ACGT with GC 41 %, ~10 % of the bases covered
+    by two repeat families (300-bp and 6-kbp elements) whose copies diverge 1-15 % from the consensus, and a few N gaps."""
+    rng = np.random.default_rng(seed)
+    acgt = np.frombuffer(b"ACGT", np.uint8)
+    p = [0.295, 0.205, 0.205, 0.295]
+    fams = [rng.choice(acgt, size=300, p=p), rng.choice(acgt, size=6000, p=p)]
+    sizes = rng.dirichlet(np.ones(n_seqs) * 3) * total_len
+    out = []
+    for s in range(n_seqs):
+        L = max(20000, int(sizes[s]))
+        g = rng.choice(acgt, size=L, p=p).copy()
+        for fam, cover in ((fams[0], 0.07), (fams[1], 0.03)):
+            fl = len(fam)
+            for _ in range(max(1, int(L * cover / fl))):
+                pos = int(rng.integers(0, L - fl))
+                cp = fam.copy()
+                mut = rng.random(fl) < rng.uniform(0.01, 0.15)
+                cp[mut] = rng.choice(acgt, size=int(mut.sum()))
+                g[pos:pos + fl] = cp
+        for _ in range(3):
+            pos = int(rng.integers(1000, L - 2000))
+            g[pos:pos + int(rng.integers(10, 500))] = ord("N")
+        out.append((f"chr{s + 1} synthetic len={L}", g.tobytes()))
+    return out
+
+
 def synth_genome(n_seqs: int, total_len: int, seed: int, with_gaps: bool = False, repeats: bool = True) -> list[tuple[str, bytes]]:
     rng = np.random.default_rng(seed)
     sizes = rng.dirichlet(np.ones(n_seqs) * 3) * total_len
@@ -43,12 +70,12 @@ def write_fasta(path: Path, seqs: list[tuple[str, bytes]]) -> None:
 
 
 def build_synth_index(tag: str, n_seqs: int, total_len: int, seed: int, ftab_chars: int = 10, off_rate: int = 5,
-                      with_gaps: bool = False, threads: int = 8):
+                      with_gaps: bool = False, threads: int = 8, style: str = "flat"):
     """Build (once; cached under oracle/_ref/cache) an index with the reference's bowtie-build.
     Returns (basename, genome)."""
     CACHE.mkdir(parents=True, exist_ok=True)
     base = CACHE / f"{tag}_{n_seqs}_{total_len}_{seed}_{ftab_chars}_{off_rate}_{int(with_gaps)}"
-    genome = synth_genome(n_seqs, total_len, seed, with_gaps)
+    genome = synth_genome_survey(n_seqs, total_len, seed) if style == "survey" else synth_genome(n_seqs, total_len, seed, with_gaps)
     if not Path(str(base) + ".rev.2.ebwt").exists():
         fa = Path(str(base) + ".fa")
         write_fasta(fa, genome)
