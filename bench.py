@@ -260,7 +260,8 @@ def main() -> None:
             st.wait_event(e0)
         for k in range(nsteps):
             fn(k)
-        for st in streams:
+        for cx, st in zip(ctxs, streams):
+            cx.join(st.cuda_stream)            # the batch's heavy / overflow passes (and D2H) run on the context's side stream
             ev = torch.cuda.Event()
             ev.record(st)
             main.wait_event(ev)
@@ -361,7 +362,7 @@ def main() -> None:
                    "counters_allreduced": [int(x) for x in ctr.tolist()]},
         "clocks": clk.summary(),
         "e2e": {"value": e2e_val, "unit": "reads/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
-        "gpu_launches": 5 * args.steps,   # ctl_set, search, ctl_set, collect, search(retry) per step
+        "gpu_launches": 9 * args.steps,   # per step: 3 ctl_set, main search, 3 collect, heavy search, overflow search
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
                      "peak_source": "MEASURED_PEAKS.json hbm_gbs" if peaks else "fallback 6650 GB/s",
                      "side_fetches_per_read": st.side_fetches / (B * args.steps), "block_loads_per_read": st.block_loads / (B * args.steps),

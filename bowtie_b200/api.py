@@ -86,8 +86,9 @@ def load_library() -> C.CDLL:
     L.bt_context_create.restype = C.c_int
     L.bt_context_create.argtypes = [C.c_void_p, C.POINTER(C.c_void_p)]
     L.bt_context_free.argtypes = [C.c_void_p]
-    L.bt_context_sync.restype = C.c_int
-    L.bt_context_sync.argtypes = [C.c_void_p, C.c_void_p]
+    for fn in (L.bt_context_sync, L.bt_context_join):
+        fn.restype = C.c_int
+        fn.argtypes = [C.c_void_p, C.c_void_p]
     L.bt_stats_get.argtypes = [C.c_void_p, C.POINTER(_Stats), C.c_int]
     L.bt_debug_lf.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_uint32, C.c_void_p]
     _LIB = L
@@ -259,6 +260,10 @@ class Context:
 
     def sync(self, stream=0) -> None:
         self.ix._check(self.L.bt_context_sync(self.h, C.c_void_p(stream)), "bt_context_sync")
+
+    def join(self, stream=0) -> None:
+        """Make `stream` wait for this context's outstanding batch, including its side-stream passes."""
+        self.ix._check(self.L.bt_context_join(self.h, C.c_void_p(stream)), "bt_context_join")
 
 
 def decode_hits(found: np.ndarray, hits: np.ndarray, pol: Policy):

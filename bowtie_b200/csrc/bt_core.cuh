@@ -84,7 +84,9 @@ struct BtPolicy {
 #define BT_FLAG_PART_OVF  4u   /* more seedlings than PCAP             */
 #define BT_FLAG_HITS_OVF  8u   /* more reportable hits than slots      */
 #define BT_FLAG_MM_OVF   16u   /* more mismatches than the record holds */
+#define BT_FLAG_BUDGET  32u   /* (internal) iteration budget of the main pass exceeded: moved to the heavy pass */
 #define BT_FLAG_SCRATCH_OVF 7u
+#define BT_FLAG_RETRY (BT_FLAG_SCRATCH_OVF | BT_FLAG_BUDGET)
 
 /* hit record: BT_HIT_HDR header words followed by mm_cap mismatch words (pos | refc << 16) */
 #define BT_HIT_HDR 5
@@ -127,6 +129,7 @@ struct BtKParams {
 	uint64_t *partials;           /* PCAP                                                     */
 	uint8_t *stage;               /* 2 * stage_len bytes: writable copy of the read (long reads) */
 	uint32_t R, FCAP, PCAP, stage_len;
+	uint32_t budget;              /* per-read transition budget of this pass (0 = unlimited)  */
 	unsigned long long *stats;    /* [8]: lfex, lf, chase, ftab, offs, backtracks, iters, blockloads */
 };
 
@@ -147,7 +150,7 @@ struct BtLane {
 	uint32_t rid, rlen, seed, found, flags, hasN;
 	uint8_t *rseq, *rqual;         /* writable per-lane copy of the read (shared memory, or scratch for long reads) */
 	/* control */
-	uint32_t pc, ph, done, ret, lfk, step;
+	uint32_t pc, ph, done, ret, lfk, step, it0;
 	/* backtracker object state */
 	uint32_t ebwtSel, fw, considerQuals, halfAndHalf, reportPartials, reportExacts, maqPenalty;
 	uint32_t qualThresh, maxBts;
@@ -803,7 +806,7 @@ BT_FN void bt_begin_read(BtLane &L, const BtKParams &P, uint32_t rid) {
 	L.rid = rid;
 	L.rlen = (uint32_t)(P.roff[rid + 1] - P.roff[rid]);
 	L.seed = P.seeds[rid];
-	L.found = 0; L.flags = 0; L.ph = 0; L.done = 0; L.npart = 0; L.nmuts = 0; L.pal_i = 0; L.step = 0;
+	L.found = 0; L.flags = 0; L.ph = 0; L.done = 0; L.npart = 0; L.nmuts = 0; L.pal_i = 0; L.step = 0; L.it0 = L.s_iter;
 	L.qualThresh = P.pol.mode == 0 ? 0xffffffffu : P.pol.qualThresh;
 	L.maxBts = P.pol.mode == 0 ? 0xffffffffu : P.pol.maxBts;
 	L.maqPenalty = P.pol.mode == 0 ? 1u : (uint32_t)P.pol.maqRound;
@@ -813,7 +816,7 @@ BT_FN void bt_begin_read(BtLane &L, const BtKParams &P, uint32_t rid) {
 /* HitSinkPerThread::finishRead (hit.h:741-786): the host applies -m suppression / -k truncation
  * from `found`; the kernel stored the first min(found, n, slots) hits. */
 BT_FN void bt_finish_read(BtLane &L, const BtKParams &P) {
-	if (L.flags & BT_FLAG_SCRATCH_OVF) L.found = 0;    /* retried with a larger workspace */
+	if (L.flags & BT_FLAG_RETRY) L.found = 0;          /* re-run by a later pass */
 	P.found[L.rid] = L.found;
 	P.flags[L.rid] = L.flags;
 }
@@ -877,6 +880,7 @@ BT_FN void bt_rare_iter(BtLane &L, const BtKParams &P, const BtScratch &S) {
 #pragma unroll 1
 	for (int k = 0; k < BT_RARE_CHAIN && BT_IS_RARE_STEP(L.pc); k++) {
 		if (L.flags & BT_FLAG_SCRATCH_OVF) { L.pc = PC_FINISH_READ; break; }
+		if (P.budget && (L.s_iter - L.it0) > P.budget) { L.flags |= BT_FLAG_BUDGET; L.pc = PC_FINISH_READ; break; }   /* heavy read */
 		L.s_iter++;
 		bt_rare_step(L, P, S);
 	}

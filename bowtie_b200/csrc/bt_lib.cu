@@ -166,9 +166,11 @@ bt_search_kernel(BtKParams P, BtWorkCtl *ctl) {
 	}
 }
 
-/* Builds the list of reads whose scratch overflowed and resets the work control for the retry pass. */
-__global__ void bt_collect_kernel(const uint32_t *flags, const uint32_t *sel_in, uint32_t n, uint32_t mask, uint32_t *sel_out, BtWorkCtl *ctl) {
+/* Appends to sel_out the reads (of the first n work items of sel_in / the identity) whose flags intersect `mask`;
+ * ctl->nwork is the list length.  If `count_ctl` is set, the number of work items is read from it (device-sized lists). */
+__global__ void bt_collect_kernel(const uint32_t *flags, const uint32_t *sel_in, uint32_t n, const BtWorkCtl *count_ctl, uint32_t mask, uint32_t *sel_out, BtWorkCtl *ctl) {
 	uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+	if (count_ctl) n = (uint32_t)count_ctl->nwork;
 	if (i >= n) return;
 	uint32_t rid = sel_in ? sel_in[i] : i;
 	if (flags[rid] & mask) {
@@ -225,9 +227,11 @@ struct bt_index {
  * context; different contexts may be in flight concurrently on different streams. */
 struct bt_context {
 	bt_index *ix = nullptr;
-	Workspace ws1, ws2;          /* first pass / retry pass scratch */
-	BtWorkCtl *ctl = nullptr;    /* [2] */
-	uint32_t *retry_sel = nullptr; uint32_t retry_cap = 0;
+	Workspace ws1, wsh, ws2;     /* main pass / heavy-read pass / scratch-overflow pass */
+	BtWorkCtl *ctl = nullptr;    /* [3] */
+	uint32_t *heavy_sel = nullptr, *retry_sel = nullptr; uint32_t retry_cap = 0;
+	cudaStream_t side = nullptr; /* the heavy and overflow passes run here, overlapping the next batch's main pass */
+	cudaEvent_t ev_main = nullptr, ev_tail = nullptr;
 	uint8_t *d_seq = nullptr, *d_qual = nullptr; uint64_t *d_offs = nullptr; uint32_t *d_seeds = nullptr, *d_sel = nullptr;
 	uint32_t *d_found = nullptr, *d_flags = nullptr, *d_hits = nullptr;
 	size_t cap_seq = 0, cap_qual = 0, cap_offs = 0, cap_seeds = 0, cap_found = 0, cap_flags = 0, cap_hitwords = 0, cap_sel = 0;
@@ -332,8 +336,11 @@ extern "C" void bt_policy_init(bt_policy_t *p) {
 extern "C" void bt_context_free(bt_context_t *cx) {
 	if (!cx) return;
 	cudaSetDevice(cx->ix->device);
-	cx->ws1.release(); cx->ws2.release();
-	cudaFree(cx->ctl); cudaFree(cx->retry_sel);
+	if (cx->side) { cudaStreamSynchronize(cx->side); cudaStreamDestroy(cx->side); }
+	if (cx->ev_main) cudaEventDestroy(cx->ev_main);
+	if (cx->ev_tail) cudaEventDestroy(cx->ev_tail);
+	cx->ws1.release(); cx->wsh.release(); cx->ws2.release();
+	cudaFree(cx->ctl); cudaFree(cx->retry_sel); cudaFree(cx->heavy_sel);
 	cudaFree(cx->d_seq); cudaFree(cx->d_qual); cudaFree(cx->d_offs); cudaFree(cx->d_seeds); cudaFree(cx->d_sel);
 	cudaFree(cx->d_found); cudaFree(cx->d_flags); cudaFree(cx->d_hits);
 	delete cx;
@@ -345,7 +352,10 @@ extern "C" int bt_context_create(bt_index_t *ix, bt_context_t **out) {
 	CUDA_TRY(cudaSetDevice(ix->device));
 	bt_context *cx = new bt_context();
 	cx->ix = ix;
-	if (cudaMalloc((void **)&cx->ctl, 2 * sizeof(BtWorkCtl)) != cudaSuccess) { delete cx; return fail("bt_context_create: cudaMalloc failed"); }
+	if (cudaMalloc((void **)&cx->ctl, 3 * sizeof(BtWorkCtl)) != cudaSuccess || cudaStreamCreateWithFlags(&cx->side, cudaStreamNonBlocking) != cudaSuccess ||
+	    cudaEventCreateWithFlags(&cx->ev_main, cudaEventDisableTiming) != cudaSuccess || cudaEventCreateWithFlags(&cx->ev_tail, cudaEventDisableTiming) != cudaSuccess) {
+		bt_context_free(cx); return fail("bt_context_create: CUDA resource allocation failed");
+	}
 	*out = cx;
 	return 0;
 }
@@ -439,22 +449,40 @@ static int check_policy(const bt_index_t *ix, const bt_policy_t *pol) {
 }
 
 /* Enqueue first pass + collect + retry pass.  All pointers are device pointers. `maxlen` bounds the read length. */
+#ifndef BT_MAIN_BUDGET
+#define BT_MAIN_BUDGET 24000u      /* transitions a read may take in the main pass before it is moved to the heavy pass */
+#endif
+#define BT_HEAVY_BLOCKS_PER_SM 8   /* heavy pass: 32-thread blocks, so finished warps free their slots */
+
+static void set_ws(BtKParams &P, const Workspace &w) {
+	P.rows = w.rows; P.elims = w.elims; P.frames = w.frames; P.partials = w.partials;
+	P.R = w.R; P.FCAP = w.FCAP; P.PCAP = w.PCAP; P.stage = w.stage; P.stage_len = w.stage_len;
+}
+
+/* Enqueues one batch.  All pointers are device pointers; `maxlen` bounds the read length.
+ *   main pass      on `st`:        every read, with a per-read transition budget and first-tier scratch
+ *   heavy pass     on cx->side:    the few reads that exhausted the budget (long sequential searches), no budget
+ *   overflow pass  on cx->side:    reads whose scratch overflowed in either pass, with worst-case scratch
+ * The side stream lets the long tail of batch k overlap the main pass of batch k+1 (another context); the
+ * batch is complete when cx->ev_tail has fired (bt_context_join / bt_context_sync). */
 static int enqueue_align(bt_context *cx, const bt_policy_t *pol, const bt_read_batch_t *in, bt_hit_batch_t *out, uint32_t maxlen, cudaStream_t st) {
 	bt_index_t *ix = cx->ix;
 	const uint32_t nwork = in->sel ? in->nsel : in->nreads;
 	if (nwork == 0) return 0;
 	if (maxlen < 1) maxlen = 1;
 	if (maxlen > 1023) return fail("bt_align: reads longer than 1023 bases are not supported (the reference's Hit::mms is a FixedBitset<1024>)");
-	/* first-pass workspace: enough for the common case; rare deep searches go to the retry pass */
-	uint32_t nthreads = (uint32_t)ix->sms * (uint32_t)ix->blocks_per_sm * BT_THREADS;
+	const uint32_t nthreads = (uint32_t)ix->sms * (uint32_t)ix->blocks_per_sm * BT_THREADS;
 	const uint32_t stage_len = maxlen > BT_SMEM_LEN ? maxlen : 0;
 	if (ensure_ws(cx->ws1, nthreads, 6 * maxlen + 8, 8, 64, stage_len)) return 1;
+	const uint32_t nthreads_h = (uint32_t)ix->sms * BT_HEAVY_BLOCKS_PER_SM * 32;
+	if (ensure_ws(cx->wsh, nthreads_h, 6 * maxlen + 8, 8, 64, stage_len)) return 1;
 	const uint32_t nthreads2 = (uint32_t)ix->sms * 32;
 	uint32_t R2 = maxlen * maxlen + 8; if (R2 > 65000) R2 = 65000;   /* BtFrame::rowbase is 16 bits */
 	if (ensure_ws(cx->ws2, nthreads2, R2, maxlen + 2, 4096, stage_len)) return 1;
 	if (cx->retry_cap < nwork) {
-		cudaFree(cx->retry_sel); cx->retry_sel = nullptr; cx->retry_cap = 0;
+		cudaFree(cx->retry_sel); cudaFree(cx->heavy_sel); cx->retry_sel = cx->heavy_sel = nullptr; cx->retry_cap = 0;
 		CUDA_TRY(cudaMalloc((void **)&cx->retry_sel, (size_t)nwork * 4));
+		CUDA_TRY(cudaMalloc((void **)&cx->heavy_sel, (size_t)nwork * 4));
 		cx->retry_cap = nwork;
 	}
 	BtKParams P; memset(&P, 0, sizeof P);
@@ -464,24 +492,37 @@ static int enqueue_align(bt_context *cx, const bt_policy_t *pol, const bt_read_b
 	P.seq = in->seq; P.qual = in->qual; P.roff = in->offs; P.seeds = in->seeds; P.sel = in->sel; P.nwork = nwork;
 	P.found = out->found; P.flags = out->flags; P.hits = out->hits; P.slots = out->slots; P.mm_cap = out->mm_cap; P.rec_words = BT_HIT_HDR + out->mm_cap;
 	P.stats = ix->stats;
-	/* pass 1 */
-	P.rows = cx->ws1.rows; P.elims = cx->ws1.elims; P.frames = cx->ws1.frames; P.partials = cx->ws1.partials;
-	P.R = cx->ws1.R; P.FCAP = cx->ws1.FCAP; P.PCAP = cx->ws1.PCAP; P.stage = cx->ws1.stage; P.stage_len = cx->ws1.stage_len;
+	const uint32_t cblocks = (nwork + 255) / 256;
+	/* this context's previous batch must have finished with the scratch and the lists */
+	CUDA_TRY(cudaStreamWaitEvent(st, cx->ev_tail, 0));
+	/* main pass */
+	set_ws(P, cx->ws1);
+	P.budget = BT_MAIN_BUDGET;
 	bt_ctl_set_kernel<<<1, 1, 0, st>>>(cx->ctl, nwork);
+	bt_ctl_set_kernel<<<1, 1, 0, st>>>(cx->ctl + 1, 0);
+	bt_ctl_set_kernel<<<1, 1, 0, st>>>(cx->ctl + 2, 0);
 	uint32_t grid = (uint32_t)ix->sms * (uint32_t)ix->blocks_per_sm;
-	uint32_t need = (nwork + BT_THREADS - 1) / BT_THREADS;
+	const uint32_t need = (nwork + BT_THREADS - 1) / BT_THREADS;
 	if (grid > need) grid = need;
 	bt_search_kernel<<<grid, BT_THREADS, BT_THREADS * BT_SMEM_STRIDE, st>>>(P, cx->ctl);
-	/* retry pass for reads whose scratch overflowed (sized on the device) */
-	bt_ctl_set_kernel<<<1, 1, 0, st>>>(cx->ctl + 1, 0);
-	bt_collect_kernel<<<(nwork + 255) / 256, 256, 0, st>>>(out->flags, in->sel, nwork, BT_FLAG_STACK_OVF | BT_FLAG_FRAME_OVF | BT_FLAG_PART_OVF, cx->retry_sel, cx->ctl + 1);
+	bt_collect_kernel<<<cblocks, 256, 0, st>>>(out->flags, in->sel, nwork, nullptr, BT_FLAG_BUDGET, cx->heavy_sel, cx->ctl + 1);
+	bt_collect_kernel<<<cblocks, 256, 0, st>>>(out->flags, in->sel, nwork, nullptr, BT_FLAG_SCRATCH_OVF, cx->retry_sel, cx->ctl + 2);
+	CUDA_TRY(cudaEventRecord(cx->ev_main, st));
+	/* heavy pass and overflow pass on the side stream */
+	CUDA_TRY(cudaStreamWaitEvent(cx->side, cx->ev_main, 0));
+	P.sel = cx->heavy_sel; P.budget = 0;
+	set_ws(P, cx->wsh);
+	bt_search_kernel<<<ix->sms * BT_HEAVY_BLOCKS_PER_SM, 32, 32 * BT_SMEM_STRIDE, cx->side>>>(P, cx->ctl + 1);
+	bt_collect_kernel<<<cblocks, 256, 0, cx->side>>>(out->flags, cx->heavy_sel, nwork, cx->ctl + 1, BT_FLAG_SCRATCH_OVF, cx->retry_sel, cx->ctl + 2);
 	P.sel = cx->retry_sel;
-	P.rows = cx->ws2.rows; P.elims = cx->ws2.elims; P.frames = cx->ws2.frames; P.partials = cx->ws2.partials;
-	P.R = cx->ws2.R; P.FCAP = cx->ws2.FCAP; P.PCAP = cx->ws2.PCAP; P.stage = cx->ws2.stage; P.stage_len = cx->ws2.stage_len;
-	bt_search_kernel<<<ix->sms, 32, 32 * BT_SMEM_STRIDE, st>>>(P, cx->ctl + 1);
+	set_ws(P, cx->ws2);
+	bt_search_kernel<<<ix->sms, 32, 32 * BT_SMEM_STRIDE, cx->side>>>(P, cx->ctl + 2);
 	CUDA_TRY(cudaGetLastError());
 	return 0;
 }
+
+/* Marks the batch complete on the side stream (after optional D2H copies enqueued there by the caller). */
+static int finish_tail(bt_context *cx) { CUDA_TRY(cudaEventRecord(cx->ev_tail, cx->side)); return 0; }
 
 extern "C" int bt_context_align_device(bt_context_t *cx, const bt_policy_t *pol, const bt_read_batch_t *in, bt_hit_batch_t *out, void *stream) {
 	if (!cx || !pol || !in || !out) return fail("bt_context_align_device: null argument");
@@ -489,14 +530,24 @@ extern "C" int bt_context_align_device(bt_context_t *cx, const bt_policy_t *pol,
 	if (in->max_len == 0) return fail("bt_context_align_device: max_len must be set (the offsets live on the device)");
 	std::lock_guard<std::mutex> g(cx->mu);
 	CUDA_TRY(cudaSetDevice(cx->ix->device));
-	return enqueue_align(cx, pol, in, out, in->max_len, (cudaStream_t)stream);
+	if (enqueue_align(cx, pol, in, out, in->max_len, (cudaStream_t)stream)) return 1;
+	return finish_tail(cx);
+}
+
+/* Makes `stream` wait until the context's outstanding batch (including its heavy / overflow passes) is complete. */
+extern "C" int bt_context_join(bt_context_t *cx, void *stream) {
+	if (!cx) return fail("bt_context_join: null argument");
+	CUDA_TRY(cudaSetDevice(cx->ix->device));
+	CUDA_TRY(cudaStreamWaitEvent((cudaStream_t)stream, cx->ev_tail, 0));
+	return 0;
 }
 
 extern "C" int bt_align_batch_device(bt_index_t *ix, const bt_policy_t *pol, const bt_read_batch_t *in, bt_hit_batch_t *out, void *stream) {
 	if (!ix) return fail("bt_align_batch_device: null argument");
 	bt_context *cx = default_ctx(ix);
 	if (!cx) return 1;
-	return bt_context_align_device(cx, pol, in, out, stream);
+	if (bt_context_align_device(cx, pol, in, out, stream)) return 1;
+	return bt_context_join(cx, stream);      /* simple entry point: complete when `stream` is */
 }
 
 template <typename T> static int grow(T **p, size_t &cap, size_t need) {
@@ -541,13 +592,16 @@ static int align_host(bt_context *cx, const bt_policy_t *pol, const bt_read_batc
 		dout.found = cx->d_found; dout.flags = cx->d_flags; dout.hits = cx->d_hits;
 		if (enqueue_align(cx, pol, &din, &dout, maxlen, st)) return 1;
 		if (!in->sel) {
-			CUDA_TRY(cudaMemcpyAsync(out->found, cx->d_found, (size_t)n * 4, cudaMemcpyDeviceToHost, st));
-			CUDA_TRY(cudaMemcpyAsync(out->flags, cx->d_flags, (size_t)n * 4, cudaMemcpyDeviceToHost, st));
-			CUDA_TRY(cudaMemcpyAsync(out->hits, cx->d_hits, hitwords * 4, cudaMemcpyDeviceToHost, st));
-			if (sync) CUDA_TRY(cudaStreamSynchronize(st));
+			/* results leave on the side stream, behind the heavy / overflow passes */
+			CUDA_TRY(cudaMemcpyAsync(out->found, cx->d_found, (size_t)n * 4, cudaMemcpyDeviceToHost, cx->side));
+			CUDA_TRY(cudaMemcpyAsync(out->flags, cx->d_flags, (size_t)n * 4, cudaMemcpyDeviceToHost, cx->side));
+			CUDA_TRY(cudaMemcpyAsync(out->hits, cx->d_hits, hitwords * 4, cudaMemcpyDeviceToHost, cx->side));
+			if (finish_tail(cx)) return 1;
+			if (sync) CUDA_TRY(cudaStreamSynchronize(cx->side));
 		} else {
 			/* selection call: only the selected reads' entries are defined; copy them back one by one */
-			CUDA_TRY(cudaStreamSynchronize(st));
+			if (finish_tail(cx)) return 1;
+			CUDA_TRY(cudaStreamSynchronize(cx->side));
 			for (uint32_t k = 0; k < in->nsel; k++) {
 				uint32_t r = in->sel[k];
 				CUDA_TRY(cudaMemcpy(out->found + r, cx->d_found + r, 4, cudaMemcpyDeviceToHost));
@@ -571,6 +625,7 @@ extern "C" int bt_context_sync(bt_context_t *cx, void *stream) {
 	if (!cx) return fail("bt_context_sync: null argument");
 	CUDA_TRY(cudaSetDevice(cx->ix->device));
 	CUDA_TRY(cudaStreamSynchronize((cudaStream_t)stream));
+	CUDA_TRY(cudaStreamSynchronize(cx->side));
 	return 0;
 }
 extern "C" int bt_align_batch(bt_index_t *ix, const bt_policy_t *pol, const bt_read_batch_t *in, bt_hit_batch_t *out, void *stream) {

@@ -135,6 +135,10 @@ int  bt_context_align(bt_context_t *cx, const bt_policy_t *pol, const bt_read_ba
 int  bt_context_align_async(bt_context_t *cx, const bt_policy_t *pol, const bt_read_batch_t *in, bt_hit_batch_t *out, void *stream);
 int  bt_context_align_device(bt_context_t *cx, const bt_policy_t *pol, const bt_read_batch_t *in, bt_hit_batch_t *out, void *stream);
 int  bt_context_sync(bt_context_t *cx, void *stream);
+/* The library runs the few very long searches of a batch ("heavy" reads) and scratch-overflow retries on an internal
+ * side stream so that they overlap the next batch; bt_context_join makes `stream` wait for them (results of
+ * bt_context_align_device are complete only after join or sync; bt_align_batch_device joins by itself). */
+int  bt_context_join(bt_context_t *cx, void *stream);
 
 int  bt_stats_get(bt_index_t *ix, bt_stats_t *out, int reset);    /* synchronises the device */
 
