@@ -225,7 +225,8 @@ def main() -> None:
     torch.cuda.set_device(local)
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
-    bowtie_b200.build_library()
+    if not os.environ.get("BOWTIE_B200_LIB"):
+        bowtie_b200.build_library()
     ix = bowtie_b200.Index(str(base), need_mirror=True, device=local)
     pol = bowtie_b200.Policy(mode=1, mms=2, khits=1)
     B, L, slots, mm_cap = args.reads_per_step, READ_LEN, 1, 7
@@ -340,7 +341,7 @@ def main() -> None:
         except Exception:
             pass
     cpu = None
-    if world == 1:
+    if world == 1 and not os.environ.get("BT_BENCH_NO_CPU"):
         try:
             n = min(args.cpu_sample, B)
             with tempfile.TemporaryDirectory() as td:
