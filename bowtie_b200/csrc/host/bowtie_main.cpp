@@ -1,0 +1,600 @@
+/*
+ * bowtie_main.cpp — `bowtie`-compatible host driver over libbowtie_b200.so.
+ *
+ * Keeps the reference's command line (ebwt_search.cpp:443-545, 614-919), read-file formats
+ * (pat.cpp: FASTQ 862-975, FASTA 575-640, raw 1168-1213, -c 437-523), the default hit format
+ * (hit.cpp:73-301) and SAM (sam.cpp:20-257), and the stderr summary (hit.h:270-346); the search
+ * itself (everything the reference's *SearchWorker* functions do) is one bt_context_align_async()
+ * call per batch of reads.  Options of the reference's stateful path (--best, --strata, -M, -v 3,
+ * paired-end) are rejected with a message; nothing falls back to a CPU search.
+ */
+#include <getopt.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+#include <zlib.h>
+#include <algorithm>
+#include <chrono>
+#include <string>
+#include <vector>
+
+#include "../../../include/bowtie_b200.h"
+
+#define BOWTIE_VERSION "1.3.1"
+
+/* ---------------------------------------------------------------------------------------------- */
+/* options (names follow the reference's globals)                                                  */
+/* ---------------------------------------------------------------------------------------------- */
+enum { FASTQ = 1, FASTA, RAW, CMDLINE };
+struct Opts {
+	int format = FASTQ;
+	std::string ebwtFile, outfile;
+	std::vector<std::string> queries;
+	int mismatches = 0, seedMms = 2, maqLike = 1, seedLen = 28, qualThresh = 70, maxBts = 125;
+	bool noMaqRound = false, nofw = false, norc = false, allHits = false;
+	uint32_t khits = 1, mhits = 0xffffffffu;
+	uint32_t skipReads = 0, qUpto = 0xffffffffu;
+	int trim3 = 0, trim5 = 0;
+	bool solexaQuals = false, phred64Quals = false;
+	bool sam = false, samNoHead = false, samNoSQ = false, noUnal = false, fullRef = false, refIdx = false, printCost = false;
+	bool noQnameTrunc = false, quiet = false, timing = false;
+	std::string rgs;
+	int defaultMapq = 255, offBase = 0;
+	uint32_t seed = 0;
+	std::vector<bool> suppress = std::vector<bool>(64, false);
+	int nthreads = 1, device = 0;
+	uint32_t batch = 1u << 20;
+	std::string argstr;
+};
+
+static void die(const std::string &m) { fprintf(stderr, "%s\n", m.c_str()); exit(1); }
+static void unsupported(const char *what) {
+	die(std::string("Error: ") + what + " belongs to the reference's stateful (best-first / paired-end) path, which the B200 search path does not provide yet");
+}
+
+enum {
+	ARG_PHRED33 = 256, ARG_PHRED64, ARG_SOLEXA, ARG_SOLEXA13, ARG_NOMAQROUND, ARG_NOFW, ARG_NORC, ARG_MAXBTS, ARG_BEST, ARG_STRATA,
+	ARG_QUIET, ARG_REFIDX, ARG_SUPPRESS, ARG_FULLREF, ARG_MAPQ, ARG_SAM_NOHEAD, ARG_SAM_NOSQ, ARG_SAM_RG, ARG_NO_UNAL, ARG_SEED,
+	ARG_COST, ARG_REORDER, ARG_WRAPPER, ARG_VERSION, ARG_IGNORED0, ARG_IGNORED1, ARG_DEVICE, ARG_BATCH, ARG_SAM_NO_QNAME_TRUNC,
+	ARG_LARGE_INDEX, ARG_PAIRED
+};
+
+static const char *short_options = "fqrchu:v:s:at3:5:e:n:l:p:k:m:M:1:2:I:X:x:B:yS";
+static struct option long_options[] = {
+	{"skip", required_argument, 0, 's'}, {"qupto", required_argument, 0, 'u'}, {"trim5", required_argument, 0, '5'},
+	{"trim3", required_argument, 0, '3'}, {"phred33-quals", no_argument, 0, ARG_PHRED33}, {"phred64-quals", no_argument, 0, ARG_PHRED64},
+	{"solexa-quals", no_argument, 0, ARG_SOLEXA}, {"solexa1.3-quals", no_argument, 0, ARG_SOLEXA13}, {"seedmms", required_argument, 0, 'n'},
+	{"maqerr", required_argument, 0, 'e'}, {"seedlen", required_argument, 0, 'l'}, {"nomaqround", no_argument, 0, ARG_NOMAQROUND},
+	{"nofw", no_argument, 0, ARG_NOFW}, {"norc", no_argument, 0, ARG_NORC}, {"maxbts", required_argument, 0, ARG_MAXBTS},
+	{"tryhard", no_argument, 0, 'y'}, {"all", no_argument, 0, 'a'}, {"best", no_argument, 0, ARG_BEST}, {"strata", no_argument, 0, ARG_STRATA},
+	{"time", no_argument, 0, 't'}, {"offbase", required_argument, 0, 'B'}, {"quiet", no_argument, 0, ARG_QUIET},
+	{"refidx", no_argument, 0, ARG_REFIDX}, {"suppress", required_argument, 0, ARG_SUPPRESS}, {"fullref", no_argument, 0, ARG_FULLREF},
+	{"sam", no_argument, 0, 'S'}, {"mapq", required_argument, 0, ARG_MAPQ}, {"sam-nohead", no_argument, 0, ARG_SAM_NOHEAD},
+	{"sam-nosq", no_argument, 0, ARG_SAM_NOSQ}, {"sam-noSQ", no_argument, 0, ARG_SAM_NOSQ}, {"sam-RG", required_argument, 0, ARG_SAM_RG},
+	{"no-unal", no_argument, 0, ARG_NO_UNAL}, {"sam-no-qname-trunc", no_argument, 0, ARG_SAM_NO_QNAME_TRUNC},
+	{"threads", required_argument, 0, 'p'}, {"seed", required_argument, 0, ARG_SEED}, {"cost", no_argument, 0, ARG_COST},
+	{"reorder", no_argument, 0, ARG_REORDER}, {"wrapper", required_argument, 0, ARG_WRAPPER}, {"version", no_argument, 0, ARG_VERSION},
+	{"mm", no_argument, 0, ARG_IGNORED0}, {"shmem", no_argument, 0, ARG_IGNORED1}, {"help", no_argument, 0, 'h'},
+	{"device", required_argument, 0, ARG_DEVICE}, {"reads-per-batch", required_argument, 0, ARG_BATCH},
+	{"large-index", no_argument, 0, ARG_LARGE_INDEX}, {"12", required_argument, 0, ARG_PAIRED}, {"interleaved", required_argument, 0, ARG_PAIRED},
+	{"ff", no_argument, 0, ARG_PAIRED}, {"fr", no_argument, 0, ARG_IGNORED0}, {"rf", no_argument, 0, ARG_PAIRED},
+	{0, 0, 0, 0}
+};
+
+static long parse_int(long lo, const char *msg) {
+	char *end = NULL;
+	long v = strtol(optarg, &end, 10);
+	if (end == optarg || *end != 0 || v < lo) die(msg);
+	return v;
+}
+static void split(const std::string &s, char sep, std::vector<std::string> &out) {
+	size_t a = 0;
+	while (a <= s.size()) { size_t b = s.find(sep, a); if (b == std::string::npos) b = s.size(); if (b > a) out.push_back(s.substr(a, b - a)); a = b + 1; }
+}
+
+static void parse_options(int argc, char **argv, Opts &o) {
+	for (int i = 0; i < argc; i++) { o.argstr += argv[i]; if (i < argc - 1) o.argstr += " "; }
+	int c, idx = 0;
+	bool vset = false;
+	while ((c = getopt_long(argc, argv, short_options, long_options, &idx)) != -1) {
+		switch (c) {
+		case 'f': o.format = FASTA; break;
+		case 'q': o.format = FASTQ; break;
+		case 'r': o.format = RAW; break;
+		case 'c': o.format = CMDLINE; break;
+		case 'x': o.ebwtFile = optarg; break;
+		case 's': o.skipReads = (uint32_t)parse_int(0, "-s arg must be positive"); break;
+		case 'u': o.qUpto = (uint32_t)parse_int(1, "-u/--qupto arg must be at least 1"); break;
+		case '3': o.trim3 = (int)parse_int(0, "-3/--trim3 arg must be at least 0"); break;
+		case '5': o.trim5 = (int)parse_int(0, "-5/--trim5 arg must be at least 0"); break;
+		case 'v': o.maqLike = 0; o.mismatches = (int)parse_int(0, "-v arg must be at least 0"); vset = true;
+			if (o.mismatches > 3) die("-v arg must be at most 3"); break;
+		case 'n': o.seedMms = (int)parse_int(0, "-n/--seedmms arg must be at least 0 and at most 3"); o.maqLike = 1;
+			if (o.seedMms > 3) die("-n/--seedmms arg must be at least 0 and at most 3"); break;
+		case 'e': o.qualThresh = (int)parse_int(1, "-e/--err arg must be at least 1"); break;
+		case 'l': o.seedLen = (int)parse_int(5, "-l/--seedlen arg must be at least 5"); break;
+		case 'k': o.khits = (uint32_t)parse_int(1, "-k arg must be at least 1"); break;
+		case 'm': o.mhits = (uint32_t)parse_int(1, "-m arg must be at least 1"); break;
+		case 'a': o.allHits = true; break;
+		case 'p': o.nthreads = (int)parse_int(1, "-p/--threads arg must be at least 1"); break;
+		case 't': o.timing = true; break;
+		case 'B': o.offBase = (int)parse_int(-999999, "-B/--offbase cannot be a large negative number"); break;
+		case 'S': o.sam = true; break;
+		case 'y': o.maxBts = 0x7fffffff; break;
+		case 'h': printf("Usage: bowtie-b200-align [options]* -x <ebwt> {<s> | -c <seqs>} [<hits>]\n  (option names follow bowtie 1.3.1; see DESIGN.md for the supported subset)\n"); exit(0);
+		case 'M': unsupported("-M"); break;
+		case '1': case '2': case 'I': case 'X': case ARG_PAIRED: unsupported("paired-end alignment"); break;
+		case ARG_BEST: unsupported("--best"); break;
+		case ARG_STRATA: unsupported("--strata"); break;
+		case ARG_LARGE_INDEX: die("Error: large (64-bit) indexes are not supported"); break;
+		case ARG_PHRED33: o.solexaQuals = false; o.phred64Quals = false; break;
+		case ARG_PHRED64: case ARG_SOLEXA13: o.solexaQuals = false; o.phred64Quals = true; break;
+		case ARG_SOLEXA: o.solexaQuals = true; o.phred64Quals = false; break;
+		case ARG_NOMAQROUND: o.noMaqRound = true; break;
+		case ARG_NOFW: o.nofw = true; break;
+		case ARG_NORC: o.norc = true; break;
+		case ARG_MAXBTS: o.maxBts = (int)parse_int(0, "--maxbts must be positive"); break;
+		case ARG_QUIET: o.quiet = true; break;
+		case ARG_REFIDX: o.refIdx = true; break;
+		case ARG_FULLREF: o.fullRef = true; break;
+		case ARG_SUPPRESS: { std::vector<std::string> f; split(optarg, ',', f); for (auto &x : f) { int ii = atoi(x.c_str()); if (ii < 1) die("--suppress arg must be at least 1"); if (ii <= 64) o.suppress[ii - 1] = true; } break; }
+		case ARG_MAPQ: o.defaultMapq = (int)parse_int(0, "--mapq must be positive"); break;
+		case ARG_SAM_NOHEAD: o.samNoHead = true; break;
+		case ARG_SAM_NOSQ: o.samNoSQ = true; break;
+		case ARG_SAM_RG: if (!o.rgs.empty()) o.rgs += '\t'; o.rgs += optarg; break;
+		case ARG_NO_UNAL: o.noUnal = true; break;
+		case ARG_SAM_NO_QNAME_TRUNC: o.noQnameTrunc = true; break;
+		case ARG_SEED: o.seed = (uint32_t)parse_int(0, "--seed arg must be at least 0"); break;
+		case ARG_COST: o.printCost = true; break;
+		case ARG_VERSION: printf("%s version %s (B200 search path)\n", argv[0], BOWTIE_VERSION); exit(0);
+		case ARG_DEVICE: o.device = (int)parse_int(0, "--device must be >= 0"); break;
+		case ARG_BATCH: o.batch = (uint32_t)parse_int(1, "--reads-per-batch arg must be at least 1"); break;
+		case ARG_REORDER: case ARG_WRAPPER: case ARG_IGNORED0: case ARG_IGNORED1: break;   /* output is always in read order */
+		default: die("Error: unknown or unsupported option (see --help)");
+		}
+	}
+	(void)vset;
+	if (!o.maqLike && o.mismatches == 3) unsupported("-v 3");
+	if (o.qUpto + o.skipReads > o.qUpto) o.qUpto += o.skipReads;                 /* ebwt_search.cpp:893-895 */
+	if (o.ebwtFile.empty()) {
+		if (optind >= argc) die("No index, query, or output file specified!");
+		fprintf(stderr, "Setting the index via positional argument will be deprecated in a future release. Please use -x option instead.\n");
+		o.ebwtFile = argv[optind++];
+	}
+	if (optind >= argc) die("No query or output file specified!");
+	split(argv[optind++], ',', o.queries);
+	if (optind < argc) o.outfile = argv[optind++];
+	if (optind < argc) die(std::string("Extra parameter(s) specified: ") + argv[optind]);
+	if (o.sam) std::fill(o.suppress.begin(), o.suppress.end(), false);
+}
+
+/* ---------------------------------------------------------------------------------------------- */
+/* read input                                                                                      */
+/* ---------------------------------------------------------------------------------------------- */
+static uint8_t asc2dna[256];
+static const unsigned char solToPhred[] = {   /* qual.cpp: Solexa (log-odds) -> Phred, index = sol + 10 */
+	0, 1, 1, 1, 1, 1, 1, 2, 2, 3, 3, 4, 4, 5, 5, 6, 7, 8, 9, 10, 10, 11, 12, 13, 14, 15, 16, 17, 18, 19, 20, 21, 22, 23, 24, 25, 26, 27, 28, 29,
+	30, 31, 32, 33, 34, 35, 36, 37, 38, 39, 40, 41, 42, 43, 44, 45, 46, 47, 48, 49, 50, 51, 52, 53, 54, 55, 56, 57, 58, 59, 60, 61, 62, 63, 64, 65,
+	66, 67, 68, 69, 70, 71, 72, 73, 74, 75, 76, 77, 78, 79, 80, 81, 82, 83, 84, 85, 86, 87, 88, 89, 90, 91, 92, 93, 94, 95, 96, 97, 98, 99, 100 };
+
+struct ReadRec { std::string name, seq /* codes 0..4 */, qual /* phred+33 */; };
+
+struct Reader {
+	const Opts &o;
+	size_t fileIdx = 0;
+	gzFile f = NULL;
+	std::string buf; size_t pos = 0; bool eof = true;
+	uint64_t rdid = 0;
+	bool first = true;
+	size_t cmdIdx = 0;
+	explicit Reader(const Opts &oo) : o(oo) {}
+	bool open_next() {
+		if (f) { gzclose(f); f = NULL; }
+		if (fileIdx >= o.queries.size()) return false;
+		const std::string &fn = o.queries[fileIdx++];
+		f = (fn == "-") ? gzdopen(0, "rb") : gzopen(fn.c_str(), "rb");
+		if (!f) die("Warning: Could not open read file \"" + fn + "\" for reading");
+		gzbuffer(f, 1 << 20);
+		buf.clear(); pos = 0; eof = false; first = true;
+		return true;
+	}
+	int getc_() {
+		if (pos >= buf.size()) {
+			if (eof) return -1;
+			buf.resize(1 << 22);
+			int n = gzread(f, &buf[0], (unsigned)buf.size());
+			if (n <= 0) { eof = true; buf.clear(); pos = 0; return -1; }
+			buf.resize((size_t)n); pos = 0;
+		}
+		return (unsigned char)buf[pos++];
+	}
+	int peek_() { int c = getc_(); if (c >= 0) pos--; return c; }
+	bool getline_(std::string &s) {   /* returns false at EOF with nothing read; strips \n, keeps \r handling to callers */
+		s.clear();
+		int c = getc_();
+		if (c < 0) return false;
+		while (c >= 0 && c != '\n') { s.push_back((char)c); c = getc_(); }
+		return true;
+	}
+	char to_phred33(int c, const std::string &name) const {
+		if (c == ' ') die("Saw a space but expected an ASCII-encoded quality value.\nAre quality values formatted as integers?  If so, try --integer-quals.");
+		if (o.solexaQuals) {
+			int sol = c - 64; int p = sol < -10 ? 0 : solToPhred[sol + 10];
+			return (char)(p + 33);
+		} else if (o.phred64Quals) {
+			if (c < 64) die("Saw ASCII character " + std::to_string(c) + " but expected 64-based Phred qual.\nTry not specifying --solexa1.3-quals/--phred64-quals.");
+			return (char)(c - 31);
+		}
+		if (c < 33) die("Saw ASCII character " + std::to_string(c) + " but expected 33-based Phred qual.");
+		(void)name;
+		return (char)c;
+	}
+	void finish_seq(ReadRec &r, const std::string &raw, int &trimmed5, int &trimmed3) const {
+		int nchar = 0;
+		r.seq.clear();
+		for (char ch : raw) {
+			int c = (unsigned char)ch;
+			if (c == '.') c = 'N';
+			if (isalpha(c)) { if (nchar++ >= o.trim5) r.seq.push_back((char)asc2dna[c]); }
+		}
+		trimmed5 = nchar - (int)r.seq.size();
+		trimmed3 = std::min<int>(o.trim3, (int)r.seq.size());
+		r.seq.resize(r.seq.size() - (size_t)trimmed3);
+	}
+	/* Returns false when all input is consumed. */
+	bool next(ReadRec &r) {
+		if (o.format == CMDLINE) {
+			/* VectorPatternSource (pat.cpp:437-523): names are the ordinal, qualities 'I' */
+			if (cmdIdx >= o.queries.size()) return false;
+			std::string s = o.queries[cmdIdx++];
+			std::string q;
+			size_t colon = s.find(':');
+			if (colon != std::string::npos) { q = s.substr(colon + 1); s = s.substr(0, colon); }
+			int t5, t3; finish_seq(r, s, t5, t3);
+			if (q.empty()) r.qual.assign(r.seq.size(), 'I');
+			else { r.qual.clear(); int nq = 0; for (char ch : q) { if (++nq > o.trim5) r.qual.push_back(to_phred33((unsigned char)ch, r.name)); } r.qual.resize(r.seq.size()); }
+			r.name = std::to_string(rdid);
+			rdid++;
+			return true;
+		}
+		for (;;) {
+			if (!f && !open_next()) return false;
+			std::string l1, l2, l3, l4;
+			if (o.format == FASTQ) {
+				/* FastqPatternSource (pat.cpp:797-975) */
+				if (first) { int c = peek_(); while (c == '\r' || c == '\n') { getc_(); c = peek_(); } if (c < 0) { gzclose(f); f = NULL; continue; }
+					if (c != '@') die("Error: reads file does not look like a FASTQ file"); first = false; }
+				if (!getline_(l1)) { gzclose(f); f = NULL; continue; }
+				if (l1.empty()) continue;
+				if (!getline_(l2) || !getline_(l3)) { gzclose(f); f = NULL; continue; }
+				getline_(l4);
+				while (!l1.empty() && l1.back() == '\r') l1.pop_back();
+				while (!l4.empty() && l4.back() == '\r') l4.pop_back();
+				r.name = l1.substr(1);
+				int t5, t3; finish_seq(r, l2, t5, t3);
+				r.qual.clear();
+				int nq = 0;
+				for (char ch : l4) { char pc = to_phred33((unsigned char)ch, r.name); if (nq++ >= t5) r.qual.push_back(pc); }
+				if ((int)r.qual.size() >= t3) r.qual.resize(r.qual.size() - (size_t)t3);
+				if (r.qual.size() < r.seq.size()) die("Error: Read " + r.name + " has more read characters than quality values.");
+				if (r.qual.size() > r.seq.size()) die("Error: Read " + r.name + " has more quality values than read characters.");
+			} else if (o.format == FASTA) {
+				/* FastaPatternSource (pat.cpp:531-640): header line, then the first sequence line */
+				if (first) { int c = peek_(); while (c == '\r' || c == '\n') { getc_(); c = peek_(); } if (c < 0) { gzclose(f); f = NULL; continue; }
+					if (c != '>') die("Error: reads file does not look like a FASTA file"); first = false; }
+				if (!getline_(l1)) { gzclose(f); f = NULL; continue; }
+				if (l1.empty() || l1[0] != '>') continue;
+				while (!l1.empty() && l1.back() == '\r') l1.pop_back();
+				r.name = l1.substr(1);
+				int c = peek_();
+				while (c == '\r' || c == '\n') { getc_(); c = peek_(); }
+				if (c < 0 || c == '>') { if (c < 0) { gzclose(f); f = NULL; } continue; }      /* FASTA ended prematurely */
+				getline_(l2);
+				int t5, t3; finish_seq(r, l2, t5, t3);
+				r.qual.assign(r.seq.size(), 'I');
+				/* skip continuation lines up to the next record */
+				c = peek_();
+				while (c >= 0 && c != '>') { getline_(l3); c = peek_(); }
+			} else {
+				/* RawPatternSource (pat.cpp:1129-1213): one sequence per line, name = ordinal */
+				if (!getline_(l1)) { gzclose(f); f = NULL; continue; }
+				bool any = false; for (char ch : l1) if (isalpha((unsigned char)ch)) any = true;
+				if (!any) continue;
+				int t5, t3; finish_seq(r, l1, t5, t3);
+				r.qual.assign(r.seq.size(), 'I');
+				r.name.clear();
+			}
+			if (r.name.empty()) r.name = std::to_string(rdid);
+			rdid++;
+			return true;
+		}
+	}
+};
+
+/* genRandSeed (pat.cpp:21-57) */
+static uint32_t gen_rand_seed(const ReadRec &r, uint32_t seed) {
+	uint32_t rseed = (seed + 101u) * 59u * 61u * 67u * 71u * 73u * 79u * 83u;
+	for (size_t i = 0; i < r.seq.size(); i++) rseed ^= ((uint32_t)(uint8_t)r.seq[i] << ((i & 15) << 1));
+	for (size_t i = 0; i < r.qual.size(); i++) rseed ^= ((uint32_t)(uint8_t)r.qual[i] << ((i & 3) << 3));
+	for (size_t i = 0; i < r.name.size(); i++) rseed ^= ((uint32_t)(uint8_t)r.name[i] << ((i & 3) << 3));
+	return rseed;
+}
+
+/* ---------------------------------------------------------------------------------------------- */
+/* output                                                                                          */
+/* ---------------------------------------------------------------------------------------------- */
+struct Out {
+	FILE *fp = stdout;
+	std::string buf;
+	void flush() { if (!buf.empty()) { fwrite(buf.data(), 1, buf.size(), fp); buf.clear(); } }
+	void maybe_flush() { if (buf.size() > (1u << 22)) flush(); }
+};
+static void put_uint(std::string &o, uint64_t v) { char t[24]; int n = snprintf(t, sizeof t, "%llu", (unsigned long long)v); o.append(t, (size_t)n); }
+static void put_int(std::string &o, long long v) { char t[24]; int n = snprintf(t, sizeof t, "%lld", v); o.append(t, (size_t)n); }
+static void put_upto_ws(std::string &o, const char *s, bool ws) {      /* printUptoWs (hit.h:1265-1276) */
+	if (!ws) { o += s; return; }
+	size_t n = strcspn(s, " \t");
+	o.append(s, n);
+}
+
+struct HitView { uint32_t tidx, toff, oms, cost, stratum, fw, nmm; const uint32_t *mm; };
+
+/* VerboseHitSink::append (hit.cpp:73-301), partition == 0 */
+static void append_default(std::string &o, const Opts &op, const bt_index_t *ix, const ReadRec &r, const HitView &h) {
+	const size_t len = r.seq.size();
+	size_t field = 0; bool firstfield = true;
+	auto sep = [&]() { if (firstfield) firstfield = false; else o += '\t'; };
+	if (!op.suppress[field++]) { sep(); o += r.name; }
+	if (!op.suppress[field++]) { sep(); o += (h.fw ? '+' : '-'); }
+	if (!op.suppress[field++]) {
+		sep();
+		const char *nm = op.refIdx ? NULL : bt_index_refname(ix, h.tidx);
+		if (nm) put_upto_ws(o, nm, !op.fullRef); else put_uint(o, h.tidx);
+	}
+	if (!op.suppress[field++]) { sep(); put_int(o, (long long)h.toff + op.offBase); }
+	if (!op.suppress[field++]) {
+		sep();
+		if (h.fw) for (size_t i = 0; i < len; i++) o += "ACGTN"[(int)r.seq[i]];
+		else for (size_t i = len; i > 0; i--) { int c = r.seq[i - 1]; o += "ACGTN"[c < 4 ? (c ^ 3) : 4]; }
+	}
+	if (!op.suppress[field++]) {
+		sep();
+		if (h.fw) o += r.qual; else o.append(r.qual.rbegin(), r.qual.rend());
+	}
+	if (!op.suppress[field++]) { sep(); put_uint(o, h.oms); }
+	if (!op.suppress[field++]) {
+		sep();
+		/* mismatches in increasing offset from the 5' end; refc printed as stored, read char from the printed sequence */
+		uint32_t ord[1024]; uint32_t n = h.nmm < 1024 ? h.nmm : 1024;
+		for (uint32_t i = 0; i < n; i++) ord[i] = h.mm[i];
+		std::sort(ord, ord + n, [](uint32_t a, uint32_t b) { return (a & 0xffffu) < (b & 0xffffu); });
+		for (uint32_t i = 0; i < n; i++) {
+			uint32_t pos = ord[i] & 0xffffu, refc = (ord[i] >> 16) & 0xff;
+			if (i) o += ',';
+			put_uint(o, pos);
+			/* qryChar = fw ? patSeq[i] : patSeq[len-i-1] where patSeq is the printed (possibly rc) sequence */
+			int c = r.seq[pos]; char q = h.fw ? "ACGTN"[c] : "ACGTN"[c < 4 ? (c ^ 3) : 4];
+			o += ':'; o += "ACGT"[refc & 3]; o += '>'; o += q;
+		}
+	}
+	if (op.printCost) {
+		if (!op.suppress[field++]) { sep(); put_uint(o, h.stratum); }
+		if (!op.suppress[field++]) { sep(); put_uint(o, h.cost); }
+	}
+	o += '\n';
+}
+
+static void append_qname(std::string &o, const Opts &op, const std::string &name) {
+	for (char ch : name) { if (!op.noQnameTrunc && isspace((unsigned char)ch)) break; o += ch; }
+}
+
+/* SAMHitSink::append (sam.cpp:129-257), unpaired */
+static void append_sam(std::string &o, const Opts &op, const bt_index_t *ix, const ReadRec &r, const HitView &h, int mapq, int xms) {
+	const size_t len = r.seq.size();
+	append_qname(o, op, r.name);
+	o += '\t'; put_uint(o, h.fw ? 0 : 16); o += '\t';
+	const char *nm = op.refIdx ? NULL : bt_index_refname(ix, h.tidx);
+	if (nm) put_upto_ws(o, nm, !op.fullRef); else put_uint(o, h.tidx);
+	o += '\t'; put_uint(o, (uint64_t)h.toff + 1);
+	o += '\t'; put_int(o, mapq);
+	o += '\t'; put_uint(o, len); o += 'M';
+	o += "\t*\t0\t0\t";
+	if (h.fw) for (size_t i = 0; i < len; i++) o += "ACGTN"[(int)r.seq[i]];
+	else for (size_t i = len; i > 0; i--) { int c = r.seq[i - 1]; o += "ACGTN"[c < 4 ? (c ^ 3) : 4]; }
+	o += '\t';
+	if (h.fw) o += r.qual; else o.append(r.qual.rbegin(), r.qual.rend());
+	o += "\tXA:i:"; put_uint(o, h.stratum);
+	o += "\tMD:Z:";
+	/* mms[] is indexed from the 5' end; MD runs along the reference: 5'->3' for fw, reversed for rc */
+	static thread_local std::vector<int8_t> refAt;
+	refAt.assign(len, -1);
+	for (uint32_t i = 0; i < h.nmm; i++) { uint32_t pos = h.mm[i] & 0xffffu; if (pos < len) refAt[pos] = (int8_t)((h.mm[i] >> 16) & 3); }
+	int nmcnt = 0, run = 0;
+	if (h.fw) { for (size_t i = 0; i < len; i++) { if (refAt[i] >= 0) { nmcnt++; put_int(o, run); o += "ACGT"[(int)refAt[i]]; run = 0; } else run++; } }
+	else { for (size_t i = len; i > 0; i--) { if (refAt[i - 1] >= 0) { nmcnt++; put_int(o, run); o += "ACGT"[(int)refAt[i - 1]]; run = 0; } else run++; } }
+	put_int(o, run);
+	o += "\tNM:i:"; put_int(o, nmcnt);
+	if (xms > 0) { o += "\tXM:i:"; put_int(o, xms); }
+	o += '\n';
+}
+
+/* SAMHitSink::reportUnOrMax (sam.cpp:57-124), unpaired, un == true */
+static void append_sam_unaligned(std::string &o, const Opts &op, const ReadRec &r) {
+	append_qname(o, op, r.name);
+	o += "\t4\t*\t0\t0\t*\t*\t0\t0\t";
+	for (size_t i = 0; i < r.seq.size(); i++) o += "ACGTN"[(int)r.seq[i]];
+	o += '\t'; o += r.qual;
+	o += "\tXM:i:0\n";
+}
+
+/* SAMHitSink::appendHeaders (sam.cpp:20-50) */
+static void sam_headers(std::string &o, const Opts &op, const bt_index_t *ix, uint32_t nrefs) {
+	o += "@HD\tVN:1.0\tSO:unsorted\n";
+	if (!op.samNoSQ) {
+		for (uint32_t i = 0; i < nrefs; i++) {
+			o += "@SQ\tSN:";
+			const char *nm = op.refIdx ? NULL : bt_index_refname(ix, i);
+			if (nm) put_upto_ws(o, nm, !op.fullRef); else put_uint(o, i);
+			o += "\tLN:"; put_uint(o, bt_index_reflen(ix, i)); o += '\n';
+		}
+	}
+	if (!op.rgs.empty()) { o += "@RG\t"; o += op.rgs; o += '\n'; }
+	o += "@PG\tID:Bowtie\tVN:" BOWTIE_VERSION "\tCL:\""; o += op.argstr; o += "\"\n";
+}
+
+/* ---------------------------------------------------------------------------------------------- */
+/* batches                                                                                         */
+/* ---------------------------------------------------------------------------------------------- */
+struct Batch {
+	std::vector<ReadRec> reads;
+	std::vector<uint8_t> seq, qual; std::vector<uint64_t> offs; std::vector<uint32_t> seeds;
+	std::vector<uint32_t> found, flags, hits;
+	uint32_t slots = 1, mm_cap = 8;
+	bt_context_t *cx = NULL;
+	bool inflight = false;
+};
+
+int main(int argc, char **argv) {
+	for (int i = 0; i < 256; i++) asc2dna[i] = 4;
+	asc2dna['A'] = asc2dna['a'] = 0; asc2dna['C'] = asc2dna['c'] = 1; asc2dna['G'] = asc2dna['g'] = 2; asc2dna['T'] = asc2dna['t'] = 3;
+	Opts op;
+	parse_options(argc, argv, op);
+	auto t_start = std::chrono::steady_clock::now();
+
+	bt_policy_t pol; bt_policy_init(&pol);
+	pol.mode = op.maqLike ? 1 : 0; pol.mms = op.maqLike ? op.seedMms : op.mismatches;
+	pol.seed_len = op.seedLen; pol.qual_thresh = (uint32_t)op.qualThresh; pol.max_bts = (uint32_t)op.maxBts;
+	pol.khits = op.khits; pol.mhits = op.mhits; pol.all_hits = op.allHits; pol.nofw = op.nofw; pol.norc = op.norc; pol.maq_round = !op.noMaqRound;
+	const bool needMirror = op.maqLike || op.mismatches > 0;
+
+	/* adjustEbwtBase (ebwt.cpp:36-85): as given, else under $BOWTIE_INDEXES */
+	std::string base = op.ebwtFile;
+	{
+		FILE *t = fopen((base + ".1.ebwt").c_str(), "rb");
+		if (!t) { const char *e = getenv("BOWTIE_INDEXES"); if (e) { std::string b2 = std::string(e) + "/" + base; FILE *t2 = fopen((b2 + ".1.ebwt").c_str(), "rb"); if (t2) { fclose(t2); base = b2; } } }
+		else fclose(t);
+	}
+	bt_index_t *ix = NULL;
+	if (bt_index_load(base.c_str(), needMirror, op.device, &ix)) die(std::string("Error: ") + bt_last_error());
+	bt_index_info_t info; bt_index_info(ix, &info);
+	auto t_loaded = std::chrono::steady_clock::now();
+
+	Out out;
+	if (!op.outfile.empty()) { out.fp = fopen(op.outfile.c_str(), "wb"); if (!out.fp) die("Error: could not open alignment output file " + op.outfile); }
+	if (op.sam && !op.samNoHead) sam_headers(out.buf, op, ix, info.n_refs);
+
+	Reader rd(op);
+	Batch bt[2];
+	const uint32_t nlim = op.allHits ? 0xffffffffu : op.khits;
+	for (auto &b : bt) {
+		if (bt_context_create(ix, &b.cx)) die(std::string("Error: ") + bt_last_error());
+		b.slots = op.allHits ? 8 : op.khits;
+		b.mm_cap = op.maqLike ? 10 : (uint32_t)std::max(1, op.mismatches);
+	}
+	uint64_t numAligned = 0, numUnaligned = 0, numMaxed = 0, numReported = 0;
+	bool input_done = false;
+	ReadRec rec;
+
+	auto fill = [&](Batch &b) {
+		b.reads.clear(); b.seq.clear(); b.qual.clear(); b.offs.assign(1, 0); b.seeds.clear();
+		while (!input_done && b.reads.size() < op.batch) {
+			if (rd.rdid >= op.qUpto) { input_done = true; break; }
+			if (!rd.next(rec)) { input_done = true; break; }
+			if (rd.rdid - 1 < op.skipReads) continue;                              /* -s: skipped reads are not counted */
+			b.seq.insert(b.seq.end(), rec.seq.begin(), rec.seq.end());
+			b.qual.insert(b.qual.end(), rec.qual.begin(), rec.qual.end());
+			b.offs.push_back(b.seq.size());
+			b.seeds.push_back(gen_rand_seed(rec, op.seed));
+			b.reads.push_back(rec);
+		}
+	};
+	auto launch = [&](Batch &b) {
+		if (b.reads.empty()) return;
+		const size_t n = b.reads.size(), rw = BT_HIT_HDR_WORDS + b.mm_cap;
+		b.found.assign(n, 0); b.flags.assign(n, 0); b.hits.assign(n * b.slots * rw, 0);
+		bt_read_batch_t in; memset(&in, 0, sizeof in);
+		in.nreads = (uint32_t)n; in.seq = b.seq.data(); in.qual = b.qual.data(); in.offs = b.offs.data(); in.seeds = b.seeds.data();
+		bt_hit_batch_t ho = { b.found.data(), b.flags.data(), b.hits.data(), b.slots, b.mm_cap };
+		if (bt_context_align_async(b.cx, &pol, &in, &ho, NULL)) die(std::string("Error: ") + bt_last_error());
+		b.inflight = true;
+	};
+	auto finish = [&](Batch &b) {
+		if (!b.inflight) return;
+		if (bt_context_sync(b.cx, NULL)) die(std::string("Error: ") + bt_last_error());
+		b.inflight = false;
+		const size_t n = b.reads.size();
+		size_t rw = BT_HIT_HDR_WORDS + b.mm_cap;
+		/* reads whose records did not fit: run them again with exact capacities (ABI contract) */
+		std::vector<uint32_t> need; uint32_t maxFound = 0, maxLen = 1;
+		for (size_t i = 0; i < n; i++) if (b.flags[i] & (BT_OVF_HITS | BT_OVF_MM)) { need.push_back((uint32_t)i); maxFound = std::max(maxFound, b.found[i]); maxLen = std::max<uint32_t>(maxLen, (uint32_t)b.reads[i].seq.size()); }
+		for (size_t i = 0; i < n; i++) if (b.flags[i] & (BT_OVF_STACK | BT_OVF_FRAME | BT_OVF_PART)) die("Error: search scratch exhausted for read " + b.reads[i].name);
+		std::vector<uint32_t> found2, flags2, hits2; uint32_t slots2 = 0, mm2 = 0;
+		if (!need.empty()) {
+			slots2 = std::max<uint32_t>(1, std::min(maxFound, nlim)); mm2 = maxLen;
+			found2.assign(n, 0); flags2.assign(n, 0); hits2.assign(n * (size_t)slots2 * (BT_HIT_HDR_WORDS + mm2), 0);
+			bt_read_batch_t in; memset(&in, 0, sizeof in);
+			in.nreads = (uint32_t)n; in.seq = b.seq.data(); in.qual = b.qual.data(); in.offs = b.offs.data(); in.seeds = b.seeds.data();
+			in.sel = need.data(); in.nsel = (uint32_t)need.size();
+			bt_hit_batch_t ho = { found2.data(), flags2.data(), hits2.data(), slots2, mm2 };
+			if (bt_context_align(b.cx, &pol, &in, &ho, NULL)) die(std::string("Error: ") + bt_last_error());
+		}
+		size_t ni = 0;
+		for (size_t i = 0; i < n; i++) {
+			const ReadRec &r = b.reads[i];
+			const uint32_t *recs = &b.hits[i * b.slots * rw]; size_t rwi = rw; uint32_t found = b.found[i];
+			if (ni < need.size() && need[ni] == i) { rwi = BT_HIT_HDR_WORDS + mm2; recs = &hits2[i * (size_t)slots2 * rwi]; found = found2[i]; ni++; }
+			/* HitSinkPerThread::finishRead (hit.h:741-786) */
+			const bool maxed = found > op.mhits, unal = (found == 0);
+			if (maxed) { numMaxed++; }
+			else if (unal) { numUnaligned++; if (op.sam && !op.noUnal) append_sam_unaligned(out.buf, op, r); }
+			else {
+				uint32_t nrep = std::min(found, nlim);
+				for (uint32_t s = 0; s < nrep; s++) {
+					const uint32_t *w = recs + (size_t)s * rwi;
+					HitView h = { w[0], w[1], w[2], w[3] & 0xffffu, (w[3] >> 16) & 0xff, (w[3] >> 24) & 1, w[4], w + BT_HIT_HDR_WORDS };
+					if (op.sam) append_sam(out.buf, op, ix, r, h, op.defaultMapq, (int)nrep); else append_default(out.buf, op, ix, r, h);
+				}
+				numAligned++; numReported += nrep;
+			}
+			out.maybe_flush();
+		}
+	};
+
+	/* double-buffered: the GPU works on one batch while the host parses the next and formats the previous */
+	int cur = 0;
+	fill(bt[cur]); launch(bt[cur]);
+	while (bt[cur].inflight) {
+		int nxt = cur ^ 1;
+		fill(bt[nxt]);
+		launch(bt[nxt]);
+		finish(bt[cur]);
+		cur = nxt;
+	}
+	out.flush();
+	if (out.fp != stdout) fclose(out.fp);
+	auto t_end = std::chrono::steady_clock::now();
+
+	/* HitSink::finish (hit.h:270-346) */
+	if (!op.quiet) {
+		uint64_t tot = numAligned + numUnaligned + numMaxed;
+		double alPct = 0, unalPct = 0, maxPct = 0;
+		if (tot > 0) { alPct = 100.0 * (double)(numAligned + numMaxed) / (double)tot; unalPct = 100.0 * (double)numUnaligned / (double)tot; maxPct = 100.0 * (double)numMaxed / (double)tot; }
+		fprintf(stderr, "# reads processed: %llu\n", (unsigned long long)tot);
+		fprintf(stderr, "# reads with at least one alignment: %llu (%.2f%%)\n", (unsigned long long)(numAligned + numMaxed), alPct);
+		fprintf(stderr, "# reads that failed to align: %llu (%.2f%%)\n", (unsigned long long)numUnaligned, unalPct);
+		if (numMaxed > 0) fprintf(stderr, "# reads with alignments suppressed due to -m: %llu (%.2f%%)\n", (unsigned long long)numMaxed, maxPct);
+		if (numReported == 0) fprintf(stderr, "No alignments\n");
+		else fprintf(stderr, "Reported %llu alignments\n", (unsigned long long)numReported);
+	}
+	if (op.timing) {
+		auto secs = [](std::chrono::steady_clock::duration d) { return (long)std::chrono::duration_cast<std::chrono::seconds>(d).count(); };
+		long a = secs(t_loaded - t_start), s = secs(t_end - t_loaded), t = secs(t_end - t_start);
+		fprintf(stderr, "Time loading index: %02ld:%02ld:%02ld\n", a / 3600, (a / 60) % 60, a % 60);
+		fprintf(stderr, "Time searching: %02ld:%02ld:%02ld\n", s / 3600, (s / 60) % 60, s % 60);
+		fprintf(stderr, "Overall time: %02ld:%02ld:%02ld\n", t / 3600, (t / 60) % 60, t % 60);
+	}
+	for (auto &b : bt) bt_context_free(b.cx);
+	bt_index_free(ix);
+	return 0;
+}

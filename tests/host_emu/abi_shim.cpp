@@ -1,0 +1,102 @@
+/*
+ * tests/host_emu/abi_shim.cpp — TEST-ONLY stand-in for libbowtie_b200.so on machines without a GPU.
+ *
+ * Exports the C ABI of include/bowtie_b200.h but runs the device state machine (bt_core.cuh) through the
+ * host emulation, one lane at a time.  Its only purpose is to let `pytest -m "not gpu"` exercise the HOST
+ * code of the product (the bowtie-compatible driver: option parsing, read parsing, default/SAM formatting)
+ * against the reference binary.  It is built into tests/host_emu/shim/ and is only ever found through an
+ * explicit LD_LIBRARY_PATH set by tests/test_cli_parity.py; the product never loads it.
+ */
+#define BT_HOST_EMU 1
+#include <stdlib.h>
+#include <string.h>
+#include <string>
+#include <vector>
+#include "../../bowtie_b200/csrc/bt_native.cuh"
+#include "../../include/bowtie_b200.h"
+extern "C" {
+#include "../../oracle/bt_oracle.h"
+}
+
+struct EmuIx { std::vector<uint4> blocks; bto_index *raw; BtDevIndex dev; };
+struct bt_index { EmuIx *e[2]; bool mirror; std::vector<std::string> names; bt_stats_t st; };
+struct bt_context { bt_index *ix; };
+static std::string g_err;
+
+static EmuIx *load_one(const char *base, int mirror) {
+	char err[256];
+	bto_index *ix = bto_index_load(base, mirror, err, sizeof err);
+	if (!ix) { g_err = err; return NULL; }
+	EmuIx *e = new EmuIx(); e->raw = ix;
+	BtNativeIndex n; n.ebwt = ix->ebwt; n.len = ix->len; n.zOff = ix->zOff; n.zEbwtByteOff = ix->zEbwtByteOff; n.zEbwtBpOff = (uint32_t)ix->zEbwtBpOff;
+	memcpy(n.fchr, ix->fchr, sizeof n.fchr);
+	uint32_t nb = (ix->len >> 6) + 1; e->blocks.resize(2 * (size_t)nb);
+	for (uint32_t k = 0; k < nb; k++) bt_relayout_block(n, k, &e->blocks[2 * (size_t)k]);
+	BtDevIndex &d = e->dev;
+	d.blocks = e->blocks.data(); d.offs = ix->offs; d.ftab = ix->ftab; d.eftab = ix->eftab; d.rstarts = ix->rstarts; d.plen = ix->plen;
+	d.len = ix->len; d.zOff = ix->zOff; d.nFrag = ix->nFrag; d.nPat = ix->nPat; d.offMask = ix->offMask; d.offRate = ix->offRate; d.ftabChars = ix->ftabChars;
+	memcpy(d.fchr, ix->fchr, sizeof d.fchr); d.fw = (uint32_t)ix->fw;
+	return e;
+}
+
+extern "C" {
+int bt_abi_version(void) { return BT_ABI_VERSION; }
+const char *bt_last_error(void) { return g_err.c_str(); }
+int bt_index_load(const char *basename, int need_mirror, int, bt_index_t **out) {
+	bt_index *ix = new bt_index(); memset(&ix->st, 0, sizeof ix->st); ix->e[0] = ix->e[1] = NULL; ix->mirror = need_mirror != 0;
+	ix->e[0] = load_one(basename, 0);
+	if (ix->e[0] && need_mirror) ix->e[1] = load_one(basename, 1);
+	if (!ix->e[0] || (need_mirror && !ix->e[1])) { delete ix; return 1; }
+	bto_index *r = ix->e[0]->raw;
+	for (uint32_t i = 0; i < r->nRefnames; i++) ix->names.push_back(r->refnames[i]);
+	while (!ix->names.empty() && ix->names.back().empty()) ix->names.pop_back();
+	*out = ix; return 0;
+}
+void bt_index_free(bt_index_t *ix) { if (!ix) return; for (int k = 0; k < 2; k++) if (ix->e[k]) { bto_index_free(ix->e[k]->raw); delete ix->e[k]; } delete ix; }
+int bt_index_info(const bt_index_t *ix, bt_index_info_t *info) { bto_index *r = ix->e[0]->raw; info->len = r->len; info->n_refs = r->nPat; info->off_rate = r->offRate; info->ftab_chars = r->ftabChars; info->has_mirror = ix->mirror; info->device_bytes = 0; return 0; }
+const char *bt_index_refname(const bt_index_t *ix, uint32_t i) { return i < ix->names.size() ? ix->names[i].c_str() : NULL; }
+uint32_t bt_index_reflen(const bt_index_t *ix, uint32_t i) { bto_index *r = ix->e[0]->raw; return i < r->nPat ? r->plen[i] : 0; }
+void bt_policy_init(bt_policy_t *p) { memset(p, 0, sizeof *p); p->mode = 1; p->mms = 2; p->seed_len = 28; p->qual_thresh = 70; p->max_bts = 125; p->khits = 1; p->mhits = 0xffffffffu; p->maq_round = 1; }
+
+static int run(bt_index *ix, const bt_policy_t *pol, const bt_read_batch_t *in, bt_hit_batch_t *out) {
+	BtKParams P; memset(&P, 0, sizeof P);
+	P.ix[0] = ix->e[0]->dev; if (ix->e[1]) P.ix[1] = ix->e[1]->dev;
+	memcpy(&P.pol, pol, sizeof(BtPolicy));
+	bt_build_prog(pol->mode, pol->mms, pol->nofw, pol->norc, P.prog);
+	P.seq = in->seq; P.qual = in->qual; P.roff = in->offs; P.seeds = in->seeds;
+	P.found = out->found; P.flags = out->flags; P.hits = out->hits; P.slots = out->slots; P.mm_cap = out->mm_cap; P.rec_words = BT_HIT_HDR + out->mm_cap;
+	uint32_t maxlen = 1; for (uint32_t i = 0; i < in->nreads; i++) { uint64_t l = in->offs[i + 1] - in->offs[i]; if (l > maxlen) maxlen = (uint32_t)l; }
+	uint32_t R = maxlen * maxlen + 8; if (R > 65000) R = 65000;
+	std::vector<uint4> rows(2 * (size_t)R); std::vector<uint8_t> elims(R), stage; std::vector<BtFrame> frames(maxlen + 2); std::vector<uint64_t> parts(1 << 16);
+	P.R = R; P.FCAP = maxlen + 2; P.PCAP = 1 << 16;
+	BtScratch S = { rows.data(), elims.data(), frames.data(), parts.data() };
+	BtLane L; memset(&L, 0, sizeof L);
+	const uint32_t nwork = in->sel ? in->nsel : in->nreads;
+	for (uint32_t w = 0; w < nwork; w++) {
+		uint32_t r = in->sel ? in->sel[w] : w;
+		bt_begin_read(L, P, r);
+		stage.assign(2 * (size_t)L.rlen + 2, 0);
+		memcpy(stage.data(), in->seq + in->offs[r], L.rlen); memcpy(stage.data() + L.rlen, in->qual + in->offs[r], L.rlen);
+		L.rseq = stage.data(); L.rqual = stage.data() + L.rlen; L.hasN = memchr(stage.data(), 4, L.rlen) != NULL;
+		while (L.pc != PC_FINISH_READ) { if (BT_IS_FAST(L.pc)) bt_fast_iter(L, P, S); else bt_rare_iter(L, P, S); }
+		bt_finish_read(L, P);
+	}
+	return 0;
+}
+static int check(const bt_index *ix, const bt_policy_t *pol) {
+	if (pol->mode == 0 && pol->mms > 2) { g_err = "-v 3 is the reference's stateful path"; return 1; }
+	if ((pol->mode == 1 || pol->mms > 0) && !ix->mirror) { g_err = "mirror index needed"; return 1; }
+	return 0;
+}
+int bt_align_batch(bt_index_t *ix, const bt_policy_t *pol, const bt_read_batch_t *in, bt_hit_batch_t *out, void *) { if (check(ix, pol)) return 1; return run(ix, pol, in, out); }
+int bt_align_batch_device(bt_index_t *, const bt_policy_t *, const bt_read_batch_t *, bt_hit_batch_t *, void *) { g_err = "emulation shim has no device entry point"; return 1; }
+int bt_context_create(bt_index_t *ix, bt_context_t **out) { bt_context *c = new bt_context(); c->ix = ix; *out = c; return 0; }
+void bt_context_free(bt_context_t *cx) { delete cx; }
+int bt_context_align(bt_context_t *cx, const bt_policy_t *pol, const bt_read_batch_t *in, bt_hit_batch_t *out, void *s) { return bt_align_batch(cx->ix, pol, in, out, s); }
+int bt_context_align_async(bt_context_t *cx, const bt_policy_t *pol, const bt_read_batch_t *in, bt_hit_batch_t *out, void *s) { return bt_align_batch(cx->ix, pol, in, out, s); }
+int bt_context_align_device(bt_context_t *, const bt_policy_t *, const bt_read_batch_t *, bt_hit_batch_t *, void *) { g_err = "emulation shim has no device entry point"; return 1; }
+int bt_context_sync(bt_context_t *, void *) { return 0; }
+int bt_context_join(bt_context_t *, void *) { return 0; }
+int bt_stats_get(bt_index_t *ix, bt_stats_t *out, int) { *out = ix->st; return 0; }
+int bt_debug_lf(bt_index_t *, int, const uint32_t *, uint32_t, uint32_t *) { g_err = "not in the shim"; return 1; }
+}

@@ -1,0 +1,105 @@
+"""Drop-in check of the bowtie-compatible host driver (bowtie_b200/bowtie-b200-align): its hit file and
+stderr summary must equal the unmodified reference binary's (oracle/_ref/bowtie-align-s) byte for byte.
+
+* not-gpu variant: the driver runs against tests/host_emu/shim/libbowtie_b200.so (the device state machine
+  compiled for the host, test-only) — this checks the HOST code: option parsing, read parsing, formatting.
+* gpu variant: the same comparisons with the real CUDA library.
+"""
+import os
+import subprocess
+from pathlib import Path
+
+import pytest
+
+from helpers import FIXTURES, REF_ALIGN, ROOT, ensure_oracle_built, have_reference
+
+CLI = ROOT / "bowtie_b200" / "bowtie-b200-align"
+SHIM_DIR = ROOT / "tests" / "host_emu" / "shim"
+
+CASES = [
+    ("n2-default", ["-n", "2"], "fq"),
+    ("v0", ["-v", "0"], "fq"),
+    ("v2-k3", ["-v", "2", "-k", "3"], "fq"),
+    ("n2-a-cost", ["-n", "2", "-a", "--cost"], "fq"),
+    ("n3-m2", ["-n", "3", "-m", "2"], "fq"),
+    ("n2-sam", ["-n", "2", "-S"], "fq"),
+    ("v2-sam-a", ["-v", "2", "-a", "-S", "--mapq", "42", "--sam-RG", "ID:x", "--sam-RG", "SM:y"], "fq"),
+    ("n2-sam-m1-nounal", ["-n", "2", "-m", "1", "-S", "--no-unal"], "fq"),
+    ("n2-sam-nohead", ["-n", "2", "-S", "--sam-nohead"], "fq"),
+    ("v1-fasta", ["-v", "1", "-f"], "fa"),
+    ("n2-raw", ["-n", "2", "-r"], "raw"),
+    ("n2-trim", ["-n", "2", "-5", "3", "-3", "2"], "fq"),
+    ("n1-skip-upto", ["-n", "1", "-s", "100", "-u", "500"], "fq"),
+    ("n2-suppress-offbase", ["-n", "2", "--suppress", "1,5,6", "-B", "1"], "fq"),
+    ("n2-refidx", ["-n", "2", "--refidx"], "fq"),
+    ("n2-fullref-nofw", ["-n", "2", "--fullref", "--nofw"], "fq"),
+    ("n2-l20-e100-nomaqround", ["-n", "2", "-l", "20", "-e", "100", "--nomaqround"], "fq"),
+    ("v2-cmdline", ["-a", "-v", "2", "--suppress", "1,5,6,7", "-c"], "cmd"),     # MANUAL.markdown:246-253 Example 1
+    ("n2-seed7", ["-n", "2", "--seed", "7", "-k", "2"], "fq"),
+]
+
+
+@pytest.fixture(scope="module")
+def cli():
+    ensure_oracle_built()
+    if not have_reference():
+        pytest.skip("reference binary / fixtures not available")
+    import bowtie_b200
+    bowtie_b200.build_library()            # also builds the driver
+    if not CLI.exists():
+        pytest.fail("bowtie-b200-align was not built")
+    return CLI
+
+
+def build_shim():
+    so = SHIM_DIR / "libbowtie_b200.so"
+    srcs = [ROOT / "tests" / "host_emu" / "abi_shim.cpp", ROOT / "bowtie_b200" / "csrc" / "bt_core.cuh", ROOT / "oracle" / "bt_oracle.c"]
+    if not so.exists() or so.stat().st_mtime < max(s.stat().st_mtime for s in srcs):
+        SHIM_DIR.mkdir(exist_ok=True)
+        subprocess.run(["g++", "-O2", "-std=c++17", "-fPIC", "-shared", "-o", str(so), str(srcs[0]), str(srcs[2])], check=True, capture_output=True)
+    return so
+
+
+def reads_arg(kind):
+    return {"fq": str(FIXTURES / "e_coli_1000.fq"), "fa": str(FIXTURES / "e_coli_1000.fa"), "raw": str(FIXTURES / "e_coli_1000.raw"),
+            "cmd": "ATGCATCATGCGCCAT"}[kind]
+
+
+def run(exe, flags, kind, out, env=None, ref=False):
+    cmd = [str(exe), *flags] + (["-p", "1"] if ref else []) + ["-x", str(FIXTURES / "e_coli"), reads_arg(kind), str(out)]
+    p = subprocess.run(cmd, capture_output=True, text=True, env=env)
+    assert p.returncode == 0, p.stderr
+    body = Path(out).read_bytes()
+    body = b"".join(l for l in body.splitlines(keepends=True) if not l.startswith(b"@PG"))   # @PG embeds the command line
+    summary = "\n".join(l for l in p.stderr.splitlines() if l.startswith("#") or l.startswith("Reported") or l.startswith("No alignments"))
+    return body, summary
+
+
+def compare(cli, flags, kind, tmp_path, env):
+    ref_body, ref_sum = run(REF_ALIGN, flags, kind, tmp_path / "ref.out", ref=True)
+    our_body, our_sum = run(cli, flags, kind, tmp_path / "our.out", env=env)
+    assert our_body == ref_body
+    assert our_sum == ref_sum
+    assert len(ref_body) > 0
+
+
+@pytest.mark.parametrize("name,flags,kind", CASES, ids=[c[0] for c in CASES])
+def test_cli_host_logic_matches_reference(name, flags, kind, cli, tmp_path):
+    build_shim()
+    env = dict(os.environ, LD_LIBRARY_PATH=str(SHIM_DIR))
+    compare(cli, flags, kind, tmp_path, env)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("name,flags,kind", CASES, ids=[c[0] for c in CASES])
+def test_cli_gpu_matches_reference(name, flags, kind, cli, tmp_path):
+    env = {k: v for k, v in os.environ.items() if k != "LD_LIBRARY_PATH"}
+    compare(cli, flags, kind, tmp_path, env)
+
+
+def test_cli_rejects_stateful_options(cli, tmp_path):
+    build_shim()
+    env = dict(os.environ, LD_LIBRARY_PATH=str(SHIM_DIR))
+    for flags in (["--best"], ["-v", "3"], ["-M", "1"], ["-1", "a", "-2", "b"]):
+        p = subprocess.run([str(cli), *flags, "-x", str(FIXTURES / "e_coli"), str(FIXTURES / "e_coli_1000.fq")], capture_output=True, text=True, env=env)
+        assert p.returncode != 0 and "stateful" in p.stderr
