@@ -150,7 +150,7 @@ struct BtLane {
 	uint32_t rid, rlen, seed, found, flags, hasN;
 	uint8_t *rseq, *rqual;         /* writable per-lane copy of the read (shared memory, or scratch for long reads) */
 	/* control */
-	uint32_t pc, ph, done, ret, lfk, step, it0;
+	uint32_t pc, ph, done, ret, lfk, step, nit;   /* nit: transitions taken by the current read */
 	/* backtracker object state */
 	uint32_t ebwtSel, fw, considerQuals, halfAndHalf, reportPartials, reportExacts, maqPenalty;
 	uint32_t qualThresh, maxBts;
@@ -806,7 +806,7 @@ BT_FN void bt_begin_read(BtLane &L, const BtKParams &P, uint32_t rid) {
 	L.rid = rid;
 	L.rlen = (uint32_t)(P.roff[rid + 1] - P.roff[rid]);
 	L.seed = P.seeds[rid];
-	L.found = 0; L.flags = 0; L.ph = 0; L.done = 0; L.npart = 0; L.nmuts = 0; L.pal_i = 0; L.step = 0; L.it0 = L.s_iter;
+	L.found = 0; L.flags = 0; L.ph = 0; L.done = 0; L.npart = 0; L.nmuts = 0; L.pal_i = 0; L.step = 0; L.nit = 0;
 	L.qualThresh = P.pol.mode == 0 ? 0xffffffffu : P.pol.qualThresh;
 	L.maxBts = P.pol.mode == 0 ? 0xffffffffu : P.pol.maxBts;
 	L.maqPenalty = P.pol.mode == 0 ? 1u : (uint32_t)P.pol.maqRound;
@@ -833,7 +833,7 @@ BT_FN void bt_fast_iter(BtLane &L, const BtKParams &P, const BtScratch &S) {
 	if (!isChase && (L.lfk == LFK_EX || L.lfk == LFK_PAIR) && (L.lbot >> 6) != (L.ltop >> 6)) { bB = bt_load_block(ix, L.lbot); L.s_blk++; }
 	uint32_t nc = 4, nq = 0;
 	if (!isChase && L.d + 1 < L.qlen) { nc = bt_qry(L, L.qlen - L.d - 2); nq = bt_qual_at(L, L.qlen - L.d - 2); }
-	L.s_iter++;
+	L.s_iter++; L.nit++;
 	if (isChase) {
 		/* one step of the row walk of Ebwt::reportChaseOne (ebwt.h:2727-2734): mapLF(l) */
 		const uint32_t c = bt_row_l(bA, L.crow);
@@ -880,8 +880,8 @@ BT_FN void bt_rare_iter(BtLane &L, const BtKParams &P, const BtScratch &S) {
 #pragma unroll 1
 	for (int k = 0; k < BT_RARE_CHAIN && BT_IS_RARE_STEP(L.pc); k++) {
 		if (L.flags & BT_FLAG_SCRATCH_OVF) { L.pc = PC_FINISH_READ; break; }
-		if (P.budget && (L.s_iter - L.it0) > P.budget) { L.flags |= BT_FLAG_BUDGET; L.pc = PC_FINISH_READ; break; }   /* heavy read */
-		L.s_iter++;
+		if (P.budget && L.nit > P.budget) { L.flags |= BT_FLAG_BUDGET; L.pc = PC_FINISH_READ; break; }   /* heavy read */
+		L.s_iter++; L.nit++;
 		bt_rare_step(L, P, S);
 	}
 }

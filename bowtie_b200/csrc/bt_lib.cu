@@ -16,6 +16,7 @@
 #include <mutex>
 
 #include "bt_native.cuh"
+#include "bt_ctxq.cuh"
 #include "../../include/bowtie_b200.h"
 
 static_assert(sizeof(bt_policy_t) == sizeof(BtPolicy), "bt_policy_t and BtPolicy must share a layout");
@@ -58,6 +59,12 @@ __global__ void bt_debug_lf_kernel(BtDevIndex ix, const uint32_t *rows, uint32_t
 #endif
 #ifndef BT_RARE_THRESH
 #define BT_RARE_THRESH 24          /* ... or as soon as this many lanes of the warp wait for one          */
+#endif
+#ifndef BT_Q_NCTX
+#define BT_Q_NCTX 384               /* read contexts per block of the queue-driven kernel                    */
+#endif
+#ifndef BT_Q_THREADS
+#define BT_Q_THREADS 384            /* worker threads per block                                               */
 #endif
 #define BT_SMEM_LEN 128            /* reads up to this length are staged in shared memory                   */
 #define BT_SMEM_STRIDE (2 * BT_SMEM_LEN + 4)   /* +4: lanes' equal offsets fall in different banks          */
@@ -165,6 +172,136 @@ bt_search_kernel(BtKParams P, BtWorkCtl *ctl) {
 		if (lane == 0 && x) atomicAdd(&P.stats[k], x);
 	}
 }
+
+/* ------------------------------------------------------------------------------------------- */
+/* Queue-driven search kernel (v5): contexts in shared memory, state-homogeneous warps.            */
+/* ------------------------------------------------------------------------------------------- */
+#define BT_QCAP 512                 /* ring capacity (power of two) >= contexts per block           */
+#define BT_NQ 3                     /* work queues: LF steps, chase steps, everything else          */
+enum { QF = 0, QC = 1, QR = 2 };
+
+struct BtQueues { uint32_t head[BT_NQ], tail[BT_NQ], live, pad; uint32_t item[BT_NQ][BT_QCAP]; };
+
+__device__ __forceinline__ uint32_t bt_class_of(uint32_t pc) { return pc == PC_LF ? QF : pc == PC_CHASE ? QC : QR; }
+
+/* One block = `nctx` read contexts (packed in shared memory) served by blockDim.x/32 worker warps.  A warp
+ * repeatedly takes up to 32 contexts of ONE class from that class's queue, loads them into registers,
+ * advances each by one fast transition (or one chain of rare transitions), stores them back and routes
+ * them to the queue of their new class.  Lanes of a warp therefore execute the same code, and no context
+ * ever waits for another one.  Reads come from the global cursor as before (ctl->next / ctl->nwork). */
+__global__ void __launch_bounds__(384, 1)
+bt_search_kernel_q(BtKParams P, BtWorkCtl *ctl, uint32_t nctx) {
+	extern __shared__ __align__(16) uint8_t bt_smem[];
+	BtQueues *Q = reinterpret_cast<BtQueues *>(bt_smem);
+	uint32_t *ctx = reinterpret_cast<uint32_t *>(bt_smem + sizeof(BtQueues));
+	uint8_t *stage0 = bt_smem + sizeof(BtQueues) + (size_t)BT_CTX_WORDS * nctx * 4;
+	const uint32_t lane = threadIdx.x & 31;
+	const unsigned long long nwork = ctl->nwork;
+	if (threadIdx.x == 0) {
+		for (int k = 0; k < BT_NQ; k++) { Q->head[k] = 0; Q->tail[k] = 0; }
+		Q->tail[QR] = nctx; Q->live = nctx;
+	}
+	for (uint32_t i = threadIdx.x; i < BT_NQ * BT_QCAP; i += blockDim.x) (&Q->item[0][0])[i] = 0;
+	__syncthreads();
+	for (uint32_t i = threadIdx.x; i < nctx; i += blockDim.x) {
+		Q->item[QR][i] = i + 1;
+		ctx[(size_t)26 * nctx + i] = PC_NEXT_READ;             /* word 26 holds pc in its low bits */
+		ctx[(size_t)25 * nctx + i] = 0;
+	}
+	__syncthreads();
+	BtLane L;
+	memset(&L, 0, sizeof L);
+	L.qualThresh = P.pol.mode == 0 ? 0xffffffffu : P.pol.qualThresh;
+	L.maxBts = P.pol.mode == 0 ? 0xffffffffu : P.pol.maxBts;
+	L.maqPenalty = P.pol.mode == 0 ? 1u : (uint32_t)P.pol.maqRound;
+	volatile uint32_t *vhead = Q->head, *vtail = Q->tail;
+	volatile uint32_t *vlive = &Q->live;
+	for (;;) {
+		/* pick the fullest queue (lane 0), reserve up to 32 entries */
+		int k = -1; uint32_t h = 0, n = 0;
+		if (lane == 0) {
+			for (;;) {
+				uint32_t best = 0; k = -1;
+				for (int q = 0; q < BT_NQ; q++) { uint32_t sz = vtail[q] - vhead[q]; if (sz > best) { best = sz; k = q; } }
+				if (k < 0) { if (*vlive == 0) { k = -2; } break; }
+				h = vhead[k]; uint32_t t = vtail[k];
+				n = t - h; if ((int32_t)n <= 0) continue;
+				if (n > 32) n = 32;
+				if (atomicCAS(&Q->head[k], h, h + n) == h) break;
+			}
+		}
+		k = __shfl_sync(0xffffffffu, k, 0); h = __shfl_sync(0xffffffffu, h, 0); n = __shfl_sync(0xffffffffu, n, 0);
+		if (k == -2) break;
+		if (k < 0) { __nanosleep(100); continue; }
+		const bool active = lane < n;
+		uint32_t id = 0;
+		if (active) {
+			volatile uint32_t *slot = &Q->item[k][(h + lane) & (BT_QCAP - 1)];
+			uint32_t v;
+			while ((v = *slot) == 0) { }                         /* the producer bumps tail before it writes the slot */
+			*slot = 0;
+			id = v - 1;
+		}
+		__threadfence_block();
+		uint32_t ncls = 0xffffffffu;                             /* class after this visit; none = context retired */
+		if (active) {
+			const uint32_t gid = blockIdx.x * nctx + id;
+			BtScratch S;
+			S.rows = P.rows + (size_t)gid * P.R * 2; S.elims = P.elims + (size_t)gid * P.R;
+			S.frames = P.frames + (size_t)gid * P.FCAP; S.partials = P.partials + (size_t)gid * P.PCAP;
+			bt_ctx_load(L, ctx, nctx, id);
+			if (L.rlen <= BT_SMEM_LEN) { L.rseq = stage0 + (size_t)id * BT_SMEM_STRIDE; L.rqual = L.rseq + BT_SMEM_LEN; }
+			else { L.rseq = P.stage + (size_t)gid * 2 * P.stage_len; L.rqual = L.rseq + P.stage_len; }
+			if (k != QR) bt_fast_iter(L, P, S);
+			else {
+				if (L.pc == PC_FINISH_READ) { bt_finish_read(L, P); L.pc = PC_NEXT_READ; }
+				if (L.pc == PC_NEXT_READ) {
+					const unsigned long long w = atomicAdd(&ctl->next, 1ull);
+					if (w < nwork) {
+						const uint32_t rid = P.sel ? P.sel[w] : (uint32_t)w;
+						bt_begin_read(L, P, rid);
+						const unsigned long long ro = P.roff[rid];
+						uint8_t *dst; uint32_t qoff;
+						if (L.rlen <= BT_SMEM_LEN) { dst = stage0 + (size_t)id * BT_SMEM_STRIDE; qoff = BT_SMEM_LEN; }
+						else { dst = P.stage + (size_t)gid * 2 * P.stage_len; qoff = P.stage_len; }
+						bool sawN = false;
+						for (uint32_t i = 0; i < L.rlen; i++) {
+							const uint8_t b = __ldg(P.seq + ro + i);
+							dst[i] = b; dst[qoff + i] = __ldg(P.qual + ro + i);
+							sawN |= (b == 4);
+						}
+						L.rseq = dst; L.rqual = dst + qoff; L.hasN = sawN;
+					} else L.pc = PC_EXIT;
+				}
+				if (BT_IS_RARE_STEP(L.pc)) bt_rare_iter(L, P, S);
+			}
+			if (L.pc != PC_EXIT) { ncls = bt_class_of(L.pc); bt_ctx_store(L, ctx, nctx, id); }
+		}
+		__threadfence_block();                                   /* context words visible before the id is published */
+		unsigned retired = __ballot_sync(0xffffffffu, active && ncls == 0xffffffffu);
+		if (retired && lane == 0) atomicSub(&Q->live, (uint32_t)__popc(retired));
+#pragma unroll
+		for (int q = 0; q < BT_NQ; q++) {
+			const unsigned m = __ballot_sync(0xffffffffu, ncls == (uint32_t)q);
+			if (m) {
+				uint32_t base = 0;
+				if (lane == 0) base = atomicAdd(&Q->tail[q], (uint32_t)__popc(m));
+				base = __shfl_sync(0xffffffffu, base, 0);
+				if (ncls == (uint32_t)q) Q->item[q][(base + (uint32_t)__popc(m & ((1u << lane) - 1u))) & (BT_QCAP - 1)] = id + 1;
+			}
+		}
+	}
+	/* statistics: warp-reduce, one atomic per warp and counter */
+	unsigned long long v[8] = { L.s_lfex, L.s_lf, L.s_chase, L.s_ftab, L.s_offs, L.s_bt, L.s_iter, L.s_blk };
+#pragma unroll
+	for (int kk = 0; kk < 8; kk++) {
+		unsigned long long x = v[kk];
+		for (int o = 16; o > 0; o >>= 1) x += __shfl_down_sync(0xffffffffu, x, o);
+		if (lane == 0 && x) atomicAdd(&P.stats[kk], x);
+	}
+}
+
+static size_t bt_q_smem(uint32_t nctx) { return sizeof(BtQueues) + (size_t)nctx * (BT_CTX_WORDS * 4 + BT_SMEM_STRIDE); }
 
 /* Appends to sel_out the reads (of the first n work items of sel_in / the identity) whose flags intersect `mask`;
  * ctl->nwork is the list length.  If `count_ctl` is set, the number of work items is read from it (device-sized lists). */
@@ -403,6 +540,7 @@ extern "C" int bt_index_load(const char *basename, int need_mirror, int device, 
 			int bps = 0;
 			if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bps, bt_search_kernel, BT_THREADS, BT_THREADS * BT_SMEM_STRIDE) != cudaSuccess || bps < 1) bps = 1;
 			ix->blocks_per_sm = bps;
+			if (cudaFuncSetAttribute(bt_search_kernel_q, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bt_q_smem(BT_Q_NCTX)) != cudaSuccess) rc = fail("cudaFuncSetAttribute(shared memory) failed");
 		}
 	}
 	if (!rc && (cudaMalloc((void **)&ix->stats, 8 * sizeof(unsigned long long)) != cudaSuccess ||
@@ -471,7 +609,7 @@ static int enqueue_align(bt_context *cx, const bt_policy_t *pol, const bt_read_b
 	if (nwork == 0) return 0;
 	if (maxlen < 1) maxlen = 1;
 	if (maxlen > 1023) return fail("bt_align: reads longer than 1023 bases are not supported (the reference's Hit::mms is a FixedBitset<1024>)");
-	const uint32_t nthreads = (uint32_t)ix->sms * (uint32_t)ix->blocks_per_sm * BT_THREADS;
+	const uint32_t nthreads = (uint32_t)ix->sms * BT_Q_NCTX;            /* contexts of the main pass: one block per SM */
 	const uint32_t stage_len = maxlen > BT_SMEM_LEN ? maxlen : 0;
 	if (ensure_ws(cx->ws1, nthreads, 6 * maxlen + 8, 8, 64, stage_len)) return 1;
 	const uint32_t nthreads_h = (uint32_t)ix->sms * BT_HEAVY_BLOCKS_PER_SM * 32;
@@ -501,10 +639,10 @@ static int enqueue_align(bt_context *cx, const bt_policy_t *pol, const bt_read_b
 	bt_ctl_set_kernel<<<1, 1, 0, st>>>(cx->ctl, nwork);
 	bt_ctl_set_kernel<<<1, 1, 0, st>>>(cx->ctl + 1, 0);
 	bt_ctl_set_kernel<<<1, 1, 0, st>>>(cx->ctl + 2, 0);
-	uint32_t grid = (uint32_t)ix->sms * (uint32_t)ix->blocks_per_sm;
-	const uint32_t need = (nwork + BT_THREADS - 1) / BT_THREADS;
+	uint32_t grid = (uint32_t)ix->sms;
+	const uint32_t need = (nwork + BT_Q_NCTX - 1) / BT_Q_NCTX;
 	if (grid > need) grid = need;
-	bt_search_kernel<<<grid, BT_THREADS, BT_THREADS * BT_SMEM_STRIDE, st>>>(P, cx->ctl);
+	bt_search_kernel_q<<<grid, BT_Q_THREADS, bt_q_smem(BT_Q_NCTX), st>>>(P, cx->ctl, BT_Q_NCTX);
 	bt_collect_kernel<<<cblocks, 256, 0, st>>>(out->flags, in->sel, nwork, nullptr, BT_FLAG_BUDGET, cx->heavy_sel, cx->ctl + 1);
 	bt_collect_kernel<<<cblocks, 256, 0, st>>>(out->flags, in->sel, nwork, nullptr, BT_FLAG_SCRATCH_OVF, cx->retry_sel, cx->ctl + 2);
 	CUDA_TRY(cudaEventRecord(cx->ev_main, st));
@@ -512,11 +650,11 @@ static int enqueue_align(bt_context *cx, const bt_policy_t *pol, const bt_read_b
 	CUDA_TRY(cudaStreamWaitEvent(cx->side, cx->ev_main, 0));
 	P.sel = cx->heavy_sel; P.budget = 0;
 	set_ws(P, cx->wsh);
-	bt_search_kernel<<<ix->sms * BT_HEAVY_BLOCKS_PER_SM, 32, 32 * BT_SMEM_STRIDE, cx->side>>>(P, cx->ctl + 1);
+	bt_search_kernel_q<<<ix->sms * BT_HEAVY_BLOCKS_PER_SM, 32, bt_q_smem(32), cx->side>>>(P, cx->ctl + 1, 32);
 	bt_collect_kernel<<<cblocks, 256, 0, cx->side>>>(out->flags, cx->heavy_sel, nwork, cx->ctl + 1, BT_FLAG_SCRATCH_OVF, cx->retry_sel, cx->ctl + 2);
 	P.sel = cx->retry_sel;
 	set_ws(P, cx->ws2);
-	bt_search_kernel<<<ix->sms, 32, 32 * BT_SMEM_STRIDE, cx->side>>>(P, cx->ctl + 2);
+	bt_search_kernel_q<<<ix->sms, 32, bt_q_smem(32), cx->side>>>(P, cx->ctl + 2, 32);
 	CUDA_TRY(cudaGetLastError());
 	return 0;
 }
