@@ -61,7 +61,7 @@ __global__ void bt_debug_lf_kernel(BtDevIndex ix, const uint32_t *rows, uint32_t
 #define BT_RARE_THRESH 24          /* ... or as soon as this many lanes of the warp wait for one          */
 #endif
 #ifndef BT_Q_NCTX
-#define BT_Q_NCTX 384               /* read contexts per block of the queue-driven kernel                    */
+#define BT_Q_NCTX 1024              /* read contexts per block of the queue-driven kernel                    */
 #endif
 #ifndef BT_Q_THREADS
 #define BT_Q_THREADS 384            /* worker threads per block                                               */
@@ -176,7 +176,7 @@ bt_search_kernel(BtKParams P, BtWorkCtl *ctl) {
 /* ------------------------------------------------------------------------------------------- */
 /* Queue-driven search kernel (v5): contexts in shared memory, state-homogeneous warps.            */
 /* ------------------------------------------------------------------------------------------- */
-#define BT_QCAP 512                 /* ring capacity (power of two) >= contexts per block           */
+#define BT_QCAP 1024                /* ring capacity (power of two) >= contexts per block           */
 #define BT_NQ 3                     /* work queues: LF steps, chase steps, everything else          */
 enum { QF = 0, QC = 1, QR = 2 };
 
@@ -194,7 +194,6 @@ bt_search_kernel_q(BtKParams P, BtWorkCtl *ctl, uint32_t nctx) {
 	extern __shared__ __align__(16) uint8_t bt_smem[];
 	BtQueues *Q = reinterpret_cast<BtQueues *>(bt_smem);
 	uint32_t *ctx = reinterpret_cast<uint32_t *>(bt_smem + sizeof(BtQueues));
-	uint8_t *stage0 = bt_smem + sizeof(BtQueues) + (size_t)BT_CTX_WORDS * nctx * 4;
 	const uint32_t lane = threadIdx.x & 31;
 	const unsigned long long nwork = ctl->nwork;
 	if (threadIdx.x == 0) {
@@ -222,7 +221,7 @@ bt_search_kernel_q(BtKParams P, BtWorkCtl *ctl, uint32_t nctx) {
 		if (lane == 0) {
 			for (;;) {
 				uint32_t best = 0; k = -1;
-				for (int q = 0; q < BT_NQ; q++) { uint32_t sz = vtail[q] - vhead[q]; if (sz > best) { best = sz; k = q; } }
+				for (int q = 0; q < BT_NQ; q++) { uint32_t sz = vtail[q] - vhead[q]; if ((int32_t)sz > (int32_t)best) { best = sz; k = q; } }
 				if (k < 0) { if (*vlive == 0) { k = -2; } break; }
 				h = vhead[k]; uint32_t t = vtail[k];
 				n = t - h; if ((int32_t)n <= 0) continue;
@@ -250,8 +249,7 @@ bt_search_kernel_q(BtKParams P, BtWorkCtl *ctl, uint32_t nctx) {
 			S.rows = P.rows + (size_t)gid * P.R * 2; S.elims = P.elims + (size_t)gid * P.R;
 			S.frames = P.frames + (size_t)gid * P.FCAP; S.partials = P.partials + (size_t)gid * P.PCAP;
 			bt_ctx_load(L, ctx, nctx, id);
-			if (L.rlen <= BT_SMEM_LEN) { L.rseq = stage0 + (size_t)id * BT_SMEM_STRIDE; L.rqual = L.rseq + BT_SMEM_LEN; }
-			else { L.rseq = P.stage + (size_t)gid * 2 * P.stage_len; L.rqual = L.rseq + P.stage_len; }
+			L.rseq = P.stage + (size_t)gid * 2 * P.stage_len; L.rqual = L.rseq + P.stage_len;   /* the context's writable copy of its read */
 			if (k != QR) bt_fast_iter(L, P, S);
 			else {
 				if (L.pc == PC_FINISH_READ) { bt_finish_read(L, P); L.pc = PC_NEXT_READ; }
@@ -261,9 +259,7 @@ bt_search_kernel_q(BtKParams P, BtWorkCtl *ctl, uint32_t nctx) {
 						const uint32_t rid = P.sel ? P.sel[w] : (uint32_t)w;
 						bt_begin_read(L, P, rid);
 						const unsigned long long ro = P.roff[rid];
-						uint8_t *dst; uint32_t qoff;
-						if (L.rlen <= BT_SMEM_LEN) { dst = stage0 + (size_t)id * BT_SMEM_STRIDE; qoff = BT_SMEM_LEN; }
-						else { dst = P.stage + (size_t)gid * 2 * P.stage_len; qoff = P.stage_len; }
+						uint8_t *dst = P.stage + (size_t)gid * 2 * P.stage_len; const uint32_t qoff = P.stage_len;
 						bool sawN = false;
 						for (uint32_t i = 0; i < L.rlen; i++) {
 							const uint8_t b = __ldg(P.seq + ro + i);
@@ -301,7 +297,7 @@ bt_search_kernel_q(BtKParams P, BtWorkCtl *ctl, uint32_t nctx) {
 	}
 }
 
-static size_t bt_q_smem(uint32_t nctx) { return sizeof(BtQueues) + (size_t)nctx * (BT_CTX_WORDS * 4 + BT_SMEM_STRIDE); }
+static size_t bt_q_smem(uint32_t nctx) { return sizeof(BtQueues) + (size_t)nctx * BT_CTX_WORDS * 4; }
 
 /* Appends to sel_out the reads (of the first n work items of sel_in / the identity) whose flags intersect `mask`;
  * ctl->nwork is the list length.  If `count_ctl` is set, the number of work items is read from it (device-sized lists). */
@@ -610,7 +606,7 @@ static int enqueue_align(bt_context *cx, const bt_policy_t *pol, const bt_read_b
 	if (maxlen < 1) maxlen = 1;
 	if (maxlen > 1023) return fail("bt_align: reads longer than 1023 bases are not supported (the reference's Hit::mms is a FixedBitset<1024>)");
 	const uint32_t nthreads = (uint32_t)ix->sms * BT_Q_NCTX;            /* contexts of the main pass: one block per SM */
-	const uint32_t stage_len = maxlen > BT_SMEM_LEN ? maxlen : 0;
+	const uint32_t stage_len = (maxlen + 15) & ~15u;                     /* every context keeps a writable copy of its read */
 	if (ensure_ws(cx->ws1, nthreads, 6 * maxlen + 8, 8, 64, stage_len)) return 1;
 	const uint32_t nthreads_h = (uint32_t)ix->sms * BT_HEAVY_BLOCKS_PER_SM * 32;
 	if (ensure_ws(cx->wsh, nthreads_h, 6 * maxlen + 8, 8, 64, stage_len)) return 1;
