@@ -177,19 +177,35 @@ bt_search_kernel(BtKParams P, BtWorkCtl *ctl) {
 /* Queue-driven search kernel (v5): contexts in shared memory, state-homogeneous warps.            */
 /* ------------------------------------------------------------------------------------------- */
 #define BT_QCAP 1024                /* ring capacity (power of two) >= contexts per block           */
-#define BT_NQ 3                     /* work queues: LF steps, chase steps, everything else          */
-enum { QF = 0, QC = 1, QR = 2 };
+#define BT_NQ 8                     /* work queues, one per class of state                          */
+enum { QF = 0, QC = 1, QPH = 2, QPOS = 3, QBT = 4, QRET = 5, QREP = 6, QIO = 7 };
 
 struct BtQueues { uint32_t head[BT_NQ], tail[BT_NQ], live, pad; uint32_t item[BT_NQ][BT_QCAP]; };
 
-__device__ __forceinline__ uint32_t bt_class_of(uint32_t pc) { return pc == PC_LF ? QF : pc == PC_CHASE ? QC : QR; }
+/* Classes group the states whose code a warp can execute together:
+ *   QF   one query position (LF step)            QC   one locate step
+ *   QPH  phase program, backtrack() entry/exit   QPOS frame entry, position prologue with its own loads
+ *   QBT  backtrack-target selection + push       QRET frame pop, bookkeeping after a recursive call
+ *   QREP reporting (alignment, rows, resolve)    QIO  finishing a read, fetching the next one          */
+__device__ __forceinline__ uint32_t bt_class_of(uint32_t pc) {
+	switch (pc) {
+	case PC_LF: return QF;
+	case PC_CHASE: return QC;
+	case PC_PHASE: case PC_BT_BEGIN: case PC_BT_END: return QPH;
+	case PC_FRAME_ENTER: case PC_POS: case PC_POS_END: return QPOS;
+	case PC_BTLOOP: return QBT;
+	case PC_FRAME_RET: case PC_CHILD_RET: return QRET;
+	case PC_REPORT: case PC_REPORT_ROW: case PC_RESOLVE: case PC_REPORT_RET: return QREP;
+	default: return QIO;
+	}
+}
 
 /* One block = `nctx` read contexts (packed in shared memory) served by blockDim.x/32 worker warps.  A warp
  * repeatedly takes up to 32 contexts of ONE class from that class's queue, loads them into registers,
  * advances each by one fast transition (or one chain of rare transitions), stores them back and routes
  * them to the queue of their new class.  Lanes of a warp therefore execute the same code, and no context
  * ever waits for another one.  Reads come from the global cursor as before (ctl->next / ctl->nwork). */
-__global__ void __launch_bounds__(384, 1)
+__global__ void __launch_bounds__(BT_Q_THREADS, 1)
 bt_search_kernel_q(BtKParams P, BtWorkCtl *ctl, uint32_t nctx) {
 	extern __shared__ __align__(16) uint8_t bt_smem[];
 	BtQueues *Q = reinterpret_cast<BtQueues *>(bt_smem);
@@ -198,12 +214,12 @@ bt_search_kernel_q(BtKParams P, BtWorkCtl *ctl, uint32_t nctx) {
 	const unsigned long long nwork = ctl->nwork;
 	if (threadIdx.x == 0) {
 		for (int k = 0; k < BT_NQ; k++) { Q->head[k] = 0; Q->tail[k] = 0; }
-		Q->tail[QR] = nctx; Q->live = nctx;
+		Q->tail[QIO] = nctx; Q->live = nctx;
 	}
 	for (uint32_t i = threadIdx.x; i < BT_NQ * BT_QCAP; i += blockDim.x) (&Q->item[0][0])[i] = 0;
 	__syncthreads();
 	for (uint32_t i = threadIdx.x; i < nctx; i += blockDim.x) {
-		Q->item[QR][i] = i + 1;
+		Q->item[QIO][i] = i + 1;
 		ctx[(size_t)26 * nctx + i] = PC_NEXT_READ;             /* word 26 holds pc in its low bits */
 		ctx[(size_t)25 * nctx + i] = 0;
 	}
@@ -250,8 +266,8 @@ bt_search_kernel_q(BtKParams P, BtWorkCtl *ctl, uint32_t nctx) {
 			S.frames = P.frames + (size_t)gid * P.FCAP; S.partials = P.partials + (size_t)gid * P.PCAP;
 			bt_ctx_load(L, ctx, nctx, id);
 			L.rseq = P.stage + (size_t)gid * 2 * P.stage_len; L.rqual = L.rseq + P.stage_len;   /* the context's writable copy of its read */
-			if (k != QR) bt_fast_iter(L, P, S);
-			else {
+			if (k == QF || k == QC) bt_fast_iter(L, P, S);
+			else if (k == QIO) {
 				if (L.pc == PC_FINISH_READ) { bt_finish_read(L, P); L.pc = PC_NEXT_READ; }
 				if (L.pc == PC_NEXT_READ) {
 					const unsigned long long w = atomicAdd(&ctl->next, 1ull);
@@ -269,7 +285,15 @@ bt_search_kernel_q(BtKParams P, BtWorkCtl *ctl, uint32_t nctx) {
 						L.rseq = dst; L.rqual = dst + qoff; L.hasN = sawN;
 					} else L.pc = PC_EXIT;
 				}
-				if (BT_IS_RARE_STEP(L.pc)) bt_rare_iter(L, P, S);
+			} else {
+				/* rare transitions, chained while the context stays in this class */
+#pragma unroll 1
+				for (int c = 0; c < BT_RARE_CHAIN && bt_class_of(L.pc) == (uint32_t)k; c++) {
+					if (L.flags & BT_FLAG_SCRATCH_OVF) { L.pc = PC_FINISH_READ; break; }
+					if (P.budget && L.nit > P.budget) { L.flags |= BT_FLAG_BUDGET; L.pc = PC_FINISH_READ; break; }
+					L.s_iter++; L.nit++;
+					bt_rare_step(L, P, S);
+				}
 			}
 			if (L.pc != PC_EXIT) { ncls = bt_class_of(L.pc); bt_ctx_store(L, ctx, nctx, id); }
 		}
