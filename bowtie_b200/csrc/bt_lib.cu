@@ -610,6 +610,18 @@ static int check_policy(const bt_index_t *ix, const bt_policy_t *pol) {
 #ifndef BT_MAIN_BUDGET
 #define BT_MAIN_BUDGET 24000u      /* transitions a read may take in the main pass before it is moved to the heavy pass */
 #endif
+/* Main-pass kernel: thread-per-lane (default) or the queue-driven kernel (BT_MAIN_KERNEL=q, experimental). */
+static uint32_t main_budget() {
+	static long v = -1;
+	if (v < 0) { const char *e = getenv("BT_MAIN_BUDGET"); v = e ? atol(e) : (long)BT_MAIN_BUDGET; }
+	return (uint32_t)v;
+}
+static bool main_kernel_is_queue() {
+	static int v = -1;
+	if (v < 0) { const char *e = getenv("BT_MAIN_KERNEL"); v = (e && e[0] == 'q') ? 1 : 0; }
+	return v == 1;
+}
+
 #define BT_HEAVY_BLOCKS_PER_SM 8   /* heavy pass: 32-thread blocks, so finished warps free their slots */
 
 static void set_ws(BtKParams &P, const Workspace &w) {
@@ -629,7 +641,7 @@ static int enqueue_align(bt_context *cx, const bt_policy_t *pol, const bt_read_b
 	if (nwork == 0) return 0;
 	if (maxlen < 1) maxlen = 1;
 	if (maxlen > 1023) return fail("bt_align: reads longer than 1023 bases are not supported (the reference's Hit::mms is a FixedBitset<1024>)");
-	const uint32_t nthreads = (uint32_t)ix->sms * BT_Q_NCTX;            /* contexts of the main pass: one block per SM */
+	const uint32_t nthreads = main_kernel_is_queue() ? (uint32_t)ix->sms * BT_Q_NCTX : (uint32_t)ix->sms * (uint32_t)ix->blocks_per_sm * BT_THREADS;
 	const uint32_t stage_len = (maxlen + 15) & ~15u;                     /* every context keeps a writable copy of its read */
 	if (ensure_ws(cx->ws1, nthreads, 6 * maxlen + 8, 8, 64, stage_len)) return 1;
 	const uint32_t nthreads_h = (uint32_t)ix->sms * BT_HEAVY_BLOCKS_PER_SM * 32;
@@ -655,14 +667,21 @@ static int enqueue_align(bt_context *cx, const bt_policy_t *pol, const bt_read_b
 	CUDA_TRY(cudaStreamWaitEvent(st, cx->ev_tail, 0));
 	/* main pass */
 	set_ws(P, cx->ws1);
-	P.budget = BT_MAIN_BUDGET;
+	P.budget = main_budget();
 	bt_ctl_set_kernel<<<1, 1, 0, st>>>(cx->ctl, nwork);
 	bt_ctl_set_kernel<<<1, 1, 0, st>>>(cx->ctl + 1, 0);
 	bt_ctl_set_kernel<<<1, 1, 0, st>>>(cx->ctl + 2, 0);
-	uint32_t grid = (uint32_t)ix->sms;
-	const uint32_t need = (nwork + BT_Q_NCTX - 1) / BT_Q_NCTX;
-	if (grid > need) grid = need;
-	bt_search_kernel_q<<<grid, BT_Q_THREADS, bt_q_smem(BT_Q_NCTX), st>>>(P, cx->ctl, BT_Q_NCTX);
+	if (main_kernel_is_queue()) {
+		uint32_t grid = (uint32_t)ix->sms;
+		const uint32_t need = (nwork + BT_Q_NCTX - 1) / BT_Q_NCTX;
+		if (grid > need) grid = need;
+		bt_search_kernel_q<<<grid, BT_Q_THREADS, bt_q_smem(BT_Q_NCTX), st>>>(P, cx->ctl, BT_Q_NCTX);
+	} else {
+		uint32_t grid = (uint32_t)ix->sms * (uint32_t)ix->blocks_per_sm;
+		const uint32_t need = (nwork + BT_THREADS - 1) / BT_THREADS;
+		if (grid > need) grid = need;
+		bt_search_kernel<<<grid, BT_THREADS, BT_THREADS * BT_SMEM_STRIDE, st>>>(P, cx->ctl);
+	}
 	bt_collect_kernel<<<cblocks, 256, 0, st>>>(out->flags, in->sel, nwork, nullptr, BT_FLAG_BUDGET, cx->heavy_sel, cx->ctl + 1);
 	bt_collect_kernel<<<cblocks, 256, 0, st>>>(out->flags, in->sel, nwork, nullptr, BT_FLAG_SCRATCH_OVF, cx->retry_sel, cx->ctl + 2);
 	CUDA_TRY(cudaEventRecord(cx->ev_main, st));
@@ -670,11 +689,11 @@ static int enqueue_align(bt_context *cx, const bt_policy_t *pol, const bt_read_b
 	CUDA_TRY(cudaStreamWaitEvent(cx->side, cx->ev_main, 0));
 	P.sel = cx->heavy_sel; P.budget = 0;
 	set_ws(P, cx->wsh);
-	bt_search_kernel_q<<<ix->sms * BT_HEAVY_BLOCKS_PER_SM, 32, bt_q_smem(32), cx->side>>>(P, cx->ctl + 1, 32);
+	bt_search_kernel<<<ix->sms * BT_HEAVY_BLOCKS_PER_SM, 32, 32 * BT_SMEM_STRIDE, cx->side>>>(P, cx->ctl + 1);   /* latency matters here: thread-per-lane kernel */
 	bt_collect_kernel<<<cblocks, 256, 0, cx->side>>>(out->flags, cx->heavy_sel, nwork, cx->ctl + 1, BT_FLAG_SCRATCH_OVF, cx->retry_sel, cx->ctl + 2);
 	P.sel = cx->retry_sel;
 	set_ws(P, cx->ws2);
-	bt_search_kernel_q<<<ix->sms, 32, bt_q_smem(32), cx->side>>>(P, cx->ctl + 2, 32);
+	bt_search_kernel<<<ix->sms, 32, 32 * BT_SMEM_STRIDE, cx->side>>>(P, cx->ctl + 2);
 	CUDA_TRY(cudaGetLastError());
 	return 0;
 }
