@@ -608,7 +608,7 @@ static int check_policy(const bt_index_t *ix, const bt_policy_t *pol) {
 
 /* Enqueue first pass + collect + retry pass.  All pointers are device pointers. `maxlen` bounds the read length. */
 #ifndef BT_MAIN_BUDGET
-#define BT_MAIN_BUDGET 24000u      /* transitions a read may take in the main pass before it is moved to the heavy pass */
+#define BT_MAIN_BUDGET 8000u       /* transitions a read may take in the main pass before it is moved to the heavy pass */
 #endif
 /* Main-pass kernel: thread-per-lane (default) or the queue-driven kernel (BT_MAIN_KERNEL=q, experimental). */
 static uint32_t main_budget() {

@@ -3,7 +3,7 @@ on the same inputs.  Bit-exact: every hit field, mismatch list, per-read counts 
 import numpy as np
 import pytest
 
-from helpers import FIXTURES, Policy, decode_device_result, results_equal
+from helpers import FIXTURES, ROOT as ROOT_DIR, Policy, decode_device_result, results_equal
 
 pytestmark = pytest.mark.gpu
 
@@ -157,3 +157,68 @@ def test_gpu_large_batch_properties(ecoli_ix, oracle, ecoli_base):
     ok, why = results_equal(a, b)
     assert ok, why
     assert r1.counters[0] > 0.9 * len(batch)
+
+
+def test_gpu_concurrent_contexts_match_single(ecoli_ix, oracle, ecoli_base):
+    """Four batches in flight on four contexts / CUDA streams (the pipelined form bench.py uses) give exactly the
+    results of the synchronous entry point, and reads that exceed the main-pass budget come back through the
+    heavy pass with the same answers."""
+    import torch
+    import bowtie_b200
+    from synth import synth_reads
+    genome = [(">e", open(FIXTURES / "NC_008253.fna", "rb").read().split(b"\n", 1)[1].replace(b"\n", b""))]
+    pol = Policy(mode=1, mms=2, khits=2)
+    dpol = to_dev(pol)
+    batches = [synth_reads(genome, 20000, 100, seed=100 + i, sub_rate=0.02, qual_profile="mixed") for i in range(4)]
+    want = [gpu_align(ecoli_ix, b, pol, slots=2, mm_cap=8) for b in batches]
+    ctxs = [bowtie_b200.Context(ecoli_ix) for _ in range(4)]
+    streams = [torch.cuda.Stream() for _ in range(4)]
+    dev, outs = [], []
+    for b in batches:
+        dev.append([torch.from_numpy(np.ascontiguousarray(a)).cuda() for a in (b.seq_codes, b.qual_cat, b.offs.view(np.int64), b.seeds.view(np.int32))])
+        n = len(b)
+        outs.append((torch.zeros(n, dtype=torch.int32, device="cuda"), torch.zeros(n, dtype=torch.int32, device="cuda"),
+                     torch.zeros(n * 2 * 13, dtype=torch.int32, device="cuda")))
+    torch.cuda.synchronize()
+    for rep in range(2):
+        for i in range(4):
+            d, o = dev[i], outs[i]
+            ctxs[i].align_device(d[0].data_ptr(), d[1].data_ptr(), d[2].data_ptr(), d[3].data_ptr(), len(batches[i]), 100, dpol,
+                                 o[0].data_ptr(), o[1].data_ptr(), o[2].data_ptr(), 2, 8, streams[i].cuda_stream)
+    for i in range(4):
+        ctxs[i].join(streams[i].cuda_stream)
+    torch.cuda.synchronize()
+    for i in range(4):
+        found = outs[i][0].cpu().numpy().view(np.uint32)
+        flags = outs[i][1].cpu().numpy().view(np.uint32)
+        hits = outs[i][2].cpu().numpy().view(np.uint32)
+        assert not flags.any()
+        got = decode_device_result(found, hits, 2, 8, pol)
+        ok, why = results_equal(want[i], got)
+        assert ok, (i, why)
+    for c in ctxs:
+        c.close()
+
+
+def test_gpu_heavy_pass_is_exact(ecoli_base, oracle, ecoli_reads):
+    """With a main-pass budget of 40 transitions nearly every read is finished by the heavy pass; results unchanged.
+    (Runs in a subprocess because the budget is read once per process.)"""
+    import subprocess, sys, json
+    code = """
+import sys, json, numpy as np
+sys.path.insert(0, %r); sys.path.insert(0, %r)
+import bowtie_b200
+from helpers import parse_fastq, FIXTURES, Policy, decode_device_result, md5, render_default, load_refnames
+ix = bowtie_b200.Index(str(FIXTURES / 'e_coli'))
+b = parse_fastq(FIXTURES / 'e_coli_1000.fq')
+pol = Policy(mode=1, mms=2)
+f, g, h = ix.align(b.seq_codes, b.qual_cat, b.offs, b.seeds, bowtie_b200.Policy(**pol.__dict__), slots=1, mm_cap=8)
+assert not g.any()
+res = decode_device_result(f, h.reshape(-1), 1, 8, pol)
+print(md5(render_default(b, res, load_refnames(FIXTURES / 'e_coli'))))
+""" % (str(ROOT_DIR), str(ROOT_DIR / "tests"))
+    import os
+    env = dict(os.environ, BT_MAIN_BUDGET="40")
+    p = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, env=env)
+    assert p.returncode == 0, p.stderr
+    assert p.stdout.strip() == "7238b0f529dfcdf602f82ae1a754a1bd"      # golden md5 of the reference binary for -n 2 (SURVEY §8c)
