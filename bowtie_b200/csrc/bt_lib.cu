@@ -610,18 +610,29 @@ static int check_policy(const bt_index_t *ix, const bt_policy_t *pol) {
 #ifndef BT_MAIN_BUDGET
 #define BT_MAIN_BUDGET 8000u       /* transitions a read may take in the main pass before it is moved to the heavy pass */
 #endif
-/* Main-pass kernel: thread-per-lane (default) or the queue-driven kernel (BT_MAIN_KERNEL=q, experimental). */
+/* Main / heavy pass kernels: queue-driven (default) or thread-per-lane (BT_MAIN_KERNEL=t / BT_HEAVY_KERNEL=t). */
 static uint32_t main_budget() {
 	static long v = -1;
 	if (v < 0) { const char *e = getenv("BT_MAIN_BUDGET"); v = e ? atol(e) : (long)BT_MAIN_BUDGET; }
 	return (uint32_t)v;
 }
+static bool heavy_kernel_is_queue() {
+	static int v = -1;
+	if (v < 0) { const char *e = getenv("BT_HEAVY_KERNEL"); v = (e && e[0] == 't') ? 0 : 1; }
+	return v == 1;
+}
+static uint32_t heavy_budget() {
+	static long v = -1;
+	if (v < 0) { const char *e = getenv("BT_HEAVY_BUDGET"); v = e ? atol(e) : 200000l; }
+	return (uint32_t)v;
+}
 static bool main_kernel_is_queue() {
 	static int v = -1;
-	if (v < 0) { const char *e = getenv("BT_MAIN_KERNEL"); v = (e && e[0] == 'q') ? 1 : 0; }
+	if (v < 0) { const char *e = getenv("BT_MAIN_KERNEL"); v = (e && e[0] == 't') ? 0 : 1; }
 	return v == 1;
 }
 
+#define BT_HEAVY_NCTX 256           /* heavy pass, queue kernel: contexts per block (one block per SM)        */
 #define BT_HEAVY_BLOCKS_PER_SM 8   /* heavy pass: 32-thread blocks, so finished warps free their slots */
 
 static void set_ws(BtKParams &P, const Workspace &w) {
@@ -689,8 +700,16 @@ static int enqueue_align(bt_context *cx, const bt_policy_t *pol, const bt_read_b
 	CUDA_TRY(cudaStreamWaitEvent(cx->side, cx->ev_main, 0));
 	P.sel = cx->heavy_sel; P.budget = 0;
 	set_ws(P, cx->wsh);
-	bt_search_kernel<<<ix->sms * BT_HEAVY_BLOCKS_PER_SM, 32, 32 * BT_SMEM_STRIDE, cx->side>>>(P, cx->ctl + 1);   /* latency matters here: thread-per-lane kernel */
-	bt_collect_kernel<<<cblocks, 256, 0, cx->side>>>(out->flags, cx->heavy_sel, nwork, cx->ctl + 1, BT_FLAG_SCRATCH_OVF, cx->retry_sel, cx->ctl + 2);
+	if (heavy_kernel_is_queue()) {
+		/* heavy reads are ~1 % of the reads but ~45 % of the work: run them SIMT-efficiently too; the handful that exceed
+		 * the second budget (sequential searches of 10^5..10^6 transitions) finish in the last pass, where latency matters */
+		P.budget = heavy_budget();
+		bt_search_kernel_q<<<ix->sms, BT_Q_THREADS, bt_q_smem(BT_HEAVY_NCTX), cx->side>>>(P, cx->ctl + 1, BT_HEAVY_NCTX);
+		P.budget = 0;
+	} else {
+		bt_search_kernel<<<ix->sms * BT_HEAVY_BLOCKS_PER_SM, 32, 32 * BT_SMEM_STRIDE, cx->side>>>(P, cx->ctl + 1);
+	}
+	bt_collect_kernel<<<cblocks, 256, 0, cx->side>>>(out->flags, cx->heavy_sel, nwork, cx->ctl + 1, BT_FLAG_RETRY, cx->retry_sel, cx->ctl + 2);
 	P.sel = cx->retry_sel;
 	set_ws(P, cx->ws2);
 	bt_search_kernel<<<ix->sms, 32, 32 * BT_SMEM_STRIDE, cx->side>>>(P, cx->ctl + 2);
