@@ -610,7 +610,8 @@ static int check_policy(const bt_index_t *ix, const bt_policy_t *pol) {
 #ifndef BT_MAIN_BUDGET
 #define BT_MAIN_BUDGET 8000u       /* transitions a read may take in the main pass before it is moved to the heavy pass */
 #endif
-/* Main / heavy pass kernels: queue-driven (default) or thread-per-lane (BT_MAIN_KERNEL=t / BT_HEAVY_KERNEL=t). */
+/* Main / heavy pass kernels: thread-per-lane (default) or the experimental queue-driven kernel
+ * (BT_MAIN_KERNEL=q / BT_HEAVY_KERNEL=q; see DESIGN.md §4.2 for the measurements that decided the default). */
 static uint32_t main_budget() {
 	static long v = -1;
 	if (v < 0) { const char *e = getenv("BT_MAIN_BUDGET"); v = e ? atol(e) : (long)BT_MAIN_BUDGET; }
@@ -618,17 +619,17 @@ static uint32_t main_budget() {
 }
 static bool heavy_kernel_is_queue() {
 	static int v = -1;
-	if (v < 0) { const char *e = getenv("BT_HEAVY_KERNEL"); v = (e && e[0] == 't') ? 0 : 1; }
+	if (v < 0) { const char *e = getenv("BT_HEAVY_KERNEL"); v = (e && e[0] == 'q') ? 1 : 0; }
 	return v == 1;
 }
 static uint32_t heavy_budget() {
 	static long v = -1;
-	if (v < 0) { const char *e = getenv("BT_HEAVY_BUDGET"); v = e ? atol(e) : 200000l; }
+	if (v < 0) { const char *e = getenv("BT_HEAVY_BUDGET"); v = e ? atol(e) : 50000l; }
 	return (uint32_t)v;
 }
 static bool main_kernel_is_queue() {
 	static int v = -1;
-	if (v < 0) { const char *e = getenv("BT_MAIN_KERNEL"); v = (e && e[0] == 't') ? 0 : 1; }
+	if (v < 0) { const char *e = getenv("BT_MAIN_KERNEL"); v = (e && e[0] == 'q') ? 1 : 0; }
 	return v == 1;
 }
 
