@@ -210,11 +210,14 @@ struct Reader {
 		return (unsigned char)buf[pos++];
 	}
 	int peek_() { int c = getc_(); if (c >= 0) pos--; return c; }
+	bool line_hit_eof = false;        /* the last getline_ ended at EOF instead of a newline */
 	bool getline_(std::string &s) {   /* returns false at EOF with nothing read; strips \n, keeps \r handling to callers */
 		s.clear();
+		line_hit_eof = false;
 		int c = getc_();
-		if (c < 0) return false;
+		if (c < 0) { line_hit_eof = true; return false; }
 		while (c >= 0 && c != '\n') { s.push_back((char)c); c = getc_(); }
+		if (c < 0) line_hit_eof = true;
 		return true;
 	}
 	char to_phred33(int c, const std::string &name) const {
@@ -273,6 +276,7 @@ struct Reader {
 				while (!l4.empty() && l4.back() == '\r') l4.pop_back();
 				r.name = l1.substr(1);
 				int t5, t3; finish_seq(r, l2, t5, t3);
+				if (l4.empty()) die("Saw ASCII character 10 but expected 33-based Phred qual.");   /* pat.cpp:926: the first quality character is converted unconditionally */
 				r.qual.clear();
 				int nq = 0;
 				for (char ch : l4) { char pc = to_phred33((unsigned char)ch, r.name); if (nq++ >= t5) r.qual.push_back(pc); }
@@ -291,6 +295,9 @@ struct Reader {
 				while (c == '\r' || c == '\n') { getc_(); c = peek_(); }
 				if (c < 0 || c == '>') { if (c < 0) { gzclose(f); f = NULL; } continue; }      /* FASTA ended prematurely */
 				getline_(l2);
+				/* FastaPatternSource::parse stops at `cur < buflen` before it appends the character it just fetched
+				 * (pat.cpp:607-619): a sequence line that ends at EOF without a newline loses its last character */
+				if (line_hit_eof && !l2.empty()) l2.pop_back();
 				int t5, t3; finish_seq(r, l2, t5, t3);
 				r.qual.assign(r.seq.size(), 'I');
 				/* skip continuation lines up to the next record */
