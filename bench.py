@@ -180,8 +180,8 @@ def main() -> None:
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--reads-per-step", type=int, default=int(os.environ.get("BT_BENCH_READS", 2_000_000)))
-    ap.add_argument("--streams", type=int, default=int(os.environ.get("BT_BENCH_STREAMS", 4)),
+    ap.add_argument("--reads-per-step", type=int, default=int(os.environ.get("BT_BENCH_READS", 4_000_000)))
+    ap.add_argument("--streams", type=int, default=int(os.environ.get("BT_BENCH_STREAMS", 8)),
                     help="batches kept in flight (one bt_context_t + CUDA stream each), like the reference's -p worker threads")
     ap.add_argument("--cpu-sample", type=int, default=int(os.environ.get("BT_BENCH_CPU_SAMPLE", 1_000_000)))
     args = ap.parse_args()
@@ -232,7 +232,7 @@ def main() -> None:
     B, L, slots, mm_cap = args.reads_per_step, READ_LEN, 1, 7
     rw = bowtie_b200.BT_HIT_HDR_WORDS + mm_cap
     genome = load_genome(base)
-    # two distinct batches per rank, alternated, each larger than L2 (2M reads x 200 B = 400 MB)
+    # two distinct batches per rank, alternated, each larger than L2 (4M reads x 200 B = 800 MB)
     host = [make_reads(genome, B, seed=12345 + 1000 * rank + k) for k in range(2)]
     dev = [tuple(torch.from_numpy(np.ascontiguousarray(a)).cuda() for a in (h[0], h[1], h[2].view(np.int64), h[3].view(np.int32))) for h in host]
     NS = max(1, min(args.streams, args.steps))
@@ -358,7 +358,7 @@ def main() -> None:
         "dtype": "u32", "data": "synthetic",
         "config": {"workload": cfg_workload, "reads_per_step_per_gpu": B, "index_len_bp": ix.len, "index_device_bytes": ix.device_bytes,
                    "parallelism": f"reads sharded over {world} GPU(s), full index per GPU; {NS} batches in flight per GPU (contexts/streams)",
-                   "l2": "two alternating read batches of 400 MB each (> 126 MB L2); index smaller than L2 stays partly resident",
+                   "l2": f"two alternating read batches of {2 * B * L / 1e6:.0f} MB each (> 126 MB L2); the index ({ix.device_bytes / 1e6:.0f} MB on the device) exceeds L2 too",
                    "aligned_frac_last_step": aligned / B, "aligned_frac_last_e2e_step": e2e_aligned / B, "overflow_flags": flags_bad,
                    "counters_allreduced": [int(x) for x in ctr.tolist()]},
         "clocks": clk.summary(),

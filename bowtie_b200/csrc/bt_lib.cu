@@ -761,7 +761,8 @@ static int align_host(bt_context *cx, const bt_policy_t *pol, const bt_read_batc
 	bt_index_t *ix = cx->ix;
 	if (check_policy(ix, pol)) return 1;
 	if (in->nreads == 0) return 0;
-	if (!in->seq || !in->qual || !in->offs || !in->seeds || !out->found || !out->flags || !out->hits) return fail("bt_align_batch: null buffer");
+	if (!in->offs || !in->seeds || !out->found || !out->flags || !out->hits) return fail("bt_align_batch: null buffer");
+	if ((!in->seq || !in->qual) && in->offs[in->nreads] != 0) return fail("bt_align_batch: null sequence buffer");
 	if (out->slots == 0) return fail("bt_align_batch: slots must be >= 1");
 	cudaStream_t st = (cudaStream_t)stream;
 	uint32_t maxlen = 0;
@@ -778,8 +779,10 @@ static int align_host(bt_context *cx, const bt_policy_t *pol, const bt_read_batc
 		    grow(&cx->d_found, cx->cap_found, n) || grow(&cx->d_flags, cx->cap_flags, n)) return 1;
 		if (grow(&cx->d_hits, cx->cap_hitwords, hitwords)) return 1;
 		if (in->sel && grow(&cx->d_sel, cx->cap_sel, in->nsel)) return 1;
-		CUDA_TRY(cudaMemcpyAsync(cx->d_seq, in->seq, nb, cudaMemcpyHostToDevice, st));
-		CUDA_TRY(cudaMemcpyAsync(cx->d_qual, in->qual, nb, cudaMemcpyHostToDevice, st));
+		if (nb) {
+			CUDA_TRY(cudaMemcpyAsync(cx->d_seq, in->seq, nb, cudaMemcpyHostToDevice, st));
+			CUDA_TRY(cudaMemcpyAsync(cx->d_qual, in->qual, nb, cudaMemcpyHostToDevice, st));
+		}
 		CUDA_TRY(cudaMemcpyAsync(cx->d_offs, in->offs, ((size_t)n + 1) * 8, cudaMemcpyHostToDevice, st));
 		CUDA_TRY(cudaMemcpyAsync(cx->d_seeds, in->seeds, (size_t)n * 4, cudaMemcpyHostToDevice, st));
 		if (in->sel) CUDA_TRY(cudaMemcpyAsync(cx->d_sel, in->sel, (size_t)in->nsel * 4, cudaMemcpyHostToDevice, st));
