@@ -130,6 +130,7 @@ struct BtKParams {
 	uint8_t *stage;               /* 2 * stage_len bytes: writable copy of the read (long reads) */
 	uint32_t R, FCAP, PCAP, stage_len;
 	uint32_t budget;              /* per-read transition budget of this pass (0 = unlimited)  */
+	uint32_t rare_period, rare_thresh;   /* deferral of rare transitions in the thread-per-lane kernel */
 	unsigned long long *stats;    /* [8]: lfex, lf, chase, ftab, offs, backtracks, iters, blockloads */
 };
 

@@ -103,7 +103,7 @@ bt_search_kernel(BtKParams P, BtWorkCtl *ctl) {
 		const unsigned fmask = __ballot_sync(0xffffffffu, fast);
 		const unsigned rmask = __ballot_sync(0xffffffffu, rare);
 		if ((fmask | rmask) == 0) break;                                  /* every lane has exited */
-		const bool run_rare = (fmask == 0) || (__popc(rmask) >= BT_RARE_THRESH) || ((it % BT_RARE_PERIOD) == 0);
+		const bool run_rare = (fmask == 0) || ((uint32_t)__popc(rmask) >= P.rare_thresh) || ((it % P.rare_period) == 0);
 		if (run_rare) {
 			if (L.pc == PC_FINISH_READ) { bt_finish_read(L, P); L.pc = PC_NEXT_READ; }
 			/* work distribution: warp-aggregated grab from the global cursor, then the warp copies each new
@@ -612,6 +612,7 @@ static int check_policy(const bt_index_t *ix, const bt_policy_t *pol) {
 #endif
 /* Main / heavy pass kernels: thread-per-lane (default) or the experimental queue-driven kernel
  * (BT_MAIN_KERNEL=q / BT_HEAVY_KERNEL=q; see DESIGN.md §4.2 for the measurements that decided the default). */
+static uint32_t env_u32(const char *name, uint32_t dflt) { const char *e = getenv(name); return e ? (uint32_t)atol(e) : dflt; }
 static uint32_t main_budget() {
 	static long v = -1;
 	if (v < 0) { const char *e = getenv("BT_MAIN_BUDGET"); v = e ? atol(e) : (long)BT_MAIN_BUDGET; }
@@ -680,6 +681,7 @@ static int enqueue_align(bt_context *cx, const bt_policy_t *pol, const bt_read_b
 	/* main pass */
 	set_ws(P, cx->ws1);
 	P.budget = main_budget();
+	{ static uint32_t p = env_u32("BT_RARE_PERIOD", BT_RARE_PERIOD), t = env_u32("BT_RARE_THRESH", BT_RARE_THRESH); P.rare_period = p ? p : 1; P.rare_thresh = t; }
 	bt_ctl_set_kernel<<<1, 1, 0, st>>>(cx->ctl, nwork);
 	bt_ctl_set_kernel<<<1, 1, 0, st>>>(cx->ctl + 1, 0);
 	bt_ctl_set_kernel<<<1, 1, 0, st>>>(cx->ctl + 2, 0);
@@ -701,6 +703,7 @@ static int enqueue_align(bt_context *cx, const bt_policy_t *pol, const bt_read_b
 	CUDA_TRY(cudaStreamWaitEvent(cx->side, cx->ev_main, 0));
 	P.sel = cx->heavy_sel; P.budget = 0;
 	set_ws(P, cx->wsh);
+	{ static uint32_t p = env_u32("BT_HEAVY_PERIOD", BT_RARE_PERIOD), t = env_u32("BT_HEAVY_THRESH", BT_RARE_THRESH); P.rare_period = p ? p : 1; P.rare_thresh = t; }
 	if (heavy_kernel_is_queue()) {
 		/* heavy reads are ~1 % of the reads but ~45 % of the work: run them SIMT-efficiently too; the handful that exceed
 		 * the second budget (sequential searches of 10^5..10^6 transitions) finish in the last pass, where latency matters */
