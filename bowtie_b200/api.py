@@ -34,7 +34,8 @@ def build_library(force: bool = False) -> Path:
 class _Policy(C.Structure):
     _fields_ = [("mode", C.c_int32), ("mms", C.c_int32), ("seed_len", C.c_int32), ("qual_thresh", C.c_uint32),
                 ("max_bts", C.c_uint32), ("khits", C.c_uint32), ("mhits", C.c_uint32), ("all_hits", C.c_int32),
-                ("nofw", C.c_int32), ("norc", C.c_int32), ("maq_round", C.c_int32)]
+                ("nofw", C.c_int32), ("norc", C.c_int32), ("maq_round", C.c_int32),
+                ("best", C.c_int32), ("strata", C.c_int32), ("max_bts_best", C.c_uint32), ("sample_max", C.c_int32)]
 
 
 class _ReadBatch(C.Structure):
@@ -109,10 +110,19 @@ class Policy:
     nofw: bool = False
     norc: bool = False
     maq_round: bool = True
+    best: bool = False       # --best: the reference's best-first ("stateful") aligners; implied by strata and -v 3
+    strata: bool = False     # --strata
+    max_bts_best: int = 800  # --maxbts on the best-first path
+    sample_max: bool = False # -M: keep every hit up to the mhits ceiling
 
     def to_c(self) -> _Policy:
         return _Policy(self.mode, self.mms, self.seed_len, self.qual_thresh, self.max_bts, self.khits, self.mhits,
-                       int(self.all_hits), int(self.nofw), int(self.norc), int(self.maq_round))
+                       int(self.all_hits), int(self.nofw), int(self.norc), int(self.maq_round),
+                       int(self.best or self.strata or self.sample_max), int(self.strata), self.max_bts_best, int(self.sample_max))
+
+    @property
+    def stateful(self) -> bool:
+        return self.best or self.strata or self.sample_max or (self.mode == 0 and self.mms == 3)
 
     @property
     def needs_mirror(self) -> bool:

@@ -76,6 +76,9 @@ struct BtPolicy {
 	uint32_t maxBts;
 	uint32_t khits, mhits;
 	int32_t allHits, nofw, norc, maqRound;
+	int32_t best, strata;   /* best-first ("stateful") path, bt_best.cuh    */
+	uint32_t maxBtsBest;    /* its backtrack budget (maxBts, ebwt_search.cpp:186) */
+	int32_t sampleMax;      /* -M: keep every hit up to the -m ceiling      */
 };
 
 /* flags written per read */

@@ -487,7 +487,7 @@ extern "C" const char *bt_last_error(void) { return g_err.c_str(); }
 
 extern "C" void bt_policy_init(bt_policy_t *p) {
 	memset(p, 0, sizeof *p);
-	p->mode = 1; p->mms = 2; p->seed_len = 28; p->qual_thresh = 70; p->max_bts = 125; p->khits = 1; p->mhits = 0xffffffffu; p->maq_round = 1;
+	p->mode = 1; p->mms = 2; p->seed_len = 28; p->qual_thresh = 70; p->max_bts = 125; p->khits = 1; p->mhits = 0xffffffffu; p->maq_round = 1; p->max_bts_best = 800;
 }
 
 extern "C" void bt_context_free(bt_context_t *cx) {

@@ -31,7 +31,8 @@ struct Opts {
 	int format = FASTQ;
 	std::string ebwtFile, outfile;
 	std::vector<std::string> queries;
-	int mismatches = 0, seedMms = 2, maqLike = 1, seedLen = 28, qualThresh = 70, maxBts = 125;
+	int mismatches = 0, seedMms = 2, maqLike = 1, seedLen = 28, qualThresh = 70, maxBts = 125, maxBtsBest = 800;
+	bool best = false, strata = false, sampleMax = false;
 	bool noMaqRound = false, nofw = false, norc = false, allHits = false;
 	uint32_t khits = 1, mhits = 0xffffffffu;
 	uint32_t skipReads = 0, qUpto = 0xffffffffu;
@@ -121,12 +122,12 @@ static void parse_options(int argc, char **argv, Opts &o) {
 		case 't': o.timing = true; break;
 		case 'B': o.offBase = (int)parse_int(-999999, "-B/--offbase cannot be a large negative number"); break;
 		case 'S': o.sam = true; break;
-		case 'y': o.maxBts = 0x7fffffff; break;
+		case 'y': o.maxBts = o.maxBtsBest = 0x7fffffff; break;
 		case 'h': printf("Usage: bowtie-b200-align [options]* -x <ebwt> {<s> | -c <seqs>} [<hits>]\n  (option names follow bowtie 1.3.1; see DESIGN.md for the supported subset)\n"); exit(0);
-		case 'M': unsupported("-M"); break;
+		case 'M': o.sampleMax = true; o.mhits = (uint32_t)parse_int(1, "-m arg must be at least 1"); break;
 		case '1': case '2': case 'I': case 'X': case ARG_PAIRED: unsupported("paired-end alignment"); break;
-		case ARG_BEST: unsupported("--best"); break;
-		case ARG_STRATA: unsupported("--strata"); break;
+		case ARG_BEST: o.best = true; break;
+		case ARG_STRATA: o.strata = true; break;
 		case ARG_LARGE_INDEX: die("Error: large (64-bit) indexes are not supported"); break;
 		case ARG_PHRED33: o.solexaQuals = false; o.phred64Quals = false; break;
 		case ARG_PHRED64: case ARG_SOLEXA13: o.solexaQuals = false; o.phred64Quals = true; break;
@@ -134,7 +135,7 @@ static void parse_options(int argc, char **argv, Opts &o) {
 		case ARG_NOMAQROUND: o.noMaqRound = true; break;
 		case ARG_NOFW: o.nofw = true; break;
 		case ARG_NORC: o.norc = true; break;
-		case ARG_MAXBTS: o.maxBts = (int)parse_int(0, "--maxbts must be positive"); break;
+		case ARG_MAXBTS: o.maxBts = o.maxBtsBest = (int)parse_int(0, "--maxbts must be positive"); break;
 		case ARG_QUIET: o.quiet = true; break;
 		case ARG_REFIDX: o.refIdx = true; break;
 		case ARG_FULLREF: o.fullRef = true; break;
@@ -155,7 +156,14 @@ static void parse_options(int argc, char **argv, Opts &o) {
 		}
 	}
 	(void)vset;
-	if (!o.maqLike && o.mismatches == 3) unsupported("-v 3");
+	/* ebwt_search.cpp:851-854, 877-891 */
+	if (!o.maqLike && o.mismatches == 3) o.best = true;
+	if (!o.best && o.sampleMax) {
+		if (!o.quiet) fprintf(stderr, "Warning: -M was specified w/o --best; automatically enabling --best\n");
+		o.best = true;
+	}
+	if (o.strata && !o.best) die("--strata must be combined with --best");
+	if (o.strata && !o.allHits && o.khits == 1 && o.mhits == 0xffffffffu) die("--strata has no effect unless combined with -m, -a, or -k N where N > 1");
 	if (o.qUpto + o.skipReads > o.qUpto) o.qUpto += o.skipReads;                 /* ebwt_search.cpp:893-895 */
 	if (o.ebwtFile.empty()) {
 		if (optind >= argc) die("No index, query, or output file specified!");
@@ -473,6 +481,7 @@ int main(int argc, char **argv) {
 	pol.mode = op.maqLike ? 1 : 0; pol.mms = op.maqLike ? op.seedMms : op.mismatches;
 	pol.seed_len = op.seedLen; pol.qual_thresh = (uint32_t)op.qualThresh; pol.max_bts = (uint32_t)op.maxBts;
 	pol.khits = op.khits; pol.mhits = op.mhits; pol.all_hits = op.allHits; pol.nofw = op.nofw; pol.norc = op.norc; pol.maq_round = !op.noMaqRound;
+	pol.best = op.best; pol.strata = op.strata; pol.max_bts_best = (uint32_t)op.maxBtsBest; pol.sample_max = op.sampleMax;
 	const bool needMirror = op.maqLike || op.mismatches > 0;
 
 	/* adjustEbwtBase (ebwt.cpp:36-85): as given, else under $BOWTIE_INDEXES */
@@ -497,6 +506,7 @@ int main(int argc, char **argv) {
 	for (auto &b : bt) {
 		if (bt_context_create(ix, &b.cx)) die(std::string("Error: ") + bt_last_error());
 		b.slots = op.allHits ? 8 : op.khits;
+		if (op.sampleMax && op.mhits != 0xffffffffu) b.slots = std::max(b.slots, op.mhits);   /* -M keeps every hit up to the ceiling */
 		b.mm_cap = op.maqLike ? 10 : (uint32_t)std::max(1, op.mismatches);
 	}
 	uint64_t numAligned = 0, numUnaligned = 0, numMaxed = 0, numReported = 0;
@@ -538,7 +548,7 @@ int main(int argc, char **argv) {
 		for (size_t i = 0; i < n; i++) if (b.flags[i] & (BT_OVF_STACK | BT_OVF_FRAME | BT_OVF_PART)) die("Error: search scratch exhausted for read " + b.reads[i].name);
 		std::vector<uint32_t> found2, flags2, hits2; uint32_t slots2 = 0, mm2 = 0;
 		if (!need.empty()) {
-			slots2 = std::max<uint32_t>(1, std::min(maxFound, nlim)); mm2 = maxLen;
+			slots2 = std::max<uint32_t>(1, std::min(maxFound, op.sampleMax ? std::max(nlim, op.mhits) : nlim)); mm2 = maxLen;
 			found2.assign(n, 0); flags2.assign(n, 0); hits2.assign(n * (size_t)slots2 * (BT_HIT_HDR_WORDS + mm2), 0);
 			bt_read_batch_t in; memset(&in, 0, sizeof in);
 			in.nreads = (uint32_t)n; in.seq = b.seq.data(); in.qual = b.qual.data(); in.offs = b.offs.data(); in.seeds = b.seeds.data();
@@ -553,13 +563,29 @@ int main(int argc, char **argv) {
 			if (ni < need.size() && need[ni] == i) { rwi = BT_HIT_HDR_WORDS + mm2; recs = &hits2[i * (size_t)slots2 * rwi]; found = found2[i]; ni++; }
 			/* HitSinkPerThread::finishRead (hit.h:741-786) */
 			const bool maxed = found > op.mhits, unal = (found == 0);
-			if (maxed) { numMaxed++; }
+			if (maxed) {
+				numMaxed++;
+				if (op.sampleMax) {
+					/* VerboseHitSink::reportMaxed (hit.cpp:16-68) / SAMHitSink::reportMaxed (sam.cpp:263-311): one of the
+					 * buffered hits of the best stratum, picked with a fresh RandomSource seeded by the read */
+					const uint32_t nbuf = op.mhits;                               /* hits buffered before the ceiling was exceeded */
+					uint32_t num = 1;
+					for (uint32_t s = 1; s < nbuf; s++) { if (((recs[(size_t)s * rwi + 3] >> 16) & 0xff) == ((recs[(size_t)(s - 1) * rwi + 3] >> 16) & 0xff)) num++; else break; }
+					uint32_t last = b.seeds[i];
+					last = 1664525u * last + 1013904223u; uint32_t rr = last >> 16; last = 1664525u * last + 1013904223u; rr ^= last;   /* RandomSource::nextU32 */
+					const uint32_t *w = recs + (size_t)(rr % num) * rwi;
+					HitView h = { w[0], w[1], nbuf, w[3] & 0xffffu, (w[3] >> 16) & 0xff, (w[3] >> 24) & 1, w[4], w + BT_HIT_HDR_WORDS };
+					if (op.sam) append_sam(out.buf, op, ix, r, h, 0, (int)nbuf + 1); else append_default(out.buf, op, ix, r, h);
+					numAligned++; numReported++;
+				}
+			}
 			else if (unal) { numUnaligned++; if (op.sam && !op.noUnal) append_sam_unaligned(out.buf, op, r); }
 			else {
 				uint32_t nrep = std::min(found, nlim);
 				for (uint32_t s = 0; s < nrep; s++) {
 					const uint32_t *w = recs + (size_t)s * rwi;
 					HitView h = { w[0], w[1], w[2], w[3] & 0xffffu, (w[3] >> 16) & 0xff, (w[3] >> 24) & 1, w[4], w + BT_HIT_HDR_WORDS };
+					if (op.strata) h.oms = found - 1;                           /* NBestFirstStratHitSinkPerThread::finishReadImpl (hit.h:1099-1108) */
 					if (op.sam) append_sam(out.buf, op, ix, r, h, op.defaultMapq, (int)nrep); else append_default(out.buf, op, ix, r, h);
 				}
 				numAligned++; numReported += nrep;
@@ -584,13 +610,14 @@ int main(int argc, char **argv) {
 
 	/* HitSink::finish (hit.h:270-346) */
 	if (!op.quiet) {
-		uint64_t tot = numAligned + numUnaligned + numMaxed;
+		const uint64_t alShown = numAligned + (op.sampleMax ? 0 : numMaxed);
+		uint64_t tot = alShown + numUnaligned;
 		double alPct = 0, unalPct = 0, maxPct = 0;
-		if (tot > 0) { alPct = 100.0 * (double)(numAligned + numMaxed) / (double)tot; unalPct = 100.0 * (double)numUnaligned / (double)tot; maxPct = 100.0 * (double)numMaxed / (double)tot; }
+		if (tot > 0) { alPct = 100.0 * (double)alShown / (double)tot; unalPct = 100.0 * (double)numUnaligned / (double)tot; maxPct = 100.0 * (double)numMaxed / (double)tot; }
 		fprintf(stderr, "# reads processed: %llu\n", (unsigned long long)tot);
-		fprintf(stderr, "# reads with at least one alignment: %llu (%.2f%%)\n", (unsigned long long)(numAligned + numMaxed), alPct);
+		fprintf(stderr, "# reads with at least one alignment: %llu (%.2f%%)\n", (unsigned long long)alShown, alPct);
 		fprintf(stderr, "# reads that failed to align: %llu (%.2f%%)\n", (unsigned long long)numUnaligned, unalPct);
-		if (numMaxed > 0) fprintf(stderr, "# reads with alignments suppressed due to -m: %llu (%.2f%%)\n", (unsigned long long)numMaxed, maxPct);
+		if (numMaxed > 0) fprintf(stderr, op.sampleMax ? "# reads with alignments sampled due to -M: %llu (%.2f%%)\n" : "# reads with alignments suppressed due to -m: %llu (%.2f%%)\n", (unsigned long long)numMaxed, maxPct);
 		if (numReported == 0) fprintf(stderr, "No alignments\n");
 		else fprintf(stderr, "Reported %llu alignments\n", (unsigned long long)numReported);
 	}

@@ -26,7 +26,7 @@
 extern "C" {
 #endif
 
-#define BT_ABI_VERSION 1
+#define BT_ABI_VERSION 2
 
 typedef struct bt_index bt_index_t;
 typedef struct bt_context bt_context_t;
@@ -35,7 +35,7 @@ typedef struct bt_context bt_context_t;
  * Layout is shared with the kernels (BtPolicy in bt_core.cuh). */
 typedef struct bt_policy {
 	int32_t  mode;        /* 0: -v <mms> end-to-end mismatches ; 1: -n <mms> seeded, quality-aware ("maqLike") */
-	int32_t  mms;         /* -v: 0..2 ; -n: 0..3   (-v 3, --best, -M, paired-end are the reference's stateful path: not this ABI yet) */
+	int32_t  mms;         /* -v: 0..3 ; -n: 0..3   (-v 3 always runs on the best-first path, ebwt_search.cpp:851-854)         */
 	int32_t  seed_len;    /* -l, default 28                                  */
 	uint32_t qual_thresh; /* -e, default 70                                  */
 	uint32_t max_bts;     /* --maxbts, default 125 (maxBtsBetter)            */
@@ -44,6 +44,11 @@ typedef struct bt_policy {
 	int32_t  all_hits;    /* -a                                              */
 	int32_t  nofw, norc;  /* --nofw / --norc                                 */
 	int32_t  maq_round;   /* 1 unless --nomaqround                           */
+	int32_t  best;        /* --best (also implied by --strata, -M, -v 3): the reference's "stateful" best-first aligners
+	                         (UnpairedAlignerV2 over EbwtRangeSource drivers, aligner.h:381-599) instead of the DFS workers */
+	int32_t  strata;      /* --strata: NBestFirstStratHitSinkPerThread (hit.h:1070-1129); needs best                       */
+	uint32_t max_bts_best;/* --maxbts on the best-first path, default 800 (maxBts, ebwt_search.cpp:186,2644)               */
+	int32_t  sample_max;  /* -M: records are kept up to the mhits ceiling (the caller samples one, hit.cpp:16-68); needs best */
 } bt_policy_t;
 
 /* Per-read overflow flags (bt_hit_batch_t::flags).  Scratch-related overflows are retried inside the

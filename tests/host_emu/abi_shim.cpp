@@ -13,6 +13,7 @@
 #include <string>
 #include <vector>
 #include "../../bowtie_b200/csrc/bt_native.cuh"
+#include "../../bowtie_b200/csrc/bt_best_prog.h"
 #include "../../include/bowtie_b200.h"
 extern "C" {
 #include "../../oracle/bt_oracle.h"
@@ -56,9 +57,12 @@ void bt_index_free(bt_index_t *ix) { if (!ix) return; for (int k = 0; k < 2; k++
 int bt_index_info(const bt_index_t *ix, bt_index_info_t *info) { bto_index *r = ix->e[0]->raw; info->len = r->len; info->n_refs = r->nPat; info->off_rate = r->offRate; info->ftab_chars = r->ftabChars; info->has_mirror = ix->mirror; info->device_bytes = 0; return 0; }
 const char *bt_index_refname(const bt_index_t *ix, uint32_t i) { return i < ix->names.size() ? ix->names[i].c_str() : NULL; }
 uint32_t bt_index_reflen(const bt_index_t *ix, uint32_t i) { bto_index *r = ix->e[0]->raw; return i < r->nPat ? r->plen[i] : 0; }
-void bt_policy_init(bt_policy_t *p) { memset(p, 0, sizeof *p); p->mode = 1; p->mms = 2; p->seed_len = 28; p->qual_thresh = 70; p->max_bts = 125; p->khits = 1; p->mhits = 0xffffffffu; p->maq_round = 1; }
+void bt_policy_init(bt_policy_t *p) { memset(p, 0, sizeof *p); p->mode = 1; p->mms = 2; p->seed_len = 28; p->qual_thresh = 70; p->max_bts = 125; p->khits = 1; p->mhits = 0xffffffffu; p->maq_round = 1; p->max_bts_best = 800; }
 
+static int run_best(bt_index *ix, const bt_policy_t *pol, const bt_read_batch_t *in, bt_hit_batch_t *out);
+static bool stateful(const bt_policy_t *pol);
 static int run(bt_index *ix, const bt_policy_t *pol, const bt_read_batch_t *in, bt_hit_batch_t *out) {
+	if (stateful(pol)) return run_best(ix, pol, in, out);
 	BtKParams P; memset(&P, 0, sizeof P);
 	P.ix[0] = ix->e[0]->dev; if (ix->e[1]) P.ix[1] = ix->e[1]->dev;
 	memcpy(&P.pol, pol, sizeof(BtPolicy));
@@ -83,8 +87,37 @@ static int run(bt_index *ix, const bt_policy_t *pol, const bt_read_batch_t *in, 
 	}
 	return 0;
 }
+static bool stateful(const bt_policy_t *pol) { return pol->best || pol->strata || (pol->mode == 0 && pol->mms == 3); }
+/* the best-first path (bt_best.cuh), one read at a time */
+static int run_best(bt_index *ix, const bt_policy_t *pol, const bt_read_batch_t *in, bt_hit_batch_t *out) {
+	BfKParams P; memset(&P, 0, sizeof P);
+	P.ix[0] = ix->e[0]->dev; if (ix->e[1]) P.ix[1] = ix->e[1]->dev;
+	memcpy(&P.pol, pol, sizeof(BtPolicy));
+	bf_build_prog(pol->mode, pol->mms, pol->seed_len, pol->qual_thresh, pol->nofw, pol->norc, &P.prog);
+	P.seq = in->seq; P.qual = in->qual; P.roff = in->offs; P.seeds = in->seeds;
+	P.found = out->found; P.flags = out->flags; P.hits = out->hits; P.slots = out->slots; P.mm_cap = out->mm_cap; P.rec_words = BT_HIT_HDR + out->mm_cap;
+	static std::vector<uint32_t> arena; arena.resize((size_t)16 << 20);
+	const char *env = getenv("BT_EMU_ARENA_WORDS");
+	const uint32_t words = env ? (uint32_t)atol(env) : (uint32_t)arena.size();
+	const uint32_t nwork = in->sel ? in->nsel : in->nreads;
+	for (uint32_t w = 0; w < nwork; w++) {
+		const uint32_t r = in->sel ? in->sel[w] : w;
+		BfCtx X; memset(&X, 0, sizeof X);
+		X.P = &P; X.rid = r; X.rlen = (uint32_t)(in->offs[r + 1] - in->offs[r]); X.seed = in->seeds[r];
+		X.seq = in->seq + in->offs[r]; X.qual = in->qual + in->offs[r];
+		X.A = arena.data(); X.acap = words; X.atop = 1;
+		bf_align_read(X);
+		if ((X.flags & BT_FLAG_STACK_OVF) && words < arena.size()) {      /* what the larger-arena passes of the product do */
+			memset(&X.top, 0, sizeof X.top); X.flags = 0; X.acap = (uint32_t)arena.size(); X.atop = 1;
+			bf_align_read(X);
+		}
+		if (X.flags & (BT_FLAG_STACK_OVF | BT_FLAG_FRAME_OVF)) X.found = 0;
+		out->found[r] = X.found; out->flags[r] = X.flags;
+	}
+	return 0;
+}
 static int check(const bt_index *ix, const bt_policy_t *pol) {
-	if (pol->mode == 0 && pol->mms > 2) { g_err = "-v 3 is the reference's stateful path"; return 1; }
+	if (pol->mode == 0 && pol->mms > 3) { g_err = "-v must be 0..3"; return 1; }
 	if ((pol->mode == 1 || pol->mms > 0) && !ix->mirror) { g_err = "mirror index needed"; return 1; }
 	return 0;
 }
