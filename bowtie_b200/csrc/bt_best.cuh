@@ -25,7 +25,6 @@
 #pragma once
 #include "bt_core.cuh"
 
-#define BF_MAX_EDITS 16
 #define BF_MAX_TOP 8
 #define BF_ADV_COST_CHANGES 2
 
@@ -39,16 +38,18 @@ struct BfSrcCfg {            /* constructor arguments of one EbwtRangeSource + E
 struct BfTopCfg { uint32_t kind; BfSrcCfg a, b; };   /* a: the driver (or the seedling generator); b: the per-seedling extension driver */
 struct BfProg { uint32_t ntop, seedLen, qualLim, strandFix; BfTopCfg top[BF_MAX_TOP]; };
 
-struct BfEdit { uint16_t pos; uint8_t chr, pad; };    /* pos = depth of the edit, chr = reference base code */
+/* an edit is one arena word: pos | chr << 16 (pos = depth of the edit in a Branch, query offset in a Range; chr = reference base) */
+#define BF_EDIT(pos, chr) ((uint32_t)(pos) | ((uint32_t)(chr) << 16))
+#define BF_EDIT_POS(e) ((e) & 0xffffu)
+#define BF_EDIT_CHR(e) (((e) >> 16) & 0xffu)
 struct BfRS { uint32_t tops[4], bots[4], eq; };       /* RangeState: eq bits 0-3 = mm{A,C,G,T} eliminated, 8-14 = quallo, 31 = eliminated_ */
 #define BF_RS_WORDS 9
 #define BF_RS_ELIM 0x80000000u
 
 struct BfBranch {
-	uint32_t id, top, bot, ltop, lbot, ranges;
+	uint32_t id, top, bot, ltop, lbot, ranges, edits;      /* edits: nedits arena words */
 	uint16_t depth0, depth1, depth2, depth3, rdepth, len, cost, ham, rangesSz, i0, delayedCost, nedits;
 	uint8_t curtailed, exhausted, delayedIncrease, lbotValid;
-	BfEdit edits[BF_MAX_EDITS];
 };
 #define BF_BRANCH_WORDS ((uint32_t)(sizeof(BfBranch) / 4))
 
@@ -57,13 +58,13 @@ struct BfHdr { uint8_t kind, done, foundRange, fw; uint16_t minCost, minCostAdj;
 struct BfSrc {               /* EbwtRangeSourceDriver + its EbwtRangeSource + its PathManager */
 	BfHdr h;
 	BfSrcCfg cfg;
-	uint8_t rsDone, rsFound, skipping, seedValid, seedNmm, viewRev, viewComp, rNmm;
+	uint8_t rsDone, rsFound, skipping, seedValid, seedNmm, viewRev, viewComp, pad3;
 	uint16_t seedCost, rCost, pmMinCost, pad0;
+	uint32_t rNmm, rEdits, rEditsCap;                      /* the current Range's mismatches: arena words */
 	uint32_t qlen, depth5, depth3, off0, off1, off2, off3, rnd;
 	uint16_t seedMms[3]; uint8_t seedRefc[3], pad1;
 	uint16_t ovPos[3], pad2;
 	uint32_t rTop, rBot;
-	BfEdit rEdits[BF_MAX_EDITS + 3];
 	uint32_t heapOff, heapCap, heapSz, bcur;
 };
 #define BF_SRC_WORDS ((uint32_t)(sizeof(BfSrc) / 4))
@@ -203,10 +204,18 @@ BT_FN bool bf_eliminated(BfCtx &X, const BfBranch &b, uint32_t i) {      /* Bran
 /* Branch::init (range_source.h:531-607).  Returns the branch ref or 0 when the arena is exhausted. */
 BT_NOINLINE uint32_t bf_branch_new(BfCtx &X, BfSrc &s, uint32_t qlen, uint32_t d0, uint32_t d1, uint32_t d2, uint32_t d3,
                                    uint32_t rdepth, uint32_t len, uint32_t cost, uint32_t ham, uint32_t top, uint32_t bot,
-                                   const BfBranch *parent) {
+                                   const BfBranch *parent, uint32_t newEdit) {
 	const uint32_t ref = bf_alloc(X, BF_BRANCH_WORDS);
 	if (!ref) return 0;
 	BfBranch &b = *BF_BR(X, ref);
+	b.nedits = 0; b.edits = 0;
+	if (parent) {                                                        /* edits_ of the parent plus the edit that starts this branch */
+		b.nedits = (uint16_t)(parent->nedits + 1);
+		b.edits = bf_alloc(X, b.nedits);
+		if (!b.edits) return 0;
+		for (uint32_t i = 0; i < parent->nedits; i++) X.A[b.edits + i] = X.A[parent->edits + i];
+		X.A[b.edits + parent->nedits] = newEdit;
+	}
 	s.bcur++;                                                            /* bpool.alloc(); id = bpool.lastId() */
 	b.id = s.bcur;
 	b.delayedCost = 0;
@@ -223,8 +232,6 @@ BT_NOINLINE uint32_t bf_branch_new(BfCtx &X, BfSrc &s, uint32_t qlen, uint32_t d
 		if (!b.ranges) return 0;
 	}
 	b.curtailed = 0; b.exhausted = 0; b.delayedIncrease = 0;
-	b.nedits = 0;
-	if (parent) { b.nedits = parent->nedits; for (uint32_t i = 0; i < parent->nedits && i < BF_MAX_EDITS; i++) b.edits[i] = parent->edits[i]; }
 	for (uint32_t i = b.i0; i < len && i < b.rangesSz; i++) bf_rs(X, b, i)->eq |= BF_RS_ELIM;
 	return ref;
 }
@@ -232,6 +239,7 @@ BT_FN void bf_branch_free(BfCtx &X, BfSrc &s, uint32_t ref) {            /* Bran
 	BfBranch &b = *BF_BR(X, ref);
 	if (b.ranges) bf_free_top(X, b.ranges, (uint32_t)(b.rangesSz - b.i0) * BF_RS_WORDS);
 	if (b.id == s.bcur && s.bcur > 0) s.bcur--;
+	if (b.edits) bf_free_top(X, b.edits, b.nedits);
 	bf_free_top(X, ref, BF_BRANCH_WORDS);
 }
 /* Branch::curtail (range_source.h:876-923); the trimming of ranges_ only returns memory */
@@ -296,12 +304,8 @@ BT_NOINLINE uint32_t bf_branch_split(BfCtx &X, BfSrc &s, uint32_t srcRef, uint32
 	const uint32_t depth = pos + b.rdepth;
 	const uint32_t nd0 = depth < b.depth1 ? b.depth1 : b.depth0, nd1 = depth < b.depth2 ? b.depth2 : b.depth1,
 	               nd2 = depth < b.depth3 ? b.depth3 : b.depth2, nd3 = b.depth3;
-	const uint32_t nref = bf_branch_new(X, s, qlen, nd0, nd1, nd2, nd3, depth + 1, 0, b.cost, (uint32_t)b.ham + (best & ~0xc000u), top, bot, &b);
+	const uint32_t nref = bf_branch_new(X, s, qlen, nd0, nd1, nd2, nd3, depth + 1, 0, b.cost, (uint32_t)b.ham + (best & ~0xc000u), top, bot, &b, BF_EDIT(depth, chr));
 	if (!nref) return 0;
-	BfBranch &nb = *BF_BR(X, nref);
-	if (nb.nedits < BF_MAX_EDITS) { nb.edits[nb.nedits].pos = (uint16_t)depth; nb.edits[nb.nedits].chr = (uint8_t)chr; nb.edits[nb.nedits].pad = 0; }
-	else X.flags |= BT_FLAG_MM_OVF;
-	nb.nedits++;
 	if (notElim == 1 && last) b.exhausted = 1;
 	else if (numTied == 1 && last) {
 		if (best != next) { b.delayedCost = (uint16_t)(b.cost - best + next); b.delayedIncrease = 1; }
@@ -351,24 +355,29 @@ BT_NOINLINE bool bf_pm_split_and_prep(BfCtx &X, BfSrc &s, uint32_t qlen, uint32_
 }
 
 /* ---- EbwtRangeSource ---------------------------------------------------------------------------- */
-BT_FN void bf_add_partial_edits(BfSrc &s) {                              /* addPartialEdits, ebwt_search_backtrack.h:2372-2381 */
-	if (!s.seedValid) return;
-	for (uint32_t i = 0; i < s.seedNmm; i++) {
-		BfEdit &e = s.rEdits[s.rNmm + i];                                /* stored as (query offset, refc): see bf_report */
-		e.pos = (uint16_t)(s.qlen - s.seedMms[i] - 1); e.chr = s.seedRefc[i]; e.pad = 1;
+/* curRange_.mms / refcs: the branch's edits as query offsets, then the seedling's (addPartialEdits, ebwt_search_backtrack.h:2372-2381) */
+BT_NOINLINE void bf_set_range_edits(BfCtx &X, BfSrc &s, const BfBranch *br) {
+	const uint32_t nb = br ? br->nedits : 0u, need = nb + (s.seedValid ? s.seedNmm : 0u);
+	if (need > s.rEditsCap) {
+		const uint32_t cap = need < 8 ? 8 : need;
+		const uint32_t off = bf_alloc(X, cap);
+		if (!off) { s.rNmm = 0; return; }
+		s.rEdits = off; s.rEditsCap = cap;
 	}
-	s.rNmm = (uint8_t)(s.rNmm + s.seedNmm);
+	for (uint32_t i = 0; i < nb; i++) { const uint32_t e = X.A[br->edits + i]; X.A[s.rEdits + i] = BF_EDIT(s.qlen - BF_EDIT_POS(e) - 1, BF_EDIT_CHR(e)); }
+	if (s.seedValid) for (uint32_t i = 0; i < s.seedNmm; i++) X.A[s.rEdits + nb + i] = BF_EDIT(s.qlen - s.seedMms[i] - 1, s.seedRefc[i]);
+	s.rNmm = need;
 }
 BT_FN bool bf_hh_check_top(const BfSrc &s, const BfBranch &b, uint32_t d) {       /* ebwt_search_backtrack.h:2420-2445 */
 	if (d == s.depth5) { if (b.nedits == 0) return false; }
 	else if (d == s.depth3) { if (b.nedits < s.cfg.hh) return false; }
 	return true;
 }
-BT_FN bool bf_hh_check(const BfSrc &s, const BfBranch &b, uint32_t depth, bool empty) {   /* ebwt_search_backtrack.h:2383-2414 */
+BT_FN bool bf_hh_check(const BfCtx &X, const BfSrc &s, const BfBranch &b, uint32_t depth, bool empty) {   /* ebwt_search_backtrack.h:2383-2414 */
 	if (depth == s.depth5 - 1 && !empty) return b.nedits > 0;
 	if (depth == s.depth3 - 1 && !empty) {
 		uint32_t lo = 0, hi = 0;
-		for (uint32_t i = 0; i < b.nedits && i < BF_MAX_EDITS; i++) { if (b.edits[i].pos < s.depth5) hi++; else if (b.edits[i].pos < s.depth3) lo++; }
+		for (uint32_t i = 0; i < b.nedits; i++) { const uint32_t pos = BF_EDIT_POS(X.A[b.edits + i]); if (pos < s.depth5) hi++; else if (pos < s.depth3) lo++; }
 		return b.nedits >= s.cfg.hh && !(lo == 0 || hi == 0);
 	}
 	return true;
@@ -408,15 +417,15 @@ BT_NOINLINE void bf_init_branch(BfCtx &X, BfSrc &s) {
 		const uint32_t top = bt_ftab_hi(ix, off), bot = bt_ftab_lo(ix, off + 1);
 		X.s_ftab++;
 		if (s.qlen == ftabChars && bot > top) {
-			s.rTop = top; s.rBot = bot; s.rCost = (uint16_t)icost; s.rNmm = 0;
-			bf_add_partial_edits(s);
+			s.rTop = top; s.rBot = bot; s.rCost = (uint16_t)icost;
+			bf_set_range_edits(X, s, 0);
 			s.rsFound = 1;
 		} else if (bot > top) {
-			const uint32_t b = bf_branch_new(X, s, s.qlen, s.off0, s.off1, s.off2, s.off3, 0, ftabChars, icost, iham, top, bot, 0);
+			const uint32_t b = bf_branch_new(X, s, s.qlen, s.off0, s.off1, s.off2, s.off3, 0, ftabChars, icost, iham, top, bot, 0, 0);
 			if (b) bf_pm_push(X, s, b);
 		}
 	} else {
-		const uint32_t b = bf_branch_new(X, s, s.qlen, s.off0, s.off1, s.off2, s.off3, 0, 0, icost, iham, 0, 0, 0);
+		const uint32_t b = bf_branch_new(X, s, s.qlen, s.off0, s.off1, s.off2, s.off3, 0, 0, icost, iham, 0, 0, 0, 0);
 		if (b) bf_pm_push(X, s, b);
 	}
 }
@@ -492,13 +501,10 @@ BT_NOINLINE void bf_advance_branch(BfCtx &X, BfSrc &s) {
 			const bool hit = cur == 0 && !empty;
 			const uint32_t nedits = br.nedits;
 			const bool invalidExact = hit && nedits == 0 && !s.cfg.reportExacts;
-			if (s.cfg.hh && !bf_hh_check(s, br, depth, empty)) bf_pm_curtail(X, s, brRef, s.depth3);
+			if (s.cfg.hh && !bf_hh_check(X, s, br, depth, empty)) bf_pm_curtail(X, s, brRef, s.depth3);
 			else if (hit && !invalidExact) {
-				s.rTop = br.top; s.rBot = br.bot; s.rCost = br.cost; s.rNmm = (uint8_t)nedits;
-				for (uint32_t i = 0; i < nedits && i < BF_MAX_EDITS; i++) {
-					s.rEdits[i].pos = (uint16_t)(s.qlen - br.edits[i].pos - 1); s.rEdits[i].chr = br.edits[i].chr; s.rEdits[i].pad = 0;
-				}
-				bf_add_partial_edits(s);
+				s.rTop = br.top; s.rBot = br.bot; s.rCost = br.cost;
+				bf_set_range_edits(X, s, &br);
 				s.rsFound = 1;
 				bf_pm_curtail(X, s, brRef, s.depth3);
 			} else if (empty || cur == 0) bf_pm_curtail(X, s, brRef, s.depth3);
@@ -531,8 +537,9 @@ BT_NOINLINE void bf_src_set_query(BfCtx &X, BfSrc &s, const BfSrc *seed) {
 		uint32_t n = seed->rNmm; if (n > 3) { n = 3; X.flags |= BT_FLAG_MM_OVF; }
 		s.seedNmm = (uint8_t)n;
 		for (uint32_t i = 0; i < n; i++) {
-			s.seedMms[i] = seed->rEdits[i].pos; s.seedRefc[i] = seed->rEdits[i].chr;
-			s.ovPos[i] = (uint16_t)(len - seed->rEdits[i].pos - 1);
+			const uint32_t e = X.A[seed->rEdits + i];
+			s.seedMms[i] = (uint16_t)BF_EDIT_POS(e); s.seedRefc[i] = (uint8_t)BF_EDIT_CHR(e);
+			s.ovPos[i] = (uint16_t)(len - BF_EDIT_POS(e) - 1);
 		}
 	}
 	/* initRangeSource */
@@ -786,9 +793,10 @@ BT_NOINLINE bool bf_report(BfCtx &X, const BfSrc &ra, uint32_t tidx, uint32_t to
 			rec[4] = ra.rNmm;
 			const bool flip = (ra.cfg.ebwtSel == 0) != (ra.cfg.fw != 0);        /* ebwt.h:1339-1350 */
 			for (uint32_t i = 0; i < ra.rNmm; i++) {
-				uint32_t pos = ra.rEdits[i].pos;
+				const uint32_t e = X.A[ra.rEdits + i];
+				uint32_t pos = BF_EDIT_POS(e);
 				if (flip) pos = X.rlen - pos - 1;
-				if (i < P.mm_cap) rec[BT_HIT_HDR + i] = pos | ((uint32_t)ra.rEdits[i].chr << 16); else X.flags |= BT_FLAG_MM_OVF;
+				if (i < P.mm_cap) rec[BT_HIT_HDR + i] = BF_EDIT(pos, BF_EDIT_CHR(e)); else X.flags |= BT_FLAG_MM_OVF;
 			}
 		} else X.flags |= BT_FLAG_HITS_OVF;
 	}

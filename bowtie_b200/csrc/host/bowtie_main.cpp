@@ -5,9 +5,10 @@
  * (pat.cpp: FASTQ 862-975, FASTA 575-640, raw 1168-1213, -c 437-523), the default hit format
  * (hit.cpp:73-301) and SAM (sam.cpp:20-257), and the stderr summary (hit.h:270-346); the search
  * itself (everything the reference's *SearchWorker* functions do) is one bt_context_align_async()
- * call per batch of reads.  Options of the reference's stateful path (--best, --strata, -M, -v 3,
- * paired-end) are rejected with a message; nothing falls back to a CPU search.
+ * call per batch of reads.  --best, --strata, -M and -v 3 select the library's best-first path;
+ * paired-end options are rejected with a message; nothing falls back to a CPU search.
  */
+#include <algorithm>
 #include <getopt.h>
 #include <stdint.h>
 #include <stdio.h>
@@ -76,7 +77,7 @@ static struct option long_options[] = {
 	{"no-unal", no_argument, 0, ARG_NO_UNAL}, {"sam-no-qname-trunc", no_argument, 0, ARG_SAM_NO_QNAME_TRUNC},
 	{"threads", required_argument, 0, 'p'}, {"seed", required_argument, 0, ARG_SEED}, {"cost", no_argument, 0, ARG_COST},
 	{"reorder", no_argument, 0, ARG_REORDER}, {"wrapper", required_argument, 0, ARG_WRAPPER}, {"version", no_argument, 0, ARG_VERSION},
-	{"mm", no_argument, 0, ARG_IGNORED0}, {"shmem", no_argument, 0, ARG_IGNORED1}, {"help", no_argument, 0, 'h'},
+	{"chunkmbs", required_argument, 0, ARG_IGNORED1}, {"mm", no_argument, 0, ARG_IGNORED0}, {"shmem", no_argument, 0, ARG_IGNORED1}, {"help", no_argument, 0, 'h'},
 	{"device", required_argument, 0, ARG_DEVICE}, {"reads-per-batch", required_argument, 0, ARG_BATCH},
 	{"large-index", no_argument, 0, ARG_LARGE_INDEX}, {"12", required_argument, 0, ARG_PAIRED}, {"interleaved", required_argument, 0, ARG_PAIRED},
 	{"ff", no_argument, 0, ARG_PAIRED}, {"fr", no_argument, 0, ARG_IGNORED0}, {"rf", no_argument, 0, ARG_PAIRED},
@@ -543,24 +544,54 @@ int main(int argc, char **argv) {
 		const size_t n = b.reads.size();
 		size_t rw = BT_HIT_HDR_WORDS + b.mm_cap;
 		/* reads whose records did not fit: run them again with exact capacities (ABI contract) */
-		std::vector<uint32_t> need; uint32_t maxFound = 0, maxLen = 1;
-		for (size_t i = 0; i < n; i++) if (b.flags[i] & (BT_OVF_HITS | BT_OVF_MM)) { need.push_back((uint32_t)i); maxFound = std::max(maxFound, b.found[i]); maxLen = std::max<uint32_t>(maxLen, (uint32_t)b.reads[i].seq.size()); }
+		std::vector<uint32_t> need;
+		for (size_t i = 0; i < n; i++) if (b.flags[i] & (BT_OVF_HITS | BT_OVF_MM)) need.push_back((uint32_t)i);
 		for (size_t i = 0; i < n; i++) if (b.flags[i] & (BT_OVF_STACK | BT_OVF_FRAME | BT_OVF_PART)) die("Error: search scratch exhausted for read " + b.reads[i].name);
-		std::vector<uint32_t> found2, flags2, hits2; uint32_t slots2 = 0, mm2 = 0;
+		/* the retried reads go through compact sub-batches of bounded size (a read reported with -a can have millions of hits);
+		 * their records are kept in hits2 at off2[k], rw2[k] words each */
+		std::vector<uint32_t> hits2, found2(need.size(), 0); std::vector<size_t> off2(need.size(), 0), rw2(need.size(), 0);
 		if (!need.empty()) {
-			slots2 = std::max<uint32_t>(1, std::min(maxFound, op.sampleMax ? std::max(nlim, op.mhits) : nlim)); mm2 = maxLen;
-			found2.assign(n, 0); flags2.assign(n, 0); hits2.assign(n * (size_t)slots2 * (BT_HIT_HDR_WORDS + mm2), 0);
-			bt_read_batch_t in; memset(&in, 0, sizeof in);
-			in.nreads = (uint32_t)n; in.seq = b.seq.data(); in.qual = b.qual.data(); in.offs = b.offs.data(); in.seeds = b.seeds.data();
-			in.sel = need.data(); in.nsel = (uint32_t)need.size();
-			bt_hit_batch_t ho = { found2.data(), flags2.data(), hits2.data(), slots2, mm2 };
-			if (bt_context_align(b.cx, &pol, &in, &ho, NULL)) die(std::string("Error: ") + bt_last_error());
+			const uint32_t storeLim = op.sampleMax ? std::max(nlim, op.mhits) : nlim;
+			std::vector<uint32_t> order(need.size());
+			for (size_t k = 0; k < need.size(); k++) order[k] = (uint32_t)k;
+			std::sort(order.begin(), order.end(), [&](uint32_t x, uint32_t y) { return b.found[need[x]] < b.found[need[y]]; });
+			const size_t budgetWords = (size_t)1 << 26;
+			size_t g0 = 0;
+			while (g0 < order.size()) {
+				size_t g1 = g0; uint32_t gSlots = 1, gLen = 1;
+				while (g1 < order.size()) {
+					const uint32_t i = need[order[g1]];
+					const uint32_t sl = std::max<uint32_t>(1, std::min(b.found[i], storeLim)), ln = std::max<uint32_t>(gLen, (uint32_t)b.reads[i].seq.size());
+					if (g1 > g0 && (g1 - g0 + 1) * (size_t)sl * (BT_HIT_HDR_WORDS + ln) > budgetWords) break;
+					gSlots = sl; gLen = ln; g1++;                                /* sorted by found: the last read sets the slot count */
+				}
+				const size_t gn = g1 - g0, grw = BT_HIT_HDR_WORDS + gLen;
+				std::vector<uint8_t> gseq, gqual; std::vector<uint64_t> goffs(1, 0); std::vector<uint32_t> gseeds, gfound(gn, 0), gflags(gn, 0), ghits(gn * (size_t)gSlots * grw, 0);
+				for (size_t k = g0; k < g1; k++) {
+					const uint32_t i = need[order[k]];
+					gseq.insert(gseq.end(), b.seq.begin() + b.offs[i], b.seq.begin() + b.offs[i + 1]);
+					gqual.insert(gqual.end(), b.qual.begin() + b.offs[i], b.qual.begin() + b.offs[i + 1]);
+					goffs.push_back(gseq.size()); gseeds.push_back(b.seeds[i]);
+				}
+				bt_read_batch_t in; memset(&in, 0, sizeof in);
+				in.nreads = (uint32_t)gn; in.seq = gseq.data(); in.qual = gqual.data(); in.offs = goffs.data(); in.seeds = gseeds.data();
+				bt_hit_batch_t ho = { gfound.data(), gflags.data(), ghits.data(), gSlots, gLen };
+				if (bt_context_align(b.cx, &pol, &in, &ho, NULL)) die(std::string("Error: ") + bt_last_error());
+				for (size_t k = g0; k < g1; k++) {
+					const size_t j = k - g0, kk = order[k];
+					if (gflags[j] & (BT_OVF_STACK | BT_OVF_FRAME | BT_OVF_PART | BT_OVF_HITS | BT_OVF_MM)) die("Error: search scratch exhausted for read " + b.reads[need[kk]].name);
+					const uint32_t nst = std::min(gfound[j], gSlots);
+					found2[kk] = gfound[j]; off2[kk] = hits2.size(); rw2[kk] = grw;
+					hits2.insert(hits2.end(), ghits.begin() + j * (size_t)gSlots * grw, ghits.begin() + (j * (size_t)gSlots + nst) * grw);
+				}
+				g0 = g1;
+			}
 		}
 		size_t ni = 0;
 		for (size_t i = 0; i < n; i++) {
 			const ReadRec &r = b.reads[i];
 			const uint32_t *recs = &b.hits[i * b.slots * rw]; size_t rwi = rw; uint32_t found = b.found[i];
-			if (ni < need.size() && need[ni] == i) { rwi = BT_HIT_HDR_WORDS + mm2; recs = &hits2[i * (size_t)slots2 * rwi]; found = found2[i]; ni++; }
+			if (ni < need.size() && need[ni] == i) { rwi = rw2[ni]; recs = hits2.data() + off2[ni]; found = found2[ni]; ni++; }
 			/* HitSinkPerThread::finishRead (hit.h:741-786) */
 			const bool maxed = found > op.mhits, unal = (found == 0);
 			if (maxed) {
