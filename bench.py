@@ -155,13 +155,13 @@ class ClockSampler:
 # reference arm / cpu baseline: the UNMODIFIED reference binary on the host cores
 # ------------------------------------------------------------------------------------------------
 
-def run_reference_sample(base: Path, fq: Path, n: int, threads: int) -> tuple[float, float]:
+def run_reference_sample(base: Path, fq: Path, n: int, threads: int, flags=("-n", "2", "-k", "1")) -> tuple[float, float]:
     """bowtie-align-s -n 2 -k 1 -t -p <threads>; returns (search seconds from -t, wall seconds)."""
     exe = REF_DIR / "bowtie-align-s"
     if not exe.exists():
         raise RuntimeError("oracle/_ref/bowtie-align-s missing (built by oracle/Makefile from /root/reference)")
     t0 = time.time()
-    p = subprocess.run([str(exe), "-n", "2", "-k", "1", "-t", "-p", str(threads), "-x", str(base), str(fq), "/dev/null"],
+    p = subprocess.run([str(exe), *flags, "-t", "-p", str(threads), "-x", str(base), str(fq), "/dev/null"],
                        capture_output=True, text=True)
     wall = time.time() - t0
     if p.returncode != 0:
@@ -183,11 +183,14 @@ def main() -> None:
     ap.add_argument("--reads-per-step", type=int, default=int(os.environ.get("BT_BENCH_READS", 4_000_000)))
     ap.add_argument("--streams", type=int, default=int(os.environ.get("BT_BENCH_STREAMS", 8)),
                     help="batches kept in flight (one bt_context_t + CUDA stream each), like the reference's -p worker threads")
+    ap.add_argument("--policy", default=os.environ.get("BT_BENCH_POLICY", "n2k1"), choices=["n2k1", "best"],
+                    help="n2k1: the headline workload (-n 2 -k 1, SURVEY config 4); best: -n 2 --best (SURVEY config 3, best-first path)")
     ap.add_argument("--cpu-sample", type=int, default=int(os.environ.get("BT_BENCH_CPU_SAMPLE", 1_000_000)))
     args = ap.parse_args()
     rank, world, local = int(os.environ.get("RANK", 0)), int(os.environ.get("WORLD_SIZE", 1)), int(os.environ.get("LOCAL_RANK", 0))
     base, idx_name = pick_index()
-    cfg_workload = f"-n 2 -k 1, {READ_LEN} bp synthetic reads (1% subs, both strands), index {idx_name}"
+    ref_flags = ["-n", "2", "-k", "1"] if args.policy == "n2k1" else ["-n", "2", "--best"]
+    cfg_workload = f"{' '.join(ref_flags)}, {READ_LEN} bp synthetic reads (1% subs, both strands), index {idx_name}"
     cores = os.cpu_count() or 1
 
     if args.impl == "reference":
@@ -201,7 +204,7 @@ def main() -> None:
             write_fastq(fq, codes, quals, name, n)
             times = []
             for it in range(args.warmup + args.steps):
-                search, wall = run_reference_sample(base, fq, n, cores)
+                search, wall = run_reference_sample(base, fq, n, cores, ref_flags)
                 if it >= args.warmup:
                     times.append(wall)
         tot = sum(times)
@@ -211,7 +214,7 @@ def main() -> None:
                 "scaling": "weak", "vs_baseline": None, "dtype": "u32", "data": "synthetic",
                 "config": {"workload": cfg_workload, "reads_per_step": n, "parallelism": f"{cores} host threads (bowtie -p)"},
                 "cpu_baseline": {"value": val, "unit": "reads/s", "cores": cores, "kind": "reference",
-                                 "sample": f"{n} reads per step, wall clock of bowtie-align-s -n 2 -k 1 -p {cores} incl. index load"},
+                                 "sample": f"{n} reads per step, wall clock of bowtie-align-s {' '.join(ref_flags)} -p {cores} incl. index load"},
                 "e2e": {"value": val, "unit": "reads/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
         print(json.dumps(line))
         return
@@ -228,7 +231,9 @@ def main() -> None:
     if not os.environ.get("BOWTIE_B200_LIB"):
         bowtie_b200.build_library()
     ix = bowtie_b200.Index(str(base), need_mirror=True, device=local)
-    pol = bowtie_b200.Policy(mode=1, mms=2, khits=1)
+    pol = bowtie_b200.Policy(mode=1, mms=2, khits=1, best=(args.policy == "best"))
+    if args.policy == "best":
+        args.streams = min(args.streams, 3)      # every context of the best-first path owns ~15 GB of arenas
     B, L, slots, mm_cap = args.reads_per_step, READ_LEN, 1, 7
     rw = bowtie_b200.BT_HIT_HDR_WORDS + mm_cap
     genome = load_genome(base)
@@ -347,9 +352,9 @@ def main() -> None:
             with tempfile.TemporaryDirectory() as td:
                 fq = Path(td) / "s.fq"
                 write_fastq(fq, host[0][0], host[0][1], host[0][4], n)
-                search, wall = run_reference_sample(base, fq, n, cores)
+                search, wall = run_reference_sample(base, fq, n, cores, ref_flags)
             cpu = {"value": n / wall, "unit": "reads/s", "cores": cores, "kind": "reference",
-                   "sample": f"first {n} reads of step 0, bowtie-align-s -n 2 -k 1 -p {cores}, wall clock {wall:.1f}s incl. index load ('Time searching' {search:.0f}s)"}
+                   "sample": f"first {n} reads of step 0, bowtie-align-s {' '.join(ref_flags)} -p {cores}, wall clock {wall:.1f}s incl. index load ('Time searching' {search:.0f}s)"}
         except Exception as ex:  # the reference binary did not travel: report why instead of a number
             cpu = {"value": None, "unit": "reads/s", "cores": cores, "kind": "reference", "sample": f"unavailable: {ex}"}
     line = {
@@ -363,7 +368,8 @@ def main() -> None:
                    "counters_allreduced": [int(x) for x in ctr.tolist()]},
         "clocks": clk.summary(),
         "e2e": {"value": e2e_val, "unit": "reads/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
-        "gpu_launches": 9 * args.steps,   # per step: 3 ctl_set, main search, 3 collect, heavy search, overflow search
+        # per step: 3 ctl_set, main search, 3 collect, heavy search, overflow search (best-first: 3 ctl_set, 3 arena tiers, 2 collect)
+        "gpu_launches": (9 if args.policy == "n2k1" else 8) * args.steps,
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
                      "peak_source": "MEASURED_PEAKS.json hbm_gbs" if peaks else "fallback 6650 GB/s",
                      "side_fetches_per_read": st.side_fetches / (B * args.steps), "block_loads_per_read": st.block_loads / (B * args.steps),

@@ -658,7 +658,10 @@ BT_NOINLINE bool bf_ca_found_first(BfCtx &X, BfCA &ca, uint32_t r, bool strandFi
 	}
 	return false;
 }
-/* CostAwareRangeSourceDriver::advanceImpl (range_source.h:2131-2180) */
+/* CostAwareRangeSourceDriver::advanceImpl (range_source.h:2131-2180).  TOP: the aligner's driver list (plain and seeded
+ * drivers, strand fix); otherwise the per-seedling list inside a seeded driver, whose elements are always plain
+ * drivers — spelled out so that the device call graph has no cycle. */
+template <bool TOP>
 BT_NOINLINE void bf_ca_advance(BfCtx &X, BfCA &ca, bool strandFix) {
 	ca.lastRange = 0;
 	if (ca.delayedRange != 0) {
@@ -670,11 +673,12 @@ BT_NOINLINE void bf_ca_advance(BfCtx &X, BfCA &ca, bool strandFix) {
 	if (ca.nAct == 0) { ca.done = 1; return; }
 	const uint32_t p = X.A[ca.actOff];
 	const uint32_t precost = bf_hdr(X, p).minCost;
-	if (!bf_hdr(X, p).foundRange) bf_node_advance(X, p);
+	if (!bf_hdr(X, p).foundRange) { if (TOP) bf_node_advance(X, p); else bf_src_advance(X, *BF_AT(BfSrc, X, p)); }
 	if (X.flags & (BT_FLAG_STACK_OVF | BT_FLAG_FRAME_OVF)) return;
 	bool needsSort = false;
 	if (bf_hdr(X, p).foundRange) {
-		needsSort = bf_ca_found_first(X, ca, bf_node_range(X, p), strandFix);
+		if (TOP) needsSort = bf_ca_found_first(X, ca, bf_node_range(X, p), strandFix);
+		else { ca.foundRange = 1; ca.lastRange = p; }
 		bf_hdr(X, p).foundRange = 0;
 	}
 	if (bf_hdr(X, p).done || precost != bf_hdr(X, p).minCost || needsSort) {
@@ -688,9 +692,12 @@ BT_FN void bf_ca_copy_active(BfCtx &X, BfCA &ca) {                       /* acti
 	if (ca.actCap >= ca.nRss) { for (uint32_t i = 0; i < ca.nRss; i++) X.A[ca.actOff + i] = X.A[ca.rssOff + i]; ca.nAct = ca.nRss; }
 }
 /* CostAwareRangeSourceDriver::setQueryImpl (range_source.h:2072-2088) */
-BT_NOINLINE void bf_ca_set_query(BfCtx &X, BfCA &ca) {
+BT_FN void bf_ca_set_query_empty(BfCtx &X, BfCA &ca) {                    /* rss_ is empty: the seeded driver's list after clearSources */
 	ca.done = 0; ca.foundRange = 0; ca.lastRange = 0; ca.delayedRange = 0;
 	ca.rnd = X.seed;
+}
+BT_NOINLINE void bf_ca_set_query(BfCtx &X, BfCA &ca) {
+	bf_ca_set_query_empty(X, ca);
 	if (ca.nRss == 0) return;
 	for (uint32_t i = 0; i < ca.nRss; i++) { bf_node_set_query(X, X.A[ca.rssOff + i]); if (X.flags & BT_FLAG_STACK_OVF) return; }
 	bf_ca_copy_active(X, ca);
@@ -705,7 +712,7 @@ BT_NOINLINE void bf_seeded_set_query(BfCtx &X, BfSeeded &sd) {
 	sd.h.minCostAdj = gen.h.minCostAdj > gen.h.minCost ? gen.h.minCostAdj : gen.h.minCost;
 	sd.h.minCost = sd.h.minCostAdj;
 	sd.full.nRss = 0; sd.full.nAct = 0;                                   /* clearSources */
-	bf_ca_set_query(X, sd.full);
+	bf_ca_set_query_empty(X, sd.full);
 	sd.full.minCost = sd.h.minCost;
 	sd.h.foundRange = 0;
 }
@@ -753,7 +760,7 @@ BT_NOINLINE void bf_seeded_advance(BfCtx &X, uint32_t node) {
 		}
 	} else {
 		const uint32_t oldFull = full.minCost;
-		if (!full.foundRange) bf_ca_advance(X, full, false);
+		if (!full.foundRange) bf_ca_advance<false>(X, full, false);
 		if (full.foundRange) { sd.h.foundRange = 1; full.foundRange = 0; }
 		if (full.minCost > oldFull) sd.h.minCost = full.minCost < gen.h.minCost ? full.minCost : gen.h.minCost;
 	}
@@ -888,7 +895,7 @@ BT_NOINLINE void bf_align_read(BfCtx &X) {
 				else top.foundRange = 0;
 			} else {
 				done = bf_irrelevant_cost(X, top.minCost);
-				if (!done) bf_ca_advance(X, top, strandFix);
+				if (!done) bf_ca_advance<true>(X, top, strandFix);
 			}
 			if (top.done && !top.foundRange && !chase) done = true;
 		}

@@ -4,6 +4,7 @@
  *   bt_relayout_kernel   .ebwt sides -> 32-byte rank blocks (once per index load)
  *   bt_search_kernel     persistent lanes, one read per thread, dynamic work queue
  *   bt_collect_kernel    device-side list of reads whose scratch overflowed (for the retry pass)
+ *   bt_best_kernel       the best-first ("stateful") path: one read per thread, per-read arena (bt_best.cuh)
  *
  * There is no host search path in this library: without a CUDA device every entry point fails.
  */
@@ -17,6 +18,7 @@
 
 #include "bt_native.cuh"
 #include "bt_ctxq.cuh"
+#include "bt_best_prog.h"
 #include "../../include/bowtie_b200.h"
 
 static_assert(sizeof(bt_policy_t) == sizeof(BtPolicy), "bt_policy_t and BtPolicy must share a layout");
@@ -323,6 +325,40 @@ bt_search_kernel_q(BtKParams P, BtWorkCtl *ctl, uint32_t nctx) {
 
 static size_t bt_q_smem(uint32_t nctx) { return sizeof(BtQueues) + (size_t)nctx * BT_CTX_WORDS * 4; }
 
+/* Best-first path (--best / --strata / -M / -v 3): every thread takes reads from the global cursor and runs the whole
+ * UnpairedAlignerV2 loop for each on its own arena of P.arenaWords words.  `lanes` threads of each block are active. */
+#define BF_THREADS 64
+__global__ void __launch_bounds__(BF_THREADS)
+bt_best_kernel(const __grid_constant__ BfKParams P, BtWorkCtl *ctl, uint32_t lanes) {
+	if (threadIdx.x >= lanes) return;
+	const uint32_t tid = blockIdx.x * lanes + threadIdx.x;
+	BfCtx X;
+	X.P = &P;
+	X.A = P.arena + (size_t)tid * P.arenaWords; X.acap = P.arenaWords;
+	X.s_lfex = X.s_lf = X.s_chase = X.s_ftab = X.s_offs = X.s_bt = 0;
+	const unsigned long long nwork = ctl->nwork;
+	for (;;) {
+		const unsigned long long w = atomicAdd(&ctl->next, 1ull);
+		if (w >= nwork) break;
+		const uint32_t rid = P.sel ? P.sel[w] : (uint32_t)w;
+		const unsigned long long ro = P.roff[rid];
+		X.rid = rid; X.rlen = (uint32_t)(P.roff[rid + 1] - ro); X.seed = P.seeds[rid];
+		X.seq = P.seq + ro; X.qual = P.qual + ro;
+		X.atop = 1; X.flags = 0; X.found = 0;
+		X.top.rssOff = X.top.rssCap = X.top.nRss = X.top.actOff = X.top.actCap = X.top.nAct = 0;
+		X.top.lastRange = X.top.delayedRange = 0; X.top.minCost = 0; X.top.done = 0; X.top.foundRange = 0; X.top.rnd = 0;
+		bf_align_read(X);
+		if (X.flags & (BT_FLAG_STACK_OVF | BT_FLAG_FRAME_OVF)) X.found = 0;     /* STACK_OVF: re-run by a pass with a larger arena */
+		P.found[rid] = X.found; P.flags[rid] = X.flags;
+	}
+	if (X.s_lfex) atomicAdd(&P.stats[0], (unsigned long long)X.s_lfex);
+	if (X.s_lf) atomicAdd(&P.stats[1], (unsigned long long)X.s_lf);
+	if (X.s_chase) atomicAdd(&P.stats[2], (unsigned long long)X.s_chase);
+	if (X.s_ftab) atomicAdd(&P.stats[3], (unsigned long long)X.s_ftab);
+	if (X.s_offs) atomicAdd(&P.stats[4], (unsigned long long)X.s_offs);
+	if (X.s_bt) atomicAdd(&P.stats[5], (unsigned long long)X.s_bt);
+}
+
 /* Appends to sel_out the reads (of the first n work items of sel_in / the identity) whose flags intersect `mask`;
  * ctl->nwork is the list length.  If `count_ctl` is set, the number of work items is read from it (device-sized lists). */
 __global__ void bt_collect_kernel(const uint32_t *flags, const uint32_t *sel_in, uint32_t n, const BtWorkCtl *count_ctl, uint32_t mask, uint32_t *sel_out, BtWorkCtl *ctl) {
@@ -385,6 +421,7 @@ struct bt_index {
 struct bt_context {
 	bt_index *ix = nullptr;
 	Workspace ws1, wsh, ws2;     /* main pass / heavy-read pass / scratch-overflow pass */
+	uint32_t *arena[3] = { nullptr, nullptr, nullptr }; size_t arena_words[3] = { 0, 0, 0 };   /* best-first path: three arena tiers */
 	BtWorkCtl *ctl = nullptr;    /* [3] */
 	uint32_t *heavy_sel = nullptr, *retry_sel = nullptr; uint32_t retry_cap = 0;
 	cudaStream_t side = nullptr; /* the heavy and overflow passes run here, overlapping the next batch's main pass */
@@ -497,6 +534,7 @@ extern "C" void bt_context_free(bt_context_t *cx) {
 	if (cx->ev_main) cudaEventDestroy(cx->ev_main);
 	if (cx->ev_tail) cudaEventDestroy(cx->ev_tail);
 	cx->ws1.release(); cx->wsh.release(); cx->ws2.release();
+	for (int k = 0; k < 3; k++) cudaFree(cx->arena[k]);
 	cudaFree(cx->ctl); cudaFree(cx->retry_sel); cudaFree(cx->heavy_sel);
 	cudaFree(cx->d_seq); cudaFree(cx->d_qual); cudaFree(cx->d_offs); cudaFree(cx->d_seeds); cudaFree(cx->d_sel);
 	cudaFree(cx->d_found); cudaFree(cx->d_flags); cudaFree(cx->d_hits);
@@ -597,8 +635,9 @@ static int ensure_ws(Workspace &w, uint32_t nthreads, uint32_t R, uint32_t FCAP,
 	return 0;
 }
 
+static bool policy_is_best(const bt_policy_t *pol) { return pol->best || pol->strata || pol->sample_max || (pol->mode == 0 && pol->mms == 3); }
 static int check_policy(const bt_index_t *ix, const bt_policy_t *pol) {
-	if (pol->mode == 0) { if (pol->mms < 0 || pol->mms > 2) return fail("bt_align: -v 3 is the reference's stateful (best-first) path; not provided by this ABI version"); }
+	if (pol->mode == 0) { if (pol->mms < 0 || pol->mms > 3) return fail("bt_align: -v must be 0..3"); }
 	else if (pol->mode == 1) { if (pol->mms < 0 || pol->mms > 3) return fail("bt_align: -n must be 0..3"); if (pol->seed_len < 5) return fail("bt_align: -l must be >= 5"); }
 	else return fail("bt_align: bad mode");
 	if ((pol->mode == 1 || pol->mms > 0) && !ix->has_mirror) return fail("bt_align: this policy needs the mirror index (load with need_mirror=1)");
@@ -637,6 +676,61 @@ static bool main_kernel_is_queue() {
 #define BT_HEAVY_NCTX 256           /* heavy pass, queue kernel: contexts per block (one block per SM)        */
 #define BT_HEAVY_BLOCKS_PER_SM 8   /* heavy pass: 32-thread blocks, so finished warps free their slots */
 
+/* The best-first path (bt_best.cuh).  Three passes with growing per-read arenas: every read with 64 KB on the caller's
+ * stream; the reads that exhausted it with 1 MB, then with 16 MB, on the side stream. */
+static int enqueue_best(bt_context *cx, const bt_policy_t *pol, const bt_read_batch_t *in, bt_hit_batch_t *out, uint32_t maxlen, cudaStream_t st) {
+	bt_index_t *ix = cx->ix;
+	const uint32_t nwork = in->sel ? in->nsel : in->nreads;
+	static const uint32_t kw0 = env_u32("BT_BEST_ARENA_KW", 16);
+	const uint32_t tierWords[3] = { kw0 << 10, 256u << 10, 4096u << 10 };
+	const uint32_t tierLanes[3] = { BF_THREADS, 32, 2 };                 /* active threads per block */
+	const uint32_t tierBlocks[3] = { (uint32_t)ix->sms * 8, (uint32_t)ix->sms, (uint32_t)ix->sms };
+	for (int k = 0; k < 3; k++) {
+		const size_t need = (size_t)tierBlocks[k] * tierLanes[k] * tierWords[k];
+		if (cx->arena_words[k] < need) {
+			cudaFree(cx->arena[k]); cx->arena[k] = nullptr; cx->arena_words[k] = 0;
+			CUDA_TRY(cudaMalloc((void **)&cx->arena[k], need * 4));
+			cx->arena_words[k] = need;
+		}
+	}
+	if (cx->retry_cap < nwork) {
+		cudaFree(cx->retry_sel); cudaFree(cx->heavy_sel); cx->retry_sel = cx->heavy_sel = nullptr; cx->retry_cap = 0;
+		CUDA_TRY(cudaMalloc((void **)&cx->retry_sel, (size_t)nwork * 4));
+		CUDA_TRY(cudaMalloc((void **)&cx->heavy_sel, (size_t)nwork * 4));
+		cx->retry_cap = nwork;
+	}
+	BfKParams P; memset(&P, 0, sizeof P);
+	P.ix[0] = ix->dev[0].dev; P.ix[1] = ix->dev[1].dev;
+	memcpy(&P.pol, pol, sizeof(BtPolicy));
+	bf_build_prog(pol->mode, pol->mms, pol->seed_len, pol->qual_thresh, pol->nofw, pol->norc, &P.prog);
+	P.seq = in->seq; P.qual = in->qual; P.roff = in->offs; P.seeds = in->seeds; P.sel = in->sel; P.nwork = nwork;
+	P.found = out->found; P.flags = out->flags; P.hits = out->hits; P.slots = out->slots; P.mm_cap = out->mm_cap; P.rec_words = BT_HIT_HDR + out->mm_cap;
+	P.stats = ix->stats;
+	(void)maxlen;
+	const uint32_t cblocks = (nwork + 255) / 256;
+	CUDA_TRY(cudaStreamWaitEvent(st, cx->ev_tail, 0));
+	bt_ctl_set_kernel<<<1, 1, 0, st>>>(cx->ctl, nwork);
+	bt_ctl_set_kernel<<<1, 1, 0, st>>>(cx->ctl + 1, 0);
+	bt_ctl_set_kernel<<<1, 1, 0, st>>>(cx->ctl + 2, 0);
+	P.arena = cx->arena[0]; P.arenaWords = tierWords[0];
+	{
+		uint32_t grid = tierBlocks[0];
+		const uint32_t need = (nwork + tierLanes[0] - 1) / tierLanes[0];
+		if (grid > need) grid = need;
+		bt_best_kernel<<<grid, BF_THREADS, 0, st>>>(P, cx->ctl, tierLanes[0]);
+	}
+	bt_collect_kernel<<<cblocks, 256, 0, st>>>(out->flags, in->sel, nwork, nullptr, BT_FLAG_STACK_OVF, cx->heavy_sel, cx->ctl + 1);
+	CUDA_TRY(cudaEventRecord(cx->ev_main, st));
+	CUDA_TRY(cudaStreamWaitEvent(cx->side, cx->ev_main, 0));
+	P.sel = cx->heavy_sel; P.arena = cx->arena[1]; P.arenaWords = tierWords[1];
+	bt_best_kernel<<<tierBlocks[1], BF_THREADS, 0, cx->side>>>(P, cx->ctl + 1, tierLanes[1]);
+	bt_collect_kernel<<<cblocks, 256, 0, cx->side>>>(out->flags, cx->heavy_sel, nwork, cx->ctl + 1, BT_FLAG_STACK_OVF, cx->retry_sel, cx->ctl + 2);
+	P.sel = cx->retry_sel; P.arena = cx->arena[2]; P.arenaWords = tierWords[2];
+	bt_best_kernel<<<tierBlocks[2], BF_THREADS, 0, cx->side>>>(P, cx->ctl + 2, tierLanes[2]);
+	CUDA_TRY(cudaGetLastError());
+	return 0;
+}
+
 static void set_ws(BtKParams &P, const Workspace &w) {
 	P.rows = w.rows; P.elims = w.elims; P.frames = w.frames; P.partials = w.partials;
 	P.R = w.R; P.FCAP = w.FCAP; P.PCAP = w.PCAP; P.stage = w.stage; P.stage_len = w.stage_len;
@@ -653,6 +747,10 @@ static int enqueue_align(bt_context *cx, const bt_policy_t *pol, const bt_read_b
 	const uint32_t nwork = in->sel ? in->nsel : in->nreads;
 	if (nwork == 0) return 0;
 	if (maxlen < 1) maxlen = 1;
+	if (policy_is_best(pol)) {
+		if (maxlen > 1023) return fail("bt_align: reads longer than 1023 bases are not supported (the reference's Hit::mms is a FixedBitset<1024>)");
+		return enqueue_best(cx, pol, in, out, maxlen, st);
+	}
 	if (maxlen > 1023) return fail("bt_align: reads longer than 1023 bases are not supported (the reference's Hit::mms is a FixedBitset<1024>)");
 	const uint32_t nthreads = main_kernel_is_queue() ? (uint32_t)ix->sms * BT_Q_NCTX : (uint32_t)ix->sms * (uint32_t)ix->blocks_per_sm * BT_THREADS;
 	const uint32_t stage_len = (maxlen + 15) & ~15u;                     /* every context keeps a writable copy of its read */

@@ -36,7 +36,28 @@ CASES = [
     ("n2-l20-e100-nomaqround", ["-n", "2", "-l", "20", "-e", "100", "--nomaqround"], "fq"),
     ("v2-cmdline", ["-a", "-v", "2", "--suppress", "1,5,6,7", "-c"], "cmd"),     # MANUAL.markdown:246-253 Example 1
     ("n2-seed7", ["-n", "2", "--seed", "7", "-k", "2"], "fq"),
+    # the best-first ("stateful") path: SURVEY.md §8(c) goldens and the options that select it
+    ("best-n2", ["-n", "2", "--best"], "fq"),                                   # md5 89343691214487f3c47e35cbe4cf5a15
+    ("best-n2-strata-k5", ["-n", "2", "--best", "--strata", "-k", "5"], "fq"),  # md5 fa7667c8d4e433be247da97e79a61cbb
+    ("v3", ["-v", "3"], "fq"),                                                  # md5 13e0579a9fc872cede00a27d9bd9c5bf
+    ("v3-a-strata", ["-v", "3", "-a", "--best", "--strata"], "fq"),
+    ("best-v2-k3", ["-v", "2", "--best", "-k", "3"], "fq"),
+    ("best-v1-strata-m3", ["-v", "1", "--best", "--strata", "-m", "3", "-a"], "fq"),
+    ("best-v0", ["-v", "0", "--best"], "fq"),
+    ("best-n0", ["-n", "0", "--best", "--strata", "-k", "2"], "fq"),
+    ("best-n1-a", ["-n", "1", "--best", "-a"], "fq"),
+    ("best-n3-strata-a-nomaqround", ["-n", "3", "--best", "--strata", "-a", "--nomaqround"], "fq"),
+    ("best-n2-m1", ["-n", "2", "--best", "-m", "1"], "fq"),
+    ("M1", ["-n", "2", "-M", "1"], "fq"),
+    ("M2-strata-sam", ["-n", "2", "-M", "2", "--best", "--strata", "-k", "2", "-S"], "fq"),
+    ("best-n2-sam", ["-n", "2", "--best", "-S"], "fq"),
+    ("best-n2-norc-l20", ["-n", "2", "--best", "--norc", "-l", "20", "-e", "100"], "fq"),
+    ("best-n3-maxbts", ["-n", "3", "--best", "--maxbts", "20", "-a", "--strata"], "fq"),
+    ("best-n2-tryhard", ["-n", "2", "--best", "-y", "-a"], "fq"),
+    ("best-fasta", ["-v", "3", "-f", "-k", "2"], "fa"),
 ]
+
+GOLDEN_MD5 = {"best-n2": "89343691214487f3c47e35cbe4cf5a15", "best-n2-strata-k5": "fa7667c8d4e433be247da97e79a61cbb", "v3": "13e0579a9fc872cede00a27d9bd9c5bf"}
 
 
 @pytest.fixture(scope="module")
@@ -53,7 +74,9 @@ def cli():
 
 def build_shim():
     so = SHIM_DIR / "libbowtie_b200.so"
-    srcs = [ROOT / "tests" / "host_emu" / "abi_shim.cpp", ROOT / "bowtie_b200" / "csrc" / "bt_core.cuh", ROOT / "oracle" / "bt_oracle.c"]
+    csrc = ROOT / "bowtie_b200" / "csrc"
+    srcs = [ROOT / "tests" / "host_emu" / "abi_shim.cpp", csrc / "bt_core.cuh", ROOT / "oracle" / "bt_oracle.c", csrc / "bt_best.cuh", csrc / "bt_best_prog.h",
+            ROOT / "include" / "bowtie_b200.h"]
     if not so.exists() or so.stat().st_mtime < max(s.stat().st_mtime for s in srcs):
         SHIM_DIR.mkdir(exist_ok=True)
         subprocess.run(["g++", "-O2", "-std=c++17", "-fPIC", "-shared", "-o", str(so), str(srcs[0]), str(srcs[2])], check=True, capture_output=True)
@@ -81,25 +104,36 @@ def compare(cli, flags, kind, tmp_path, env):
     assert our_body == ref_body
     assert our_sum == ref_sum
     assert len(ref_body) > 0
+    return our_body
 
 
 @pytest.mark.parametrize("name,flags,kind", CASES, ids=[c[0] for c in CASES])
 def test_cli_host_logic_matches_reference(name, flags, kind, cli, tmp_path):
     build_shim()
     env = dict(os.environ, LD_LIBRARY_PATH=str(SHIM_DIR))
-    compare(cli, flags, kind, tmp_path, env)
+    body = compare(cli, flags, kind, tmp_path, env)
+    if name in GOLDEN_MD5:
+        import hashlib
+        assert hashlib.md5(body).hexdigest() == GOLDEN_MD5[name]
 
 
 @pytest.mark.gpu
 @pytest.mark.parametrize("name,flags,kind", CASES, ids=[c[0] for c in CASES])
 def test_cli_gpu_matches_reference(name, flags, kind, cli, tmp_path):
     env = {k: v for k, v in os.environ.items() if k != "LD_LIBRARY_PATH"}
-    compare(cli, flags, kind, tmp_path, env)
+    body = compare(cli, flags, kind, tmp_path, env)
+    if name in GOLDEN_MD5:
+        import hashlib
+        assert hashlib.md5(body).hexdigest() == GOLDEN_MD5[name]
 
 
-def test_cli_rejects_stateful_options(cli, tmp_path):
+def test_cli_rejects_paired_end_and_bad_strata(cli, tmp_path):
     build_shim()
     env = dict(os.environ, LD_LIBRARY_PATH=str(SHIM_DIR))
-    for flags in (["--best"], ["-v", "3"], ["-M", "1"], ["-1", "a", "-2", "b"]):
-        p = subprocess.run([str(cli), *flags, "-x", str(FIXTURES / "e_coli"), str(FIXTURES / "e_coli_1000.fq")], capture_output=True, text=True, env=env)
-        assert p.returncode != 0 and "stateful" in p.stderr
+    p = subprocess.run([str(cli), "-1", "a", "-2", "b", "-x", str(FIXTURES / "e_coli"), str(FIXTURES / "e_coli_1000.fq")], capture_output=True, text=True, env=env)
+    assert p.returncode != 0 and "paired-end" in p.stderr
+    # ebwt_search.cpp:883-890
+    p = subprocess.run([str(cli), "--strata", "-x", str(FIXTURES / "e_coli"), str(FIXTURES / "e_coli_1000.fq")], capture_output=True, text=True, env=env)
+    assert p.returncode != 0 and "--strata must be combined with --best" in p.stderr
+    p = subprocess.run([str(cli), "--best", "--strata", "-x", str(FIXTURES / "e_coli"), str(FIXTURES / "e_coli_1000.fq")], capture_output=True, text=True, env=env)
+    assert p.returncode != 0 and "--strata has no effect" in p.stderr
