@@ -677,15 +677,18 @@ static bool main_kernel_is_queue() {
 #define BT_HEAVY_BLOCKS_PER_SM 8   /* heavy pass: 32-thread blocks, so finished warps free their slots */
 
 /* The best-first path (bt_best.cuh).  Three passes with growing per-read arenas: every read with 64 KB on the caller's
- * stream; the reads that exhausted it with 1 MB, then with 16 MB, on the side stream. */
+ * stream (148 x 8 x 64 lanes); the reads that exhausted it with 1 MB (148 x 32 lanes), then with 16 MB (148 lanes), on the
+ * side stream.  About 5 + 5 + 2.5 GB per context for full batches. */
 static int enqueue_best(bt_context *cx, const bt_policy_t *pol, const bt_read_batch_t *in, bt_hit_batch_t *out, uint32_t maxlen, cudaStream_t st) {
 	bt_index_t *ix = cx->ix;
 	const uint32_t nwork = in->sel ? in->nsel : in->nreads;
 	static const uint32_t kw0 = env_u32("BT_BEST_ARENA_KW", 16);
 	const uint32_t tierWords[3] = { kw0 << 10, 256u << 10, 4096u << 10 };
-	const uint32_t tierLanes[3] = { BF_THREADS, 32, 2 };                 /* active threads per block */
-	const uint32_t tierBlocks[3] = { (uint32_t)ix->sms * 8, (uint32_t)ix->sms, (uint32_t)ix->sms };
+	const uint32_t tierLanes[3] = { BF_THREADS, 32, 1 };                 /* active threads per block */
+	uint32_t tierBlocks[3] = { (uint32_t)ix->sms * 8, (uint32_t)ix->sms, (uint32_t)ix->sms };
 	for (int k = 0; k < 3; k++) {
+		const uint32_t need_blocks = (nwork + tierLanes[k] - 1) / tierLanes[k];   /* small batches do not need a full machine of arenas */
+		if (tierBlocks[k] > need_blocks) tierBlocks[k] = need_blocks;
 		const size_t need = (size_t)tierBlocks[k] * tierLanes[k] * tierWords[k];
 		if (cx->arena_words[k] < need) {
 			cudaFree(cx->arena[k]); cx->arena[k] = nullptr; cx->arena_words[k] = 0;
@@ -713,12 +716,7 @@ static int enqueue_best(bt_context *cx, const bt_policy_t *pol, const bt_read_ba
 	bt_ctl_set_kernel<<<1, 1, 0, st>>>(cx->ctl + 1, 0);
 	bt_ctl_set_kernel<<<1, 1, 0, st>>>(cx->ctl + 2, 0);
 	P.arena = cx->arena[0]; P.arenaWords = tierWords[0];
-	{
-		uint32_t grid = tierBlocks[0];
-		const uint32_t need = (nwork + tierLanes[0] - 1) / tierLanes[0];
-		if (grid > need) grid = need;
-		bt_best_kernel<<<grid, BF_THREADS, 0, st>>>(P, cx->ctl, tierLanes[0]);
-	}
+	bt_best_kernel<<<tierBlocks[0], BF_THREADS, 0, st>>>(P, cx->ctl, tierLanes[0]);
 	bt_collect_kernel<<<cblocks, 256, 0, st>>>(out->flags, in->sel, nwork, nullptr, BT_FLAG_STACK_OVF, cx->heavy_sel, cx->ctl + 1);
 	CUDA_TRY(cudaEventRecord(cx->ev_main, st));
 	CUDA_TRY(cudaStreamWaitEvent(cx->side, cx->ev_main, 0));
