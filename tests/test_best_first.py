@@ -104,3 +104,16 @@ def test_best_first_gpu_arena_tiers(setup, tmp_path):
     base, d = setup
     compare(["-n", "2", "--best", "-k", "3"], base, d / "low.fq", tmp_path, gpu_env(BT_BEST_ARENA_KW="1"))
     compare(["-n", "3", "--best", "-a", "--strata"], base, d / "big.fq", tmp_path, gpu_env(BT_BEST_ARENA_KW="2"), ref_threads=8)
+
+
+def test_fuzz_both_paths_against_reference(setup):
+    """tools/fuzz_cli.py (random genomes / reads / option sets, both search paths) — a short run as a regression test."""
+    build_shim()
+    p = subprocess.run([str(ROOT / "tools" / "fuzz_cli.py"), "--iters", "25", "--seed", "11"], capture_output=True, text=True)
+    assert p.returncode == 0, p.stdout[-3000:]
+
+
+@pytest.mark.gpu
+def test_fuzz_both_paths_gpu(setup):
+    p = subprocess.run([str(ROOT / "tools" / "fuzz_cli.py"), "--iters", "12", "--seed", "12", "--gpu"], capture_output=True, text=True, env=gpu_env())
+    assert p.returncode == 0, p.stdout[-3000:]

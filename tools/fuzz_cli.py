@@ -1,0 +1,152 @@
+#!/usr/bin/env python
+"""Differential fuzzer in the spirit of the reference's scripts/test/random_bowtie_tests.pl: random small genomes
+(repeats, N gaps, several sequences), random reads (ragged lengths, Ns, low qualities) and random option sets for both
+search paths; bowtie-b200-align (through tests/host_emu/shim, i.e. the device code compiled for the host — or the real
+library with --gpu) must produce the reference binary's hit file and summary byte for byte.
+
+usage: tools/fuzz_cli.py [--iters N] [--seed S] [--gpu]
+"""
+import argparse
+import os
+import random
+import subprocess
+import sys
+import tempfile
+from pathlib import Path
+
+ROOT = Path(__file__).resolve().parent.parent
+REF = ROOT / "oracle" / "_ref"
+CLI = ROOT / "bowtie_b200" / "bowtie-b200-align"
+SHIM = ROOT / "tests" / "host_emu" / "shim"
+
+
+def rand_genome(rng):
+    nseq = rng.randint(1, 4)
+    seqs = []
+    rep = "".join(rng.choice("ACGT") for _ in range(rng.randint(20, 200)))
+    for i in range(nseq):
+        L = rng.randint(60, 3000)
+        s = [rng.choice("ACGT") for _ in range(L)]
+        for _ in range(rng.randint(0, 4)):                       # copies of a repeat, some diverged
+            p = rng.randint(0, max(0, L - len(rep)))
+            r = list(rep)
+            for k in range(len(r)):
+                if rng.random() < 0.03:
+                    r[k] = rng.choice("ACGT")
+            s[p:p + len(r)] = r[:max(0, L - p)]
+        if rng.random() < 0.4:                                    # N gap -> more fragments than sequences
+            p = rng.randint(0, L - 1)
+            for k in range(p, min(L, p + rng.randint(1, 30))):
+                s[k] = "N"
+        seqs.append(("seq%d some description" % i, "".join(s[:L])))
+    return seqs
+
+
+def rand_reads(rng, genome, n):
+    comp = str.maketrans("ACGTN", "TGCAN")
+    out = []
+    for i in range(n):
+        name, g = rng.choice(genome)
+        L = rng.randint(4, min(70, len(g)))
+        if rng.random() < 0.08:
+            r = "".join(rng.choice("ACGT") for _ in range(L))
+        else:
+            p = rng.randint(0, len(g) - L)
+            r = list(g[p:p + L])
+            for k in range(L):
+                if rng.random() < 0.04:
+                    r[k] = rng.choice("ACGT")
+                if rng.random() < 0.01:
+                    r[k] = "N"
+            r = "".join(r)
+            if rng.random() < 0.5:
+                r = r.translate(comp)[::-1]
+        q = "".join(chr(33 + rng.choice([40, 40, 30, 20, 12, 8, 3, 0])) for _ in range(L))
+        out.append((f"r{i}", r, q))
+    return out
+
+
+def rand_flags(rng):
+    f = []
+    if rng.random() < 0.5:
+        f += ["-v", str(rng.randint(0, 3))]
+    else:
+        f += ["-n", str(rng.randint(0, 3)), "-l", str(rng.choice([5, 8, 12, 20, 28, 40])), "-e", str(rng.choice([10, 40, 70, 150, 400]))]
+        if rng.random() < 0.3:
+            f += ["--nomaqround"]
+    best = rng.random() < 0.5
+    rep = rng.choice(["k1", "k", "a", "m", "M"])
+    if rep == "k":
+        f += ["-k", str(rng.randint(2, 6))]
+    elif rep == "a":
+        f += ["-a"]
+    elif rep == "m":
+        f += ["-m", str(rng.randint(1, 4))] + rng.choice([[], ["-k", "3"], ["-a"]])
+    elif rep == "M":
+        f += ["-M", str(rng.randint(1, 4))]
+        best = True
+    if best:
+        f += ["--best"]
+        if rep in ("k", "a", "m") and rng.random() < 0.5:
+            f += ["--strata"]
+    if rng.random() < 0.15:
+        f += [rng.choice(["--nofw", "--norc"])]
+    if rng.random() < 0.2:
+        f += ["--maxbts", str(rng.choice([1, 3, 10, 50]))]
+    if rng.random() < 0.1:
+        f += ["-y"]
+    if rng.random() < 0.2:
+        f += ["-S"]
+    if rng.random() < 0.2:
+        f += ["--seed", str(rng.randint(0, 1000))]
+    return f
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--iters", type=int, default=50)
+    ap.add_argument("--seed", type=int, default=1)
+    ap.add_argument("--gpu", action="store_true")
+    ap.add_argument("--keep", default="/tmp/fuzz_fail")
+    a = ap.parse_args()
+    env = {k: v for k, v in os.environ.items() if k != "LD_LIBRARY_PATH"}
+    if not a.gpu:
+        env["LD_LIBRARY_PATH"] = str(SHIM)
+    nfail = 0
+    for it in range(a.iters):
+        rng = random.Random(a.seed * 100003 + it)
+        with tempfile.TemporaryDirectory() as td:
+            td = Path(td)
+            genome = rand_genome(rng)
+            (td / "g.fa").write_text("".join(f">{n}\n{s}\n" for n, s in genome))
+            p = subprocess.run([str(REF / "bowtie-build-s"), "-q", "-t", str(rng.choice([1, 2, 4, 6])), "-o", str(rng.choice([1, 3, 5])), str(td / "g.fa"), str(td / "g")],
+                               capture_output=True, text=True)
+            if p.returncode != 0:
+                continue
+            reads = rand_reads(rng, [(n, s) for n, s in genome if len(s) >= 4], rng.randint(20, 200))
+            (td / "r.fq").write_text("".join(f"@{n}\n{s}\n+\n{q}\n" for n, s, q in reads))
+            for sub in range(4):
+                flags = rand_flags(rng)
+                r = subprocess.run([str(REF / "bowtie-align-s"), *flags, "-p", "1", "-x", str(td / "g"), str(td / "r.fq"), str(td / "ref.out")], capture_output=True, text=True)
+                if "Exhausted best-first chunk memory" in r.stderr:
+                    continue
+                o = subprocess.run([str(CLI), *flags, "-x", str(td / "g"), str(td / "r.fq"), str(td / "our.out")], capture_output=True, text=True, env=env)
+                def body(pth):
+                    return b"".join(l for l in Path(pth).read_bytes().splitlines(keepends=True) if not l.startswith(b"@PG")) if Path(pth).exists() else b"<none>"
+                def summ(t):
+                    return [l for l in t.splitlines() if l.startswith("#") or l.startswith("Reported") or l.startswith("No alignments")]
+                ok = r.returncode == o.returncode and (r.returncode != 0 or (body(td / "ref.out") == body(td / "our.out") and summ(r.stderr) == summ(o.stderr)))
+                if not ok:
+                    nfail += 1
+                    keep = Path(a.keep + f"_{a.seed}_{it}_{sub}")
+                    subprocess.run(["rm", "-rf", str(keep)]); subprocess.run(["cp", "-r", str(td), str(keep)])
+                    (keep / "flags.txt").write_text(" ".join(flags) + "\n" + r.stderr[-2000:] + "\n---\n" + o.stderr[-2000:])
+                    print(f"FAIL iter {it}.{sub}: {' '.join(flags)}  (rc ref {r.returncode} ours {o.returncode}) -> {keep}", flush=True)
+        if it % 10 == 9:
+            print(f"iter {it + 1}: {nfail} failures so far", flush=True)
+    print(f"done: {a.iters} iterations, {nfail} failures")
+    sys.exit(1 if nfail else 0)
+
+
+if __name__ == "__main__":
+    main()
