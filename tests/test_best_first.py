@@ -45,7 +45,7 @@ def setup(tmp_path_factory):
 
 
 def run(exe, flags, base, reads, out, env=None, ref_threads=0):
-    cmd = [str(exe), *flags] + (["-p", str(ref_threads), "--reorder"] if ref_threads else []) + ["-x", str(base), str(reads), str(out)]
+    cmd = [str(exe), *flags] + (["-p", "1"] if ref_threads else []) + ["-x", str(base), str(reads), str(out)]   # one thread: output in read order
     p = subprocess.run(cmd, capture_output=True, text=True, env=env)
     assert p.returncode == 0, p.stderr
     summary = "\n".join(l for l in p.stderr.splitlines() if l.startswith("#") or l.startswith("Reported") or l.startswith("No alignments"))
@@ -95,7 +95,7 @@ def test_best_first_gpu_matches_reference(flags, reads, setup, tmp_path):
 @pytest.mark.parametrize("flags", [["-n", "2", "--best"], ["-v", "3", "-k", "2"], ["-n", "2", "--best", "--strata", "-k", "3"]], ids=["n2best", "v3k2", "n2strata"])
 def test_best_first_gpu_20k_reads(flags, setup, tmp_path):
     base, d = setup
-    compare(flags, base, d / "big.fq", tmp_path, gpu_env(), ref_threads=8)
+    compare(flags, base, d / "big.fq", tmp_path, gpu_env(), ref_threads=1)
 
 
 @pytest.mark.gpu
@@ -103,7 +103,7 @@ def test_best_first_gpu_arena_tiers(setup, tmp_path):
     """A 4 KB first-tier arena sends most reads through the 1 MB (and some through the 16 MB) pass: same bytes out."""
     base, d = setup
     compare(["-n", "2", "--best", "-k", "3"], base, d / "low.fq", tmp_path, gpu_env(BT_BEST_ARENA_KW="1"))
-    compare(["-n", "3", "--best", "-a", "--strata"], base, d / "big.fq", tmp_path, gpu_env(BT_BEST_ARENA_KW="2"), ref_threads=8)
+    compare(["-n", "3", "--best", "-a", "--strata"], base, d / "big.fq", tmp_path, gpu_env(BT_BEST_ARENA_KW="2"), ref_threads=1)
 
 
 def test_fuzz_both_paths_against_reference(setup):
