@@ -35,7 +35,9 @@ class _Policy(C.Structure):
     _fields_ = [("mode", C.c_int32), ("mms", C.c_int32), ("seed_len", C.c_int32), ("qual_thresh", C.c_uint32),
                 ("max_bts", C.c_uint32), ("khits", C.c_uint32), ("mhits", C.c_uint32), ("all_hits", C.c_int32),
                 ("nofw", C.c_int32), ("norc", C.c_int32), ("maq_round", C.c_int32),
-                ("best", C.c_int32), ("strata", C.c_int32), ("max_bts_best", C.c_uint32), ("sample_max", C.c_int32)]
+                ("best", C.c_int32), ("strata", C.c_int32), ("max_bts_best", C.c_uint32), ("sample_max", C.c_int32),
+                ("paired", C.c_int32), ("min_ins", C.c_uint32), ("max_ins", C.c_uint32), ("mate1fw", C.c_int32), ("mate2fw", C.c_int32),
+                ("pair_tries", C.c_uint32)]
 
 
 class _ReadBatch(C.Structure):
@@ -114,11 +116,18 @@ class Policy:
     strata: bool = False     # --strata
     max_bts_best: int = 800  # --maxbts on the best-first path
     sample_max: bool = False # -M: keep every hit up to the mhits ceiling
+    paired: bool = False     # reads 2p, 2p+1 are the mates of pair p
+    min_ins: int = 0         # -I
+    max_ins: int = 250       # -X
+    mate1fw: bool = True     # --fr
+    mate2fw: bool = False
+    pair_tries: int = 100    # --pairtries
 
     def to_c(self) -> _Policy:
         return _Policy(self.mode, self.mms, self.seed_len, self.qual_thresh, self.max_bts, self.khits, self.mhits,
                        int(self.all_hits), int(self.nofw), int(self.norc), int(self.maq_round),
-                       int(self.best or self.strata or self.sample_max), int(self.strata), self.max_bts_best, int(self.sample_max))
+                       int(self.best or self.strata or self.sample_max), int(self.strata), self.max_bts_best, int(self.sample_max),
+                       int(self.paired), self.min_ins, self.max_ins, int(self.mate1fw), int(self.mate2fw), self.pair_tries)
 
     @property
     def stateful(self) -> bool:

@@ -32,11 +32,26 @@ enum { BF_PIN_BEGINNING = 1, BF_PIN_LEN, BF_PIN_HI_HALF, BF_PIN_SEED };   /* Sea
 enum { BF_KIND_SRC = 0, BF_KIND_SEEDED = 1 };
 
 struct BfSrcCfg {            /* constructor arguments of one EbwtRangeSource + EbwtRangeSourceDriver */
-	uint8_t ebwtSel, fw, reportExacts, hh, seed, nudgeLeft, useBtCnt, pad;
+	uint8_t ebwtSel, fw, reportExacts, hh, seed, nudgeLeft, useBtCnt, mate;   /* mate: 0 = the read / mate 1, 1 = mate 2 */
 	uint8_t rev[4];
 };
 struct BfTopCfg { uint32_t kind; BfSrcCfg a, b; };   /* a: the driver (or the seedling generator); b: the per-seedling extension driver */
-struct BfProg { uint32_t ntop, seedLen, qualLim, strandFix; BfTopCfg top[BF_MAX_TOP]; };
+struct BfProg {
+	uint32_t ntop, seedLen, qualLim, strandFix; BfTopCfg top[BF_MAX_TOP];
+	/* paired-end (PairedBWAlignerV1): which of the four per-mate, per-strand driver lists exist (do1Fw, do1Rc, do2Fw, do2Rc),
+	 * the reference-scan policy of the opposite mate (RefAligner family) and the insert-size window */
+	uint32_t paired, doList[4], refMms, refSeedLen, refQualMax, minIns, maxIns, fw1, fw2, mixedAttemptLim, symCeiling;
+};
+
+/* BitPairReference (reference.h:20-723): the 2-bit reference of X.4.ebwt with the stretch records of X.3.ebwt */
+struct BtDevRef {
+	const uint32_t *recs;          /* 2 words per record: off (ambiguous characters before the stretch), len */
+	const uint32_t *refRecOffs;    /* nRefs + 1: first record of every reference that has unambiguous characters */
+	const uint32_t *refOffs;       /* nRefs + 1: offset of its first character in buf */
+	const uint32_t *approxLen;     /* nRefs */
+	const uint8_t *buf;            /* 4 characters per byte */
+	uint32_t nRefs;
+};
 
 /* an edit is one arena word: pos | chr << 16 (pos = depth of the edit in a Branch, query offset in a Range; chr = reference base) */
 #define BF_EDIT(pos, chr) ((uint32_t)(pos) | ((uint32_t)(chr) << 16))
@@ -80,6 +95,7 @@ struct BfKParams {
 	BtDevIndex ix[2];
 	BtPolicy pol;
 	BfProg prog;
+	BtDevRef ref;
 	const uint8_t *seq, *qual; const uint64_t *roff; const uint32_t *seeds; const uint32_t *sel; uint32_t nwork;
 	uint32_t *found, *flags, *hits; uint32_t slots, mm_cap, rec_words;
 	uint32_t *arena; uint32_t arenaWords;     /* per lane */
@@ -88,8 +104,8 @@ struct BfKParams {
 
 struct BfCtx {
 	const BfKParams *P;
-	const uint8_t *seq, *qual;
-	uint32_t rid, rlen, seed;
+	const uint8_t *seqM[2], *qualM[2];                    /* [0]: the read (mate 1), [1]: mate 2 */
+	uint32_t rid, rlenM[2], seedM[2];
 	uint32_t *A; uint32_t acap, atop;
 	uint32_t flags, found, randA;
 	int32_t bestStratum, btCnt;
@@ -127,11 +143,11 @@ BT_FN void bf_vec_push(BfCtx &X, uint32_t &off, uint32_t &cap, uint32_t &n, uint
 /* ---- read views (EbwtRangeSource::setQuery, ebwt_search_backtrack.h:1831-1866) ---------------- */
 BT_FN uint32_t bf_qry(const BfCtx &X, const BfSrc &s, uint32_t cur) {
 	for (uint32_t k = 0; k < s.seedNmm; k++) if (s.ovPos[k] == cur) return s.seedRefc[k];   /* qryBuf_ */
-	uint32_t c = X.seq[s.viewRev ? (X.rlen - 1 - cur) : cur];
+	uint32_t c = X.seqM[s.cfg.mate][s.viewRev ? (X.rlenM[s.cfg.mate] - 1 - cur) : cur];
 	if (s.viewComp && c < 4) c ^= 3;
 	return c;
 }
-BT_FN uint32_t bf_qualch(const BfCtx &X, const BfSrc &s, uint32_t cur) { return X.qual[s.viewRev ? (X.rlen - 1 - cur) : cur]; }
+BT_FN uint32_t bf_qualch(const BfCtx &X, const BfSrc &s, uint32_t cur) { return X.qualM[s.cfg.mate][s.viewRev ? (X.rlenM[s.cfg.mate] - 1 - cur) : cur]; }
 BT_FN uint32_t bf_phred(uint32_t ch) { return ch >= 33 ? ch - 33 : 0; }
 
 /* ---- PathManager / BranchQueue ------------------------------------------------------------------ */
@@ -524,14 +540,14 @@ BT_FN uint32_t bf_cext(uint32_t cext, uint32_t sRight, uint32_t s, uint32_t len)
 /* SingleRangeSourceDriver::setQueryImpl (range_source.h:1725-1747) with EbwtRangeSource::setQuery (1831-1866) and
  * EbwtRangeSourceDriver::initRangeSource (2724-2797).  `seed` = the seedling (a BfSrc whose current range it is) or NULL. */
 BT_NOINLINE void bf_src_set_query(BfCtx &X, BfSrc &s, const BfSrc *seed) {
-	const uint32_t len = X.rlen, maq = (uint32_t)X.P->pol.maqRound;
+	const uint32_t len = X.rlenM[s.cfg.mate], maq = (uint32_t)X.P->pol.maqRound;
 	s.h.done = 0;
 	bf_pm_reset(s);
 	s.heapOff = 0; s.heapCap = 0;
 	const bool ebwtFw = s.cfg.ebwtSel == 0;
 	s.viewRev = ebwtFw ? !s.cfg.fw : s.cfg.fw; s.viewComp = !s.cfg.fw;
 	s.seedValid = 0; s.seedNmm = 0; s.seedCost = 0;
-	s.qlen = len; s.skipping = 0; s.rsDone = 0; s.rsFound = 0; s.rnd = X.seed;
+	s.qlen = len; s.skipping = 0; s.rsDone = 0; s.rsFound = 0; s.rnd = X.seedM[s.cfg.mate];
 	if (seed) {
 		s.seedValid = 1; s.seedCost = seed->rCost;
 		uint32_t n = seed->rNmm; if (n > 3) { n = 3; X.flags |= BT_FLAG_MM_OVF; }
@@ -694,7 +710,7 @@ BT_FN void bf_ca_copy_active(BfCtx &X, BfCA &ca) {                       /* acti
 /* CostAwareRangeSourceDriver::setQueryImpl (range_source.h:2072-2088) */
 BT_FN void bf_ca_set_query_empty(BfCtx &X, BfCA &ca) {                    /* rss_ is empty: the seeded driver's list after clearSources */
 	ca.done = 0; ca.foundRange = 0; ca.lastRange = 0; ca.delayedRange = 0;
-	ca.rnd = X.seed;
+	ca.rnd = X.seedM[0];                                                  /* rand_.init(patsrc->bufa().seed) */
 }
 BT_NOINLINE void bf_ca_set_query(BfCtx &X, BfCA &ca) {
 	bf_ca_set_query_empty(X, ca);
@@ -781,34 +797,49 @@ BT_FN bool bf_irrelevant_cost(const BfCtx &X, uint32_t cost) {
 	if (X.found) return (int32_t)(cost >> 14) > X.bestStratum;
 	return false;
 }
-/* UnpairedAlignerV2::report → EbwtSearchParams::reportHit (ebwt.h:1288-1405) → the per-thread sink's reportHit
- * (NGood hit.h:969-985, NBestFirstStrat 1070-1094, AllHit 1201-1209).  Returns true when the read is finished. */
-BT_NOINLINE bool bf_report(BfCtx &X, const BfSrc &ra, uint32_t tidx, uint32_t toff) {
+/* A Range as the aligners hand it to EbwtSearchParams::reportHit: found by a range source (index) or by the reference scan */
+struct BfRangeView { uint32_t top, bot, cost, nmm, edits; uint8_t fw, ebwtFw, mate, pad; };
+BT_FN BfRangeView bf_view_of(const BfSrc &s) {
+	BfRangeView v; v.top = s.rTop; v.bot = s.rBot; v.cost = s.rCost; v.nmm = s.rNmm; v.edits = s.rEdits;
+	v.fw = s.cfg.fw; v.ebwtFw = s.cfg.ebwtSel == 0; v.mate = s.cfg.mate; v.pad = 0;
+	return v;
+}
+/* EbwtSearchParams::reportHit (ebwt.h:1288-1405) → the per-thread sink's reportHit (NGood hit.h:969-985, NBestFirstStrat
+ * 1070-1094, AllHit 1201-1209).  `mult` = 2 for paired sinks (createMult), `mateNo` = Hit::mate (0 unpaired, 1, 2).
+ * Returns true when the read (pair) is finished. */
+BT_NOINLINE bool bf_report_hit(BfCtx &X, const BfRangeView &ra, uint32_t tidx, uint32_t toff, uint32_t oms, uint32_t mateNo, uint32_t mult) {
 	const BfKParams &P = *X.P;
 	const BtPolicy &pol = P.pol;
-	const uint32_t n = pol.allHits ? (pol.strata ? 0x7fffffffu : 0xffffffffu) : pol.khits;
-	const uint32_t stratum = ra.rCost >> 14;
+	uint32_t n = pol.allHits ? (pol.strata ? 0x7fffffffu : 0xffffffffu) : pol.khits;
+	uint32_t mx = pol.mhits;
+	if (mult > 1) { if (n != 0xffffffffu) n *= mult; if (mx != 0xffffffffu) mx *= mult; }
+	const uint32_t stratum = ra.cost >> 14;
 	X.found++;
 	if ((int32_t)stratum < X.bestStratum) X.bestStratum = (int32_t)stratum;
-	if (X.found > pol.mhits) return true;
-	const uint32_t keep = (pol.sampleMax && pol.mhits != 0xffffffffu && pol.mhits > n) ? pol.mhits : n;   /* bufferHit precedes the n test */
+	if (X.found > mx) return true;
+	const uint32_t keep = (pol.sampleMax && mx != 0xffffffffu && mx > n) ? mx : n;   /* bufferHit precedes the n test */
 	if (X.found <= keep) {
 		if (X.found <= P.slots) {
 			uint32_t *rec = P.hits + ((size_t)X.rid * P.slots + (X.found - 1)) * P.rec_words;
-			rec[0] = tidx; rec[1] = toff; rec[2] = ra.rBot - ra.rTop - 1;
-			rec[3] = (uint32_t)ra.rCost | (stratum << 16) | ((uint32_t)ra.cfg.fw << 24);
-			rec[4] = ra.rNmm;
-			const bool flip = (ra.cfg.ebwtSel == 0) != (ra.cfg.fw != 0);        /* ebwt.h:1339-1350 */
-			for (uint32_t i = 0; i < ra.rNmm; i++) {
-				const uint32_t e = X.A[ra.rEdits + i];
+			rec[0] = tidx; rec[1] = toff; rec[2] = oms;
+			rec[3] = (ra.cost & 0xffffu) | (stratum << 16) | ((uint32_t)ra.fw << 24) | (mateNo << 25);
+			rec[4] = ra.nmm;
+			const bool flip = (ra.ebwtFw != 0) != (ra.fw != 0);                 /* ebwt.h:1339-1350 */
+			const uint32_t qlen = X.rlenM[ra.mate];
+			for (uint32_t i = 0; i < ra.nmm; i++) {
+				const uint32_t e = X.A[ra.edits + i];
 				uint32_t pos = BF_EDIT_POS(e);
-				if (flip) pos = X.rlen - pos - 1;
+				if (flip) pos = qlen - pos - 1;
 				if (i < P.mm_cap) rec[BT_HIT_HDR + i] = BF_EDIT(pos, BF_EDIT_CHR(e)); else X.flags |= BT_FLAG_MM_OVF;
 			}
 		} else X.flags |= BT_FLAG_HITS_OVF;
 	}
-	if (!(pol.allHits && !pol.strata) && X.found == n && (pol.mhits == 0xffffffffu || pol.mhits < n)) return true;
+	if (!(pol.allHits && !pol.strata) && X.found == n && (mx == 0xffffffffu || mx < n)) return true;
 	return false;
+}
+/* UnpairedAlignerV2::report (aligner.h:462-492) */
+BT_FN bool bf_report(BfCtx &X, const BfSrc &ra, uint32_t tidx, uint32_t toff) {
+	return bf_report_hit(X, bf_view_of(ra), tidx, toff, ra.rBot - ra.rTop - 1, 0, 1);
 }
 
 /* RowChaser (row_chaser.h:60-110): resolve one BW row to a joined-text offset */
@@ -827,9 +858,9 @@ BT_FN uint32_t bf_resolve_row(BfCtx &X, const BtDevIndex &ix, uint32_t row) {
 /* ---- UnpairedAlignerV2 (aligner.h:420-560) ------------------------------------------------------ */
 BT_NOINLINE void bf_align_read(BfCtx &X) {
 	const BfKParams &P = *X.P;
-	X.randA = X.seed;                                                     /* Aligner::setQuery: rand_.init(seed) */
+	X.randA = X.seedM[0];                                                 /* Aligner::setQuery: rand_.init(seed) */
 	X.found = 0; X.bestStratum = 999; X.btCnt = (int32_t)P.pol.maxBtsBest;
-	if (X.rlen < 4) return;                                               /* "Skipping read ... less than 4 characters long" */
+	if (X.rlenM[0] < 4) return;                                           /* "Skipping read ... less than 4 characters long" */
 	/* build this read's driver tree (the reference builds it once per thread and re-targets it with setQuery) */
 	BfCA &top = X.top;
 	top.rssOff = bf_alloc(X, BF_MAX_TOP); top.rssCap = BF_MAX_TOP; top.nRss = 0;
@@ -869,7 +900,7 @@ BT_NOINLINE void bf_align_read(BfCtx &X) {
 				}
 				cPending = false;
 				const uint32_t off = bf_resolve_row(X, ix, cRow);
-				foundOff = bt_joined_to_text(ix, X.rlen, off, tidx, toff);
+				foundOff = bt_joined_to_text(ix, X.rlenM[0], off, tidx, toff);
 			}
 			if (foundOff) done = bf_report(X, ra, tidx, toff);
 			else { chase = false; top.foundRange = 0; done = top.done; }
@@ -886,7 +917,7 @@ BT_NOINLINE void bf_align_read(BfCtx &X) {
 				for (;;) {
 					if (cRow != ix.zOff && (cRow & ix.offMask) != cRow) { cPending = true; break; }
 					const uint32_t off = bf_resolve_row(X, ix, cRow);
-					if (bt_joined_to_text(ix, X.rlen, off, tidx, toff)) { foundOff = true; break; }
+					if (bt_joined_to_text(ix, X.rlenM[0], off, tidx, toff)) { foundOff = true; break; }
 					cRow++; if (cRow == cBot) cRow = cTop;
 					if (cRow == cIrow) { cDone = true; break; }
 				}
@@ -899,5 +930,352 @@ BT_NOINLINE void bf_align_read(BfCtx &X) {
 			}
 			if (top.done && !top.foundRange && !chase) done = true;
 		}
+	}
+}
+
+/* ================================================================================================= */
+/* Paired-end: PairedBWAlignerV1 (aligner.h:606-1468) with dontReconcileMates (the default,          */
+/* ebwt_search.cpp:219): every resolved offset of one mate anchors a scan of the reference window in  */
+/* which the opposite mate may lie (RefAligner family, ref_aligner.h; BitPairReference, reference.h). */
+/* ================================================================================================= */
+
+/* BitPairReference::getStretch (reference.h:455-640; the naive form 417-453 defines it): `count` characters of reference
+ * `tidx` from `toff`, 4 for ambiguous stretches and past the end.  Staged as bytes in the arena; returns the word offset. */
+BT_NOINLINE uint32_t bf_ref_stretch(BfCtx &X, uint32_t tidx, uint32_t toff, uint32_t count) {
+	const BtDevRef &R = X.P->ref;
+	const uint32_t words = (count + 3) / 4 + 1;
+	const uint32_t aoff = bf_alloc(X, words);
+	if (!aoff) return 0;
+	uint8_t *dest = (uint8_t *)(X.A + aoff);
+	uint32_t cur = 0, off = 0;
+	const uint32_t reci = BT_LDG(R.refRecOffs + tidx), recf = BT_LDG(R.refRecOffs + tidx + 1);
+	uint32_t bufOff = BT_LDG(R.refOffs + tidx);
+	for (uint32_t i = reci; i < recf && count > 0; i++) {
+		const uint32_t roff = BT_LDG(R.recs + 2 * (size_t)i), rlen = BT_LDG(R.recs + 2 * (size_t)i + 1);
+		off += roff;
+		for (; toff < off && count > 0; toff++) { dest[cur++] = 4; count--; }
+		if (count == 0) break;
+		if (toff < off + rlen) bufOff += toff - off; else bufOff += rlen;
+		off += rlen;
+		for (; toff < off && count > 0; toff++) {
+			dest[cur++] = (uint8_t)((BT_LDG(R.buf + (bufOff >> 2)) >> ((bufOff & 3) << 1)) & 3);
+			bufOff++; count--;
+		}
+	}
+	while (count > 0) { dest[cur++] = 4; count--; }
+	return aoff;
+}
+
+struct BfPairSet { uint32_t off, cap, n; };       /* TSetPairs pairs_fw_ / pairs_rc_: (tidx, lo, hi) triples */
+
+/* RefAligner::find(1, ...) (ref_aligner.h:63-97).  The eight concrete aligners (Exact/OneMM/TwoMM/ThreeMM for -v,
+ * Seed0..3 for -n) are hand-unrolled 64-bit-anchor scans of one definition — their naiveFind members, which the
+ * reference's debug build checks them against: candidates in zig-zag order from the middle of the window, a reference N
+ * anywhere kills the candidate, a query N is a mismatch, at most `refMms` mismatches in the seed (the whole read for -v),
+ * quality-weighted distance <= qualMax, first survivor that is not already in `pairs` wins.
+ * qry = the mate in the orientation it must have on the forward reference strand; the seed is at its 5' end, which is the
+ * left end iff `seedOnLeft` (= fw).  Returns true and fills `out` / `result` (leftmost reference offset). */
+BT_NOINLINE bool bf_ref_find(BfCtx &X, uint32_t mate, bool fw, uint32_t tidx, uint32_t begin, uint32_t end, uint32_t aoff,
+                             BfPairSet &pairs, BfRangeView &out, uint32_t &result) {
+	const BfProg &g = X.P->prog;
+	const uint32_t qlen = X.rlenM[mate], maq = (uint32_t)X.P->pol.maqRound;
+	const uint8_t *seq = X.seqM[mate], *qual = X.qualM[mate];
+	const bool seedOnLeft = fw;
+	const uint32_t slen = g.refSeedLen ? (qlen < g.refSeedLen ? qlen : g.refSeedLen) : qlen;
+	const uint32_t spread = end - begin;
+	const uint32_t refOff = bf_ref_stretch(X, tidx, begin, spread);
+	if (!refOff) return false;
+	const uint8_t *ref = (const uint8_t *)(X.A + refOff);
+	const uint32_t editsOff = bf_alloc(X, qlen ? qlen : 1);                    /* worst case: every position mismatches */
+	if (!editsOff) return false;
+	const uint32_t lim = end - qlen - begin;
+	const uint32_t halfway = begin + (lim >> 1);
+	bool hi = false, found = false;
+	for (uint32_t i = 1; i <= lim + 1 && !found; i++) {
+		const uint32_t L = hi ? halfway + (i >> 1) : halfway - (i >> 1);
+		hi = !hi;
+		const uint32_t rir = L - begin;
+		bool match = true;
+		uint32_t mms = 0, seedMms = 0, ham = 0;
+		for (uint32_t jj = 0; jj < qlen; jj++) {
+			const uint32_t j = seedOnLeft ? jj : qlen - 1 - jj;
+			const uint32_t r = ref[rir + j];
+			if (r & 4) { match = false; break; }
+			uint32_t q = fw ? seq[j] : seq[qlen - 1 - j];
+			if (!fw && q < 4) q ^= 3;
+			if (q != r) {
+				if (mms + 1 > g.refMms && jj < slen) { match = false; break; }
+				const uint32_t qc = fw ? qual[j] : qual[qlen - 1 - j];
+				ham += bt_mm_penalty(maq, bf_phred(qc));
+				if (ham > g.refQualMax) { match = false; break; }
+				X.A[editsOff + mms] = BF_EDIT(j, r);
+				mms++;
+				if (jj < slen) seedMms++;
+			}
+		}
+		if (!match) continue;
+		const uint32_t lo = L < aoff ? L : aoff, hi2 = L < aoff ? aoff : L;
+		bool dup = false;
+		for (uint32_t k = 0; k < pairs.n; k++) { const uint32_t *t = X.A + pairs.off + 3 * k; if (t[0] == tidx && t[1] == lo && t[2] == hi2) { dup = true; break; } }
+		if (dup) continue;
+		{   /* pairs->insert(p) */
+			if (pairs.n == pairs.cap) {
+				const uint32_t ncap = pairs.cap ? pairs.cap * 2 : 8;
+				const uint32_t noff = bf_alloc(X, 3 * ncap);
+				if (!noff) return false;
+				for (uint32_t k = 0; k < 3 * pairs.n; k++) X.A[noff + k] = X.A[pairs.off + k];
+				pairs.off = noff; pairs.cap = ncap;
+			}
+			uint32_t *t = X.A + pairs.off + 3 * pairs.n++;
+			t[0] = tidx; t[1] = lo; t[2] = hi2;
+		}
+		out.nmm = mms; out.edits = editsOff; out.cost = seedMms << 14;           /* r.cost |= (r.stratum << 14), aligner.h:1064 */
+		out.fw = fw; out.ebwtFw = 1; out.mate = (uint8_t)mate; out.pad = 0;
+		result = L;
+		found = true;
+	}
+	return found;
+}
+
+/* RangeChaser + RowChaser, step for step (range_chaser.h:40-210, row_chaser.h:60-110) */
+struct BfChaser { uint32_t top, bot, irow, row, qlen, ebwtSel, tidx, toff; bool done, rowDone, hasOff; };
+BT_FN void bf_chaser_set_row(BfCtx &X, BfChaser &c, uint32_t row) {
+	const BtDevIndex &ix = X.P->ix[c.ebwtSel];
+	c.row = row;
+	for (;;) {
+		if (c.row != ix.zOff && (c.row & ix.offMask) != c.row) { c.rowDone = false; return; }   /* needs a walk: RangeChaser::advance does it */
+		c.rowDone = true;
+		const uint32_t off = bf_resolve_row(X, ix, c.row);
+		if (bt_joined_to_text(ix, c.qlen, off, c.tidx, c.toff)) { c.hasOff = true; return; }
+		c.row++;
+		if (c.row == c.bot) c.row = c.top;
+		if (c.row == c.irow) { c.done = true; return; }
+	}
+}
+BT_FN void bf_chaser_set_top_bot(BfCtx &X, BfChaser &c, uint32_t top, uint32_t bot, uint32_t qlen, uint32_t ebwtSel) {
+	c.ebwtSel = ebwtSel; c.qlen = qlen; c.top = top; c.bot = bot;
+	c.irow = top + bt_rand_next(X.randA) % (bot - top);
+	c.done = false; c.hasOff = false;
+	bf_chaser_set_row(X, c, c.irow);
+}
+BT_FN void bf_chaser_advance(BfCtx &X, BfChaser &c) {
+	c.hasOff = false;
+	if (c.rowDone) {
+		c.row++;
+		if (c.row == c.bot) c.row = c.top;
+		if (c.row == c.irow) { c.done = true; return; }
+		bf_chaser_set_row(X, c, c.row);
+	} else {
+		const BtDevIndex &ix = X.P->ix[c.ebwtSel];
+		const uint32_t off = bf_resolve_row(X, ix, c.row);
+		c.rowDone = true;
+		if (bt_joined_to_text(ix, c.qlen, off, c.tidx, c.toff)) c.hasOff = true;
+	}
+}
+
+struct BfPairState {
+	BfCA dr[4];                       /* 0: mate 1 fw, 1: mate 1 rc, 2: mate 2 fw, 3: mate 2 rc                   */
+	bool chase[4], delayed[4]; uint32_t offsSz[4];
+	BfPairSet pairs[2];               /* [0] fw orientation of the pair, [1] rc                                     */
+	BfChaser rc;
+	uint32_t L, R, mixedAttempts;
+	bool doneFw, doneFwFirst, done;
+};
+
+/* PairedBWAlignerV1::report (aligner.h:855-945): the upstream mate first, then the downstream one */
+BT_NOINLINE bool bf_pair_report(BfCtx &X, const BfRangeView &rL, const BfRangeView &rR, uint32_t tidx, uint32_t upOff, uint32_t dnOff, bool pairFw) {
+	const uint32_t spreadL = rL.bot - rL.top, spreadR = rR.bot - rR.top;
+	const uint32_t oms = (spreadL < spreadR ? spreadL : spreadR) - 1;
+	if (bf_report_hit(X, rL, tidx, upOff, oms, pairFw ? 1u : 2u, 2)) return true;    /* "can happen when -m is set" */
+	return bf_report_hit(X, rR, tidx, dnOff, oms, pairFw ? 2u : 1u, 2);
+}
+
+/* PairedBWAlignerV1::resolveOutstandingInRef (aligner.h:951-1087).  off1: the anchor is mate 1. */
+BT_NOINLINE bool bf_pair_resolve_in_ref(BfCtx &X, BfPairState &S, bool off1, uint32_t tidx, uint32_t toff, const BfSrc &range) {
+	const BfProg &g = X.P->prog;
+	const bool matchRight = off1 ? !S.doneFw : S.doneFw;
+	bool fw = off1 ? (g.fw2 != 0) : (g.fw1 != 0);                       /* orientation of the outstanding mate */
+	if (S.doneFw) fw = !fw;
+	const uint32_t omate = off1 ? 1u : 0u;
+	const uint32_t qlen = X.rlenM[omate], alen = X.rlenM[omate ^ 1];
+	const uint32_t minins = g.minIns, maxins = g.maxIns;                    /* trimming adjustments are applied by the host (policy) */
+	if (maxins <= (qlen > alen ? qlen : alen)) return false;
+	uint32_t begin, end;
+	const uint32_t insDiff = maxins - minins;
+	const uint32_t approx = BT_LDG(X.P->ref.approxLen + tidx);
+	if (matchRight) {
+		end = toff + maxins;
+		begin = toff + 1;
+		if (qlen < alen) begin += alen - qlen;
+		if (end > insDiff + qlen) { const uint32_t b2 = end - insDiff - qlen; if (b2 > begin) begin = b2; }
+		if (end > approx) end = approx;
+		if (begin > approx) begin = approx;
+	} else {
+		if (toff + alen < maxins) begin = 0; else begin = toff + alen - maxins;
+		const uint32_t mi = alen < qlen ? alen : qlen;
+		end = toff + mi - 1;
+		const uint32_t e2 = toff + alen - minins + qlen - 1;
+		if (e2 < end) end = e2;
+		if (toff + alen + qlen < minins + 1) end = 0;
+	}
+	if (end < begin || end - begin < qlen) return false;
+	const uint32_t mark = X.atop;
+	BfRangeView r; uint32_t result = 0;
+	const bool got = bf_ref_find(X, omate, fw, tidx, begin, end, toff, S.pairs[S.doneFw ? 1 : 0], r, result);
+	bool ret = false;
+	if (got) {
+		r.top = range.rTop; r.bot = range.rBot;
+		const BfRangeView a = bf_view_of(range);
+		BfRangeView av = a;
+		/* the found mate is reported as if aligned on the forward index; the anchor keeps its own index direction */
+		ret = bf_pair_report(X, matchRight ? av : r, matchRight ? r : av, tidx, matchRight ? toff : result, matchRight ? result : toff, !S.doneFw);
+	}
+	/* scratch of this attempt (window, edits) is dead; the pair set may have been re-allocated above `mark` */
+	if (X.atop > mark) {
+		BfPairSet &ps = S.pairs[S.doneFw ? 1 : 0];
+		if (!(ps.off >= mark)) X.atop = mark;
+	}
+	return ret;
+}
+
+/* PairedBWAlignerV1::advanceOrientation (aligner.h:1092-1326) */
+BT_NOINLINE void bf_pair_advance_orientation(BfCtx &X, BfPairState &S, bool pairFw) {
+	const BfProg &g = X.P->prog;
+	const uint32_t L = S.L, R = S.R;
+	BfCA &drL = S.dr[L], &drR = S.dr[R];
+	bool &donePair = S.doneFw ? S.done : S.doneFw;
+	const uint32_t qlenL = S.doneFw ? X.rlenM[1] : X.rlenM[0], qlenR = S.doneFw ? X.rlenM[0] : X.rlenM[1];
+	if (S.chase[L]) {
+		if (S.rc.hasOff) {
+			if (!S.done) {                                                  /* overThresh || dontReconcile_ */
+				const BfSrc &r = *BF_AT(BfSrc, X, drL.lastRange);
+				S.done = bf_pair_resolve_in_ref(X, S, pairFw, S.rc.tidx, S.rc.toff, r);
+				if (++S.mixedAttempts > g.mixedAttemptLim) { donePair = true; return; }
+			}
+			S.rc.hasOff = false;
+		} else {
+			S.chase[L] = false; drL.foundRange = 0;
+			if (S.delayed[R]) {
+				const BfSrc &r = *BF_AT(BfSrc, X, drR.lastRange);
+				bf_chaser_set_top_bot(X, S.rc, r.rTop, r.rBot, qlenR, r.cfg.ebwtSel);
+				S.chase[R] = true; S.delayed[R] = false;
+			}
+		}
+	} else if (S.chase[R]) {
+		if (S.rc.hasOff) {
+			if (!S.done) {
+				const BfSrc &r = *BF_AT(BfSrc, X, drR.lastRange);
+				S.done = bf_pair_resolve_in_ref(X, S, !pairFw, S.rc.tidx, S.rc.toff, r);
+				if (++S.mixedAttempts > g.mixedAttemptLim) { donePair = true; return; }
+			}
+			S.rc.hasOff = false;
+		} else {
+			S.chase[R] = false; drR.foundRange = 0;
+			if (S.delayed[L]) {
+				const BfSrc &r = *BF_AT(BfSrc, X, drL.lastRange);
+				bf_chaser_set_top_bot(X, S.rc, r.rTop, r.rBot, qlenL, r.cfg.ebwtSel);
+				S.chase[L] = true; S.delayed[L] = false;
+			}
+		}
+	}
+	if (!S.done && !donePair && !S.chase[L] && !S.chase[R]) {
+		if ((S.offsSz[L] < S.offsSz[R] || drR.done) && !drL.done) {
+			if (drR.done && S.offsSz[R] == 0) { donePair = true; return; }
+			if (!drL.foundRange) bf_ca_advance<true>(X, drL, g.strandFix != 0);
+			if (X.flags & (BT_FLAG_STACK_OVF | BT_FLAG_FRAME_OVF)) return;
+			if (drL.foundRange) {
+				const BfSrc &rl = *BF_AT(BfSrc, X, drL.lastRange);
+				S.offsSz[L] += rl.rBot - rl.rTop;
+				if (S.offsSz[R] == 0 && S.offsSz[L] > 3) S.delayed[L] = true;   /* !dontReconcile_ || offsLsz > 3 */
+				else {
+					if (S.offsSz[L] > g.symCeiling && S.offsSz[R] > g.symCeiling) { donePair = true; return; }
+					if (S.delayed[R] && S.offsSz[R] < S.offsSz[L]) {
+						S.delayed[R] = false; S.delayed[L] = true; S.chase[R] = true;
+						const BfSrc &r = *BF_AT(BfSrc, X, drR.lastRange);
+						bf_chaser_set_top_bot(X, S.rc, r.rTop, r.rBot, qlenR, r.cfg.ebwtSel);
+					} else {
+						S.chase[L] = true;
+						bf_chaser_set_top_bot(X, S.rc, rl.rTop, rl.rBot, qlenL, rl.cfg.ebwtSel);
+					}
+				}
+			}
+		} else if (!drR.done) {
+			if (drL.done && S.offsSz[L] == 0) { donePair = true; return; }
+			if (!drR.foundRange) bf_ca_advance<true>(X, drR, g.strandFix != 0);
+			if (X.flags & (BT_FLAG_STACK_OVF | BT_FLAG_FRAME_OVF)) return;
+			if (drR.foundRange) {
+				const BfSrc &rr = *BF_AT(BfSrc, X, drR.lastRange);
+				S.offsSz[R] += rr.rBot - rr.rTop;
+				if (S.offsSz[L] == 0 && S.offsSz[R] > 3) S.delayed[R] = true;
+				else {
+					if (S.offsSz[L] > g.symCeiling && S.offsSz[R] > g.symCeiling) { donePair = true; return; }
+					if (S.delayed[L] && S.offsSz[L] < S.offsSz[R]) {
+						S.delayed[L] = false; S.delayed[R] = true; S.chase[L] = true;
+						const BfSrc &r = *BF_AT(BfSrc, X, drL.lastRange);
+						bf_chaser_set_top_bot(X, S.rc, r.rTop, r.rBot, qlenL, r.cfg.ebwtSel);
+					} else {
+						S.chase[R] = true;
+						bf_chaser_set_top_bot(X, S.rc, rr.rTop, rr.rBot, qlenR, rr.cfg.ebwtSel);
+					}
+				}
+			}
+		} else donePair = true;
+	}
+}
+
+/* PairedBWAlignerV1::setQuery + the advance() loop of MixedMultiAligner (aligner.h:733-848, 244-304) */
+BT_NOINLINE void bf_align_pair(BfCtx &X) {
+	const BfKParams &P = *X.P;
+	const BfProg &g = P.prog;
+	X.randA = X.seedM[0];
+	X.found = 0; X.bestStratum = 999; X.btCnt = (int32_t)P.pol.maxBtsBest;
+	if (X.rlenM[0] < 4 || X.rlenM[1] < 4) return;                           /* "Skipping pair ... a mate is less than 4 characters long" */
+	BfPairState S;
+	for (uint32_t k = 0; k < 4; k++) {
+		BfCA &ca = S.dr[k];
+		ca.rssOff = bf_alloc(X, BF_MAX_TOP); ca.rssCap = BF_MAX_TOP; ca.nRss = 0;
+		ca.actOff = bf_alloc(X, BF_MAX_TOP); ca.actCap = BF_MAX_TOP; ca.nAct = 0;
+		ca.minCost = 0; ca.lastRange = ca.delayedRange = 0; ca.done = 0; ca.foundRange = 0; ca.rnd = 0;
+		S.chase[k] = S.delayed[k] = false; S.offsSz[k] = 0;
+		if (X.flags & BT_FLAG_STACK_OVF) return;
+		if (g.doList[k]) {
+			const uint32_t wantFw = (k & 1) ? 0u : 1u, mate = k >> 1;
+			for (uint32_t i = 0; i < g.ntop; i++) {
+				BfTopCfg tc = g.top[i];
+				if (tc.a.fw != wantFw) continue;
+				tc.a.mate = (uint8_t)mate; tc.b.mate = (uint8_t)mate;
+				uint32_t node;
+				if (tc.kind == BF_KIND_SRC) node = bf_src_new(X, tc.a);
+				else {
+					node = bf_alloc_zero(X, BF_SEEDED_WORDS);
+					if (node) {
+						BfSeeded &sd = *BF_AT(BfSeeded, X, node);
+						sd.h.kind = BF_KIND_SEEDED; sd.h.done = 1; sd.h.fw = tc.a.fw; sd.fact = tc.b;
+						sd.seedgen = bf_src_new(X, tc.a);
+					}
+				}
+				if (X.flags & BT_FLAG_STACK_OVF) return;
+				X.A[ca.rssOff + ca.nRss++] = node;
+			}
+		}
+	}
+	for (uint32_t k = 0; k < 4; k++) {
+		/* CostAwareRangeSourceDriver's constructor leaves an empty list "not done, nothing found"; setQuery on it returns early */
+		bf_ca_set_query(X, S.dr[k]);
+		if (X.flags & BT_FLAG_STACK_OVF) return;
+	}
+	S.pairs[0].off = S.pairs[0].cap = S.pairs[0].n = 0; S.pairs[1] = S.pairs[0];
+	S.rc.done = false; S.rc.hasOff = false; S.rc.rowDone = true;
+	S.doneFw = false; S.doneFwFirst = true; S.done = false; S.mixedAttempts = 0;
+	S.L = g.fw1 ? 0u : 1u; S.R = g.fw2 ? 2u : 3u;
+	while (!S.done) {
+		if (X.flags & (BT_FLAG_STACK_OVF | BT_FLAG_FRAME_OVF)) return;
+		if (S.doneFw && S.doneFwFirst) {
+			S.L = g.fw2 ? 3u : 2u; S.R = g.fw1 ? 1u : 0u;
+			S.doneFwFirst = false; S.mixedAttempts = 0;
+		}
+		const bool chasing = S.chase[S.L] || S.chase[S.R];
+		if (chasing && !S.rc.hasOff && !S.rc.done) { bf_chaser_advance(X, S.rc); continue; }
+		bf_pair_advance_orientation(X, S, !S.doneFw);
 	}
 }

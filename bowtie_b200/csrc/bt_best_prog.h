@@ -24,8 +24,23 @@ static inline BfSrcCfg bf_cfg(int mirror, int fw, int reportExacts, int hh, int 
 	return c;
 }
 
-static inline void bf_build_prog(int mode, int mms, int seedLen, uint32_t qualThresh, int nofw, int norc, BfProg *out) {
+/* Paired-end additions: PairedExact/1mm/23mm/SeedAlignerFactory::create (aligner_0mm.h:213-345, aligner_1mm.h:255-470,
+ * aligner_23mm.h:319-650, aligner_seed_mm.h:650-1351) build the same driver lists once per mate and strand and pick the
+ * RefAligner that matches the policy. */
+static inline void bf_build_prog(int mode, int mms, int seedLen, uint32_t qualThresh, int nofw, int norc, BfProg *out,
+                                 int paired = 0, int mate1fw = 1, int mate2fw = 0, uint32_t minIns = 0, uint32_t maxIns = 250,
+                                 uint32_t pairTries = 100, uint32_t mhits = 0xffffffffu) {
 	BfProg &g = *out; memset(&g, 0, sizeof g);
+	if (paired) {
+		g.paired = 1; g.fw1 = mate1fw ? 1 : 0; g.fw2 = mate2fw ? 1 : 0; g.minIns = minIns; g.maxIns = maxIns;
+		g.mixedAttemptLim = pairTries; g.symCeiling = mhits;
+		g.refMms = (uint32_t)mms; g.refSeedLen = mode == 0 ? 0u : (uint32_t)seedLen; g.refQualMax = mode == 0 ? 0xffffffffu : qualThresh;
+		bool d1f = true, d1r = true, d2f = true, d2r = true;
+		if (nofw) { if (mate1fw) d1f = false; else d1r = false; if (mate2fw) d2f = false; else d2r = false; }
+		if (norc) { if (mate1fw) d1r = false; else d1f = false; if (mate2fw) d2r = false; else d2f = false; }
+		g.doList[0] = d1f; g.doList[1] = d1r; g.doList[2] = d2f; g.doList[3] = d2r;
+		nofw = norc = 0;                                                 /* the table below holds both strands; doList selects */
+	}
 	const int B = BF_PIN_BEGINNING, L = BF_PIN_LEN, H = BF_PIN_HI_HALF, S = BF_PIN_SEED;
 	g.strandFix = 1;                                                     /* ebwt_search.cpp:227 */
 #define SRC(cfg) do { g.top[g.ntop].kind = BF_KIND_SRC; g.top[g.ntop].a = (cfg); g.ntop++; } while (0)

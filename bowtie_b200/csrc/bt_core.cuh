@@ -79,6 +79,10 @@ struct BtPolicy {
 	int32_t best, strata;   /* best-first ("stateful") path, bt_best.cuh    */
 	uint32_t maxBtsBest;    /* its backtrack budget (maxBts, ebwt_search.cpp:186) */
 	int32_t sampleMax;      /* -M: keep every hit up to the -m ceiling      */
+	int32_t paired;         /* reads 2p, 2p+1 of the batch are mates 1, 2   */
+	uint32_t minIns, maxIns;/* -I / -X (after trimming adjustments)          */
+	int32_t mate1fw, mate2fw;   /* --fr: 1,0  --rf: 0,1  --ff: 1,1            */
+	uint32_t pairTries;     /* --pairtries (mixedAttemptLim)                 */
 };
 
 /* flags written per read */

@@ -342,8 +342,9 @@ bt_best_kernel(const __grid_constant__ BfKParams P, BtWorkCtl *ctl, uint32_t lan
 		if (w >= nwork) break;
 		const uint32_t rid = P.sel ? P.sel[w] : (uint32_t)w;
 		const unsigned long long ro = P.roff[rid];
-		X.rid = rid; X.rlen = (uint32_t)(P.roff[rid + 1] - ro); X.seed = P.seeds[rid];
-		X.seq = P.seq + ro; X.qual = P.qual + ro;
+		X.rid = rid; X.rlenM[0] = (uint32_t)(P.roff[rid + 1] - ro); X.seedM[0] = P.seeds[rid];
+		X.seqM[0] = P.seq + ro; X.qualM[0] = P.qual + ro;
+		X.rlenM[1] = 0; X.seedM[1] = 0; X.seqM[1] = X.seqM[0]; X.qualM[1] = X.qualM[0];
 		X.atop = 1; X.flags = 0; X.found = 0;
 		X.top.rssOff = X.top.rssCap = X.top.nRss = X.top.actOff = X.top.actCap = X.top.nAct = 0;
 		X.top.lastRange = X.top.delayedRange = 0; X.top.minCost = 0; X.top.done = 0; X.top.foundRange = 0; X.top.rnd = 0;
@@ -524,7 +525,7 @@ extern "C" const char *bt_last_error(void) { return g_err.c_str(); }
 
 extern "C" void bt_policy_init(bt_policy_t *p) {
 	memset(p, 0, sizeof *p);
-	p->mode = 1; p->mms = 2; p->seed_len = 28; p->qual_thresh = 70; p->max_bts = 125; p->khits = 1; p->mhits = 0xffffffffu; p->maq_round = 1; p->max_bts_best = 800;
+	p->mode = 1; p->mms = 2; p->seed_len = 28; p->qual_thresh = 70; p->max_bts = 125; p->khits = 1; p->mhits = 0xffffffffu; p->maq_round = 1; p->max_bts_best = 800; p->max_ins = 250; p->mate1fw = 1; p->pair_tries = 100;
 }
 
 extern "C" void bt_context_free(bt_context_t *cx) {

@@ -34,6 +34,8 @@ struct Opts {
 	std::vector<std::string> queries;
 	int mismatches = 0, seedMms = 2, maqLike = 1, seedLen = 28, qualThresh = 70, maxBts = 125, maxBtsBest = 800;
 	bool best = false, strata = false, sampleMax = false;
+	std::vector<std::string> mates1, mates2;
+	uint32_t minInsert = 0, maxInsert = 250, pairTries = 100; bool mate1fw = true, mate2fw = false;
 	bool noMaqRound = false, nofw = false, norc = false, allHits = false;
 	uint32_t khits = 1, mhits = 0xffffffffu;
 	uint32_t skipReads = 0, qUpto = 0xffffffffu;
@@ -59,7 +61,7 @@ enum {
 	ARG_PHRED33 = 256, ARG_PHRED64, ARG_SOLEXA, ARG_SOLEXA13, ARG_NOMAQROUND, ARG_NOFW, ARG_NORC, ARG_MAXBTS, ARG_BEST, ARG_STRATA,
 	ARG_QUIET, ARG_REFIDX, ARG_SUPPRESS, ARG_FULLREF, ARG_MAPQ, ARG_SAM_NOHEAD, ARG_SAM_NOSQ, ARG_SAM_RG, ARG_NO_UNAL, ARG_SEED,
 	ARG_COST, ARG_REORDER, ARG_WRAPPER, ARG_VERSION, ARG_IGNORED0, ARG_IGNORED1, ARG_DEVICE, ARG_BATCH, ARG_SAM_NO_QNAME_TRUNC,
-	ARG_LARGE_INDEX, ARG_PAIRED
+	ARG_LARGE_INDEX, ARG_PAIRED, ARG_FF, ARG_FR, ARG_RF, ARG_PAIRTRIES
 };
 
 static const char *short_options = "fqrchu:v:s:at3:5:e:n:l:p:k:m:M:1:2:I:X:x:B:yS";
@@ -80,7 +82,8 @@ static struct option long_options[] = {
 	{"chunkmbs", required_argument, 0, ARG_IGNORED1}, {"mm", no_argument, 0, ARG_IGNORED0}, {"shmem", no_argument, 0, ARG_IGNORED1}, {"help", no_argument, 0, 'h'},
 	{"device", required_argument, 0, ARG_DEVICE}, {"reads-per-batch", required_argument, 0, ARG_BATCH},
 	{"large-index", no_argument, 0, ARG_LARGE_INDEX}, {"12", required_argument, 0, ARG_PAIRED}, {"interleaved", required_argument, 0, ARG_PAIRED},
-	{"ff", no_argument, 0, ARG_PAIRED}, {"fr", no_argument, 0, ARG_IGNORED0}, {"rf", no_argument, 0, ARG_PAIRED},
+	{"ff", no_argument, 0, ARG_FF}, {"fr", no_argument, 0, ARG_FR}, {"rf", no_argument, 0, ARG_RF}, {"pairtries", required_argument, 0, ARG_PAIRTRIES},
+	{"minins", required_argument, 0, 'I'}, {"maxins", required_argument, 0, 'X'},
 	{0, 0, 0, 0}
 };
 
@@ -126,7 +129,15 @@ static void parse_options(int argc, char **argv, Opts &o) {
 		case 'y': o.maxBts = o.maxBtsBest = 0x7fffffff; break;
 		case 'h': printf("Usage: bowtie-b200-align [options]* -x <ebwt> {<s> | -c <seqs>} [<hits>]\n  (option names follow bowtie 1.3.1; see DESIGN.md for the supported subset)\n"); exit(0);
 		case 'M': o.sampleMax = true; o.mhits = (uint32_t)parse_int(1, "-m arg must be at least 1"); break;
-		case '1': case '2': case 'I': case 'X': case ARG_PAIRED: unsupported("paired-end alignment"); break;
+		case '1': split(optarg, ',', o.mates1); break;
+		case '2': split(optarg, ',', o.mates2); break;
+		case 'I': o.minInsert = (uint32_t)parse_int(0, "-I arg must be positive"); break;
+		case 'X': o.maxInsert = (uint32_t)parse_int(1, "-X arg must be at least 1"); break;
+		case ARG_FF: o.mate1fw = true; o.mate2fw = true; break;
+		case ARG_FR: o.mate1fw = true; o.mate2fw = false; break;
+		case ARG_RF: o.mate1fw = false; o.mate2fw = true; break;
+		case ARG_PAIRTRIES: o.pairTries = (uint32_t)parse_int(1, "--pairtries arg must be at least 1"); break;
+		case ARG_PAIRED: unsupported("--12 / --interleaved input"); break;
 		case ARG_BEST: o.best = true; break;
 		case ARG_STRATA: o.strata = true; break;
 		case ARG_LARGE_INDEX: die("Error: large (64-bit) indexes are not supported"); break;
@@ -171,8 +182,14 @@ static void parse_options(int argc, char **argv, Opts &o) {
 		fprintf(stderr, "Setting the index via positional argument will be deprecated in a future release. Please use -x option instead.\n");
 		o.ebwtFile = argv[optind++];
 	}
-	if (optind >= argc) die("No query or output file specified!");
-	split(argv[optind++], ',', o.queries);
+	if (o.mates1.size() != o.mates2.size()) {
+		fprintf(stderr, "Error: %zu mate files/sequences were specified with -1, but %zu\nmate files/sequences were specified with -2.  The same number of mate files/\nsequences must be specified with -1 and -2.\n", o.mates1.size(), o.mates2.size());
+		exit(1);
+	}
+	if (o.mates1.empty()) {
+		if (optind >= argc) die("No query or output file specified!");
+		split(argv[optind++], ',', o.queries);
+	} else if (o.best) unsupported("paired-end alignment with --best / --strata / -M / -v 3 (PairedBWAlignerV2)");
 	if (optind < argc) o.outfile = argv[optind++];
 	if (optind < argc) die(std::string("Extra parameter(s) specified: ") + argv[optind]);
 	if (o.sam) std::fill(o.suppress.begin(), o.suppress.end(), false);
@@ -197,11 +214,12 @@ struct Reader {
 	uint64_t rdid = 0;
 	bool first = true;
 	size_t cmdIdx = 0;
-	explicit Reader(const Opts &oo) : o(oo) {}
+	const std::vector<std::string> &files;
+	Reader(const Opts &oo, const std::vector<std::string> &ff) : o(oo), files(ff) {}
 	bool open_next() {
 		if (f) { gzclose(f); f = NULL; }
-		if (fileIdx >= o.queries.size()) return false;
-		const std::string &fn = o.queries[fileIdx++];
+		if (fileIdx >= files.size()) return false;
+		const std::string &fn = files[fileIdx++];
 		f = (fn == "-") ? gzdopen(0, "rb") : gzopen(fn.c_str(), "rb");
 		if (!f) die("Warning: Could not open read file \"" + fn + "\" for reading");
 		gzbuffer(f, 1 << 20);
@@ -258,8 +276,8 @@ struct Reader {
 	bool next(ReadRec &r) {
 		if (o.format == CMDLINE) {
 			/* VectorPatternSource (pat.cpp:437-523): names are the ordinal, qualities 'I' */
-			if (cmdIdx >= o.queries.size()) return false;
-			std::string s = o.queries[cmdIdx++];
+			if (cmdIdx >= files.size()) return false;
+			std::string s = files[cmdIdx++];
 			std::string q;
 			size_t colon = s.find(':');
 			if (colon != std::string::npos) { q = s.substr(colon + 1); s = s.substr(0, colon); }
@@ -354,7 +372,7 @@ static void put_upto_ws(std::string &o, const char *s, bool ws) {      /* printU
 	o.append(s, n);
 }
 
-struct HitView { uint32_t tidx, toff, oms, cost, stratum, fw, nmm; const uint32_t *mm; };
+struct HitView { uint32_t tidx, toff, oms, cost, stratum, fw, nmm; const uint32_t *mm; uint32_t mate = 0, mtoff = 0, mfw = 0, mlen = 0; };   /* mate: Hit::mate (0 = unpaired), then Hit::mh.second, mfw, mlen */
 
 /* VerboseHitSink::append (hit.cpp:73-301), partition == 0 */
 static void append_default(std::string &o, const Opts &op, const bt_index_t *ix, const ReadRec &r, const HitView &h) {
@@ -408,14 +426,23 @@ static void append_qname(std::string &o, const Opts &op, const std::string &name
 /* SAMHitSink::append (sam.cpp:129-257), unpaired */
 static void append_sam(std::string &o, const Opts &op, const bt_index_t *ix, const ReadRec &r, const HitView &h, int mapq, int xms) {
 	const size_t len = r.seq.size();
-	append_qname(o, op, r.name);
-	o += '\t'; put_uint(o, h.fw ? 0 : 16); o += '\t';
+	append_qname(o, op, h.mate ? r.name.substr(0, r.name.size() >= 2 ? r.name.size() - 2 : 0) : r.name);
+	uint32_t flags = h.fw ? 0 : 16;
+	if (h.mate == 1) flags |= 1 | 64 | 2; else if (h.mate == 2) flags |= 1 | 128 | 2;      /* PAIRED | FIRST/SECOND_IN_PAIR | MAPPED_PAIRED */
+	if (h.mate && !h.mfw) flags |= 32;                                                       /* MATE_STRAND */
+	o += '\t'; put_uint(o, flags); o += '\t';
 	const char *nm = op.refIdx ? NULL : bt_index_refname(ix, h.tidx);
 	if (nm) put_upto_ws(o, nm, !op.fullRef); else put_uint(o, h.tidx);
 	o += '\t'; put_uint(o, (uint64_t)h.toff + 1);
 	o += '\t'; put_int(o, mapq);
 	o += '\t'; put_uint(o, len); o += 'M';
-	o += "\t*\t0\t0\t";
+	if (h.mate) {
+		o += "\t=\t"; put_uint(o, (uint64_t)h.mtoff + 1); o += '\t';
+		long long ins;
+		if (h.toff > h.mtoff) ins = -((long long)h.toff - (long long)h.mtoff + (long long)len);
+		else ins = (long long)h.mtoff - (long long)h.toff + (long long)h.mlen;
+		put_int(o, (int)ins); o += '\t';
+	} else o += "\t*\t0\t0\t";
 	if (h.fw) for (size_t i = 0; i < len; i++) o += "ACGTN"[(int)r.seq[i]];
 	else for (size_t i = len; i > 0; i--) { int c = r.seq[i - 1]; o += "ACGTN"[c < 4 ? (c ^ 3) : 4]; }
 	o += '\t';
@@ -436,9 +463,10 @@ static void append_sam(std::string &o, const Opts &op, const bt_index_t *ix, con
 }
 
 /* SAMHitSink::reportUnOrMax (sam.cpp:57-124), unpaired, un == true */
-static void append_sam_unaligned(std::string &o, const Opts &op, const ReadRec &r) {
-	append_qname(o, op, r.name);
-	o += "\t4\t*\t0\t0\t*\t*\t0\t0\t";
+static void append_sam_unaligned(std::string &o, const Opts &op, const ReadRec &r, int mate = 0) {
+	append_qname(o, op, mate ? r.name.substr(0, r.name.size() >= 2 ? r.name.size() - 2 : 0) : r.name);
+	o += mate == 0 ? "\t4" : mate == 1 ? "\t77" : "\t141";                               /* UNMAPPED [| PAIRED | FIRST/SECOND | MATE_UNMAPPED] */
+	o += "\t*\t0\t0\t*\t*\t0\t0\t";
 	for (size_t i = 0; i < r.seq.size(); i++) o += "ACGTN"[(int)r.seq[i]];
 	o += '\t'; o += r.qual;
 	o += "\tXM:i:0\n";
@@ -483,7 +511,15 @@ int main(int argc, char **argv) {
 	pol.seed_len = op.seedLen; pol.qual_thresh = (uint32_t)op.qualThresh; pol.max_bts = (uint32_t)op.maxBts;
 	pol.khits = op.khits; pol.mhits = op.mhits; pol.all_hits = op.allHits; pol.nofw = op.nofw; pol.norc = op.norc; pol.maq_round = !op.noMaqRound;
 	pol.best = op.best; pol.strata = op.strata; pol.max_bts_best = (uint32_t)op.maxBtsBest; pol.sample_max = op.sampleMax;
+	const bool paired = !op.mates1.empty();
+	if (paired) {
+		/* aligner.h:975-990: the insert window shrinks by the bases trimmed from the outer ends of the fragment */
+		const int adj = (op.mate1fw ? op.trim5 : op.trim3) + (op.mate2fw ? op.trim3 : op.trim5);
+		pol.paired = 1; pol.mate1fw = op.mate1fw; pol.mate2fw = op.mate2fw; pol.pair_tries = op.pairTries;
+		pol.min_ins = (uint32_t)std::max(0, (int)op.minInsert - adj); pol.max_ins = (uint32_t)std::max(0, (int)op.maxInsert - adj);
+	}
 	const bool needMirror = op.maqLike || op.mismatches > 0;
+	const uint32_t mult = paired ? 2u : 1u;                                       /* HitSinkPerThreadFactory::createMult */
 
 	/* adjustEbwtBase (ebwt.cpp:36-85): as given, else under $BOWTIE_INDEXES */
 	std::string base = op.ebwtFile;
@@ -501,38 +537,47 @@ int main(int argc, char **argv) {
 	if (!op.outfile.empty()) { out.fp = fopen(op.outfile.c_str(), "wb"); if (!out.fp) die("Error: could not open alignment output file " + op.outfile); }
 	if (op.sam && !op.samNoHead) sam_headers(out.buf, op, ix, info.n_refs);
 
-	Reader rd(op);
+	Reader rd(op, paired ? op.mates1 : op.queries), rd2(op, op.mates2);
 	Batch bt[2];
 	const uint32_t nlim = op.allHits ? 0xffffffffu : op.khits;
 	for (auto &b : bt) {
 		if (bt_context_create(ix, &b.cx)) die(std::string("Error: ") + bt_last_error());
-		b.slots = op.allHits ? 8 : op.khits;
-		if (op.sampleMax && op.mhits != 0xffffffffu) b.slots = std::max(b.slots, op.mhits);   /* -M keeps every hit up to the ceiling */
+		b.slots = op.allHits ? 8 : op.khits * mult;
+		if (op.sampleMax && op.mhits != 0xffffffffu) b.slots = std::max(b.slots, op.mhits * mult);   /* -M keeps every hit up to the ceiling */
 		b.mm_cap = op.maqLike ? 10 : (uint32_t)std::max(1, op.mismatches);
 	}
 	uint64_t numAligned = 0, numUnaligned = 0, numMaxed = 0, numReported = 0;
 	bool input_done = false;
-	ReadRec rec;
+	ReadRec rec, rec2;
+	auto fix_mate_name = [](std::string &name, int i) {                           /* Read::fixMateName (read.h:141-165) */
+		const size_t n = name.size();
+		if (n < 2 || name[n - 2] != '/' || name[n - 1] != "012"[i]) { name += '/'; name += "012"[i]; }
+	};
 
 	auto fill = [&](Batch &b) {
 		b.reads.clear(); b.seq.clear(); b.qual.clear(); b.offs.assign(1, 0); b.seeds.clear();
-		while (!input_done && b.reads.size() < op.batch) {
+		while (!input_done && b.reads.size() < (size_t)op.batch * mult) {
 			if (rd.rdid >= op.qUpto) { input_done = true; break; }
 			if (!rd.next(rec)) { input_done = true; break; }
+			if (paired && !rd2.next(rec2)) die("Error, fewer reads in file specified with -2 than in file specified with -1");
 			if (rd.rdid - 1 < op.skipReads) continue;                              /* -s: skipped reads are not counted */
-			b.seq.insert(b.seq.end(), rec.seq.begin(), rec.seq.end());
-			b.qual.insert(b.qual.end(), rec.qual.begin(), rec.qual.end());
-			b.offs.push_back(b.seq.size());
-			b.seeds.push_back(gen_rand_seed(rec, op.seed));
-			b.reads.push_back(rec);
+			for (int m = 0; m < (paired ? 2 : 1); m++) {
+				ReadRec &rr = m ? rec2 : rec;
+				if (paired) fix_mate_name(rr.name, m + 1);                         /* PatternSourcePerThread::finalizePair (pat.cpp:75-87) */
+				b.seq.insert(b.seq.end(), rr.seq.begin(), rr.seq.end());
+				b.qual.insert(b.qual.end(), rr.qual.begin(), rr.qual.end());
+				b.offs.push_back(b.seq.size());
+				b.seeds.push_back(gen_rand_seed(rr, op.seed));
+				b.reads.push_back(rr);
+			}
 		}
 	};
 	auto launch = [&](Batch &b) {
 		if (b.reads.empty()) return;
-		const size_t n = b.reads.size(), rw = BT_HIT_HDR_WORDS + b.mm_cap;
+		const size_t n = b.reads.size() / mult, rw = BT_HIT_HDR_WORDS + b.mm_cap;
 		b.found.assign(n, 0); b.flags.assign(n, 0); b.hits.assign(n * b.slots * rw, 0);
 		bt_read_batch_t in; memset(&in, 0, sizeof in);
-		in.nreads = (uint32_t)n; in.seq = b.seq.data(); in.qual = b.qual.data(); in.offs = b.offs.data(); in.seeds = b.seeds.data();
+		in.nreads = (uint32_t)b.reads.size(); in.seq = b.seq.data(); in.qual = b.qual.data(); in.offs = b.offs.data(); in.seeds = b.seeds.data();
 		bt_hit_batch_t ho = { b.found.data(), b.flags.data(), b.hits.data(), b.slots, b.mm_cap };
 		if (bt_context_align_async(b.cx, &pol, &in, &ho, NULL)) die(std::string("Error: ") + bt_last_error());
 		b.inflight = true;
@@ -541,17 +586,18 @@ int main(int argc, char **argv) {
 		if (!b.inflight) return;
 		if (bt_context_sync(b.cx, NULL)) die(std::string("Error: ") + bt_last_error());
 		b.inflight = false;
-		const size_t n = b.reads.size();
+		const size_t n = b.reads.size() / mult;                                    /* work units: reads or pairs */
+		const uint32_t nlimU = (nlim == 0xffffffffu) ? nlim : nlim * mult, mhitsU = (op.mhits == 0xffffffffu) ? op.mhits : op.mhits * mult;
 		size_t rw = BT_HIT_HDR_WORDS + b.mm_cap;
 		/* reads whose records did not fit: run them again with exact capacities (ABI contract) */
 		std::vector<uint32_t> need;
 		for (size_t i = 0; i < n; i++) if (b.flags[i] & (BT_OVF_HITS | BT_OVF_MM)) need.push_back((uint32_t)i);
-		for (size_t i = 0; i < n; i++) if (b.flags[i] & (BT_OVF_STACK | BT_OVF_FRAME | BT_OVF_PART)) die("Error: search scratch exhausted for read " + b.reads[i].name);
+		for (size_t i = 0; i < n; i++) if (b.flags[i] & (BT_OVF_STACK | BT_OVF_FRAME | BT_OVF_PART)) die("Error: search scratch exhausted for read " + b.reads[i * mult].name);
 		/* the retried reads go through compact sub-batches of bounded size (a read reported with -a can have millions of hits);
 		 * their records are kept in hits2 at off2[k], rw2[k] words each */
 		std::vector<uint32_t> hits2, found2(need.size(), 0); std::vector<size_t> off2(need.size(), 0), rw2(need.size(), 0);
 		if (!need.empty()) {
-			const uint32_t storeLim = op.sampleMax ? std::max(nlim, op.mhits) : nlim;
+			const uint32_t storeLim = op.sampleMax ? std::max(nlimU, mhitsU) : nlimU;
 			std::vector<uint32_t> order(need.size());
 			for (size_t k = 0; k < need.size(); k++) order[k] = (uint32_t)k;
 			std::sort(order.begin(), order.end(), [&](uint32_t x, uint32_t y) { return b.found[need[x]] < b.found[need[y]]; });
@@ -561,25 +607,28 @@ int main(int argc, char **argv) {
 				size_t g1 = g0; uint32_t gSlots = 1, gLen = 1;
 				while (g1 < order.size()) {
 					const uint32_t i = need[order[g1]];
-					const uint32_t sl = std::max<uint32_t>(1, std::min(b.found[i], storeLim)), ln = std::max<uint32_t>(gLen, (uint32_t)b.reads[i].seq.size());
+					uint32_t rl = (uint32_t)b.reads[i * mult].seq.size(); if (paired) rl = std::max<uint32_t>(rl, (uint32_t)b.reads[i * mult + 1].seq.size());
+					const uint32_t sl = std::max<uint32_t>(1, std::min(b.found[i], storeLim)), ln = std::max<uint32_t>(gLen, rl);
 					if (g1 > g0 && (g1 - g0 + 1) * (size_t)sl * (BT_HIT_HDR_WORDS + ln) > budgetWords) break;
 					gSlots = sl; gLen = ln; g1++;                                /* sorted by found: the last read sets the slot count */
 				}
 				const size_t gn = g1 - g0, grw = BT_HIT_HDR_WORDS + gLen;
 				std::vector<uint8_t> gseq, gqual; std::vector<uint64_t> goffs(1, 0); std::vector<uint32_t> gseeds, gfound(gn, 0), gflags(gn, 0), ghits(gn * (size_t)gSlots * grw, 0);
 				for (size_t k = g0; k < g1; k++) {
-					const uint32_t i = need[order[k]];
-					gseq.insert(gseq.end(), b.seq.begin() + b.offs[i], b.seq.begin() + b.offs[i + 1]);
-					gqual.insert(gqual.end(), b.qual.begin() + b.offs[i], b.qual.begin() + b.offs[i + 1]);
-					goffs.push_back(gseq.size()); gseeds.push_back(b.seeds[i]);
+					for (uint32_t m = 0; m < mult; m++) {
+						const uint32_t i = need[order[k]] * mult + m;
+						gseq.insert(gseq.end(), b.seq.begin() + b.offs[i], b.seq.begin() + b.offs[i + 1]);
+						gqual.insert(gqual.end(), b.qual.begin() + b.offs[i], b.qual.begin() + b.offs[i + 1]);
+						goffs.push_back(gseq.size()); gseeds.push_back(b.seeds[i]);
+					}
 				}
 				bt_read_batch_t in; memset(&in, 0, sizeof in);
-				in.nreads = (uint32_t)gn; in.seq = gseq.data(); in.qual = gqual.data(); in.offs = goffs.data(); in.seeds = gseeds.data();
+				in.nreads = (uint32_t)(gn * mult); in.seq = gseq.data(); in.qual = gqual.data(); in.offs = goffs.data(); in.seeds = gseeds.data();
 				bt_hit_batch_t ho = { gfound.data(), gflags.data(), ghits.data(), gSlots, gLen };
 				if (bt_context_align(b.cx, &pol, &in, &ho, NULL)) die(std::string("Error: ") + bt_last_error());
 				for (size_t k = g0; k < g1; k++) {
 					const size_t j = k - g0, kk = order[k];
-					if (gflags[j] & (BT_OVF_STACK | BT_OVF_FRAME | BT_OVF_PART | BT_OVF_HITS | BT_OVF_MM)) die("Error: search scratch exhausted for read " + b.reads[need[kk]].name);
+					if (gflags[j] & (BT_OVF_STACK | BT_OVF_FRAME | BT_OVF_PART | BT_OVF_HITS | BT_OVF_MM)) die("Error: search scratch exhausted for read " + b.reads[need[kk] * mult].name);
 					const uint32_t nst = std::min(gfound[j], gSlots);
 					found2[kk] = gfound[j]; off2[kk] = hits2.size(); rw2[kk] = grw;
 					hits2.insert(hits2.end(), ghits.begin() + j * (size_t)gSlots * grw, ghits.begin() + (j * (size_t)gSlots + nst) * grw);
@@ -589,11 +638,11 @@ int main(int argc, char **argv) {
 		}
 		size_t ni = 0;
 		for (size_t i = 0; i < n; i++) {
-			const ReadRec &r = b.reads[i];
+			const ReadRec &r = b.reads[i * mult];
 			const uint32_t *recs = &b.hits[i * b.slots * rw]; size_t rwi = rw; uint32_t found = b.found[i];
 			if (ni < need.size() && need[ni] == i) { rwi = rw2[ni]; recs = hits2.data() + off2[ni]; found = found2[ni]; ni++; }
 			/* HitSinkPerThread::finishRead (hit.h:741-786) */
-			const bool maxed = found > op.mhits, unal = (found == 0);
+			const bool maxed = found > mhitsU, unal = (found == 0);
 			if (maxed) {
 				numMaxed++;
 				if (op.sampleMax) {
@@ -610,14 +659,23 @@ int main(int argc, char **argv) {
 					numAligned++; numReported++;
 				}
 			}
-			else if (unal) { numUnaligned++; if (op.sam && !op.noUnal) append_sam_unaligned(out.buf, op, r); }
-			else {
-				uint32_t nrep = std::min(found, nlim);
+			else if (unal) {
+				numUnaligned++;
+				if (op.sam && !op.noUnal) { if (paired) { append_sam_unaligned(out.buf, op, r, 1); append_sam_unaligned(out.buf, op, b.reads[i * mult + 1], 2); } else append_sam_unaligned(out.buf, op, r); }
+			} else {
+				uint32_t nrep = std::min(found, nlimU);
 				for (uint32_t s = 0; s < nrep; s++) {
 					const uint32_t *w = recs + (size_t)s * rwi;
 					HitView h = { w[0], w[1], w[2], w[3] & 0xffffu, (w[3] >> 16) & 0xff, (w[3] >> 24) & 1, w[4], w + BT_HIT_HDR_WORDS };
 					if (op.strata) h.oms = found - 1;                           /* NBestFirstStratHitSinkPerThread::finishReadImpl (hit.h:1099-1108) */
-					if (op.sam) append_sam(out.buf, op, ix, r, h, op.defaultMapq, (int)nrep); else append_default(out.buf, op, ix, r, h);
+					h.mate = (w[3] >> 25) & 3;
+					const ReadRec *rr = &r;
+					if (h.mate) {                                               /* records come in (upstream, downstream) couples */
+						const uint32_t *mw = recs + (size_t)(s ^ 1) * rwi;
+						rr = &b.reads[i * mult + (h.mate - 1)];
+						h.mtoff = mw[1]; h.mfw = (mw[3] >> 24) & 1; h.mlen = (uint32_t)b.reads[i * mult + (2 - h.mate)].seq.size();
+					}
+					if (op.sam) append_sam(out.buf, op, ix, *rr, h, op.defaultMapq, (int)(nrep / mult)); else append_default(out.buf, op, ix, *rr, h);
 				}
 				numAligned++; numReported += nrep;
 			}
@@ -650,6 +708,7 @@ int main(int argc, char **argv) {
 		fprintf(stderr, "# reads that failed to align: %llu (%.2f%%)\n", (unsigned long long)numUnaligned, unalPct);
 		if (numMaxed > 0) fprintf(stderr, op.sampleMax ? "# reads with alignments sampled due to -M: %llu (%.2f%%)\n" : "# reads with alignments suppressed due to -m: %llu (%.2f%%)\n", (unsigned long long)numMaxed, maxPct);
 		if (numReported == 0) fprintf(stderr, "No alignments\n");
+		else if (paired) fprintf(stderr, "Reported %llu paired-end alignments\n", (unsigned long long)(numReported >> 1));
 		else fprintf(stderr, "Reported %llu alignments\n", (unsigned long long)numReported);
 	}
 	if (op.timing) {

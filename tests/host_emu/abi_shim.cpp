@@ -14,13 +14,14 @@
 #include <vector>
 #include "../../bowtie_b200/csrc/bt_native.cuh"
 #include "../../bowtie_b200/csrc/bt_best_prog.h"
+#include "../../bowtie_b200/csrc/bt_ref_load.h"
 #include "../../include/bowtie_b200.h"
 extern "C" {
 #include "../../oracle/bt_oracle.h"
 }
 
 struct EmuIx { std::vector<uint4> blocks; bto_index *raw; BtDevIndex dev; };
-struct bt_index { EmuIx *e[2]; bool mirror; std::vector<std::string> names; bt_stats_t st; };
+struct bt_index { EmuIx *e[2]; bool mirror; std::vector<std::string> names; bt_stats_t st; std::string base; BtHostRef href; bool ref_loaded = false; };
 struct bt_context { bt_index *ix; };
 static std::string g_err;
 
@@ -44,7 +45,7 @@ extern "C" {
 int bt_abi_version(void) { return BT_ABI_VERSION; }
 const char *bt_last_error(void) { return g_err.c_str(); }
 int bt_index_load(const char *basename, int need_mirror, int, bt_index_t **out) {
-	bt_index *ix = new bt_index(); memset(&ix->st, 0, sizeof ix->st); ix->e[0] = ix->e[1] = NULL; ix->mirror = need_mirror != 0;
+	bt_index *ix = new bt_index(); memset(&ix->st, 0, sizeof ix->st); ix->e[0] = ix->e[1] = NULL; ix->mirror = need_mirror != 0; ix->base = basename;
 	ix->e[0] = load_one(basename, 0);
 	if (ix->e[0] && need_mirror) ix->e[1] = load_one(basename, 1);
 	if (!ix->e[0] || (need_mirror && !ix->e[1])) { delete ix; return 1; }
@@ -57,7 +58,7 @@ void bt_index_free(bt_index_t *ix) { if (!ix) return; for (int k = 0; k < 2; k++
 int bt_index_info(const bt_index_t *ix, bt_index_info_t *info) { bto_index *r = ix->e[0]->raw; info->len = r->len; info->n_refs = r->nPat; info->off_rate = r->offRate; info->ftab_chars = r->ftabChars; info->has_mirror = ix->mirror; info->device_bytes = 0; return 0; }
 const char *bt_index_refname(const bt_index_t *ix, uint32_t i) { return i < ix->names.size() ? ix->names[i].c_str() : NULL; }
 uint32_t bt_index_reflen(const bt_index_t *ix, uint32_t i) { bto_index *r = ix->e[0]->raw; return i < r->nPat ? r->plen[i] : 0; }
-void bt_policy_init(bt_policy_t *p) { memset(p, 0, sizeof *p); p->mode = 1; p->mms = 2; p->seed_len = 28; p->qual_thresh = 70; p->max_bts = 125; p->khits = 1; p->mhits = 0xffffffffu; p->maq_round = 1; p->max_bts_best = 800; }
+void bt_policy_init(bt_policy_t *p) { memset(p, 0, sizeof *p); p->mode = 1; p->mms = 2; p->seed_len = 28; p->qual_thresh = 70; p->max_bts = 125; p->khits = 1; p->mhits = 0xffffffffu; p->maq_round = 1; p->max_bts_best = 800; p->max_ins = 250; p->mate1fw = 1; p->pair_tries = 100; }
 
 static int run_best(bt_index *ix, const bt_policy_t *pol, const bt_read_batch_t *in, bt_hit_batch_t *out);
 static bool stateful(const bt_policy_t *pol);
@@ -87,29 +88,40 @@ static int run(bt_index *ix, const bt_policy_t *pol, const bt_read_batch_t *in, 
 	}
 	return 0;
 }
-static bool stateful(const bt_policy_t *pol) { return pol->best || pol->strata || (pol->mode == 0 && pol->mms == 3); }
+static bool stateful(const bt_policy_t *pol) { return pol->best || pol->strata || pol->paired || (pol->mode == 0 && pol->mms == 3); }
 /* the best-first path (bt_best.cuh), one read at a time */
 static int run_best(bt_index *ix, const bt_policy_t *pol, const bt_read_batch_t *in, bt_hit_batch_t *out) {
 	BfKParams P; memset(&P, 0, sizeof P);
 	P.ix[0] = ix->e[0]->dev; if (ix->e[1]) P.ix[1] = ix->e[1]->dev;
 	memcpy(&P.pol, pol, sizeof(BtPolicy));
-	bf_build_prog(pol->mode, pol->mms, pol->seed_len, pol->qual_thresh, pol->nofw, pol->norc, &P.prog);
+	bf_build_prog(pol->mode, pol->mms, pol->seed_len, pol->qual_thresh, pol->nofw, pol->norc, &P.prog,
+	              pol->paired, pol->mate1fw, pol->mate2fw, pol->min_ins, pol->max_ins, pol->pair_tries, pol->mhits);
+	if (pol->paired) {
+		if (!ix->ref_loaded) { if (!bt_load_ref(ix->base, ix->href, g_err)) return 1; ix->ref_loaded = true; }
+		const BtHostRef &h = ix->href;
+		P.ref.recs = h.recs.data(); P.ref.refRecOffs = h.refRecOffs.data(); P.ref.refOffs = h.refOffs.data(); P.ref.approxLen = h.approxLen.data();
+		P.ref.buf = h.buf.data(); P.ref.nRefs = h.nRefs;
+	}
 	P.seq = in->seq; P.qual = in->qual; P.roff = in->offs; P.seeds = in->seeds;
 	P.found = out->found; P.flags = out->flags; P.hits = out->hits; P.slots = out->slots; P.mm_cap = out->mm_cap; P.rec_words = BT_HIT_HDR + out->mm_cap;
 	static std::vector<uint32_t> arena; arena.resize((size_t)16 << 20);
 	const char *env = getenv("BT_EMU_ARENA_WORDS");
 	const uint32_t words = env ? (uint32_t)atol(env) : (uint32_t)arena.size();
-	const uint32_t nwork = in->sel ? in->nsel : in->nreads;
+	const uint32_t nwork = in->sel ? in->nsel : (pol->paired ? in->nreads / 2 : in->nreads);
 	for (uint32_t w = 0; w < nwork; w++) {
 		const uint32_t r = in->sel ? in->sel[w] : w;
 		BfCtx X; memset(&X, 0, sizeof X);
-		X.P = &P; X.rid = r; X.rlen = (uint32_t)(in->offs[r + 1] - in->offs[r]); X.seed = in->seeds[r];
-		X.seq = in->seq + in->offs[r]; X.qual = in->qual + in->offs[r];
+		X.P = &P; X.rid = r;
+		for (uint32_t m = 0; m < (pol->paired ? 2u : 1u); m++) {
+			const uint32_t rd = pol->paired ? 2 * r + m : r;
+			X.rlenM[m] = (uint32_t)(in->offs[rd + 1] - in->offs[rd]); X.seedM[m] = in->seeds[rd];
+			X.seqM[m] = in->seq + in->offs[rd]; X.qualM[m] = in->qual + in->offs[rd];
+		}
 		X.A = arena.data(); X.acap = words; X.atop = 1;
-		bf_align_read(X);
+		if (pol->paired) bf_align_pair(X); else bf_align_read(X);
 		if ((X.flags & BT_FLAG_STACK_OVF) && words < arena.size()) {      /* what the larger-arena passes of the product do */
 			memset(&X.top, 0, sizeof X.top); X.flags = 0; X.acap = (uint32_t)arena.size(); X.atop = 1;
-			bf_align_read(X);
+			if (pol->paired) bf_align_pair(X); else bf_align_read(X);
 		}
 		if (X.flags & (BT_FLAG_STACK_OVF | BT_FLAG_FRAME_OVF)) X.found = 0;
 		out->found[r] = X.found; out->flags[r] = X.flags;
