@@ -169,6 +169,7 @@ static void parse_options(int argc, char **argv, Opts &o) {
 	}
 	(void)vset;
 	/* ebwt_search.cpp:851-854, 877-891 */
+	const bool bestAsked = o.best || o.strata || o.sampleMax;                    /* -v 3 alone keeps the V1 paired aligner (useV1, ebwt_search.cpp:776) */
 	if (!o.maqLike && o.mismatches == 3) o.best = true;
 	if (!o.best && o.sampleMax) {
 		if (!o.quiet) fprintf(stderr, "Warning: -M was specified w/o --best; automatically enabling --best\n");
@@ -189,7 +190,8 @@ static void parse_options(int argc, char **argv, Opts &o) {
 	if (o.mates1.empty()) {
 		if (optind >= argc) die("No query or output file specified!");
 		split(argv[optind++], ',', o.queries);
-	} else if (o.best) unsupported("paired-end alignment with --best / --strata / -M / -v 3 (PairedBWAlignerV2)");
+	} else if (bestAsked) unsupported("paired-end alignment with --best / --strata / -M (PairedBWAlignerV2)");
+	else o.best = false;
 	if (optind < argc) o.outfile = argv[optind++];
 	if (optind < argc) die(std::string("Extra parameter(s) specified: ") + argv[optind]);
 	if (o.sam) std::fill(o.suppress.begin(), o.suppress.end(), false);

@@ -133,3 +133,57 @@ def write_fastq(path: Path, batch: ReadBatch) -> None:
     with open(path, "wb") as f:
         for n, s, q in zip(batch.names, batch.seqs, batch.quals):
             f.write(b"@" + n + b"\n" + s + b"\n+\n" + q + b"\n")
+
+
+def synth_pairs(genome: list[tuple[str, bytes]], n: int, length: int | tuple[int, int], seed: int, frag_mean: float = 200.0, frag_sd: float = 20.0,
+                sub_rate: float = 0.02, n_rate: float = 0.0, qual_profile: str = "mixed", broken_frac: float = 0.05):
+    """Paired reads in --fr orientation: mate 1 from the fragment's left end (forward), mate 2 the reverse complement of
+    its right end; the whole fragment is flipped half of the time.  `broken_frac` of the pairs get an unrelated mate 2.
+    Returns (names, seqs1, quals1, seqs2, quals2) as lists of bytes."""
+    rng = np.random.default_rng(seed)
+    seqs = [np.frombuffer(s, np.uint8) for _, s in genome]
+    w = np.array([len(s) for s in seqs], float)
+    w /= w.sum()
+    acgt = np.frombuffer(b"ACGT", np.uint8)
+    qchoices = {"high": [40, 40, 40, 35, 30], "low": [40, 30, 20, 12, 8, 3, 2]}.get(qual_profile, [40, 40, 40, 35, 30, 20, 10])
+
+    def mutate(r):
+        r = r.copy()
+        mut = rng.random(len(r)) < sub_rate
+        r[mut] = rng.choice(acgt, size=int(mut.sum()))
+        if n_rate > 0:
+            r[rng.random(len(r)) < n_rate] = ord("N")
+        return r
+
+    def rc(r):
+        return np.frombuffer(r.tobytes().translate(_COMP)[::-1], np.uint8)
+
+    names, s1, q1, s2, q2 = [], [], [], [], []
+    for i in range(n):
+        L1 = length if isinstance(length, int) else int(rng.integers(length[0], length[1] + 1))
+        L2 = length if isinstance(length, int) else int(rng.integers(length[0], length[1] + 1))
+        while True:
+            si = int(rng.choice(len(seqs), p=w))
+            F = max(max(L1, L2) + 1, int(rng.normal(frag_mean, frag_sd)))
+            if len(seqs[si]) > F + 1:
+                break
+        p = int(rng.integers(0, len(seqs[si]) - F))
+        frag = seqs[si][p:p + F]
+        if rng.random() < 0.5:
+            frag = rc(frag)
+        a, b = mutate(frag[:L1]), mutate(rc(frag[F - L2:]))
+        if rng.random() < broken_frac:
+            b = rng.choice(acgt, size=L2)
+        names.append(f"p{i}".encode())
+        s1.append(a.tobytes()); s2.append(b.tobytes())
+        q1.append((rng.choice(qchoices, size=L1) + 33).astype(np.uint8).tobytes())
+        q2.append((rng.choice(qchoices, size=L2) + 33).astype(np.uint8).tobytes())
+    return names, s1, q1, s2, q2
+
+
+def write_fastq_pairs(path1: Path, path2: Path, pairs) -> None:
+    names, s1, q1, s2, q2 = pairs
+    with open(path1, "wb") as f1, open(path2, "wb") as f2:
+        for n, a, qa, b, qb in zip(names, s1, q1, s2, q2):
+            f1.write(b"@" + n + b"/1\n" + a + b"\n+\n" + qa + b"\n")
+            f2.write(b"@" + n + b"/2\n" + b + b"\n+\n" + qb + b"\n")
