@@ -19,6 +19,7 @@
 #include "bt_native.cuh"
 #include "bt_ctxq.cuh"
 #include "bt_best_prog.h"
+#include "bt_ref_load.h"
 #include "../../include/bowtie_b200.h"
 
 static_assert(sizeof(bt_policy_t) == sizeof(BtPolicy), "bt_policy_t and BtPolicy must share a layout");
@@ -328,6 +329,7 @@ static size_t bt_q_smem(uint32_t nctx) { return sizeof(BtQueues) + (size_t)nctx 
 /* Best-first path (--best / --strata / -M / -v 3): every thread takes reads from the global cursor and runs the whole
  * UnpairedAlignerV2 loop for each on its own arena of P.arenaWords words.  `lanes` threads of each block are active. */
 #define BF_THREADS 64
+template <bool PAIRED>
 __global__ void __launch_bounds__(BF_THREADS)
 bt_best_kernel(const __grid_constant__ BfKParams P, BtWorkCtl *ctl, uint32_t lanes) {
 	if (threadIdx.x >= lanes) return;
@@ -340,15 +342,21 @@ bt_best_kernel(const __grid_constant__ BfKParams P, BtWorkCtl *ctl, uint32_t lan
 	for (;;) {
 		const unsigned long long w = atomicAdd(&ctl->next, 1ull);
 		if (w >= nwork) break;
-		const uint32_t rid = P.sel ? P.sel[w] : (uint32_t)w;
-		const unsigned long long ro = P.roff[rid];
-		X.rid = rid; X.rlenM[0] = (uint32_t)(P.roff[rid + 1] - ro); X.seedM[0] = P.seeds[rid];
+		const uint32_t rid = P.sel ? P.sel[w] : (uint32_t)w;                 /* read id, or pair id (mates are reads 2p, 2p+1) */
+		const uint32_t r0 = PAIRED ? 2 * rid : rid;
+		const unsigned long long ro = P.roff[r0];
+		X.rid = rid; X.rlenM[0] = (uint32_t)(P.roff[r0 + 1] - ro); X.seedM[0] = P.seeds[r0];
 		X.seqM[0] = P.seq + ro; X.qualM[0] = P.qual + ro;
 		X.rlenM[1] = 0; X.seedM[1] = 0; X.seqM[1] = X.seqM[0]; X.qualM[1] = X.qualM[0];
+		if (PAIRED) {
+			const unsigned long long ro1 = P.roff[r0 + 1];
+			X.rlenM[1] = (uint32_t)(P.roff[r0 + 2] - ro1); X.seedM[1] = P.seeds[r0 + 1];
+			X.seqM[1] = P.seq + ro1; X.qualM[1] = P.qual + ro1;
+		}
 		X.atop = 1; X.flags = 0; X.found = 0;
 		X.top.rssOff = X.top.rssCap = X.top.nRss = X.top.actOff = X.top.actCap = X.top.nAct = 0;
 		X.top.lastRange = X.top.delayedRange = 0; X.top.minCost = 0; X.top.done = 0; X.top.foundRange = 0; X.top.rnd = 0;
-		bf_align_read(X);
+		if (PAIRED) bf_align_pair(X); else bf_align_read(X);
 		if (X.flags & (BT_FLAG_STACK_OVF | BT_FLAG_FRAME_OVF)) X.found = 0;     /* STACK_OVF: re-run by a pass with a larger arena */
 		P.found[rid] = X.found; P.flags[rid] = X.flags;
 	}
@@ -413,6 +421,8 @@ struct bt_index {
 	unsigned long long *stats = nullptr;
 	int sms = 0, blocks_per_sm = 0;
 	bt_context *def = nullptr;   /* context behind bt_align_batch / bt_align_batch_device */
+	std::string base;            /* index basename: the bit-pair reference (X.3.ebwt / X.4.ebwt) is loaded on the first paired-end call */
+	bool ref_loaded = false; BtDevRef dref; uint32_t *d_refwords[4] = { nullptr, nullptr, nullptr, nullptr }; uint8_t *d_refbuf = nullptr;
 	std::mutex mu;
 };
 
@@ -570,6 +580,8 @@ extern "C" void bt_index_free(bt_index_t *ix) {
 		cudaFree(d.blocks); cudaFree(d.offs); cudaFree(d.ftab); cudaFree(d.eftab); cudaFree(d.rstarts); cudaFree(d.plen);
 	}
 	if (ix->def) bt_context_free(ix->def);
+	for (int k = 0; k < 4; k++) cudaFree(ix->d_refwords[k]);
+	cudaFree(ix->d_refbuf);
 	cudaFree(ix->stats);
 	delete ix;
 }
@@ -584,6 +596,7 @@ extern "C" int bt_index_load(const char *basename, int need_mirror, int device, 
 	CUDA_TRY(cudaSetDevice(device));
 	bt_index *ix = new bt_index();
 	ix->device = device;
+	ix->base = basename;
 	ix->has_mirror = need_mirror != 0;
 	int rc = parse_ebwt(basename, false, ix->host[0]);
 	if (!rc) rc = upload_index(ix->host[0], true, ix->dev[0]);
@@ -636,13 +649,29 @@ static int ensure_ws(Workspace &w, uint32_t nthreads, uint32_t R, uint32_t FCAP,
 	return 0;
 }
 
-static bool policy_is_best(const bt_policy_t *pol) { return pol->best || pol->strata || pol->sample_max || (pol->mode == 0 && pol->mms == 3); }
+static bool policy_is_best(const bt_policy_t *pol) { return pol->best || pol->strata || pol->sample_max || pol->paired || (pol->mode == 0 && pol->mms == 3); }
+/* BitPairReference (reference.h) onto the device, once per index */
+static int ensure_ref(bt_index_t *ix) {
+	std::lock_guard<std::mutex> g(ix->mu);
+	if (ix->ref_loaded) return 0;
+	BtHostRef h; std::string err;
+	if (!bt_load_ref(ix->base, h, err)) return fail("bt_align (paired-end): " + err);
+	uint64_t bytes = 0;
+	const std::vector<uint32_t> *v[4] = { &h.recs, &h.refRecOffs, &h.refOffs, &h.approxLen };
+	for (int k = 0; k < 4; k++) if (upload(*v[k], &ix->d_refwords[k], bytes)) return 1;
+	if (upload(h.buf, &ix->d_refbuf, bytes)) return 1;
+	ix->dref.recs = ix->d_refwords[0]; ix->dref.refRecOffs = ix->d_refwords[1]; ix->dref.refOffs = ix->d_refwords[2]; ix->dref.approxLen = ix->d_refwords[3];
+	ix->dref.buf = ix->d_refbuf; ix->dref.nRefs = h.nRefs;
+	ix->ref_loaded = true;
+	return 0;
+}
 static int check_policy(const bt_index_t *ix, const bt_policy_t *pol) {
 	if (pol->mode == 0) { if (pol->mms < 0 || pol->mms > 3) return fail("bt_align: -v must be 0..3"); }
 	else if (pol->mode == 1) { if (pol->mms < 0 || pol->mms > 3) return fail("bt_align: -n must be 0..3"); if (pol->seed_len < 5) return fail("bt_align: -l must be >= 5"); }
 	else return fail("bt_align: bad mode");
 	if ((pol->mode == 1 || pol->mms > 0) && !ix->has_mirror) return fail("bt_align: this policy needs the mirror index (load with need_mirror=1)");
 	if (!pol->all_hits && pol->khits == 0) return fail("bt_align: -k must be >= 1");
+	if (pol->paired && (pol->best || pol->strata || pol->sample_max)) return fail("bt_align: paired-end with --best/--strata/-M is the reference's PairedBWAlignerV2; not provided");
 	return 0;
 }
 
@@ -682,7 +711,10 @@ static bool main_kernel_is_queue() {
  * side stream.  About 5 + 5 + 2.5 GB per context for full batches. */
 static int enqueue_best(bt_context *cx, const bt_policy_t *pol, const bt_read_batch_t *in, bt_hit_batch_t *out, uint32_t maxlen, cudaStream_t st) {
 	bt_index_t *ix = cx->ix;
-	const uint32_t nwork = in->sel ? in->nsel : in->nreads;
+	if (pol->paired && (in->nreads & 1)) return fail("bt_align (paired-end): nreads must be even (mates are adjacent reads)");
+	const uint32_t nwork = in->sel ? in->nsel : (pol->paired ? in->nreads / 2 : in->nreads);
+	if (nwork == 0) return 0;
+	if (pol->paired && ensure_ref(ix)) return 1;
 	static const uint32_t kw0 = env_u32("BT_BEST_ARENA_KW", 16);
 	const uint32_t tierWords[3] = { kw0 << 10, 256u << 10, 4096u << 10 };
 	const uint32_t tierLanes[3] = { BF_THREADS, 32, 1 };                 /* active threads per block */
@@ -706,7 +738,9 @@ static int enqueue_best(bt_context *cx, const bt_policy_t *pol, const bt_read_ba
 	BfKParams P; memset(&P, 0, sizeof P);
 	P.ix[0] = ix->dev[0].dev; P.ix[1] = ix->dev[1].dev;
 	memcpy(&P.pol, pol, sizeof(BtPolicy));
-	bf_build_prog(pol->mode, pol->mms, pol->seed_len, pol->qual_thresh, pol->nofw, pol->norc, &P.prog);
+	bf_build_prog(pol->mode, pol->mms, pol->seed_len, pol->qual_thresh, pol->nofw, pol->norc, &P.prog,
+	              pol->paired, pol->mate1fw, pol->mate2fw, pol->min_ins, pol->max_ins, pol->pair_tries, pol->mhits);
+	if (pol->paired) P.ref = ix->dref;
 	P.seq = in->seq; P.qual = in->qual; P.roff = in->offs; P.seeds = in->seeds; P.sel = in->sel; P.nwork = nwork;
 	P.found = out->found; P.flags = out->flags; P.hits = out->hits; P.slots = out->slots; P.mm_cap = out->mm_cap; P.rec_words = BT_HIT_HDR + out->mm_cap;
 	P.stats = ix->stats;
@@ -717,15 +751,16 @@ static int enqueue_best(bt_context *cx, const bt_policy_t *pol, const bt_read_ba
 	bt_ctl_set_kernel<<<1, 1, 0, st>>>(cx->ctl + 1, 0);
 	bt_ctl_set_kernel<<<1, 1, 0, st>>>(cx->ctl + 2, 0);
 	P.arena = cx->arena[0]; P.arenaWords = tierWords[0];
-	bt_best_kernel<<<tierBlocks[0], BF_THREADS, 0, st>>>(P, cx->ctl, tierLanes[0]);
+	auto kernel = pol->paired ? bt_best_kernel<true> : bt_best_kernel<false>;
+	kernel<<<tierBlocks[0], BF_THREADS, 0, st>>>(P, cx->ctl, tierLanes[0]);
 	bt_collect_kernel<<<cblocks, 256, 0, st>>>(out->flags, in->sel, nwork, nullptr, BT_FLAG_STACK_OVF, cx->heavy_sel, cx->ctl + 1);
 	CUDA_TRY(cudaEventRecord(cx->ev_main, st));
 	CUDA_TRY(cudaStreamWaitEvent(cx->side, cx->ev_main, 0));
 	P.sel = cx->heavy_sel; P.arena = cx->arena[1]; P.arenaWords = tierWords[1];
-	bt_best_kernel<<<tierBlocks[1], BF_THREADS, 0, cx->side>>>(P, cx->ctl + 1, tierLanes[1]);
+	kernel<<<tierBlocks[1], BF_THREADS, 0, cx->side>>>(P, cx->ctl + 1, tierLanes[1]);
 	bt_collect_kernel<<<cblocks, 256, 0, cx->side>>>(out->flags, cx->heavy_sel, nwork, cx->ctl + 1, BT_FLAG_STACK_OVF, cx->retry_sel, cx->ctl + 2);
 	P.sel = cx->retry_sel; P.arena = cx->arena[2]; P.arenaWords = tierWords[2];
-	bt_best_kernel<<<tierBlocks[2], BF_THREADS, 0, cx->side>>>(P, cx->ctl + 2, tierLanes[2]);
+	kernel<<<tierBlocks[2], BF_THREADS, 0, cx->side>>>(P, cx->ctl + 2, tierLanes[2]);
 	CUDA_TRY(cudaGetLastError());
 	return 0;
 }
@@ -873,10 +908,11 @@ static int align_host(bt_context *cx, const bt_policy_t *pol, const bt_read_batc
 		const size_t nb = (size_t)in->offs[n];
 		for (uint32_t i = 0; i < n; i++) { uint64_t l = in->offs[i + 1] - in->offs[i]; if (l > maxlen) maxlen = (uint32_t)l; }
 		const size_t rec_words = BT_HIT_HDR + out->mm_cap;
-		const size_t hitwords = (size_t)n * out->slots * rec_words;
+		const uint32_t nout = pol->paired ? n / 2 : n;                        /* results are per read, or per pair */
+		const size_t hitwords = (size_t)nout * out->slots * rec_words;
 		if (grow(&cx->d_seq, cx->cap_seq, nb + 1) || grow(&cx->d_qual, cx->cap_qual, nb + 1)) return 1;
 		if (grow(&cx->d_offs, cx->cap_offs, (size_t)n + 1) || grow(&cx->d_seeds, cx->cap_seeds, n) ||
-		    grow(&cx->d_found, cx->cap_found, n) || grow(&cx->d_flags, cx->cap_flags, n)) return 1;
+		    grow(&cx->d_found, cx->cap_found, nout) || grow(&cx->d_flags, cx->cap_flags, nout)) return 1;
 		if (grow(&cx->d_hits, cx->cap_hitwords, hitwords)) return 1;
 		if (in->sel && grow(&cx->d_sel, cx->cap_sel, in->nsel)) return 1;
 		if (nb) {
@@ -886,15 +922,15 @@ static int align_host(bt_context *cx, const bt_policy_t *pol, const bt_read_batc
 		CUDA_TRY(cudaMemcpyAsync(cx->d_offs, in->offs, ((size_t)n + 1) * 8, cudaMemcpyHostToDevice, st));
 		CUDA_TRY(cudaMemcpyAsync(cx->d_seeds, in->seeds, (size_t)n * 4, cudaMemcpyHostToDevice, st));
 		if (in->sel) CUDA_TRY(cudaMemcpyAsync(cx->d_sel, in->sel, (size_t)in->nsel * 4, cudaMemcpyHostToDevice, st));
-		else { CUDA_TRY(cudaMemsetAsync(cx->d_found, 0, (size_t)n * 4, st)); CUDA_TRY(cudaMemsetAsync(cx->d_flags, 0, (size_t)n * 4, st)); }
+		else { CUDA_TRY(cudaMemsetAsync(cx->d_found, 0, (size_t)nout * 4, st)); CUDA_TRY(cudaMemsetAsync(cx->d_flags, 0, (size_t)nout * 4, st)); }
 		bt_read_batch_t din = *in; bt_hit_batch_t dout = *out;
 		din.seq = cx->d_seq; din.qual = cx->d_qual; din.offs = cx->d_offs; din.seeds = cx->d_seeds; din.sel = in->sel ? cx->d_sel : nullptr;
 		dout.found = cx->d_found; dout.flags = cx->d_flags; dout.hits = cx->d_hits;
 		if (enqueue_align(cx, pol, &din, &dout, maxlen, st)) return 1;
 		if (!in->sel) {
 			/* results leave on the side stream, behind the heavy / overflow passes */
-			CUDA_TRY(cudaMemcpyAsync(out->found, cx->d_found, (size_t)n * 4, cudaMemcpyDeviceToHost, cx->side));
-			CUDA_TRY(cudaMemcpyAsync(out->flags, cx->d_flags, (size_t)n * 4, cudaMemcpyDeviceToHost, cx->side));
+			CUDA_TRY(cudaMemcpyAsync(out->found, cx->d_found, (size_t)nout * 4, cudaMemcpyDeviceToHost, cx->side));
+			CUDA_TRY(cudaMemcpyAsync(out->flags, cx->d_flags, (size_t)nout * 4, cudaMemcpyDeviceToHost, cx->side));
 			CUDA_TRY(cudaMemcpyAsync(out->hits, cx->d_hits, hitwords * 4, cudaMemcpyDeviceToHost, cx->side));
 			if (finish_tail(cx)) return 1;
 			if (sync) CUDA_TRY(cudaStreamSynchronize(cx->side));

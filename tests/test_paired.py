@@ -1,0 +1,111 @@
+"""Paired-end alignment (BASELINE config 5): PairedBWAlignerV1 over the best-first drivers, the
+reference-window scan for the opposite mate (RefAligner family) and the bit-pair reference (X.3/X.4.ebwt), through the
+bowtie-compatible driver, byte for byte against the unmodified reference binary.
+
+* not-gpu: through tests/host_emu/shim (device code compiled for the host).
+* gpu: the CUDA library.
+"""
+import hashlib
+import os
+import subprocess
+from pathlib import Path
+
+import pytest
+
+from helpers import FIXTURES, REF_ALIGN, ROOT, ensure_oracle_built, have_reference
+from test_cli_parity import CLI, SHIM_DIR, build_shim
+
+# md5 of the reference's hit file for the shipped paired reads
+GOLDEN = {"-n 3": "13330dbc5beb1b9b3070d6c6939ac9b7", "-n 2": "13330dbc5beb1b9b3070d6c6939ac9b7", "-v 2": "956cd5667fdec6116b3672ea1eac78b2"}
+
+ECOLI_FLAGS = [
+    "-n 3", "-n 2", "-n 1", "-n 0", "-v 0", "-v 1", "-v 2", "-v 3", "-n 2 -k 3", "-n 2 -a", "-n 2 -m 1", "-n 2 -m 2 -k 2", "-v 2 -a",
+    "-n 2 -S", "-v 1 -S -k 2", "-n 2 -X 150", "-n 2 -I 100 -X 300", "-n 2 --ff", "-n 2 --rf", "-n 2 --nofw", "-n 2 --norc",
+    "-n 2 -l 20 -e 100", "-n 3 --nomaqround -a", "-n 2 --pairtries 2", "-n 2 -5 2 -3 3", "-n 2 --maxbts 3", "-n 2 -S --no-unal -X 120",
+]
+SYNTH_FLAGS = ["-n 2", "-n 3 -a", "-n 1 -k 3", "-v 0", "-v 2 -k 2", "-v 3", "-n 2 -m 2", "-n 2 -I 150 -X 260", "-n 2 -l 15 -e 200 -a", "-n 2 -S", "-v 1 -a -X 500"]
+
+
+@pytest.fixture(scope="module")
+def setup(tmp_path_factory):
+    ensure_oracle_built()
+    if not have_reference():
+        pytest.skip("reference binary / fixtures not available")
+    import bowtie_b200
+    bowtie_b200.build_library()
+    from synth import build_synth_index, synth_pairs, write_fastq_pairs
+    d = tmp_path_factory.mktemp("pe")
+    base, genome = build_synth_index("t1", 3, 300000, 7)
+    write_fastq_pairs(d / "low_1.fq", d / "low_2.fq", synth_pairs(genome, 400, (20, 110), seed=21, sub_rate=0.03, n_rate=0.004, qual_profile="low"))
+    gbase, ggenome = build_synth_index("t1", 3, 300000, 7, with_gaps=True)
+    write_fastq_pairs(d / "gap_1.fq", d / "gap_2.fq", synth_pairs(ggenome, 400, (30, 60), seed=23, sub_rate=0.02, n_rate=0.002, frag_mean=120, frag_sd=30))
+    write_fastq_pairs(d / "big_1.fq", d / "big_2.fq", synth_pairs(genome, 10000, 100, seed=25, sub_rate=0.015))
+    return {"low": (base, d / "low_1.fq", d / "low_2.fq"), "gap": (gbase, d / "gap_1.fq", d / "gap_2.fq"), "big": (base, d / "big_1.fq", d / "big_2.fq"),
+            "ecoli": (FIXTURES / "e_coli", FIXTURES / "e_coli_1000_1.fq", FIXTURES / "e_coli_1000_2.fq")}
+
+
+def run(exe, flags, case, out, env=None, ref=False):
+    base, m1, m2 = case
+    cmd = [str(exe), *flags.split()] + (["-p", "1"] if ref else []) + ["-x", str(base), "-1", str(m1), "-2", str(m2), str(out)]
+    p = subprocess.run(cmd, capture_output=True, text=True, env=env)
+    assert p.returncode == 0, p.stderr
+    body = b"".join(l for l in Path(out).read_bytes().splitlines(keepends=True) if not l.startswith(b"@PG"))
+    summary = "\n".join(l for l in p.stderr.splitlines() if l.startswith("#") or l.startswith("Reported") or l.startswith("No alignments"))
+    return body, summary
+
+
+def compare(flags, case, tmp_path, env):
+    ref = run(REF_ALIGN, flags, case, tmp_path / "ref.out", ref=True)
+    ours = run(CLI, flags, case, tmp_path / "our.out", env=env)
+    assert ours[0] == ref[0]
+    assert ours[1] == ref[1]
+    return ours[0]
+
+
+def shim_env():
+    build_shim()
+    return dict(os.environ, LD_LIBRARY_PATH=str(SHIM_DIR))
+
+
+def gpu_env():
+    return {k: v for k, v in os.environ.items() if k != "LD_LIBRARY_PATH"}
+
+
+@pytest.mark.parametrize("flags", ECOLI_FLAGS, ids=[f.replace(" ", "_") for f in ECOLI_FLAGS])
+def test_paired_ecoli_logic(flags, setup, tmp_path):
+    body = compare(flags, setup["ecoli"], tmp_path, shim_env())
+    if flags in GOLDEN:
+        assert hashlib.md5(body).hexdigest() == GOLDEN[flags]
+
+
+@pytest.mark.parametrize("flags", SYNTH_FLAGS, ids=[f.replace(" ", "_") for f in SYNTH_FLAGS])
+@pytest.mark.parametrize("reads", ["low", "gap"])
+def test_paired_synthetic_logic(flags, reads, setup, tmp_path):
+    compare(flags, setup[reads], tmp_path, shim_env())
+
+
+def test_paired_best_is_rejected(setup, tmp_path):
+    base, m1, m2 = setup["ecoli"]
+    p = subprocess.run([str(CLI), "--best", "-x", str(base), "-1", str(m1), "-2", str(m2)], capture_output=True, text=True, env=shim_env())
+    assert p.returncode != 0 and "PairedBWAlignerV2" in p.stderr
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("flags", ECOLI_FLAGS, ids=[f.replace(" ", "_") for f in ECOLI_FLAGS])
+def test_paired_ecoli_gpu(flags, setup, tmp_path):
+    body = compare(flags, setup["ecoli"], tmp_path, gpu_env())
+    if flags in GOLDEN:
+        assert hashlib.md5(body).hexdigest() == GOLDEN[flags]
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("flags", SYNTH_FLAGS, ids=[f.replace(" ", "_") for f in SYNTH_FLAGS])
+@pytest.mark.parametrize("reads", ["low", "gap"])
+def test_paired_synthetic_gpu(flags, reads, setup, tmp_path):
+    compare(flags, setup[reads], tmp_path, gpu_env())
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("flags", ["-n 3", "-v 2 -k 2"])
+def test_paired_gpu_10k_pairs(flags, setup, tmp_path):
+    compare(flags, setup["big"], tmp_path, gpu_env())
