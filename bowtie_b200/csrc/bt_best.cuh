@@ -38,6 +38,7 @@ struct BfSrcCfg {            /* constructor arguments of one EbwtRangeSource + E
 struct BfTopCfg { uint32_t kind; BfSrcCfg a, b; };   /* a: the driver (or the seedling generator); b: the per-seedling extension driver */
 struct BfProg {
 	uint32_t ntop, seedLen, qualLim, strandFix; BfTopCfg top[BF_MAX_TOP];
+	BfTopCfg top2[BF_MAX_TOP];   /* paired-end: mate 2's drivers (the -v factories configure the two mates differently) */
 	/* paired-end (PairedBWAlignerV1): which of the four per-mate, per-strand driver lists exist (do1Fw, do1Rc, do2Fw, do2Rc),
 	 * the reference-scan policy of the opposite mate (RefAligner family) and the insert-size window */
 	uint32_t paired, doList[4], refMms, refSeedLen, refQualMax, minIns, maxIns, fw1, fw2, mixedAttemptLim, symCeiling;
@@ -1138,6 +1139,14 @@ BT_NOINLINE bool bf_pair_resolve_in_ref(BfCtx &X, BfPairState &S, bool off1, uin
 	return ret;
 }
 
+#if defined(BT_HOST_EMU) && defined(BF_TRACE_EVENTS)
+#include <stdio.h>
+#define BF_TRACE(msg) fprintf(stderr, "%s\n", msg)          /* the reference's --verbose messages, for diffing event traces */
+#define BF_TRACE_RANGE(r) fprintf(stderr, "   range top=%u bot=%u idx=%u fw=%u mate=%u cost=%u nmm=%u e0=%x\n", (r).rTop, (r).rBot, (r).cfg.ebwtSel, (r).cfg.fw, (r).cfg.mate, (r).rCost, (r).rNmm, (r).rNmm ? X.A[(r).rEdits] : 0)
+#else
+#define BF_TRACE(msg) ((void)0)
+#define BF_TRACE_RANGE(r) ((void)0)
+#endif
 /* PairedBWAlignerV1::advanceOrientation (aligner.h:1092-1326) */
 BT_NOINLINE void bf_pair_advance_orientation(BfCtx &X, BfPairState &S, bool pairFw) {
 	const BfProg &g = X.P->prog;
@@ -1148,6 +1157,7 @@ BT_NOINLINE void bf_pair_advance_orientation(BfCtx &X, BfPairState &S, bool pair
 	if (S.chase[L]) {
 		if (S.rc.hasOff) {
 			if (!S.done) {                                                  /* overThresh || dontReconcile_ */
+				BF_TRACE("Making an attempt to find the outstanding mate");
 				const BfSrc &r = *BF_AT(BfSrc, X, drL.lastRange);
 				S.done = bf_pair_resolve_in_ref(X, S, pairFw, S.rc.tidx, S.rc.toff, r);
 				if (++S.mixedAttempts > g.mixedAttemptLim) { donePair = true; return; }
@@ -1155,7 +1165,9 @@ BT_NOINLINE void bf_pair_advance_orientation(BfCtx &X, BfPairState &S, bool pair
 			S.rc.hasOff = false;
 		} else {
 			S.chase[L] = false; drL.foundRange = 0;
+			BF_TRACE("Done with chase for first mate");
 			if (S.delayed[R]) {
+				BF_TRACE("Resuming delayed chase for second mate");
 				const BfSrc &r = *BF_AT(BfSrc, X, drR.lastRange);
 				bf_chaser_set_top_bot(X, S.rc, r.rTop, r.rBot, qlenR, r.cfg.ebwtSel);
 				S.chase[R] = true; S.delayed[R] = false;
@@ -1164,6 +1176,7 @@ BT_NOINLINE void bf_pair_advance_orientation(BfCtx &X, BfPairState &S, bool pair
 	} else if (S.chase[R]) {
 		if (S.rc.hasOff) {
 			if (!S.done) {
+				BF_TRACE("Making an attempt to find the outstanding mate");
 				const BfSrc &r = *BF_AT(BfSrc, X, drR.lastRange);
 				S.done = bf_pair_resolve_in_ref(X, S, !pairFw, S.rc.tidx, S.rc.toff, r);
 				if (++S.mixedAttempts > g.mixedAttemptLim) { donePair = true; return; }
@@ -1171,7 +1184,9 @@ BT_NOINLINE void bf_pair_advance_orientation(BfCtx &X, BfPairState &S, bool pair
 			S.rc.hasOff = false;
 		} else {
 			S.chase[R] = false; drR.foundRange = 0;
+			BF_TRACE("Done with chase for second mate");
 			if (S.delayed[L]) {
+				BF_TRACE("Resuming delayed chase for first mate");
 				const BfSrc &r = *BF_AT(BfSrc, X, drL.lastRange);
 				bf_chaser_set_top_bot(X, S.rc, r.rTop, r.rBot, qlenL, r.cfg.ebwtSel);
 				S.chase[L] = true; S.delayed[L] = false;
@@ -1180,14 +1195,15 @@ BT_NOINLINE void bf_pair_advance_orientation(BfCtx &X, BfPairState &S, bool pair
 	}
 	if (!S.done && !donePair && !S.chase[L] && !S.chase[R]) {
 		if ((S.offsSz[L] < S.offsSz[R] || drR.done) && !drL.done) {
-			if (drR.done && S.offsSz[R] == 0) { donePair = true; return; }
+			if (drR.done && S.offsSz[R] == 0) { BF_TRACE("Giving up on paired orientation in mate 1"); donePair = true; return; }
 			if (!drL.foundRange) bf_ca_advance<true>(X, drL, g.strandFix != 0);
 			if (X.flags & (BT_FLAG_STACK_OVF | BT_FLAG_FRAME_OVF)) return;
 			if (drL.foundRange) {
 				const BfSrc &rl = *BF_AT(BfSrc, X, drL.lastRange);
 				S.offsSz[L] += rl.rBot - rl.rTop;
-				if (S.offsSz[R] == 0 && S.offsSz[L] > 3) S.delayed[L] = true;   /* !dontReconcile_ || offsLsz > 3 */
+				if (S.offsSz[R] == 0 && S.offsSz[L] > 3) { BF_TRACE("Delaying a chase for first mate"); S.delayed[L] = true; }   /* !dontReconcile_ || offsLsz > 3 */
 				else {
+					BF_TRACE("Chasing a range for first mate");
 					if (S.offsSz[L] > g.symCeiling && S.offsSz[R] > g.symCeiling) { donePair = true; return; }
 					if (S.delayed[R] && S.offsSz[R] < S.offsSz[L]) {
 						S.delayed[R] = false; S.delayed[L] = true; S.chase[R] = true;
@@ -1195,19 +1211,21 @@ BT_NOINLINE void bf_pair_advance_orientation(BfCtx &X, BfPairState &S, bool pair
 						bf_chaser_set_top_bot(X, S.rc, r.rTop, r.rBot, qlenR, r.cfg.ebwtSel);
 					} else {
 						S.chase[L] = true;
+						BF_TRACE_RANGE(rl);
 						bf_chaser_set_top_bot(X, S.rc, rl.rTop, rl.rBot, qlenL, rl.cfg.ebwtSel);
 					}
 				}
 			}
 		} else if (!drR.done) {
-			if (drL.done && S.offsSz[L] == 0) { donePair = true; return; }
+			if (drL.done && S.offsSz[L] == 0) { BF_TRACE("Giving up on paired orientation in mate 2"); donePair = true; return; }
 			if (!drR.foundRange) bf_ca_advance<true>(X, drR, g.strandFix != 0);
 			if (X.flags & (BT_FLAG_STACK_OVF | BT_FLAG_FRAME_OVF)) return;
 			if (drR.foundRange) {
 				const BfSrc &rr = *BF_AT(BfSrc, X, drR.lastRange);
 				S.offsSz[R] += rr.rBot - rr.rTop;
-				if (S.offsSz[L] == 0 && S.offsSz[R] > 3) S.delayed[R] = true;
+				if (S.offsSz[L] == 0 && S.offsSz[R] > 3) { BF_TRACE("Delaying a chase for second mate"); S.delayed[R] = true; }
 				else {
+					BF_TRACE("Chasing a range for second mate");
 					if (S.offsSz[L] > g.symCeiling && S.offsSz[R] > g.symCeiling) { donePair = true; return; }
 					if (S.delayed[L] && S.offsSz[L] < S.offsSz[R]) {
 						S.delayed[L] = false; S.delayed[R] = true; S.chase[L] = true;
@@ -1241,7 +1259,7 @@ BT_NOINLINE void bf_align_pair(BfCtx &X) {
 		if (g.doList[k]) {
 			const uint32_t wantFw = (k & 1) ? 0u : 1u, mate = k >> 1;
 			for (uint32_t i = 0; i < g.ntop; i++) {
-				BfTopCfg tc = g.top[i];
+				BfTopCfg tc = mate ? g.top2[i] : g.top[i];
 				if (tc.a.fw != wantFw) continue;
 				tc.a.mate = (uint8_t)mate; tc.b.mate = (uint8_t)mate;
 				uint32_t node;

@@ -29,7 +29,7 @@ static inline BfSrcCfg bf_cfg(int mirror, int fw, int reportExacts, int hh, int 
  * RefAligner that matches the policy. */
 static inline void bf_build_prog(int mode, int mms, int seedLen, uint32_t qualThresh, int nofw, int norc, BfProg *out,
                                  int paired = 0, int mate1fw = 1, int mate2fw = 0, uint32_t minIns = 0, uint32_t maxIns = 250,
-                                 uint32_t pairTries = 100, uint32_t mhits = 0xffffffffu) {
+                                 uint32_t pairTries = 100, uint32_t mhits = 0xffffffffu, int forMate2 = 0) {
 	BfProg &g = *out; memset(&g, 0, sizeof g);
 	if (paired) {
 		g.paired = 1; g.fw1 = mate1fw ? 1 : 0; g.fw2 = mate2fw ? 1 : 0; g.minIns = minIns; g.maxIns = maxIns;
@@ -54,14 +54,18 @@ static inline void bf_build_prog(int mode, int mms, int seedLen, uint32_t qualTh
 			const int ia = fw ? 1 : 0, ib = fw ? 0 : 1;
 			if (mms == 0) SRC(bf_cfg(0, fw, 1, 0, 0, 1, 0, L, L, L, L));             /* both strands on the forward index */
 			else if (mms == 1) {
-				SRC(bf_cfg(ia, fw, 1, 0, 0, ia ? 0 : 1, 0, H, L, L, L));
-				SRC(bf_cfg(ib, fw, 0, 0, 0, ib ? 0 : 1, 0, H, L, L, L));
+				/* nudgeLeft: "true for Fw index, false for Bw" unpaired (aligner_1mm.h:87-135); the paired factory gives
+				 * true to the first and false to the second driver of every list (aligner_1mm.h:292-420) */
+				SRC(bf_cfg(ia, fw, 1, 0, 0, paired ? 1 : (ia ? 0 : 1), 0, H, L, L, L));
+				SRC(bf_cfg(ib, fw, 0, 0, 0, paired ? 0 : (ib ? 0 : 1), 0, H, L, L, L));
 			} else {
 				const int two = mms == 2, r2 = two ? L : H;
 				SRC(bf_cfg(ia, fw, 1, 0, 0, 1, 0, H, H, r2, L));
 				SRC(bf_cfg(ib, fw, 0, 0, 0, 0, 0, H, H, r2, L));
 				SRC(bf_cfg(ia, fw, 0, 2, 0, 1, 0, B, H, r2, L));
-				if (!two) SRC(bf_cfg(ib, fw, 0, 3, 0, 0, 0, B, H, H, L));
+				/* the 3-mismatch half-and-half driver: (B,H,H,L) unpaired and for mate 1 rc; (B,B,H,L) for mate 1 fw and both
+				 * strands of mate 2 (aligner_23mm.h:126-136,191-201 vs 403-413,468-478,532-542,597-607) */
+				if (!two) SRC(bf_cfg(ib, fw, 0, 3, 0, 0, 0, B, (paired && (fw || forMate2)) ? B : H, H, L));
 			}
 		}
 	} else {
@@ -89,4 +93,9 @@ static inline void bf_build_prog(int mode, int mms, int seedLen, uint32_t qualTh
 	}
 #undef SRC
 #undef SEEDED
+	if (paired && !forMate2) {
+		BfProg m2;
+		bf_build_prog(mode, mms, seedLen, qualThresh, 0, 0, &m2, 1, mate1fw, mate2fw, minIns, maxIns, pairTries, mhits, 1);
+		memcpy(g.top2, m2.top, sizeof g.top2);
+	}
 }

@@ -1,7 +1,7 @@
 #!/usr/bin/env python
 """Differential fuzzer in the spirit of the reference's scripts/test/random_bowtie_tests.pl: random small genomes
 (repeats, N gaps, several sequences), random reads (ragged lengths, Ns, low qualities) and random option sets for both
-search paths; bowtie-b200-align (through tests/host_emu/shim, i.e. the device code compiled for the host — or the real
+search paths and for paired-end alignment; bowtie-b200-align (through tests/host_emu/shim, i.e. the device code compiled for the host — or the real
 library with --gpu) must produce the reference binary's hit file and summary byte for byte.
 
 usage: tools/fuzz_cli.py [--iters N] [--seed S] [--gpu]
@@ -66,6 +66,64 @@ def rand_reads(rng, genome, n):
     return out
 
 
+def rand_pairs(rng, genome, n):
+    comp = str.maketrans("ACGTN", "TGCAN")
+    m1, m2 = [], []
+    for i in range(n):
+        name, g = rng.choice(genome)
+        F = rng.randint(8, min(260, len(g)))
+        p = rng.randint(0, len(g) - F)
+        frag = g[p:p + F]
+        if rng.random() < 0.5:
+            frag = frag.translate(comp)[::-1]
+        L1, L2 = rng.randint(4, min(60, F)), rng.randint(4, min(60, F))
+        a, b = list(frag[:L1]), list(frag[F - L2:].translate(comp)[::-1])
+        if rng.random() < 0.1:
+            b = [rng.choice("ACGT") for _ in range(L2)]
+        for r in (a, b):
+            for k in range(len(r)):
+                if rng.random() < 0.03:
+                    r[k] = rng.choice("ACGT")
+                if rng.random() < 0.008:
+                    r[k] = "N"
+        qa = "".join(chr(33 + rng.choice([40, 40, 30, 20, 12, 8, 3, 0])) for _ in range(L1))
+        qb = "".join(chr(33 + rng.choice([40, 40, 30, 20, 12, 8, 3, 0])) for _ in range(L2))
+        m1.append((f"p{i}/1", "".join(a), qa)); m2.append((f"p{i}/2", "".join(b), qb))
+    return m1, m2
+
+
+def rand_paired_flags(rng):
+    f = []
+    if rng.random() < 0.5:
+        f += ["-v", str(rng.randint(0, 3))]
+    else:
+        f += ["-n", str(rng.randint(0, 3)), "-l", str(rng.choice([5, 8, 12, 20, 28])), "-e", str(rng.choice([40, 70, 150, 400]))]
+        if rng.random() < 0.3:
+            f += ["--nomaqround"]
+    rep = rng.choice(["k1", "k", "a", "m"])
+    if rep == "k":
+        f += ["-k", str(rng.randint(2, 5))]
+    elif rep == "a":
+        f += ["-a"]
+    elif rep == "m":
+        f += ["-m", str(rng.randint(1, 3))] + rng.choice([[], ["-k", "3"], ["-a"]])
+    if rng.random() < 0.4:
+        f += ["-X", str(rng.choice([60, 120, 200, 400]))]
+    if rng.random() < 0.25:
+        f += ["-I", str(rng.choice([10, 40, 100]))]
+    if rng.random() < 0.15:
+        f += [rng.choice(["--ff", "--rf", "--fr"])]
+    if rng.random() < 0.15:
+        f += [rng.choice(["--nofw", "--norc"])]
+    if rng.random() < 0.15:
+        f += ["--pairtries", str(rng.choice([1, 3, 20]))]
+    if rng.random() < 0.15:
+        f += ["--maxbts", str(rng.choice([1, 5, 40]))]
+    if rng.random() < 0.2:
+        f += ["-S"]
+    return f
+
+
 def rand_flags(rng):
     f = []
     if rng.random() < 0.5:
@@ -125,12 +183,20 @@ def main():
                 continue
             reads = rand_reads(rng, [(n, s) for n, s in genome if len(s) >= 4], rng.randint(20, 200))
             (td / "r.fq").write_text("".join(f"@{n}\n{s}\n+\n{q}\n" for n, s, q in reads))
-            for sub in range(4):
-                flags = rand_flags(rng)
-                r = subprocess.run([str(REF / "bowtie-align-s"), *flags, "-p", "1", "-x", str(td / "g"), str(td / "r.fq"), str(td / "ref.out")], capture_output=True, text=True)
+            m1, m2 = rand_pairs(rng, [(n, s) for n, s in genome if len(s) >= 8], rng.randint(20, 150))
+            (td / "m1.fq").write_text("".join(f"@{n}\n{s}\n+\n{q}\n" for n, s, q in m1))
+            (td / "m2.fq").write_text("".join(f"@{n}\n{s}\n+\n{q}\n" for n, s, q in m2))
+            for sub in range(6):
+                if sub < 4:
+                    flags = rand_flags(rng)
+                    inputs = [str(td / "r.fq")]
+                else:
+                    flags = rand_paired_flags(rng)
+                    inputs = ["-1", str(td / "m1.fq"), "-2", str(td / "m2.fq")]
+                r = subprocess.run([str(REF / "bowtie-align-s"), *flags, "-p", "1", "-x", str(td / "g"), *inputs, str(td / "ref.out")], capture_output=True, text=True)
                 if "Exhausted best-first chunk memory" in r.stderr:
                     continue
-                o = subprocess.run([str(CLI), *flags, "-x", str(td / "g"), str(td / "r.fq"), str(td / "our.out")], capture_output=True, text=True, env=env)
+                o = subprocess.run([str(CLI), *flags, "-x", str(td / "g"), *inputs, str(td / "our.out")], capture_output=True, text=True, env=env)
                 def body(pth):
                     return b"".join(l for l in Path(pth).read_bytes().splitlines(keepends=True) if not l.startswith(b"@PG")) if Path(pth).exists() else b"<none>"
                 def summ(t):
