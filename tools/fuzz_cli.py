@@ -107,10 +107,12 @@ def rand_paired_flags(rng):
         f += ["-a"]
     elif rep == "m":
         f += ["-m", str(rng.randint(1, 3))] + rng.choice([[], ["-k", "3"], ["-a"]])
+    maxins = 250
     if rng.random() < 0.4:
-        f += ["-X", str(rng.choice([60, 120, 200, 400]))]
+        maxins = rng.choice([60, 120, 200, 400])
+        f += ["-X", str(maxins)]
     if rng.random() < 0.25:
-        f += ["-I", str(rng.choice([10, 40, 100]))]
+        f += ["-I", str(rng.choice([i for i in (10, 40, 100) if i <= maxins]))]      # -I > -X is undefined behaviour in the reference (it may crash)
     if rng.random() < 0.15:
         f += [rng.choice(["--ff", "--rf", "--fr"])]
     if rng.random() < 0.15:
@@ -194,7 +196,7 @@ def main():
                     flags = rand_paired_flags(rng)
                     inputs = ["-1", str(td / "m1.fq"), "-2", str(td / "m2.fq")]
                 r = subprocess.run([str(REF / "bowtie-align-s"), *flags, "-p", "1", "-x", str(td / "g"), *inputs, str(td / "ref.out")], capture_output=True, text=True)
-                if "Exhausted best-first chunk memory" in r.stderr:
+                if "Exhausted best-first chunk memory" in r.stderr or r.returncode < 0:     # the reference's own memory limit / a crash of the reference
                     continue
                 o = subprocess.run([str(CLI), *flags, "-x", str(td / "g"), *inputs, str(td / "our.out")], capture_output=True, text=True, env=env)
                 def body(pth):
