@@ -99,6 +99,54 @@ def make_reads(genome: np.ndarray, n: int, seed: int):
     return codes.reshape(-1), quals.reshape(-1), offs, seeds.astype(np.uint32), name
 
 
+def make_pairs(genome: np.ndarray, n: int, seed: int):
+    """n pairs of 2 x 100 bp in --fr geometry: fragment length N(200, 20) clipped to [101, 250], mate 1 the
+    fragment's first 100 bases, mate 2 the reverse complement of its last 100, the whole fragment flipped half of the time,
+    1 % substitutions.  Reads are interleaved (mate 1, mate 2, mate 1, ...); names "r%09d/1", "r%09d/2"."""
+    rng = np.random.default_rng(seed)
+    L = READ_LEN
+    F = np.clip(rng.normal(200.0, 20.0, n).round().astype(np.int64), L + 1, 250)
+    pos = rng.integers(0, len(genome) - 251, n)
+    left = genome[pos[:, None] + np.arange(L)[None, :]]
+    right = genome[(pos + F - L)[:, None] + np.arange(L)[None, :]]
+    rcomp = lambda a: np.where(a[:, ::-1] < 4, 3 - a[:, ::-1], 4)
+    flip = rng.random(n) < 0.5
+    m1 = np.where(flip[:, None], rcomp(right), left)
+    m2 = np.where(flip[:, None], left, rcomp(right))
+    codes = np.empty((2 * n, L), np.uint8)
+    codes[0::2] = m1; codes[1::2] = m2
+    mut = rng.random((2 * n, L)) < 0.01
+    codes[mut] = (codes[mut] + rng.integers(1, 4, int(mut.sum()))) & 3
+    quals = (rng.choice(np.array([40, 40, 40, 35, 30, 20, 10], np.uint8), (2 * n, L)) + 33).astype(np.uint8)
+    ids = np.repeat(np.arange(n, dtype=np.uint32), 2)
+    name = np.zeros((2 * n, 12), np.uint8)
+    name[:, 0] = ord("r")
+    for d in range(9):
+        name[:, 9 - d] = (ids // 10 ** d) % 10 + 48
+    name[:, 10] = ord("/"); name[0::2, 11] = ord("1"); name[1::2, 11] = ord("2")
+    seeds = np.full(2 * n, ((0 + 101) * 59 * 61 * 67 * 71 * 73 * 79 * 83) & 0xFFFFFFFF, np.uint32)
+    i = np.arange(L)
+    seeds ^= np.bitwise_xor.reduce(codes.astype(np.uint32) << ((i & 15) << 1).astype(np.uint32), axis=1)
+    seeds ^= np.bitwise_xor.reduce(quals.astype(np.uint32) << ((i & 3) << 3).astype(np.uint32), axis=1)
+    j = np.arange(12)
+    seeds ^= np.bitwise_xor.reduce(name.astype(np.uint32) << ((j & 3) << 3).astype(np.uint32), axis=1)
+    offs = (np.arange(2 * n + 1, dtype=np.uint64) * L)
+    return codes.reshape(-1), quals.reshape(-1), offs, seeds.astype(np.uint32), name
+
+
+def write_fastq_pairs(p1: Path, p2: Path, codes, quals, name, npairs: int) -> None:
+    L = READ_LEN
+    lut = np.frombuffer(b"ACGTN", np.uint8)
+    seq = lut[codes[: 2 * npairs * L]].reshape(2 * npairs, L)
+    q = quals[: 2 * npairs * L].reshape(2 * npairs, L)
+    W = name.shape[1]
+    rec = np.empty((2 * npairs, 1 + W + 1 + L + 3 + L + 1), np.uint8)
+    rec[:, 0] = ord("@"); rec[:, 1:1 + W] = name[: 2 * npairs]; rec[:, 1 + W] = 10
+    rec[:, 2 + W:2 + W + L] = seq; rec[:, 2 + W + L] = 10; rec[:, 3 + W + L] = ord("+"); rec[:, 4 + W + L] = 10
+    rec[:, 5 + W + L:5 + W + 2 * L] = q; rec[:, 5 + W + 2 * L] = 10
+    p1.write_bytes(rec[0::2].tobytes()); p2.write_bytes(rec[1::2].tobytes())
+
+
 def write_fastq(path: Path, codes, quals, name, n: int) -> None:
     L = READ_LEN
     lut = np.frombuffer(b"ACGTN", np.uint8)
@@ -155,13 +203,14 @@ class ClockSampler:
 # reference arm / cpu baseline: the UNMODIFIED reference binary on the host cores
 # ------------------------------------------------------------------------------------------------
 
-def run_reference_sample(base: Path, fq: Path, n: int, threads: int, flags=("-n", "2", "-k", "1")) -> tuple[float, float]:
+def run_reference_sample(base: Path, fq, n: int, threads: int, flags=("-n", "2", "-k", "1")) -> tuple[float, float]:
     """bowtie-align-s -n 2 -k 1 -t -p <threads>; returns (search seconds from -t, wall seconds)."""
     exe = REF_DIR / "bowtie-align-s"
     if not exe.exists():
         raise RuntimeError("oracle/_ref/bowtie-align-s missing (built by oracle/Makefile from /root/reference)")
     t0 = time.time()
-    p = subprocess.run([str(exe), *flags, "-t", "-p", str(threads), "-x", str(base), str(fq), "/dev/null"],
+    inputs = ["-1", str(fq[0]), "-2", str(fq[1])] if isinstance(fq, (tuple, list)) else [str(fq)]      # a pair of mate files, or one file
+    p = subprocess.run([str(exe), *flags, "-t", "-p", str(threads), "-x", str(base), *inputs, "/dev/null"],
                        capture_output=True, text=True)
     wall = time.time() - t0
     if p.returncode != 0:
@@ -183,14 +232,26 @@ def main() -> None:
     ap.add_argument("--reads-per-step", type=int, default=int(os.environ.get("BT_BENCH_READS", 4_000_000)))
     ap.add_argument("--streams", type=int, default=int(os.environ.get("BT_BENCH_STREAMS", 8)),
                     help="batches kept in flight (one bt_context_t + CUDA stream each), like the reference's -p worker threads")
-    ap.add_argument("--policy", default=os.environ.get("BT_BENCH_POLICY", "n2k1"), choices=["n2k1", "best"],
-                    help="n2k1: the headline workload (-n 2 -k 1, SURVEY config 4); best: -n 2 --best (SURVEY config 3, best-first path)")
+    ap.add_argument("--policy", default=os.environ.get("BT_BENCH_POLICY", "n2k1"), choices=["n2k1", "best", "paired"],
+                    help="n2k1: the headline workload (-n 2 -k 1, SURVEY config 4); best: -n 2 --best (config 3, best-first path); "
+                         "paired: -n 3 on 2x100 bp pairs (config 5; value counts PAIRS per second)")
     ap.add_argument("--cpu-sample", type=int, default=int(os.environ.get("BT_BENCH_CPU_SAMPLE", 1_000_000)))
     args = ap.parse_args()
     rank, world, local = int(os.environ.get("RANK", 0)), int(os.environ.get("WORLD_SIZE", 1)), int(os.environ.get("LOCAL_RANK", 0))
     base, idx_name = pick_index()
-    ref_flags = ["-n", "2", "-k", "1"] if args.policy == "n2k1" else ["-n", "2", "--best"]
-    cfg_workload = f"{' '.join(ref_flags)}, {READ_LEN} bp synthetic reads (1% subs, both strands), index {idx_name}"
+    ref_flags = {"n2k1": ["-n", "2", "-k", "1"], "best": ["-n", "2", "--best"], "paired": ["-n", "3"]}[args.policy]
+    R = 2 if args.policy == "paired" else 1                     # reads per work unit
+    unit = "pairs/s" if R == 2 else "reads/s"
+    metric = "aligned read pairs/sec (2x100 bp, -n 3 paired-end)" if R == 2 else "aligned reads/sec (100 bp, -n 2)"
+    gen = make_pairs if R == 2 else make_reads
+    cfg_workload = f"{' '.join(ref_flags)}, {'2x' if R == 2 else ''}{READ_LEN} bp synthetic {'pairs (--fr, fragments N(200,20))' if R == 2 else 'reads'} (1% subs, both strands), index {idx_name}"
+
+    def write_sample(td: Path, h, n: int):
+        if R == 2:
+            write_fastq_pairs(td / "s_1.fq", td / "s_2.fq", h[0], h[1], h[4], n)
+            return (td / "s_1.fq", td / "s_2.fq")
+        write_fastq(td / "s.fq", h[0], h[1], h[4], n)
+        return td / "s.fq"
     cores = os.cpu_count() or 1
 
     if args.impl == "reference":
@@ -198,10 +259,9 @@ def main() -> None:
             return
         genome = load_genome(base)
         n = min(args.cpu_sample, args.reads_per_step)
-        codes, quals, offs, seeds, name = make_reads(genome, n, seed=12345)
+        h0 = gen(genome, n, seed=12345)
         with tempfile.TemporaryDirectory() as td:
-            fq = Path(td) / "s.fq"
-            write_fastq(fq, codes, quals, name, n)
+            fq = write_sample(Path(td), h0, n)
             times = []
             for it in range(args.warmup + args.steps):
                 search, wall = run_reference_sample(base, fq, n, cores, ref_flags)
@@ -209,13 +269,13 @@ def main() -> None:
                     times.append(wall)
         tot = sum(times)
         val = n * args.steps / tot
-        line = {"impl": "reference", "metric": "aligned reads/sec (100 bp, -n 2)", "value": val, "unit": "reads/s", "n_gpus": args.gpus,
+        line = {"impl": "reference", "metric": metric, "value": val, "unit": unit, "n_gpus": args.gpus,
                 "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * tot / args.steps, "higher_is_better": True,
                 "scaling": "weak", "vs_baseline": None, "dtype": "u32", "data": "synthetic",
                 "config": {"workload": cfg_workload, "reads_per_step": n, "parallelism": f"{cores} host threads (bowtie -p)"},
-                "cpu_baseline": {"value": val, "unit": "reads/s", "cores": cores, "kind": "reference",
+                "cpu_baseline": {"value": val, "unit": unit, "cores": cores, "kind": "reference",
                                  "sample": f"{n} reads per step, wall clock of bowtie-align-s {' '.join(ref_flags)} -p {cores} incl. index load"},
-                "e2e": {"value": val, "unit": "reads/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+                "e2e": {"value": val, "unit": unit, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
         print(json.dumps(line))
         return
 
@@ -231,14 +291,14 @@ def main() -> None:
     if not os.environ.get("BOWTIE_B200_LIB"):
         bowtie_b200.build_library()
     ix = bowtie_b200.Index(str(base), need_mirror=True, device=local)
-    pol = bowtie_b200.Policy(mode=1, mms=2, khits=1, best=(args.policy == "best"))
-    if args.policy == "best":
-        args.streams = min(args.streams, 3)      # every context of the best-first path owns ~15 GB of arenas
-    B, L, slots, mm_cap = args.reads_per_step, READ_LEN, 1, 7
+    pol = bowtie_b200.Policy(mode=1, mms=3 if R == 2 else 2, khits=1, best=(args.policy == "best"), paired=(R == 2))
+    if args.policy != "n2k1":
+        args.streams = min(args.streams, 3)      # every context of the best-first path owns ~12 GB of arenas
+    B, L, slots, mm_cap = args.reads_per_step, READ_LEN, R, 7
     rw = bowtie_b200.BT_HIT_HDR_WORDS + mm_cap
     genome = load_genome(base)
     # two distinct batches per rank, alternated, each larger than L2 (4M reads x 200 B = 800 MB)
-    host = [make_reads(genome, B, seed=12345 + 1000 * rank + k) for k in range(2)]
+    host = [gen(genome, B, seed=12345 + 1000 * rank + k) for k in range(2)]
     dev = [tuple(torch.from_numpy(np.ascontiguousarray(a)).cuda() for a in (h[0], h[1], h[2].view(np.int64), h[3].view(np.int32))) for h in host]
     NS = max(1, min(args.streams, args.steps))
     ctxs = [bowtie_b200.Context(ix) for _ in range(NS)]
@@ -250,7 +310,7 @@ def main() -> None:
     def step_dev(k: int) -> None:
         s, q, o, sd = dev[k & 1]
         f, g, h = d_out[k % NS]
-        ctxs[k % NS].align_device(s.data_ptr(), q.data_ptr(), o.data_ptr(), sd.data_ptr(), B, L, pol, f.data_ptr(), g.data_ptr(),
+        ctxs[k % NS].align_device(s.data_ptr(), q.data_ptr(), o.data_ptr(), sd.data_ptr(), B * R, L, pol, f.data_ptr(), g.data_ptr(),
                                   h.data_ptr(), slots, mm_cap, streams[k % NS].cuda_stream)
 
     def barrier() -> None:
@@ -322,7 +382,7 @@ def main() -> None:
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     e2e_val = B * args.steps * world / float(t.item())
-    h2d = 2 * B * L + 8 * (B + 1) + 4 * B
+    h2d = 2 * B * R * L + 8 * (B * R + 1) + 4 * B * R
     d2h = 4 * B + 4 * B + 4 * B * slots * rw
 
     if rank != 0:
@@ -350,15 +410,14 @@ def main() -> None:
         try:
             n = min(args.cpu_sample, B)
             with tempfile.TemporaryDirectory() as td:
-                fq = Path(td) / "s.fq"
-                write_fastq(fq, host[0][0], host[0][1], host[0][4], n)
+                fq = write_sample(Path(td), host[0], n)
                 search, wall = run_reference_sample(base, fq, n, cores, ref_flags)
-            cpu = {"value": n / wall, "unit": "reads/s", "cores": cores, "kind": "reference",
+            cpu = {"value": n / wall, "unit": unit, "cores": cores, "kind": "reference",
                    "sample": f"first {n} reads of step 0, bowtie-align-s {' '.join(ref_flags)} -p {cores}, wall clock {wall:.1f}s incl. index load ('Time searching' {search:.0f}s)"}
         except Exception as ex:  # the reference binary did not travel: report why instead of a number
-            cpu = {"value": None, "unit": "reads/s", "cores": cores, "kind": "reference", "sample": f"unavailable: {ex}"}
+            cpu = {"value": None, "unit": unit, "cores": cores, "kind": "reference", "sample": f"unavailable: {ex}"}
     line = {
-        "metric": "aligned reads/sec (100 bp, -n 2)", "value": value, "unit": "reads/s", "n_gpus": world, "steps": args.steps,
+        "metric": metric, "value": value, "unit": unit, "n_gpus": world, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": ms_max / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "u32", "data": "synthetic",
         "config": {"workload": cfg_workload, "reads_per_step_per_gpu": B, "index_len_bp": ix.len, "index_device_bytes": ix.device_bytes,
@@ -367,7 +426,7 @@ def main() -> None:
                    "aligned_frac_last_step": aligned / B, "aligned_frac_last_e2e_step": e2e_aligned / B, "overflow_flags": flags_bad,
                    "counters_allreduced": [int(x) for x in ctr.tolist()]},
         "clocks": clk.summary(),
-        "e2e": {"value": e2e_val, "unit": "reads/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
+        "e2e": {"value": e2e_val, "unit": unit, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
         # per step: 3 ctl_set, main search, 3 collect, heavy search, overflow search (best-first: 3 ctl_set, 3 arena tiers, 2 collect)
         "gpu_launches": (9 if args.policy == "n2k1" else 8) * args.steps,
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
