@@ -23,8 +23,11 @@ def lib_path() -> Path:
 def build_library(force: bool = False) -> Path:
     """Compile the CUDA library in-tree for sm_100a (nvcc cross-compiles without a GPU)."""
     so = lib_path()
-    srcs = [_PKG / "csrc" / n for n in ("bt_lib.cu", "bt_core.cuh", "bt_native.cuh")] + [_PKG.parent / "include" / "bowtie_b200.h"]
-    if force or not so.exists() or so.stat().st_mtime < max(s.stat().st_mtime for s in srcs):
+    csrc = _PKG / "csrc"
+    srcs = [p for p in csrc.iterdir() if p.suffix in (".cu", ".cuh", ".h")] + list((csrc / "host").glob("*.cpp")) + [_PKG.parent / "include" / "bowtie_b200.h"]
+    cli = _PKG / "bowtie-b200-align"
+    newest = max(s.stat().st_mtime for s in srcs)
+    if force or not so.exists() or not cli.exists() or min(so.stat().st_mtime, cli.stat().st_mtime) < newest:
         p = subprocess.run(["make", "-C", str(_PKG / "csrc")], capture_output=True, text=True)
         if p.returncode != 0:
             raise RuntimeError("building libbowtie_b200.so failed:\n" + p.stdout + p.stderr)
