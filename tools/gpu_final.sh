@@ -1,10 +1,9 @@
 #!/bin/bash
-# Round-end validation on one B200: GPU parity tests, smoke, the headline bench line and the best-first bench line.
+# Round-end validation on one B200: GPU parity tests (all), the paired-end bench line, launch list of the best-first bench.
 mkdir -p gpurun_out
 t0=$(date +%s)
-timeout 600 python -m pytest tests -m gpu -q -n 3 --timeout 200 > gpurun_out/pytest_gpu.log 2>&1; echo "pytest rc=$? t=$(( $(date +%s) - t0 ))s" >> gpurun_out/pytest_gpu.log
+timeout 330 python -m pytest tests -m gpu -q -n 3 --timeout 150 > gpurun_out/pytest_gpu.log 2>&1; echo "pytest rc=$? t=$(( $(date +%s) - t0 ))s" >> gpurun_out/pytest_gpu.log
 tail -4 gpurun_out/pytest_gpu.log
-timeout 300 python __graft_entry__.py smoke > gpurun_out/smoke.log 2>&1; echo "smoke rc=$?"; tail -3 gpurun_out/smoke.log
-timeout 420 python bench.py > gpurun_out/bench_r1_n1.json 2> gpurun_out/bench_r1_n1.err; echo "bench rc=$?"; tail -c 700 gpurun_out/bench_r1_n1.json
-BT_BENCH_READS=1000000 timeout 300 python bench.py --policy best --steps 3 --warmup 3 > gpurun_out/bench_r1_best.json 2> gpurun_out/bench_r1_best.err; echo "bench best rc=$?"; tail -c 900 gpurun_out/bench_r1_best.json; tail -3 gpurun_out/bench_r1_best.err
+BT_BENCH_READS=500000 timeout 150 python bench.py --policy paired --steps 3 --warmup 3 --cpu-sample 500000 > gpurun_out/bench_r1_paired.json 2> gpurun_out/bench_r1_paired.err; echo "bench paired rc=$?"; tail -c 1000 gpurun_out/bench_r1_paired.json; tail -3 gpurun_out/bench_r1_paired.err
+BT_BENCH_READS=200000 BT_BENCH_NO_CPU=1 BT_BENCH_STREAMS=1 timeout 100 ncu --metrics gpu__time_duration.sum --clock-control none --csv --log-file gpurun_out/launches_r1_best.csv python bench.py --policy best --steps 2 --warmup 3 > gpurun_out/ncu_best.log 2>&1; echo "ncu rc=$?"; grep -c bt_best_kernel gpurun_out/launches_r1_best.csv
 echo "total t=$(( $(date +%s) - t0 ))s"
