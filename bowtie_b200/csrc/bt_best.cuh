@@ -41,7 +41,7 @@ struct BfProg {
 	BfTopCfg top2[BF_MAX_TOP];   /* paired-end: mate 2's drivers (the -v factories configure the two mates differently) */
 	/* paired-end (PairedBWAlignerV1): which of the four per-mate, per-strand driver lists exist (do1Fw, do1Rc, do2Fw, do2Rc),
 	 * the reference-scan policy of the opposite mate (RefAligner family) and the insert-size window */
-	uint32_t paired, doList[4], refMms, refSeedLen, refQualMax, minIns, maxIns, fw1, fw2, mixedAttemptLim, symCeiling;
+	uint32_t paired, pairedV2, doList[4], refMms, refSeedLen, refQualMax, minIns, maxIns, fw1, fw2, mixedAttemptLim, symCeiling;
 };
 
 /* BitPairReference (reference.h:20-723): the 2-bit reference of X.4.ebwt with the stretch records of X.3.ebwt */
@@ -69,7 +69,7 @@ struct BfBranch {
 };
 #define BF_BRANCH_WORDS ((uint32_t)(sizeof(BfBranch) / 4))
 
-struct BfHdr { uint8_t kind, done, foundRange, fw; uint16_t minCost, minCostAdj; };
+struct BfHdr { uint8_t kind, done, foundRange, fw; uint16_t minCost, minCostAdj; uint8_t mate, pad[3]; };   /* mate: RangeSourceDriver::mate1() ? 0 : 1 */
 
 struct BfSrc {               /* EbwtRangeSourceDriver + its EbwtRangeSource + its PathManager */
 	BfHdr h;
@@ -88,6 +88,7 @@ struct BfSrc {               /* EbwtRangeSourceDriver + its EbwtRangeSource + it
 struct BfCA {                /* CostAwareRangeSourceDriver */
 	uint32_t rssOff, rssCap, nRss, actOff, actCap, nAct, rnd, lastRange, delayedRange;
 	uint16_t minCost; uint8_t done, foundRange;
+	uint32_t paired;             /* calcPaired(): drivers of both mates in one list (PairedBWAlignerV2) */
 };
 struct BfSeeded { BfHdr h; BfSrcCfg fact; uint32_t seedgen; BfCA full; };
 #define BF_SEEDED_WORDS ((uint32_t)(sizeof(BfSeeded) / 4))
@@ -609,7 +610,7 @@ BT_NOINLINE uint32_t bf_src_new(BfCtx &X, const BfSrcCfg &cfg) {
 	const uint32_t ref = bf_alloc_zero(X, BF_SRC_WORDS);
 	if (!ref) return 0;
 	BfSrc &s = *BF_AT(BfSrc, X, ref);
-	s.h.kind = BF_KIND_SRC; s.h.done = 1; s.h.fw = cfg.fw; s.cfg = cfg;
+	s.h.kind = BF_KIND_SRC; s.h.done = 1; s.h.fw = cfg.fw; s.h.mate = cfg.mate; s.cfg = cfg;
 	return ref;
 }
 
@@ -644,15 +645,22 @@ BT_NOINLINE void bf_ca_sort(BfCtx &X, BfCA &ca) {
 	}
 	if (ca.delayedRange == 0 && sz > 0) ca.minCost = bf_hdr(X, v[0]).minCost;
 }
+/* mateEliminated (range_source.h:2302-2315): in a list that mixes both mates, no live driver is left for one of them */
+BT_FN bool bf_ca_mate_eliminated(BfCtx &X, const BfCA &ca) {
+	if (!ca.paired) return false;
+	bool left[2] = { false, false };
+	for (uint32_t i = 0; i < ca.nAct; i++) { const BfHdr &h = bf_hdr(X, X.A[ca.actOff + i]); if (!h.done) left[h.mate & 1] = true; }
+	return !left[0] || !left[1];
+}
 /* foundFirstRange (range_source.h:2339-2377); strandFix is only ever set on the top-level driver */
 BT_NOINLINE bool bf_ca_found_first(BfCtx &X, BfCA &ca, uint32_t r, bool strandFix) {
 	ca.foundRange = 1;
 	ca.lastRange = r;
 	if (strandFix) {
-		const uint32_t rfw = BF_AT(BfSrc, X, r)->cfg.fw;
+		const uint32_t rfw = BF_AT(BfSrc, X, r)->cfg.fw, rmate = BF_AT(BfSrc, X, r)->cfg.mate;
 		const uint32_t *rss = X.A + ca.rssOff; const uint32_t *act = X.A + ca.actOff;
 		for (uint32_t i = 1; i < ca.nAct; i++) {
-			if (bf_hdr(X, rss[i]).fw != rfw) {                             /* sic: tests rss_[i], then uses active_[i] */
+			if (bf_hdr(X, rss[i]).mate == rmate && bf_hdr(X, rss[i]).fw != rfw) {   /* sic: tests rss_[i], then uses active_[i] */
 				const uint32_t p = act[i];
 				const uint32_t minCost = ca.minCost > bf_hdr(X, p).minCost ? ca.minCost : bf_hdr(X, p).minCost;
 				if (minCost > BF_AT(BfSrc, X, r)->rCost) break;
@@ -687,7 +695,7 @@ BT_NOINLINE void bf_ca_advance(BfCtx &X, BfCA &ca, bool strandFix) {
 		else ca.done = 1;
 		return;
 	}
-	if (ca.nAct == 0) { ca.done = 1; return; }
+	if ((TOP && bf_ca_mate_eliminated(X, ca)) || ca.nAct == 0) { ca.nAct = 0; ca.done = 1; return; }
 	const uint32_t p = X.A[ca.actOff];
 	const uint32_t precost = bf_hdr(X, p).minCost;
 	if (!bf_hdr(X, p).foundRange) { if (TOP) bf_node_advance(X, p); else bf_src_advance(X, *BF_AT(BfSrc, X, p)); }
@@ -700,7 +708,7 @@ BT_NOINLINE void bf_ca_advance(BfCtx &X, BfCA &ca, bool strandFix) {
 	}
 	if (bf_hdr(X, p).done || precost != bf_hdr(X, p).minCost || needsSort) {
 		bf_ca_sort(X, ca);
-		if (ca.nAct == 0) ca.done = (ca.delayedRange == 0);
+		if ((TOP && bf_ca_mate_eliminated(X, ca)) || ca.nAct == 0) { ca.nAct = 0; ca.done = (ca.delayedRange == 0); }
 	}
 }
 BT_FN void bf_ca_copy_active(BfCtx &X, BfCA &ca) {                       /* active_ = rss_ */
@@ -875,7 +883,7 @@ BT_NOINLINE void bf_align_read(BfCtx &X) {
 			node = bf_alloc_zero(X, BF_SEEDED_WORDS);
 			if (node) {
 				BfSeeded &sd = *BF_AT(BfSeeded, X, node);
-				sd.h.kind = BF_KIND_SEEDED; sd.h.done = 1; sd.h.fw = tc.a.fw; sd.fact = tc.b;
+				sd.h.kind = BF_KIND_SEEDED; sd.h.done = 1; sd.h.fw = tc.a.fw; sd.h.mate = tc.a.mate; sd.fact = tc.b;
 				sd.seedgen = bf_src_new(X, tc.a);
 			}
 		}
@@ -1253,7 +1261,7 @@ BT_NOINLINE void bf_align_pair(BfCtx &X) {
 		BfCA &ca = S.dr[k];
 		ca.rssOff = bf_alloc(X, BF_MAX_TOP); ca.rssCap = BF_MAX_TOP; ca.nRss = 0;
 		ca.actOff = bf_alloc(X, BF_MAX_TOP); ca.actCap = BF_MAX_TOP; ca.nAct = 0;
-		ca.minCost = 0; ca.lastRange = ca.delayedRange = 0; ca.done = 0; ca.foundRange = 0; ca.rnd = 0;
+		ca.minCost = 0; ca.lastRange = ca.delayedRange = 0; ca.done = 0; ca.foundRange = 0; ca.rnd = 0; ca.paired = 0;
 		S.chase[k] = S.delayed[k] = false; S.offsSz[k] = 0;
 		if (X.flags & BT_FLAG_STACK_OVF) return;
 		if (g.doList[k]) {
@@ -1268,7 +1276,7 @@ BT_NOINLINE void bf_align_pair(BfCtx &X) {
 					node = bf_alloc_zero(X, BF_SEEDED_WORDS);
 					if (node) {
 						BfSeeded &sd = *BF_AT(BfSeeded, X, node);
-						sd.h.kind = BF_KIND_SEEDED; sd.h.done = 1; sd.h.fw = tc.a.fw; sd.fact = tc.b;
+						sd.h.kind = BF_KIND_SEEDED; sd.h.done = 1; sd.h.fw = tc.a.fw; sd.h.mate = tc.a.mate; sd.fact = tc.b;
 						sd.seedgen = bf_src_new(X, tc.a);
 					}
 				}
@@ -1295,5 +1303,135 @@ BT_NOINLINE void bf_align_pair(BfCtx &X) {
 		const bool chasing = S.chase[S.L] || S.chase[S.R];
 		if (chasing && !S.rc.hasOff && !S.rc.done) { bf_chaser_advance(X, S.rc); continue; }
 		bf_pair_advance_orientation(X, S, !S.doneFw);
+	}
+}
+
+
+/* ================================================================================================= */
+/* Paired-end with --best / --strata / -M: PairedBWAlignerV2 (aligner.h:1483-2053).  One cost-aware  */
+/* list holds the drivers of both mates and both strands; every located row of every range, in cost   */
+/* order, anchors a reference scan for the opposite mate.  (reportSe, i.e. the per-mate sinks, is off  */
+/* by default and not provided.)                                                                       */
+/* ================================================================================================= */
+
+/* PairedBWAlignerV2::resolveOutstandingInRef (aligner.h:1851-1963) */
+BT_NOINLINE bool bf_pair2_resolve_in_ref(BfCtx &X, BfPairSet pairs[2], uint32_t tidx, uint32_t toff, const BfSrc &range) {
+	const BfProg &g = X.P->prog;
+	const bool mate1 = range.cfg.mate == 0;
+	const bool pairFw = mate1 ? ((range.cfg.fw != 0) == (g.fw1 != 0)) : ((range.cfg.fw != 0) == (g.fw2 != 0));
+	const bool matchRight = pairFw ? mate1 : !mate1;
+	bool fw = mate1 ? (g.fw2 != 0) : (g.fw1 != 0);
+	if (!pairFw) fw = !fw;
+	const uint32_t omate = mate1 ? 1u : 0u;
+	const uint32_t qlen = X.rlenM[omate], alen = X.rlenM[omate ^ 1];
+	const uint32_t minins = g.minIns, maxins = g.maxIns;
+	if (maxins <= (qlen > alen ? qlen : alen)) return false;
+	uint32_t begin, end;
+	const uint32_t insDiff = maxins - minins;
+	const uint32_t approx = BT_LDG(X.P->ref.approxLen + tidx);
+	if (matchRight) {
+		end = toff + maxins;
+		begin = toff + 1;
+		if (qlen < alen) begin += alen - qlen;
+		if (end > insDiff + qlen) { const uint32_t b2 = end - insDiff - qlen; if (b2 > begin) begin = b2; }
+		if (end > approx) end = approx;
+		if (begin > approx) begin = approx;
+	} else {
+		if (toff + alen < maxins) begin = 0; else begin = toff + alen - maxins;
+		const uint32_t mi = alen < qlen ? alen : qlen;
+		end = toff + mi - 1;
+		const uint32_t e2 = toff + alen - minins + qlen - 1;
+		if (e2 < end) end = e2;
+		if (toff + alen + qlen < minins + 1) end = 0;
+	}
+	if (end < begin || end - begin < qlen) return false;
+	const uint32_t mark = X.atop;
+	BfRangeView r; uint32_t result = 0;
+	BfPairSet &ps = pairs[pairFw ? 0 : 1];
+	const bool got = bf_ref_find(X, omate, fw, tidx, begin, end, toff, ps, r, result);
+	bool ret = false;
+	if (got) {
+		r.top = range.rTop; r.bot = range.rBot;
+		const BfRangeView av = bf_view_of(range);
+		ret = bf_pair_report(X, matchRight ? av : r, matchRight ? r : av, tidx, matchRight ? toff : result, matchRight ? result : toff, pairFw);
+	}
+	if (X.atop > mark && !(ps.off >= mark)) X.atop = mark;
+	return ret;
+}
+
+/* PairedBWAlignerV2::setQuery + advance (aligner.h:1566-1700) without single-end reporting */
+BT_NOINLINE void bf_align_pair_v2(BfCtx &X) {
+	const BfKParams &P = *X.P;
+	const BfProg &g = P.prog;
+	X.randA = X.seedM[0];
+	X.found = 0; X.bestStratum = 999; X.btCnt = (int32_t)P.pol.maxBtsBest;
+	if (X.rlenM[0] < 4 || X.rlenM[1] < 4) return;
+	BfCA &top = X.top;
+	const uint32_t cap = 4 * BF_MAX_TOP;
+	top.rssOff = bf_alloc(X, cap); top.rssCap = cap; top.nRss = 0;
+	top.actOff = bf_alloc(X, cap); top.actCap = cap; top.nAct = 0;
+	top.minCost = 0; top.lastRange = top.delayedRange = 0; top.done = 0; top.foundRange = 0;
+	if (X.flags & BT_FLAG_STACK_OVF) return;
+	/* the factories push the per-mate, per-strand lists in this order: -v: 1Fw 1Rc 2Fw 2Rc (aligner_0mm.h:322-325,
+	 * aligner_1mm.h:284-420, aligner_23mm.h:352-610); -n: 1Fw 2Fw 1Rc 2Rc (aligner_seed_mm.h:707-1313) */
+	const uint32_t orderV[4] = { 0, 1, 2, 3 }, orderN[4] = { 0, 2, 1, 3 };
+	bool saw[2] = { false, false };
+	for (uint32_t kk = 0; kk < 4; kk++) {
+		const uint32_t k = (P.pol.mode == 0 ? orderV : orderN)[kk];
+		if (!g.doList[k]) continue;
+		const uint32_t wantFw = (k & 1) ? 0u : 1u, mate = k >> 1;
+		for (uint32_t i = 0; i < g.ntop; i++) {
+			BfTopCfg tc = mate ? g.top2[i] : g.top[i];
+			if (tc.a.fw != wantFw) continue;
+			tc.a.mate = (uint8_t)mate; tc.b.mate = (uint8_t)mate;
+			uint32_t node;
+			if (tc.kind == BF_KIND_SRC) node = bf_src_new(X, tc.a);
+			else {
+				node = bf_alloc_zero(X, BF_SEEDED_WORDS);
+				if (node) {
+					BfSeeded &sd = *BF_AT(BfSeeded, X, node);
+					sd.h.kind = BF_KIND_SEEDED; sd.h.done = 1; sd.h.fw = tc.a.fw; sd.h.mate = (uint8_t)mate; sd.fact = tc.b;
+					sd.seedgen = bf_src_new(X, tc.a);
+				}
+			}
+			if (X.flags & BT_FLAG_STACK_OVF) return;
+			X.A[top.rssOff + top.nRss++] = node;
+			saw[mate] = true;
+		}
+	}
+	top.paired = saw[0] && saw[1];
+	bf_ca_set_query(X, top);
+	BfPairSet pairs[2]; pairs[0].off = pairs[0].cap = pairs[0].n = 0; pairs[1] = pairs[0];
+	BfChaser rc; rc.done = false; rc.hasOff = false; rc.rowDone = true;
+	bool done = false, chase = false, donePe = false;
+	uint32_t mixedAttempts = 0;
+	const bool strandFix = g.strandFix != 0;
+	while (!done) {
+		if (X.flags & (BT_FLAG_STACK_OVF | BT_FLAG_FRAME_OVF)) return;
+		if (chase) {
+			if (!rc.hasOff && !rc.done) { bf_chaser_advance(X, rc); continue; }
+			if (rc.hasOff) {
+				/* resolveOutstanding (aligner.h:1827-1849) */
+				if (!donePe) {
+					const BfSrc &r = *BF_AT(BfSrc, X, top.lastRange);
+					const bool ret = bf_pair2_resolve_in_ref(X, pairs, rc.tidx, rc.toff, r);
+					if (++mixedAttempts > g.mixedAttemptLim || ret) donePe = true;
+					done = donePe;
+				}
+				rc.hasOff = false;
+			} else { chase = false; done = top.done; }
+		}
+		if (!done && !chase) {
+			if (!top.done) {
+				if (!donePe) { donePe = bf_irrelevant_cost(X, top.minCost); if (donePe) done = true; }
+				if (!done) bf_ca_advance<true>(X, top, strandFix);
+				if (X.flags & (BT_FLAG_STACK_OVF | BT_FLAG_FRAME_OVF)) return;
+				if (top.foundRange) {
+					chase = true; top.foundRange = 0;
+					const BfSrc &r = *BF_AT(BfSrc, X, top.lastRange);
+					bf_chaser_set_top_bot(X, rc, r.rTop, r.rBot, X.rlenM[r.cfg.mate], r.cfg.ebwtSel);
+				}
+			} else done = true;
+		}
 	}
 }

@@ -29,10 +29,10 @@ static inline BfSrcCfg bf_cfg(int mirror, int fw, int reportExacts, int hh, int 
  * RefAligner that matches the policy. */
 static inline void bf_build_prog(int mode, int mms, int seedLen, uint32_t qualThresh, int nofw, int norc, BfProg *out,
                                  int paired = 0, int mate1fw = 1, int mate2fw = 0, uint32_t minIns = 0, uint32_t maxIns = 250,
-                                 uint32_t pairTries = 100, uint32_t mhits = 0xffffffffu, int forMate2 = 0) {
+                                 uint32_t pairTries = 100, uint32_t mhits = 0xffffffffu, int forMate2 = 0, int best = 0) {
 	BfProg &g = *out; memset(&g, 0, sizeof g);
 	if (paired) {
-		g.paired = 1; g.fw1 = mate1fw ? 1 : 0; g.fw2 = mate2fw ? 1 : 0; g.minIns = minIns; g.maxIns = maxIns;
+		g.paired = 1; g.pairedV2 = best ? 1 : 0; g.fw1 = mate1fw ? 1 : 0; g.fw2 = mate2fw ? 1 : 0; g.minIns = minIns; g.maxIns = maxIns;
 		g.mixedAttemptLim = pairTries; g.symCeiling = mhits;
 		g.refMms = (uint32_t)mms; g.refSeedLen = mode == 0 ? 0u : (uint32_t)seedLen; g.refQualMax = mode == 0 ? 0xffffffffu : qualThresh;
 		bool d1f = true, d1r = true, d2f = true, d2r = true;

@@ -355,8 +355,8 @@ bt_best_kernel(const __grid_constant__ BfKParams P, BtWorkCtl *ctl, uint32_t lan
 		}
 		X.atop = 1; X.flags = 0; X.found = 0;
 		X.top.rssOff = X.top.rssCap = X.top.nRss = X.top.actOff = X.top.actCap = X.top.nAct = 0;
-		X.top.lastRange = X.top.delayedRange = 0; X.top.minCost = 0; X.top.done = 0; X.top.foundRange = 0; X.top.rnd = 0;
-		if (PAIRED) bf_align_pair(X); else bf_align_read(X);
+		X.top.lastRange = X.top.delayedRange = 0; X.top.minCost = 0; X.top.done = 0; X.top.foundRange = 0; X.top.rnd = 0; X.top.paired = 0;
+		if (PAIRED) { if (P.prog.pairedV2) bf_align_pair_v2(X); else bf_align_pair(X); } else bf_align_read(X);
 		if (X.flags & (BT_FLAG_STACK_OVF | BT_FLAG_FRAME_OVF)) X.found = 0;     /* STACK_OVF: re-run by a pass with a larger arena */
 		P.found[rid] = X.found; P.flags[rid] = X.flags;
 	}
@@ -671,7 +671,6 @@ static int check_policy(const bt_index_t *ix, const bt_policy_t *pol) {
 	else return fail("bt_align: bad mode");
 	if ((pol->mode == 1 || pol->mms > 0) && !ix->has_mirror) return fail("bt_align: this policy needs the mirror index (load with need_mirror=1)");
 	if (!pol->all_hits && pol->khits == 0) return fail("bt_align: -k must be >= 1");
-	if (pol->paired && (pol->best || pol->strata || pol->sample_max)) return fail("bt_align: paired-end with --best/--strata/-M is the reference's PairedBWAlignerV2; not provided");
 	return 0;
 }
 
@@ -739,7 +738,7 @@ static int enqueue_best(bt_context *cx, const bt_policy_t *pol, const bt_read_ba
 	P.ix[0] = ix->dev[0].dev; P.ix[1] = ix->dev[1].dev;
 	memcpy(&P.pol, pol, sizeof(BtPolicy));
 	bf_build_prog(pol->mode, pol->mms, pol->seed_len, pol->qual_thresh, pol->nofw, pol->norc, &P.prog,
-	              pol->paired, pol->mate1fw, pol->mate2fw, pol->min_ins, pol->max_ins, pol->pair_tries, pol->mhits);
+	              pol->paired, pol->mate1fw, pol->mate2fw, pol->min_ins, pol->max_ins, pol->pair_tries, pol->mhits, 0, pol->best);
 	if (pol->paired) P.ref = ix->dref;
 	P.seq = in->seq; P.qual = in->qual; P.roff = in->offs; P.seeds = in->seeds; P.sel = in->sel; P.nwork = nwork;
 	P.found = out->found; P.flags = out->flags; P.hits = out->hits; P.slots = out->slots; P.mm_cap = out->mm_cap; P.rec_words = BT_HIT_HDR + out->mm_cap;

@@ -33,7 +33,7 @@ struct Opts {
 	std::string ebwtFile, outfile;
 	std::vector<std::string> queries;
 	int mismatches = 0, seedMms = 2, maqLike = 1, seedLen = 28, qualThresh = 70, maxBts = 125, maxBtsBest = 800;
-	bool best = false, strata = false, sampleMax = false;
+	bool best = false, strata = false, sampleMax = false, bestFlag = false;   /* bestFlag: --best itself (it alone selects the V2 paired aligner) */
 	std::vector<std::string> mates1, mates2;
 	uint32_t minInsert = 0, maxInsert = 250, pairTries = 100; bool mate1fw = true, mate2fw = false;
 	bool noMaqRound = false, nofw = false, norc = false, allHits = false;
@@ -138,7 +138,7 @@ static void parse_options(int argc, char **argv, Opts &o) {
 		case ARG_RF: o.mate1fw = false; o.mate2fw = true; break;
 		case ARG_PAIRTRIES: o.pairTries = (uint32_t)parse_int(1, "--pairtries arg must be at least 1"); break;
 		case ARG_PAIRED: unsupported("--12 / --interleaved input"); break;
-		case ARG_BEST: o.best = true; break;
+		case ARG_BEST: o.best = true; o.bestFlag = true; break;
 		case ARG_STRATA: o.strata = true; break;
 		case ARG_LARGE_INDEX: die("Error: large (64-bit) indexes are not supported"); break;
 		case ARG_PHRED33: o.solexaQuals = false; o.phred64Quals = false; break;
@@ -169,7 +169,6 @@ static void parse_options(int argc, char **argv, Opts &o) {
 	}
 	(void)vset;
 	/* ebwt_search.cpp:851-854, 877-891 */
-	const bool bestAsked = o.best || o.strata || o.sampleMax;                    /* -v 3 alone keeps the V1 paired aligner (useV1, ebwt_search.cpp:776) */
 	if (!o.maqLike && o.mismatches == 3) o.best = true;
 	if (!o.best && o.sampleMax) {
 		if (!o.quiet) fprintf(stderr, "Warning: -M was specified w/o --best; automatically enabling --best\n");
@@ -190,8 +189,7 @@ static void parse_options(int argc, char **argv, Opts &o) {
 	if (o.mates1.empty()) {
 		if (optind >= argc) die("No query or output file specified!");
 		split(argv[optind++], ',', o.queries);
-	} else if (bestAsked) unsupported("paired-end alignment with --best / --strata / -M (PairedBWAlignerV2)");
-	else o.best = false;
+	} else o.best = o.bestFlag;                                                   /* pairs: only --best switches to PairedBWAlignerV2 (useV1 = false, ebwt_search.cpp:776); -M / -v 3 alone keep V1 */
 	if (optind < argc) o.outfile = argv[optind++];
 	if (optind < argc) die(std::string("Extra parameter(s) specified: ") + argv[optind]);
 	if (o.sam) std::fill(o.suppress.begin(), o.suppress.end(), false);
@@ -650,15 +648,36 @@ int main(int argc, char **argv) {
 				if (op.sampleMax) {
 					/* VerboseHitSink::reportMaxed (hit.cpp:16-68) / SAMHitSink::reportMaxed (sam.cpp:263-311): one of the
 					 * buffered hits of the best stratum, picked with a fresh RandomSource seeded by the read */
-					const uint32_t nbuf = op.mhits;                               /* hits buffered before the ceiling was exceeded */
-					uint32_t num = 1;
-					for (uint32_t s = 1; s < nbuf; s++) { if (((recs[(size_t)s * rwi + 3] >> 16) & 0xff) == ((recs[(size_t)(s - 1) * rwi + 3] >> 16) & 0xff)) num++; else break; }
-					uint32_t last = b.seeds[i];
+					const uint32_t nbuf = mhitsU;                                 /* hits buffered before the ceiling was exceeded */
+					auto stratum_of = [&](uint32_t s) { return (recs[(size_t)s * rwi + 3] >> 16) & 0xff; };
+					uint32_t last = b.seeds[i * mult];
 					last = 1664525u * last + 1013904223u; uint32_t rr = last >> 16; last = 1664525u * last + 1013904223u; rr ^= last;   /* RandomSource::nextU32 */
-					const uint32_t *w = recs + (size_t)(rr % num) * rwi;
-					HitView h = { w[0], w[1], nbuf, w[3] & 0xffffu, (w[3] >> 16) & 0xff, (w[3] >> 24) & 1, w[4], w + BT_HIT_HDR_WORDS };
-					if (op.sam) append_sam(out.buf, op, ix, r, h, 0, (int)nbuf + 1); else append_default(out.buf, op, ix, r, h);
-					numAligned++; numReported++;
+					if (!paired) {
+						uint32_t num = 1;
+						for (uint32_t s = 1; s < nbuf; s++) { if (stratum_of(s) == stratum_of(s - 1)) num++; else break; }
+						const uint32_t *w = recs + (size_t)(rr % num) * rwi;
+						HitView h = { w[0], w[1], nbuf, w[3] & 0xffffu, (w[3] >> 16) & 0xff, (w[3] >> 24) & 1, w[4], w + BT_HIT_HDR_WORDS };
+						if (op.sam) append_sam(out.buf, op, ix, r, h, 0, (int)nbuf + 1); else append_default(out.buf, op, ix, r, h);
+						numAligned++; numReported++;
+					} else {
+						/* pairs: among the couples whose better mate is in the best stratum (hit.cpp:28-54, sam.cpp:275-299) */
+						uint32_t bestS = 999, num = 0;
+						for (uint32_t s = 0; s + 1 < nbuf; s += 2) { const uint32_t st = std::min(stratum_of(s), stratum_of(s + 1)); if (st < bestS) { bestS = st; num = 1; } else if (st == bestS) num++; }
+						const uint32_t pick = rr % num; num = 0;
+						for (uint32_t s = 0; s + 1 < nbuf; s += 2) {
+							if (std::min(stratum_of(s), stratum_of(s + 1)) != bestS) continue;
+							if (num++ != pick) continue;
+							for (uint32_t k = s; k < s + 2; k++) {
+								const uint32_t *w = recs + (size_t)k * rwi, *mw = recs + (size_t)(k ^ 1) * rwi;
+								HitView h = { w[0], w[1], nbuf / 2, w[3] & 0xffffu, (w[3] >> 16) & 0xff, (w[3] >> 24) & 1, w[4], w + BT_HIT_HDR_WORDS };
+								h.mate = (w[3] >> 25) & 3; h.mtoff = mw[1]; h.mfw = (mw[3] >> 24) & 1; h.mlen = (uint32_t)b.reads[i * mult + (2 - h.mate)].seq.size();
+								const ReadRec &rr2 = b.reads[i * mult + (h.mate - 1)];
+								if (op.sam) append_sam(out.buf, op, ix, rr2, h, 0, (int)(nbuf / 2) + 1); else append_default(out.buf, op, ix, rr2, h);
+							}
+							break;
+						}
+						numAligned++; numReported += 2;
+					}
 				}
 			}
 			else if (unal) {
@@ -669,7 +688,7 @@ int main(int argc, char **argv) {
 				for (uint32_t s = 0; s < nrep; s++) {
 					const uint32_t *w = recs + (size_t)s * rwi;
 					HitView h = { w[0], w[1], w[2], w[3] & 0xffffu, (w[3] >> 16) & 0xff, (w[3] >> 24) & 1, w[4], w + BT_HIT_HDR_WORDS };
-					if (op.strata) h.oms = found - 1;                           /* NBestFirstStratHitSinkPerThread::finishReadImpl (hit.h:1099-1108) */
+					if (op.strata) h.oms = found / mult - 1;                    /* NBestFirstStratHitSinkPerThread::finishReadImpl (hit.h:1099-1108): sz / mult - 1 */
 					h.mate = (w[3] >> 25) & 3;
 					const ReadRec *rr = &r;
 					if (h.mate) {                                               /* records come in (upstream, downstream) couples */

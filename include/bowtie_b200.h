@@ -51,7 +51,7 @@ typedef struct bt_policy {
 	int32_t  sample_max;  /* -M: records are kept up to the mhits ceiling (the caller samples one, hit.cpp:16-68); needs best */
 	int32_t  paired;      /* paired-end (PairedBWAlignerV1, aligner.h:606-1468): reads 2p and 2p+1 of the batch are mates 1 and 2 of
 	                         pair p; found/flags/hits are indexed by p; records alternate upstream/downstream mate (mate number in
-	                         bits 25-26 of word 3); needs the index's X.3.ebwt/X.4.ebwt.  Not combinable with best.                    */
+	                         bits 25-26 of word 3); needs the index's X.3.ebwt/X.4.ebwt.  With best: PairedBWAlignerV2 (aligner.h:1483-2053). */
 	uint32_t min_ins, max_ins;   /* -I (default 0) / -X (default 250), minus the trimmed bases as in aligner.h:975-990                 */
 	int32_t  mate1fw, mate2fw;   /* --fr (default): 1, 0 ; --rf: 0, 1 ; --ff: 1, 1                                                    */
 	uint32_t pair_tries;  /* --pairtries, default 100 (mixedAttemptLim)                                                              */

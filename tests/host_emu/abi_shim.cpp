@@ -95,7 +95,7 @@ static int run_best(bt_index *ix, const bt_policy_t *pol, const bt_read_batch_t 
 	P.ix[0] = ix->e[0]->dev; if (ix->e[1]) P.ix[1] = ix->e[1]->dev;
 	memcpy(&P.pol, pol, sizeof(BtPolicy));
 	bf_build_prog(pol->mode, pol->mms, pol->seed_len, pol->qual_thresh, pol->nofw, pol->norc, &P.prog,
-	              pol->paired, pol->mate1fw, pol->mate2fw, pol->min_ins, pol->max_ins, pol->pair_tries, pol->mhits);
+	              pol->paired, pol->mate1fw, pol->mate2fw, pol->min_ins, pol->max_ins, pol->pair_tries, pol->mhits, 0, pol->best);
 	if (pol->paired) {
 		if (!ix->ref_loaded) { if (!bt_load_ref(ix->base, ix->href, g_err)) return 1; ix->ref_loaded = true; }
 		const BtHostRef &h = ix->href;
@@ -118,10 +118,10 @@ static int run_best(bt_index *ix, const bt_policy_t *pol, const bt_read_batch_t 
 			X.seqM[m] = in->seq + in->offs[rd]; X.qualM[m] = in->qual + in->offs[rd];
 		}
 		X.A = arena.data(); X.acap = words; X.atop = 1;
-		if (pol->paired) bf_align_pair(X); else bf_align_read(X);
+		if (pol->paired) { if (P.prog.pairedV2) bf_align_pair_v2(X); else bf_align_pair(X); } else bf_align_read(X);
 		if ((X.flags & BT_FLAG_STACK_OVF) && words < arena.size()) {      /* what the larger-arena passes of the product do */
 			memset(&X.top, 0, sizeof X.top); X.flags = 0; X.acap = (uint32_t)arena.size(); X.atop = 1;
-			if (pol->paired) bf_align_pair(X); else bf_align_read(X);
+			if (pol->paired) { if (P.prog.pairedV2) bf_align_pair_v2(X); else bf_align_pair(X); } else bf_align_read(X);
 		}
 		if (X.flags & (BT_FLAG_STACK_OVF | BT_FLAG_FRAME_OVF)) X.found = 0;
 		out->found[r] = X.found; out->flags[r] = X.flags;

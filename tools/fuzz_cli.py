@@ -16,8 +16,8 @@ from pathlib import Path
 
 ROOT = Path(__file__).resolve().parent.parent
 REF = ROOT / "oracle" / "_ref"
-CLI = ROOT / "bowtie_b200" / "bowtie-b200-align"
-SHIM = ROOT / "tests" / "host_emu" / "shim"
+CLI = Path(os.environ.get("BT_FUZZ_CLI", ROOT / "bowtie_b200" / "bowtie-b200-align"))      # copies let a long run survive rebuilds
+SHIM = Path(os.environ.get("BT_FUZZ_SHIM", ROOT / "tests" / "host_emu" / "shim"))
 
 
 def rand_genome(rng):
