@@ -16,14 +16,19 @@ from helpers import FIXTURES, REF_ALIGN, ROOT, ensure_oracle_built, have_referen
 from test_cli_parity import CLI, SHIM_DIR, build_shim
 
 # md5 of the reference's hit file for the shipped paired reads
-GOLDEN = {"-n 3": "13330dbc5beb1b9b3070d6c6939ac9b7", "-n 2": "13330dbc5beb1b9b3070d6c6939ac9b7", "-v 2": "956cd5667fdec6116b3672ea1eac78b2"}
+GOLDEN = {"-n 3": "13330dbc5beb1b9b3070d6c6939ac9b7", "-n 2": "13330dbc5beb1b9b3070d6c6939ac9b7", "-v 2": "956cd5667fdec6116b3672ea1eac78b2",
+          "-n 3 --best": "95df699b45a45d4a4c6072e7b0361463"}
 
 ECOLI_FLAGS = [
     "-n 3", "-n 2", "-n 1", "-n 0", "-v 0", "-v 1", "-v 2", "-v 3", "-n 2 -k 3", "-n 2 -a", "-n 2 -m 1", "-n 2 -m 2 -k 2", "-v 2 -a",
     "-n 2 -S", "-v 1 -S -k 2", "-n 2 -X 150", "-n 2 -I 100 -X 300", "-n 2 --ff", "-n 2 --rf", "-n 2 --nofw", "-n 2 --norc",
     "-n 2 -l 20 -e 100", "-n 3 --nomaqround -a", "-n 2 --pairtries 2", "-n 2 -5 2 -3 3", "-n 2 --maxbts 3", "-n 2 -S --no-unal -X 120",
+    # PairedBWAlignerV2 (--best) and -M on pairs
+    "-n 3 --best", "-n 2 --best", "-v 2 --best", "-n 2 --best --strata -k 3", "-n 2 --best -a", "-v 3 --best -k 2", "-n 2 -M 1", "-n 2 -M 2 --best",
+    "-n 2 --best -S", "-n 2 -M 1 -S", "-n 2 --best --strata -a -m 3",
 ]
-SYNTH_FLAGS = ["-n 2", "-n 3 -a", "-n 1 -k 3", "-v 0", "-v 2 -k 2", "-v 3", "-n 2 -m 2", "-n 2 -I 150 -X 260", "-n 2 -l 15 -e 200 -a", "-n 2 -S", "-v 1 -a -X 500"]
+SYNTH_FLAGS = ["-n 2", "-n 3 -a", "-n 1 -k 3", "-v 0", "-v 2 -k 2", "-v 3", "-n 2 -m 2", "-n 2 -I 150 -X 260", "-n 2 -l 15 -e 200 -a", "-n 2 -S", "-v 1 -a -X 500",
+               "-n 2 --best", "-n 3 --best --strata -a", "-v 3 --best -k 3", "-n 2 -M 2", "-v 1 --best -a -X 400", "-n 1 --best --strata -m 3 -k 2"]
 
 
 @pytest.fixture(scope="module")
@@ -82,12 +87,6 @@ def test_paired_ecoli_logic(flags, setup, tmp_path):
 @pytest.mark.parametrize("reads", ["low", "gap"])
 def test_paired_synthetic_logic(flags, reads, setup, tmp_path):
     compare(flags, setup[reads], tmp_path, shim_env())
-
-
-def test_paired_best_is_rejected(setup, tmp_path):
-    base, m1, m2 = setup["ecoli"]
-    p = subprocess.run([str(CLI), "--best", "-x", str(base), "-1", str(m1), "-2", str(m2)], capture_output=True, text=True, env=shim_env())
-    assert p.returncode != 0 and "PairedBWAlignerV2" in p.stderr
 
 
 @pytest.mark.gpu

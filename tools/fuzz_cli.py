@@ -100,13 +100,20 @@ def rand_paired_flags(rng):
         f += ["-n", str(rng.randint(0, 3)), "-l", str(rng.choice([5, 8, 12, 20, 28])), "-e", str(rng.choice([40, 70, 150, 400]))]
         if rng.random() < 0.3:
             f += ["--nomaqround"]
-    rep = rng.choice(["k1", "k", "a", "m"])
+    rep = rng.choice(["k1", "k", "a", "m", "M"])
+    best = rng.random() < 0.4
     if rep == "k":
         f += ["-k", str(rng.randint(2, 5))]
     elif rep == "a":
         f += ["-a"]
     elif rep == "m":
         f += ["-m", str(rng.randint(1, 3))] + rng.choice([[], ["-k", "3"], ["-a"]])
+    elif rep == "M":
+        f += ["-M", str(rng.randint(1, 3))]
+    if best:
+        f += ["--best"]                                       # PairedBWAlignerV2
+        if rep in ("k", "a", "m") and rng.random() < 0.5:
+            f += ["--strata"]
     maxins = 250
     if rng.random() < 0.4:
         maxins = rng.choice([60, 120, 200, 400])
