@@ -427,8 +427,8 @@ def main() -> None:
                    "counters_allreduced": [int(x) for x in ctr.tolist()]},
         "clocks": clk.summary(),
         "e2e": {"value": e2e_val, "unit": unit, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
-        # per step: 3 ctl_set, main search, 3 collect, heavy search, overflow search (best-first: 3 ctl_set, 3 arena tiers, 2 collect)
-        "gpu_launches": (9 if args.policy == "n2k1" else 8) * args.steps,
+        # per step: 3 ctl_set, main search, 3 collect, heavy search, overflow search (best-first / paired: 4 ctl_set, 4 arena tiers, 3 collect)
+        "gpu_launches": (9 if args.policy == "n2k1" else 11) * args.steps,
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
                      "peak_source": "MEASURED_PEAKS.json hbm_gbs" if peaks else "fallback 6650 GB/s",
                      "side_fetches_per_read": st.side_fetches / (B * args.steps), "block_loads_per_read": st.block_loads / (B * args.steps),

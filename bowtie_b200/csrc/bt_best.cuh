@@ -17,7 +17,7 @@
  * sits at the top of the queue (extend(), curtail() without a cost change), so the pop order of the reference
  * depends on the heap's physical layout, not only on the comparison.
  * Range states are stored only for positions where an edit can ever be considered (i >= depth0 - rdepth,
- * range_source.h:671-672,890-891).  Arena exhaustion sets BT_FLAG_STACK_OVF and the read is re-run by a pass
+ * range_source.h:671-672,890-891), in blocks of 8 that a branch acquires as it extends (most branches die young).  Arena exhaustion sets BT_FLAG_STACK_OVF and the read is re-run by a pass
  * with a larger arena (the reference's own limit is --chunkmbs; it skips the read instead).
  *
  * Compiles for the device and, for tests/host_emu only, for the host (BT_HOST_EMU).
@@ -61,9 +61,10 @@ struct BtDevRef {
 struct BfRS { uint32_t tops[4], bots[4], eq; };       /* RangeState: eq bits 0-3 = mm{A,C,G,T} eliminated, 8-14 = quallo, 31 = eliminated_ */
 #define BF_RS_WORDS 9
 #define BF_RS_ELIM 0x80000000u
+#define BF_RS_BLK 8              /* range states are allocated in blocks of 8 positions, when a branch first reaches them */
 
 struct BfBranch {
-	uint32_t id, top, bot, ltop, lbot, ranges, edits;      /* edits: nedits arena words */
+	uint32_t id, top, bot, ltop, lbot, ranges, edits;      /* ranges: table of block refs (0 = not yet allocated); edits: nedits arena words */
 	uint16_t depth0, depth1, depth2, depth3, rdepth, len, cost, ham, rangesSz, i0, delayedCost, nedits;
 	uint8_t curtailed, exhausted, delayedIncrease, lbotValid;
 };
@@ -108,9 +109,10 @@ struct BfCtx {
 	const BfKParams *P;
 	const uint8_t *seqM[2], *qualM[2];                    /* [0]: the read (mate 1), [1]: mate 2 */
 	uint32_t rid, rlenM[2], seedM[2];
-	uint32_t *A; uint32_t acap, atop;
+	uint32_t *A; uint32_t acap, atop, amax;               /* amax: high-water mark of the arena (diagnostics) */
 	uint32_t flags, found, randA;
 	int32_t bestStratum, btCnt;
+	BfRS spare;                                            /* where range-state writes land once the arena is exhausted */
 	BfCA top;
 	uint32_t s_lfex, s_lf, s_chase, s_ftab, s_offs, s_bt;
 };
@@ -119,6 +121,7 @@ struct BfCtx {
 BT_FN uint32_t bf_alloc(BfCtx &X, uint32_t words) {
 	if (X.atop + words > X.acap) { X.flags |= BT_FLAG_STACK_OVF; return 0; }
 	const uint32_t off = X.atop; X.atop += words;
+	if (X.atop > X.amax) X.amax = X.atop;
 	return off;
 }
 BT_FN uint32_t bf_alloc_zero(BfCtx &X, uint32_t words) {
@@ -214,7 +217,18 @@ BT_FN void bf_branch_prep(BfBranch &b) {                                 /* Bran
 	if (b.bot > b.top + 1) { b.ltop = b.top; b.lbot = b.bot; b.lbotValid = 1; }
 	else if (b.bot > b.top) { b.ltop = b.top; b.lbotValid = 0; }
 }
-BT_FN BfRS *bf_rs(BfCtx &X, const BfBranch &b, uint32_t i) { return BF_AT(BfRS, X, b.ranges + (i - b.i0) * BF_RS_WORDS); }
+/* The reference reserves qlen - rdepth RangeStates per Branch (range_source.h:570-578); most branches die within a few
+ * positions, so here a branch owns a table of block refs and a block of BF_RS_BLK zeroed states is carved on first touch. */
+BT_FN BfRS *bf_rs(BfCtx &X, const BfBranch &b, uint32_t i) {
+	const uint32_t idx = i - b.i0;
+	uint32_t blk = X.A[b.ranges + idx / BF_RS_BLK];
+	if (!blk) {
+		blk = bf_alloc_zero(X, BF_RS_BLK * BF_RS_WORDS);
+		if (!blk) { X.spare.eq = 0; return &X.spare; }
+		X.A[b.ranges + idx / BF_RS_BLK] = blk;
+	}
+	return BF_AT(BfRS, X, blk + (idx % BF_RS_BLK) * BF_RS_WORDS);
+}
 BT_FN bool bf_eliminated(BfCtx &X, const BfBranch &b, uint32_t i) {      /* Branch::eliminated, range_source.h:619-634 */
 	if (i <= b.len && i < b.rangesSz) return (bf_rs(X, b, i)->eq & BF_RS_ELIM) != 0;
 	return true;
@@ -246,7 +260,7 @@ BT_NOINLINE uint32_t bf_branch_new(BfCtx &X, BfSrc &s, uint32_t qlen, uint32_t d
 	b.i0 = (uint16_t)(i0 < b.rangesSz ? i0 : b.rangesSz);
 	b.ranges = 0;
 	if (b.rangesSz > b.i0) {
-		b.ranges = bf_alloc_zero(X, (uint32_t)(b.rangesSz - b.i0) * BF_RS_WORDS);
+		b.ranges = bf_alloc_zero(X, ((uint32_t)(b.rangesSz - b.i0) + BF_RS_BLK - 1) / BF_RS_BLK);
 		if (!b.ranges) return 0;
 	}
 	b.curtailed = 0; b.exhausted = 0; b.delayedIncrease = 0;
@@ -255,7 +269,7 @@ BT_NOINLINE uint32_t bf_branch_new(BfCtx &X, BfSrc &s, uint32_t qlen, uint32_t d
 }
 BT_FN void bf_branch_free(BfCtx &X, BfSrc &s, uint32_t ref) {            /* Branch::free: only the newest slot is really reclaimed */
 	BfBranch &b = *BF_BR(X, ref);
-	if (b.ranges) bf_free_top(X, b.ranges, (uint32_t)(b.rangesSz - b.i0) * BF_RS_WORDS);
+	if (b.ranges) bf_free_top(X, b.ranges, ((uint32_t)(b.rangesSz - b.i0) + BF_RS_BLK - 1) / BF_RS_BLK);
 	if (b.id == s.bcur && s.bcur > 0) s.bcur--;
 	if (b.edits) bf_free_top(X, b.edits, b.nedits);
 	bf_free_top(X, ref, BF_BRANCH_WORDS);

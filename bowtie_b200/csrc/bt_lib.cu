@@ -327,7 +327,7 @@ bt_search_kernel_q(BtKParams P, BtWorkCtl *ctl, uint32_t nctx) {
 static size_t bt_q_smem(uint32_t nctx) { return sizeof(BtQueues) + (size_t)nctx * BT_CTX_WORDS * 4; }
 
 /* Best-first path (--best / --strata / -M / -v 3): every thread takes reads from the global cursor and runs the whole
- * UnpairedAlignerV2 loop for each on its own arena of P.arenaWords words.  `lanes` threads of each block are active. */
+ * aligner loop (UnpairedAlignerV2 / PairedBWAlignerV1 / V2) for each on its own arena of P.arenaWords words.  `lanes` threads of each block are active. */
 #define BF_THREADS 64
 template <bool PAIRED>
 __global__ void __launch_bounds__(BF_THREADS)
@@ -353,7 +353,7 @@ bt_best_kernel(const __grid_constant__ BfKParams P, BtWorkCtl *ctl, uint32_t lan
 			X.rlenM[1] = (uint32_t)(P.roff[r0 + 2] - ro1); X.seedM[1] = P.seeds[r0 + 1];
 			X.seqM[1] = P.seq + ro1; X.qualM[1] = P.qual + ro1;
 		}
-		X.atop = 1; X.flags = 0; X.found = 0;
+		X.atop = 1; X.amax = 1; X.flags = 0; X.found = 0;
 		X.top.rssOff = X.top.rssCap = X.top.nRss = X.top.actOff = X.top.actCap = X.top.nAct = 0;
 		X.top.lastRange = X.top.delayedRange = 0; X.top.minCost = 0; X.top.done = 0; X.top.foundRange = 0; X.top.rnd = 0; X.top.paired = 0;
 		if (PAIRED) { if (P.prog.pairedV2) bf_align_pair_v2(X); else bf_align_pair(X); } else bf_align_read(X);
@@ -432,8 +432,8 @@ struct bt_index {
 struct bt_context {
 	bt_index *ix = nullptr;
 	Workspace ws1, wsh, ws2;     /* main pass / heavy-read pass / scratch-overflow pass */
-	uint32_t *arena[3] = { nullptr, nullptr, nullptr }; size_t arena_words[3] = { 0, 0, 0 };   /* best-first path: three arena tiers */
-	BtWorkCtl *ctl = nullptr;    /* [3] */
+	uint32_t *arena[4] = { nullptr, nullptr, nullptr, nullptr }; size_t arena_words[4] = { 0, 0, 0, 0 };   /* best-first path: four arena tiers */
+	BtWorkCtl *ctl = nullptr;    /* [4] */
 	uint32_t *heavy_sel = nullptr, *retry_sel = nullptr; uint32_t retry_cap = 0;
 	cudaStream_t side = nullptr; /* the heavy and overflow passes run here, overlapping the next batch's main pass */
 	cudaEvent_t ev_main = nullptr, ev_tail = nullptr;
@@ -545,7 +545,7 @@ extern "C" void bt_context_free(bt_context_t *cx) {
 	if (cx->ev_main) cudaEventDestroy(cx->ev_main);
 	if (cx->ev_tail) cudaEventDestroy(cx->ev_tail);
 	cx->ws1.release(); cx->wsh.release(); cx->ws2.release();
-	for (int k = 0; k < 3; k++) cudaFree(cx->arena[k]);
+	for (int k = 0; k < 4; k++) cudaFree(cx->arena[k]);
 	cudaFree(cx->ctl); cudaFree(cx->retry_sel); cudaFree(cx->heavy_sel);
 	cudaFree(cx->d_seq); cudaFree(cx->d_qual); cudaFree(cx->d_offs); cudaFree(cx->d_seeds); cudaFree(cx->d_sel);
 	cudaFree(cx->d_found); cudaFree(cx->d_flags); cudaFree(cx->d_hits);
@@ -558,7 +558,7 @@ extern "C" int bt_context_create(bt_index_t *ix, bt_context_t **out) {
 	CUDA_TRY(cudaSetDevice(ix->device));
 	bt_context *cx = new bt_context();
 	cx->ix = ix;
-	if (cudaMalloc((void **)&cx->ctl, 3 * sizeof(BtWorkCtl)) != cudaSuccess || cudaStreamCreateWithFlags(&cx->side, cudaStreamNonBlocking) != cudaSuccess ||
+	if (cudaMalloc((void **)&cx->ctl, 4 * sizeof(BtWorkCtl)) != cudaSuccess || cudaStreamCreateWithFlags(&cx->side, cudaStreamNonBlocking) != cudaSuccess ||
 	    cudaEventCreateWithFlags(&cx->ev_main, cudaEventDisableTiming) != cudaSuccess || cudaEventCreateWithFlags(&cx->ev_tail, cudaEventDisableTiming) != cudaSuccess) {
 		bt_context_free(cx); return fail("bt_context_create: CUDA resource allocation failed");
 	}
@@ -706,8 +706,9 @@ static bool main_kernel_is_queue() {
 #define BT_HEAVY_BLOCKS_PER_SM 8   /* heavy pass: 32-thread blocks, so finished warps free their slots */
 
 /* The best-first path (bt_best.cuh).  Three passes with growing per-read arenas: every read with 64 KB on the caller's
- * stream (148 x 8 x 64 lanes); the reads that exhausted it with 1 MB (148 x 32 lanes), then with 16 MB (148 lanes), on the
- * side stream.  About 5 + 5 + 2.5 GB per context for full batches. */
+ * stream (148 x 8 x 64 lanes); the reads that exhausted it with 1 MB (148 x 32 lanes), then 16 MB (148 lanes), then 256 MB
+ * (8 lanes; the reference's own ceiling is 64 MB of chunked pools per thread) on the side stream.
+ * About 5 + 5 + 2.5 + 2 GB per context for full batches. */
 static int enqueue_best(bt_context *cx, const bt_policy_t *pol, const bt_read_batch_t *in, bt_hit_batch_t *out, uint32_t maxlen, cudaStream_t st) {
 	bt_index_t *ix = cx->ix;
 	if (pol->paired && (in->nreads & 1)) return fail("bt_align (paired-end): nreads must be even (mates are adjacent reads)");
@@ -715,10 +716,11 @@ static int enqueue_best(bt_context *cx, const bt_policy_t *pol, const bt_read_ba
 	if (nwork == 0) return 0;
 	if (pol->paired && ensure_ref(ix)) return 1;
 	static const uint32_t kw0 = env_u32("BT_BEST_ARENA_KW", 16);
-	const uint32_t tierWords[3] = { kw0 << 10, 256u << 10, 4096u << 10 };
-	const uint32_t tierLanes[3] = { BF_THREADS, 32, 1 };                 /* active threads per block */
-	uint32_t tierBlocks[3] = { (uint32_t)ix->sms * 8, (uint32_t)ix->sms, (uint32_t)ix->sms };
-	for (int k = 0; k < 3; k++) {
+	enum { NT = 4 };
+	const uint32_t tierWords[NT] = { kw0 << 10, 256u << 10, 4096u << 10, 65536u << 10 };   /* 64 KB, 1 MB, 16 MB, 256 MB per read */
+	const uint32_t tierLanes[NT] = { BF_THREADS, 32, 1, 1 };                                /* active threads per block */
+	uint32_t tierBlocks[NT] = { (uint32_t)ix->sms * 8, (uint32_t)ix->sms, (uint32_t)ix->sms, 8 };
+	for (int k = 0; k < NT; k++) {
 		const uint32_t need_blocks = (nwork + tierLanes[k] - 1) / tierLanes[k];   /* small batches do not need a full machine of arenas */
 		if (tierBlocks[k] > need_blocks) tierBlocks[k] = need_blocks;
 		const size_t need = (size_t)tierBlocks[k] * tierLanes[k] * tierWords[k];
@@ -747,19 +749,17 @@ static int enqueue_best(bt_context *cx, const bt_policy_t *pol, const bt_read_ba
 	const uint32_t cblocks = (nwork + 255) / 256;
 	CUDA_TRY(cudaStreamWaitEvent(st, cx->ev_tail, 0));
 	bt_ctl_set_kernel<<<1, 1, 0, st>>>(cx->ctl, nwork);
-	bt_ctl_set_kernel<<<1, 1, 0, st>>>(cx->ctl + 1, 0);
-	bt_ctl_set_kernel<<<1, 1, 0, st>>>(cx->ctl + 2, 0);
-	P.arena = cx->arena[0]; P.arenaWords = tierWords[0];
+	for (int k = 1; k < NT; k++) bt_ctl_set_kernel<<<1, 1, 0, st>>>(cx->ctl + k, 0);
 	auto kernel = pol->paired ? bt_best_kernel<true> : bt_best_kernel<false>;
-	kernel<<<tierBlocks[0], BF_THREADS, 0, st>>>(P, cx->ctl, tierLanes[0]);
-	bt_collect_kernel<<<cblocks, 256, 0, st>>>(out->flags, in->sel, nwork, nullptr, BT_FLAG_STACK_OVF, cx->heavy_sel, cx->ctl + 1);
-	CUDA_TRY(cudaEventRecord(cx->ev_main, st));
-	CUDA_TRY(cudaStreamWaitEvent(cx->side, cx->ev_main, 0));
-	P.sel = cx->heavy_sel; P.arena = cx->arena[1]; P.arenaWords = tierWords[1];
-	kernel<<<tierBlocks[1], BF_THREADS, 0, cx->side>>>(P, cx->ctl + 1, tierLanes[1]);
-	bt_collect_kernel<<<cblocks, 256, 0, cx->side>>>(out->flags, cx->heavy_sel, nwork, cx->ctl + 1, BT_FLAG_STACK_OVF, cx->retry_sel, cx->ctl + 2);
-	P.sel = cx->retry_sel; P.arena = cx->arena[2]; P.arenaWords = tierWords[2];
-	kernel<<<tierBlocks[2], BF_THREADS, 0, cx->side>>>(P, cx->ctl + 2, tierLanes[2]);
+	uint32_t *sels[2] = { cx->heavy_sel, cx->retry_sel };                 /* tier k reads the list tier k-1 wrote; two buffers alternate */
+	for (int k = 0; k < NT; k++) {
+		cudaStream_t s = k == 0 ? st : cx->side;
+		const uint32_t *sel_in = k == 0 ? in->sel : sels[(k - 1) & 1];
+		P.sel = sel_in; P.arena = cx->arena[k]; P.arenaWords = tierWords[k];
+		kernel<<<tierBlocks[k], BF_THREADS, 0, s>>>(P, cx->ctl + k, tierLanes[k]);
+		if (k + 1 < NT) bt_collect_kernel<<<cblocks, 256, 0, s>>>(out->flags, sel_in, nwork, k == 0 ? nullptr : cx->ctl + k, BT_FLAG_STACK_OVF, sels[k & 1], cx->ctl + k + 1);
+		if (k == 0) { CUDA_TRY(cudaEventRecord(cx->ev_main, st)); CUDA_TRY(cudaStreamWaitEvent(cx->side, cx->ev_main, 0)); }
+	}
 	CUDA_TRY(cudaGetLastError());
 	return 0;
 }

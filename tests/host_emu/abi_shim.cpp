@@ -8,6 +8,7 @@
  * explicit LD_LIBRARY_PATH set by tests/test_cli_parity.py; the product never loads it.
  */
 #define BT_HOST_EMU 1
+#include <stdio.h>
 #include <stdlib.h>
 #include <string.h>
 #include <string>
@@ -124,6 +125,7 @@ static int run_best(bt_index *ix, const bt_policy_t *pol, const bt_read_batch_t 
 			if (pol->paired) { if (P.prog.pairedV2) bf_align_pair_v2(X); else bf_align_pair(X); } else bf_align_read(X);
 		}
 		if (X.flags & (BT_FLAG_STACK_OVF | BT_FLAG_FRAME_OVF)) X.found = 0;
+		if (getenv("BT_EMU_ARENA_STATS")) fprintf(stderr, "arena %u %u\n", r, X.amax);
 		out->found[r] = X.found; out->flags[r] = X.flags;
 	}
 	return 0;
