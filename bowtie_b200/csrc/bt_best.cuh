@@ -17,7 +17,7 @@
  * sits at the top of the queue (extend(), curtail() without a cost change), so the pop order of the reference
  * depends on the heap's physical layout, not only on the comparison.
  * Range states are stored only for positions where an edit can ever be considered (i >= depth0 - rdepth,
- * range_source.h:671-672,890-891), in blocks of 8 that a branch acquires as it extends (most branches die young).  Arena exhaustion sets BT_FLAG_STACK_OVF and the read is re-run by a pass
+ * range_source.h:671-672,890-891), in chained blocks of 4 that a branch acquires as it extends (most branches die young).  Arena exhaustion sets BT_FLAG_STACK_OVF and the read is re-run by a pass
  * with a larger arena (the reference's own limit is --chunkmbs; it skips the read instead).
  *
  * Compiles for the device and, for tests/host_emu only, for the host (BT_HOST_EMU).
@@ -61,12 +61,15 @@ struct BtDevRef {
 struct BfRS { uint32_t tops[4], bots[4], eq; };       /* RangeState: eq bits 0-3 = mm{A,C,G,T} eliminated, 8-14 = quallo, 31 = eliminated_ */
 #define BF_RS_WORDS 9
 #define BF_RS_ELIM 0x80000000u
-#define BF_RS_BLK 8              /* range states are allocated in blocks of 8 positions, when a branch first reaches them */
+#define BF_RS_BLK 4              /* range states live in chained blocks of 4 positions (word 0 = next block), carved when a branch first reaches them */
+#define BF_RS_BLK_WORDS (1 + BF_RS_BLK * BF_RS_WORDS)
 
 struct BfBranch {
-	uint32_t id, top, bot, ltop, lbot, ranges, edits;      /* ranges: table of block refs (0 = not yet allocated); edits: nedits arena words */
+	uint32_t id, top, bot, ltop, lbot, ranges, edits;      /* ranges: first block of the chain (0 = none yet); edits: nedits arena words */
+	uint32_t tipBlk, curBlk;                               /* last block of the chain; the block of the latest access (scans are sequential) */
 	uint16_t depth0, depth1, depth2, depth3, rdepth, len, cost, ham, rangesSz, i0, delayedCost, nedits;
 	uint8_t curtailed, exhausted, delayedIncrease, lbotValid;
+	uint16_t nblk, curK;                                   /* blocks in the chain; index of curBlk */
 };
 #define BF_BRANCH_WORDS ((uint32_t)(sizeof(BfBranch) / 4))
 
@@ -218,18 +221,29 @@ BT_FN void bf_branch_prep(BfBranch &b) {                                 /* Bran
 	else if (b.bot > b.top) { b.ltop = b.top; b.lbotValid = 0; }
 }
 /* The reference reserves qlen - rdepth RangeStates per Branch (range_source.h:570-578); most branches die within a few
- * positions, so here a branch owns a table of block refs and a block of BF_RS_BLK zeroed states is carved on first touch. */
-BT_FN BfRS *bf_rs(BfCtx &X, const BfBranch &b, uint32_t i) {
-	const uint32_t idx = i - b.i0;
-	uint32_t blk = X.A[b.ranges + idx / BF_RS_BLK];
-	if (!blk) {
-		blk = bf_alloc_zero(X, BF_RS_BLK * BF_RS_WORDS);
-		if (!blk) { X.spare.eq = 0; return &X.spare; }
-		X.A[b.ranges + idx / BF_RS_BLK] = blk;
+ * positions, so here a branch owns a chain of blocks of BF_RS_BLK zeroed states and a block is carved on first touch
+ * (positions are first touched in increasing order: init marks [i0, len), extension then reaches one position at a time). */
+BT_NOINLINE BfRS *bf_rs(BfCtx &X, BfBranch &b, uint32_t i) {
+	const uint32_t idx = i - b.i0, k = idx / BF_RS_BLK;
+	uint32_t blk;
+	if (b.curBlk && k == b.curK) blk = b.curBlk;
+	else if (b.curBlk && k == (uint32_t)b.curK + 1 && X.A[b.curBlk]) blk = X.A[b.curBlk];
+	else if (k + 1 == b.nblk) blk = b.tipBlk;
+	else if (k < b.nblk) { blk = b.ranges; for (uint32_t j = 0; j < k; j++) blk = X.A[blk]; }
+	else {
+		blk = b.tipBlk;
+		while (b.nblk <= k) {                                             /* normally one step */
+			const uint32_t nb = bf_alloc_zero(X, BF_RS_BLK_WORDS);
+			if (!nb) { X.spare.eq = 0; return &X.spare; }
+			if (b.nblk) X.A[b.tipBlk] = nb; else b.ranges = nb;
+			b.tipBlk = nb; b.nblk++;
+			blk = nb;
+		}
 	}
-	return BF_AT(BfRS, X, blk + (idx % BF_RS_BLK) * BF_RS_WORDS);
+	b.curBlk = blk; b.curK = (uint16_t)k;
+	return BF_AT(BfRS, X, blk + 1 + (idx % BF_RS_BLK) * BF_RS_WORDS);
 }
-BT_FN bool bf_eliminated(BfCtx &X, const BfBranch &b, uint32_t i) {      /* Branch::eliminated, range_source.h:619-634 */
+BT_FN bool bf_eliminated(BfCtx &X, BfBranch &b, uint32_t i) {      /* Branch::eliminated, range_source.h:619-634 */
 	if (i <= b.len && i < b.rangesSz) return (bf_rs(X, b, i)->eq & BF_RS_ELIM) != 0;
 	return true;
 }
@@ -258,18 +272,14 @@ BT_NOINLINE uint32_t bf_branch_new(BfCtx &X, BfSrc &s, uint32_t qlen, uint32_t d
 	b.rangesSz = (uint16_t)(qlen - rdepth);
 	const uint32_t i0 = d0 > rdepth ? d0 - rdepth : 0;
 	b.i0 = (uint16_t)(i0 < b.rangesSz ? i0 : b.rangesSz);
-	b.ranges = 0;
-	if (b.rangesSz > b.i0) {
-		b.ranges = bf_alloc_zero(X, ((uint32_t)(b.rangesSz - b.i0) + BF_RS_BLK - 1) / BF_RS_BLK);
-		if (!b.ranges) return 0;
-	}
+	b.ranges = 0; b.tipBlk = 0; b.curBlk = 0; b.nblk = 0; b.curK = 0;
 	b.curtailed = 0; b.exhausted = 0; b.delayedIncrease = 0;
 	for (uint32_t i = b.i0; i < len && i < b.rangesSz; i++) bf_rs(X, b, i)->eq |= BF_RS_ELIM;
 	return ref;
 }
 BT_FN void bf_branch_free(BfCtx &X, BfSrc &s, uint32_t ref) {            /* Branch::free: only the newest slot is really reclaimed */
 	BfBranch &b = *BF_BR(X, ref);
-	if (b.ranges) bf_free_top(X, b.ranges, ((uint32_t)(b.rangesSz - b.i0) + BF_RS_BLK - 1) / BF_RS_BLK);
+	if (b.nblk == 1) bf_free_top(X, b.tipBlk, BF_RS_BLK_WORDS);           /* the common early death: struct, edits and one block sit on top */
 	if (b.id == s.bcur && s.bcur > 0) s.bcur--;
 	if (b.edits) bf_free_top(X, b.edits, b.nedits);
 	bf_free_top(X, ref, BF_BRANCH_WORDS);

@@ -717,7 +717,9 @@ static int enqueue_best(bt_context *cx, const bt_policy_t *pol, const bt_read_ba
 	if (pol->paired && ensure_ref(ix)) return 1;
 	static const uint32_t kw0 = env_u32("BT_BEST_ARENA_KW", 16);
 	enum { NT = 4 };
-	const uint32_t tierWords[NT] = { kw0 << 10, 256u << 10, 4096u << 10, 65536u << 10 };   /* 64 KB, 1 MB, 16 MB, 256 MB per read */
+	/* 64 KB (pairs: 96 KB), 1 MB, 16 MB, 256 MB per read.  Measured high-water marks on the bench workloads (host emulation,
+	 * profiles/README.md): -n 2 --best p99 35 KB, p99.9 282 KB; paired -n 3 p95 60 KB, p99 113 KB, p99.9 326 KB */
+	const uint32_t tierWords[NT] = { (pol->paired ? kw0 + kw0 / 2 : kw0) << 10, 256u << 10, 4096u << 10, 65536u << 10 };
 	const uint32_t tierLanes[NT] = { BF_THREADS, 32, 1, 1 };                                /* active threads per block */
 	uint32_t tierBlocks[NT] = { (uint32_t)ix->sms * 8, (uint32_t)ix->sms, (uint32_t)ix->sms, 8 };
 	for (int k = 0; k < NT; k++) {
