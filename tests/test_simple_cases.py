@@ -1,5 +1,5 @@
 """Known-answer cases transcribed from the reference's own black-box suite (scripts/test/simple_tests.pl:119-900;
-the unpaired, non --best cases): tiny literal references + reads + the expected {offset => count} per read.
+the unpaired cases and the -1/-2 paired cases): tiny literal references + reads + the expected {offset => count} per read.
 Each case is run through (1) the unmodified reference binary, whose output must contain exactly the expected
 offsets (this pins the transcription), and (2) our bowtie-compatible driver, whose hit file and exit status
 must equal the reference's byte for byte (default and SAM output).  On the CPU test box the driver runs against the
@@ -62,6 +62,29 @@ for mode in (["-v", "0"], ["-n", "0"]):
 for mode in (["-v", "2"], ["-n", "2"]):
     case("Checking edits 1 " + " ".join(mode), "TTGCCCGT", "c", "TTGTTCGT", mode, hits=[{0: 1}])
     case("Checking edits 2 " + " ".join(mode), "TTGTTCGT", "c", "ACGGGCAA", mode, hits=[{0: 1}])
+
+# paired-end cases (simple_tests.pl:187-234, 319-367, 452-497, 565-610): (name, ref, kind, mate-1 text, mate-2 text, args, expected "lo,hi" per pair)
+REFP = "AGCATCGATCAAAAACTGA"
+P = []
+def pcase(name, kind, t1, t2, args=(), pairhits=()):
+    P.append((name, REFP, kind, t1, t2, list(args), list(pairhits)))
+
+pcase("Cline paired 1", "c", "AGCATCGATC:IIIIIIIIII,TCAGTTTTTGA", "TCAGTTTTTGA,AGCATCGATC:IIIIIIIIII", pairhits=[(0, 8), (0, 8)])
+pcase("Cline paired 2", "c", "AGCATCGATC:IIIIIIIIII,TCAGTTTTTGA:IIIIIIIIIII", "TCAGTTTTTGA:IIIIIIIIIII,AGCATCGATC:IIIIIIIIII", ["-s", "1"], [(0, 8)])
+pcase("Cline paired 3", "c", "AGCATCGATC:IIIIIIIIII,TCAGTTTTTGA:IIIIIIIIIII", "TCAGTTTTTGA:IIIIIIIIIII,AGCATCGATC:IIIIIIIIII", ["-u", "1"], [(0, 8)])
+pcase("Cline paired 4", "c", "AGCATCG:IIIIIII", "GATCAAAAACTGA:IIIIIIIIIIIII", ["-3", "7"], [])
+pcase("Fastq paired 1", "q", "@r0\nAGCATCGATC\r\n+\nIIIIIIIIII\n@r1\nTCAGTTTTTGA\r\n+\nIIIIIIIIIII\n", "@r0\nTCAGTTTTTGA\n+\nIIIIIIIIIII\n@r1\nAGCATCGATC\r\n+\nIIIIIIIIII", pairhits=[(0, 8), (0, 8)])
+pcase("Fastq paired 2", "q", "@r0\nAGCATCGATC\r\n+\nIIIIIIIIII\n@r1\nTCAGTTTTTGA\n+\nIIIIIIIIIII\n", "@r0\nTCAGTTTTTGA\n+\nIIIIIIIIIII\n@r1\nAGCATCGATC\r\n+\nIIIIIIIIII", ["-s", "1"], [(0, 8)])
+pcase("Fastq paired 3", "q", "@r0\nAGCATCGATC\r\n+\nIIIIIIIIII\n@r1\nTCAGTTTTTGA\r\n+\nIIIIIIIIIII\n", "@r0\nTCAGTTTTTGA\n+\nIIIIIIIIIII\n@r1\nAGCATCGATC\r\n+\nIIIIIIIIII", ["-u", "1"], [(0, 8)])
+pcase("Fastq paired 4", "q", "@r0\nAGCATCG\n+\nIIIIIII\n", "@r0\nGATCAAAAACTGA\n+\nIIIIIIIIIIIII\n", ["-3", "7"], [])
+pcase("Fasta paired 1", "f", "\n\n\r\n>r0\nAGCATCGATC\r\n\n\n>r1\nTCAGTTTTTGA\r\n", "\n\n\r\n>r0\nTCAGTTTTTGA\n\n\n\r\n>r1\nAGCATCGATC", pairhits=[(0, 8), (0, 8)])
+pcase("Fasta paired 2", "f", ">r0\nAGCATCGATC\r\n\n\n>r1\nTCAGTTTTTGA\n", "\n\n\r\n>r0\nTCAGTTTTTGA\n\n\n\r\n>r1\nAGCATCGATC", ["-s", "1"], [(0, 8)])
+pcase("Fasta paired 3", "f", "\n\n\r\n>r0\nAGCATCGATC\r\n\n\n>r1\nTCAGTTTTTGA\r\n", "\n\n\r\n>r0\nTCAGTTTTTGA\n\n\n\r\n>r1\nAGCATCGATC", ["-u", "1"], [(0, 8)])
+pcase("Fasta paired 4", "f", ">\nAGCATCG\n", ">\nGATCAAAAACTGA\n", ["-3", "7"], [])
+pcase("Raw paired 1", "r", "\n\n\r\nAGCATCGATC\r\n\n\nTCAGTTTTTGA\r\n", "\n\n\r\nTCAGTTTTTGA\n\n\n\r\nAGCATCGATC", pairhits=[(0, 8), (0, 8)])
+pcase("Raw paired 2", "r", "AGCATCGATC\r\n\n\nTCAGTTTTTGA\n", "\n\n\r\nTCAGTTTTTGA\n\n\n\r\nAGCATCGATC", ["-s", "1"], [(0, 8)])
+pcase("Raw paired 3", "r", "\n\n\r\nAGCATCGATC\r\n\n\nTCAGTTTTTGA\r\n", "\n\n\r\nTCAGTTTTTGA\n\n\n\r\nAGCATCGATC", ["-u", "1"], [(0, 8)])
+pcase("Raw paired 4", "r", "\nAGCATCG\n", "\nGATCAAAAACTGA\n", ["-3", "7"], [])
 
 
 @pytest.fixture(scope="module")
@@ -135,6 +158,54 @@ def check(i, sam, env, tmp_path_factory):
 @pytest.mark.parametrize("sam", [False, True], ids=["default", "sam"])
 def test_simple_case_host_logic(i, sam, env_cpu, tmp_path_factory):
     check(i, sam, env_cpu, tmp_path_factory)
+
+
+def run_pair(exe, base, kind, t1, t2, args, sam, out, env=None, ref=False):
+    flags = list(args) + (["-S", "--sam-nohead"] if sam else [])
+    if kind == "c":
+        src = ["-c", "-1", t1, "-2", t2]
+    else:
+        f1, f2 = out.parent / f"m1.{kind}", out.parent / f"m2.{kind}"
+        f1.write_bytes(t1.encode()); f2.write_bytes(t2.encode())
+        src = [{"q": "-q", "f": "-f", "r": "-r"}[kind], "-1", str(f1), "-2", str(f2)]
+    if out.exists():
+        out.unlink()
+    p = subprocess.run([str(exe), *flags] + (["-p", "1"] if ref else []) + ["-x", str(base), *src, str(out)], capture_output=True, text=True, env=env)
+    body = out.read_bytes() if out.exists() else b""
+    summ = "\n".join(l for l in p.stderr.splitlines() if l.startswith("#") or l.startswith("Reported") or l.startswith("No alignments"))
+    return p.returncode, body, summ
+
+
+def check_pair(i, sam, env, tmp_path_factory):
+    name, ref, kind, t1, t2, args, pairhits = P[i]
+    root = tmp_path_factory.getbasetemp()
+    base = index_for(ref, root)
+    d = root / f"pcase{i}_{int(sam)}"
+    d.mkdir(exist_ok=True)
+    rc_r, body_r, sum_r = run_pair(REF_ALIGN, base, kind, t1, t2, args, sam, d / "ref.out", ref=True)
+    rc_o, body_o, sum_o = run_pair(CLI, base, kind, t1, t2, args, sam, d / "our.out", env=env)
+    assert rc_r == 0 and rc_o == 0, (name, rc_r, rc_o)
+    if not sam:
+        lines = body_r.decode().splitlines()
+        got = [tuple(sorted((int(lines[k].split("\t")[3]), int(lines[k + 1].split("\t")[3])))) for k in range(0, len(lines), 2)]
+        assert sorted(got) == sorted(pairhits), (name, got, pairhits)      # pins the transcription
+    assert body_o == body_r, name
+    assert sum_o == sum_r, name
+
+
+@pytest.mark.parametrize("i", range(len(P)), ids=[c[0] for c in P])
+@pytest.mark.parametrize("sam", [False, True], ids=["default", "sam"])
+def test_simple_paired_case_host_logic(i, sam, env_cpu, tmp_path_factory):
+    check_pair(i, sam, env_cpu, tmp_path_factory)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("i", range(len(P)), ids=[c[0] for c in P])
+def test_simple_paired_case_gpu(i, tmp_path_factory):
+    ensure_oracle_built()
+    if not REF_ALIGN.exists() or not REF_BUILD.exists():
+        pytest.skip("reference binaries not available")
+    check_pair(i, False, {k: v for k, v in os.environ.items() if k != "LD_LIBRARY_PATH"}, tmp_path_factory)
 
 
 @pytest.mark.gpu
