@@ -34,7 +34,7 @@ struct Opts {
 	std::vector<std::string> queries;
 	int mismatches = 0, seedMms = 2, maqLike = 1, seedLen = 28, qualThresh = 70, maxBts = 125, maxBtsBest = 800;
 	bool best = false, strata = false, sampleMax = false, bestFlag = false;   /* bestFlag: --best itself (it alone selects the V2 paired aligner) */
-	std::vector<std::string> mates1, mates2;
+	std::vector<std::string> mates1, mates2, interleaved;
 	uint32_t minInsert = 0, maxInsert = 250, pairTries = 100; bool mate1fw = true, mate2fw = false;
 	bool noMaqRound = false, nofw = false, norc = false, allHits = false;
 	uint32_t khits = 1, mhits = 0xffffffffu;
@@ -61,7 +61,7 @@ enum {
 	ARG_PHRED33 = 256, ARG_PHRED64, ARG_SOLEXA, ARG_SOLEXA13, ARG_NOMAQROUND, ARG_NOFW, ARG_NORC, ARG_MAXBTS, ARG_BEST, ARG_STRATA,
 	ARG_QUIET, ARG_REFIDX, ARG_SUPPRESS, ARG_FULLREF, ARG_MAPQ, ARG_SAM_NOHEAD, ARG_SAM_NOSQ, ARG_SAM_RG, ARG_NO_UNAL, ARG_SEED,
 	ARG_COST, ARG_REORDER, ARG_WRAPPER, ARG_VERSION, ARG_IGNORED0, ARG_IGNORED1, ARG_DEVICE, ARG_BATCH, ARG_SAM_NO_QNAME_TRUNC,
-	ARG_LARGE_INDEX, ARG_PAIRED, ARG_FF, ARG_FR, ARG_RF, ARG_PAIRTRIES
+	ARG_LARGE_INDEX, ARG_PAIRED, ARG_INTERLEAVED, ARG_FF, ARG_FR, ARG_RF, ARG_PAIRTRIES
 };
 
 static const char *short_options = "fqrchu:v:s:at3:5:e:n:l:p:k:m:M:1:2:I:X:x:B:yS";
@@ -81,7 +81,7 @@ static struct option long_options[] = {
 	{"reorder", no_argument, 0, ARG_REORDER}, {"wrapper", required_argument, 0, ARG_WRAPPER}, {"version", no_argument, 0, ARG_VERSION},
 	{"chunkmbs", required_argument, 0, ARG_IGNORED1}, {"mm", no_argument, 0, ARG_IGNORED0}, {"shmem", no_argument, 0, ARG_IGNORED1}, {"help", no_argument, 0, 'h'},
 	{"device", required_argument, 0, ARG_DEVICE}, {"reads-per-batch", required_argument, 0, ARG_BATCH},
-	{"large-index", no_argument, 0, ARG_LARGE_INDEX}, {"12", required_argument, 0, ARG_PAIRED}, {"interleaved", required_argument, 0, ARG_PAIRED},
+	{"large-index", no_argument, 0, ARG_LARGE_INDEX}, {"12", required_argument, 0, ARG_PAIRED}, {"interleaved", required_argument, 0, ARG_INTERLEAVED},
 	{"ff", no_argument, 0, ARG_FF}, {"fr", no_argument, 0, ARG_FR}, {"rf", no_argument, 0, ARG_RF}, {"pairtries", required_argument, 0, ARG_PAIRTRIES},
 	{"minins", required_argument, 0, 'I'}, {"maxins", required_argument, 0, 'X'},
 	{0, 0, 0, 0}
@@ -137,7 +137,8 @@ static void parse_options(int argc, char **argv, Opts &o) {
 		case ARG_FR: o.mate1fw = true; o.mate2fw = false; break;
 		case ARG_RF: o.mate1fw = false; o.mate2fw = true; break;
 		case ARG_PAIRTRIES: o.pairTries = (uint32_t)parse_int(1, "--pairtries arg must be at least 1"); break;
-		case ARG_PAIRED: unsupported("--12 / --interleaved input"); break;
+		case ARG_INTERLEAVED: split(optarg, ',', o.interleaved); break;
+		case ARG_PAIRED: unsupported("--12 input (records that mix paired and unpaired reads)"); break;
 		case ARG_BEST: o.best = true; o.bestFlag = true; break;
 		case ARG_STRATA: o.strata = true; break;
 		case ARG_LARGE_INDEX: die("Error: large (64-bit) indexes are not supported"); break;
@@ -186,7 +187,7 @@ static void parse_options(int argc, char **argv, Opts &o) {
 		fprintf(stderr, "Error: %zu mate files/sequences were specified with -1, but %zu\nmate files/sequences were specified with -2.  The same number of mate files/\nsequences must be specified with -1 and -2.\n", o.mates1.size(), o.mates2.size());
 		exit(1);
 	}
-	if (o.mates1.empty()) {
+	if (o.mates1.empty() && o.interleaved.empty()) {
 		if (optind >= argc) die("No query or output file specified!");
 		split(argv[optind++], ',', o.queries);
 	} else o.best = o.bestFlag;                                                   /* pairs: only --best switches to PairedBWAlignerV2 (useV1 = false, ebwt_search.cpp:776); -M / -v 3 alone keep V1 */
@@ -511,7 +512,7 @@ int main(int argc, char **argv) {
 	pol.seed_len = op.seedLen; pol.qual_thresh = (uint32_t)op.qualThresh; pol.max_bts = (uint32_t)op.maxBts;
 	pol.khits = op.khits; pol.mhits = op.mhits; pol.all_hits = op.allHits; pol.nofw = op.nofw; pol.norc = op.norc; pol.maq_round = !op.noMaqRound;
 	pol.best = op.best; pol.strata = op.strata; pol.max_bts_best = (uint32_t)op.maxBtsBest; pol.sample_max = op.sampleMax;
-	const bool paired = !op.mates1.empty();
+	const bool paired = !op.mates1.empty() || !op.interleaved.empty(), interleaved = !op.interleaved.empty();
 	if (paired) {
 		/* aligner.h:975-990: the insert window shrinks by the bases trimmed from the outer ends of the fragment */
 		const int adj = (op.mate1fw ? op.trim5 : op.trim3) + (op.mate2fw ? op.trim3 : op.trim5);
@@ -537,7 +538,7 @@ int main(int argc, char **argv) {
 	if (!op.outfile.empty()) { out.fp = fopen(op.outfile.c_str(), "wb"); if (!out.fp) die("Error: could not open alignment output file " + op.outfile); }
 	if (op.sam && !op.samNoHead) sam_headers(out.buf, op, ix, info.n_refs);
 
-	Reader rd(op, paired ? op.mates1 : op.queries), rd2(op, op.mates2);
+	Reader rd(op, interleaved ? op.interleaved : paired ? op.mates1 : op.queries), rd2(op, op.mates2);
 	Batch bt[2];
 	const uint32_t nlim = op.allHits ? 0xffffffffu : op.khits;
 	for (auto &b : bt) {
@@ -559,7 +560,8 @@ int main(int argc, char **argv) {
 		while (!input_done && b.reads.size() < (size_t)op.batch * mult) {
 			if (rd.rdid >= op.qUpto) { input_done = true; break; }
 			if (!rd.next(rec)) { input_done = true; break; }
-			if (paired && !rd2.next(rec2)) die("Error, fewer reads in file specified with -2 than in file specified with -1");
+			if (interleaved) { if (!rd.next(rec2)) die("Error: odd number of reads in an --interleaved file"); rd.rdid--; }   /* a pair is one read id */
+			else if (paired && !rd2.next(rec2)) die("Error, fewer reads in file specified with -2 than in file specified with -1");
 			if (rd.rdid - 1 < op.skipReads) continue;                              /* -s: skipped reads are not counted */
 			for (int m = 0; m < (paired ? 2 : 1); m++) {
 				ReadRec &rr = m ? rec2 : rec;

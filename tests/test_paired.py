@@ -108,3 +108,19 @@ def test_paired_synthetic_gpu(flags, reads, setup, tmp_path):
 @pytest.mark.parametrize("flags", ["-n 3", "-v 2 -k 2"])
 def test_paired_gpu_10k_pairs(flags, setup, tmp_path):
     compare(flags, setup["big"], tmp_path, gpu_env())
+
+
+def test_interleaved_input(setup, tmp_path):
+    """--interleaved: one FASTQ file with alternating mates (pat.cpp) must give what -1/-2 give, and what the reference gives."""
+    base, m1, m2 = setup["ecoli"]
+    inter = tmp_path / "inter.fq"
+    a, b = Path(m1).read_text().splitlines(), Path(m2).read_text().splitlines()
+    inter.write_text("".join("\n".join(a[4 * i:4 * i + 4]) + "\n" + "\n".join(b[4 * i:4 * i + 4]) + "\n" for i in range(len(a) // 4)))
+    for flags in (["-n", "2"], ["-v", "2", "-k", "2", "-S"], ["-n", "2", "-s", "10", "-u", "300"]):
+        outs = []
+        for exe, env, extra in ((REF_ALIGN, None, ["-p", "1"]), (CLI, shim_env(), [])):
+            out = tmp_path / f"{Path(exe).name}.out"
+            p = subprocess.run([str(exe), *flags, *extra, "-x", str(base), "--interleaved", str(inter), str(out)], capture_output=True, text=True, env=env)
+            assert p.returncode == 0, p.stderr
+            outs.append(b"".join(l for l in out.read_bytes().splitlines(keepends=True) if not l.startswith(b"@PG")))
+        assert outs[0] == outs[1] and len(outs[0]) > 0
