@@ -108,6 +108,7 @@ static int run_best(bt_index *ix, const bt_policy_t *pol, const bt_read_batch_t 
 	static std::vector<uint32_t> arena; arena.resize((size_t)16 << 20);
 	const char *env = getenv("BT_EMU_ARENA_WORDS");
 	const uint32_t words = env ? (uint32_t)atol(env) : (uint32_t)arena.size();
+	const char *pz = getenv("BT_EMU_ARENA_POISON"); const bool poison = pz != NULL; const size_t poison_words = pz ? (size_t)atol(pz) : 0;
 	const uint32_t nwork = in->sel ? in->nsel : (pol->paired ? in->nreads / 2 : in->nreads);
 	for (uint32_t w = 0; w < nwork; w++) {
 		const uint32_t r = in->sel ? in->sel[w] : w;
@@ -119,6 +120,7 @@ static int run_best(bt_index *ix, const bt_policy_t *pol, const bt_read_batch_t 
 			X.seqM[m] = in->seq + in->offs[rd]; X.qualM[m] = in->qual + in->offs[rd];
 		}
 		X.A = arena.data(); X.acap = words; X.atop = 1;
+		if (poison) memset(arena.data(), 0xA5, (size_t)(poison_words < arena.size() ? poison_words : arena.size()) * 4);   /* the GPU arenas are never zeroed either */
 		if (pol->paired) { if (P.prog.pairedV2) bf_align_pair_v2(X); else bf_align_pair(X); } else bf_align_read(X);
 		if ((X.flags & BT_FLAG_STACK_OVF) && words < arena.size()) {      /* what the larger-arena passes of the product do */
 			memset(&X.top, 0, sizeof X.top); X.flags = 0; X.acap = (uint32_t)arena.size(); X.atop = 1;
