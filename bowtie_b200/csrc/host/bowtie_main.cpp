@@ -34,7 +34,8 @@ struct Opts {
 	std::vector<std::string> queries;
 	int mismatches = 0, seedMms = 2, maqLike = 1, seedLen = 28, qualThresh = 70, maxBts = 125, maxBtsBest = 800;
 	bool best = false, strata = false, sampleMax = false, bestFlag = false;   /* bestFlag: --best itself (it alone selects the V2 paired aligner) */
-	std::vector<std::string> mates1, mates2, interleaved;
+	std::vector<std::string> mates1, mates2, interleaved, tabbed;
+	bool bestPaired = false;   /* the pairs' --best: PairedBWAlignerV2 */
 	uint32_t minInsert = 0, maxInsert = 250, pairTries = 100; bool mate1fw = true, mate2fw = false;
 	bool noMaqRound = false, nofw = false, norc = false, allHits = false;
 	uint32_t khits = 1, mhits = 0xffffffffu;
@@ -138,7 +139,7 @@ static void parse_options(int argc, char **argv, Opts &o) {
 		case ARG_RF: o.mate1fw = false; o.mate2fw = true; break;
 		case ARG_PAIRTRIES: o.pairTries = (uint32_t)parse_int(1, "--pairtries arg must be at least 1"); break;
 		case ARG_INTERLEAVED: split(optarg, ',', o.interleaved); break;
-		case ARG_PAIRED: unsupported("--12 input (records that mix paired and unpaired reads)"); break;
+		case ARG_PAIRED: split(optarg, ',', o.tabbed); break;                       /* --12: one record per line, unpaired (3 fields) or paired (5) */
 		case ARG_BEST: o.best = true; o.bestFlag = true; break;
 		case ARG_STRATA: o.strata = true; break;
 		case ARG_LARGE_INDEX: die("Error: large (64-bit) indexes are not supported"); break;
@@ -187,10 +188,11 @@ static void parse_options(int argc, char **argv, Opts &o) {
 		fprintf(stderr, "Error: %zu mate files/sequences were specified with -1, but %zu\nmate files/sequences were specified with -2.  The same number of mate files/\nsequences must be specified with -1 and -2.\n", o.mates1.size(), o.mates2.size());
 		exit(1);
 	}
-	if (o.mates1.empty() && o.interleaved.empty()) {
+	o.bestPaired = o.bestFlag;                                                    /* pairs: only --best switches to PairedBWAlignerV2 (useV1 = false, ebwt_search.cpp:776); -M / -v 3 alone keep V1 */
+	if (o.mates1.empty() && o.interleaved.empty() && o.tabbed.empty()) {
 		if (optind >= argc) die("No query or output file specified!");
 		split(argv[optind++], ',', o.queries);
-	} else o.best = o.bestFlag;                                                   /* pairs: only --best switches to PairedBWAlignerV2 (useV1 = false, ebwt_search.cpp:776); -M / -v 3 alone keep V1 */
+	}
 	if (optind < argc) o.outfile = argv[optind++];
 	if (optind < argc) die(std::string("Extra parameter(s) specified: ") + argv[optind]);
 	if (o.sam) std::fill(o.suppress.begin(), o.suppress.end(), false);
@@ -272,6 +274,36 @@ struct Reader {
 		trimmed5 = nchar - (int)r.seq.size();
 		trimmed3 = std::min<int>(o.trim3, (int)r.seq.size());
 		r.seq.resize(r.seq.size() - (size_t)trimmed3);
+	}
+	/* TabbedPatternSource (pat.cpp:980-1124), --12: name <tab> seq <tab> quals [<tab> seq2 <tab> quals2] per line */
+	bool next_tab(ReadRec &a, ReadRec &b, bool &isPair) {
+		for (;;) {
+			if (!f && !open_next()) return false;
+			std::string line;
+			if (!getline_(line)) { gzclose(f); f = NULL; continue; }
+			while (!line.empty() && line.back() == '\r') line.pop_back();
+			if (line.empty()) continue;
+			std::vector<std::string> fld; size_t p0 = 0;
+			for (;;) { size_t t = line.find('\t', p0); if (t == std::string::npos) { fld.push_back(line.substr(p0)); break; } fld.push_back(line.substr(p0, t - p0)); p0 = t + 1; }
+			rdid++;
+			if (fld.size() < 3) continue;                                    /* "record ended prematurely": the read is skipped */
+			isPair = fld.size() >= 5;
+			for (int e = 0; e < (isPair ? 2 : 1); e++) {
+				ReadRec &r = e ? b : a;
+				r.name = fld[0];
+				const std::string &sq = fld[1 + 2 * e], &ql = fld[2 + 2 * e];
+				int nchar = 0; r.seq.clear();
+				for (char ch : sq) if (isalpha((unsigned char)ch)) { if (nchar++ >= o.trim5) r.seq.push_back((char)asc2dna[(unsigned char)ch]); }
+				const size_t t3 = std::min<size_t>((size_t)o.trim3, r.seq.size());
+				r.seq.resize(r.seq.size() - t3);
+				r.qual.clear(); int nqual = 0;
+				for (char ch : ql) { char pc = to_phred33((unsigned char)ch, r.name); if (++nqual > o.trim5) r.qual.push_back(pc); }
+				if (nchar > nqual) die("Error: Read " + r.name + " has more read characters than quality values.");
+				if (nqual > nchar) die("Error: Read " + r.name + " has more quality values than read characters.");
+				r.qual.resize(r.qual.size() - std::min<size_t>((size_t)o.trim3, r.qual.size()));
+			}
+			return true;
+		}
 	}
 	/* Returns false when all input is consumed. */
 	bool next(ReadRec &r) {
@@ -492,6 +524,7 @@ static void sam_headers(std::string &o, const Opts &op, const bt_index_t *ix, ui
 /* batches                                                                                         */
 /* ---------------------------------------------------------------------------------------------- */
 struct Batch {
+	bool paired = false;           /* every unit of the batch is a pair (mates adjacent) */
 	std::vector<ReadRec> reads;
 	std::vector<uint8_t> seq, qual; std::vector<uint64_t> offs; std::vector<uint32_t> seeds;
 	std::vector<uint32_t> found, flags, hits;
@@ -512,15 +545,16 @@ int main(int argc, char **argv) {
 	pol.seed_len = op.seedLen; pol.qual_thresh = (uint32_t)op.qualThresh; pol.max_bts = (uint32_t)op.maxBts;
 	pol.khits = op.khits; pol.mhits = op.mhits; pol.all_hits = op.allHits; pol.nofw = op.nofw; pol.norc = op.norc; pol.maq_round = !op.noMaqRound;
 	pol.best = op.best; pol.strata = op.strata; pol.max_bts_best = (uint32_t)op.maxBtsBest; pol.sample_max = op.sampleMax;
-	const bool paired = !op.mates1.empty() || !op.interleaved.empty(), interleaved = !op.interleaved.empty();
-	if (paired) {
+	const bool pairedInput = !op.mates1.empty() || !op.interleaved.empty(), interleaved = !op.interleaved.empty(), tabbed = !op.tabbed.empty();
+	bt_policy_t polU = pol, polP = pol;                                           /* unpaired reads / pairs (a --12 file can hold both) */
+	{
 		/* aligner.h:975-990: the insert window shrinks by the bases trimmed from the outer ends of the fragment */
 		const int adj = (op.mate1fw ? op.trim5 : op.trim3) + (op.mate2fw ? op.trim3 : op.trim5);
-		pol.paired = 1; pol.mate1fw = op.mate1fw; pol.mate2fw = op.mate2fw; pol.pair_tries = op.pairTries;
-		pol.min_ins = (uint32_t)std::max(0, (int)op.minInsert - adj); pol.max_ins = (uint32_t)std::max(0, (int)op.maxInsert - adj);
+		polP.paired = 1; polP.mate1fw = op.mate1fw; polP.mate2fw = op.mate2fw; polP.pair_tries = op.pairTries; polP.best = op.bestPaired;
+		polP.min_ins = (uint32_t)std::max(0, (int)op.minInsert - adj); polP.max_ins = (uint32_t)std::max(0, (int)op.maxInsert - adj);
 	}
+	if (tabbed) polU.best = 1;                                                    /* any paired input makes the whole run stateful (ebwt_search.cpp:3001-3002): single reads go through UnpairedAlignerV2 */
 	const bool needMirror = op.maqLike || op.mismatches > 0;
-	const uint32_t mult = paired ? 2u : 1u;                                       /* HitSinkPerThreadFactory::createMult */
 
 	/* adjustEbwtBase (ebwt.cpp:36-85): as given, else under $BOWTIE_INDEXES */
 	std::string base = op.ebwtFile;
@@ -538,16 +572,15 @@ int main(int argc, char **argv) {
 	if (!op.outfile.empty()) { out.fp = fopen(op.outfile.c_str(), "wb"); if (!out.fp) die("Error: could not open alignment output file " + op.outfile); }
 	if (op.sam && !op.samNoHead) sam_headers(out.buf, op, ix, info.n_refs);
 
-	Reader rd(op, interleaved ? op.interleaved : paired ? op.mates1 : op.queries), rd2(op, op.mates2);
+	Reader rd(op, tabbed ? op.tabbed : interleaved ? op.interleaved : pairedInput ? op.mates1 : op.queries), rd2(op, op.mates2);
 	Batch bt[2];
 	const uint32_t nlim = op.allHits ? 0xffffffffu : op.khits;
 	for (auto &b : bt) {
 		if (bt_context_create(ix, &b.cx)) die(std::string("Error: ") + bt_last_error());
-		b.slots = op.allHits ? 8 : op.khits * mult;
-		if (op.sampleMax && op.mhits != 0xffffffffu) b.slots = std::max(b.slots, op.mhits * mult);   /* -M keeps every hit up to the ceiling */
 		b.mm_cap = op.maqLike ? 10 : (uint32_t)std::max(1, op.mismatches);
 	}
-	uint64_t numAligned = 0, numUnaligned = 0, numMaxed = 0, numReported = 0;
+	uint64_t numAligned = 0, numUnaligned = 0, numMaxed = 0, numReported = 0, numReportedPaired = 0;
+	ReadRec lrec, lrec2; bool haveLook = false, lookPair = false;                 /* --12: one record of lookahead (a batch is all pairs or all single reads) */
 	bool input_done = false;
 	ReadRec rec, rec2;
 	auto fix_mate_name = [](std::string &name, int i) {                           /* Read::fixMateName (read.h:141-165) */
@@ -557,11 +590,23 @@ int main(int argc, char **argv) {
 
 	auto fill = [&](Batch &b) {
 		b.reads.clear(); b.seq.clear(); b.qual.clear(); b.offs.assign(1, 0); b.seeds.clear();
-		while (!input_done && b.reads.size() < (size_t)op.batch * mult) {
-			if (rd.rdid >= op.qUpto) { input_done = true; break; }
-			if (!rd.next(rec)) { input_done = true; break; }
-			if (interleaved) { if (!rd.next(rec2)) die("Error: odd number of reads in an --interleaved file"); rd.rdid--; }   /* a pair is one read id */
-			else if (paired && !rd2.next(rec2)) die("Error, fewer reads in file specified with -2 than in file specified with -1");
+		b.paired = pairedInput;
+		while (!input_done && b.reads.size() < (size_t)op.batch * (b.paired ? 2 : 1)) {
+			bool paired = pairedInput;
+			if (tabbed) {
+				if (!haveLook) {
+					if (rd.rdid >= op.qUpto) { input_done = true; break; }
+					if (!rd.next_tab(lrec, lrec2, lookPair)) { input_done = true; break; }
+					haveLook = true;
+				}
+				if (b.reads.empty()) b.paired = lookPair; else if (lookPair != b.paired) break;   /* the other kind starts the next batch */
+				rec = lrec; rec2 = lrec2; paired = lookPair; haveLook = false;
+			} else {
+				if (rd.rdid >= op.qUpto) { input_done = true; break; }
+				if (!rd.next(rec)) { input_done = true; break; }
+				if (interleaved) { if (!rd.next(rec2)) die("Error: odd number of reads in an --interleaved file"); rd.rdid--; }   /* a pair is one read id */
+				else if (paired && !rd2.next(rec2)) die("Error, fewer reads in file specified with -2 than in file specified with -1");
+			}
 			if (rd.rdid - 1 < op.skipReads) continue;                              /* -s: skipped reads are not counted */
 			for (int m = 0; m < (paired ? 2 : 1); m++) {
 				ReadRec &rr = m ? rec2 : rec;
@@ -576,6 +621,10 @@ int main(int argc, char **argv) {
 	};
 	auto launch = [&](Batch &b) {
 		if (b.reads.empty()) return;
+		const uint32_t mult = b.paired ? 2u : 1u;                                  /* HitSinkPerThreadFactory::createMult */
+		const bt_policy_t &pol = b.paired ? polP : polU;
+		b.slots = op.allHits ? 8 : op.khits * mult;
+		if (op.sampleMax && op.mhits != 0xffffffffu) b.slots = std::max(b.slots, op.mhits * mult);   /* -M keeps every hit up to the ceiling */
 		const size_t n = b.reads.size() / mult, rw = BT_HIT_HDR_WORDS + b.mm_cap;
 		b.found.assign(n, 0); b.flags.assign(n, 0); b.hits.assign(n * b.slots * rw, 0);
 		bt_read_batch_t in; memset(&in, 0, sizeof in);
@@ -588,6 +637,8 @@ int main(int argc, char **argv) {
 		if (!b.inflight) return;
 		if (bt_context_sync(b.cx, NULL)) die(std::string("Error: ") + bt_last_error());
 		b.inflight = false;
+		const bool paired = b.paired; const uint32_t mult = paired ? 2u : 1u;
+		const bt_policy_t &pol = paired ? polP : polU;
 		const size_t n = b.reads.size() / mult;                                    /* work units: reads or pairs */
 		const uint32_t nlimU = (nlim == 0xffffffffu) ? nlim : nlim * mult, mhitsU = (op.mhits == 0xffffffffu) ? op.mhits : op.mhits * mult;
 		size_t rw = BT_HIT_HDR_WORDS + b.mm_cap;
@@ -678,7 +729,7 @@ int main(int argc, char **argv) {
 							}
 							break;
 						}
-						numAligned++; numReported += 2;
+						numAligned++; numReportedPaired += 2;
 					}
 				}
 			}
@@ -700,7 +751,7 @@ int main(int argc, char **argv) {
 					}
 					if (op.sam) append_sam(out.buf, op, ix, *rr, h, op.defaultMapq, (int)(nrep / mult)); else append_default(out.buf, op, ix, *rr, h);
 				}
-				numAligned++; numReported += nrep;
+				numAligned++; if (paired) numReportedPaired += nrep; else numReported += nrep;
 			}
 			out.maybe_flush();
 		}
@@ -730,9 +781,11 @@ int main(int argc, char **argv) {
 		fprintf(stderr, "# reads with at least one alignment: %llu (%.2f%%)\n", (unsigned long long)alShown, alPct);
 		fprintf(stderr, "# reads that failed to align: %llu (%.2f%%)\n", (unsigned long long)numUnaligned, unalPct);
 		if (numMaxed > 0) fprintf(stderr, op.sampleMax ? "# reads with alignments sampled due to -M: %llu (%.2f%%)\n" : "# reads with alignments suppressed due to -m: %llu (%.2f%%)\n", (unsigned long long)numMaxed, maxPct);
-		if (numReported == 0) fprintf(stderr, "No alignments\n");
-		else if (paired) fprintf(stderr, "Reported %llu paired-end alignments\n", (unsigned long long)(numReported >> 1));
-		else fprintf(stderr, "Reported %llu alignments\n", (unsigned long long)numReported);
+		/* HitSink::finish (hit.h:322-337) */
+		if (numReported == 0 && numReportedPaired == 0) fprintf(stderr, "No alignments\n");
+		else if (numReportedPaired > 0 && numReported == 0) fprintf(stderr, "Reported %llu paired-end alignments\n", (unsigned long long)(numReportedPaired >> 1));
+		else if (numReported > 0 && numReportedPaired == 0) fprintf(stderr, "Reported %llu alignments\n", (unsigned long long)numReported);
+		else fprintf(stderr, "Reported %llu paired-end alignments and %llu singleton alignments\n", (unsigned long long)(numReportedPaired >> 1), (unsigned long long)numReported);
 	}
 	if (op.timing) {
 		auto secs = [](std::chrono::steady_clock::duration d) { return (long)std::chrono::duration_cast<std::chrono::seconds>(d).count(); };

@@ -124,3 +124,49 @@ def test_interleaved_input(setup, tmp_path):
             assert p.returncode == 0, p.stderr
             outs.append(b"".join(l for l in out.read_bytes().splitlines(keepends=True) if not l.startswith(b"@PG")))
         assert outs[0] == outs[1] and len(outs[0]) > 0
+
+
+def make_tabbed(setup, tmp_path, mixed):
+    import random
+    base, m1, m2 = setup["ecoli"]
+    a, b = Path(m1).read_text().splitlines(), Path(m2).read_text().splitlines()
+    u = (FIXTURES / "e_coli_1000.fq").read_text().splitlines()
+    rng = random.Random(3)
+    out = []
+    for i in range(600):
+        if not mixed or rng.random() < 0.5:
+            out.append("\t".join([a[4 * i][1:].replace("/1", ""), a[4 * i + 1], a[4 * i + 3], b[4 * i + 1], b[4 * i + 3]]))
+        else:
+            out.append("\t".join([u[4 * i][1:], u[4 * i + 1], u[4 * i + 3]]))
+        if rng.random() < 0.1:
+            out.append("")
+    f = tmp_path / "reads.tab"
+    f.write_text("\n".join(out) + "\n")
+    return base, f
+
+
+def check_tabbed(setup, tmp_path, env):
+    """--12 (TabbedPatternSource): records may mix pairs and single reads; any paired input makes the whole run stateful, and the
+    summary reports "N paired-end alignments and M singleton alignments" (hit.h:322-337)."""
+    for mixed in (True, False):
+        base, f = make_tabbed(setup, tmp_path, mixed)
+        for flags in (["-n", "2"], ["-v", "2", "-k", "2", "-S"], ["-n", "2", "-s", "10", "-u", "300", "-5", "2", "-3", "1"], ["-v", "3", "-a"],
+                      ["-n", "2", "--best", "--strata", "-k", "3"], ["-n", "2", "-M", "1"]):
+            res = []
+            for exe, e, extra in ((REF_ALIGN, None, ["-p", "1"]), (CLI, env, [])):
+                out = tmp_path / f"{Path(exe).name}.out"
+                p = subprocess.run([str(exe), *flags, *extra, "-x", str(base), "--12", str(f), str(out)], capture_output=True, text=True, env=e)
+                assert p.returncode == 0, p.stderr
+                body = b"".join(l for l in out.read_bytes().splitlines(keepends=True) if not l.startswith(b"@PG"))
+                res.append((body, [l for l in p.stderr.splitlines() if l.startswith("#") or l.startswith("Reported")]))
+            assert res[0] == res[1], (mixed, flags)
+            assert len(res[0][0]) > 0
+
+
+def test_tabbed_input(setup, tmp_path):
+    check_tabbed(setup, tmp_path, shim_env())
+
+
+@pytest.mark.gpu
+def test_tabbed_input_gpu(setup, tmp_path):
+    check_tabbed(setup, tmp_path, gpu_env())
