@@ -36,6 +36,18 @@ def ensure_oracle_built() -> None:
         subprocess.run(["make", "-C", str(ORACLE_DIR), "port"], check=True, capture_output=True)
     if not REF_ALIGN.exists() and Path("/root/reference/ebwt_search.cpp").exists():
         subprocess.run(["make", "-C", str(ORACLE_DIR), "-j8", "ref"], check=True, capture_output=True)
+    # the fixtures are copies of the reference's shipped files; a copy that was clobbered (e.g. by handing it to an aligner as
+    # an output path) is restored where the originals are available, and reported where they are not
+    for f in FIXTURES.glob("*") if FIXTURES.exists() else []:
+        if f.is_file() and f.stat().st_size == 0:
+            for d in ("reads", "indexes", "genomes"):
+                src = Path("/root/reference") / d / f.name
+                if src.exists():
+                    import shutil
+                    shutil.copyfile(src, f)
+                    break
+            else:
+                raise RuntimeError(f"fixture {f} is empty and /root/reference is not available to restore it")
 
 
 def have_reference() -> bool:
