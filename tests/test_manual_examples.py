@@ -1,0 +1,52 @@
+"""The reporting-mode examples of the reference's MANUAL (MANUAL.markdown:246-368, Examples 1-9): the exact lines the
+manual prints for `-c ATGCATCATGCGCCAT` on the shipped e_coli index.  A documented golden vector of the reference that
+covers -a / -k / default / --best / --strata / -m on both search paths."""
+import os
+import subprocess
+
+import pytest
+
+from helpers import FIXTURES, ensure_oracle_built, have_reference
+from test_cli_parity import CLI, SHIM_DIR, build_shim
+
+G = "gi|110640213|ref|NC_008253.1|"
+H = {148810: f"-\t{G}\t148810\t10:A>G,13:C>G", 2852852: f"-\t{G}\t2852852\t8:T>A", 4930433: f"-\t{G}\t4930433\t4:G>T,6:C>G",
+     905664: f"-\t{G}\t905664\t6:A>G,7:G>T", 1093035: f"+\t{G}\t1093035\t2:T>G,15:A>T"}
+EXAMPLES = [
+    ("Example 1: -a", ["-a", "-v", "2"], [148810, 2852852, 4930433, 905664, 1093035]),
+    ("Example 2: -k 3", ["-k", "3", "-v", "2"], [148810, 2852852, 4930433]),
+    ("Example 3: -k 6", ["-k", "6", "-v", "2"], [148810, 2852852, 4930433, 905664, 1093035]),
+    ("Example 4: default", ["-v", "2"], [148810]),
+    ("Example 5: -a --best", ["-a", "--best", "-v", "2"], [2852852, 1093035, 905664, 148810, 4930433]),
+    ("Example 6: -a --best --strata", ["-a", "--best", "--strata", "-v", "2"], [2852852]),
+    ("Example 7: -a -m 3", ["-a", "-m", "3", "-v", "2"], []),
+    ("Example 8: -a -m 5", ["-a", "-m", "5", "-v", "2"], [148810, 2852852, 4930433, 905664, 1093035]),
+    ("Example 9: -a -m 3 --best --strata", ["-a", "-m", "3", "--best", "--strata", "-v", "2"], [2852852]),
+]
+
+
+def run_example(flags, env):
+    p = subprocess.run([str(CLI), *flags, "--suppress", "1,5,6,7", "-x", str(FIXTURES / "e_coli"), "-c", "ATGCATCATGCGCCAT"], capture_output=True, text=True, env=env)
+    assert p.returncode == 0, p.stderr
+    return p.stdout.splitlines()
+
+
+@pytest.fixture(scope="module")
+def ready():
+    ensure_oracle_built()
+    if not have_reference():
+        pytest.skip("fixtures not available")
+    import bowtie_b200
+    bowtie_b200.build_library()
+
+
+@pytest.mark.parametrize("name,flags,want", EXAMPLES, ids=[e[0].split(":")[0].replace(" ", "") for e in EXAMPLES])
+def test_manual_example_host_logic(name, flags, want, ready):
+    build_shim()
+    assert run_example(flags, dict(os.environ, LD_LIBRARY_PATH=str(SHIM_DIR))) == [H[k] for k in want]
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("name,flags,want", EXAMPLES, ids=[e[0].split(":")[0].replace(" ", "") for e in EXAMPLES])
+def test_manual_example_gpu(name, flags, want, ready):
+    assert run_example(flags, {k: v for k, v in os.environ.items() if k != "LD_LIBRARY_PATH"}) == [H[k] for k in want]
