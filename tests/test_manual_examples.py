@@ -1,12 +1,14 @@
 """The reporting-mode examples of the reference's MANUAL (MANUAL.markdown:246-368, Examples 1-9): the exact lines the
 manual prints for `-c ATGCATCATGCGCCAT` on the shipped e_coli index.  A documented golden vector of the reference that
-covers -a / -k / default / --best / --strata / -m on both search paths."""
+covers -a / -k / default / --best / --strata / -m on both search paths.  (Example 5 lists the four 2-mismatch hits in an
+order that 1.3.1 itself no longer prints — the order among equal-cost ranges depends on the release — so that one is
+checked as "best hit first, same set" against the manual and line by line against the reference binary.)"""
 import os
 import subprocess
 
 import pytest
 
-from helpers import FIXTURES, ensure_oracle_built, have_reference
+from helpers import FIXTURES, REF_ALIGN, ensure_oracle_built, have_reference
 from test_cli_parity import CLI, SHIM_DIR, build_shim
 
 G = "gi|110640213|ref|NC_008253.1|"
@@ -25,10 +27,19 @@ EXAMPLES = [
 ]
 
 
-def run_example(flags, env):
-    p = subprocess.run([str(CLI), *flags, "--suppress", "1,5,6,7", "-x", str(FIXTURES / "e_coli"), "-c", "ATGCATCATGCGCCAT"], capture_output=True, text=True, env=env)
+def run_example(flags, env, exe=None):
+    p = subprocess.run([str(exe or CLI), *flags, "--suppress", "1,5,6,7", "-x", str(FIXTURES / "e_coli"), "-c", "ATGCATCATGCGCCAT"], capture_output=True, text=True, env=env)
     assert p.returncode == 0, p.stderr
     return p.stdout.splitlines()
+
+
+def check(name, flags, want, env):
+    got = run_example(flags, env)
+    if name.startswith("Example 5"):
+        assert got[0] == H[want[0]] and sorted(got) == sorted(H[k] for k in want)
+    else:
+        assert got == [H[k] for k in want]
+    assert got == run_example(flags, None, exe=REF_ALIGN)
 
 
 @pytest.fixture(scope="module")
@@ -43,10 +54,10 @@ def ready():
 @pytest.mark.parametrize("name,flags,want", EXAMPLES, ids=[e[0].split(":")[0].replace(" ", "") for e in EXAMPLES])
 def test_manual_example_host_logic(name, flags, want, ready):
     build_shim()
-    assert run_example(flags, dict(os.environ, LD_LIBRARY_PATH=str(SHIM_DIR))) == [H[k] for k in want]
+    check(name, flags, want, dict(os.environ, LD_LIBRARY_PATH=str(SHIM_DIR)))
 
 
 @pytest.mark.gpu
 @pytest.mark.parametrize("name,flags,want", EXAMPLES, ids=[e[0].split(":")[0].replace(" ", "") for e in EXAMPLES])
 def test_manual_example_gpu(name, flags, want, ready):
-    assert run_example(flags, {k: v for k, v in os.environ.items() if k != "LD_LIBRARY_PATH"}) == [H[k] for k in want]
+    check(name, flags, want, {k: v for k, v in os.environ.items() if k != "LD_LIBRARY_PATH"})
