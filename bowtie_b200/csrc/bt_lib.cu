@@ -706,9 +706,9 @@ static bool main_kernel_is_queue() {
 #define BT_HEAVY_BLOCKS_PER_SM 8   /* heavy pass: 32-thread blocks, so finished warps free their slots */
 
 /* The best-first path (bt_best.cuh).  Three passes with growing per-read arenas: every read with 64 KB on the caller's
- * stream (148 x 8 x 64 lanes); the reads that exhausted it with 1 MB (148 x 32 lanes), then 16 MB (148 lanes), then 256 MB
+ * stream (148 x 12 x 64 lanes); the reads that exhausted it with 1 MB (148 x 32 lanes), then 16 MB (148 lanes), then 256 MB
  * (8 lanes; the reference's own ceiling is 64 MB of chunked pools per thread) on the side stream.
- * About 5 + 5 + 2.5 + 2 GB per context for full batches. */
+ * About 7.5 (pairs: 11) + 5 + 2.5 + 2 GB per context for full batches. */
 static int enqueue_best(bt_context *cx, const bt_policy_t *pol, const bt_read_batch_t *in, bt_hit_batch_t *out, uint32_t maxlen, cudaStream_t st) {
 	bt_index_t *ix = cx->ix;
 	if (pol->paired && (in->nreads & 1)) return fail("bt_align (paired-end): nreads must be even (mates are adjacent reads)");
@@ -721,7 +721,8 @@ static int enqueue_best(bt_context *cx, const bt_policy_t *pol, const bt_read_ba
 	 * profiles/README.md): -n 2 --best p99 35 KB, p99.9 282 KB; paired -n 3 p95 60 KB, p99 113 KB, p99.9 326 KB */
 	const uint32_t tierWords[NT] = { (pol->paired ? kw0 + kw0 / 2 : kw0) << 10, 256u << 10, 4096u << 10, 65536u << 10 };
 	const uint32_t tierLanes[NT] = { BF_THREADS, 32, 1, 1 };                                /* active threads per block */
-	uint32_t tierBlocks[NT] = { (uint32_t)ix->sms * 8, (uint32_t)ix->sms, (uint32_t)ix->sms, 8 };
+	/* first tier: 12 blocks of 64 lanes per SM = 768 resident threads (72 / 80 registers per thread: the register file allows 910 / 819) */
+	uint32_t tierBlocks[NT] = { (uint32_t)ix->sms * 12, (uint32_t)ix->sms, (uint32_t)ix->sms, 8 };
 	for (int k = 0; k < NT; k++) {
 		const uint32_t need_blocks = (nwork + tierLanes[k] - 1) / tierLanes[k];   /* small batches do not need a full machine of arenas */
 		if (tierBlocks[k] > need_blocks) tierBlocks[k] = need_blocks;
