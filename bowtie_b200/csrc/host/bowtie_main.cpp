@@ -9,6 +9,7 @@
  * paired-end options are rejected with a message; nothing falls back to a CPU search.
  */
 #include <algorithm>
+#include <map>
 #include <getopt.h>
 #include <stdint.h>
 #include <stdio.h>
@@ -35,6 +36,7 @@ struct Opts {
 	int mismatches = 0, seedMms = 2, maqLike = 1, seedLen = 28, qualThresh = 70, maxBts = 125, maxBtsBest = 800;
 	bool best = false, strata = false, sampleMax = false, bestFlag = false;   /* bestFlag: --best itself (it alone selects the V2 paired aligner) */
 	std::vector<std::string> mates1, mates2, interleaved, tabbed;
+	std::string dumpAl, dumpUn, dumpMax;                   /* --al / --un / --max: dump reads by outcome (hit.h:385-492) */
 	bool bestPaired = false;   /* the pairs' --best: PairedBWAlignerV2 */
 	uint32_t minInsert = 0, maxInsert = 250, pairTries = 100; bool mate1fw = true, mate2fw = false;
 	bool noMaqRound = false, nofw = false, norc = false, allHits = false;
@@ -62,7 +64,7 @@ enum {
 	ARG_PHRED33 = 256, ARG_PHRED64, ARG_SOLEXA, ARG_SOLEXA13, ARG_NOMAQROUND, ARG_NOFW, ARG_NORC, ARG_MAXBTS, ARG_BEST, ARG_STRATA,
 	ARG_QUIET, ARG_REFIDX, ARG_SUPPRESS, ARG_FULLREF, ARG_MAPQ, ARG_SAM_NOHEAD, ARG_SAM_NOSQ, ARG_SAM_RG, ARG_NO_UNAL, ARG_SEED,
 	ARG_COST, ARG_REORDER, ARG_WRAPPER, ARG_VERSION, ARG_IGNORED0, ARG_IGNORED1, ARG_DEVICE, ARG_BATCH, ARG_SAM_NO_QNAME_TRUNC,
-	ARG_LARGE_INDEX, ARG_PAIRED, ARG_INTERLEAVED, ARG_FF, ARG_FR, ARG_RF, ARG_PAIRTRIES
+	ARG_LARGE_INDEX, ARG_PAIRED, ARG_INTERLEAVED, ARG_AL, ARG_UN, ARG_MAXDUMP, ARG_FF, ARG_FR, ARG_RF, ARG_PAIRTRIES
 };
 
 static const char *short_options = "fqrchu:v:s:at3:5:e:n:l:p:k:m:M:1:2:I:X:x:B:yS";
@@ -84,6 +86,7 @@ static struct option long_options[] = {
 	{"device", required_argument, 0, ARG_DEVICE}, {"reads-per-batch", required_argument, 0, ARG_BATCH},
 	{"large-index", no_argument, 0, ARG_LARGE_INDEX}, {"12", required_argument, 0, ARG_PAIRED}, {"interleaved", required_argument, 0, ARG_INTERLEAVED},
 	{"ff", no_argument, 0, ARG_FF}, {"fr", no_argument, 0, ARG_FR}, {"rf", no_argument, 0, ARG_RF}, {"pairtries", required_argument, 0, ARG_PAIRTRIES},
+	{"al", required_argument, 0, ARG_AL}, {"un", required_argument, 0, ARG_UN}, {"max", required_argument, 0, ARG_MAXDUMP},
 	{"minins", required_argument, 0, 'I'}, {"maxins", required_argument, 0, 'X'},
 	{0, 0, 0, 0}
 };
@@ -139,6 +142,9 @@ static void parse_options(int argc, char **argv, Opts &o) {
 		case ARG_RF: o.mate1fw = false; o.mate2fw = true; break;
 		case ARG_PAIRTRIES: o.pairTries = (uint32_t)parse_int(1, "--pairtries arg must be at least 1"); break;
 		case ARG_INTERLEAVED: split(optarg, ',', o.interleaved); break;
+		case ARG_AL: o.dumpAl = optarg; break;
+		case ARG_UN: o.dumpUn = optarg; break;
+		case ARG_MAXDUMP: o.dumpMax = optarg; break;
 		case ARG_PAIRED: split(optarg, ',', o.tabbed); break;                       /* --12: one record per line, unpaired (3 fields) or paired (5) */
 		case ARG_BEST: o.best = true; o.bestFlag = true; break;
 		case ARG_STRATA: o.strata = true; break;
@@ -207,7 +213,7 @@ static const unsigned char solToPhred[] = {   /* qual.cpp: Solexa (log-odds) -> 
 	30, 31, 32, 33, 34, 35, 36, 37, 38, 39, 40, 41, 42, 43, 44, 45, 46, 47, 48, 49, 50, 51, 52, 53, 54, 55, 56, 57, 58, 59, 60, 61, 62, 63, 64, 65,
 	66, 67, 68, 69, 70, 71, 72, 73, 74, 75, 76, 77, 78, 79, 80, 81, 82, 83, 84, 85, 86, 87, 88, 89, 90, 91, 92, 93, 94, 95, 96, 97, 98, 99, 100 };
 
-struct ReadRec { std::string name, seq /* codes 0..4 */, qual /* phred+33 */; };
+struct ReadRec { std::string name, seq /* codes 0..4 */, qual /* phred+33 */, orig /* Read::readOrigBuf: the record as it stood in the input (for --al/--un/--max) */; };
 
 struct Reader {
 	const Opts &o;
@@ -286,6 +292,7 @@ struct Reader {
 			std::vector<std::string> fld; size_t p0 = 0;
 			for (;;) { size_t t = line.find('\t', p0); if (t == std::string::npos) { fld.push_back(line.substr(p0)); break; } fld.push_back(line.substr(p0, t - p0)); p0 = t + 1; }
 			rdid++;
+			a.orig = line; a.orig += '\n'; b.orig.clear();
 			if (fld.size() < 3) continue;                                    /* "record ended prematurely": the read is skipped */
 			isPair = fld.size() >= 5;
 			for (int e = 0; e < (isPair ? 2 : 1); e++) {
@@ -332,6 +339,7 @@ struct Reader {
 				if (l1.empty()) continue;
 				if (!getline_(l2) || !getline_(l3)) { gzclose(f); f = NULL; continue; }
 				getline_(l4);
+				r.orig = l1; r.orig += '\n'; r.orig += l2; r.orig += '\n'; r.orig += l3; r.orig += '\n'; r.orig += l4; r.orig += '\n';   /* pat.cpp:818-839 */
 				while (!l1.empty() && l1.back() == '\r') l1.pop_back();
 				while (!l4.empty() && l4.back() == '\r') l4.pop_back();
 				r.name = l1.substr(1);
@@ -355,6 +363,7 @@ struct Reader {
 				while (c == '\r' || c == '\n') { getc_(); c = peek_(); }
 				if (c < 0 || c == '>') { if (c < 0) { gzclose(f); f = NULL; } continue; }      /* FASTA ended prematurely */
 				getline_(l2);
+				r.orig = l1; r.orig += '\n'; r.orig += l2; r.orig += '\n';      /* header and first sequence line */
 				/* FastaPatternSource::parse stops at `cur < buflen` before it appends the character it just fetched
 				 * (pat.cpp:607-619): a sequence line that ends at EOF without a newline loses its last character */
 				if (line_hit_eof && !l2.empty()) l2.pop_back();
@@ -371,6 +380,7 @@ struct Reader {
 				int t5, t3; finish_seq(r, l1, t5, t3);
 				r.qual.assign(r.seq.size(), 'I');
 				r.name.clear();
+				r.orig = l1; r.orig += '\n';
 			}
 			if (r.name.empty()) r.name = std::to_string(rdid);
 			rdid++;
@@ -580,6 +590,21 @@ int main(int argc, char **argv) {
 		b.mm_cap = op.maqLike ? 10 : (uint32_t)std::max(1, op.mismatches);
 	}
 	uint64_t numAligned = 0, numUnaligned = 0, numMaxed = 0, numReported = 0, numReportedPaired = 0;
+	/* HitSink::dumpAlign / dumpUnal / dumpMaxed (hit.h:385-492): files are opened when the first read lands in them; pairs go to
+	 * <base>_1.<ext> / <base>_2.<ext> (openOf, hit.h:629-660); maxed reads fall back to --un when --max is not given */
+	std::map<std::string, FILE *> dumps;
+	auto dump_to = [&](const std::string &base, int mate, const std::string &text) {
+		std::string nm = base;
+		if (mate) { const size_t dot = base.find_last_of('.'); const char *sfx = mate == 1 ? "_1" : "_2"; nm = dot == std::string::npos ? base + sfx : base.substr(0, dot) + sfx + base.substr(dot); }
+		FILE *&fp = dumps[nm];
+		if (!fp) { fp = fopen(nm.c_str(), "wb"); if (!fp) die((mate ? "Could not open paired-end aligned/unaligned-read file for writing: " : "Could not open single-ended aligned/unaligned-read file for writing: ") + base); }
+		fwrite(text.data(), 1, text.size(), fp);
+	};
+	auto dump_unit = [&](const std::string &base, const Batch &b, size_t i) {
+		if (base.empty()) return;
+		if (b.paired) { dump_to(base, 1, b.reads[2 * i].orig); dump_to(base, 2, b.reads[2 * i + 1].orig); }
+		else dump_to(base, 0, b.reads[i].orig);
+	};
 	ReadRec lrec, lrec2; bool haveLook = false, lookPair = false;                 /* --12: one record of lookahead (a batch is all pairs or all single reads) */
 	bool input_done = false;
 	ReadRec rec, rec2;
@@ -698,6 +723,7 @@ int main(int argc, char **argv) {
 			const bool maxed = found > mhitsU, unal = (found == 0);
 			if (maxed) {
 				numMaxed++;
+				dump_unit(op.dumpMax.empty() ? op.dumpUn : op.dumpMax, b, i);
 				if (op.sampleMax) {
 					/* VerboseHitSink::reportMaxed (hit.cpp:16-68) / SAMHitSink::reportMaxed (sam.cpp:263-311): one of the
 					 * buffered hits of the best stratum, picked with a fresh RandomSource seeded by the read */
@@ -735,6 +761,7 @@ int main(int argc, char **argv) {
 			}
 			else if (unal) {
 				numUnaligned++;
+				dump_unit(op.dumpUn, b, i);
 				if (op.sam && !op.noUnal) { if (paired) { append_sam_unaligned(out.buf, op, r, 1); append_sam_unaligned(out.buf, op, b.reads[i * mult + 1], 2); } else append_sam_unaligned(out.buf, op, r); }
 			} else {
 				uint32_t nrep = std::min(found, nlimU);
@@ -752,6 +779,7 @@ int main(int argc, char **argv) {
 					if (op.sam) append_sam(out.buf, op, ix, *rr, h, op.defaultMapq, (int)(nrep / mult)); else append_default(out.buf, op, ix, *rr, h);
 				}
 				numAligned++; if (paired) numReportedPaired += nrep; else numReported += nrep;
+				dump_unit(op.dumpAl, b, i);
 			}
 			out.maybe_flush();
 		}
@@ -769,6 +797,7 @@ int main(int argc, char **argv) {
 	}
 	out.flush();
 	if (out.fp != stdout) fclose(out.fp);
+	for (auto &kv : dumps) if (kv.second) fclose(kv.second);
 	auto t_end = std::chrono::steady_clock::now();
 
 	/* HitSink::finish (hit.h:270-346) */

@@ -140,3 +140,35 @@ def test_cli_rejects_unsupported_combinations(cli, tmp_path):
     assert p.returncode != 0 and "--strata must be combined with --best" in p.stderr
     p = subprocess.run([str(cli), "--best", "--strata", "-x", str(FIXTURES / "e_coli"), "-c", "ACGTACGTACGT"], capture_output=True, text=True, env=env)
     assert p.returncode != 0 and "--strata has no effect" in p.stderr
+
+
+def check_dumps(cli, tmp_path, env):
+    """--al / --un / --max (HitSink::dumpAlign/dumpUnal/dumpMaxed, hit.h:385-492): the reads, as they stood in the input, split by
+    outcome; pairs go to <base>_1/<base>_2; maxed reads fall back to --un without --max."""
+    fq, fa, raw = FIXTURES / "e_coli_1000.fq", FIXTURES / "e_coli_1000.fa", FIXTURES / "e_coli_1000.raw"
+    m1, m2 = FIXTURES / "e_coli_1000_1.fq", FIXTURES / "e_coli_1000_2.fq"
+    runs = [(["-n", "2", "-m", "1"], ["-q", str(fq)], True), (["-n", "2", "-M", "1"], ["-q", str(fq)], True), (["-v", "1", "-m", "1"], ["-q", str(fq)], False),
+            (["-n", "2", "-m", "1"], ["-f", str(fa)], True), (["-n", "2", "-m", "1"], ["-r", str(raw)], True),
+            (["-n", "2", "-m", "1", "-X", "150"], ["-1", str(m1), "-2", str(m2)], True)]
+    for flags, src, with_max in runs:
+        got = []
+        for tag, exe, e, extra in (("ref", REF_ALIGN, None, ["-p", "1"]), ("our", cli, env, [])):
+            d = tmp_path / f"{tag}_{len(got)}_{abs(hash(tuple(flags + src))) % 10000}"
+            d.mkdir()
+            dump = ["--un", str(d / "un.fq"), "--al", str(d / "al.fq")] + (["--max", str(d / "max.fq")] if with_max else [])
+            p = subprocess.run([str(exe), *flags, *extra, *dump, "-x", str(FIXTURES / "e_coli"), *src, str(d / "hits.out")], capture_output=True, text=True, env=e)
+            assert p.returncode == 0, p.stderr
+            got.append({f.name: f.read_bytes() for f in sorted(d.iterdir()) if f.name != "hits.out"})
+        assert got[0].keys() == got[1].keys(), (flags, src)
+        assert got[0] == got[1], (flags, src)
+        assert any(len(v) for v in got[0].values())
+
+
+def test_cli_read_dumps(cli, tmp_path):
+    build_shim()
+    check_dumps(cli, tmp_path, dict(os.environ, LD_LIBRARY_PATH=str(SHIM_DIR)))
+
+
+@pytest.mark.gpu
+def test_cli_read_dumps_gpu(cli, tmp_path):
+    check_dumps(cli, tmp_path, {k: v for k, v in os.environ.items() if k != "LD_LIBRARY_PATH"})
