@@ -26,7 +26,6 @@
 #include "bt_core.cuh"
 
 #define BF_MAX_TOP 8
-#define BF_ADV_COST_CHANGES 2
 
 enum { BF_PIN_BEGINNING = 1, BF_PIN_LEN, BF_PIN_HI_HALF, BF_PIN_SEED };   /* SearchConstraintExtent, ebwt_search_backtrack.h:2658-2663 */
 enum { BF_KIND_SRC = 0, BF_KIND_SEEDED = 1 };
@@ -587,9 +586,8 @@ BT_NOINLINE void bf_src_set_query(BfCtx &X, BfSrc &s, const BfSrc *seed) {
 	/* initRangeSource */
 	const uint32_t seedLen = X.P->prog.seedLen;
 	const uint32_t sl = seedLen > 0 ? (seedLen < len ? seedLen : len) : len;
-	uint32_t sLeft = sl >> 1, sRight = sl >> 1;
-	if (sl & 1) { if (s.cfg.nudgeLeft) sLeft++; else sRight++; }
-	(void)sLeft;
+	uint32_t sRight = sl >> 1;                                          /* the odd base goes left (nudgeLeft) or right */
+	if ((sl & 1) && !s.cfg.nudgeLeft) sRight++;
 	const uint32_t r0 = bf_cext(s.cfg.rev[0], sRight, sl, len), r1 = bf_cext(s.cfg.rev[1], sRight, sl, len),
 	               r2 = bf_cext(s.cfg.rev[2], sRight, sl, len), r3 = bf_cext(s.cfg.rev[3], sRight, sl, len);
 	uint32_t qlen = len;
@@ -1171,9 +1169,11 @@ BT_NOINLINE bool bf_pair_resolve_in_ref(BfCtx &X, BfPairState &S, bool off1, uin
 	return ret;
 }
 
+/* Debug aid of the host emulation (g++ -DBF_TRACE_EVENTS): print the reference's own --verbose event messages so that the two
+ * event streams can be diffed (`bowtie-align-s --verbose ... | grep -E "Chasing|Delaying|Resuming|Done with chase|Making an attempt"`). */
 #if defined(BT_HOST_EMU) && defined(BF_TRACE_EVENTS)
 #include <stdio.h>
-#define BF_TRACE(msg) fprintf(stderr, "%s\n", msg)          /* the reference's --verbose messages, for diffing event traces */
+#define BF_TRACE(msg) fprintf(stderr, "%s\n", msg)
 #define BF_TRACE_RANGE(r) fprintf(stderr, "   range top=%u bot=%u idx=%u fw=%u mate=%u cost=%u nmm=%u e0=%x\n", (r).rTop, (r).rBot, (r).cfg.ebwtSel, (r).cfg.fw, (r).cfg.mate, (r).rCost, (r).rNmm, (r).rNmm ? X.A[(r).rEdits] : 0)
 #else
 #define BF_TRACE(msg) ((void)0)
