@@ -334,7 +334,8 @@ struct Reader {
 			if (o.format == FASTQ) {
 				/* FastqPatternSource (pat.cpp:797-975) */
 				if (first) { int c = peek_(); while (c == '\r' || c == '\n') { getc_(); c = peek_(); } if (c < 0) { gzclose(f); f = NULL; continue; }
-					if (c != '@') die("Error: reads file does not look like a FASTQ file"); first = false; }
+					if (c != '@') die("Error: reads file does not look like a FASTQ file");
+					first = false; }
 				if (!getline_(l1)) { gzclose(f); f = NULL; continue; }
 				if (l1.empty()) continue;
 				if (!getline_(l2) || !getline_(l3)) { gzclose(f); f = NULL; continue; }
@@ -354,7 +355,8 @@ struct Reader {
 			} else if (o.format == FASTA) {
 				/* FastaPatternSource (pat.cpp:531-640): header line, then the first sequence line */
 				if (first) { int c = peek_(); while (c == '\r' || c == '\n') { getc_(); c = peek_(); } if (c < 0) { gzclose(f); f = NULL; continue; }
-					if (c != '>') die("Error: reads file does not look like a FASTA file"); first = false; }
+					if (c != '>') die("Error: reads file does not look like a FASTA file");
+					first = false; }
 				if (!getline_(l1)) { gzclose(f); f = NULL; continue; }
 				if (l1.empty() || l1[0] != '>') continue;
 				while (!l1.empty() && l1.back() == '\r') l1.pop_back();
