@@ -56,9 +56,6 @@ struct Opts {
 };
 
 static void die(const std::string &m) { fprintf(stderr, "%s\n", m.c_str()); exit(1); }
-static void unsupported(const char *what) {
-	die(std::string("Error: ") + what + " belongs to the reference's stateful (best-first / paired-end) path, which the B200 search path does not provide yet");
-}
 
 enum {
 	ARG_PHRED33 = 256, ARG_PHRED64, ARG_SOLEXA, ARG_SOLEXA13, ARG_NOMAQROUND, ARG_NOFW, ARG_NORC, ARG_MAXBTS, ARG_BEST, ARG_STRATA,
@@ -118,9 +115,11 @@ static void parse_options(int argc, char **argv, Opts &o) {
 		case '3': o.trim3 = (int)parse_int(0, "-3/--trim3 arg must be at least 0"); break;
 		case '5': o.trim5 = (int)parse_int(0, "-5/--trim5 arg must be at least 0"); break;
 		case 'v': o.maqLike = 0; o.mismatches = (int)parse_int(0, "-v arg must be at least 0"); vset = true;
-			if (o.mismatches > 3) die("-v arg must be at most 3"); break;
+			if (o.mismatches > 3) die("-v arg must be at most 3");
+			break;
 		case 'n': o.seedMms = (int)parse_int(0, "-n/--seedmms arg must be at least 0 and at most 3"); o.maqLike = 1;
-			if (o.seedMms > 3) die("-n/--seedmms arg must be at least 0 and at most 3"); break;
+			if (o.seedMms > 3) die("-n/--seedmms arg must be at least 0 and at most 3");
+			break;
 		case 'e': o.qualThresh = (int)parse_int(1, "-e/--err arg must be at least 1"); break;
 		case 'l': o.seedLen = (int)parse_int(5, "-l/--seedlen arg must be at least 5"); break;
 		case 'k': o.khits = (uint32_t)parse_int(1, "-k arg must be at least 1"); break;
