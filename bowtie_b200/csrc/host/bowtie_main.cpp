@@ -2,11 +2,12 @@
  * bowtie_main.cpp — `bowtie`-compatible host driver over libbowtie_b200.so.
  *
  * Keeps the reference's command line (ebwt_search.cpp:443-545, 614-919), read-file formats
- * (pat.cpp: FASTQ 862-975, FASTA 575-640, raw 1168-1213, -c 437-523), the default hit format
- * (hit.cpp:73-301) and SAM (sam.cpp:20-257), and the stderr summary (hit.h:270-346); the search
- * itself (everything the reference's *SearchWorker* functions do) is one bt_context_align_async()
- * call per batch of reads.  --best, --strata, -M and -v 3 select the library's best-first path;
- * paired-end options are rejected with a message; nothing falls back to a CPU search.
+ * (pat.cpp: FASTQ 862-975, FASTA 575-640, raw 1168-1213, -c 437-523, --12 980-1124; -1/-2, --interleaved), the default
+ * hit format (hit.cpp:73-301) and SAM (sam.cpp:20-257) for single reads and pairs, the read dumps --al/--un/--max
+ * (hit.h:385-492) and the stderr summary (hit.h:270-346); the search itself (everything the reference's
+ * *SearchWorker* functions do) is one bt_context_align_async() call per batch of reads or pairs.  --best, --strata,
+ * -M and -v 3 select the library's best-first path, paired input its paired-end path; what is not provided is
+ * rejected with a message — nothing falls back to a CPU search.
  */
 #include <algorithm>
 #include <map>
