@@ -26,6 +26,9 @@
 #include "bt_core.cuh"
 
 #define BF_MAX_TOP 8
+/* No legitimate search comes near this many branch-extension steps for one read (the longest seen, -a -y on short reads, is
+ * ~10^7); a read that does is abandoned with BT_FLAG_FRAME_OVF instead of occupying a GPU lane without bound. */
+#define BF_MAX_STEPS 0x40000000u
 
 enum { BF_PIN_BEGINNING = 1, BF_PIN_LEN, BF_PIN_HI_HALF, BF_PIN_SEED };   /* SearchConstraintExtent, ebwt_search_backtrack.h:2658-2663 */
 enum { BF_KIND_SRC = 0, BF_KIND_SEEDED = 1 };
@@ -112,6 +115,7 @@ struct BfCtx {
 	const uint8_t *seqM[2], *qualM[2];                    /* [0]: the read (mate 1), [1]: mate 2 */
 	uint32_t rid, rlenM[2], seedM[2];
 	uint32_t *A; uint32_t acap, atop, amax;               /* amax: high-water mark of the arena (diagnostics) */
+	uint32_t steps;                                        /* branch-extension steps of this read: a watchdog, see BF_MAX_STEPS */
 	uint32_t flags, found, randA;
 	int32_t bestStratum, btCnt;
 	BfRS spare;                                            /* where range-state writes land once the arena is exhausted */
@@ -477,6 +481,7 @@ BT_NOINLINE void bf_advance_branch(BfCtx &X, BfSrc &s) {
 	const uint32_t qualLim = X.P->prog.qualLim, maq = (uint32_t)X.P->pol.maqRound;
 	s.rsFound = 0;
 	do {
+		if (++X.steps > BF_MAX_STEPS) { X.flags |= BT_FLAG_FRAME_OVF; bf_pm_reset(s); return; }
 		const uint32_t brRef = X.A[s.heapOff];
 		BfBranch &br = *BF_BR(X, brRef);
 		const uint32_t depth = (uint32_t)br.rdepth + br.len;

@@ -353,7 +353,7 @@ bt_best_kernel(const __grid_constant__ BfKParams P, BtWorkCtl *ctl, uint32_t lan
 			X.rlenM[1] = (uint32_t)(P.roff[r0 + 2] - ro1); X.seedM[1] = P.seeds[r0 + 1];
 			X.seqM[1] = P.seq + ro1; X.qualM[1] = P.qual + ro1;
 		}
-		X.atop = 1; X.amax = 1; X.flags = 0; X.found = 0;
+		X.atop = 1; X.amax = 1; X.steps = 0; X.flags = 0; X.found = 0;
 		X.top.rssOff = X.top.rssCap = X.top.nRss = X.top.actOff = X.top.actCap = X.top.nAct = 0;
 		X.top.lastRange = X.top.delayedRange = 0; X.top.minCost = 0; X.top.done = 0; X.top.foundRange = 0; X.top.rnd = 0; X.top.paired = 0;
 		if (PAIRED) { if (P.prog.pairedV2) bf_align_pair_v2(X); else bf_align_pair(X); } else bf_align_read(X);

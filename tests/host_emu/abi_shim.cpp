@@ -123,7 +123,7 @@ static int run_best(bt_index *ix, const bt_policy_t *pol, const bt_read_batch_t 
 		if (poison) memset(arena.data(), 0xA5, (size_t)(poison_words < arena.size() ? poison_words : arena.size()) * 4);   /* the GPU arenas are never zeroed either */
 		if (pol->paired) { if (P.prog.pairedV2) bf_align_pair_v2(X); else bf_align_pair(X); } else bf_align_read(X);
 		if ((X.flags & BT_FLAG_STACK_OVF) && words < arena.size()) {      /* what the larger-arena passes of the product do */
-			memset(&X.top, 0, sizeof X.top); X.flags = 0; X.acap = (uint32_t)arena.size(); X.atop = 1;
+			memset(&X.top, 0, sizeof X.top); X.flags = 0; X.steps = 0; X.acap = (uint32_t)arena.size(); X.atop = 1;
 			if (pol->paired) { if (P.prog.pairedV2) bf_align_pair_v2(X); else bf_align_pair(X); } else bf_align_read(X);
 		}
 		if (X.flags & (BT_FLAG_STACK_OVF | BT_FLAG_FRAME_OVF)) X.found = 0;
