@@ -10,7 +10,11 @@
  * rejected with a message — nothing falls back to a CPU search.
  */
 #include <algorithm>
+#include <array>
 #include <map>
+#include <condition_variable>
+#include <mutex>
+#include <thread>
 #include <getopt.h>
 #include <stdint.h>
 #include <stdio.h>
@@ -208,6 +212,7 @@ static void parse_options(int argc, char **argv, Opts &o) {
 /* read input                                                                                      */
 /* ---------------------------------------------------------------------------------------------- */
 static uint8_t asc2dna[256];
+static uint8_t alpha_code[256];       /* asc2dna for letters, 4 for '.', 255 for characters a read line skips */
 static const unsigned char solToPhred[] = {   /* qual.cpp: Solexa (log-odds) -> Phred, index = sol + 10 */
 	0, 1, 1, 1, 1, 1, 1, 2, 2, 3, 3, 4, 4, 5, 5, 6, 7, 8, 9, 10, 10, 11, 12, 13, 14, 15, 16, 17, 18, 19, 20, 21, 22, 23, 24, 25, 26, 27, 28, 29,
 	30, 31, 32, 33, 34, 35, 36, 37, 38, 39, 40, 41, 42, 43, 44, 45, 46, 47, 48, 49, 50, 51, 52, 53, 54, 55, 56, 57, 58, 59, 60, 61, 62, 63, 64, 65,
@@ -215,16 +220,22 @@ static const unsigned char solToPhred[] = {   /* qual.cpp: Solexa (log-odds) -> 
 
 struct ReadRec { std::string name, seq /* codes 0..4 */, qual /* phred+33 */, orig /* Read::readOrigBuf: the record as it stood in the input (for --al/--un/--max) */; };
 
+static uint32_t gen_rand_seed(const ReadRec &r, uint32_t seed);
+
 struct Reader {
 	const Opts &o;
 	size_t fileIdx = 0;
 	gzFile f = NULL;
-	std::string buf; size_t pos = 0; bool eof = true;
+	std::vector<char> buf; size_t len = 0, pos = 0; bool eof = true;   /* buf[pos, len) is unread input */
 	uint64_t rdid = 0;
 	bool first = true;
 	size_t cmdIdx = 0;
 	const std::vector<std::string> &files;
-	Reader(const Opts &oo, const std::vector<std::string> &ff) : o(oo), files(ff) {}
+	const bool keepOrig;                /* --al/--un/--max need the records as they stood in the input */
+	std::string l1, l2, l3, l4;         /* line buffers, reused from record to record */
+	bool recEof = false;                /* FASTA: the last record ran to the end of the file */
+	std::vector<std::string> rawPieces; size_t rawQ = 0;   /* raw: the CR-separated pieces of the current line */
+	Reader(const Opts &oo, const std::vector<std::string> &ff) : o(oo), files(ff), keepOrig(!oo.dumpAl.empty() || !oo.dumpUn.empty() || !oo.dumpMax.empty()) {}
 	bool open_next() {
 		if (f) { gzclose(f); f = NULL; }
 		if (fileIdx >= files.size()) return false;
@@ -232,17 +243,38 @@ struct Reader {
 		f = (fn == "-") ? gzdopen(0, "rb") : gzopen(fn.c_str(), "rb");
 		if (!f) die("Warning: Could not open read file \"" + fn + "\" for reading");
 		gzbuffer(f, 1 << 20);
-		buf.clear(); pos = 0; eof = false; first = true;
+		if (buf.empty()) buf.resize(1 << 22);
+		len = pos = 0; eof = false; first = true; recEof = false;
 		return true;
 	}
-	int getc_() {
-		if (pos >= buf.size()) {
-			if (eof) return -1;
-			buf.resize(1 << 22);
-			int n = gzread(f, &buf[0], (unsigned)buf.size());
-			if (n <= 0) { eof = true; buf.clear(); pos = 0; return -1; }
-			buf.resize((size_t)n); pos = 0;
+	bool refill() {                     /* false at end of input */
+		if (eof) return false;
+		const int n = gzread(f, buf.data(), (unsigned)buf.size());
+		if (n <= 0) { eof = true; len = pos = 0; return false; }
+		len = (size_t)n; pos = 0;
+		return true;
+	}
+	/* true iff what is left of the file holds exactly one or two newlines; the unread input stays in the buffer */
+	bool tail_aborts() {
+		size_t scanned = pos; int nl = 0;
+		for (;;) {
+			while (nl < 3) {
+				const char *q = (const char *)memchr(buf.data() + scanned, '\n', len - scanned);
+				if (!q) { scanned = len; break; }
+				nl++; scanned = (size_t)(q - buf.data()) + 1;
+			}
+			if (nl >= 3) return false;
+			if (eof) break;
+			if (pos > 0) { memmove(buf.data(), buf.data() + pos, len - pos); scanned -= pos; len -= pos; pos = 0; }
+			if (len == buf.size()) buf.resize(buf.size() * 2);
+			const int n = gzread(f, buf.data() + len, (unsigned)(buf.size() - len));
+			if (n <= 0) { eof = true; break; }
+			len += (size_t)n;
 		}
+		return nl == 1 || nl == 2;
+	}
+	int getc_() {
+		if (pos >= len && !refill()) return -1;
 		return (unsigned char)buf[pos++];
 	}
 	int peek_() { int c = getc_(); if (c >= 0) pos--; return c; }
@@ -250,11 +282,17 @@ struct Reader {
 	bool getline_(std::string &s) {   /* returns false at EOF with nothing read; strips \n, keeps \r handling to callers */
 		s.clear();
 		line_hit_eof = false;
-		int c = getc_();
-		if (c < 0) { line_hit_eof = true; return false; }
-		while (c >= 0 && c != '\n') { s.push_back((char)c); c = getc_(); }
-		if (c < 0) line_hit_eof = true;
-		return true;
+		if (pos >= len && !refill()) { line_hit_eof = true; return false; }
+		for (;;) {                      /* whole spans at a time: memchr for the newline, append, refill when the buffer runs out */
+			const char *b = buf.data() + pos;
+			const char *nl = (const char *)memchr(b, '\n', len - pos);
+			if (nl) { s.append(b, (size_t)(nl - b)); pos += (size_t)(nl - b) + 1; return true; }
+			s.append(b, len - pos); pos = len;
+			if (!refill()) { line_hit_eof = true; return true; }
+		}
+	}
+	static void wrong_quality_format(const std::string &name) {        /* wrongQualityFormat, pat.cpp:1215-1220 */
+		die("Encountered a space parsing the quality string for read " + name + "\nIf this is a FASTQ file with integer (non-ASCII-encoded) qualities, please\nre-run Bowtie with the --integer-quals option.");
 	}
 	char to_phred33(int c, const std::string &name) const {
 		if (c == ' ') die("Saw a space but expected an ASCII-encoded quality value.\nAre quality values formatted as integers?  If so, try --integer-quals.");
@@ -271,15 +309,128 @@ struct Reader {
 	}
 	void finish_seq(ReadRec &r, const std::string &raw, int &trimmed5, int &trimmed3) const {
 		int nchar = 0;
-		r.seq.clear();
-		for (char ch : raw) {
-			int c = (unsigned char)ch;
-			if (c == '.') c = 'N';
-			if (isalpha(c)) { if (nchar++ >= o.trim5) r.seq.push_back((char)asc2dna[c]); }
+		r.seq.resize(raw.size());
+		size_t k = 0;
+		for (char ch : raw) {                                                /* alpha_code: letters and '.' -> base code, everything else skipped */
+			const uint8_t code = alpha_code[(unsigned char)ch];
+			if (code != 255) { if (nchar++ >= o.trim5) r.seq[k++] = (char)code; }
 		}
+		r.seq.resize(k);
 		trimmed5 = nchar - (int)r.seq.size();
 		trimmed3 = std::min<int>(o.trim3, (int)r.seq.size());
 		r.seq.resize(r.seq.size() - (size_t)trimmed3);
+	}
+	/* Fast path for the common case — well-formed 4-line FASTQ records, Phred+33, no trimming: the records that are complete
+	 * in the current buffer are located with memchr and parsed by `nth` threads; anything unusual (blank lines, CR, a quality
+	 * character below '!', lengths that disagree, a record that straddles the buffer) ends the run before that record and is
+	 * left to next(), whose behaviour — including the reference's error messages — is the specification. */
+	struct FqSpan { size_t l1, n1, l2, n2, l4, n4, end; };
+	std::vector<FqSpan> spans_;
+	bool fast_ok() const { return o.format == FASTQ && f && !first && !keepOrig && o.trim5 == 0 && o.trim3 == 0 && !o.solexaQuals && !o.phred64Quals; }
+	size_t fast_batch(std::vector<ReadRec> &recs, std::vector<uint32_t> &seeds, size_t maxRecs, size_t nth, uint32_t gseed) {
+		std::vector<FqSpan> &spans = spans_;        /* (a member: worker threads must see this thread's list) */
+		spans.clear();
+		const char *base = buf.data();
+		size_t p = pos;
+		while (spans.size() < maxRecs && p < len) {
+			FqSpan sp; size_t q = p;
+			if (base[q] != '@') break;
+			const char *nl = (const char *)memchr(base + q, '\n', len - q); if (!nl) break;
+			sp.l1 = q + 1; sp.n1 = (size_t)(nl - base) - q - 1; q = (size_t)(nl - base) + 1;
+			nl = (const char *)memchr(base + q, '\n', len - q); if (!nl) break;
+			sp.l2 = q; sp.n2 = (size_t)(nl - base) - q; q = (size_t)(nl - base) + 1;
+			if (q >= len || base[q] != '+') break;
+			nl = (const char *)memchr(base + q, '\n', len - q); if (!nl) break;
+			q = (size_t)(nl - base) + 1;
+			nl = (const char *)memchr(base + q, '\n', len - q); if (!nl) break;
+			sp.l4 = q; sp.n4 = (size_t)(nl - base) - q; q = (size_t)(nl - base) + 1;
+			if (sp.n4 == 0 || sp.n2 == 0 || base[sp.l1 + sp.n1 - (sp.n1 ? 1 : 0)] == '\r' || base[sp.l2 + sp.n2 - 1] == '\r' || base[sp.l4 + sp.n4 - 1] == '\r') break;
+			sp.end = q;
+			spans.push_back(sp);
+			p = q;
+		}
+		if (!spans.empty()) {                       /* the last record is next()'s unless three more newlines are in sight (tail_aborts) */
+			size_t q = p; int nl = 0;
+			while (nl < 3) { const char *e = (const char *)memchr(base + q, '\n', len - q); if (!e) break; nl++; q = (size_t)(e - base) + 1; }
+			if (nl < 3) spans.pop_back();
+		}
+		const size_t n = spans.size();
+		if (n == 0) return 0;
+		const size_t r0 = recs.size();
+		recs.resize(r0 + n); seeds.resize(r0 + n);
+		std::vector<uint8_t> okv(n, 1);
+		if (nth > n / 2048 + 1) nth = n / 2048 + 1;
+		const uint64_t id0 = rdid;
+		auto work = [&](size_t lo, size_t hi) {
+			for (size_t k = lo; k < hi; k++) {
+				const FqSpan &sp = spans[k];
+				ReadRec &r = recs[r0 + k];
+				if (sp.n1) r.name.assign(base + sp.l1, sp.n1); else r.name = std::to_string(id0 + k);
+				r.seq.resize(sp.n2);
+				size_t m = 0;
+				for (size_t i = 0; i < sp.n2; i++) { const uint8_t code = alpha_code[(unsigned char)base[sp.l2 + i]]; if (code != 255) r.seq[m++] = (char)code; }
+				r.seq.resize(m);
+				bool ok = (m == sp.n4) && m == sp.n2 && (sp.n1 == 0 || !memchr(base + sp.l1, '\r', sp.n1));
+				for (size_t i = 0; ok && i < sp.n4; i++) if ((unsigned char)base[sp.l4 + i] < 33) ok = false;
+				if (!ok) { okv[k] = 0; continue; }
+				r.qual.assign(base + sp.l4, sp.n4);
+				r.orig.clear();
+				seeds[r0 + k] = gen_rand_seed(r, gseed);
+			}
+		};
+		if (nth <= 1) work(0, n);
+		else {
+			std::vector<std::thread> th;
+			for (size_t t = 0; t < nth; t++) th.emplace_back(work, n * t / nth, n * (t + 1) / nth);
+			for (auto &x : th) x.join();
+		}
+		size_t good = 0;
+		while (good < n && okv[good]) good++;
+		recs.resize(r0 + good); seeds.resize(r0 + good);
+		pos = good ? spans[good - 1].end : pos;
+		rdid += good;
+		return good;
+	}
+	/* FastqPatternSource::parse (pat.cpp:858-975) works on the characters of the 4-newline chunk, not on lines: the first character
+	 * is skipped whatever it is, the name ends at the first CR/LF and every CR/LF after it is skipped, the sequence is every letter
+	 * or '.' up to the first '+', the rest of the '+' line and the line breaks after it are skipped, and the qualities run to the
+	 * next CR/LF — the first quality character is converted unconditionally, which is what turns a misplaced blank line into
+	 * "Saw ASCII character 10".  Reads past the end of the chunk (undefined in the reference) see '\n' here. */
+	std::string chunk;
+	void parse_fastq_chunk(const std::string &ck, ReadRec &r) const {
+		const size_t n = ck.size(); size_t cur = 1;
+		auto get = [&]() -> int { return cur < n ? (unsigned char)ck[cur++] : (cur++, (int)'\n'); };
+		int c;
+		r.name.clear(); r.seq.clear(); r.qual.clear();
+		for (;;) {
+			c = get();
+			if (c == '\n' || c == '\r') { do { c = get(); } while ((c == '\n' || c == '\r') && cur <= n); break; }
+			r.name.push_back((char)c);
+		}
+		int nchar = 0;
+		while (c != '+' && cur < n) {
+			const uint8_t code = alpha_code[c];
+			if (code != 255) { if (nchar++ >= o.trim5) r.seq.push_back((char)code); }
+			c = get();
+		}
+		const int trimmed5 = nchar - (int)r.seq.size();
+		const int trimmed3 = std::min<int>(o.trim3, (int)r.seq.size());
+		r.seq.resize(r.seq.size() - (size_t)trimmed3);
+		do { c = get(); } while (c != '\n' && c != '\r');
+		while (cur < n && (c == '\n' || c == '\r')) c = get();
+		int nqual = 0;
+		char pc = to_phred33(c, r.name);
+		if (nqual++ >= trimmed5) r.qual.push_back(pc);
+		while (cur < n) {
+			c = get();
+			if (c == '\r' || c == '\n') break;
+			if (c == ' ') wrong_quality_format(r.name);
+			pc = to_phred33(c, r.name);
+			if (nqual++ >= trimmed5) r.qual.push_back(pc);
+		}
+		r.qual.resize(r.qual.size() - std::min<size_t>((size_t)trimmed3, r.qual.size()));
+		if (r.qual.size() < r.seq.size()) die("Too few quality values for read: " + r.name + "\n\tare you sure this is a FASTQ-int file?");
+		if (r.qual.size() > r.seq.size()) die("Reads file contained a pattern with more than 1024 quality values.\nPlease truncate reads and quality values and and re-run Bowtie");
 	}
 	/* TabbedPatternSource (pat.cpp:980-1124), --12: name <tab> seq <tab> quals [<tab> seq2 <tab> quals2] per line */
 	bool next_tab(ReadRec &a, ReadRec &b, bool &isPair) {
@@ -292,7 +443,7 @@ struct Reader {
 			std::vector<std::string> fld; size_t p0 = 0;
 			for (;;) { size_t t = line.find('\t', p0); if (t == std::string::npos) { fld.push_back(line.substr(p0)); break; } fld.push_back(line.substr(p0, t - p0)); p0 = t + 1; }
 			rdid++;
-			a.orig = line; a.orig += '\n'; b.orig.clear();
+			if (keepOrig) { a.orig = line; a.orig += '\n'; b.orig.clear(); }
 			if (fld.size() < 3) continue;                                    /* "record ended prematurely": the read is skipped */
 			isPair = fld.size() >= 5;
 			for (int e = 0; e < (isPair ? 2 : 1); e++) {
@@ -304,9 +455,9 @@ struct Reader {
 				const size_t t3 = std::min<size_t>((size_t)o.trim3, r.seq.size());
 				r.seq.resize(r.seq.size() - t3);
 				r.qual.clear(); int nqual = 0;
-				for (char ch : ql) { char pc = to_phred33((unsigned char)ch, r.name); if (++nqual > o.trim5) r.qual.push_back(pc); }
-				if (nchar > nqual) die("Error: Read " + r.name + " has more read characters than quality values.");
-				if (nqual > nchar) die("Error: Read " + r.name + " has more quality values than read characters.");
+				for (char ch : ql) { if (ch == ' ') wrong_quality_format(r.name); char pc = to_phred33((unsigned char)ch, r.name); if (++nqual > o.trim5) r.qual.push_back(pc); }
+				if (nchar > nqual) die("Too few quality values for read: " + r.name + "\n\tare you sure this is a FASTQ-int file?");
+				if (nqual > nchar) die("Reads file contained a pattern with more than 1024 quality values.\nPlease truncate reads and quality values and and re-run Bowtie");
 				r.qual.resize(r.qual.size() - std::min<size_t>((size_t)o.trim3, r.qual.size()));
 			}
 			return true;
@@ -315,74 +466,127 @@ struct Reader {
 	/* Returns false when all input is consumed. */
 	bool next(ReadRec &r) {
 		if (o.format == CMDLINE) {
-			/* VectorPatternSource (pat.cpp:437-523): names are the ordinal, qualities 'I' */
-			if (cmdIdx >= files.size()) return false;
-			std::string s = files[cmdIdx++];
-			std::string q;
-			size_t colon = s.find(':');
-			if (colon != std::string::npos) { q = s.substr(colon + 1); s = s.substr(0, colon); }
-			int t5, t3; finish_seq(r, s, t5, t3);
-			if (q.empty()) r.qual.assign(r.seq.size(), 'I');
-			else { r.qual.clear(); int nq = 0; for (char ch : q) { if (++nq > o.trim5) r.qual.push_back(to_phred33((unsigned char)ch, r.name)); } r.qual.resize(r.seq.size()); }
-			r.name = std::to_string(rdid);
-			rdid++;
-			return true;
+			/* VectorPatternSource (pat.cpp:357-523): "seq[:quals]" becomes the tabbed record "<ordinal> TAB seq TAB quals" — quals
+			 * default to one 'I' per character of seq — and is parsed like one: letters only, plain Phred+33, counts must agree */
+			for (;;) {
+				if (cmdIdx >= files.size()) return false;
+				const std::string &tok = files[cmdIdx++];
+				const size_t colon = tok.find(':');
+				const std::string s = tok.substr(0, colon);
+				const std::string q = (colon == std::string::npos || colon + 1 >= tok.size()) ? std::string(s.size(), 'I') : tok.substr(colon + 1);   /* tokenize() drops an empty second token */
+				r.name = std::to_string(rdid);
+				rdid++;
+				if (q.empty()) continue;                                         /* "record ended prematurely": skipped, but it has used its id */
+				int nchar = 0, nqual = 0;
+				r.seq.clear(); r.qual.clear();
+				for (char ch : s) if (isalpha((unsigned char)ch)) { if (nchar++ >= o.trim5) r.seq.push_back((char)asc2dna[(unsigned char)ch]); }
+				r.seq.resize(r.seq.size() - std::min<size_t>((size_t)o.trim3, r.seq.size()));
+				for (char ch : q) {
+					if (ch == '\t' || ch == '\n' || ch == '\r') break;
+					if (ch == ' ') wrong_quality_format(r.name);
+					if ((unsigned char)ch < 33) die("Saw ASCII character " + std::to_string((int)(unsigned char)ch) + " but expected 33-based Phred qual.");
+					if (++nqual > o.trim5) r.qual.push_back(ch);
+				}
+				if (nchar > nqual) die("Too few quality values for read: " + r.name + "\n\tare you sure this is a FASTQ-int file?");
+				if (nqual > nchar) die("Reads file contained a pattern with more than 1024 quality values.\nPlease truncate reads and quality values and and re-run Bowtie");
+				r.qual.resize(r.qual.size() - std::min<size_t>((size_t)o.trim3, r.qual.size()));
+				return true;
+			}
 		}
 		for (;;) {
 			if (!f && !open_next()) return false;
-			std::string l1, l2, l3, l4;
 			if (o.format == FASTQ) {
 				/* FastqPatternSource (pat.cpp:797-975) */
-				if (first) { int c = peek_(); while (c == '\r' || c == '\n') { getc_(); c = peek_(); } if (c < 0) { gzclose(f); f = NULL; continue; }
-					if (c != '@') die("Error: reads file does not look like a FASTQ file");
+				if (first) { int c = peek_(); while (c == '\r' || c == '\n') { getc_(); c = peek_(); }
+					if (c != '@') die("Error: reads file does not look like a FASTQ file");          /* an empty file too (pat.cpp:805-812) */
 					first = false; }
-				if (!getline_(l1)) { gzclose(f); f = NULL; continue; }
-				if (l1.empty()) continue;
-				if (!getline_(l2) || !getline_(l3)) { gzclose(f); f = NULL; continue; }
-				getline_(l4);
-				r.orig = l1; r.orig += '\n'; r.orig += l2; r.orig += '\n'; r.orig += l3; r.orig += '\n'; r.orig += l4; r.orig += '\n';   /* pat.cpp:818-839 */
-				while (!l1.empty() && l1.back() == '\r') l1.pop_back();
-				while (!l4.empty() && l4.back() == '\r') l4.pop_back();
-				r.name = l1.substr(1);
-				int t5, t3; finish_seq(r, l2, t5, t3);
-				if (l4.empty()) die("Saw ASCII character 10 but expected 33-based Phred qual.");   /* pat.cpp:926: the first quality character is converted unconditionally */
-				r.qual.clear();
-				int nq = 0;
-				for (char ch : l4) { char pc = to_phred33((unsigned char)ch, r.name); if (nq++ >= t5) r.qual.push_back(pc); }
-				if ((int)r.qual.size() >= t3) r.qual.resize(r.qual.size() - (size_t)t3);
-				if (r.qual.size() < r.seq.size()) die("Error: Read " + r.name + " has more read characters than quality values.");
-				if (r.qual.size() > r.seq.size()) die("Error: Read " + r.name + " has more quality values than read characters.");
+				/* light parse (nextBatchFromFile): a record is whatever lies up to the fourth newline; EOF stands in for the last
+				 * newline, and a record cut short earlier is dropped */
+				chunk.clear();
+				bool counted = false, aborted = false;
+				for (int idx = 0; idx < 4; idx++) {
+					if (!getline_(l1)) { if (idx == 3) { chunk += '\n'; counted = true; } else aborted = idx > 0; break; }
+					chunk += l1;
+					if (line_hit_eof) { if (idx == 3) { chunk += '\n'; counted = true; } else aborted = idx > 0; break; }
+					chunk += '\n';
+					if (idx == 3) counted = true;
+				}
+				/* an incomplete record in the first slot of a light-parse batch: the reference's count goes to -1 and it parses the
+				 * slot's leftovers, which ends in this message */
+				if (aborted && (rdid & 15) == 0) die("Saw ASCII character 10 but expected 33-based Phred qual.");
+				if (!counted) { gzclose(f); f = NULL; continue; }
+				/* a file that ends inside a record — one or two newlines after this one, a stray blank line included — makes
+				 * nextBatchFromFile step its read count back (pat.cpp:853-855), which discards the record BEFORE the incomplete one
+				 * unless that one closed a light-parse batch of 16 */
+				if ((rdid & 15) != 15 && tail_aborts()) { gzclose(f); f = NULL; continue; }
+				parse_fastq_chunk(chunk, r);
+				if (keepOrig) r.orig = chunk;                                       /* Read::readOrigBuf */
 			} else if (o.format == FASTA) {
-				/* FastaPatternSource (pat.cpp:531-640): header line, then the first sequence line */
-				if (first) { int c = peek_(); while (c == '\r' || c == '\n') { getc_(); c = peek_(); } if (c < 0) { gzclose(f); f = NULL; continue; }
+				/* FastaPatternSource (pat.cpp:531-640).  Light parse: a record is '>' plus everything up to the next '>' — wherever
+				 * that is — or EOF.  parse(): the name ends at the first CR/LF, line breaks after it are skipped, the sequence is the
+				 * letters and '.' of the next line only, and a record with nothing after its name is skipped (it keeps its id). */
+				if (first) {
+					int c = getc_();
+					if (c < 0) { gzclose(f); f = NULL; continue; }                     /* empty file: no reads, no error */
+					while (c == '\r' || c == '\n') c = getc_();
 					if (c != '>') die("Error: reads file does not look like a FASTA file");
-					first = false; }
-				if (!getline_(l1)) { gzclose(f); f = NULL; continue; }
-				if (l1.empty() || l1[0] != '>') continue;
-				while (!l1.empty() && l1.back() == '\r') l1.pop_back();
-				r.name = l1.substr(1);
-				int c = peek_();
-				while (c == '\r' || c == '\n') { getc_(); c = peek_(); }
-				if (c < 0 || c == '>') { if (c < 0) { gzclose(f); f = NULL; } continue; }      /* FASTA ended prematurely */
-				getline_(l2);
-				r.orig = l1; r.orig += '\n'; r.orig += l2; r.orig += '\n';      /* header and first sequence line */
-				/* FastaPatternSource::parse stops at `cur < buflen` before it appends the character it just fetched
-				 * (pat.cpp:607-619): a sequence line that ends at EOF without a newline loses its last character */
-				if (line_hit_eof && !l2.empty()) l2.pop_back();
-				int t5, t3; finish_seq(r, l2, t5, t3);
+					first = false; recEof = false;
+				} else if (recEof) { gzclose(f); f = NULL; continue; }
+				chunk.assign(1, '>');
+				for (;;) {
+					if (pos >= len && !refill()) { recEof = true; break; }
+					const char *b0 = buf.data() + pos;
+					const char *g = (const char *)memchr(b0, '>', len - pos);
+					if (g) { chunk.append(b0, (size_t)(g - b0)); pos += (size_t)(g - b0) + 1; break; }
+					chunk.append(b0, len - pos); pos = len;
+				}
+				if (recEof && chunk.size() == 1) { gzclose(f); f = NULL; continue; }   /* "immediate EOF case" */
+				const size_t n = chunk.size(); size_t cur = 1; int c = -1;
+				r.name.clear(); r.seq.clear();
+				while (cur < n) {
+					c = (unsigned char)chunk[cur++];
+					if (c == '\n' || c == '\r') {
+						do { c = cur < n ? (unsigned char)chunk[cur] : 0; cur++; } while ((c == '\n' || c == '\r') && cur < n);
+						break;
+					}
+					r.name.push_back((char)c);
+				}
+				if (cur >= n) { rdid++; continue; }                                    /* "FASTA ended prematurely" */
+				int nchar = 0;
+				/* the loop tests `cur < buflen` before it takes the character it fetched last: a sequence line that ends at EOF
+				 * without a newline loses its last character (pat.cpp:607-619) */
+				while (c != '\n' && cur < n) {
+					const uint8_t code = alpha_code[c];
+					if (code != 255) { if (nchar++ >= o.trim5) r.seq.push_back((char)code); }
+					c = (unsigned char)chunk[cur++];
+				}
+				r.seq.resize(r.seq.size() - std::min<size_t>((size_t)o.trim3, r.seq.size()));
 				r.qual.assign(r.seq.size(), 'I');
-				/* skip continuation lines up to the next record */
-				c = peek_();
-				while (c >= 0 && c != '>') { getline_(l3); c = peek_(); }
+				if (keepOrig) r.orig = chunk;
 			} else {
-				/* RawPatternSource (pat.cpp:1129-1213): one sequence per line, name = ordinal */
-				if (!getline_(l1)) { gzclose(f); f = NULL; continue; }
-				bool any = false; for (char ch : l1) if (isalpha((unsigned char)ch)) any = true;
-				if (!any) continue;
-				int t5, t3; finish_seq(r, l1, t5, t3);
+				/* RawPatternSource (pat.cpp:1129-1213): a record is a non-empty run of characters between CR/LFs — a line without a
+				 * single letter is an empty read, not a skipped one — letters only ('.' is not N here), name = ordinal */
+				if (rawQ >= rawPieces.size()) {
+					rawPieces.clear(); rawQ = 0;
+					if (!getline_(l1)) { gzclose(f); f = NULL; continue; }
+					size_t p0 = 0;
+					for (;;) {
+						const size_t e = l1.find('\r', p0);
+						const size_t stop = e == std::string::npos ? l1.size() : e;
+						if (stop > p0) rawPieces.push_back(l1.substr(p0, stop - p0));
+						if (e == std::string::npos) break;
+						p0 = e + 1;
+					}
+					if (rawPieces.empty()) continue;
+				}
+				const std::string &pc = rawPieces[rawQ++];
+				int nchar = 0;
+				r.seq.clear();
+				for (char ch : pc) if (isalpha((unsigned char)ch)) { if (nchar++ >= o.trim5) r.seq.push_back((char)asc2dna[(unsigned char)ch]); }
+				r.seq.resize(r.seq.size() - std::min<size_t>((size_t)o.trim3, r.seq.size()));
 				r.qual.assign(r.seq.size(), 'I');
 				r.name.clear();
-				r.orig = l1; r.orig += '\n';
+				if (keepOrig) { r.orig = pc; r.orig += '\n'; }
 			}
 			if (r.name.empty()) r.name = std::to_string(rdid);
 			rdid++;
@@ -548,6 +752,8 @@ struct Batch {
 int main(int argc, char **argv) {
 	for (int i = 0; i < 256; i++) asc2dna[i] = 4;
 	asc2dna['A'] = asc2dna['a'] = 0; asc2dna['C'] = asc2dna['c'] = 1; asc2dna['G'] = asc2dna['g'] = 2; asc2dna['T'] = asc2dna['t'] = 3;
+	for (int i = 0; i < 256; i++) alpha_code[i] = isalpha(i) ? asc2dna[i] : 255;
+	alpha_code['.'] = 4;
 	Opts op;
 	parse_options(argc, argv, op);
 	auto t_start = std::chrono::steady_clock::now();
@@ -585,13 +791,15 @@ int main(int argc, char **argv) {
 	if (op.sam && !op.samNoHead) sam_headers(out.buf, op, ix, info.n_refs);
 
 	Reader rd(op, tabbed ? op.tabbed : interleaved ? op.interleaved : pairedInput ? op.mates1 : op.queries), rd2(op, op.mates2);
-	Batch bt[2];
+	enum { NB = 3 };                                                              /* one batch being parsed, one on the GPU, one being formatted */
+	Batch bt[NB];
 	const uint32_t nlim = op.allHits ? 0xffffffffu : op.khits;
 	for (auto &b : bt) {
 		if (bt_context_create(ix, &b.cx)) die(std::string("Error: ") + bt_last_error());
 		b.mm_cap = op.maqLike ? 10 : (uint32_t)std::max(1, op.mismatches);
 	}
 	uint64_t numAligned = 0, numUnaligned = 0, numMaxed = 0, numReported = 0, numReportedPaired = 0;
+	const size_t fmtThreads = op.nthreads > 1 ? (size_t)op.nthreads : std::max<size_t>(1, std::min<size_t>(16, std::thread::hardware_concurrency() / 2));   /* -p: host threads that format output */
 	/* HitSink::dumpAlign / dumpUnal / dumpMaxed (hit.h:385-492): files are opened when the first read lands in them; pairs go to
 	 * <base>_1.<ext> / <base>_2.<ext> (openOf, hit.h:629-660); maxed reads fall back to --un when --max is not given */
 	std::map<std::string, FILE *> dumps;
@@ -615,6 +823,24 @@ int main(int argc, char **argv) {
 		if (n < 2 || name[n - 2] != '/' || name[n - 1] != "012"[i]) { name += '/'; name += "012"[i]; }
 	};
 
+	/* What the workers say about reads too short to search (the search itself leaves them unaligned): search_1mm_phase1.c:12-15,
+	 * search_23mm_phase1.c:13-20, search_seeded_phase1.c:17-21, aligner.h:440-448,744-751 */
+	const bool statefulU = polU.best || polU.strata || polU.sample_max || (!op.maqLike && op.mismatches == 3);
+	auto short_read_check = [&](const ReadRec &a, const ReadRec *mate) {
+		const size_t la = a.seq.size();
+		if (mate) {
+			if ((la < 4 || mate->seq.size() < 4) && !op.quiet) fprintf(stderr, "Warning: Skipping pair %s because a mate is less than 4 characters long\n", a.name.c_str());
+		} else if (statefulU) {
+			if (la < 4 && !op.quiet) fprintf(stderr, "Warning: Skipping read %s because it is less than 4 characters long\n", a.name.c_str());
+		} else if (op.maqLike) {
+			if (la < 4 && !op.quiet) fprintf(stderr, "Warning: Skipping read (%s) because it is less than 4 characters long\n", a.name.c_str());
+		} else if (op.mismatches == 1) {
+			if (la < 2) die("Error: Reads must be at least 2 characters long in 1-mismatch mode");
+		} else if (op.mismatches == 2) {
+			if (la < 3) die("Error: Read (" + a.name + ") is less than 3 characters long");
+			if (la < 4) die("Error: Read (" + a.name + ") is less than 4 characters long");
+		}
+	};
 	auto fill = [&](Batch &b) {
 		b.reads.clear(); b.seq.clear(); b.qual.clear(); b.offs.assign(1, 0); b.seeds.clear();
 		b.paired = pairedInput;
@@ -630,19 +856,35 @@ int main(int argc, char **argv) {
 				rec = lrec; rec2 = lrec2; paired = lookPair; haveLook = false;
 			} else {
 				if (rd.rdid >= op.qUpto) { input_done = true; break; }
+				if (!pairedInput && rd.fast_ok() && rd.rdid >= op.skipReads) {
+					/* plain single-end FASTQ: whole runs of records at a time, parsed by several threads (Reader::fast_batch) */
+					const size_t r0 = b.reads.size();
+					const size_t want = std::min<size_t>((size_t)op.batch - r0, (size_t)(op.qUpto - rd.rdid));
+					if (rd.fast_batch(b.reads, b.seeds, want, fmtThreads, op.seed) > 0) {
+						for (size_t k = r0; k < b.reads.size(); k++) {
+							const ReadRec &rr = b.reads[k];
+							if (rr.seq.size() < 4) short_read_check(rr, NULL);
+							b.seq.insert(b.seq.end(), rr.seq.begin(), rr.seq.end());
+							b.qual.insert(b.qual.end(), rr.qual.begin(), rr.qual.end());
+							b.offs.push_back(b.seq.size());
+						}
+						continue;
+					}
+				}
 				if (!rd.next(rec)) { input_done = true; break; }
 				if (interleaved) { if (!rd.next(rec2)) die("Error: odd number of reads in an --interleaved file"); rd.rdid--; }   /* a pair is one read id */
 				else if (paired && !rd2.next(rec2)) die("Error, fewer reads in file specified with -2 than in file specified with -1");
 			}
 			if (rd.rdid - 1 < op.skipReads) continue;                              /* -s: skipped reads are not counted */
+			if (paired) { fix_mate_name(rec.name, 1); fix_mate_name(rec2.name, 2); }   /* PatternSourcePerThread::finalizePair (pat.cpp:75-87) */
+			if (rec.seq.size() < 4 || (paired && rec2.seq.size() < 4)) short_read_check(rec, paired ? &rec2 : NULL);
 			for (int m = 0; m < (paired ? 2 : 1); m++) {
 				ReadRec &rr = m ? rec2 : rec;
-				if (paired) fix_mate_name(rr.name, m + 1);                         /* PatternSourcePerThread::finalizePair (pat.cpp:75-87) */
 				b.seq.insert(b.seq.end(), rr.seq.begin(), rr.seq.end());
 				b.qual.insert(b.qual.end(), rr.qual.begin(), rr.qual.end());
 				b.offs.push_back(b.seq.size());
 				b.seeds.push_back(gen_rand_seed(rr, op.seed));
-				b.reads.push_back(rr);
+				b.reads.push_back(std::move(rr));
 			}
 		}
 	};
@@ -653,7 +895,7 @@ int main(int argc, char **argv) {
 		b.slots = op.allHits ? 8 : op.khits * mult;
 		if (op.sampleMax && op.mhits != 0xffffffffu) b.slots = std::max(b.slots, op.mhits * mult);   /* -M keeps every hit up to the ceiling */
 		const size_t n = b.reads.size() / mult, rw = BT_HIT_HDR_WORDS + b.mm_cap;
-		b.found.assign(n, 0); b.flags.assign(n, 0); b.hits.assign(n * b.slots * rw, 0);
+		b.found.resize(n); b.flags.resize(n); b.hits.resize(n * b.slots * rw);    /* the library overwrites every entry it is asked for */
 		bt_read_batch_t in; memset(&in, 0, sizeof in);
 		in.nreads = (uint32_t)b.reads.size(); in.seq = b.seq.data(); in.qual = b.qual.data(); in.offs = b.offs.data(); in.seeds = b.seeds.data();
 		bt_hit_batch_t ho = { b.found.data(), b.flags.data(), b.hits.data(), b.slots, b.mm_cap };
@@ -716,16 +958,18 @@ int main(int argc, char **argv) {
 				g0 = g1;
 			}
 		}
-		size_t ni = 0;
-		for (size_t i = 0; i < n; i++) {
+		/* formats the units [lo, hi) into `obuf`; cnt = { aligned, unaligned, maxed, reported, reportedPaired } */
+		auto emit_range = [&](size_t lo, size_t hi, std::string &obuf, uint64_t cnt[5], bool serial) {
+		size_t ni = (size_t)(std::lower_bound(need.begin(), need.end(), (uint32_t)lo) - need.begin());
+		for (size_t i = lo; i < hi; i++) {
 			const ReadRec &r = b.reads[i * mult];
 			const uint32_t *recs = &b.hits[i * b.slots * rw]; size_t rwi = rw; uint32_t found = b.found[i];
 			if (ni < need.size() && need[ni] == i) { rwi = rw2[ni]; recs = hits2.data() + off2[ni]; found = found2[ni]; ni++; }
 			/* HitSinkPerThread::finishRead (hit.h:741-786) */
 			const bool maxed = found > mhitsU, unal = (found == 0);
 			if (maxed) {
-				numMaxed++;
-				dump_unit(op.dumpMax.empty() ? op.dumpUn : op.dumpMax, b, i);
+				cnt[2]++;
+				if (serial) dump_unit(op.dumpMax.empty() ? op.dumpUn : op.dumpMax, b, i);
 				if (op.sampleMax) {
 					/* VerboseHitSink::reportMaxed (hit.cpp:16-68) / SAMHitSink::reportMaxed (sam.cpp:263-311): one of the
 					 * buffered hits of the best stratum, picked with a fresh RandomSource seeded by the read */
@@ -738,8 +982,8 @@ int main(int argc, char **argv) {
 						for (uint32_t s = 1; s < nbuf; s++) { if (stratum_of(s) == stratum_of(s - 1)) num++; else break; }
 						const uint32_t *w = recs + (size_t)(rr % num) * rwi;
 						HitView h = { w[0], w[1], nbuf, w[3] & 0xffffu, (w[3] >> 16) & 0xff, (w[3] >> 24) & 1, w[4], w + BT_HIT_HDR_WORDS };
-						if (op.sam) append_sam(out.buf, op, ix, r, h, 0, (int)nbuf + 1); else append_default(out.buf, op, ix, r, h);
-						numAligned++; numReported++;
+						if (op.sam) append_sam(obuf, op, ix, r, h, 0, (int)nbuf + 1); else append_default(obuf, op, ix, r, h);
+						cnt[0]++; cnt[3]++;
 					} else {
 						/* pairs: among the couples whose better mate is in the best stratum (hit.cpp:28-54, sam.cpp:275-299) */
 						uint32_t bestS = 999, num = 0;
@@ -753,18 +997,18 @@ int main(int argc, char **argv) {
 								HitView h = { w[0], w[1], nbuf / 2, w[3] & 0xffffu, (w[3] >> 16) & 0xff, (w[3] >> 24) & 1, w[4], w + BT_HIT_HDR_WORDS };
 								h.mate = (w[3] >> 25) & 3; h.mtoff = mw[1]; h.mfw = (mw[3] >> 24) & 1; h.mlen = (uint32_t)b.reads[i * mult + (2 - h.mate)].seq.size();
 								const ReadRec &rr2 = b.reads[i * mult + (h.mate - 1)];
-								if (op.sam) append_sam(out.buf, op, ix, rr2, h, 0, (int)(nbuf / 2) + 1); else append_default(out.buf, op, ix, rr2, h);
+								if (op.sam) append_sam(obuf, op, ix, rr2, h, 0, (int)(nbuf / 2) + 1); else append_default(obuf, op, ix, rr2, h);
 							}
 							break;
 						}
-						numAligned++; numReportedPaired += 2;
+						cnt[0]++; cnt[4] += 2;
 					}
 				}
 			}
 			else if (unal) {
-				numUnaligned++;
-				dump_unit(op.dumpUn, b, i);
-				if (op.sam && !op.noUnal) { if (paired) { append_sam_unaligned(out.buf, op, r, 1); append_sam_unaligned(out.buf, op, b.reads[i * mult + 1], 2); } else append_sam_unaligned(out.buf, op, r); }
+				cnt[1]++;
+				if (serial) dump_unit(op.dumpUn, b, i);
+				if (op.sam && !op.noUnal) { if (paired) { append_sam_unaligned(obuf, op, r, 1); append_sam_unaligned(obuf, op, b.reads[i * mult + 1], 2); } else append_sam_unaligned(obuf, op, r); }
 			} else {
 				uint32_t nrep = std::min(found, nlimU);
 				for (uint32_t s = 0; s < nrep; s++) {
@@ -778,32 +1022,75 @@ int main(int argc, char **argv) {
 						rr = &b.reads[i * mult + (h.mate - 1)];
 						h.mtoff = mw[1]; h.mfw = (mw[3] >> 24) & 1; h.mlen = (uint32_t)b.reads[i * mult + (2 - h.mate)].seq.size();
 					}
-					if (op.sam) append_sam(out.buf, op, ix, *rr, h, op.defaultMapq, (int)(nrep / mult)); else append_default(out.buf, op, ix, *rr, h);
+					if (op.sam) append_sam(obuf, op, ix, *rr, h, op.defaultMapq, (int)(nrep / mult)); else append_default(obuf, op, ix, *rr, h);
 				}
-				numAligned++; if (paired) numReportedPaired += nrep; else numReported += nrep;
-				dump_unit(op.dumpAl, b, i);
+				cnt[0]++; if (paired) cnt[4] += nrep; else cnt[3] += nrep;
+				if (serial) dump_unit(op.dumpAl, b, i);
 			}
-			out.maybe_flush();
+			if (serial) { out.buf.swap(obuf); out.maybe_flush(); out.buf.swap(obuf); }
 		}
+		};
+		/* the reference formats inside its -p worker threads; here the units of a batch are formatted by a few host threads into
+		 * private buffers that are written out in unit order (read dumps keep one thread: their files are shared) */
+		const bool dumping = !op.dumpAl.empty() || !op.dumpUn.empty() || !op.dumpMax.empty();
+		const size_t nth = (dumping || n < 16384) ? 1 : std::min<size_t>(fmtThreads, n / 4096);
+		uint64_t cnt[5] = { 0, 0, 0, 0, 0 };
+		if (nth <= 1) emit_range(0, n, out.buf, cnt, true);
+		else {
+			std::vector<std::string> bufs(nth); std::vector<std::array<uint64_t, 5>> cs(nth);
+			std::vector<std::thread> th;
+			for (size_t t = 0; t < nth; t++) th.emplace_back([&, t]() { cs[t].fill(0); emit_range(n * t / nth, n * (t + 1) / nth, bufs[t], cs[t].data(), false); });
+			for (auto &x : th) x.join();
+			for (size_t t = 0; t < nth; t++) { out.flush(); fwrite(bufs[t].data(), 1, bufs[t].size(), out.fp); for (int k = 0; k < 5; k++) cnt[k] += cs[t][k]; }
+		}
+		numAligned += cnt[0]; numUnaligned += cnt[1]; numMaxed += cnt[2]; numReported += cnt[3]; numReportedPaired += cnt[4];
 	};
 
-	/* double-buffered: the GPU works on one batch while the host parses the next and formats the previous */
-	int cur = 0;
-	fill(bt[cur]); launch(bt[cur]);
-	while (bt[cur].inflight) {
-		int nxt = cur ^ 1;
-		fill(bt[nxt]);
-		launch(bt[nxt]);
-		finish(bt[cur]);
-		cur = nxt;
+	/* Three batches in a ring: a parser thread fills batch k+1 while the GPU searches batch k and this thread formats batch k-1
+	 * (the reference parses and formats inside its -p worker threads; here the search needs no host thread at all). */
+	std::mutex mu; std::condition_variable cv;
+	bool filled[NB] = { false, false, false };
+	double t_fill = 0, t_launch = 0, t_finish = 0;                               /* BT_CLI_TIMING=1 prints where the host time goes */
+	std::thread parser([&]() {
+		for (size_t k = 0;; k++) {
+			Batch &b = bt[k % NB];
+			{ std::unique_lock<std::mutex> lk(mu); cv.wait(lk, [&] { return !filled[k % NB]; }); }
+			auto t0 = std::chrono::steady_clock::now();
+			fill(b);
+			t_fill += std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+			const bool end = b.reads.empty();
+			{ std::lock_guard<std::mutex> lk(mu); filled[k % NB] = true; }
+			cv.notify_all();
+			if (end) break;
+		}
+	});
+	int prev = -1;
+	for (size_t k = 0;; k++) {
+		Batch &b = bt[k % NB];
+		{ std::unique_lock<std::mutex> lk(mu); cv.wait(lk, [&] { return filled[k % NB]; }); }
+		if (b.reads.empty()) break;                                                /* end of input */
+		auto t0 = std::chrono::steady_clock::now();
+		launch(b);
+		auto t1 = std::chrono::steady_clock::now();
+		t_launch += std::chrono::duration<double>(t1 - t0).count();
+		if (prev >= 0) {
+			finish(bt[prev]);
+			t_finish += std::chrono::duration<double>(std::chrono::steady_clock::now() - t1).count();
+			{ std::lock_guard<std::mutex> lk(mu); filled[prev] = false; }
+			cv.notify_all();
+		}
+		prev = (int)(k % NB);
 	}
+	if (prev >= 0) { auto t1 = std::chrono::steady_clock::now(); finish(bt[prev]); t_finish += std::chrono::duration<double>(std::chrono::steady_clock::now() - t1).count(); }
+	parser.join();
+	if (getenv("BT_CLI_TIMING")) fprintf(stderr, "host pipeline: parse %.2f s (parser thread), launch %.2f s, sync+format %.2f s\n", t_fill, t_launch, t_finish);
 	out.flush();
 	if (out.fp != stdout) fclose(out.fp);
 	for (auto &kv : dumps) if (kv.second) fclose(kv.second);
 	auto t_end = std::chrono::steady_clock::now();
 
-	/* HitSink::finish (hit.h:270-346) */
-	if (!op.quiet) {
+	/* HitSink::finish (hit.h:270-346); the sink's quiet_ is never set (hit.h:160), so --quiet does not silence the summary */
+	{
 		const uint64_t alShown = numAligned + (op.sampleMax ? 0 : numMaxed);
 		uint64_t tot = alShown + numUnaligned;
 		double alPct = 0, unalPct = 0, maxPct = 0;

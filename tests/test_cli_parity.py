@@ -172,3 +172,50 @@ def test_cli_read_dumps(cli, tmp_path):
 @pytest.mark.gpu
 def test_cli_read_dumps_gpu(cli, tmp_path):
     check_dumps(cli, tmp_path, {k: v for k, v in os.environ.items() if k != "LD_LIBRARY_PATH"})
+
+
+def odd_fastq(path, n=9000):
+    """The e_coli reads repeated to `n` records (enough for the multi-threaded FASTQ path to split the work) with the oddities
+    FastqPatternSource tolerates (pat.cpp:797-975) sprinkled in: CRLF records, '.', '-', lower case,
+    an empty name, and a last record without a newline."""
+    import random
+    rng = random.Random(5)
+    lines = (FIXTURES / "e_coli_1000.fq").read_text().splitlines()
+    recs = [lines[i:i + 4] for i in range(0, len(lines), 4)]
+    out = []
+    for k in range(n):
+        name, seq, plus, qual = recs[k % len(recs)]
+        name = f"{name}_{k}"
+        what = rng.randrange(60)
+        if what == 0:
+            out.append("\r\n".join([name, seq, plus, qual]) + "\r\n")
+            continue
+        if what == 2:
+            seq = seq[:5] + "." + seq[6:]
+        elif what == 3:
+            seq = seq[:7] + "-" + seq[7:]
+        elif what == 4:
+            seq = seq.lower()
+        elif what == 5:
+            name = "@"
+        out.append("\n".join([name, seq, plus, qual]) + "\n")
+    out[-1] = out[-1].rstrip("\n")
+    Path(path).write_text("".join(out))
+
+
+@pytest.mark.parametrize("threads", ["1", "4"])
+def test_cli_fastq_fast_path_matches_reference(threads, cli, tmp_path):
+    """Reader::fast_batch (whole buffers of well-formed records, parsed by several threads) hands anything unusual to the
+    record-at-a-time parser; names, sequences, qualities, per-read seeds and the order must come out as the reference's."""
+    build_shim()
+    env = dict(os.environ, LD_LIBRARY_PATH=str(SHIM_DIR))
+    fq = tmp_path / "odd.fq"
+    odd_fastq(fq)
+    outs = []
+    for exe, extra, e in ((REF_ALIGN, ["-p", "1"], None), (cli, ["-p", threads, "--reads-per-batch", "4096"], env)):
+        out = tmp_path / f"{Path(exe).name}.out"
+        p = subprocess.run([str(exe), "-n", "2", "-k", "2", *extra, "-x", str(FIXTURES / "e_coli"), str(fq), str(out)], capture_output=True, text=True, env=e)
+        assert p.returncode == 0, p.stderr
+        outs.append((out.read_bytes(), [l for l in p.stderr.splitlines() if l.startswith("#") or l.startswith("Reported")]))
+    assert outs[0] == outs[1]
+    assert outs[0][0].count(b"\n") > 5000

@@ -1,0 +1,200 @@
+"""Read-input edge cases of the bowtie-compatible driver, checked against the reference binary on the same files.
+
+The reference's parsers (pat.cpp: FASTQ 797-975, FASTA 531-640, raw 1129-1213, -c 357-523) work on characters, not on lines,
+in two steps — a "light parse" that cuts the file into records and parse() that picks name/sequence/qualities out of a
+record — and the cases below are the places where that shows: blank lines, CRs, '>' or '+' in the wrong place, files that end
+inside a record (which also costs the reference the record BEFORE the incomplete one), records that close a light-parse batch
+of 16, reads too short to search.  Output, exit status and the messages on stderr must all match.  Host logic only (the search
+runs on the emulation shim), so this runs in the CPU suite.
+"""
+import os
+import subprocess
+from pathlib import Path
+
+import pytest
+
+from helpers import FIXTURES, REF_ALIGN, ROOT, ensure_oracle_built, have_reference
+from test_cli_parity import SHIM_DIR, build_shim
+
+CLI = ROOT / "bowtie_b200" / "bowtie-b200-align"
+
+
+@pytest.fixture(scope="module")
+def cli():
+    ensure_oracle_built()
+    if not have_reference():
+        pytest.skip("reference binary / fixtures not available")
+    import bowtie_b200
+    bowtie_b200.build_library()
+    build_shim()
+    return CLI
+
+
+def recs(n, start=0):
+    lines = (FIXTURES / "e_coli_1000.fq").read_text().splitlines()
+    return [lines[i:i + 4] for i in range(4 * start, 4 * (start + n), 4)]
+
+
+def both(cli, tmp_path, tag, flags, src):
+    """src: list of arguments naming the reads (files are created by the caller).  Returns nothing; asserts equality."""
+    env = dict(os.environ, LD_LIBRARY_PATH=str(SHIM_DIR))
+    res = []
+    for who, exe, extra, e in (("ref", REF_ALIGN, ["-p", "1"], None), ("our", cli, [], env)):
+        out = tmp_path / f"{tag}.{who}"
+        p = subprocess.run([str(exe), *flags, *extra, "-x", str(FIXTURES / "e_coli"), *src, str(out)], capture_output=True, text=True, env=e)
+        msgs = [l for l in p.stderr.splitlines() if not l.startswith("Command:")]
+        body = out.read_bytes() if p.returncode == 0 and out.exists() else b""
+        res.append((p.returncode, body, msgs))
+    assert res[0][0] in (0, 1), (tag, res[0])            # a reference crash is not a specification
+    assert res[0] == res[1], tag
+
+
+def fq(rs):
+    return "".join("\n".join(r) + "\n" for r in rs)
+
+
+def fa(rs):
+    return "".join(f">{r[0][1:]}\n{r[1]}\n" for r in rs)
+
+
+def raw(rs):
+    return "".join(r[1] + "\n" for r in rs)
+
+
+X = recs(1, 20)[0]          # a record to doctor
+
+
+def fastq_cases():
+    name, seq, plus, qual = X
+    one = lambda n_, s_, p_, q_: "\n".join([n_, s_, p_, q_]) + "\n"
+    for n in (3, 15, 16, 17, 32):
+        b = fq(recs(n))
+        yield f"ok{n}", b
+        yield f"nonl{n}", b.rstrip("\n")
+        yield f"trail1_{n}", b + "\n"
+        yield f"trail2_{n}", b + "\n\n"
+        yield f"trail3_{n}", b + "\n\n\n" if n != 3 else b          # (3 newlines: the reference reads stale bytes)
+        yield f"cut1_{n}", b + "@x\n"
+        yield f"cut2_{n}", b + "@x\nACGT\n"
+        yield f"cut0_{n}", b + "@x"
+        yield f"cut3_{n}", b + "@x\nACGTACGTACGTACGTACGTAACCGT\n+\n"
+    b = fq(recs(5))
+    yield "crlf", b + one(name, seq, plus, qual).replace("\n", "\r\n") + b
+    yield "blank", b + "\n" + b
+    yield "blankname", b + one(name + "\n", seq, plus, qual) + b
+    yield "seq2lines", b + one(name, seq[:10] + "\n" + seq[10:], plus, qual) + b
+    yield "dot", b + one(name, seq[:5] + "." + seq[6:], plus, qual) + b
+    yield "dash", b + one(name, seq[:7] + "-" + seq[7:], plus, qual) + b
+    yield "plusinseq", b + one(name, seq[:7] + "+" + seq[7:], plus, qual) + b
+    yield "lower", b + one(name, seq.lower(), plus, qual) + b
+    yield "noname", b + one("@", seq, plus, qual) + b
+    yield "crname", b + one(name[:3] + "\r" + name[3:], seq, plus, qual) + b
+    yield "space", b + one(name, seq, plus, qual[:4] + " " + qual[5:]) + b
+    yield "space0", b + one(name, seq, plus, " " + qual[1:]) + b
+    yield "shortq", b + one(name, seq, plus, qual[:-2]) + b
+    yield "longq", b + one(name, seq, plus, qual + "II") + b
+    yield "noat", b + one("X" + name[1:], seq, plus, qual) + b
+    yield "lowq", b + one(name, seq, plus, qual[:3] + "\x1f" + qual[4:]) + b
+    yield "plusname", b + one(name, seq, "+" + name[1:], qual) + b
+    yield "shortread", b + one(name, "ACG", plus, "III") + b
+    yield "emptyread", b + one(name, "", plus, "") + b
+    yield "empty", ""
+    yield "newline", "\n"
+    yield "notfastq", "ACGT\n"
+    yield "leading", "\n\r\n" + b
+
+
+def test_fastq_edge_cases(cli, tmp_path):
+    for tag, text in fastq_cases():
+        f = tmp_path / f"fq_{tag}.fq"
+        f.write_text(text)
+        both(cli, tmp_path, f"fq_{tag}", ["-n", "2"], ["-q", str(f)])
+    # trimming and quality encodings go through the same record parser
+    f = tmp_path / "fq_ok17.fq"
+    for i, flags in enumerate((["-5", "3", "-3", "2"], ["--phred64-quals"], ["--solexa-quals"], ["-5", "40"], ["-3", "33"])):
+        both(cli, tmp_path, f"fq_flags{i}", ["-n", "2", *flags], ["-q", str(f)])
+
+
+def fasta_cases():
+    name, seq = X[0][1:], X[1]
+    for n in (3, 16, 17):
+        b = fa(recs(n))
+        yield f"ok{n}", b
+        yield f"nonl{n}", b.rstrip("\n")                       # the last base is lost (pat.cpp:607-619)
+        yield f"trail{n}", b + "\n\n"
+        yield f"gt{n}", b + ">"
+        yield f"gtname{n}", b + ">x\n"
+        yield f"gtname_nonl{n}", b + ">x"
+        yield f"onebase{n}", b + ">x\nA"
+        yield f"multi{n}", f">m\n{seq[:20]}\n{seq[20:]}\n" + b   # only the first line is the read
+        yield f"blank{n}", f">m\n\n\n{seq}\n" + b
+        yield f"gtinname{n}", f">m>k\n{seq}\n" + b               # '>' ends a record wherever it is
+        yield f"noname{n}", f">\n{seq}\n" + b
+        yield f"crlf{n}", b.replace("\n", "\r\n")
+        yield f"dotdash{n}", f">m\n{seq[:5]}.-{seq[5:]}\n" + b
+        yield f"lead{n}", "\n\r\n" + b
+        yield f"emptyseq{n}", ">m\n>k\n" + b
+    yield "empty", ""
+    yield "newline", "\n"
+    yield "notfasta", "ACGT\n"
+
+
+def test_fasta_edge_cases(cli, tmp_path):
+    for tag, text in fasta_cases():
+        f = tmp_path / f"fa_{tag}.fa"
+        f.write_text(text)
+        both(cli, tmp_path, f"fa_{tag}", ["-n", "2"], ["-f", str(f)])
+    f = tmp_path / "fa_multi17.fa"
+    both(cli, tmp_path, "fa_dump", ["-n", "2", "--un", str(tmp_path / "fa_un.fa"), "--al", str(tmp_path / "fa_al.fa")], ["-f", str(f)])
+
+
+def raw_cases():
+    seq, seq2 = X[1], recs(1, 21)[0][1]
+    for n in (3, 16, 17):
+        b = raw(recs(n))
+        yield f"ok{n}", b
+        yield f"nonl{n}", b.rstrip("\n")
+        yield f"blank{n}", "\n\n" + b + "\n\n"
+        yield f"digits{n}", "12345\n" + b                      # an empty read, not a skipped line
+        yield f"dotdash{n}", f"{seq[:5]}.-{seq[5:]}\n" + b       # '.' is not N in this format
+        yield f"cr{n}", f"{seq}\r{seq2}\n" + b                   # a CR separates records too
+        yield f"crlf{n}", b.replace("\n", "\r\n")
+    yield "empty", ""
+
+
+def test_raw_edge_cases(cli, tmp_path):
+    for tag, text in raw_cases():
+        f = tmp_path / f"raw_{tag}.txt"
+        f.write_text(text)
+        both(cli, tmp_path, f"raw_{tag}", ["-n", "2"], ["-r", str(f)])
+
+
+def test_cmdline_reads_edge_cases(cli, tmp_path):
+    s0, q0 = X[1], X[3]
+    s1 = recs(1, 6)[0][1]
+    cases = [([s0], []), ([s0 + ":" + q0], []), ([s0 + ":" + q0[:-1]], []), ([s0 + ":" + q0 + "I"], []), ([s0[:5] + "." + s0[5:]], []), ([s0 + ":"], []),
+             ([s0, s1], []), ([s0 + ":" + q0.replace(q0[3], " ")], []), ([s0 + ":" + q0], ["--solexa-quals"]), ([s0], ["-5", "3", "-3", "2"]),
+             ([s0 + ":" + q0], ["-5", "3", "-3", "2"])]
+    for i, (toks, flags) in enumerate(cases):
+        both(cli, tmp_path, f"c_{i}", ["-n", "2", *flags], ["-c", ",".join(toks)])
+
+
+SHORT_MODES = [["-v", "0"], ["-v", "1"], ["-v", "2"], ["-v", "3"], ["-n", "0"], ["-n", "2"], ["-n", "3"], ["-n", "2", "--best"], ["-v", "1", "--best"],
+               ["-n", "2", "--quiet"], ["-v", "3", "--quiet"]]
+
+
+def test_reads_too_short_to_search(cli, tmp_path):
+    """search_1mm_phase1.c:12-15, search_23mm_phase1.c:13-20 (errors), search_seeded_phase1.c:17-21, aligner.h:440-448 (warnings); --quiet
+    silences the warnings but not the summary (hit.h:160)."""
+    good = X[1]
+    k = 0
+    for mode in SHORT_MODES:
+        for short in ("A", "AC", "ACG", "ACGT"):
+            for order in (short + "," + good, good + "," + short):
+                k += 1
+                both(cli, tmp_path, f"s_{k}", mode, ["-c", order])
+    m1, m2 = tmp_path / "sp_1.fq", tmp_path / "sp_2.fq"
+    r = recs(4)
+    m1.write_text(fq(r[:2]) + "@p\nACG\n+\nIII\n" + fq(r[2:]))
+    m2.write_text(fq(r[2:]) + "@p\nACGTACGTAGGCTAGCTAGGATCGATTTAGGCAT\n+\nIIIIIIIIIIIIIIIIIIIIIIIIIIIIIIIIII\n" + fq(r[:2]))
+    both(cli, tmp_path, "s_pair", ["-n", "2"], ["-1", str(m1), "-2", str(m2)])
