@@ -21,6 +21,7 @@
 #include <stdlib.h>
 #include <string.h>
 #include <zlib.h>
+#include <sys/stat.h>
 #include <algorithm>
 #include <chrono>
 #include <string>
@@ -33,7 +34,7 @@
 /* ---------------------------------------------------------------------------------------------- */
 /* options (names follow the reference's globals)                                                  */
 /* ---------------------------------------------------------------------------------------------- */
-enum { FASTQ = 1, FASTA, RAW, CMDLINE };
+enum { FASTQ = 1, FASTA, RAW, CMDLINE, FASTA_CONT };
 struct Opts {
 	int format = FASTQ;
 	std::string ebwtFile, outfile;
@@ -48,7 +49,10 @@ struct Opts {
 	uint32_t khits = 1, mhits = 0xffffffffu;
 	uint32_t skipReads = 0, qUpto = 0xffffffffu;
 	int trim3 = 0, trim5 = 0;
-	bool solexaQuals = false, phred64Quals = false;
+	bool solexaQuals = false, phred64Quals = false, integerQuals = false;
+	std::vector<std::string> qualities, qualities1, qualities2;   /* -Q / --Q1 / --Q2: opened and counted, never read (pat.cpp:333-348) */
+	size_t fastaContLen = 0, fastaContFreq = 0;            /* -F len,freq */
+	bool pev2 = false, reorder = false;
 	bool sam = false, samNoHead = false, samNoSQ = false, noUnal = false, fullRef = false, refIdx = false, printCost = false;
 	bool noQnameTrunc = false, quiet = false, timing = false;
 	std::string rgs;
@@ -66,10 +70,11 @@ enum {
 	ARG_PHRED33 = 256, ARG_PHRED64, ARG_SOLEXA, ARG_SOLEXA13, ARG_NOMAQROUND, ARG_NOFW, ARG_NORC, ARG_MAXBTS, ARG_BEST, ARG_STRATA,
 	ARG_QUIET, ARG_REFIDX, ARG_SUPPRESS, ARG_FULLREF, ARG_MAPQ, ARG_SAM_NOHEAD, ARG_SAM_NOSQ, ARG_SAM_RG, ARG_NO_UNAL, ARG_SEED,
 	ARG_COST, ARG_REORDER, ARG_WRAPPER, ARG_VERSION, ARG_IGNORED0, ARG_IGNORED1, ARG_DEVICE, ARG_BATCH, ARG_SAM_NO_QNAME_TRUNC,
-	ARG_LARGE_INDEX, ARG_PAIRED, ARG_INTERLEAVED, ARG_AL, ARG_UN, ARG_MAXDUMP, ARG_FF, ARG_FR, ARG_RF, ARG_PAIRTRIES
+	ARG_LARGE_INDEX, ARG_PAIRED, ARG_INTERLEAVED, ARG_AL, ARG_UN, ARG_MAXDUMP, ARG_FF, ARG_FR, ARG_RF, ARG_PAIRTRIES,
+	ARG_INTEGER_QUALS, ARG_QUALS1, ARG_QUALS2, ARG_STATEFUL, ARG_PEV2, ARG_USAGE, ARG_IGNORED_ARG
 };
 
-static const char *short_options = "fqrchu:v:s:at3:5:e:n:l:p:k:m:M:1:2:I:X:x:B:yS";
+static const char *short_options = "fF:qrchu:v:s:at3:5:o:e:n:l:p:k:m:M:1:2:I:X:x:B:ySQ:";
 static struct option long_options[] = {
 	{"skip", required_argument, 0, 's'}, {"qupto", required_argument, 0, 'u'}, {"trim5", required_argument, 0, '5'},
 	{"trim3", required_argument, 0, '3'}, {"phred33-quals", no_argument, 0, ARG_PHRED33}, {"phred64-quals", no_argument, 0, ARG_PHRED64},
@@ -90,6 +95,15 @@ static struct option long_options[] = {
 	{"ff", no_argument, 0, ARG_FF}, {"fr", no_argument, 0, ARG_FR}, {"rf", no_argument, 0, ARG_RF}, {"pairtries", required_argument, 0, ARG_PAIRTRIES},
 	{"al", required_argument, 0, ARG_AL}, {"un", required_argument, 0, ARG_UN}, {"max", required_argument, 0, ARG_MAXDUMP},
 	{"minins", required_argument, 0, 'I'}, {"maxins", required_argument, 0, 'X'},
+	{"khits", required_argument, 0, 'k'}, {"mhits", required_argument, 0, 'm'}, {"offrate", required_argument, 0, 'o'},
+	{"integer-quals", no_argument, 0, ARG_INTEGER_QUALS}, {"quals", required_argument, 0, 'Q'}, {"Q1", required_argument, 0, ARG_QUALS1},
+	{"Q2", required_argument, 0, ARG_QUALS2}, {"stateful", no_argument, 0, ARG_STATEFUL}, {"pev2", no_argument, 0, ARG_PEV2},
+	{"usage", no_argument, 0, ARG_USAGE},
+	/* accepted for command-line compatibility, no effect here: diagnostics, memory tuning of the CPU implementation, defaults */
+	{"verbose", no_argument, 0, ARG_IGNORED0}, {"startverbose", no_argument, 0, ARG_IGNORED0}, {"strandfix", no_argument, 0, ARG_IGNORED0},
+	{"noreconcile", no_argument, 0, ARG_IGNORED0}, {"chunkverbose", no_argument, 0, ARG_IGNORED0}, {"filepar", no_argument, 0, ARG_IGNORED0},
+	{"chunksz", required_argument, 0, ARG_IGNORED_ARG}, {"prewidth", required_argument, 0, ARG_IGNORED_ARG},
+	{"thread-ceiling", required_argument, 0, ARG_IGNORED_ARG}, {"thread-piddir", required_argument, 0, ARG_IGNORED_ARG},
 	{0, 0, 0, 0}
 };
 
@@ -175,7 +189,23 @@ static void parse_options(int argc, char **argv, Opts &o) {
 		case ARG_VERSION: printf("%s version %s (B200 search path)\n", argv[0], BOWTIE_VERSION); exit(0);
 		case ARG_DEVICE: o.device = (int)parse_int(0, "--device must be >= 0"); break;
 		case ARG_BATCH: o.batch = (uint32_t)parse_int(1, "--reads-per-batch arg must be at least 1"); break;
-		case ARG_REORDER: case ARG_WRAPPER: case ARG_IGNORED0: case ARG_IGNORED1: break;   /* output is always in read order */
+		case ARG_REORDER: o.reorder = true; break;                                   /* output is always in read order */
+		case ARG_WRAPPER: case ARG_IGNORED0: case ARG_IGNORED1: case ARG_IGNORED_ARG: break;
+		case 'o': parse_int(1, "-o/--offrate arg must be at least 1"); break;          /* a sparser SA sample only slows the reference's locate down; results do not depend on it */
+		case ARG_INTEGER_QUALS: o.integerQuals = true; break;
+		case 'Q': split(optarg, ',', o.qualities); o.integerQuals = true; break;       /* ebwt_search.cpp:709-720 */
+		case ARG_QUALS1: split(optarg, ',', o.qualities1); o.integerQuals = true; break;
+		case ARG_QUALS2: split(optarg, ',', o.qualities2); o.integerQuals = true; break;
+		case ARG_STATEFUL: o.best = true; break;                                      /* the best-first aligners without --best's switch to PairedBWAlignerV2 */
+		case ARG_PEV2: o.pev2 = true; break;
+		case ARG_USAGE: printf("Usage: bowtie-b200-align [options]* -x <ebwt> {-1 <m1> -2 <m2> | --12 <r> | --interleaved <i> | <s>} [<hit>]\n  (option names follow bowtie 1.3.1)\n"); exit(0);
+		case 'F': {                                                                   /* -F <len>,<freq>: reads are substrings of the FASTA input */
+			std::vector<std::string> f; split(optarg, ',', f);
+			if (f.size() < 2) die("Error: -F takes <length>,<frequency>");
+			o.format = FASTA_CONT; o.fastaContLen = (size_t)strtoull(f[0].c_str(), NULL, 10); o.fastaContFreq = (size_t)strtoull(f[1].c_str(), NULL, 10);
+			if (o.fastaContLen == 0 || o.fastaContLen >= 1024 || o.fastaContFreq == 0) die("Error: -F needs 0 < length < 1024 and frequency > 0");
+			break;
+		}
 		default: die("Error: unknown or unsupported option (see --help)");
 		}
 	}
@@ -198,7 +228,9 @@ static void parse_options(int argc, char **argv, Opts &o) {
 		fprintf(stderr, "Error: %zu mate files/sequences were specified with -1, but %zu\nmate files/sequences were specified with -2.  The same number of mate files/\nsequences must be specified with -1 and -2.\n", o.mates1.size(), o.mates2.size());
 		exit(1);
 	}
-	o.bestPaired = o.bestFlag;                                                    /* pairs: only --best switches to PairedBWAlignerV2 (useV1 = false, ebwt_search.cpp:776); -M / -v 3 alone keep V1 */
+	if (o.nthreads == 1) o.reorder = false;                                       /* ebwt_search.cpp:835-842 */
+	if (o.reorder && !o.sam) die("Bowtie will reorder its output only when outputting SAM.\nPlease specify the `-S` parameter if you intend on using this option.");
+	o.bestPaired = o.bestFlag || o.pev2;                                                    /* pairs: only --best switches to PairedBWAlignerV2 (useV1 = false, ebwt_search.cpp:776); -M / -v 3 alone keep V1 */
 	if (o.mates1.empty() && o.interleaved.empty() && o.tabbed.empty()) {
 		if (optind >= argc) die("No query or output file specified!");
 		split(argv[optind++], ',', o.queries);
@@ -235,17 +267,43 @@ struct Reader {
 	std::string l1, l2, l3, l4;         /* line buffers, reused from record to record */
 	bool recEof = false;                /* FASTA: the last record ran to the end of the file */
 	std::vector<std::string> rawPieces; size_t rawQ = 0;   /* raw: the CR-separated pieces of the current line */
-	Reader(const Opts &oo, const std::vector<std::string> &ff) : o(oo), files(ff), keepOrig(!oo.dumpAl.empty() || !oo.dumpUn.empty() || !oo.dumpMax.empty()) {}
+	const std::vector<std::string> *qfiles;   /* -Q/--Q1/--Q2 with -f: one quality file per read file; the reference opens them and never reads them */
+	/* FastaContinuousPatternSource state (pat.h:596-665): the last 1024 bases, how many to skip before the next read, where we are */
+	char fcBuf[1024]; size_t fcCur = 0, fcEat = 0; bool fcBeginning = true; uint64_t fcPos = 0, fcLast = 0; std::string fcPrefix;
+	void fc_reset() { fcEat = o.fastaContLen - 1; fcPrefix.clear(); fcBeginning = true; fcCur = 0; fcLast = fcPos; }
+	Reader(const Opts &oo, const std::vector<std::string> &ff, const std::vector<std::string> *qf = NULL) : o(oo), files(ff),
+		keepOrig(!oo.dumpAl.empty() || !oo.dumpUn.empty() || !oo.dumpMax.empty()), qfiles(qf && !qf->empty() && oo.format == FASTA ? qf : NULL) {
+		if (qfiles && !files.empty() && qfiles->size() != files.size())                 /* pat.h:334-340 */
+			die("Error: Different numbers of input FASTA/quality files (" + std::to_string(files.size()) + "/" + std::to_string(qfiles->size()) + ")");
+		fc_reset();
+	}
+	/* CFilePatternSource::open (pat.cpp:283-352): files that cannot be opened are skipped with a warning; running out of files
+	 * that way — rather than by reading the last one to its end — ends the run with status 1 */
 	bool open_next() {
 		if (f) { gzclose(f); f = NULL; }
 		if (fileIdx >= files.size()) return false;
-		const std::string &fn = files[fileIdx++];
-		f = (fn == "-") ? gzdopen(0, "rb") : gzopen(fn.c_str(), "rb");
-		if (!f) die("Warning: Could not open read file \"" + fn + "\" for reading");
-		gzbuffer(f, 1 << 20);
-		if (buf.empty()) buf.resize(1 << 22);
-		len = pos = 0; eof = false; first = true; recEof = false;
-		return true;
+		while (fileIdx < files.size()) {
+			const std::string &fn = files[fileIdx++];
+			if (fn != "-") { struct stat st; if (stat(fn.c_str(), &st) != 0) perror("stat"); }   /* is_gzipped_file, pat.h:418-422 */
+			f = (fn == "-") ? gzdopen(0, "rb") : gzopen(fn.c_str(), "rb");
+			if (!f) { fprintf(stderr, "Warning: Could not open read file \"%s\" for reading; skipping...\n", fn.c_str()); continue; }
+			if (qfiles) {
+				const std::string &qn = (*qfiles)[fileIdx - 1];
+				FILE *q = qn == "-" ? NULL : fopen(qn.c_str(), "rb");
+				if (qn != "-" && !q) {
+					fprintf(stderr, "Warning: Could not open quality file \"%s\" for reading; skipping...\n", qn.c_str());
+					gzclose(f); f = NULL;
+					continue;
+				}
+				if (q) fclose(q);
+			}
+			fc_reset();
+			gzbuffer(f, 1 << 20);
+			if (buf.empty()) buf.resize(1 << 22);
+			len = pos = 0; eof = false; first = true; recEof = false;
+			return true;
+		}
+		exit(1);
 	}
 	bool refill() {                     /* false at end of input */
 		if (eof) return false;
@@ -291,6 +349,13 @@ struct Reader {
 			if (!refill()) { line_hit_eof = true; return true; }
 		}
 	}
+	char int_to_phred33(int iq) const {                                   /* intToPhred33, qual.h:135-153 */
+		int pq;
+		if (o.solexaQuals) pq = (iq < -10 ? 0 : solToPhred[std::min(iq, 90) + 10]) + 33;
+		else pq = (iq <= 93 ? iq : 93) + 33;
+		if (pq < 33) die("Saw negative Phred quality " + std::to_string(pq - 33) + ".");
+		return (char)pq;
+	}
 	static void wrong_quality_format(const std::string &name) {        /* wrongQualityFormat, pat.cpp:1215-1220 */
 		die("Encountered a space parsing the quality string for read " + name + "\nIf this is a FASTQ file with integer (non-ASCII-encoded) qualities, please\nre-run Bowtie with the --integer-quals option.");
 	}
@@ -326,7 +391,7 @@ struct Reader {
 	 * left to next(), whose behaviour — including the reference's error messages — is the specification. */
 	struct FqSpan { size_t l1, n1, l2, n2, l4, n4, end; };
 	std::vector<FqSpan> spans_;
-	bool fast_ok() const { return o.format == FASTQ && f && !first && !keepOrig && o.trim5 == 0 && o.trim3 == 0 && !o.solexaQuals && !o.phred64Quals; }
+	bool fast_ok() const { return o.format == FASTQ && f && !first && !keepOrig && o.trim5 == 0 && o.trim3 == 0 && !o.solexaQuals && !o.phred64Quals && !o.integerQuals; }
 	size_t fast_batch(std::vector<ReadRec> &recs, std::vector<uint32_t> &seeds, size_t maxRecs, size_t nth, uint32_t gseed) {
 		std::vector<FqSpan> &spans = spans_;        /* (a member: worker threads must see this thread's list) */
 		spans.clear();
@@ -419,6 +484,23 @@ struct Reader {
 		do { c = get(); } while (c != '\n' && c != '\r');
 		while (cur < n && (c == '\n' || c == '\r')) c = get();
 		int nqual = 0;
+		if (o.integerQuals) {
+			/* --integer-quals (pat.cpp:905-923): space-separated integers; this branch of the reference neither trims the 3' end of
+			 * the qualities nor compares their number with the sequence's — here they are cut or padded ('I') to the sequence */
+			int cur_int = 0;
+			while (c != '\t' && c != '\n' && c != '\r') {
+				cur_int = cur_int * 10 + (c - '0');
+				c = get();
+				if (c == ' ' || c == '\t' || c == '\n' || c == '\r') {
+					const char cadd = int_to_phred33(cur_int);
+					cur_int = 0;
+					if (c == ' ') c = get();
+					if (++nqual > o.trim5) r.qual.push_back(cadd);
+				}
+			}
+			r.qual.resize(r.seq.size(), 'I');
+			return;
+		}
 		char pc = to_phred33(c, r.name);
 		if (nqual++ >= trimmed5) r.qual.push_back(pc);
 		while (cur < n) {
@@ -455,7 +537,7 @@ struct Reader {
 				const size_t t3 = std::min<size_t>((size_t)o.trim3, r.seq.size());
 				r.seq.resize(r.seq.size() - t3);
 				r.qual.clear(); int nqual = 0;
-				for (char ch : ql) { if (ch == ' ') wrong_quality_format(r.name); char pc = to_phred33((unsigned char)ch, r.name); if (++nqual > o.trim5) r.qual.push_back(pc); }
+				for (char ch : ql) { if (ch == ' ') wrong_quality_format(r.name); if ((unsigned char)ch < 33) die("Saw ASCII character " + std::to_string((int)(unsigned char)ch) + " but expected 33-based Phred qual."); char pc = ch;   /* TabbedPatternSource is built without the quality-encoding flags (ebwt_search.cpp:2942-2943) */ if (++nqual > o.trim5) r.qual.push_back(pc); }
 				if (nchar > nqual) die("Too few quality values for read: " + r.name + "\n\tare you sure this is a FASTQ-int file?");
 				if (nqual > nchar) die("Reads file contained a pattern with more than 1024 quality values.\nPlease truncate reads and quality values and and re-run Bowtie");
 				r.qual.resize(r.qual.size() - std::min<size_t>((size_t)o.trim3, r.qual.size()));
@@ -490,6 +572,46 @@ struct Reader {
 				if (nchar > nqual) die("Too few quality values for read: " + r.name + "\n\tare you sure this is a FASTQ-int file?");
 				if (nqual > nchar) die("Reads file contained a pattern with more than 1024 quality values.\nPlease truncate reads and quality values and and re-run Bowtie");
 				r.qual.resize(r.qual.size() - std::min<size_t>((size_t)o.trim3, r.qual.size()));
+				return true;
+			}
+		}
+		if (o.format == FASTA_CONT) {
+			/* FastaContinuousPatternSource (pat.cpp:651-790): every freq-th window of `len` bases of each FASTA sequence is a read
+			 * named <first word of the header>_<offset>; IUPAC codes and '-' count as N, anything else is skipped */
+			for (;;) {
+				if (!f && !open_next()) return false;
+				int c = getc_();
+				if (c < 0) { gzclose(f); f = NULL; continue; }
+				if (c == '>') {
+					fc_reset();
+					c = getc_();
+					bool sawSpace = false;
+					while (c >= 0 && c != '\n' && c != '\r') {
+						if (!sawSpace) sawSpace = isspace(c) != 0;
+						if (!sawSpace) fcPrefix.push_back((char)c);
+						c = getc_();
+					}
+					while (c == '\n' || c == '\r') c = getc_();
+					if (c < 0) { gzclose(f); f = NULL; continue; }
+					fcPrefix.push_back('_');
+				}
+				const bool acgt = strchr("ACGTacgt", c) != NULL && c != 0;
+				const bool iupac = strchr("BDHKMNRSVWXYbdhkmnrsvwxy-", c) != NULL && c != 0;
+				if (!acgt && !iupac) continue;
+				if (iupac) c = 'N';
+				fcBuf[fcCur++] = (char)c;
+				if (fcCur == 1024) fcCur = 0;
+				if (fcEat > 0) { fcEat--; if (!fcBeginning) fcPos++; continue; }
+				r.name = fcPrefix + std::to_string(fcPos - fcLast);
+				const size_t L = o.fastaContLen;
+				r.seq.clear();                                                       /* (this source is built with trim3 = trim5 = 0, pat.h:600-604) */
+				for (size_t i = 0; i < L; i++) {
+					const char b = (L - i <= fcCur) ? fcBuf[fcCur - (L - i)] : fcBuf[fcCur + 1024 - (L - i)];
+					r.seq.push_back((char)asc2dna[(unsigned char)b]);
+				}
+				r.qual.assign(r.seq.size(), 'I');
+				fcEat = o.fastaContFreq - 1; fcPos++; fcBeginning = false;
+				rdid++;
 				return true;
 			}
 		}
@@ -790,7 +912,7 @@ int main(int argc, char **argv) {
 	if (!op.outfile.empty()) { out.fp = fopen(op.outfile.c_str(), "wb"); if (!out.fp) die("Error: could not open alignment output file " + op.outfile); }
 	if (op.sam && !op.samNoHead) sam_headers(out.buf, op, ix, info.n_refs);
 
-	Reader rd(op, tabbed ? op.tabbed : interleaved ? op.interleaved : pairedInput ? op.mates1 : op.queries), rd2(op, op.mates2);
+	Reader rd(op, tabbed ? op.tabbed : interleaved ? op.interleaved : pairedInput ? op.mates1 : op.queries, (tabbed || interleaved) ? NULL : pairedInput ? &op.qualities1 : &op.qualities), rd2(op, op.mates2, &op.qualities2);
 	enum { NB = 3 };                                                              /* one batch being parsed, one on the GPU, one being formatted */
 	Batch bt[NB];
 	const uint32_t nlim = op.allHits ? 0xffffffffu : op.khits;

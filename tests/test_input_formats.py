@@ -198,3 +198,59 @@ def test_reads_too_short_to_search(cli, tmp_path):
     m1.write_text(fq(r[:2]) + "@p\nACG\n+\nIII\n" + fq(r[2:]))
     m2.write_text(fq(r[2:]) + "@p\nACGTACGTAGGCTAGCTAGGATCGATTTAGGCAT\n+\nIIIIIIIIIIIIIIIIIIIIIIIIIIIIIIIIII\n" + fq(r[:2]))
     both(cli, tmp_path, "s_pair", ["-n", "2"], ["-1", str(m1), "-2", str(m2)])
+
+
+def test_fasta_continuous(cli, tmp_path):
+    """-F <len>,<freq> (FastaContinuousPatternSource, pat.cpp:651-790): reads are windows of the FASTA input, named after the
+    sequence and the offset; IUPAC codes and '-' are N, other characters are skipped, trimming options do not apply."""
+    genome = None
+    for cand in (ROOT / "oracle" / "_ref" / "fixtures" / "NC_008253.fna", Path("/root/reference/genomes/NC_008253.fna")):
+        if cand.exists():
+            genome = cand.read_text()
+            break
+    if genome is None:
+        pytest.skip("no genome FASTA to cut windows from")
+    g1, g2 = tmp_path / "g1.fa", tmp_path / "g2.fa"
+    g1.write_text(genome[:6000])
+    body = genome[100:1500].split("\n", 1)[1][:700]
+    g2.write_text(">seqA some words\n" + body + "\n>seqB\nACGTNNRYACGTTTGACCAGT-ACGATGCAGCTAGCTAGCTAGGATCGATCGATGCTAGCTAGCTAGCATGCATGCTAGTCGAT\nGGATTCAG*GATTAGCAT12ACAGGATACCAGGGATATTACAC\n")
+    for lf in ("30,10", "35,1", "50,7", "100,40"):
+        both(cli, tmp_path, f"F1_{lf}", ["-F", lf, "-n", "2"], [str(g1)])
+        both(cli, tmp_path, f"F2_{lf}", ["-F", lf, "-v", "2"], [str(g2)])
+        both(cli, tmp_path, f"F3_{lf}", ["-F", lf, "-v", "2", "-5", "2", "-3", "3"], [f"{g2},{g1}"])
+
+
+def test_quality_options(cli, tmp_path):
+    """--integer-quals (pat.cpp:905-923, qual.h:135-153); -Q/--Q1/--Q2 quality files are opened and counted but never read
+    (pat.cpp:333-348, pat.h:334-340); --12 ignores the quality-encoding flags (ebwt_search.cpp:2942-2943)."""
+    rs = recs(40)
+    iq = tmp_path / "iq.fq"
+    iq.write_text("".join(f"{r[0]}\n{r[1]}\n+\n{' '.join(str(ord(ch) - 33) for ch in r[3])}\n" for r in rs))
+    both(cli, tmp_path, "iq", ["-n", "2", "--integer-quals"], [str(iq)])
+    both(cli, tmp_path, "iq_sol", ["-n", "2", "--integer-quals", "--solexa-quals"], [str(iq)])
+    both(cli, tmp_path, "iq_t5", ["-n", "2", "--integer-quals", "-5", "3"], [str(iq)])
+    big = tmp_path / "iqbig.fq"
+    big.write_text(iq.read_text().replace(" 30", " 130"))
+    both(cli, tmp_path, "iq_big", ["-n", "2", "--integer-quals"], [str(big)])
+    both(cli, tmp_path, "iq_noflag", ["-n", "2"], [str(iq)])
+    rfa, rq = tmp_path / "r.fa", tmp_path / "r.qual"
+    rfa.write_text(fa(rs)); rq.write_text("x\n")
+    both(cli, tmp_path, "Q_ok", ["-n", "2", "-f", "-Q", str(rq)], [str(rfa)])
+    both(cli, tmp_path, "Q_count", ["-n", "2", "-f", "-Q", f"{rq},{rq}"], [str(rfa)])
+    both(cli, tmp_path, "Q_missing", ["-n", "2", "-f", "-Q", str(tmp_path / "none.qual")], [str(rfa)])
+    both(cli, tmp_path, "Q_missing2", ["-n", "2", "-f", "-Q", f"{tmp_path / 'none.qual'},{rq}"], [f"{rfa},{rfa}"])
+    tab = tmp_path / "t.tab"
+    tab.write_text("".join(f"{r[0][1:]}\t{r[1]}\t{r[3]}\n" for r in rs))
+    both(cli, tmp_path, "tab_p64", ["-n", "2", "--phred64-quals"], ["--12", str(tab)])
+    both(cli, tmp_path, "tab_sol", ["-n", "2", "--solexa-quals"], ["--12", str(tab)])
+
+
+def test_option_aliases_and_hidden_switches(cli, tmp_path):
+    fq1 = str(FIXTURES / "e_coli_1000.fq")
+    pair = ["-1", str(FIXTURES / "e_coli_1000_1.fq"), "-2", str(FIXTURES / "e_coli_1000_2.fq")]
+    both(cli, tmp_path, "khits", ["-n", "2", "--khits", "3", "--mhits", "5"], [fq1])
+    both(cli, tmp_path, "stateful", ["-n", "2", "--stateful"], [fq1])                 # best-first aligners, paired stays V1
+    both(cli, tmp_path, "stateful_p", ["-n", "2", "--stateful", "-u", "200"], pair)
+    both(cli, tmp_path, "pev2", ["-n", "2", "--pev2", "-u", "200"], pair)              # PairedBWAlignerV2 without --best
+    both(cli, tmp_path, "offrate", ["-n", "2", "-o", "7"], [fq1])
+    both(cli, tmp_path, "noop", ["-n", "2", "--strandfix", "--noreconcile", "--chunksz", "32"], [fq1])
