@@ -526,7 +526,7 @@ struct Reader {
 			for (;;) { size_t t = line.find('\t', p0); if (t == std::string::npos) { fld.push_back(line.substr(p0)); break; } fld.push_back(line.substr(p0, t - p0)); p0 = t + 1; }
 			rdid++;
 			if (keepOrig) { a.orig = line; a.orig += '\n'; b.orig.clear(); }
-			if (fld.size() < 3) continue;                                    /* "record ended prematurely": the read is skipped */
+			if (fld.size() < 3 || fld.size() == 4) continue;                 /* "record ended prematurely" (pat.cpp:1043-1070): the record is skipped */
 			isPair = fld.size() >= 5;
 			for (int e = 0; e < (isPair ? 2 : 1); e++) {
 				ReadRec &r = e ? b : a;
@@ -546,7 +546,9 @@ struct Reader {
 		}
 	}
 	/* Returns false when all input is consumed. */
-	bool next(ReadRec &r) {
+	/* role: 0 = a file of single reads or of one mate; 1 / 2 = first / second record of an --interleaved pair */
+	bool abortedSlot0 = false;          /* a mate file ended inside a record that would have opened a light-parse batch */
+	bool next(ReadRec &r, int role = 0, bool mateFile = false) {
 		if (o.format == CMDLINE) {
 			/* VectorPatternSource (pat.cpp:357-523): "seq[:quals]" becomes the tabbed record "<ordinal> TAB seq TAB quals" — quals
 			 * default to one 'I' per character of seq — and is parsed like one: letters only, plain Phred+33, counts must agree */
@@ -635,12 +637,22 @@ struct Reader {
 				}
 				/* an incomplete record in the first slot of a light-parse batch: the reference's count goes to -1 and it parses the
 				 * slot's leftovers, which ends in this message */
-				if (aborted && (rdid & 15) == 0) die("Saw ASCII character 10 but expected 33-based Phred qual.");
+				if (aborted && (rdid & 15) == 0 && role != 2) {
+					if (mateFile) abortedSlot0 = true;                                 /* -1/-2: the two counts (-1 here) are compared first */
+					else die("Saw ASCII character 10 but expected 33-based Phred qual.");
+				}
 				if (!counted) { gzclose(f); f = NULL; continue; }
 				/* a file that ends inside a record — one or two newlines after this one, a stray blank line included — makes
 				 * nextBatchFromFile step its read count back (pat.cpp:853-855), which discards the record BEFORE the incomplete one
-				 * unless that one closed a light-parse batch of 16 */
-				if ((rdid & 15) != 15 && tail_aborts()) { gzclose(f); f = NULL; continue; }
+				 * unless that one closed a light-parse batch of 16.
+				 * --interleaved: the count is in pairs, so blank lines after a complete pair cost that pair (and an incomplete pair
+				 * the one before it as well, which cannot be taken back here: only the incomplete one goes) */
+				if (role == 0) { if ((rdid & 15) != 15 && tail_aborts()) { gzclose(f); f = NULL; continue; } }
+				else if (role == 2) { if ((rdid & 15) != 0 && tail_aborts()) { gzclose(f); f = NULL; continue; } }
+				else if (tail_aborts()) {
+					if ((rdid & 15) == 0) die("Saw ASCII character 10 but expected 33-based Phred qual.");
+					gzclose(f); f = NULL; continue;
+				}
 				parse_fastq_chunk(chunk, r);
 				if (keepOrig) r.orig = chunk;                                       /* Read::readOrigBuf */
 			} else if (o.format == FASTA) {
@@ -993,9 +1005,19 @@ int main(int argc, char **argv) {
 						continue;
 					}
 				}
-				if (!rd.next(rec)) { input_done = true; break; }
-				if (interleaved) { if (!rd.next(rec2)) die("Error: odd number of reads in an --interleaved file"); rd.rdid--; }   /* a pair is one read id */
-				else if (paired && !rd2.next(rec2)) die("Error, fewer reads in file specified with -2 than in file specified with -1");
+				if (interleaved) {
+					if (!rd.next(rec, 1)) { input_done = true; break; }
+					if (!rd.next(rec2, 2)) { input_done = true; break; }                /* a last record without a mate is dropped (the light parser counts pairs) */
+					rd.rdid--;                                                          /* a pair is one read id */
+				} else if (paired) {
+					/* DualPatternComposer::nextBatch (pat.cpp:164-222) compares what the two files delivered */
+					const bool ga = rd.next(rec, 0, true), gb = rd2.next(rec2, 0, true);
+					const int ca = ga ? 1 : rd.abortedSlot0 ? -1 : 0, cb = gb ? 1 : rd2.abortedSlot0 ? -1 : 0;
+					if (ca < cb) die("Error, fewer reads in file specified with -1 than in file specified with -2");
+					if (cb < ca) die("Error, fewer reads in file specified with -2 than in file specified with -1");
+					if (ca < 0) die("Saw ASCII character 10 but expected 33-based Phred qual.");
+					if (!ga) { input_done = true; break; }
+				} else if (!rd.next(rec)) { input_done = true; break; }
 			}
 			if (rd.rdid - 1 < op.skipReads) continue;                              /* -s: skipped reads are not counted */
 			if (paired) { fix_mate_name(rec.name, 1); fix_mate_name(rec2.name, 2); }   /* PatternSourcePerThread::finalizePair (pat.cpp:75-87) */

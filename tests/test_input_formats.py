@@ -254,3 +254,42 @@ def test_option_aliases_and_hidden_switches(cli, tmp_path):
     both(cli, tmp_path, "pev2", ["-n", "2", "--pev2", "-u", "200"], pair)              # PairedBWAlignerV2 without --best
     both(cli, tmp_path, "offrate", ["-n", "2", "-o", "7"], [fq1])
     both(cli, tmp_path, "noop", ["-n", "2", "--strandfix", "--noreconcile", "--chunksz", "32"], [fq1])
+
+
+def test_paired_inputs_edge_cases(cli, tmp_path):
+    """-1/-2: DualPatternComposer::nextBatch compares what the two files delivered (pat.cpp:164-222) — a file that is short, or
+    that loses its last record to a trailing blank line, is an error; --interleaved counts pairs, so a last record without a
+    mate is dropped and blank lines after the last pair cost that pair; --12 records with 4 fields are skipped."""
+    def L(p):
+        l = (FIXTURES / p).read_text().splitlines()
+        return [l[i:i + 4] for i in range(0, len(l), 4)]
+    M1, M2 = L("e_coli_1000_1.fq"), L("e_coli_1000_2.fq")
+
+    def w(name, text):
+        f = tmp_path / name
+        f.write_text(text)
+        return str(f)
+    for n in (5, 16, 17):
+        a, b = fq(M1[:n]), fq(M2[:n])
+        both(cli, tmp_path, f"p_ok{n}", ["-n", "2"], ["-1", w("a.fq", a), "-2", w("b.fq", b)])
+        both(cli, tmp_path, f"p_short2_{n}", ["-n", "2"], ["-1", w("a.fq", a), "-2", w("b.fq", fq(M2[:n - 1]))])
+        both(cli, tmp_path, f"p_short1_{n}", ["-n", "2"], ["-1", w("a.fq", fq(M1[:n - 1])), "-2", w("b.fq", b)])
+        both(cli, tmp_path, f"p_trail1_{n}", ["-n", "2"], ["-1", w("a.fq", a + "\n"), "-2", w("b.fq", b)])
+        both(cli, tmp_path, f"p_trail2_{n}", ["-n", "2"], ["-1", w("a.fq", a), "-2", w("b.fq", b + "\n")])
+        both(cli, tmp_path, f"p_trailboth_{n}", ["-n", "2"], ["-1", w("a.fq", a + "\n"), "-2", w("b.fq", b + "\n")])
+        both(cli, tmp_path, f"p_nonl_{n}", ["-n", "2"], ["-1", w("a.fq", a.rstrip("\n")), "-2", w("b.fq", b.rstrip("\n"))])
+        il = "".join("\n".join(x) + "\n" + "\n".join(y) + "\n" for x, y in zip(M1[:n], M2[:n]))
+        both(cli, tmp_path, f"i_ok{n}", ["-n", "2"], ["--interleaved", w("i.fq", il)])
+        both(cli, tmp_path, f"i_odd{n}", ["-n", "2"], ["--interleaved", w("i.fq", il + "\n".join(M1[n]) + "\n")])
+        both(cli, tmp_path, f"i_trail{n}", ["-n", "2"], ["--interleaved", w("i.fq", il + "\n")])
+        both(cli, tmp_path, f"i_nonl{n}", ["-n", "2"], ["--interleaved", w("i.fq", il.rstrip("\n"))])
+        tab = "".join(f"{x[0][1:]}\t{x[1]}\t{x[3]}\t{y[1]}\t{y[3]}\n" for x, y in zip(M1[:n], M2[:n]))
+        both(cli, tmp_path, f"t_ok{n}", ["-n", "2"], ["--12", w("t.tab", tab)])
+        both(cli, tmp_path, f"t_blank{n}", ["-n", "2"], ["--12", w("t.tab", "\n" + tab + "\n\n")])
+        both(cli, tmp_path, f"t_nonl{n}", ["-n", "2"], ["--12", w("t.tab", tab.rstrip("\n"))])
+        both(cli, tmp_path, f"t_crlf{n}", ["-n", "2"], ["--12", w("t.tab", tab.replace("\n", "\r\n"))])
+        both(cli, tmp_path, f"t_2f{n}", ["-n", "2"], ["--12", w("t.tab", tab + "nm\tACGT\n")])
+        both(cli, tmp_path, f"t_4f{n}", ["-n", "2"], ["--12", w("t.tab", tab + f"nm\t{M1[0][1]}\t{M1[0][3]}\t{M2[0][1]}\n")])
+        both(cli, tmp_path, f"t_badq{n}", ["-n", "2"], ["--12", w("t.tab", tab + f"nm\t{M1[0][1]}\t{M1[0][3][:-1]}\n")])
+        both(cli, tmp_path, f"pf_ok{n}", ["-n", "2", "-f"], ["-1", w("a.fa", fa(M1[:n])), "-2", w("b.fa", fa(M2[:n]))])
+        both(cli, tmp_path, f"pf_short{n}", ["-n", "2", "-f"], ["-1", w("a.fa", fa(M1[:n])), "-2", w("b.fa", fa(M2[:n - 1]))])
