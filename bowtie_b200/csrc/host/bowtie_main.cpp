@@ -1152,7 +1152,7 @@ int main(int argc, char **argv) {
 			else if (unal) {
 				cnt[1]++;
 				if (serial) dump_unit(op.dumpUn, b, i);
-				if (op.sam && !op.noUnal) { if (paired) { append_sam_unaligned(obuf, op, r, 1); append_sam_unaligned(obuf, op, b.reads[i * mult + 1], 2); } else append_sam_unaligned(obuf, op, r); }
+				if (op.sam && !op.noUnal) { if (paired && !b.reads[i * mult + 1].seq.empty()) { append_sam_unaligned(obuf, op, r, 1); append_sam_unaligned(obuf, op, b.reads[i * mult + 1], 2); } else append_sam_unaligned(obuf, op, r); }   /* `paired = !p.bufb().empty()`, sam.cpp:75 */
 			} else {
 				uint32_t nrep = std::min(found, nlimU);
 				for (uint32_t s = 0; s < nrep; s++) {

@@ -169,6 +169,48 @@ def rand_flags(rng):
     return f
 
 
+def rand_io_flags(rng, sam, td):
+    """Options of the driver around the search: trimming, read selection, output fields.  Returns (flags, dump_files)."""
+    f, dumps = [], []
+    if rng.random() < 0.15:
+        f += ["-5", str(rng.randint(1, 4))]
+    if rng.random() < 0.15:
+        f += ["-3", str(rng.randint(1, 4))]
+    if rng.random() < 0.1:
+        f += ["-s", str(rng.randint(1, 15))]
+    if rng.random() < 0.1:
+        f += ["-u", str(rng.randint(5, 60))]
+    if rng.random() < 0.1:
+        f += ["-p", str(rng.randint(2, 4))]                      # ours only formats with threads; the reference side always gets -p 1 last
+    if sam:
+        if rng.random() < 0.2:
+            f += ["--sam-nohead"]
+        if rng.random() < 0.2:
+            f += ["--sam-nosq"]
+        if rng.random() < 0.2:
+            f += ["--sam-RG", "ID:x", "--sam-RG", "SM:y"]
+        if rng.random() < 0.2:
+            f += ["--mapq", str(rng.randint(0, 60))]
+        if rng.random() < 0.2:
+            f += ["--no-unal"]
+    else:
+        if rng.random() < 0.15:
+            f += ["--refidx"]
+        if rng.random() < 0.15:
+            f += ["--fullref"]
+        if rng.random() < 0.15:
+            f += ["-B", str(rng.randint(1, 3))]
+        if rng.random() < 0.15:
+            f += ["--suppress", ",".join(str(x) for x in sorted(rng.sample(range(1, 9), rng.randint(1, 3))))]
+        if rng.random() < 0.1:
+            f += ["--cost"]
+    if rng.random() < 0.15:
+        for opt in rng.sample(["--al", "--un", "--max"], rng.randint(1, 3)):
+            f += [opt, f"@DIR@/dump{opt[1:]}.fq"]
+            dumps.append(f"dump{opt[1:]}")
+    return f, dumps
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--iters", type=int, default=50)
@@ -202,15 +244,25 @@ def main():
                 else:
                     flags = rand_paired_flags(rng)
                     inputs = ["-1", str(td / "m1.fq"), "-2", str(td / "m2.fq")]
-                r = subprocess.run([str(REF / "bowtie-align-s"), *flags, "-p", "1", "-x", str(td / "g"), *inputs, str(td / "ref.out")], capture_output=True, text=True)
+                io, dumps = rand_io_flags(rng, "-S" in flags, td)
+                flags = flags + io
+                (td / "dr").mkdir(exist_ok=True); (td / "do").mkdir(exist_ok=True)
+                for d in ("dr", "do"):
+                    for x in (td / d).iterdir():
+                        x.unlink()
+                fr = [x.replace("@DIR@", str(td / "dr")) for x in flags]
+                fo = [x.replace("@DIR@", str(td / "do")) for x in flags]
+                r = subprocess.run([str(REF / "bowtie-align-s"), *fr, "-p", "1", "-x", str(td / "g"), *inputs, str(td / "ref.out")], capture_output=True, text=True)
                 if "Exhausted best-first chunk memory" in r.stderr or r.returncode < 0:     # the reference's own memory limit / a crash of the reference
                     continue
-                o = subprocess.run([str(CLI), *flags, "-x", str(td / "g"), *inputs, str(td / "our.out")], capture_output=True, text=True, env=env)
+                o = subprocess.run([str(CLI), *fo, "-x", str(td / "g"), *inputs, str(td / "our.out")], capture_output=True, text=True, env=env)
+                dump_r = {x.name: x.read_bytes() for x in sorted((td / "dr").iterdir())}
+                dump_o = {x.name: x.read_bytes() for x in sorted((td / "do").iterdir())}
                 def body(pth):
                     return b"".join(l for l in Path(pth).read_bytes().splitlines(keepends=True) if not l.startswith(b"@PG")) if Path(pth).exists() else b"<none>"
                 def summ(t):
                     return [l for l in t.splitlines() if l.startswith("#") or l.startswith("Reported") or l.startswith("No alignments")]
-                ok = r.returncode == o.returncode and (r.returncode != 0 or (body(td / "ref.out") == body(td / "our.out") and summ(r.stderr) == summ(o.stderr)))
+                ok = r.returncode == o.returncode and (r.returncode != 0 or (body(td / "ref.out") == body(td / "our.out") and summ(r.stderr) == summ(o.stderr) and dump_r == dump_o))
                 if not ok:
                     nfail += 1
                     keep = Path(a.keep + f"_{a.seed}_{it}_{sub}")
