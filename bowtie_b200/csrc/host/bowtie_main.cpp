@@ -391,10 +391,12 @@ struct Reader {
 	 * left to next(), whose behaviour — including the reference's error messages — is the specification. */
 	struct FqSpan { size_t l1, n1, l2, n2, l4, n4, end; };
 	std::vector<FqSpan> spans_;
+	double t_scan = 0, t_work = 0;      /* BT_CLI_TIMING */
 	bool fast_ok() const { return o.format == FASTQ && f && !first && !keepOrig && o.trim5 == 0 && o.trim3 == 0 && !o.solexaQuals && !o.phred64Quals && !o.integerQuals; }
 	size_t fast_batch(std::vector<ReadRec> &recs, std::vector<uint32_t> &seeds, size_t maxRecs, size_t nth, uint32_t gseed) {
 		std::vector<FqSpan> &spans = spans_;        /* (a member: worker threads must see this thread's list) */
 		spans.clear();
+		const auto tq0 = std::chrono::steady_clock::now();
 		const char *base = buf.data();
 		size_t p = pos;
 		while (spans.size() < maxRecs && p < len) {
@@ -421,6 +423,8 @@ struct Reader {
 		}
 		const size_t n = spans.size();
 		if (n == 0) return 0;
+		const auto tq1 = std::chrono::steady_clock::now();
+		t_scan += std::chrono::duration<double>(tq1 - tq0).count();
 		const size_t r0 = recs.size();
 		recs.resize(r0 + n); seeds.resize(r0 + n);
 		std::vector<uint8_t> okv(n, 1);
@@ -449,6 +453,7 @@ struct Reader {
 			for (size_t t = 0; t < nth; t++) th.emplace_back(work, n * t / nth, n * (t + 1) / nth);
 			for (auto &x : th) x.join();
 		}
+		t_work += std::chrono::duration<double>(std::chrono::steady_clock::now() - tq1).count();
 		size_t good = 0;
 		while (good < n && okv[good]) good++;
 		recs.resize(r0 + good); seeds.resize(r0 + good);
@@ -489,7 +494,7 @@ struct Reader {
 			 * the qualities nor compares their number with the sequence's — here they are cut or padded ('I') to the sequence */
 			int cur_int = 0;
 			while (c != '\t' && c != '\n' && c != '\r') {
-				cur_int = cur_int * 10 + (c - '0');
+				cur_int = (int)((unsigned)cur_int * 10u + (unsigned)(c - '0'));        /* (wraps, as the reference's int does in practice) */
 				c = get();
 				if (c == ' ' || c == '\t' || c == '\n' || c == '\r') {
 					const char cadd = int_to_phred33(cur_int);
@@ -1227,7 +1232,7 @@ int main(int argc, char **argv) {
 	}
 	if (prev >= 0) { auto t1 = std::chrono::steady_clock::now(); finish(bt[prev]); t_finish += std::chrono::duration<double>(std::chrono::steady_clock::now() - t1).count(); }
 	parser.join();
-	if (getenv("BT_CLI_TIMING")) fprintf(stderr, "host pipeline: parse %.2f s (parser thread), launch %.2f s, sync+format %.2f s\n", t_fill, t_launch, t_finish);
+	if (getenv("BT_CLI_TIMING")) fprintf(stderr, "host pipeline: parse %.2f s (parser thread; fast path: scan %.2f s, records %.2f s), launch %.2f s, sync+format %.2f s\n", t_fill, rd.t_scan, rd.t_work, t_launch, t_finish);
 	out.flush();
 	if (out.fp != stdout) fclose(out.fp);
 	for (auto &kv : dumps) if (kv.second) fclose(kv.second);
