@@ -705,7 +705,7 @@ static bool main_kernel_is_queue() {
 #define BT_HEAVY_NCTX 256           /* heavy pass, queue kernel: contexts per block (one block per SM)        */
 #define BT_HEAVY_BLOCKS_PER_SM 8   /* heavy pass: 32-thread blocks, so finished warps free their slots */
 
-/* The best-first path (bt_best.cuh).  Three passes with growing per-read arenas: every read with 64 KB on the caller's
+/* The best-first path (bt_best.cuh).  Four passes with growing per-read arenas: every read with 64 KB on the caller's
  * stream (148 x 12 x 64 lanes); the reads that exhausted it with 1 MB (148 x 32 lanes), then 16 MB (148 lanes), then 256 MB
  * (8 lanes; the reference's own ceiling is 64 MB of chunked pools per thread) on the side stream.
  * About 7.5 (pairs: 11) + 5 + 2.5 + 2 GB per context for full batches. */
