@@ -1,0 +1,50 @@
+/* Test-only driver for bt_build.h: the suffix sort is done here with std::sort (the product sorts on the GPU, bt_build_sa.cuh);
+ * everything else — FASTA records, joined text, side packing, ftab/eftab, file layout — is the product's host code. */
+#include <algorithm>
+#include <numeric>
+#include "../../bowtie_b200/csrc/bt_build.h"
+
+/* shared with the device path: what to read off a finished suffix array */
+static bool sa_to_result(const uint8_t *s, uint32_t len, const std::vector<uint32_t> &sa, int offRate, int ftabChars, BtSuffixResult *out) {
+	out->bwt.assign((size_t)len + 1, 0);
+	out->offs.clear(); out->absorb.clear();
+	const uint32_t K = (uint32_t)ftabChars;
+	uint32_t run = 0;
+	for (uint64_t row = 0; row <= len; row++) {
+		const uint32_t p = sa[row];
+		if (p == 0) out->zOff = (uint32_t)row; else out->bwt[row] = s[p - 1];
+		if ((row & ((1ull << offRate) - 1)) == 0) out->offs.push_back(p);
+		if (len - p < K) run++;
+		else if (run) { uint32_t v = 0; for (uint32_t i = 0; i < K; i++) v = (v << 2) | s[p + i]; out->absorb.push_back({ v, run }); run = 0; }
+	}
+	if (run) out->absorb.push_back({ (uint32_t)(1ull << (2 * K)), run });
+	return true;
+}
+
+static bool host_sort(const uint8_t *s, uint32_t len, int offRate, int ftabChars, BtSuffixResult *out, void *, std::string *) {
+	std::vector<uint32_t> sa((size_t)len + 1);
+	std::iota(sa.begin(), sa.end(), 0u);
+	std::sort(sa.begin(), sa.end(), [&](uint32_t a, uint32_t b) {
+		if (a == b) return false;
+		const uint32_t la = len - a, lb = len - b, m = la < lb ? la : lb;
+		const int c = memcmp(s + a, s + b, m);
+		if (c) return c < 0;
+		return la > lb;                                                /* the end of the text is greater than any character */
+	});
+	return sa_to_result(s, len, sa, offRate, ftabChars, out);
+}
+
+int main(int argc, char **argv) {
+	BtBuildParams P; std::vector<std::string> fa; std::string base;
+	for (int i = 1; i < argc; i++) {
+		std::string a = argv[i];
+		if (a == "-o") P.offRate = atoi(argv[++i]);
+		else if (a == "-t") P.ftabChars = atoi(argv[++i]);
+		else if (a == "--ntoa") P.nsToAs = true;
+		else if (fa.empty()) { size_t p0 = 0; for (;;) { size_t c = a.find(',', p0); fa.push_back(a.substr(p0, c == std::string::npos ? c : c - p0)); if (c == std::string::npos) break; p0 = c + 1; } }
+		else base = a;
+	}
+	std::string err;
+	if (!bt_build_all(fa, base, P, host_sort, NULL, err)) { fprintf(stderr, "%s\n", err.c_str()); return 1; }
+	return 0;
+}
