@@ -25,9 +25,9 @@ def build_library(force: bool = False) -> Path:
     so = lib_path()
     csrc = _PKG / "csrc"
     srcs = [p for p in csrc.iterdir() if p.suffix in (".cu", ".cuh", ".h")] + list((csrc / "host").glob("*.cpp")) + [_PKG.parent / "include" / "bowtie_b200.h"]
-    cli = _PKG / "bowtie-b200-align"
+    clis = [_PKG / "bowtie-b200-align", _PKG / "bowtie-b200-build"]
     newest = max(s.stat().st_mtime for s in srcs)
-    if force or not so.exists() or not cli.exists() or min(so.stat().st_mtime, cli.stat().st_mtime) < newest:
+    if force or not so.exists() or not all(c.exists() for c in clis) or min([so.stat().st_mtime] + [c.stat().st_mtime for c in clis]) < newest:
         p = subprocess.run(["make", "-C", str(_PKG / "csrc")], capture_output=True, text=True)
         if p.returncode != 0:
             raise RuntimeError("building libbowtie_b200.so failed:\n" + p.stdout + p.stderr)
@@ -97,8 +97,19 @@ def load_library() -> C.CDLL:
         fn.argtypes = [C.c_void_p, C.c_void_p]
     L.bt_stats_get.argtypes = [C.c_void_p, C.POINTER(_Stats), C.c_int]
     L.bt_debug_lf.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_uint32, C.c_void_p]
+    L.bt_index_build.restype = C.c_int
+    L.bt_index_build.argtypes = [C.POINTER(C.c_char_p), C.c_uint32, C.c_char_p, C.c_int, C.c_int, C.c_int]
     _LIB = L
     return L
+
+
+def build_index(fasta, out_base, off_rate: int = 5, ftab_chars: int = 10, device: int = 0) -> None:
+    """bowtie-build on the GPU (bt_index_build): writes out_base.{1,2,3,4}.ebwt and out_base.rev.{1,2}.ebwt."""
+    L = load_library()
+    files = [str(f).encode() for f in ([fasta] if isinstance(fasta, (str, Path)) else fasta)]
+    arr = (C.c_char_p * len(files))(*files)
+    if L.bt_index_build(arr, len(files), str(out_base).encode(), int(off_rate), int(ftab_chars), int(device)) != 0:
+        raise RuntimeError("bt_index_build: " + L.bt_last_error().decode())
 
 
 @dataclass

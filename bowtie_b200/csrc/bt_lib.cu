@@ -388,6 +388,7 @@ __global__ void bt_ctl_set_kernel(BtWorkCtl *ctl, unsigned long long nwork) { ct
 
 static thread_local std::string g_err;
 static int fail(const std::string &m) { g_err = m; return 1; }
+int bt_internal_fail(const std::string &m) { return fail(m); }       /* for bt_build.cu */
 #define CUDA_TRY(x) do { cudaError_t e_ = (x); if (e_ != cudaSuccess) return fail(std::string(#x) + ": " + cudaGetErrorString(e_)); } while (0)
 
 struct HostEbwt {     /* the parsed contents of X.1.ebwt / X.2.ebwt */

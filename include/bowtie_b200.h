@@ -153,6 +153,12 @@ int  bt_context_join(bt_context_t *cx, void *stream);
 
 int  bt_stats_get(bt_index_t *ix, bt_stats_t *out, int reset);    /* synchronises the device */
 
+/* Replaces bowtie-build (ebwt_build.cpp:303-480 driver(); Ebwt::initFromVector / joinToDisk / buildToDisk, ebwt.h:3825-4388;
+ * fastaRefReadSizes, ref_read.cpp:202-273): writes out_base.{1,2,3,4}.ebwt and out_base.rev.{1,2}.ebwt, byte-identical to the
+ * reference's files for the same FASTA input, -o (off_rate, default 5) and -t (ftab_chars, default 10).  The suffix sort
+ * runs on `device`; FASTA parsing and file packing are host work. */
+int  bt_index_build(const char *const *fasta_paths, uint32_t n_paths, const char *out_base, int off_rate, int ftab_chars, int device);
+
 /* LF primitives on the device layout, for parity tests: computes, for each row, mapLFEx-style
  * (fchr[c] + occ(c,row)) for c = 0..3 and rowL.  rows/out are host arrays; out has 5 words per row. */
 int  bt_debug_lf(bt_index_t *ix, int mirror, const uint32_t *rows, uint32_t n, uint32_t *out);

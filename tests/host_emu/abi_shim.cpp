@@ -16,6 +16,7 @@
 #include "../../bowtie_b200/csrc/bt_native.cuh"
 #include "../../bowtie_b200/csrc/bt_best_prog.h"
 #include "../../bowtie_b200/csrc/bt_ref_load.h"
+#include "bsa_host.h"
 #include "../../include/bowtie_b200.h"
 extern "C" {
 #include "../../oracle/bt_oracle.h"
@@ -148,4 +149,13 @@ int bt_context_sync(bt_context_t *, void *) { return 0; }
 int bt_context_join(bt_context_t *, void *) { return 0; }
 int bt_stats_get(bt_index_t *ix, bt_stats_t *out, int) { *out = ix->st; return 0; }
 int bt_debug_lf(bt_index_t *, int, const uint32_t *, uint32_t, uint32_t *) { g_err = "not in the shim"; return 1; }
+/* index construction: the product's host code (bt_build.h) and suffix-sort algorithm (bt_build_sa.cuh) over the host backend */
+int bt_index_build(const char *const *fasta_paths, uint32_t n_paths, const char *out_base, int off_rate, int ftab_chars, int) {
+	std::vector<std::string> files;
+	for (uint32_t i = 0; i < n_paths; i++) files.push_back(fasta_paths[i]);
+	BtBuildParams P; P.offRate = off_rate; P.ftabChars = ftab_chars;
+	std::string err;
+	if (!bt_build_all(files, out_base, P, doubling_sort, NULL, err)) { g_err = err; return 1; }
+	return 0;
+}
 }

@@ -76,10 +76,11 @@ def build_shim():
     so = SHIM_DIR / "libbowtie_b200.so"
     csrc = ROOT / "bowtie_b200" / "csrc"
     srcs = [ROOT / "tests" / "host_emu" / "abi_shim.cpp", csrc / "bt_core.cuh", ROOT / "oracle" / "bt_oracle.c", csrc / "bt_best.cuh", csrc / "bt_best_prog.h",
+            csrc / "bt_build.h", csrc / "bt_build_sa.cuh", ROOT / "tests" / "host_emu" / "bsa_host.h",
             ROOT / "include" / "bowtie_b200.h"]
     if not so.exists() or so.stat().st_mtime < max(s.stat().st_mtime for s in srcs):
         SHIM_DIR.mkdir(exist_ok=True)
-        subprocess.run(["g++", "-O2", "-std=c++17", "-fPIC", "-shared", "-o", str(so), str(srcs[0]), str(srcs[2])], check=True, capture_output=True)
+        subprocess.run(["g++", "-O2", "-std=c++17", "-fPIC", "-shared", "-o", str(so), str(srcs[0]), str(srcs[2]), "-lz"], check=True, capture_output=True)
     return so
 
 
