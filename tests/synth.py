@@ -65,24 +65,32 @@ def write_fasta(path: Path, seqs: list[tuple[str, bytes]]) -> None:
     with open(path, "wb") as f:
         for name, s in seqs:
             f.write(b">" + name.encode() + b"\n")
+            if len(s) > 50_000_000:                      # hg19-scale sequences: megabase lines, not 50 M Python iterations
+                for i in range(0, len(s), 1 << 20):
+                    f.write(s[i:i + (1 << 20)] + b"\n")
+                continue
             for i in range(0, len(s), 60):
                 f.write(s[i:i + 60] + b"\n")
 
 
 def build_synth_index(tag: str, n_seqs: int, total_len: int, seed: int, ftab_chars: int = 10, off_rate: int = 5,
-                      with_gaps: bool = False, threads: int = 8, style: str = "flat"):
-    """Build (once; cached under oracle/_ref/cache) an index with the reference's bowtie-build.
-    Returns (basename, genome)."""
+                      with_gaps: bool = False, threads: int = 8, style: str = "flat", builder: str = "reference"):
+    """Build (once; cached under oracle/_ref/cache) an index with the reference's bowtie-build, or — builder="gpu" — with
+    bt_index_build (same files, minutes instead of hours at hg19 scale; needs a GPU).  Returns (basename, genome)."""
     CACHE.mkdir(parents=True, exist_ok=True)
     base = CACHE / f"{tag}_{n_seqs}_{total_len}_{seed}_{ftab_chars}_{off_rate}_{int(with_gaps)}"
     genome = synth_genome_survey(n_seqs, total_len, seed) if style == "survey" else synth_genome(n_seqs, total_len, seed, with_gaps)
     if not Path(str(base) + ".rev.2.ebwt").exists():
         fa = Path(str(base) + ".fa")
         write_fasta(fa, genome)
-        p = subprocess.run([str(REF_BUILD), "-q", "-t", str(ftab_chars), "-o", str(off_rate), "--threads", str(threads), str(fa), str(base)],
-                           capture_output=True, text=True)
-        if p.returncode != 0:
-            raise RuntimeError("bowtie-build failed: " + p.stderr)
+        if builder == "gpu":
+            import bowtie_b200
+            bowtie_b200.build_index(fa, base, off_rate=off_rate, ftab_chars=ftab_chars)
+        else:
+            p = subprocess.run([str(REF_BUILD), "-q", "-t", str(ftab_chars), "-o", str(off_rate), "--threads", str(threads), str(fa), str(base)],
+                               capture_output=True, text=True)
+            if p.returncode != 0:
+                raise RuntimeError("bowtie-build failed: " + p.stderr)
     return base, genome
 
 
