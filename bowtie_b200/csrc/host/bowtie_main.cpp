@@ -21,6 +21,7 @@
 #include <stdlib.h>
 #include <string.h>
 #include <zlib.h>
+#include <unistd.h>
 #include <sys/stat.h>
 #include <algorithm>
 #include <chrono>
@@ -64,7 +65,16 @@ struct Opts {
 	std::string argstr;
 };
 
-static void die(const std::string &m) { fprintf(stderr, "%s\n", m.c_str()); exit(1); }
+/* Errors can surface on the parser thread while the main thread has CUDA work in flight: leaving through exit() there would run
+ * the runtime's teardown under the main thread's feet, so threads other than the main one leave with _exit(). */
+static const std::thread::id g_main_thread = std::this_thread::get_id();
+[[noreturn]] static void leave(int rc) {
+	fflush(stderr);
+	if (std::this_thread::get_id() == g_main_thread) exit(rc);
+	fflush(stdout);
+	_exit(rc);
+}
+static void die(const std::string &m) { fprintf(stderr, "%s\n", m.c_str()); leave(1); }
 
 enum {
 	ARG_PHRED33 = 256, ARG_PHRED64, ARG_SOLEXA, ARG_SOLEXA13, ARG_NOMAQROUND, ARG_NOFW, ARG_NORC, ARG_MAXBTS, ARG_BEST, ARG_STRATA,
@@ -303,7 +313,7 @@ struct Reader {
 			len = pos = 0; eof = false; first = true; recEof = false;
 			return true;
 		}
-		exit(1);
+		leave(1);
 	}
 	bool refill() {                     /* false at end of input */
 		if (eof) return false;
