@@ -232,17 +232,19 @@ def main() -> None:
     ap.add_argument("--reads-per-step", type=int, default=int(os.environ.get("BT_BENCH_READS", 4_000_000)))
     ap.add_argument("--streams", type=int, default=int(os.environ.get("BT_BENCH_STREAMS", 8)),
                     help="batches kept in flight (one bt_context_t + CUDA stream each), like the reference's -p worker threads")
-    ap.add_argument("--policy", default=os.environ.get("BT_BENCH_POLICY", "n2k1"), choices=["n2k1", "best", "paired"],
+    ap.add_argument("--policy", default=os.environ.get("BT_BENCH_POLICY", "n2k1"), choices=["n2k1", "best", "paired", "v0"],
                     help="n2k1: the headline workload (-n 2 -k 1, SURVEY config 4); best: -n 2 --best (config 3, best-first path); "
-                         "paired: -n 3 on 2x100 bp pairs (config 5; value counts PAIRS per second)")
+                         "paired: -n 3 on 2x100 bp pairs (config 5; value counts PAIRS per second); v0: -v 0 exact on the shipped e_coli index (config 2)")
     ap.add_argument("--cpu-sample", type=int, default=int(os.environ.get("BT_BENCH_CPU_SAMPLE", 1_000_000)))
     args = ap.parse_args()
     rank, world, local = int(os.environ.get("RANK", 0)), int(os.environ.get("WORLD_SIZE", 1)), int(os.environ.get("LOCAL_RANK", 0))
+    if args.policy == "v0" and not os.environ.get("BT_BENCH_INDEX"):
+        os.environ["BT_BENCH_INDEX"] = str(REF_DIR / "fixtures" / "e_coli")          # BASELINE configs[1]: the reference's own index
     base, idx_name = pick_index()
-    ref_flags = {"n2k1": ["-n", "2", "-k", "1"], "best": ["-n", "2", "--best"], "paired": ["-n", "3"]}[args.policy]
+    ref_flags = {"n2k1": ["-n", "2", "-k", "1"], "best": ["-n", "2", "--best"], "paired": ["-n", "3"], "v0": ["-v", "0"]}[args.policy]
     R = 2 if args.policy == "paired" else 1                     # reads per work unit
     unit = "pairs/s" if R == 2 else "reads/s"
-    metric = "aligned read pairs/sec (2x100 bp, -n 3 paired-end)" if R == 2 else "aligned reads/sec (100 bp, -n 2)"
+    metric = "aligned read pairs/sec (2x100 bp, -n 3 paired-end)" if R == 2 else "aligned reads/sec (100 bp, -v 0)" if args.policy == "v0" else "aligned reads/sec (100 bp, -n 2)"
     gen = make_pairs if R == 2 else make_reads
     cfg_workload = f"{' '.join(ref_flags)}, {'2x' if R == 2 else ''}{READ_LEN} bp synthetic {'pairs (--fr, fragments N(200,20))' if R == 2 else 'reads'} (1% subs, both strands), index {idx_name}"
 
@@ -292,7 +294,9 @@ def main() -> None:
         bowtie_b200.build_library()
     ix = bowtie_b200.Index(str(base), need_mirror=True, device=local)
     pol = bowtie_b200.Policy(mode=1, mms=3 if R == 2 else 2, khits=1, best=(args.policy == "best"), paired=(R == 2))
-    if args.policy != "n2k1":
+    if args.policy == "v0":
+        pol = bowtie_b200.Policy(mode=0, mms=0, khits=1)
+    if args.policy in ("best", "paired"):
         args.streams = min(args.streams, 3)      # every context of the best-first path owns ~12 GB of arenas
     B, L, slots, mm_cap = args.reads_per_step, READ_LEN, R, 7
     rw = bowtie_b200.BT_HIT_HDR_WORDS + mm_cap
@@ -422,13 +426,14 @@ def main() -> None:
         "dtype": "u32", "data": "synthetic",
         "config": {"workload": cfg_workload, "reads_per_step_per_gpu": B, "index_len_bp": ix.len, "index_device_bytes": ix.device_bytes,
                    "parallelism": f"reads sharded over {world} GPU(s), full index per GPU; {NS} batches in flight per GPU (contexts/streams)",
-                   "l2": f"two alternating read batches of {2 * B * L / 1e6:.0f} MB each (> 126 MB L2); the index ({ix.device_bytes / 1e6:.0f} MB on the device) exceeds L2 too",
+                   "l2": f"two alternating read batches of {2 * B * L / 1e6:.0f} MB each (> 126 MB L2); the index ({ix.device_bytes / 1e6:.0f} MB on the device) "
+                         + ("exceeds L2 too" if ix.device_bytes > 126e6 else "is L2-resident (the reference's own e_coli index)"),
                    "aligned_frac_last_step": aligned / B, "aligned_frac_last_e2e_step": e2e_aligned / B, "overflow_flags": flags_bad,
                    "counters_allreduced": [int(x) for x in ctr.tolist()]},
         "clocks": clk.summary(),
         "e2e": {"value": e2e_val, "unit": unit, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
         # per step: 3 ctl_set, main search, 3 collect, heavy search, overflow search (best-first / paired: 4 ctl_set, 4 arena tiers, 3 collect)
-        "gpu_launches": (9 if args.policy == "n2k1" else 11) * args.steps,
+        "gpu_launches": (9 if args.policy in ("n2k1", "v0") else 11) * args.steps,
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
                      "peak_source": "MEASURED_PEAKS.json hbm_gbs" if peaks else "fallback 6650 GB/s",
                      "side_fetches_per_read": st.side_fetches / (B * args.steps), "block_loads_per_read": st.block_loads / (B * args.steps),

@@ -8,6 +8,7 @@ timeout 900 python -m pytest tests -m gpu -q -n 4 --timeout 300 > gpurun_out/r2_
 BT_TEST_GPU_BUILD=1 timeout 600 python -m pytest tests/test_index_build.py -m gpu -q --timeout 500 > gpurun_out/r2_pytest_build.log 2>&1; lap "index builder (CUB backend)" $?; tail -3 gpurun_out/r2_pytest_build.log
 timeout 300 python tools/fuzz_cli.py --gpu --iters 60 --seed 2026 > gpurun_out/r2_fuzz_gpu.log 2>&1; lap "fuzz --gpu" $?; tail -2 gpurun_out/r2_fuzz_gpu.log
 timeout 200 python bench.py --steps 5 --warmup 3 > gpurun_out/r2_bench_n2k1.json 2> gpurun_out/r2_bench_n2k1.err; lap "bench n2k1" $?; tail -c 400 gpurun_out/r2_bench_n2k1.json
+timeout 200 python bench.py --policy v0 --steps 5 --warmup 3 > gpurun_out/r2_bench_v0.json 2> gpurun_out/r2_bench_v0.err; lap "bench v0 (config 2)" $?; tail -c 400 gpurun_out/r2_bench_v0.json
 BT_BENCH_READS=1000000 timeout 200 python bench.py --policy best --steps 3 --warmup 3 --cpu-sample 500000 > gpurun_out/r2_bench_best.json 2> gpurun_out/r2_bench_best.err; lap "bench best" $?; tail -c 400 gpurun_out/r2_bench_best.json
 BT_BENCH_READS=1000000 timeout 200 python bench.py --policy paired --steps 3 --warmup 3 --cpu-sample 300000 > gpurun_out/r2_bench_paired.json 2> gpurun_out/r2_bench_paired.err; lap "bench paired" $?; tail -c 400 gpurun_out/r2_bench_paired.json
 BT_BENCH_READS=200000 BT_BENCH_STREAMS=1 timeout 300 ncu --metrics gpu__time_duration.sum --clock-control none -c 200 --csv --log-file gpurun_out/r2_launches_best.csv python bench.py --policy best --steps 2 --warmup 3 --cpu-sample 1000 > gpurun_out/r2_ncu_best.log 2>&1; lap "launch list best" $?
