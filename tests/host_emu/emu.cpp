@@ -9,6 +9,7 @@
 #define BT_HOST_EMU 1
 #include <stdlib.h>
 #include <string.h>
+#include <stdio.h>
 #include <vector>
 #include "../../bowtie_b200/csrc/bt_native.cuh"
 extern "C" {
@@ -61,6 +62,10 @@ int emu_align(void *fwp, void *bwp, const BtPolicy *pol, uint32_t nreads, const 
 	bt_build_prog(pol->mode, pol->mms, pol->nofw, pol->norc, P.prog);
 	BtLane L; memset(&L, 0, sizeof L);
 	std::vector<uint8_t> stage;
+	/* BT_EMU_PC_HIST=1: how many transitions of each kind the batch took (where a lane's iterations go; development aid) */
+	static unsigned long long hist_store[40];
+	unsigned long long *pc_hist = getenv("BT_EMU_PC_HIST") ? hist_store : NULL, *lfk_hist = hist_store + 32;
+	if (pc_hist) memset(hist_store, 0, sizeof hist_store);
 	for (uint32_t r = 0; r < nreads; r++) {
 		bt_begin_read(L, P, r);
 		/* the lane's writable copy of the read (shared memory on the device) */
@@ -71,11 +76,21 @@ int emu_align(void *fwp, void *bwp, const BtPolicy *pol, uint32_t nreads, const 
 		L.hasN = memchr(stage.data(), 4, L.rlen) != NULL;
 		unsigned long long guard = 0; uint32_t it0 = L.s_iter;
 		while (L.pc != PC_FINISH_READ) {
+			if (pc_hist) { pc_hist[L.pc < 32 ? L.pc : 31]++; if (L.pc == PC_LF) lfk_hist[L.lfk & 7]++; }
 			if (BT_IS_FAST(L.pc)) bt_fast_iter(L, P, S); else bt_rare_iter(L, P, S);
 			if (++guard > (1ull << 34)) return 1;
 		}
 		bt_finish_read(L, P);
 		if (iters_per_read) iters_per_read[r] = L.s_iter - it0;
+	}
+	if (pc_hist) {
+		static const char *names[] = { "LF", "CHASE", "PHASE", "BT_BEGIN", "FRAME_ENTER", "POS", "BTLOOP", "CHILD_RET", "POS_END", "FRAME_RET", "REPORT", "REPORT_ROW", "RESOLVE", "REPORT_RET", "BT_END" };
+		unsigned long long tot = 0;
+		for (int i = 0; i < 15; i++) tot += pc_hist[i];
+		fprintf(stderr, "transitions per read: %.1f\n", (double)tot / nreads);
+		for (int i = 0; i < 15; i++) fprintf(stderr, "  %-12s %8.2f per read  %5.1f %%\n", names[i], (double)pc_hist[i] / nreads, 100.0 * pc_hist[i] / tot);
+		static const char *lk[] = { "EX", "ONE", "PAIR", "FCHR", "NONE" };
+		for (int i = 0; i < 5; i++) fprintf(stderr, "  LF kind %-5s %8.2f per read\n", lk[i], (double)lfk_hist[i] / nreads);
 	}
 	stats[0] = L.s_lfex; stats[1] = L.s_lf; stats[2] = L.s_chase; stats[3] = L.s_ftab; stats[4] = L.s_offs; stats[5] = L.s_bt; stats[6] = L.s_iter; stats[7] = L.s_blk;
 	return 0;
