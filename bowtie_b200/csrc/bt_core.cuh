@@ -853,6 +853,26 @@ BT_FN void bt_fast_iter(BtLane &L, const BtKParams &P, const BtScratch &S) {
 	}
 	const uint32_t c = L.c;
 	uint32_t tops[4] = { 0, 0, 0, 0 }, bots[4] = { 0, 0, 0, 0 };
+#ifdef BT_UNIFIED_LF
+	/* Experiment (profiles/README.md, "What a lane does"): the three LF kinds are about equally frequent, so a warp usually
+	 * runs all three code paths back to back.  One path instead: the quartet on both rows, from which every kind's result
+	 * follows — mapLF1's is bots[c] - tops[c] == 1 exactly when rowL(top) == c and top is not the '$' row (the block's A count
+	 * skips '$').  Counters keep the reference's meaning.  Off by default until measured. */
+	if (L.lfk <= LFK_PAIR) {
+		bt_lf_ex(ix, bA, L.ltop, tops);
+		if (L.lfk == LFK_ONE) {
+			const uint32_t o1 = (L.ltop & 63) + 1;                        /* the row after top: same block unless top is its last row */
+			if (o1 < 64) bt_lf_ex(ix, bA, L.ltop + 1, bots);
+			else { const uint32_t rl = bt_row_l(bA, L.ltop); bots[0] = tops[0]; bots[1] = tops[1]; bots[2] = tops[2]; bots[3] = tops[3]; if (L.top != ix.zOff) bots[rl]++; }
+		} else bt_lf_ex(ix, bB, L.lbot, bots);
+		if (L.lfk == LFK_EX) { L.s_lfex++; if (c < 4) { L.top = tops[c]; L.bot = bots[c]; } }
+		else if (L.lfk == LFK_ONE) {
+			const bool hit = c < 4 && bots[c] != tops[c];
+			L.top = hit ? tops[c] : BT_OFF_MASK; L.bot = hit ? tops[c] + 1 : BT_OFF_MASK;
+			L.s_lf++;
+		} else { L.top = tops[c & 3]; L.bot = bots[c & 3]; L.s_lf += 2; }   /* (bt_position reads tops/bots only for LFK_EX / LFK_FCHR) */
+	} else
+#else
 	if (L.lfk == LFK_EX) {
 		/* mapLFEx(ltop, lbot, tops, bots) (ebwt.h:2334-2380) */
 		bt_lf_ex(ix, bA, L.ltop, tops);
@@ -871,7 +891,9 @@ BT_FN void bt_fast_iter(BtLane &L, const BtKParams &P, const BtScratch &S) {
 		const uint32_t t = bt_lf(ix, bA, L.ltop, c), b = bt_lf(ix, bB, L.lbot, c);
 		L.top = t; L.bot = b;
 		L.s_lf += 2;
-	} else if (L.lfk == LFK_FCHR) {
+	} else
+#endif
+	if (L.lfk == LFK_FCHR) {
 		/* first quartet from fchr[] (ebwt_search_backtrack.h:531-543) */
 		tops[0] = ix.fchr[0]; tops[1] = ix.fchr[1]; tops[2] = ix.fchr[2]; tops[3] = ix.fchr[3];
 		bots[0] = ix.fchr[1]; bots[1] = ix.fchr[2]; bots[2] = ix.fchr[3]; bots[3] = ix.fchr[4];
