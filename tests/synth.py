@@ -22,7 +22,13 @@ def synth_genome_survey(n_seqs: int, total_len: int, seed: int) -> list[tuple[st
     out = []
     for s in range(n_seqs):
         L = max(20000, int(sizes[s]))
-        g = rng.choice(acgt, size=L, p=p).copy()
+        if total_len >= 1_000_000_000:
+            # hg19 scale: a 256-entry table realises the base frequencies (76/52/52/76 of 256) ~30x faster than choice(p=...);
+            # smaller genomes keep the original stream so that cached indexes still match their genomes
+            lut = np.repeat(acgt, [76, 52, 52, 76])
+            g = lut[rng.integers(0, 256, size=L, dtype=np.uint8)]
+        else:
+            g = rng.choice(acgt, size=L, p=p).copy()
         for fam, cover in ((fams[0], 0.07), (fams[1], 0.03)):
             fl = len(fam)
             for _ in range(max(1, int(L * cover / fl))):
