@@ -220,3 +220,21 @@ def test_cli_fastq_fast_path_matches_reference(threads, cli, tmp_path):
         outs.append((out.read_bytes(), [l for l in p.stderr.splitlines() if l.startswith("#") or l.startswith("Reported")]))
     assert outs[0] == outs[1]
     assert outs[0][0].count(b"\n") > 5000
+
+
+@pytest.mark.parametrize("flags", [[], ["-S"], ["--best", "-k", "3", "-S"]], ids=["default", "sam", "best-sam"])
+def test_cli_parallel_formatting_matches_reference(flags, cli, tmp_path):
+    """Batches of >= 16384 units are formatted by several threads into private buffers that are written in read order."""
+    build_shim()
+    env = dict(os.environ, LD_LIBRARY_PATH=str(SHIM_DIR))
+    lines = (FIXTURES / "e_coli_1000.fq").read_text().splitlines()
+    recs = [lines[i:i + 4] for i in range(0, len(lines), 4)]
+    fq = tmp_path / "big.fq"
+    fq.write_text("".join(f"{r[0]}_{k}\n{r[1]}\n+\n{r[3]}\n" for k in range(20) for r in recs))
+    outs = []
+    for exe, extra, e in ((REF_ALIGN, ["-p", "1"], None), (cli, ["-p", "4", "--reads-per-batch", "32768"], env)):
+        out = tmp_path / f"{Path(exe).name}.out"
+        p = subprocess.run([str(exe), "-n", "2", *flags, *extra, "-x", str(FIXTURES / "e_coli"), str(fq), str(out)], capture_output=True, text=True, env=e)
+        assert p.returncode == 0, p.stderr
+        outs.append(b"".join(l for l in out.read_bytes().splitlines(keepends=True) if not l.startswith(b"@PG")))
+    assert outs[0] == outs[1] and outs[0].count(b"\n") > 13000
