@@ -403,7 +403,8 @@ struct Reader {
 	std::vector<FqSpan> spans_;
 	double t_scan = 0, t_work = 0;      /* BT_CLI_TIMING */
 	bool fast_ok() const { return o.format == FASTQ && f && !first && !keepOrig && o.trim5 == 0 && o.trim3 == 0 && !o.solexaQuals && !o.phred64Quals && !o.integerQuals; }
-	size_t fast_batch(std::vector<ReadRec> &recs, std::vector<uint32_t> &seeds, size_t maxRecs, size_t nth, uint32_t gseed) {
+	size_t fast_batch(std::vector<ReadRec> &recs, std::vector<uint32_t> &seeds, std::vector<uint8_t> &bseq, std::vector<uint8_t> &bqual, std::vector<uint64_t> &boffs,
+	                  size_t maxRecs, size_t nth, uint32_t gseed) {
 		std::vector<FqSpan> &spans = spans_;        /* (a member: worker threads must see this thread's list) */
 		spans.clear();
 		const auto tq0 = std::chrono::steady_clock::now();
@@ -437,6 +438,12 @@ struct Reader {
 		t_scan += std::chrono::duration<double>(tq1 - tq0).count();
 		const size_t r0 = recs.size();
 		recs.resize(r0 + n); seeds.resize(r0 + n);
+		/* every record of the run has as many bases as its sequence line is long (anything else ends the run below), so the
+		 * offsets are known before the lines are touched and the threads write straight into the batch's arrays */
+		const uint64_t at0 = boffs.back();
+		boffs.resize(r0 + n + 1);
+		for (size_t k = 0; k < n; k++) boffs[r0 + k + 1] = boffs[r0 + k] + spans[k].n2;
+		bseq.resize((size_t)boffs[r0 + n]); bqual.resize((size_t)boffs[r0 + n]);
 		std::vector<uint8_t> okv(n, 1);
 		if (nth > n / 2048 + 1) nth = n / 2048 + 1;
 		const uint64_t id0 = rdid;
@@ -445,16 +452,25 @@ struct Reader {
 				const FqSpan &sp = spans[k];
 				ReadRec &r = recs[r0 + k];
 				if (sp.n1) r.name.assign(base + sp.l1, sp.n1); else r.name = std::to_string(id0 + k);
-				r.seq.resize(sp.n2);
-				size_t m = 0;
-				for (size_t i = 0; i < sp.n2; i++) { const uint8_t code = alpha_code[(unsigned char)base[sp.l2 + i]]; if (code != 255) r.seq[m++] = (char)code; }
-				r.seq.resize(m);
-				bool ok = (m == sp.n4) && m == sp.n2 && (sp.n1 == 0 || !memchr(base + sp.l1, '\r', sp.n1));
-				for (size_t i = 0; ok && i < sp.n4; i++) if ((unsigned char)base[sp.l4 + i] < 33) ok = false;
+				r.seq.clear(); r.qual.clear(); r.orig.clear();
+				uint8_t *sq = bseq.data() + boffs[r0 + k], *ql = bqual.data() + boffs[r0 + k];
+				bool ok = (sp.n2 == sp.n4) && (sp.n1 == 0 || !memchr(base + sp.l1, '\r', sp.n1));
+				uint32_t rseed = (gseed + 101u) * 59u * 61u * 67u * 71u * 73u * 79u * 83u;      /* genRandSeed (pat.cpp:21-57), fused into the conversion */
+				for (size_t i = 0; ok && i < sp.n2; i++) {
+					const uint8_t code = alpha_code[(unsigned char)base[sp.l2 + i]];
+					if (code == 255) { ok = false; break; }
+					sq[i] = code;
+					rseed ^= ((uint32_t)code << ((i & 15) << 1));
+				}
+				for (size_t i = 0; ok && i < sp.n4; i++) {
+					const unsigned char q = (unsigned char)base[sp.l4 + i];
+					if (q < 33) { ok = false; break; }
+					ql[i] = q;
+					rseed ^= ((uint32_t)q << ((i & 3) << 3));
+				}
 				if (!ok) { okv[k] = 0; continue; }
-				r.qual.assign(base + sp.l4, sp.n4);
-				r.orig.clear();
-				seeds[r0 + k] = gen_rand_seed(r, gseed);
+				for (size_t i = 0; i < r.name.size(); i++) rseed ^= ((uint32_t)(uint8_t)r.name[i] << ((i & 3) << 3));
+				seeds[r0 + k] = rseed;
 			}
 		};
 		if (nth <= 1) work(0, n);
@@ -467,6 +483,8 @@ struct Reader {
 		size_t good = 0;
 		while (good < n && okv[good]) good++;
 		recs.resize(r0 + good); seeds.resize(r0 + good);
+		boffs.resize(r0 + good + 1); bseq.resize((size_t)boffs[r0 + good]); bqual.resize((size_t)boffs[r0 + good]);
+		(void)at0;
 		pos = good ? spans[good - 1].end : pos;
 		rdid += good;
 		return good;
@@ -770,11 +788,18 @@ static void put_upto_ws(std::string &o, const char *s, bool ws) {      /* printU
 	o.append(s, n);
 }
 
+/* What the formatters need of a read: its name and its slice of the batch's base-code / quality arrays (the arrays the search sees). */
+struct RView { const std::string &name; const uint8_t *seq; const char *qual; size_t len; };
+static inline void put_qual(std::string &o, const RView &r, bool fw) {
+	if (fw) o.append(r.qual, r.len);
+	else for (size_t i = r.len; i > 0; i--) o += r.qual[i - 1];
+}
+
 struct HitView { uint32_t tidx, toff, oms, cost, stratum, fw, nmm; const uint32_t *mm; uint32_t mate = 0, mtoff = 0, mfw = 0, mlen = 0; };   /* mate: Hit::mate (0 = unpaired), then Hit::mh.second, mfw, mlen */
 
 /* VerboseHitSink::append (hit.cpp:73-301), partition == 0 */
-static void append_default(std::string &o, const Opts &op, const bt_index_t *ix, const ReadRec &r, const HitView &h) {
-	const size_t len = r.seq.size();
+static void append_default(std::string &o, const Opts &op, const bt_index_t *ix, const RView &r, const HitView &h) {
+	const size_t len = r.len;
 	size_t field = 0; bool firstfield = true;
 	auto sep = [&]() { if (firstfield) firstfield = false; else o += '\t'; };
 	if (!op.suppress[field++]) { sep(); o += r.name; }
@@ -792,7 +817,7 @@ static void append_default(std::string &o, const Opts &op, const bt_index_t *ix,
 	}
 	if (!op.suppress[field++]) {
 		sep();
-		if (h.fw) o += r.qual; else o.append(r.qual.rbegin(), r.qual.rend());
+		put_qual(o, r, h.fw != 0);
 	}
 	if (!op.suppress[field++]) { sep(); put_uint(o, h.oms); }
 	if (!op.suppress[field++]) {
@@ -822,8 +847,8 @@ static void append_qname(std::string &o, const Opts &op, const std::string &name
 }
 
 /* SAMHitSink::append (sam.cpp:129-257), unpaired */
-static void append_sam(std::string &o, const Opts &op, const bt_index_t *ix, const ReadRec &r, const HitView &h, int mapq, int xms) {
-	const size_t len = r.seq.size();
+static void append_sam(std::string &o, const Opts &op, const bt_index_t *ix, const RView &r, const HitView &h, int mapq, int xms) {
+	const size_t len = r.len;
 	append_qname(o, op, h.mate ? r.name.substr(0, r.name.size() >= 2 ? r.name.size() - 2 : 0) : r.name);
 	uint32_t flags = h.fw ? 0 : 16;
 	if (h.mate == 1) flags |= 1 | 64 | 2; else if (h.mate == 2) flags |= 1 | 128 | 2;      /* PAIRED | FIRST/SECOND_IN_PAIR | MAPPED_PAIRED */
@@ -844,7 +869,7 @@ static void append_sam(std::string &o, const Opts &op, const bt_index_t *ix, con
 	if (h.fw) for (size_t i = 0; i < len; i++) o += "ACGTN"[(int)r.seq[i]];
 	else for (size_t i = len; i > 0; i--) { int c = r.seq[i - 1]; o += "ACGTN"[c < 4 ? (c ^ 3) : 4]; }
 	o += '\t';
-	if (h.fw) o += r.qual; else o.append(r.qual.rbegin(), r.qual.rend());
+	put_qual(o, r, h.fw != 0);
 	o += "\tXA:i:"; put_uint(o, h.stratum);
 	o += "\tMD:Z:";
 	/* mms[] is indexed from the 5' end; MD runs along the reference: 5'->3' for fw, reversed for rc */
@@ -861,12 +886,12 @@ static void append_sam(std::string &o, const Opts &op, const bt_index_t *ix, con
 }
 
 /* SAMHitSink::reportUnOrMax (sam.cpp:57-124), unpaired, un == true */
-static void append_sam_unaligned(std::string &o, const Opts &op, const ReadRec &r, int mate = 0) {
+static void append_sam_unaligned(std::string &o, const Opts &op, const RView &r, int mate = 0) {
 	append_qname(o, op, mate ? r.name.substr(0, r.name.size() >= 2 ? r.name.size() - 2 : 0) : r.name);
 	o += mate == 0 ? "\t4" : mate == 1 ? "\t77" : "\t141";                               /* UNMAPPED [| PAIRED | FIRST/SECOND | MATE_UNMAPPED] */
 	o += "\t*\t0\t0\t*\t*\t0\t0\t";
-	for (size_t i = 0; i < r.seq.size(); i++) o += "ACGTN"[(int)r.seq[i]];
-	o += '\t'; o += r.qual;
+	for (size_t i = 0; i < r.len; i++) o += "ACGTN"[(int)r.seq[i]];
+	o += '\t'; o.append(r.qual, r.len);
 	o += "\tXM:i:0\n";
 }
 
@@ -975,8 +1000,8 @@ int main(int argc, char **argv) {
 	/* What the workers say about reads too short to search (the search itself leaves them unaligned): search_1mm_phase1.c:12-15,
 	 * search_23mm_phase1.c:13-20, search_seeded_phase1.c:17-21, aligner.h:440-448,744-751 */
 	const bool statefulU = polU.best || polU.strata || polU.sample_max || (!op.maqLike && op.mismatches == 3);
-	auto short_read_check = [&](const ReadRec &a, const ReadRec *mate) {
-		const size_t la = a.seq.size();
+	auto short_read_check = [&](const ReadRec &a, const ReadRec *mate, size_t knownLen = (size_t)-1) {
+		const size_t la = knownLen != (size_t)-1 ? knownLen : a.seq.size();
 		if (mate) {
 			if ((la < 4 || mate->seq.size() < 4) && !op.quiet) fprintf(stderr, "Warning: Skipping pair %s because a mate is less than 4 characters long\n", a.name.c_str());
 		} else if (statefulU) {
@@ -1009,14 +1034,8 @@ int main(int argc, char **argv) {
 					/* plain single-end FASTQ: whole runs of records at a time, parsed by several threads (Reader::fast_batch) */
 					const size_t r0 = b.reads.size();
 					const size_t want = std::min<size_t>((size_t)op.batch - r0, (size_t)(op.qUpto - rd.rdid));
-					if (rd.fast_batch(b.reads, b.seeds, want, fmtThreads, op.seed) > 0) {
-						for (size_t k = r0; k < b.reads.size(); k++) {
-							const ReadRec &rr = b.reads[k];
-							if (rr.seq.size() < 4) short_read_check(rr, NULL);
-							b.seq.insert(b.seq.end(), rr.seq.begin(), rr.seq.end());
-							b.qual.insert(b.qual.end(), rr.qual.begin(), rr.qual.end());
-							b.offs.push_back(b.seq.size());
-						}
+					if (rd.fast_batch(b.reads, b.seeds, b.seq, b.qual, b.offs, want, fmtThreads, op.seed) > 0) {
+						for (size_t k = r0; k < b.reads.size(); k++) if (b.offs[k + 1] - b.offs[k] < 4) short_read_check(b.reads[k], NULL, (size_t)(b.offs[k + 1] - b.offs[k]));
 						continue;
 					}
 				}
@@ -1088,7 +1107,7 @@ int main(int argc, char **argv) {
 				size_t g1 = g0; uint32_t gSlots = 1, gLen = 1;
 				while (g1 < order.size()) {
 					const uint32_t i = need[order[g1]];
-					uint32_t rl = (uint32_t)b.reads[i * mult].seq.size(); if (paired) rl = std::max<uint32_t>(rl, (uint32_t)b.reads[i * mult + 1].seq.size());
+					uint32_t rl = (uint32_t)(b.offs[i * mult + 1] - b.offs[i * mult]); if (paired) rl = std::max<uint32_t>(rl, (uint32_t)(b.offs[i * mult + 2] - b.offs[i * mult + 1]));
 					const uint32_t sl = std::max<uint32_t>(1, std::min(b.found[i], storeLim)), ln = std::max<uint32_t>(gLen, rl);
 					if (g1 > g0 && (g1 - g0 + 1) * (size_t)sl * (BT_HIT_HDR_WORDS + ln) > budgetWords) break;
 					gSlots = sl; gLen = ln; g1++;                                /* sorted by found: the last read sets the slot count */
@@ -1120,8 +1139,10 @@ int main(int argc, char **argv) {
 		/* formats the units [lo, hi) into `obuf`; cnt = { aligned, unaligned, maxed, reported, reportedPaired } */
 		auto emit_range = [&](size_t lo, size_t hi, std::string &obuf, uint64_t cnt[5], bool serial) {
 		size_t ni = (size_t)(std::lower_bound(need.begin(), need.end(), (uint32_t)lo) - need.begin());
+		auto view = [&](size_t idx) { return RView{ b.reads[idx].name, b.seq.data() + b.offs[idx], (const char *)b.qual.data() + b.offs[idx], (size_t)(b.offs[idx + 1] - b.offs[idx]) }; };
+		auto rlen = [&](size_t idx) { return (uint32_t)(b.offs[idx + 1] - b.offs[idx]); };
 		for (size_t i = lo; i < hi; i++) {
-			const ReadRec &r = b.reads[i * mult];
+			const RView r = view(i * mult);
 			const uint32_t *recs = &b.hits[i * b.slots * rw]; size_t rwi = rw; uint32_t found = b.found[i];
 			if (ni < need.size() && need[ni] == i) { rwi = rw2[ni]; recs = hits2.data() + off2[ni]; found = found2[ni]; ni++; }
 			/* HitSinkPerThread::finishRead (hit.h:741-786) */
@@ -1154,8 +1175,8 @@ int main(int argc, char **argv) {
 							for (uint32_t k = s; k < s + 2; k++) {
 								const uint32_t *w = recs + (size_t)k * rwi, *mw = recs + (size_t)(k ^ 1) * rwi;
 								HitView h = { w[0], w[1], nbuf / 2, w[3] & 0xffffu, (w[3] >> 16) & 0xff, (w[3] >> 24) & 1, w[4], w + BT_HIT_HDR_WORDS };
-								h.mate = (w[3] >> 25) & 3; h.mtoff = mw[1]; h.mfw = (mw[3] >> 24) & 1; h.mlen = (uint32_t)b.reads[i * mult + (2 - h.mate)].seq.size();
-								const ReadRec &rr2 = b.reads[i * mult + (h.mate - 1)];
+								h.mate = (w[3] >> 25) & 3; h.mtoff = mw[1]; h.mfw = (mw[3] >> 24) & 1; h.mlen = rlen(i * mult + (2 - h.mate));
+								const RView rr2 = view(i * mult + (h.mate - 1));
 								if (op.sam) append_sam(obuf, op, ix, rr2, h, 0, (int)(nbuf / 2) + 1); else append_default(obuf, op, ix, rr2, h);
 							}
 							break;
@@ -1167,7 +1188,7 @@ int main(int argc, char **argv) {
 			else if (unal) {
 				cnt[1]++;
 				if (serial) dump_unit(op.dumpUn, b, i);
-				if (op.sam && !op.noUnal) { if (paired && !b.reads[i * mult + 1].seq.empty()) { append_sam_unaligned(obuf, op, r, 1); append_sam_unaligned(obuf, op, b.reads[i * mult + 1], 2); } else append_sam_unaligned(obuf, op, r); }   /* `paired = !p.bufb().empty()`, sam.cpp:75 */
+				if (op.sam && !op.noUnal) { if (paired && rlen(i * mult + 1) != 0) { append_sam_unaligned(obuf, op, r, 1); append_sam_unaligned(obuf, op, view(i * mult + 1), 2); } else append_sam_unaligned(obuf, op, r); }   /* `paired = !p.bufb().empty()`, sam.cpp:75 */
 			} else {
 				uint32_t nrep = std::min(found, nlimU);
 				for (uint32_t s = 0; s < nrep; s++) {
@@ -1175,13 +1196,14 @@ int main(int argc, char **argv) {
 					HitView h = { w[0], w[1], w[2], w[3] & 0xffffu, (w[3] >> 16) & 0xff, (w[3] >> 24) & 1, w[4], w + BT_HIT_HDR_WORDS };
 					if (op.strata) h.oms = found / mult - 1;                    /* NBestFirstStratHitSinkPerThread::finishReadImpl (hit.h:1099-1108): sz / mult - 1 */
 					h.mate = (w[3] >> 25) & 3;
-					const ReadRec *rr = &r;
+					size_t ridx = i * mult;
 					if (h.mate) {                                               /* records come in (upstream, downstream) couples */
 						const uint32_t *mw = recs + (size_t)(s ^ 1) * rwi;
-						rr = &b.reads[i * mult + (h.mate - 1)];
-						h.mtoff = mw[1]; h.mfw = (mw[3] >> 24) & 1; h.mlen = (uint32_t)b.reads[i * mult + (2 - h.mate)].seq.size();
+						ridx = i * mult + (h.mate - 1);
+						h.mtoff = mw[1]; h.mfw = (mw[3] >> 24) & 1; h.mlen = rlen(i * mult + (2 - h.mate));
 					}
-					if (op.sam) append_sam(obuf, op, ix, *rr, h, op.defaultMapq, (int)(nrep / mult)); else append_default(obuf, op, ix, *rr, h);
+					const RView rv = view(ridx);
+					if (op.sam) append_sam(obuf, op, ix, rv, h, op.defaultMapq, (int)(nrep / mult)); else append_default(obuf, op, ix, rv, h);
 				}
 				cnt[0]++; if (paired) cnt[4] += nrep; else cnt[3] += nrep;
 				if (serial) dump_unit(op.dumpAl, b, i);

