@@ -791,15 +791,23 @@ static void put_upto_ws(std::string &o, const char *s, bool ws) {      /* printU
 /* What the formatters need of a read: its name and its slice of the batch's base-code / quality arrays (the arrays the search sees). */
 struct RView { const std::string &name; const uint8_t *seq; const char *qual; size_t len; };
 static inline void put_qual(std::string &o, const RView &r, bool fw) {
-	if (fw) o.append(r.qual, r.len);
-	else for (size_t i = r.len; i > 0; i--) o += r.qual[i - 1];
+	if (fw) { o.append(r.qual, r.len); return; }
+	const size_t at = o.size(); o.resize(at + r.len);
+	char *d = &o[at];
+	for (size_t i = 0; i < r.len; i++) d[i] = r.qual[r.len - 1 - i];
+}
+/* the read as it is printed: as given, or reverse-complemented for a '-' hit */
+static inline void put_seq(std::string &o, const RView &r, bool fw) {
+	const size_t at = o.size(); o.resize(at + r.len);
+	char *d = &o[at];
+	if (fw) for (size_t i = 0; i < r.len; i++) d[i] = "ACGTN"[r.seq[i]];
+	else for (size_t i = 0; i < r.len; i++) { const int c = r.seq[r.len - 1 - i]; d[i] = "ACGTN"[c < 4 ? (c ^ 3) : 4]; }
 }
 
 struct HitView { uint32_t tidx, toff, oms, cost, stratum, fw, nmm; const uint32_t *mm; uint32_t mate = 0, mtoff = 0, mfw = 0, mlen = 0; };   /* mate: Hit::mate (0 = unpaired), then Hit::mh.second, mfw, mlen */
 
 /* VerboseHitSink::append (hit.cpp:73-301), partition == 0 */
 static void append_default(std::string &o, const Opts &op, const bt_index_t *ix, const RView &r, const HitView &h) {
-	const size_t len = r.len;
 	size_t field = 0; bool firstfield = true;
 	auto sep = [&]() { if (firstfield) firstfield = false; else o += '\t'; };
 	if (!op.suppress[field++]) { sep(); o += r.name; }
@@ -812,8 +820,7 @@ static void append_default(std::string &o, const Opts &op, const bt_index_t *ix,
 	if (!op.suppress[field++]) { sep(); put_int(o, (long long)h.toff + op.offBase); }
 	if (!op.suppress[field++]) {
 		sep();
-		if (h.fw) for (size_t i = 0; i < len; i++) o += "ACGTN"[(int)r.seq[i]];
-		else for (size_t i = len; i > 0; i--) { int c = r.seq[i - 1]; o += "ACGTN"[c < 4 ? (c ^ 3) : 4]; }
+		put_seq(o, r, h.fw != 0);
 	}
 	if (!op.suppress[field++]) {
 		sep();
@@ -866,8 +873,7 @@ static void append_sam(std::string &o, const Opts &op, const bt_index_t *ix, con
 		else ins = (long long)h.mtoff - (long long)h.toff + (long long)h.mlen;
 		put_int(o, (int)ins); o += '\t';
 	} else o += "\t*\t0\t0\t";
-	if (h.fw) for (size_t i = 0; i < len; i++) o += "ACGTN"[(int)r.seq[i]];
-	else for (size_t i = len; i > 0; i--) { int c = r.seq[i - 1]; o += "ACGTN"[c < 4 ? (c ^ 3) : 4]; }
+	put_seq(o, r, h.fw != 0);
 	o += '\t';
 	put_qual(o, r, h.fw != 0);
 	o += "\tXA:i:"; put_uint(o, h.stratum);
@@ -890,7 +896,7 @@ static void append_sam_unaligned(std::string &o, const Opts &op, const RView &r,
 	append_qname(o, op, mate ? r.name.substr(0, r.name.size() >= 2 ? r.name.size() - 2 : 0) : r.name);
 	o += mate == 0 ? "\t4" : mate == 1 ? "\t77" : "\t141";                               /* UNMAPPED [| PAIRED | FIRST/SECOND | MATE_UNMAPPED] */
 	o += "\t*\t0\t0\t*\t*\t0\t0\t";
-	for (size_t i = 0; i < r.len; i++) o += "ACGTN"[(int)r.seq[i]];
+	put_seq(o, r, true);
 	o += '\t'; o.append(r.qual, r.len);
 	o += "\tXM:i:0\n";
 }
