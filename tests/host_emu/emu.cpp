@@ -96,4 +96,82 @@ int emu_align(void *fwp, void *bwp, const BtPolicy *pol, uint32_t nreads, const 
 	return 0;
 }
 
+
+/* Warp-level replay of bt_search_kernel's scheduling (development aid, tools/warp_sim.py): `nwarps` x 32 lanes pull reads from one
+ * cursor and take fast / deferred-rare transitions under the kernel's rule; what comes out is how full the warps are when they
+ * execute each kind of code — the quantity ncu reports as "threads active per instruction" — for a given period / threshold /
+ * budget, without a GPU.  Code paths a warp executes in one iteration: one per LF kind present among its fast lanes, one for the
+ * chase step, one per distinct rare state present when the rare pass runs.  out[]: see the tool. */
+int emu_warp_sim(void *fwp, void *bwp, const BtPolicy *pol, uint32_t nreads, const uint8_t *seq, const uint8_t *qual, const uint64_t *roff,
+                 const uint32_t *seeds, uint32_t nwarps, uint32_t rare_period, uint32_t rare_thresh, uint32_t budget, uint32_t R, uint32_t FCAP, uint32_t PCAP,
+                 double *out) {
+	BtKParams P; memset(&P, 0, sizeof P);
+	P.ix[0] = ((EmuIndex *)fwp)->dev;
+	if (bwp) P.ix[1] = ((EmuIndex *)bwp)->dev;
+	P.pol = *pol;
+	P.seq = seq; P.qual = qual; P.roff = roff; P.seeds = seeds; P.nwork = nreads;
+	const uint32_t slots = 1, mm_cap = 8;
+	std::vector<uint32_t> found(nreads), flags(nreads), hits((size_t)nreads * slots * (BT_HIT_HDR + mm_cap));
+	P.found = found.data(); P.flags = flags.data(); P.hits = hits.data(); P.slots = slots; P.mm_cap = mm_cap; P.rec_words = BT_HIT_HDR + mm_cap;
+	P.R = R; P.FCAP = FCAP; P.PCAP = PCAP; P.rare_period = rare_period ? rare_period : 1; P.rare_thresh = rare_thresh; P.budget = budget;
+	bt_build_prog(pol->mode, pol->mms, pol->nofw, pol->norc, P.prog);
+	const uint32_t nl = nwarps * 32;
+	std::vector<BtLane> lanes(nl);
+	std::vector<std::vector<uint4>> rows(nl); std::vector<std::vector<uint8_t>> elims(nl), stage(nl); std::vector<std::vector<BtFrame>> frames(nl); std::vector<std::vector<uint64_t>> parts(nl);
+	std::vector<BtScratch> S(nl);
+	for (uint32_t i = 0; i < nl; i++) {
+		rows[i].resize(2 * (size_t)R); elims[i].resize(R); frames[i].resize(FCAP); parts[i].resize(PCAP);
+		S[i] = BtScratch{ rows[i].data(), elims[i].data(), frames[i].data(), parts[i].data() };
+		memset(&lanes[i], 0, sizeof(BtLane)); lanes[i].pc = PC_NEXT_READ; lanes[i].hasN = 1;
+	}
+	const int unify = getenv("BT_SIM_UNIFIED") ? atoi(getenv("BT_SIM_UNIFIED")) : 0;   /* 1: one code path for the three LF kinds; 2: the chase step shares it too */
+	uint64_t cursor = 0;
+	/* accumulators */
+	double warpIters = 0, fastPaths = 0, fastLaneSum = 0, rarePasses = 0, rarePaths = 0, rareLaneSum = 0, idleLaneIters = 0, liveLaneIters = 0, budgeted = 0;
+	double fastHist[33]; memset(fastHist, 0, sizeof fastHist);
+	for (uint32_t w = 0; w < nwarps; w++) {
+		BtLane *L = &lanes[w * 32];
+		for (uint32_t it = 0;; it++) {
+			uint32_t nfast = 0, nrare = 0, kinds = 0; bool wasFast[32];
+			for (int l = 0; l < 32; l++) {
+				const uint32_t pc = L[l].pc;
+				wasFast[l] = BT_IS_FAST(pc);
+				if (wasFast[l]) { nfast++; kinds |= (pc == PC_CHASE) ? (unify >= 2 ? 1u : 16u) : (unify ? 1u : (1u << (L[l].lfk & 3))); }
+				else if (pc != PC_EXIT) nrare++;
+			}
+			if (nfast + nrare == 0) break;
+			warpIters++; liveLaneIters += nfast + nrare;
+			const bool run_rare = (nfast == 0) || (nrare >= P.rare_thresh) || ((it % P.rare_period) == 0);
+			if (run_rare && nrare) {
+				uint32_t pcs = 0;
+				for (int l = 0; l < 32; l++) {
+					BtLane &X = L[l];
+					if (X.pc == PC_FINISH_READ) { bt_finish_read(X, P); X.pc = PC_NEXT_READ; }
+					if (X.pc == PC_NEXT_READ) {
+						if (cursor < nreads) {
+							const uint32_t rid = (uint32_t)cursor++;
+							bt_begin_read(X, P, rid);
+							std::vector<uint8_t> &st = stage[w * 32 + l];
+							st.assign(2 * (size_t)X.rlen + 2, 0);
+							memcpy(st.data(), seq + roff[rid], X.rlen); memcpy(st.data() + X.rlen, qual + roff[rid], X.rlen);
+							X.rseq = st.data(); X.rqual = st.data() + X.rlen; X.hasN = memchr(st.data(), 4, X.rlen) != NULL;
+						} else X.pc = PC_EXIT;
+						pcs |= 1u << 31;
+					}
+					if (BT_IS_RARE_STEP(X.pc)) { pcs |= 1u << (X.pc & 31); const uint32_t f0 = X.flags; bt_rare_iter(X, P, S[w * 32 + l]); if ((X.flags & ~f0) & BT_FLAG_BUDGET) budgeted++; }
+				}
+				rarePasses++; rarePaths += __builtin_popcount(pcs); rareLaneSum += nrare;
+			}
+			if (nfast) {                                                  /* `fast` is sampled before the rare pass, as in the kernel */
+				for (int l = 0; l < 32; l++) if (wasFast[l]) bt_fast_iter(L[l], P, S[w * 32 + l]);
+				fastPaths += __builtin_popcount(kinds); fastLaneSum += nfast; fastHist[nfast]++;
+			}
+			idleLaneIters += run_rare ? 0 : nrare;
+		}
+	}
+	out[0] = warpIters; out[1] = fastPaths; out[2] = fastLaneSum; out[3] = rarePasses; out[4] = rarePaths; out[5] = rareLaneSum; out[6] = idleLaneIters; out[7] = liveLaneIters; out[8] = budgeted;
+	for (int i = 0; i <= 32; i++) out[9 + i] = fastHist[i];
+	return 0;
+}
+
 }
