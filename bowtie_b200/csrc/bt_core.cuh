@@ -853,11 +853,12 @@ BT_FN void bt_fast_iter(BtLane &L, const BtKParams &P, const BtScratch &S) {
 	}
 	const uint32_t c = L.c;
 	uint32_t tops[4] = { 0, 0, 0, 0 }, bots[4] = { 0, 0, 0, 0 };
-#ifdef BT_UNIFIED_LF
-	/* Experiment (profiles/README.md, "What a lane does"): the three LF kinds are about equally frequent, so a warp usually
-	 * runs all three code paths back to back.  One path instead: the quartet on both rows, from which every kind's result
-	 * follows — mapLF1's is bots[c] - tops[c] == 1 exactly when rowL(top) == c and top is not the '$' row (the block's A count
-	 * skips '$').  Counters keep the reference's meaning.  Off by default until measured. */
+#ifndef BT_SPLIT_LF
+	/* One code path for the three LF kinds (profiles/README.md, "What a lane does" / "Warp-level replay"): they are about equally
+	 * frequent, so a warp that branches on the kind usually runs all three paths back to back.  Here: the quartet on both rows,
+	 * from which every kind's result follows — mapLF1's is bots[c] - tops[c] == 1 exactly when rowL(top) == c and top is not the
+	 * '$' row (the block's A count skips '$').  Counters keep the reference's meaning.  -DBT_SPLIT_LF restores the three paths
+	 * (`make experiments`) for the A/B that this change still owes: it was made without a GPU, on the replay's prediction. */
 	if (L.lfk <= LFK_PAIR) {
 		bt_lf_ex(ix, bA, L.ltop, tops);
 		if (L.lfk == LFK_ONE) {

@@ -12,9 +12,9 @@ timeout 200 python bench.py --policy v0 --steps 5 --warmup 3 > gpurun_out/r2_ben
 BT_BENCH_READS=1000000 timeout 200 python bench.py --policy best --steps 3 --warmup 3 --cpu-sample 500000 > gpurun_out/r2_bench_best.json 2> gpurun_out/r2_bench_best.err; lap "bench best" $?; tail -c 400 gpurun_out/r2_bench_best.json
 BT_BENCH_READS=1000000 timeout 200 python bench.py --policy paired --steps 3 --warmup 3 --cpu-sample 300000 > gpurun_out/r2_bench_paired.json 2> gpurun_out/r2_bench_paired.err; lap "bench paired" $?; tail -c 400 gpurun_out/r2_bench_paired.json
 BT_BENCH_READS=200000 BT_BENCH_STREAMS=1 timeout 300 ncu --metrics gpu__time_duration.sum --clock-control none -c 200 --csv --log-file gpurun_out/r2_launches_best.csv python bench.py --policy best --steps 2 --warmup 3 --cpu-sample 1000 > gpurun_out/r2_ncu_best.log 2>&1; lap "launch list best" $?
-# A/B of the unified-LF experiment (profiles/README.md): same bench, other library
+# A/B owed for the unified LF path (profiles/README.md): same bench with the three LF kinds on separate paths again
 make -C bowtie_b200/csrc experiments > gpurun_out/r2_make_experiments.log 2>&1
-BOWTIE_B200_LIB=$PWD/bowtie_b200/variants/libbt_unified_lf.so timeout 200 python bench.py --steps 5 --warmup 3 --cpu-sample 1000 > gpurun_out/r2_bench_n2k1_unified.json 2> gpurun_out/r2_bench_n2k1_unified.err; lap "bench n2k1, unified LF" $?; tail -c 300 gpurun_out/r2_bench_n2k1_unified.json
+BOWTIE_B200_LIB=$PWD/bowtie_b200/variants/libbt_split_lf.so timeout 200 python bench.py --steps 5 --warmup 3 --cpu-sample 1000 > gpurun_out/r2_bench_n2k1_splitlf.json 2> gpurun_out/r2_bench_n2k1_splitlf.err; lap "bench n2k1, split LF" $?; tail -c 300 gpurun_out/r2_bench_n2k1_splitlf.json
 # hg19-sized index: only if the builder test above passed
 if grep -q "passed" gpurun_out/r2_pytest_build.log && ! grep -q "failed" gpurun_out/r2_pytest_build.log; then
   timeout 1500 python tools/make_bench_index.py 3000 24 --gpu > gpurun_out/r2_build_3g.log 2>&1; lap "3-Gbp index" $?; tail -2 gpurun_out/r2_build_3g.log
