@@ -861,10 +861,10 @@ BT_FN void bt_fast_iter(BtLane &L, const BtKParams &P, const BtScratch &S) {
 	 * (`make experiments`) for the A/B that this change still owes: it was made without a GPU, on the replay's prediction. */
 	if (L.lfk <= LFK_PAIR) {
 		bt_lf_ex(ix, bA, L.ltop, tops);
-		if (L.lfk == LFK_ONE) {
-			const uint32_t o1 = (L.ltop & 63) + 1;                        /* the row after top: same block unless top is its last row */
-			if (o1 < 64) bt_lf_ex(ix, bA, L.ltop + 1, bots);
-			else { const uint32_t rl = bt_row_l(bA, L.ltop); bots[0] = tops[0]; bots[1] = tops[1]; bots[2] = tops[2]; bots[3] = tops[3]; if (L.top != ix.zOff) bots[rl]++; }
+		if (L.lfk == LFK_ONE) {                                          /* bot = top + 1: the quartet of the next row differs by the one character at top */
+			const uint32_t rl = bt_row_l(bA, L.ltop);
+			bots[0] = tops[0]; bots[1] = tops[1]; bots[2] = tops[2]; bots[3] = tops[3];
+			if (L.top != ix.zOff) bots[rl]++;
 		} else bt_lf_ex(ix, bB, L.lbot, bots);
 		if (L.lfk == LFK_EX) { L.s_lfex++; if (c < 4) { L.top = tops[c]; L.bot = bots[c]; } }
 		else if (L.lfk == LFK_ONE) {
