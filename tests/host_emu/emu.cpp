@@ -124,6 +124,7 @@ int emu_warp_sim(void *fwp, void *bwp, const BtPolicy *pol, uint32_t nreads, con
 		S[i] = BtScratch{ rows[i].data(), elims[i].data(), frames[i].data(), parts[i].data() };
 		memset(&lanes[i], 0, sizeof(BtLane)); lanes[i].pc = PC_NEXT_READ; lanes[i].hasN = 1;
 	}
+	const int rule = getenv("BT_SIM_RULE") ? atoi(getenv("BT_SIM_RULE")) : 0;
 	const int unify = getenv("BT_SIM_UNIFIED") ? atoi(getenv("BT_SIM_UNIFIED")) : 0;   /* 1: one code path for the three LF kinds; 2: the chase step shares it too */
 	uint64_t cursor = 0;
 	/* accumulators */
@@ -141,7 +142,9 @@ int emu_warp_sim(void *fwp, void *bwp, const BtPolicy *pol, uint32_t nreads, con
 			}
 			if (nfast + nrare == 0) break;
 			warpIters++; liveLaneIters += nfast + nrare;
-			const bool run_rare = (nfast == 0) || (nrare >= P.rare_thresh) || ((it % P.rare_period) == 0);
+			bool run_rare = (nfast == 0) || (nrare >= P.rare_thresh) || ((it % P.rare_period) == 0);
+			if (rule == 1) run_rare = run_rare || nrare > nfast;               /* more lanes waiting than working */
+			if (rule == 2) run_rare = (nfast == 0) || nrare >= P.rare_thresh || nrare > nfast;
 			if (run_rare && nrare) {
 				uint32_t pcs = 0;
 				for (int l = 0; l < 32; l++) {
