@@ -862,9 +862,8 @@ BT_FN void bt_fast_iter(BtLane &L, const BtKParams &P, const BtScratch &S) {
 	if (L.lfk <= LFK_PAIR) {
 		bt_lf_ex(ix, bA, L.ltop, tops);
 		if (L.lfk == LFK_ONE) {                                          /* bot = top + 1: the quartet of the next row differs by the one character at top */
-			const uint32_t rl = bt_row_l(bA, L.ltop);
-			bots[0] = tops[0]; bots[1] = tops[1]; bots[2] = tops[2]; bots[3] = tops[3];
-			if (L.top != ix.zOff) bots[rl]++;
+			const uint32_t rl = (L.top != ix.zOff) ? bt_row_l(bA, L.ltop) : 4u;
+			bots[0] = tops[0] + (rl == 0); bots[1] = tops[1] + (rl == 1); bots[2] = tops[2] + (rl == 2); bots[3] = tops[3] + (rl == 3);
 		} else bt_lf_ex(ix, bB, L.lbot, bots);
 		if (L.lfk == LFK_EX) { L.s_lfex++; if (c < 4) { L.top = tops[c]; L.bot = bots[c]; } }
 		else if (L.lfk == LFK_ONE) {
