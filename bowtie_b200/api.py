@@ -27,10 +27,17 @@ def build_library(force: bool = False) -> Path:
     srcs = [p for p in csrc.iterdir() if p.suffix in (".cu", ".cuh", ".h")] + list((csrc / "host").glob("*.cpp")) + [_PKG.parent / "include" / "bowtie_b200.h"]
     clis = [_PKG / "bowtie-b200-align", _PKG / "bowtie-b200-build"]
     newest = max(s.stat().st_mtime for s in srcs)
-    if force or not so.exists() or not all(c.exists() for c in clis) or min([so.stat().st_mtime] + [c.stat().st_mtime for c in clis]) < newest:
-        p = subprocess.run(["make", "-C", str(_PKG / "csrc")], capture_output=True, text=True)
-        if p.returncode != 0:
-            raise RuntimeError("building libbowtie_b200.so failed:\n" + p.stdout + p.stderr)
+
+    def stale() -> bool:
+        return force or not so.exists() or not all(c.exists() for c in clis) or min([so.stat().st_mtime] + [c.stat().st_mtime for c in clis]) < newest
+    if stale():
+        import fcntl
+        with open(_PKG / ".build.lock", "w") as lk:            # several ranks / pytest workers may get here at once: one builds, the rest wait
+            fcntl.flock(lk, fcntl.LOCK_EX)
+            if stale():
+                p = subprocess.run(["make", "-C", str(_PKG / "csrc")], capture_output=True, text=True)
+                if p.returncode != 0:
+                    raise RuntimeError("building libbowtie_b200.so failed:\n" + p.stdout + p.stderr)
     return so
 
 
