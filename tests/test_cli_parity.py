@@ -238,3 +238,16 @@ def test_cli_parallel_formatting_matches_reference(flags, cli, tmp_path):
         assert p.returncode == 0, p.stderr
         outs.append(b"".join(l for l in out.read_bytes().splitlines(keepends=True) if not l.startswith(b"@PG")))
     assert outs[0] == outs[1] and outs[0].count(b"\n") > 13000
+
+
+@pytest.mark.parametrize("rb", ["1", "7"])
+def test_cli_tiny_batches_through_the_pipeline(rb, cli, tmp_path):
+    """Hundreds of batches through the parser-thread ring: batch boundaries must not show in the output."""
+    import hashlib
+    build_shim()
+    env = dict(os.environ, LD_LIBRARY_PATH=str(SHIM_DIR))
+    out = tmp_path / "o.out"
+    p = subprocess.run([str(cli), "-n", "2", "-p", "3", "--reads-per-batch", rb, "-x", str(FIXTURES / "e_coli"), str(FIXTURES / "e_coli_1000.fq"), str(out)],
+                       capture_output=True, text=True, env=env)
+    assert p.returncode == 0, p.stderr
+    assert hashlib.md5(out.read_bytes()).hexdigest() == "7238b0f529dfcdf602f82ae1a754a1bd"      # SURVEY.md 8(c): -n 2
