@@ -2,12 +2,15 @@
  * bowtie_main.cpp — `bowtie`-compatible host driver over libbowtie_b200.so.
  *
  * Keeps the reference's command line (ebwt_search.cpp:443-545, 614-919), read-file formats
- * (pat.cpp: FASTQ 862-975, FASTA 575-640, raw 1168-1213, -c 437-523, --12 980-1124; -1/-2, --interleaved), the default
+ * (pat.cpp: FASTQ 797-975, FASTA 531-640, -F 651-790, raw 1129-1213, -c 357-523, --12 980-1124; -1/-2, --interleaved; light parse
+ * and parse() followed character for character, so malformed input behaves as it does there), the default
  * hit format (hit.cpp:73-301) and SAM (sam.cpp:20-257) for single reads and pairs, the read dumps --al/--un/--max
  * (hit.h:385-492) and the stderr summary (hit.h:270-346); the search itself (everything the reference's
  * *SearchWorker* functions do) is one bt_context_align_async() call per batch of reads or pairs.  --best, --strata,
  * -M and -v 3 select the library's best-first path, paired input its paired-end path; what is not provided is
  * rejected with a message — nothing falls back to a CPU search.
+ * Threads: one parser thread fills a ring of batches (well-formed FASTQ: several conversion threads per buffer), the main
+ * thread launches batch k+1 and formats batch k with -p threads; output order is input order.
  */
 #include <algorithm>
 #include <array>
