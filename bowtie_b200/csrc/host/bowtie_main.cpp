@@ -995,7 +995,8 @@ int main(int argc, char **argv) {
 	};
 	auto dump_unit = [&](const std::string &base, const Batch &b, size_t i) {
 		if (base.empty()) return;
-		if (b.paired) { dump_to(base, 1, b.reads[2 * i].orig); dump_to(base, 2, b.reads[2 * i + 1].orig); }
+		if (b.paired && tabbed) dump_to(base, 0, b.reads[2 * i].orig);           /* onePairFile_ (ebwt_search.cpp:3205,3215): a --12 line holds both mates */
+		else if (b.paired) { dump_to(base, 1, b.reads[2 * i].orig); dump_to(base, 2, b.reads[2 * i + 1].orig); }
 		else dump_to(base, 0, b.reads[i].orig);
 	};
 	ReadRec lrec, lrec2; bool haveLook = false, lookPair = false;                 /* --12: one record of lookahead (a batch is all pairs or all single reads) */

@@ -240,11 +240,41 @@ def main():
             for sub in range(6):
                 if sub < 4:
                     flags = rand_flags(rng)
-                    inputs = [str(td / "r.fq")]
+                    kind = rng.choice(["fq", "fq", "fq", "fa", "raw", "tab", "cmd"])           # every read source of the driver
+                    if kind == "fq":
+                        inputs = [str(td / "r.fq")]
+                    elif kind == "fa":
+                        (td / "r.fa").write_text("".join(f">{n}\n{s}\n" for n, s, q in reads))
+                        inputs = ["-f", str(td / "r.fa")]
+                    elif kind == "raw":
+                        (td / "r.raw").write_text("".join(f"{s}\n" for n, s, q in reads))
+                        inputs = ["-r", str(td / "r.raw")]
+                    elif kind == "tab":
+                        (td / "r.tab").write_text("".join(f"{n}\t{s}\t{q}\n" for n, s, q in reads))
+                        inputs = ["--12", str(td / "r.tab")]
+                    else:
+                        few = [r for r in reads[:12] if len(r[1]) >= 4 and ":" not in r[2] and "," not in r[2]]
+                        if not few:
+                            continue
+                        inputs = ["-c", ",".join(f"{s}:{q}" for n, s, q in few)]
                 else:
                     flags = rand_paired_flags(rng)
-                    inputs = ["-1", str(td / "m1.fq"), "-2", str(td / "m2.fq")]
+                    kind = rng.choice(["fq", "fq", "il", "tab", "fa"])
+                    if kind == "fq":
+                        inputs = ["-1", str(td / "m1.fq"), "-2", str(td / "m2.fq")]
+                    elif kind == "il":
+                        (td / "il.fq").write_text("".join(f"@{a[0]}\n{a[1]}\n+\n{a[2]}\n@{b[0]}\n{b[1]}\n+\n{b[2]}\n" for a, b in zip(m1, m2)))
+                        inputs = ["--interleaved", str(td / "il.fq")]
+                    elif kind == "tab":
+                        (td / "p.tab").write_text("".join(f"{a[0][:-2]}\t{a[1]}\t{a[2]}\t{b[1]}\t{b[2]}\n" for a, b in zip(m1, m2)))
+                        inputs = ["--12", str(td / "p.tab")]
+                    else:
+                        (td / "m1.fa").write_text("".join(f">{n}\n{s}\n" for n, s, q in m1))
+                        (td / "m2.fa").write_text("".join(f">{n}\n{s}\n" for n, s, q in m2))
+                        inputs = ["-f", "-1", str(td / "m1.fa"), "-2", str(td / "m2.fa")]
                 io, dumps = rand_io_flags(rng, "-S" in flags, td)
+                if dumps and inputs[0] == "-c":                                  # (the reference's -c source never resets its record buffers: its dumps pile up)
+                    io = [x for j, x in enumerate(io) if not (x in ("--al", "--un", "--max") or (j > 0 and io[j - 1] in ("--al", "--un", "--max")))]
                 flags = flags + io
                 (td / "dr").mkdir(exist_ok=True); (td / "do").mkdir(exist_ok=True)
                 for d in ("dr", "do"):
