@@ -562,7 +562,8 @@ struct Reader {
 			for (;;) { size_t t = line.find('\t', p0); if (t == std::string::npos) { fld.push_back(line.substr(p0)); break; } fld.push_back(line.substr(p0, t - p0)); p0 = t + 1; }
 			rdid++;
 			if (keepOrig) { a.orig = line; a.orig += '\n'; b.orig.clear(); }
-			if (fld.size() < 3 || fld.size() == 4) continue;                 /* "record ended prematurely" (pat.cpp:1043-1070): the record is skipped */
+			if (fld.size() < 3) continue;                                    /* "record ended prematurely" (pat.cpp:1043-1070): the record is skipped */
+			const bool four = fld.size() == 4;                               /* ... also when the second end has no qualities — but the first end is checked first */
 			isPair = fld.size() >= 5;
 			for (int e = 0; e < (isPair ? 2 : 1); e++) {
 				ReadRec &r = e ? b : a;
@@ -578,6 +579,7 @@ struct Reader {
 				if (nqual > nchar) die("Reads file contained a pattern with more than 1024 quality values.\nPlease truncate reads and quality values and and re-run Bowtie");
 				r.qual.resize(r.qual.size() - std::min<size_t>((size_t)o.trim3, r.qual.size()));
 			}
+			if (four) continue;
 			return true;
 		}
 	}
