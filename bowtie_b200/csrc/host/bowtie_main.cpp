@@ -14,6 +14,7 @@
  */
 #include <algorithm>
 #include <array>
+#include <deque>
 #include <map>
 #include <condition_variable>
 #include <mutex>
@@ -405,7 +406,7 @@ struct Reader {
 	struct FqSpan { size_t l1, n1, l2, n2, l4, n4, end; };
 	std::vector<FqSpan> spans_;
 	double t_scan = 0, t_work = 0;      /* BT_CLI_TIMING */
-	bool fast_ok() const { return o.format == FASTQ && f && !first && !keepOrig && o.trim5 == 0 && o.trim3 == 0 && !o.solexaQuals && !o.phred64Quals && !o.integerQuals; }
+	bool fast_ok() const { return o.format == FASTQ && f && !first && !keepOrig && pending.empty() && o.trim5 == 0 && o.trim3 == 0 && !o.solexaQuals && !o.phred64Quals && !o.integerQuals; }
 	size_t fast_batch(std::vector<ReadRec> &recs, std::vector<uint32_t> &seeds, std::vector<uint8_t> &bseq, std::vector<uint8_t> &bqual, std::vector<uint64_t> &boffs,
 	                  size_t maxRecs, size_t nth, uint32_t gseed) {
 		std::vector<FqSpan> &spans = spans_;        /* (a member: worker threads must see this thread's list) */
@@ -554,36 +555,107 @@ struct Reader {
 	bool next_tab(ReadRec &a, ReadRec &b, bool &isPair) {
 		for (;;) {
 			if (!f && !open_next()) return false;
-			std::string line;
-			if (!getline_(line)) { gzclose(f); f = NULL; continue; }
-			while (!line.empty() && line.back() == '\r') line.pop_back();
-			if (line.empty()) continue;
-			std::vector<std::string> fld; size_t p0 = 0;
-			for (;;) { size_t t = line.find('\t', p0); if (t == std::string::npos) { fld.push_back(line.substr(p0)); break; } fld.push_back(line.substr(p0, t - p0)); p0 = t + 1; }
+			/* light parse (pat.cpp:979-1011): skip line breaks; a record is the run of characters up to the next LF or CR — an LF is
+			 * kept, and so is a CR right after it */
+			int c = getc_();
+			while (c == '\n' || c == '\r') c = getc_();
+			if (c < 0) { gzclose(f); f = NULL; continue; }
+			chunk.clear();
+			while (c >= 0 && c != '\n' && c != '\r') { chunk.push_back((char)c); c = getc_(); }
+			if (c == '\n') { chunk.push_back('\n'); const int d = peek_(); if (d == '\r') { getc_(); chunk.push_back('\r'); } }
 			rdid++;
-			if (keepOrig) { a.orig = line; a.orig += '\n'; b.orig.clear(); }
-			if (fld.size() < 3) continue;                                    /* "record ended prematurely" (pat.cpp:1043-1070): the record is skipped */
-			const bool four = fld.size() == 4;                               /* ... also when the second end has no qualities — but the first end is checked first */
-			isPair = fld.size() >= 5;
-			for (int e = 0; e < (isPair ? 2 : 1); e++) {
+			if (keepOrig) { a.orig = chunk; b.orig.clear(); }
+			/* parse() (pat.cpp:1016-1124): name TAB seq TAB quals [TAB seq2 TAB quals2]; wherever the record runs out before a field
+			 * has started, it "ended prematurely" and is skipped — errors of the first end come first */
+			const size_t n = chunk.size(); size_t cur = 0;
+			int ch = '\t';
+			bool ok = true, second = false;
+			for (int e = 0; e < 2 && ch == '\t' && ok; e++) {
 				ReadRec &r = e ? b : a;
-				r.name = fld[0];
-				const std::string &sq = fld[1 + 2 * e], &ql = fld[2 + 2 * e];
+				if (e == 0) {
+					r.name.clear();
+					ch = (unsigned char)chunk[cur++];
+					while (ch != '\t' && cur < n) { r.name.push_back((char)ch); ch = (unsigned char)chunk[cur++]; }
+					if (cur >= n) { ok = false; break; }
+				} else { r.name = a.name; second = true; }
 				int nchar = 0; r.seq.clear();
-				for (char ch : sq) if (isalpha((unsigned char)ch)) { if (nchar++ >= o.trim5) r.seq.push_back((char)asc2dna[(unsigned char)ch]); }
-				const size_t t3 = std::min<size_t>((size_t)o.trim3, r.seq.size());
-				r.seq.resize(r.seq.size() - t3);
+				ch = (unsigned char)chunk[cur++];
+				while (ch != '\t' && cur < n) {
+					if (isalpha(ch)) { if (nchar++ >= o.trim5) r.seq.push_back((char)asc2dna[ch]); }
+					ch = (unsigned char)chunk[cur++];
+				}
+				if (cur >= n) { ok = false; break; }
+				r.seq.resize(r.seq.size() - std::min<size_t>((size_t)o.trim3, r.seq.size()));
 				r.qual.clear(); int nqual = 0;
-				for (char ch : ql) { if (ch == ' ') wrong_quality_format(r.name); if ((unsigned char)ch < 33) die("Saw ASCII character " + std::to_string((int)(unsigned char)ch) + " but expected 33-based Phred qual."); char pc = ch;   /* TabbedPatternSource is built without the quality-encoding flags (ebwt_search.cpp:2942-2943) */ if (++nqual > o.trim5) r.qual.push_back(pc); }
+				ch = (unsigned char)chunk[cur++];
+				while (ch != '\t' && ch != '\n' && ch != '\r') {
+					if (ch == ' ') wrong_quality_format(r.name);
+					/* TabbedPatternSource is built without the quality-encoding flags (ebwt_search.cpp:2942-2943): plain Phred+33 */
+					if (ch < 33) die("Saw ASCII character " + std::to_string(ch) + " but expected 33-based Phred qual.");
+					if (++nqual > o.trim5) r.qual.push_back((char)ch);
+					if (cur >= n) break;
+					ch = (unsigned char)chunk[cur++];
+				}
 				if (nchar > nqual) die("Too few quality values for read: " + r.name + "\n\tare you sure this is a FASTQ-int file?");
 				if (nqual > nchar) die("Reads file contained a pattern with more than 1024 quality values.\nPlease truncate reads and quality values and and re-run Bowtie");
 				r.qual.resize(r.qual.size() - std::min<size_t>((size_t)o.trim3, r.qual.size()));
 			}
-			if (four) continue;
+			if (!ok) continue;
+			isPair = second;
 			return true;
 		}
 	}
 	/* Returns false when all input is consumed. */
+	/* FastqPatternSource::nextBatchFromFile (pat.cpp:797-856), one record at a time: the next 4-newline chunk of the input, with the
+	 * light parser's end-of-file rules applied.  gid = the id the record will get (its slot in a light-parse batch is gid & 15). */
+	std::deque<std::string> pending;    /* chunks gathered ahead of parsing (mate files: a light-parse batch at a time) */
+	bool fq_gather(std::string &chunk, int role, bool mateFile, uint64_t gid) {
+		for (;;) {
+			if (!f && !open_next()) return false;
+				if (first) { int c = peek_(); while (c == '\r' || c == '\n') { getc_(); c = peek_(); }
+					if (c != '@') die("Error: reads file does not look like a FASTQ file");          /* an empty file too (pat.cpp:805-812) */
+					first = false; }
+				/* light parse (nextBatchFromFile): a record is whatever lies up to the fourth newline; EOF stands in for the last
+				 * newline, and a record cut short earlier is dropped */
+				chunk.clear();
+				bool counted = false, aborted = false;
+				for (int idx = 0; idx < 4; idx++) {
+					if (!getline_(l1)) { if (idx == 3) { chunk += '\n'; counted = true; } else aborted = idx > 0; break; }
+					chunk += l1;
+					if (line_hit_eof) { if (idx == 3) { chunk += '\n'; counted = true; } else aborted = idx > 0; break; }
+					chunk += '\n';
+					if (idx == 3) counted = true;
+				}
+				/* an incomplete record in the first slot of a light-parse batch: the reference's count goes to -1 and it parses the
+				 * slot's leftovers, which ends in this message */
+				if (aborted && (gid & 15) == 0 && role != 2) {
+					if (mateFile) abortedSlot0 = true;                                 /* -1/-2: the two counts (-1 here) are compared first */
+					else die("Saw ASCII character 10 but expected 33-based Phred qual.");
+				}
+				if (!counted) { gzclose(f); f = NULL; continue; }
+				/* a file that ends inside a record — one or two newlines after this one, a stray blank line included — makes
+				 * nextBatchFromFile step its read count back (pat.cpp:853-855), which discards the record BEFORE the incomplete one
+				 * unless that one closed a light-parse batch of 16.
+				 * --interleaved: the count is in pairs, so blank lines after a complete pair cost that pair (and an incomplete pair
+				 * the one before it as well, which cannot be taken back here: only the incomplete one goes) */
+				if (role == 0) { if ((gid & 15) != 15 && tail_aborts()) { gzclose(f); f = NULL; continue; } }
+				else if (role == 2) { if ((gid & 15) != 0 && tail_aborts()) { gzclose(f); f = NULL; continue; } }
+				else if (tail_aborts()) {
+					if ((gid & 15) == 0) die("Saw ASCII character 10 but expected 33-based Phred qual.");
+					gzclose(f); f = NULL; continue;
+				}
+				return true;
+		}
+	}
+	/* gathers (without parsing) until `want` records are pending; returns how many are */
+	size_t light_fill(size_t want) {
+		while (pending.size() < want) {
+			std::string c;
+			if (!fq_gather(c, 0, true, rdid + pending.size())) break;
+			pending.push_back(std::move(c));
+		}
+		return pending.size();
+	}
 	/* role: 0 = a file of single reads or of one mate; 1 / 2 = first / second record of an --interleaved pair */
 	bool abortedSlot0 = false;          /* a mate file ended inside a record that would have opened a light-parse batch */
 	bool next(ReadRec &r, int role = 0, bool mateFile = false) {
@@ -655,45 +727,19 @@ struct Reader {
 				return true;
 			}
 		}
+		if (o.format == FASTQ) {
+			/* FastqPatternSource (pat.cpp:797-975): light parse (fq_gather), then parse() */
+			if (!pending.empty()) { chunk.swap(pending.front()); pending.pop_front(); }
+			else if (!fq_gather(chunk, role, mateFile, rdid)) return false;
+			parse_fastq_chunk(chunk, r);
+			if (keepOrig) r.orig = chunk;                                           /* Read::readOrigBuf */
+			if (r.name.empty()) r.name = std::to_string(rdid);
+			rdid++;
+			return true;
+		}
 		for (;;) {
 			if (!f && !open_next()) return false;
-			if (o.format == FASTQ) {
-				/* FastqPatternSource (pat.cpp:797-975) */
-				if (first) { int c = peek_(); while (c == '\r' || c == '\n') { getc_(); c = peek_(); }
-					if (c != '@') die("Error: reads file does not look like a FASTQ file");          /* an empty file too (pat.cpp:805-812) */
-					first = false; }
-				/* light parse (nextBatchFromFile): a record is whatever lies up to the fourth newline; EOF stands in for the last
-				 * newline, and a record cut short earlier is dropped */
-				chunk.clear();
-				bool counted = false, aborted = false;
-				for (int idx = 0; idx < 4; idx++) {
-					if (!getline_(l1)) { if (idx == 3) { chunk += '\n'; counted = true; } else aborted = idx > 0; break; }
-					chunk += l1;
-					if (line_hit_eof) { if (idx == 3) { chunk += '\n'; counted = true; } else aborted = idx > 0; break; }
-					chunk += '\n';
-					if (idx == 3) counted = true;
-				}
-				/* an incomplete record in the first slot of a light-parse batch: the reference's count goes to -1 and it parses the
-				 * slot's leftovers, which ends in this message */
-				if (aborted && (rdid & 15) == 0 && role != 2) {
-					if (mateFile) abortedSlot0 = true;                                 /* -1/-2: the two counts (-1 here) are compared first */
-					else die("Saw ASCII character 10 but expected 33-based Phred qual.");
-				}
-				if (!counted) { gzclose(f); f = NULL; continue; }
-				/* a file that ends inside a record — one or two newlines after this one, a stray blank line included — makes
-				 * nextBatchFromFile step its read count back (pat.cpp:853-855), which discards the record BEFORE the incomplete one
-				 * unless that one closed a light-parse batch of 16.
-				 * --interleaved: the count is in pairs, so blank lines after a complete pair cost that pair (and an incomplete pair
-				 * the one before it as well, which cannot be taken back here: only the incomplete one goes) */
-				if (role == 0) { if ((rdid & 15) != 15 && tail_aborts()) { gzclose(f); f = NULL; continue; } }
-				else if (role == 2) { if ((rdid & 15) != 0 && tail_aborts()) { gzclose(f); f = NULL; continue; } }
-				else if (tail_aborts()) {
-					if ((rdid & 15) == 0) die("Saw ASCII character 10 but expected 33-based Phred qual.");
-					gzclose(f); f = NULL; continue;
-				}
-				parse_fastq_chunk(chunk, r);
-				if (keepOrig) r.orig = chunk;                                       /* Read::readOrigBuf */
-			} else if (o.format == FASTA) {
+			if (o.format == FASTA) {
 				/* FastaPatternSource (pat.cpp:531-640).  Light parse: a record is '>' plus everything up to the next '>' — wherever
 				 * that is — or EOF.  parse(): the name ends at the first CR/LF, line breaks after it are skipped, the sequence is the
 				 * letters and '.' of the next line only, and a record with nothing after its name is skipped (it keeps its id). */
@@ -1052,17 +1098,32 @@ int main(int argc, char **argv) {
 					}
 				}
 				if (interleaved) {
-					if (!rd.next(rec, 1)) { input_done = true; break; }
-					if (!rd.next(rec2, 2)) { input_done = true; break; }                /* a last record without a mate is dropped (the light parser counts pairs) */
+					/* the light parser counts pairs: both records are cut out of the file before either is parsed, and a last record
+					 * without a mate is dropped unparsed */
+					std::string ca, cb;
+					if (!rd.fq_gather(ca, 1, false, rd.rdid) || !rd.fq_gather(cb, 2, false, rd.rdid + 1)) { input_done = true; break; }
+					rd.pending.push_back(std::move(ca)); rd.pending.push_back(std::move(cb));
+					rd.next(rec, 1); rd.next(rec2, 2);
 					rd.rdid--;                                                          /* a pair is one read id */
 				} else if (paired) {
-					/* DualPatternComposer::nextBatch (pat.cpp:164-222) compares what the two files delivered */
-					const bool ga = rd.next(rec, 0, true), gb = rd2.next(rec2, 0, true);
-					const int ca = ga ? 1 : rd.abortedSlot0 ? -1 : 0, cb = gb ? 1 : rd2.abortedSlot0 ? -1 : 0;
-					if (ca < cb) die("Error, fewer reads in file specified with -1 than in file specified with -2");
-					if (cb < ca) die("Error, fewer reads in file specified with -2 than in file specified with -1");
-					if (ca < 0) die("Saw ASCII character 10 but expected 33-based Phred qual.");
-					if (!ga) { input_done = true; break; }
+					/* DualPatternComposer::nextBatch (pat.cpp:164-222) compares what the two files delivered — for FASTQ a light-parse
+					 * batch of 16 records from each file at a time, before any of them is parsed */
+					if (op.format == FASTQ) {
+						if (rd.pending.empty() && rd2.pending.empty()) {
+							const size_t na = rd.light_fill(16), nb = rd2.light_fill(16);
+							const long ca = na ? (long)na : rd.abortedSlot0 ? -1 : 0, cb = nb ? (long)nb : rd2.abortedSlot0 ? -1 : 0;
+							if (ca < cb) die("Error, fewer reads in file specified with -1 than in file specified with -2");
+							if (cb < ca) die("Error, fewer reads in file specified with -2 than in file specified with -1");
+							if (ca < 0) die("Saw ASCII character 10 but expected 33-based Phred qual.");
+							if (ca == 0) { input_done = true; break; }
+						}
+						rd.next(rec, 0, true); rd2.next(rec2, 0, true);
+					} else {
+						const bool ga = rd.next(rec, 0, true), gb = rd2.next(rec2, 0, true);
+						if (!ga && gb) die("Error, fewer reads in file specified with -1 than in file specified with -2");
+						if (ga && !gb) die("Error, fewer reads in file specified with -2 than in file specified with -1");
+						if (!ga) { input_done = true; break; }
+					}
 				} else if (!rd.next(rec)) { input_done = true; break; }
 			}
 			if (rd.rdid - 1 < op.skipReads) continue;                              /* -s: skipped reads are not counted */

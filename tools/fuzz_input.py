@@ -67,22 +67,33 @@ def main():
         rng = random.Random(a.seed * 7919 + it)
         n = rng.choice([3, 15, 16, 17, 33])
         rs = [recs[rng.randrange(len(recs))] for _ in range(n)]
-        kind = rng.choice(["fq", "fq", "fa", "raw", "tab"])
+        kind = rng.choice(["fq", "fq", "fa", "raw", "tab", "il", "pair", "tab5"])
         if kind == "fq":
             text, opt = "".join("\n".join(r) + "\n" for r in rs), ["-q"]
         elif kind == "fa":
             text, opt = "".join(f">{r[0][1:]}\n{r[1]}\n" for r in rs), ["-f"]
         elif kind == "raw":
             text, opt = "".join(r[1] + "\n" for r in rs), ["-r"]
-        else:
+        elif kind == "tab":
             text, opt = "".join(f"{r[0][1:]}\t{r[1]}\t{r[3]}\n" for r in rs), ["--12"]
+        elif kind == "tab5":
+            text, opt = "".join(f"{r[0][1:]}\t{r[1]}\t{r[3]}\t{q[1]}\t{q[3]}\n" for r, q in zip(rs, reversed(rs))), ["--12"]
+        else:                                                   # il / pair: FASTQ text, used as --interleaved or as the -1 file
+            text, opt = "".join("\n".join(r) + "\n" for r in rs), []
         data = mutate(rng, text.encode())
         flags = rng.choice([["-n", "2"], ["-v", "1"], ["-n", "2", "--best"], ["-n", "2", "-5", "2"], ["-v", "0", "-3", "3"]])
         with tempfile.TemporaryDirectory() as td:
             td = Path(td)
             f = td / "in.txt"
             f.write_bytes(data)
-            src = [*opt, str(f)] if kind != "tab" else ["--12", str(f)]
+            if kind == "il":
+                src = ["--interleaved", str(f)]
+            elif kind == "pair":
+                g = td / "mate2.fq"
+                g.write_text("".join("\n".join(r) + "\n" for r in reversed(rs)))
+                src = ["-1", str(f), "-2", str(g)] if rng.random() < 0.5 else ["-1", str(g), "-2", str(f)]
+            else:
+                src = [*opt, str(f)] if not kind.startswith("tab") else ["--12", str(f)]
             r1 = run(REF / "bowtie-align-s", flags, src, td / "r1.out", extra=["-p", "1"])
             r2 = run(REF / "bowtie-align-s", flags, src, td / "r2.out", extra=["-p", "1"])
             if r1 != r2 or r1[0] not in (0, 1):
