@@ -626,11 +626,11 @@ struct Reader {
 					chunk += '\n';
 					if (idx == 3) counted = true;
 				}
-				/* an incomplete record in the first slot of a light-parse batch: the reference's count goes to -1 and it parses the
-				 * slot's leftovers, which ends in this message */
+				/* an incomplete record in the first slot of a light-parse batch: the reference's count goes to -1 and it parses what
+				 * is in that slot — the incomplete record — which ends in one of parse()'s errors (past its end: this one) */
 				if (aborted && (gid & 15) == 0 && role != 2) {
 					if (mateFile) abortedSlot0 = true;                                 /* -1/-2: the two counts (-1 here) are compared first */
-					else die("Saw ASCII character 10 but expected 33-based Phred qual.");
+					else { ReadRec tmp; parse_fastq_chunk(chunk, tmp); die("Saw ASCII character 10 but expected 33-based Phred qual."); }
 				}
 				if (!counted) { gzclose(f); f = NULL; continue; }
 				/* a file that ends inside a record — one or two newlines after this one, a stray blank line included — makes
