@@ -628,6 +628,11 @@ struct Reader {
 				}
 				/* an incomplete record in the first slot of a light-parse batch: the reference's count goes to -1 and it parses what
 				 * is in that slot — the incomplete record — which ends in one of parse()'s errors (past its end: this one) */
+				if (role == 3) {                                                       /* --interleaved: il_fill() applies the pair-counting rules */
+					rawAborted = aborted;
+					if (!counted) { gzclose(f); f = NULL; if (aborted || fileIdx >= files.size()) return false; continue; }
+					return true;
+				}
 				if (aborted && (gid & 15) == 0 && role != 2) {
 					if (mateFile) abortedSlot0 = true;                                 /* -1/-2: the two counts (-1 here) are compared first */
 					else { ReadRec tmp; parse_fastq_chunk(chunk, tmp); die("Saw ASCII character 10 but expected 33-based Phred qual."); }
@@ -646,6 +651,28 @@ struct Reader {
 				}
 				return true;
 		}
+	}
+	/* --interleaved (pat.cpp:822-855): a light-parse batch holds up to 16 PAIRS; records are cut alternately into the two mate
+	 * buffers and a pair counts once its second record is in.  A file that ends inside a record steps the pair count back by one:
+	 * the last complete pair of the batch goes as well (from zero the reference goes on with -1 and parses what the first slot
+	 * holds).  A last record without a mate is simply not counted.  Returns the number of pairs made pending. */
+	bool rawAborted = false;
+	size_t il_fill() {
+		std::vector<std::string> got;
+		bool aborted = false;
+		rawAborted = false;
+		while (got.size() < 32) {
+			std::string c;
+			if (!fq_gather(c, 3, false, 0)) { aborted = rawAborted; break; }
+			got.push_back(std::move(c));
+		}
+		size_t pairs = got.size() / 2;
+		if (aborted) {
+			if (pairs == 0) { if (!got.empty()) { ReadRec tmp; parse_fastq_chunk(got[0], tmp); } die("Saw ASCII character 10 but expected 33-based Phred qual."); }
+			pairs--;
+		}
+		for (size_t i = 0; i < 2 * pairs; i++) pending.push_back(std::move(got[i]));
+		return pairs;
 	}
 	/* gathers (without parsing) until `want` records are pending; returns how many are */
 	size_t light_fill(size_t want) {
@@ -1100,9 +1127,7 @@ int main(int argc, char **argv) {
 				if (interleaved) {
 					/* the light parser counts pairs: both records are cut out of the file before either is parsed, and a last record
 					 * without a mate is dropped unparsed */
-					std::string ca, cb;
-					if (!rd.fq_gather(ca, 1, false, rd.rdid) || !rd.fq_gather(cb, 2, false, rd.rdid + 1)) { input_done = true; break; }
-					rd.pending.push_back(std::move(ca)); rd.pending.push_back(std::move(cb));
+					if (rd.pending.empty() && rd.il_fill() == 0) { input_done = true; break; }
 					rd.next(rec, 1); rd.next(rec2, 2);
 					rd.rdid--;                                                          /* a pair is one read id */
 				} else if (paired) {
