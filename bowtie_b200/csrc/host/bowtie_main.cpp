@@ -609,7 +609,7 @@ struct Reader {
 	/* FastqPatternSource::nextBatchFromFile (pat.cpp:797-856), one record at a time: the next 4-newline chunk of the input, with the
 	 * light parser's end-of-file rules applied.  gid = the id the record will get (its slot in a light-parse batch is gid & 15). */
 	std::deque<std::string> pending;    /* chunks gathered ahead of parsing (mate files: a light-parse batch at a time) */
-	bool fq_gather(std::string &chunk, int role, bool mateFile, uint64_t gid) {
+	bool fq_gather(std::string &chunk, bool raw, bool mateFile, uint64_t gid) {
 		for (;;) {
 			if (!f && !open_next()) return false;
 				if (first) { int c = peek_(); while (c == '\r' || c == '\n') { getc_(); c = peek_(); }
@@ -628,27 +628,20 @@ struct Reader {
 				}
 				/* an incomplete record in the first slot of a light-parse batch: the reference's count goes to -1 and it parses what
 				 * is in that slot — the incomplete record — which ends in one of parse()'s errors (past its end: this one) */
-				if (role == 3) {                                                       /* --interleaved: il_fill() applies the pair-counting rules */
+				if (raw) {                                                             /* --interleaved: il_fill() applies the pair-counting rules */
 					rawAborted = aborted;
 					if (!counted) { gzclose(f); f = NULL; if (aborted || fileIdx >= files.size()) return false; continue; }
 					return true;
 				}
-				if (aborted && (gid & 15) == 0 && role != 2) {
+				if (aborted && (gid & 15) == 0) {
 					if (mateFile) abortedSlot0 = true;                                 /* -1/-2: the two counts (-1 here) are compared first */
 					else { ReadRec tmp; parse_fastq_chunk(chunk, tmp); die("Saw ASCII character 10 but expected 33-based Phred qual."); }
 				}
 				if (!counted) { gzclose(f); f = NULL; continue; }
 				/* a file that ends inside a record — one or two newlines after this one, a stray blank line included — makes
 				 * nextBatchFromFile step its read count back (pat.cpp:853-855), which discards the record BEFORE the incomplete one
-				 * unless that one closed a light-parse batch of 16.
-				 * --interleaved: the count is in pairs, so blank lines after a complete pair cost that pair (and an incomplete pair
-				 * the one before it as well, which cannot be taken back here: only the incomplete one goes) */
-				if (role == 0) { if ((gid & 15) != 15 && tail_aborts()) { gzclose(f); f = NULL; continue; } }
-				else if (role == 2) { if ((gid & 15) != 0 && tail_aborts()) { gzclose(f); f = NULL; continue; } }
-				else if (tail_aborts()) {
-					if ((gid & 15) == 0) die("Saw ASCII character 10 but expected 33-based Phred qual.");
-					gzclose(f); f = NULL; continue;
-				}
+				 * unless that one closed a light-parse batch of 16 */
+				if ((gid & 15) != 15 && tail_aborts()) { gzclose(f); f = NULL; continue; }
 				return true;
 		}
 	}
@@ -663,7 +656,7 @@ struct Reader {
 		rawAborted = false;
 		while (got.size() < 32) {
 			std::string c;
-			if (!fq_gather(c, 3, false, 0)) { aborted = rawAborted; break; }
+			if (!fq_gather(c, true, false, 0)) { aborted = rawAborted; break; }
 			got.push_back(std::move(c));
 		}
 		size_t pairs = got.size() / 2;
@@ -678,14 +671,13 @@ struct Reader {
 	size_t light_fill(size_t want) {
 		while (pending.size() < want) {
 			std::string c;
-			if (!fq_gather(c, 0, true, rdid + pending.size())) break;
+			if (!fq_gather(c, false, true, rdid + pending.size())) break;
 			pending.push_back(std::move(c));
 		}
 		return pending.size();
 	}
-	/* role: 0 = a file of single reads or of one mate; 1 / 2 = first / second record of an --interleaved pair */
 	bool abortedSlot0 = false;          /* a mate file ended inside a record that would have opened a light-parse batch */
-	bool next(ReadRec &r, int role = 0, bool mateFile = false) {
+	bool next(ReadRec &r, bool mateFile = false) {
 		if (o.format == CMDLINE) {
 			/* VectorPatternSource (pat.cpp:357-523): "seq[:quals]" becomes the tabbed record "<ordinal> TAB seq TAB quals" — quals
 			 * default to one 'I' per character of seq — and is parsed like one: letters only, plain Phred+33, counts must agree */
@@ -757,7 +749,7 @@ struct Reader {
 		if (o.format == FASTQ) {
 			/* FastqPatternSource (pat.cpp:797-975): light parse (fq_gather), then parse() */
 			if (!pending.empty()) { chunk.swap(pending.front()); pending.pop_front(); }
-			else if (!fq_gather(chunk, role, mateFile, rdid)) return false;
+			else if (!fq_gather(chunk, false, mateFile, rdid)) return false;
 			parse_fastq_chunk(chunk, r);
 			if (keepOrig) r.orig = chunk;                                           /* Read::readOrigBuf */
 			if (r.name.empty()) r.name = std::to_string(rdid);
@@ -1128,7 +1120,7 @@ int main(int argc, char **argv) {
 					/* the light parser counts pairs: both records are cut out of the file before either is parsed, and a last record
 					 * without a mate is dropped unparsed */
 					if (rd.pending.empty() && rd.il_fill() == 0) { input_done = true; break; }
-					rd.next(rec, 1); rd.next(rec2, 2);
+					rd.next(rec); rd.next(rec2);
 					rd.rdid--;                                                          /* a pair is one read id */
 				} else if (paired) {
 					/* DualPatternComposer::nextBatch (pat.cpp:164-222) compares what the two files delivered — for FASTQ a light-parse
@@ -1142,9 +1134,9 @@ int main(int argc, char **argv) {
 							if (ca < 0) die("Saw ASCII character 10 but expected 33-based Phred qual.");
 							if (ca == 0) { input_done = true; break; }
 						}
-						rd.next(rec, 0, true); rd2.next(rec2, 0, true);
+						rd.next(rec, true); rd2.next(rec2, true);
 					} else {
-						const bool ga = rd.next(rec, 0, true), gb = rd2.next(rec2, 0, true);
+						const bool ga = rd.next(rec, true), gb = rd2.next(rec2, true);
 						if (!ga && gb) die("Error, fewer reads in file specified with -1 than in file specified with -2");
 						if (ga && !gb) die("Error, fewer reads in file specified with -2 than in file specified with -1");
 						if (!ga) { input_done = true; break; }
