@@ -656,12 +656,12 @@ struct Reader {
 		rawAborted = false;
 		while (got.size() < 32) {
 			std::string c;
-			if (!fq_gather(c, true, false, 0)) { aborted = rawAborted; break; }
+			if (!fq_gather(c, true, false, 0)) { aborted = rawAborted; if (aborted && got.empty()) got.push_back(std::move(c)); break; }
 			got.push_back(std::move(c));
 		}
 		size_t pairs = got.size() / 2;
 		if (aborted) {
-			if (pairs == 0) { if (!got.empty()) { ReadRec tmp; parse_fastq_chunk(got[0], tmp); } die("Saw ASCII character 10 but expected 33-based Phred qual."); }
+			if (pairs == 0) { ReadRec tmp; parse_fastq_chunk(got[0], tmp); die("Saw ASCII character 10 but expected 33-based Phred qual."); }   /* slot 0 of the first mate's buffer */
 			pairs--;
 		}
 		for (size_t i = 0; i < 2 * pairs; i++) pending.push_back(std::move(got[i]));
