@@ -564,6 +564,7 @@ struct Reader {
 			while (c >= 0 && c != '\n' && c != '\r') { chunk.push_back((char)c); c = getc_(); }
 			if (c == '\n') { chunk.push_back('\n'); const int d = peek_(); if (d == '\r') { getc_(); chunk.push_back('\r'); } }
 			rdid++;
+			if (rdid - 1 < o.skipReads) { a.name.clear(); a.seq.clear(); a.qual.clear(); isPair = false; return true; }   /* -s: not parsed */
 			if (keepOrig) { a.orig = chunk; b.orig.clear(); }
 			/* parse() (pat.cpp:1016-1124): name TAB seq TAB quals [TAB seq2 TAB quals2]; wherever the record runs out before a field
 			 * has started, it "ended prematurely" and is skipped — errors of the first end come first */
@@ -750,6 +751,7 @@ struct Reader {
 			/* FastqPatternSource (pat.cpp:797-975): light parse (fq_gather), then parse() */
 			if (!pending.empty()) { chunk.swap(pending.front()); pending.pop_front(); }
 			else if (!fq_gather(chunk, false, mateFile, rdid)) return false;
+			if (rdid < o.skipReads) { r.name.clear(); r.seq.clear(); r.qual.clear(); rdid++; return true; }   /* -s: skipped reads are never parsed (pat.cpp:108-110) */
 			parse_fastq_chunk(chunk, r);
 			if (keepOrig) r.orig = chunk;                                           /* Read::readOrigBuf */
 			if (r.name.empty()) r.name = std::to_string(rdid);
