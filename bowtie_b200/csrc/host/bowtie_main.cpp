@@ -678,6 +678,7 @@ struct Reader {
 		return pending.size();
 	}
 	bool abortedSlot0 = false;          /* a mate file ended inside a record that would have opened a light-parse batch */
+	bool skipNext = false;              /* --interleaved: the next record belongs to a pair that -s skips */
 	bool next(ReadRec &r, bool mateFile = false) {
 		if (o.format == CMDLINE) {
 			/* VectorPatternSource (pat.cpp:357-523): "seq[:quals]" becomes the tabbed record "<ordinal> TAB seq TAB quals" — quals
@@ -751,7 +752,7 @@ struct Reader {
 			/* FastqPatternSource (pat.cpp:797-975): light parse (fq_gather), then parse() */
 			if (!pending.empty()) { chunk.swap(pending.front()); pending.pop_front(); }
 			else if (!fq_gather(chunk, false, mateFile, rdid)) return false;
-			if (rdid < o.skipReads) { r.name.clear(); r.seq.clear(); r.qual.clear(); rdid++; return true; }   /* -s: skipped reads are never parsed (pat.cpp:108-110) */
+			if (rdid < o.skipReads || skipNext) { r.name.clear(); r.seq.clear(); r.qual.clear(); rdid++; return true; }   /* -s: skipped reads are never parsed (pat.cpp:108-110) */
 			parse_fastq_chunk(chunk, r);
 			if (keepOrig) r.orig = chunk;                                           /* Read::readOrigBuf */
 			if (r.name.empty()) r.name = std::to_string(rdid);
@@ -1101,15 +1102,15 @@ int main(int argc, char **argv) {
 			bool paired = pairedInput;
 			if (tabbed) {
 				if (!haveLook) {
-					if (rd.rdid >= op.qUpto) { input_done = true; break; }
+					if (rd.rdid > op.qUpto) { input_done = true; break; }   /* the record with id qUpto is still read and parsed (GET_READ, ebwt_search.cpp:934-939) */
 					if (!rd.next_tab(lrec, lrec2, lookPair)) { input_done = true; break; }
 					haveLook = true;
 				}
 				if (b.reads.empty()) b.paired = lookPair; else if (lookPair != b.paired) break;   /* the other kind starts the next batch */
 				rec = lrec; rec2 = lrec2; paired = lookPair; haveLook = false;
 			} else {
-				if (rd.rdid >= op.qUpto) { input_done = true; break; }
-				if (!pairedInput && rd.fast_ok() && rd.rdid >= op.skipReads) {
+				if (rd.rdid > op.qUpto) { input_done = true; break; }   /* the record with id qUpto is still read and parsed (GET_READ, ebwt_search.cpp:934-939) */
+				if (!pairedInput && rd.fast_ok() && rd.rdid >= op.skipReads && rd.rdid < op.qUpto) {
 					/* plain single-end FASTQ: whole runs of records at a time, parsed by several threads (Reader::fast_batch) */
 					const size_t r0 = b.reads.size();
 					const size_t want = std::min<size_t>((size_t)op.batch - r0, (size_t)(op.qUpto - rd.rdid));
@@ -1122,7 +1123,9 @@ int main(int argc, char **argv) {
 					/* the light parser counts pairs: both records are cut out of the file before either is parsed, and a last record
 					 * without a mate is dropped unparsed */
 					if (rd.pending.empty() && rd.il_fill() == 0) { input_done = true; break; }
+					rd.skipNext = rd.rdid < op.skipReads;                              /* the pair is skipped or parsed as one */
 					rd.next(rec); rd.next(rec2);
+					rd.skipNext = false;
 					rd.rdid--;                                                          /* a pair is one read id */
 				} else if (paired) {
 					/* DualPatternComposer::nextBatch (pat.cpp:164-222) compares what the two files delivered — for FASTQ a light-parse
@@ -1145,6 +1148,7 @@ int main(int argc, char **argv) {
 					}
 				} else if (!rd.next(rec)) { input_done = true; break; }
 			}
+			if (rd.rdid - 1 >= op.qUpto) { input_done = true; break; }            /* -u: ... and then dropped */
 			if (rd.rdid - 1 < op.skipReads) continue;                              /* -s: skipped reads are not counted */
 			if (paired) { fix_mate_name(rec.name, 1); fix_mate_name(rec2.name, 2); }   /* PatternSourcePerThread::finalizePair (pat.cpp:75-87) */
 			if (rec.seq.size() < 4 || (paired && rec2.seq.size() < 4)) short_read_check(rec, paired ? &rec2 : NULL);

@@ -81,7 +81,8 @@ def main():
         else:                                                   # il / pair: FASTQ text, used as --interleaved or as the -1 file
             text, opt = "".join("\n".join(r) + "\n" for r in rs), []
         data = mutate(rng, text.encode())
-        flags = rng.choice([["-n", "2"], ["-v", "1"], ["-n", "2", "--best"], ["-n", "2", "-5", "2"], ["-v", "0", "-3", "3"]])
+        flags = rng.choice([["-n", "2"], ["-v", "1"], ["-n", "2", "--best"], ["-n", "2", "-5", "2"], ["-v", "0", "-3", "3"], ["-n", "2", "-s", "3"], ["-v", "1", "-u", "7"],
+                            ["-n", "2", "-s", "14", "-u", "5"]])
         with tempfile.TemporaryDirectory() as td:
             td = Path(td)
             f = td / "in.txt"
