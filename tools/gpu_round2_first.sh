@@ -15,6 +15,8 @@ BT_BENCH_READS=200000 BT_BENCH_STREAMS=1 timeout 300 ncu --metrics gpu__time_dur
 # A/B owed for the unified LF path (profiles/README.md): same bench with the three LF kinds on separate paths again
 make -C bowtie_b200/csrc experiments > gpurun_out/r2_make_experiments.log 2>&1
 BOWTIE_B200_LIB=$PWD/bowtie_b200/variants/libbt_split_lf.so timeout 200 python bench.py --steps 5 --warmup 3 --cpu-sample 1000 > gpurun_out/r2_bench_n2k1_splitlf.json 2> gpurun_out/r2_bench_n2k1_splitlf.err; lap "bench n2k1, split LF" $?; tail -c 300 gpurun_out/r2_bench_n2k1_splitlf.json
+# the replay's other suggestion for the merged-LF kernel: a rare pass every 8th iteration (profiles/README.md)
+BT_RARE_PERIOD=8 BT_RARE_THRESH=24 timeout 200 python bench.py --steps 5 --warmup 3 --cpu-sample 1000 > gpurun_out/r2_bench_n2k1_p8t24.json 2> gpurun_out/r2_bench_n2k1_p8t24.err; lap "bench n2k1, period 8 / threshold 24" $?; tail -c 300 gpurun_out/r2_bench_n2k1_p8t24.json
 # hg19-sized index: only if the builder test above passed
 if grep -q "passed" gpurun_out/r2_pytest_build.log && ! grep -q "failed" gpurun_out/r2_pytest_build.log; then
   timeout 1500 python tools/make_bench_index.py 3000 24 --gpu > gpurun_out/r2_build_3g.log 2>&1; lap "3-Gbp index" $?; tail -2 gpurun_out/r2_build_3g.log
