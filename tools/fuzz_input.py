@@ -67,13 +67,19 @@ def main():
         rng = random.Random(a.seed * 7919 + it)
         n = rng.choice([3, 15, 16, 17, 33])
         rs = [recs[rng.randrange(len(recs))] for _ in range(n)]
-        kind = rng.choice(["fq", "fq", "fa", "raw", "tab", "il", "pair", "tab5"])
+        # ("iq", --integer-quals, is left out of the draw: that branch of the reference neither trims nor checks the number of
+        # qualities, so a damaged record comes out with a quality string of another length than its sequence)
+        kind = rng.choice(["fq", "fq", "fa", "raw", "tab", "il", "pair", "tab5", "fc"])
         if kind == "fq":
             text, opt = "".join("\n".join(r) + "\n" for r in rs), ["-q"]
         elif kind == "fa":
             text, opt = "".join(f">{r[0][1:]}\n{r[1]}\n" for r in rs), ["-f"]
         elif kind == "raw":
             text, opt = "".join(r[1] + "\n" for r in rs), ["-r"]
+        elif kind == "fc":                                      # windows of a FASTA input
+            text, opt = "".join(f">{r[0][1:]} x\n{r[1]}\n{r[1][::-1]}\n" for r in rs[:6]), ["-F", rng.choice(["20,5", "30,1", "12,7"])]
+        elif kind == "iq":
+            text, opt = "".join(f"{r[0]}\n{r[1]}\n+\n{' '.join(str(ord(c) - 33) for c in r[3])}\n" for r in rs), ["-q", "--integer-quals"]
         elif kind == "tab":
             text, opt = "".join(f"{r[0][1:]}\t{r[1]}\t{r[3]}\n" for r in rs), ["--12"]
         elif kind == "tab5":
