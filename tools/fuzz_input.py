@@ -19,7 +19,10 @@ SHIM = Path(os.environ.get("BT_FUZZ_SHIM", ROOT / "tests" / "host_emu" / "shim")
 
 
 def run(exe, flags, src, out, env=None, extra=()):
-    p = subprocess.run([str(exe), *flags, *extra, "-x", str(FIX / "e_coli"), *src, str(out)], capture_output=True, text=True, env=env, errors="replace")
+    try:
+        p = subprocess.run([str(exe), *flags, *extra, "-x", str(FIX / "e_coli"), *src, str(out)], capture_output=True, text=True, env=env, errors="replace", timeout=60)
+    except subprocess.TimeoutExpired:
+        return -999, b"", ["(timed out)"]
     body = Path(out).read_bytes() if p.returncode == 0 and Path(out).exists() else b""
     return p.returncode, body, [l for l in p.stderr.splitlines() if not l.startswith("Command:")]
 
