@@ -106,6 +106,8 @@ def load_library() -> C.CDLL:
     L.bt_debug_lf.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_uint32, C.c_void_p]
     L.bt_index_build.restype = C.c_int
     L.bt_index_build.argtypes = [C.POINTER(C.c_char_p), C.c_uint32, C.c_char_p, C.c_int, C.c_int, C.c_int]
+    L.bt_index_build_text.restype = C.c_int
+    L.bt_index_build_text.argtypes = [C.c_void_p, C.c_uint64, C.c_void_p, C.c_uint32, C.POINTER(C.c_char_p), C.c_uint32, C.c_char_p, C.c_int, C.c_int, C.c_int]
     _LIB = L
     return L
 
@@ -117,6 +119,19 @@ def build_index(fasta, out_base, off_rate: int = 5, ftab_chars: int = 10, device
     arr = (C.c_char_p * len(files))(*files)
     if L.bt_index_build(arr, len(files), str(out_base).encode(), int(off_rate), int(ftab_chars), int(device)) != 0:
         raise RuntimeError("bt_index_build: " + L.bt_last_error().decode())
+
+
+def build_index_text(codes: np.ndarray, recs, names, out_base, off_rate: int = 5, ftab_chars: int = 10, device: int = 0) -> None:
+    """bt_index_build_text: the index of an in-memory reference.  codes: uint8 base codes 0..3 of the joined unambiguous
+    characters; recs: (off, len, first) per record (RefRecord, ref_read.h:57-88); names: one per sequence."""
+    L = load_library()
+    codes = np.ascontiguousarray(codes, np.uint8)
+    r = np.ascontiguousarray(np.asarray(recs, np.uint32).reshape(-1, 3))
+    nm = [str(n).encode() for n in names]
+    arr = (C.c_char_p * len(nm))(*nm)
+    if L.bt_index_build_text(codes.ctypes.data, codes.size, r.ctypes.data, r.shape[0], arr, len(nm), str(out_base).encode(),
+                             int(off_rate), int(ftab_chars), int(device)) != 0:
+        raise RuntimeError("bt_index_build_text: " + L.bt_last_error().decode())
 
 
 @dataclass

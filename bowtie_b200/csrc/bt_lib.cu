@@ -913,6 +913,9 @@ static int align_host(bt_context *cx, const bt_policy_t *pol, const bt_read_batc
 		const size_t rec_words = BT_HIT_HDR + out->mm_cap;
 		const uint32_t nout = pol->paired ? n / 2 : n;                        /* results are per read, or per pair */
 		const size_t hitwords = (size_t)nout * out->slots * rec_words;
+		/* this context's previous batch (its heavy / overflow passes and D2H copies run on cx->side) must be finished before its
+		 * staging buffers are overwritten: the wait comes before the first copy, not only before the kernels */
+		CUDA_TRY(cudaStreamWaitEvent(st, cx->ev_tail, 0));
 		if (grow(&cx->d_seq, cx->cap_seq, nb + 1) || grow(&cx->d_qual, cx->cap_qual, nb + 1)) return 1;
 		if (grow(&cx->d_offs, cx->cap_offs, (size_t)n + 1) || grow(&cx->d_seeds, cx->cap_seeds, n) ||
 		    grow(&cx->d_found, cx->cap_found, nout) || grow(&cx->d_flags, cx->cap_flags, nout)) return 1;

@@ -1168,6 +1168,7 @@ int main(int argc, char **argv) {
 		const bt_policy_t &pol = b.paired ? polP : polU;
 		b.slots = op.allHits ? 8 : op.khits * mult;
 		if (op.sampleMax && op.mhits != 0xffffffffu) b.slots = std::max(b.slots, op.mhits * mult);   /* -M keeps every hit up to the ceiling */
+		b.slots = std::min<uint32_t>(b.slots, 16);                               /* first pass: bounded records per read (-k 1000 must not size n x 1000 records); reads with more come back with BT_OVF_HITS and are re-run below with exact capacities */
 		const size_t n = b.reads.size() / mult, rw = BT_HIT_HDR_WORDS + b.mm_cap;
 		b.found.resize(n); b.flags.resize(n); b.hits.resize(n * b.slots * rw);    /* the library overwrites every entry it is asked for */
 		bt_read_batch_t in; memset(&in, 0, sizeof in);

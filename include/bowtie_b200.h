@@ -26,7 +26,7 @@
 extern "C" {
 #endif
 
-#define BT_ABI_VERSION 3
+#define BT_ABI_VERSION 4
 
 typedef struct bt_index bt_index_t;
 typedef struct bt_context bt_context_t;
@@ -155,9 +155,18 @@ int  bt_stats_get(bt_index_t *ix, bt_stats_t *out, int reset);    /* synchronise
 
 /* Replaces bowtie-build (ebwt_build.cpp:303-480 driver(); Ebwt::initFromVector / joinToDisk / buildToDisk, ebwt.h:3825-4388;
  * fastaRefReadSizes, ref_read.cpp:202-273): writes out_base.{1,2,3,4}.ebwt and out_base.rev.{1,2}.ebwt, byte-identical to the
- * reference's files for the same FASTA input, -o (off_rate, default 5) and -t (ftab_chars, default 10).  The suffix sort
- * runs on `device`; FASTA parsing and file packing are host work. */
+ * reference's files for the same FASTA input, -o (off_rate, default 5) and -t (ftab_chars, default 10).  Everything that is
+ * O(genome) runs on `device` (suffix sort, BWT, side packing with occ words, SA sample, ftab histogram, the 2-bit reference);
+ * FASTA parsing and writing the files are host work. */
 int  bt_index_build(const char *const *fasta_paths, uint32_t n_paths, const char *out_base, int off_rate, int ftab_chars, int device);
+
+/* The same from an already parsed reference — what fastaRefReadSizes / fastaRefReadAppend (ref_read.cpp:10-141,202-273) hand to
+ * Ebwt::initFromVector: `text` = the joined unambiguous characters (codes 0..3, one per byte, host memory, text_len < 2^32 - 1),
+ * `recs` = the RefRecords (ref_read.h:57-88: `off` gap characters, then `len` unambiguous ones; `first` = 1 on the first record of
+ * a sequence), `names` = one per sequence.  Used where the reference exists in memory (synthetic genomes of bench.py). */
+typedef struct bt_ref_record { uint32_t off, len, first; } bt_ref_record_t;
+int  bt_index_build_text(const uint8_t *text, uint64_t text_len, const bt_ref_record_t *recs, uint32_t n_recs, const char *const *names, uint32_t n_names,
+                         const char *out_base, int off_rate, int ftab_chars, int device);
 
 /* LF primitives on the device layout, for parity tests: computes, for each row, mapLFEx-style
  * (fchr[c] + occ(c,row)) for c = 0..3 and rowL.  rows/out are host arrays; out has 5 words per row. */

@@ -149,13 +149,29 @@ int bt_context_sync(bt_context_t *, void *) { return 0; }
 int bt_context_join(bt_context_t *, void *) { return 0; }
 int bt_stats_get(bt_index_t *ix, bt_stats_t *out, int) { *out = ix->st; return 0; }
 int bt_debug_lf(bt_index_t *, int, const uint32_t *, uint32_t, uint32_t *) { g_err = "not in the shim"; return 1; }
-/* index construction: the product's host code (bt_build.h) and suffix-sort algorithm (bt_build_sa.cuh) over the host backend */
+/* index construction: the product's host code (bt_build.h) and per-element device code (bt_build_sa.cuh) over the host backend */
 int bt_index_build(const char *const *fasta_paths, uint32_t n_paths, const char *out_base, int off_rate, int ftab_chars, int) {
 	std::vector<std::string> files;
 	for (uint32_t i = 0; i < n_paths; i++) files.push_back(fasta_paths[i]);
 	BtBuildParams P; P.offRate = off_rate; P.ftabChars = ftab_chars;
 	std::string err;
-	if (!bt_build_all(files, out_base, P, doubling_sort, NULL, err)) { g_err = err; return 1; }
+	if (!host_build_all(files, out_base, P, err)) { g_err = err; return 1; }
+	return 0;
+}
+int bt_index_build_text(const uint8_t *text, uint64_t text_len, const bt_ref_record_t *recs, uint32_t n_recs, const char *const *names, uint32_t n_names,
+                        const char *out_base, int off_rate, int ftab_chars, int) {
+	BtRefInfo R; std::string err;
+	R.text = text; R.textLen = text_len;
+	for (uint32_t i = 0; i < n_recs; i++) {
+		R.recs.push_back({ recs[i].off, recs[i].len, (uint8_t)(recs[i].first ? 1 : 0) });
+		if (recs[i].first) R.plens.push_back(0);
+		if (R.plens.empty()) { g_err = "bt_index_build_text: the first record must start a sequence"; return 1; }
+		R.plens.back() += recs[i].off + recs[i].len;
+	}
+	for (uint32_t i = 0; i < n_names; i++) R.names.push_back(names[i] ? names[i] : "");
+	BtBuildParams P; P.offRate = off_rate; P.ftabChars = ftab_chars;
+	BsaHost be;
+	if (!bt_build_check_ref(R, err) || !bt_build_all_on(be, R, out_base, P, err)) { g_err = err; return 1; }
 	return 0;
 }
 }

@@ -1,5 +1,5 @@
-/* Test-only driver for bt_build.h: the suffix sort is done here with std::sort (the product sorts on the GPU, bt_build_sa.cuh);
- * everything else — FASTA records, joined text, side packing, ftab/eftab, file layout — is the product's host code. */
+/* Test-only driver for bt_build.h / bt_build_sa.cuh over the host backend (bsa_host.h): the same templates and per-element
+ * functors the product runs on the GPU, executed sequentially with std:: algorithms in place of CUB. */
 #include "bsa_host.h"
 
 int main(int argc, char **argv) {
@@ -13,6 +13,6 @@ int main(int argc, char **argv) {
 		else base = a;
 	}
 	std::string err;
-	if (!bt_build_all(fa, base, P, getenv("BT_BUILD_CMPSORT") ? host_sort : doubling_sort, NULL, err)) { fprintf(stderr, "%s\n", err.c_str()); return 1; }
+	if (!host_build_all(fa, base, P, err)) { fprintf(stderr, "%s\n", err.c_str()); return 1; }
 	return 0;
 }

@@ -4,7 +4,7 @@ the reference's bowtie-build writes for the same FASTA input, -o and -t.
 CPU suite: the product's host code (bt_build.h: FASTA records, joined text, side packing, ftab/eftab, file layout) and its
 suffix-sort algorithm (bt_build_sa.cuh: prefix doubling) run over the test-only host backend (tests/host_emu/bsa_host.h,
 std:: algorithms in place of CUB) through the emulation shim.  GPU suite: the same through libbowtie_b200.so, i.e. with the CUB
-backend of bt_build.cu — opt-in (BT_TEST_GPU_BUILD=1) until that backend has had its first run on a device.
+backend of bt_build.cu on the device.
 """
 import os
 import random
@@ -146,9 +146,27 @@ def test_built_index_is_searchable(tools, tmp_path):
     assert outs[0] == outs[1] and len(outs[0]) > 0
 
 
+def check_build_text(lib_env, tmp_path, total_len):
+    """bt_index_build_text on bench.py's synthetic genome (records with N gaps, no FASTA) against bowtie-build on the FASTA
+    written from the same records: the entry point bench.py builds its hg19-sized index with."""
+    p = subprocess.run([os.sys.executable, str(ROOT / "tests" / "build_text_child.py"), str(total_len), str(tmp_path / "bt_ours"), str(tmp_path / "bt.fa")],
+                       capture_output=True, text=True, env=lib_env)
+    assert p.returncode == 0, p.stderr
+    b = subprocess.run([str(REF_BUILD), "-q", "-o", "4", "-t", "8", str(tmp_path / "bt.fa"), str(tmp_path / "bt_ref")], capture_output=True, text=True)
+    assert b.returncode == 0, b.stderr
+    for e in EXTS:
+        assert (tmp_path / f"bt_ours.{e}.ebwt").read_bytes() == (tmp_path / f"bt_ref.{e}.ebwt").read_bytes(), e
+
+
+def test_build_text_matches_bowtie_build_host_emulation(tools, tmp_path):
+    build_shim()
+    check_build_text(dict(os.environ, BOWTIE_B200_LIB=str(SHIM_DIR / "libbowtie_b200.so")), tmp_path, 600_000)
+
+
 @pytest.mark.gpu
 def test_index_files_match_bowtie_build_gpu(tools, tmp_path):
-    if os.environ.get("BT_TEST_GPU_BUILD") != "1":
-        pytest.skip("the CUB backend of the builder has not run on a device yet: set BT_TEST_GPU_BUILD=1")
-    env = {k: v for k, v in os.environ.items() if k != "LD_LIBRARY_PATH"}
+    """The CUB backend on the device: e_coli against the reference's shipped index files, 25 random multi-sequence genomes and
+    the in-memory entry point against bowtie-build."""
+    env = {k: v for k, v in os.environ.items() if k not in ("LD_LIBRARY_PATH", "BOWTIE_B200_LIB")}
     check_builder(tools, env, tmp_path, 25)
+    check_build_text(env, tmp_path, 3_000_000)
