@@ -722,7 +722,7 @@ def main() -> None:
                "counters_allreduced": [int(x) for x in ctr.tolist()],
                "rank_ms_per_step": {"min": m["ms_ranks"][0] / steps, "median": m["ms_ranks"][len(m["ms_ranks"]) // 2] / steps, "max": ms_max / steps},
                # per step: ctl_set x3, main search, collect x3, heavy search, overflow search (best-first / paired: ctl_set x4, 4 arena tiers, 3 collects)
-               "gpu_launches": (9 if name in ("n2k1", "v0") else 11) * steps * 2}
+               "gpu_launches": (9 if name in ("n2k1", "v0") else 11) * steps}
         if m["clocks"] is not None:
             res["clocks"] = m["clocks"]
         # latency of ONE synchronous batch through bt_align_batch (the INTEGRATION.md stub's call): host buffers in, host buffers out

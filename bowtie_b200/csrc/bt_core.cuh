@@ -492,15 +492,19 @@ BT_FN void bt_position(BtLane &L, const BtKParams &P, const BtScratch &S,
 	bt_prologue(L, nc, nq);
 }
 
-/* A rare transition.  Every block below exists once; call sites communicate through lane fields. */
-BT_FN void bt_rare_step(BtLane &L, const BtKParams &P, const BtScratch &S) {
-	const BtDevIndex &ix = P.ix[L.ebwtSel];
-	switch (L.pc) {
-	case PC_PHASE:
+/* The rare transitions, one block each.  Every block exists once; call sites communicate through lane fields.  A block leaves
+ * L.pc at the next state; `break` inside a block ends it. */
+BT_FN void bt_blk_phase(BtLane &L, const BtKParams &P, const BtScratch &S) {
+	const BtDevIndex &ix = P.ix[L.ebwtSel]; (void)ix;
+	do {
 		bt_phase(L, P, S);
 		break;
+	} while (0);
+}
 
-	case PC_BT_BEGIN: {
+BT_FN void bt_blk_bt_begin(BtLane &L, const BtKParams &P, const BtScratch &S) {
+	const BtDevIndex &ix = P.ix[L.ebwtSel]; (void)ix;
+	do { {
 		/* backtrack(ham) (ebwt_search_backtrack.h:237-297) */
 		const uint32_t ftabChars = (uint32_t)ix.ftabChars;
 		L.numBts = 0; L.bailed = 0;
@@ -541,8 +545,12 @@ BT_FN void bt_rare_step(BtLane &L, const BtKParams &P, const BtScratch &S) {
 			else { L.ret = 0; L.pc = PC_BT_END; }
 		}
 		break; }
+	} while (0);
+}
 
-	case PC_FRAME_ENTER: {
+BT_FN void bt_blk_frame_enter(BtLane &L, const BtKParams &P, const BtScratch &S) {
+	const BtDevIndex &ix = P.ix[L.ebwtSel]; (void)ix;
+	do { {
 		/* the head of backtrack(stackDepth, depth, ...) up to the while loop (ebwt_search_backtrack.h:363-455);
 		 * the caller has filled stackDepth, depth, the rev offsets, top, bot, ham, rowbase, disableFtab */
 		L.rowd0 = L.depth > L.unrevOff ? L.depth : L.unrevOff;
@@ -556,9 +564,13 @@ BT_FN void bt_rare_step(BtLane &L, const BtKParams &P, const BtScratch &S) {
 		L.altNum = 0; L.eligibleNum = 0; L.eligibleSz = 0; L.eli = 0; L.elignore = 1; L.eltop = 0; L.elbot = 0;
 		L.elham = L.ham; L.elcint = 0; L.lowAltQual = 0xff; L.d = L.depth;
 		L.pc = PC_POS;
-	} /* fallthrough */
+	}
+	} while (0);
+}
 
-	case PC_POS: {
+BT_FN void bt_blk_pos(BtLane &L, const BtKParams &P, const BtScratch &S) {
+	const BtDevIndex &ix = P.ix[L.ebwtSel]; (void)ix;
+	do { {
 		/* top of while(cur < _qlen) (ebwt_search_backtrack.h:456-529) with its own query loads */
 		if (L.d >= L.qlen) {
 			if (L.stackDepth >= L.reportPartials) {
@@ -571,8 +583,12 @@ BT_FN void bt_rare_step(BtLane &L, const BtKParams &P, const BtScratch &S) {
 		const uint32_t cur = L.qlen - L.d - 1;
 		bt_prologue(L, bt_qry(L, cur), bt_qual_at(L, cur));
 		break; }
+	} while (0);
+}
 
-	case PC_BTLOOP: {
+BT_FN void bt_blk_btloop(BtLane &L, const BtKParams &P, const BtScratch &S) {
+	const BtDevIndex &ix = P.ix[L.ebwtSel]; (void)ix;
+	do { {
 		/* while((top == bot || backtrackDespiteMatch) && altNum > 0) (ebwt_search_backtrack.h:743-971) */
 		if (!((L.top == L.bot || L.f_bdm) && L.altNum > 0)) { L.pc = PC_POS_END; break; }
 		uint32_t i = L.d, j = 0, bttop = 0, btbot = 0, btham = L.ham, btcint = 0;
@@ -642,8 +658,12 @@ BT_FN void bt_rare_step(BtLane &L, const BtKParams &P, const BtScratch &S) {
 		L.top = ntop; L.bot = nbot; L.ham = btham; L.disableFtab = 0;
 		L.pc = PC_FRAME_ENTER;
 		break; }
+	} while (0);
+}
 
-	case PC_FRAME_RET: {
+BT_FN void bt_blk_frame_ret(BtLane &L, const BtKParams &P, const BtScratch &S) {
+	const BtDevIndex &ix = P.ix[L.ebwtSel]; (void)ix;
+	do { {
 		if (L.stackDepth == 0) { L.pc = PC_BT_END; break; }
 		/* POP: resume the parent after its recursive call returned L.ret */
 		const BtFrame &F = S.frames[L.stackDepth - 1];
@@ -656,9 +676,13 @@ BT_FN void bt_rare_step(BtLane &L, const BtKParams &P, const BtScratch &S) {
 		L.f_invHH = (F.flags & FF_INVHH) != 0; L.f_invExact = (F.flags & FF_INVEXACT) != 0; L.disableFtab = (F.flags & FF_DISABLEFTAB) != 0;
 		L.bttop = 0; L.btbot = F.btspread;
 		L.pc = PC_CHILD_RET;
-	} /* fallthrough */
+	}
+	} while (0);
+}
 
-	case PC_CHILD_RET: {
+BT_FN void bt_blk_child_ret(BtLane &L, const BtKParams &P, const BtScratch &S) {
+	const BtDevIndex &ix = P.ix[L.ebwtSel]; (void)ix;
+	do { {
 		/* after the recursive call (ebwt_search_backtrack.h:972-1064) */
 		if (L.ret) { L.pc = PC_FRAME_RET; break; }
 		if (L.bailed || (L.halfAndHalf && L.maxBts > 0 && L.numBts >= L.maxBts)) { L.bailed = 1; L.ret = 0; L.pc = PC_FRAME_RET; break; }
@@ -703,16 +727,24 @@ BT_FN void bt_rare_step(BtLane &L, const BtKParams &P, const BtScratch &S) {
 		}
 		L.pc = PC_BTLOOP;
 		break; }
+	} while (0);
+}
 
-	case PC_POS_END: {
+BT_FN void bt_blk_pos_end(BtLane &L, const BtKParams &P, const BtScratch &S) {
+	const BtDevIndex &ix = P.ix[L.ebwtSel]; (void)ix;
+	do { {
 		/* (ebwt_search_backtrack.h:1066-1078) reached when the backtrack loop gives up on a position */
 		if (L.f_must || L.f_invHH || L.f_invExact) { L.ret = 0; L.pc = PC_FRAME_RET; break; }
 		if (L.top == L.bot && L.altNum == 0) { L.ret = 0; L.pc = PC_FRAME_RET; break; }
 		L.d++;
 		L.pc = PC_POS;
 		break; }
+	} while (0);
+}
 
-	case PC_REPORT: {
+BT_FN void bt_blk_report(BtLane &L, const BtKParams &P, const BtScratch &S) {
+	const BtDevIndex &ix = P.ix[L.ebwtSel]; (void)ix;
+	do { {
 		/* reportAlignment(rep_sd, rep_top, rep_bot, rep_cost) (ebwt_search_backtrack.h:1455-1513) and the
 		 * prologue of reportFullAlignment (1522-1538) */
 		uint32_t sd = L.rep_sd;
@@ -730,9 +762,13 @@ BT_FN void bt_rare_step(BtLane &L, const BtKParams &P, const BtScratch &S) {
 		L.rep_r = L.rep_top + (bt_rand_next(L.rnd) % (L.rep_bot - L.rep_top));
 		L.rep_i = 0;
 		L.pc = PC_REPORT_ROW;
-	} /* fallthrough */
+	}
+	} while (0);
+}
 
-	case PC_REPORT_ROW: {
+BT_FN void bt_blk_report_row(BtLane &L, const BtKParams &P, const BtScratch &S) {
+	const BtDevIndex &ix = P.ix[L.ebwtSel]; (void)ix;
+	do { {
 		/* loop of reportFullAlignment (ebwt_search_backtrack.h:1539-1564) */
 		const uint32_t spread = L.rep_bot - L.rep_top;
 		if (L.rep_i >= spread) { L.ret = 0; L.pc = PC_REPORT_RET; break; }
@@ -741,9 +777,13 @@ BT_FN void bt_rare_step(BtLane &L, const BtKParams &P, const BtScratch &S) {
 		L.crow = ri; L.cjumps = 0;
 		if (((ri & ix.offMask) != ri) && ri != ix.zOff) { L.pc = PC_CHASE; break; }
 		L.pc = PC_RESOLVE;
-	} /* fallthrough */
+	}
+	} while (0);
+}
 
-	case PC_RESOLVE: {
+BT_FN void bt_blk_resolve(BtLane &L, const BtKParams &P, const BtScratch &S) {
+	const BtDevIndex &ix = P.ix[L.ebwtSel]; (void)ix;
+	do { {
 		/* marked row reached (ebwt.h:2735-2755), then Ebwt::report (2635-2682) and the sink:
 		 * NGoodHitSinkPerThread::reportHit (hit.h:969-985) / AllHitSinkPerThread::reportHit (hit.h:1201-1209)
 		 * fused with the Hit construction of EbwtSearchParams::reportHit (ebwt.h:1288-1405) */
@@ -782,8 +822,12 @@ BT_FN void bt_rare_step(BtLane &L, const BtKParams &P, const BtScratch &S) {
 		if (stop) { L.ret = 1; L.pc = PC_REPORT_RET; }
 		else { L.rep_i++; L.pc = PC_REPORT_ROW; }
 		break; }
+	} while (0);
+}
 
-	case PC_REPORT_RET: {
+BT_FN void bt_blk_report_ret(BtLane &L, const BtKParams &P, const BtScratch &S) {
+	const BtDevIndex &ix = P.ix[L.ebwtSel]; (void)ix;
+	do { {
 		switch (L.rep_site) {
 		case SITE_MAIN:
 			if (!L.ret) { L.top = L.bot; L.pc = PC_BTLOOP; }
@@ -794,8 +838,12 @@ BT_FN void bt_rare_step(BtLane &L, const BtKParams &P, const BtScratch &S) {
 		default: L.pc = PC_BT_END; break;
 		}
 		break; }
+	} while (0);
+}
 
-	case PC_BT_END: {
+BT_FN void bt_blk_bt_end(BtLane &L, const BtKParams &P, const BtScratch &S) {
+	const BtDevIndex &ix = P.ix[L.ebwtSel]; (void)ix;
+	do { {
 		/* tail of backtrack(depth, top, bot, ...) and finalize() (ebwt_search_backtrack.h:348-352, 303-324);
 		 * setMuts(NULL) of the seedling loops */
 		L.numBts = 0; L.bailed = 0;
@@ -804,7 +852,26 @@ BT_FN void bt_rare_step(BtLane &L, const BtKParams &P, const BtScratch &S) {
 		L.done = BTS_IGNORE(L.step) ? 0u : L.ret;
 		L.pc = PC_PHASE;
 		break; }
+	} while (0);
+}
 
+/* One rare transition (the queue-driven kernel and the chain below): dispatch on the state; FRAME_ENTER runs into POS, FRAME_RET
+ * into CHILD_RET, REPORT into REPORT_ROW into RESOLVE when the block left the lane there. */
+BT_FN void bt_rare_step(BtLane &L, const BtKParams &P, const BtScratch &S) {
+	switch (L.pc) {
+	case PC_PHASE: bt_blk_phase(L, P, S); break;
+	case PC_BT_BEGIN: bt_blk_bt_begin(L, P, S); break;
+	case PC_FRAME_ENTER: bt_blk_frame_enter(L, P, S); if (L.pc != PC_POS) break; /* fallthrough */
+	case PC_POS: bt_blk_pos(L, P, S); break;
+	case PC_BTLOOP: bt_blk_btloop(L, P, S); break;
+	case PC_FRAME_RET: bt_blk_frame_ret(L, P, S); if (L.pc != PC_CHILD_RET) break; /* fallthrough */
+	case PC_CHILD_RET: bt_blk_child_ret(L, P, S); break;
+	case PC_POS_END: bt_blk_pos_end(L, P, S); break;
+	case PC_REPORT: bt_blk_report(L, P, S); if (L.pc != PC_REPORT_ROW) break; /* fallthrough */
+	case PC_REPORT_ROW: bt_blk_report_row(L, P, S); if (L.pc != PC_RESOLVE) break; /* fallthrough */
+	case PC_RESOLVE: bt_blk_resolve(L, P, S); break;
+	case PC_REPORT_RET: bt_blk_report_ret(L, P, S); break;
+	case PC_BT_END: bt_blk_bt_end(L, P, S); break;
 	default: break;
 	}
 }
@@ -842,6 +909,7 @@ BT_FN void bt_fast_iter(BtLane &L, const BtKParams &P, const BtScratch &S) {
 	uint32_t nc = 4, nq = 0;
 	if (!isChase && L.d + 1 < L.qlen) { nc = bt_qry(L, L.qlen - L.d - 2); nq = bt_qual_at(L, L.qlen - L.d - 2); }
 	L.s_iter++; L.nit++;
+#if defined(BT_SPLIT_LF) || defined(BT_SPLIT_CHASE)
 	if (isChase) {
 		/* one step of the row walk of Ebwt::reportChaseOne (ebwt.h:2727-2734): mapLF(l) */
 		const uint32_t c = bt_row_l(bA, L.crow);
@@ -851,6 +919,7 @@ BT_FN void bt_fast_iter(BtLane &L, const BtKParams &P, const BtScratch &S) {
 		if (!(((nr & ix.offMask) != nr) && nr != ix.zOff)) L.pc = PC_RESOLVE;
 		return;
 	}
+#endif
 	const uint32_t c = L.c;
 	uint32_t tops[4] = { 0, 0, 0, 0 }, bots[4] = { 0, 0, 0, 0 };
 #ifndef BT_SPLIT_LF
@@ -859,10 +928,23 @@ BT_FN void bt_fast_iter(BtLane &L, const BtKParams &P, const BtScratch &S) {
 	 * from which every kind's result follows — mapLF1's is bots[c] - tops[c] == 1 exactly when rowL(top) == c and top is not the
 	 * '$' row (the block's A count skips '$').  Counters keep the reference's meaning.  -DBT_SPLIT_LF restores the three paths
 	 * (`make experiments`) for the A/B that this change still owes: it was made without a GPU, on the replay's prediction. */
-	if (L.lfk <= LFK_PAIR) {
-		bt_lf_ex(ix, bA, L.ltop, tops);
+	/* The locate step shares the path too: mapLF(row) = the quartet's entry of the row's own character (ebwt.h:2727-2734), so a warp
+	 * whose lanes are split between matching and locating still executes the block fetch and the rank arithmetic once. */
+	if (isChase || L.lfk <= LFK_PAIR) {
+		const uint32_t rowA = isChase ? L.crow : L.ltop;
+		bt_lf_ex(ix, bA, rowA, tops);
+		const uint32_t rlA = bt_row_l(bA, rowA);
+#ifndef BT_SPLIT_CHASE
+		if (isChase) {
+			const uint32_t nr = rlA == 0 ? tops[0] : rlA == 1 ? tops[1] : rlA == 2 ? tops[2] : tops[3];
+			L.crow = nr; L.cjumps++;
+			L.s_lf++; L.s_chase++;
+			if (!(((nr & ix.offMask) != nr) && nr != ix.zOff)) L.pc = PC_RESOLVE;
+			return;
+		}
+#endif
 		if (L.lfk == LFK_ONE) {                                          /* bot = top + 1: the quartet of the next row differs by the one character at top */
-			const uint32_t rl = (L.top != ix.zOff) ? bt_row_l(bA, L.ltop) : 4u;
+			const uint32_t rl = (L.top != ix.zOff) ? rlA : 4u;
 			bots[0] = tops[0] + (rl == 0); bots[1] = tops[1] + (rl == 1); bots[2] = tops[2] + (rl == 2); bots[3] = tops[3] + (rl == 3);
 		} else bt_lf_ex(ix, bB, L.lbot, bots);
 		if (L.lfk == LFK_EX) { L.s_lfex++; if (c < 4) { L.top = tops[c]; L.bot = bots[c]; } }
@@ -902,11 +984,48 @@ BT_FN void bt_fast_iter(BtLane &L, const BtKParams &P, const BtScratch &S) {
 	bt_position(L, P, S, tops, bots, nc, nq);
 }
 
-/* A batch of rare transitions: keep going until the lane needs a rank block again (or the read ends). */
+/* A batch of rare transitions: keep going until the lane needs a rank block again (or the read ends).
+ *
+ * BT_RARE_SWEEP (default): the blocks in the order a search flows through them — report -> (pop frame / bookkeeping after a child)* ->
+ * end of a backtracker -> phase program -> new backtracker -> backtrack target + push -> frame entry -> position prologue — so that a
+ * lane passes through its whole chain in ONE pass over the code and every block is executed at most once per round for all the lanes
+ * of the warp that need it (reconverging in between), instead of one `switch` per chain link in which the warp executes every distinct
+ * state of its lanes serially, link after link.  -DBT_RARE_SWEEP=0 restores the chain of single transitions. */
 #ifndef BT_RARE_CHAIN
 #define BT_RARE_CHAIN 8
 #endif
+#ifndef BT_RARE_SWEEP
+#define BT_RARE_SWEEP 1
+#endif
+#ifndef BT_SWEEP_ROUNDS
+#define BT_SWEEP_ROUNDS 3
+#endif
 BT_FN void bt_rare_iter(BtLane &L, const BtKParams &P, const BtScratch &S) {
+#if BT_RARE_SWEEP
+#define BT_STEP(state, blk) if (L.pc == (state) && !(L.flags & BT_FLAG_SCRATCH_OVF)) { L.s_iter++; L.nit++; blk(L, P, S); }
+#pragma unroll 1
+	for (int r = 0; r < BT_SWEEP_ROUNDS && BT_IS_RARE_STEP(L.pc); r++) {
+		if (L.flags & BT_FLAG_SCRATCH_OVF) { L.pc = PC_FINISH_READ; break; }
+		if (P.budget && L.nit > P.budget) { L.flags |= BT_FLAG_BUDGET; L.pc = PC_FINISH_READ; break; }   /* heavy read */
+		BT_STEP(PC_REPORT, bt_blk_report)
+		BT_STEP(PC_REPORT_ROW, bt_blk_report_row)
+		BT_STEP(PC_RESOLVE, bt_blk_resolve)
+		BT_STEP(PC_REPORT_RET, bt_blk_report_ret)
+#pragma unroll 1
+		for (int g = 0; g < 4 && (L.pc == PC_FRAME_RET || L.pc == PC_CHILD_RET); g++) {
+			BT_STEP(PC_FRAME_RET, bt_blk_frame_ret)
+			BT_STEP(PC_CHILD_RET, bt_blk_child_ret)
+		}
+		BT_STEP(PC_BT_END, bt_blk_bt_end)
+		BT_STEP(PC_PHASE, bt_blk_phase)
+		BT_STEP(PC_BT_BEGIN, bt_blk_bt_begin)
+		BT_STEP(PC_BTLOOP, bt_blk_btloop)
+		BT_STEP(PC_POS_END, bt_blk_pos_end)
+		BT_STEP(PC_FRAME_ENTER, bt_blk_frame_enter)
+		BT_STEP(PC_POS, bt_blk_pos)
+	}
+#undef BT_STEP
+#else
 #pragma unroll 1
 	for (int k = 0; k < BT_RARE_CHAIN && BT_IS_RARE_STEP(L.pc); k++) {
 		if (L.flags & BT_FLAG_SCRATCH_OVF) { L.pc = PC_FINISH_READ; break; }
@@ -914,4 +1033,5 @@ BT_FN void bt_rare_iter(BtLane &L, const BtKParams &P, const BtScratch &S) {
 		L.s_iter++; L.nit++;
 		bt_rare_step(L, P, S);
 	}
+#endif
 }
