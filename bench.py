@@ -367,8 +367,9 @@ def cpu_model() -> str:
     return "unknown"
 
 
-def run_reference(base: Path, fq, threads: int, flags, out_path="/dev/null") -> tuple[float, float]:
-    """bowtie-align-s <flags> -t -p <threads>; returns (wall seconds, 'Time searching' seconds or -1)."""
+def run_reference(base: Path, fq, threads: int, flags, out_path="/dev/null", stderr_to: list | None = None) -> tuple[float, float]:
+    """bowtie-align-s <flags> -t -p <threads>; returns (wall seconds, 'Time searching' seconds or -1); the run's stderr is
+    appended to `stderr_to` when given."""
     exe = REF_DIR / "bowtie-align-s"
     if not exe.exists():
         raise RuntimeError("oracle/_ref/bowtie-align-s missing (built by oracle/Makefile from /root/reference)")
@@ -378,6 +379,8 @@ def run_reference(base: Path, fq, threads: int, flags, out_path="/dev/null") -> 
     wall = time.time() - t0
     if p.returncode != 0:
         raise RuntimeError("reference run failed: " + p.stderr[-500:])
+    if stderr_to is not None:
+        stderr_to.append(p.stderr)
     search = -1.0
     for line in (p.stdout + p.stderr).splitlines():
         if line.startswith("Time searching:"):

@@ -70,7 +70,8 @@ __global__ void bt_debug_lf_kernel(BtDevIndex ix, const uint32_t *rows, uint32_t
 #define BT_Q_THREADS 384            /* worker threads per block                                               */
 #endif
 #define BT_SMEM_LEN 128            /* reads up to this length are staged in shared memory                   */
-#define BT_SMEM_STRIDE (2 * BT_SMEM_LEN + 4)   /* +4: lanes' equal offsets fall in different banks          */
+#define BT_SMEM_SNAP (2 * BT_SMEM_LEN)          /* 6 words: the lane's operation counters when its current read began    */
+#define BT_SMEM_STRIDE (2 * BT_SMEM_LEN + 28)  /* 71 words per lane (odd): lanes' equal offsets fall in different banks */
 
 struct BtWorkCtl { unsigned long long next; unsigned long long nwork; };
 
@@ -108,7 +109,15 @@ bt_search_kernel(BtKParams P, BtWorkCtl *ctl) {
 		if ((fmask | rmask) == 0) break;                                  /* every lane has exited */
 		const bool run_rare = (fmask == 0) || ((uint32_t)__popc(rmask) >= P.rare_thresh) || ((it % P.rare_period) == 0);
 		if (run_rare) {
-			if (L.pc == PC_FINISH_READ) { bt_finish_read(L, P); L.pc = PC_NEXT_READ; }
+			if (L.pc == PC_FINISH_READ) {
+				if (L.flags & BT_FLAG_RETRY) {
+					/* this read is re-run from scratch by a later pass: its operations so far are not part of the algorithm's
+					 * count (SURVEY.md §8d counts each read's side fetches once) */
+					const uint32_t *snap = reinterpret_cast<const uint32_t *>(my_stage + BT_SMEM_SNAP);
+					L.s_lfex = snap[0]; L.s_lf = snap[1]; L.s_chase = snap[2]; L.s_ftab = snap[3]; L.s_offs = snap[4]; L.s_blk = snap[5];
+				}
+				bt_finish_read(L, P); L.pc = PC_NEXT_READ;
+			}
 			/* work distribution: warp-aggregated grab from the global cursor, then the warp copies each new
 			 * read into the owning lane's shared-memory stage with coalesced loads */
 			const bool want = (L.pc == PC_NEXT_READ);
@@ -127,6 +136,8 @@ bt_search_kernel(BtKParams P, BtWorkCtl *ctl) {
 						bt_begin_read(L, P, rid);
 						ro = P.roff[rid];
 						got = true;
+						uint32_t *snap = reinterpret_cast<uint32_t *>(my_stage + BT_SMEM_SNAP);
+						snap[0] = L.s_lfex; snap[1] = L.s_lf; snap[2] = L.s_chase; snap[3] = L.s_ftab; snap[4] = L.s_offs; snap[5] = L.s_blk;
 					} else L.pc = PC_EXIT;
 				}
 				unsigned gmask = __ballot_sync(0xffffffffu, got && L.rlen <= BT_SMEM_LEN);
@@ -775,8 +786,9 @@ static void set_ws(BtKParams &P, const Workspace &w) {
 
 /* Enqueues one batch.  All pointers are device pointers; `maxlen` bounds the read length.
  *   main pass      on `st`:        every read, with a per-read transition budget and first-tier scratch
- *   heavy pass     on cx->side:    the few reads that exhausted the budget (long sequential searches), no budget
- *   overflow pass  on cx->side:    reads whose scratch overflowed in either pass, with worst-case scratch
+ *   tail pass      on cx->side:    the few reads that exhausted the budget (long sequential searches) or the first-tier scratch
+ *                                  (more seedlings than 64), no budget, 4096 seedlings
+ *   overflow pass  on cx->side:    reads whose scratch overflowed in the tail pass too, with worst-case scratch (normally empty)
  * The side stream lets the long tail of batch k overlap the main pass of batch k+1 (another context); the
  * batch is complete when cx->ev_tail has fired (bt_context_join / bt_context_sync). */
 static int enqueue_align(bt_context *cx, const bt_policy_t *pol, const bt_read_batch_t *in, bt_hit_batch_t *out, uint32_t maxlen, cudaStream_t st) {
@@ -792,8 +804,11 @@ static int enqueue_align(bt_context *cx, const bt_policy_t *pol, const bt_read_b
 	const uint32_t nthreads = main_kernel_is_queue() ? (uint32_t)ix->sms * BT_Q_NCTX : (uint32_t)ix->sms * (uint32_t)ix->blocks_per_sm * BT_THREADS;
 	const uint32_t stage_len = (maxlen + 15) & ~15u;                     /* every context keeps a writable copy of its read */
 	if (ensure_ws(cx->ws1, nthreads, 6 * maxlen + 8, 8, 64, stage_len)) return 1;
-	const uint32_t nthreads_h = (uint32_t)ix->sms * BT_HEAVY_BLOCKS_PER_SM * 32;
-	if (ensure_ws(cx->wsh, nthreads_h, 6 * maxlen + 8, 8, 64, stage_len)) return 1;
+	/* the tail pass takes the heavy reads AND the reads whose first-tier scratch overflowed (seedling lists of repeat reads, mostly),
+	 * so it gets the seedling capacity of the worst case: one pass instead of two serialised ones for the slowest reads of a batch */
+	static const uint32_t heavy_bps = env_u32("BT_HEAVY_BLOCKS", BT_HEAVY_BLOCKS_PER_SM);
+	const uint32_t nthreads_h = (uint32_t)ix->sms * heavy_bps * 32;
+	if (ensure_ws(cx->wsh, nthreads_h, 6 * maxlen + 8, 16, 4096, stage_len)) return 1;
 	const uint32_t nthreads2 = (uint32_t)ix->sms * 32;
 	uint32_t R2 = maxlen * maxlen + 8; if (R2 > 65000) R2 = 65000;   /* BtFrame::rowbase is 16 bits */
 	if (ensure_ws(cx->ws2, nthreads2, R2, maxlen + 2, 4096, stage_len)) return 1;
@@ -831,8 +846,7 @@ static int enqueue_align(bt_context *cx, const bt_policy_t *pol, const bt_read_b
 		if (grid > need) grid = need;
 		bt_search_kernel<<<grid, BT_THREADS, BT_THREADS * BT_SMEM_STRIDE, st>>>(P, cx->ctl);
 	}
-	bt_collect_kernel<<<cblocks, 256, 0, st>>>(out->flags, in->sel, nwork, nullptr, BT_FLAG_BUDGET, cx->heavy_sel, cx->ctl + 1);
-	bt_collect_kernel<<<cblocks, 256, 0, st>>>(out->flags, in->sel, nwork, nullptr, BT_FLAG_SCRATCH_OVF, cx->retry_sel, cx->ctl + 2);
+	bt_collect_kernel<<<cblocks, 256, 0, st>>>(out->flags, in->sel, nwork, nullptr, BT_FLAG_RETRY, cx->heavy_sel, cx->ctl + 1);
 	CUDA_TRY(cudaEventRecord(cx->ev_main, st));
 	/* heavy pass and overflow pass on the side stream */
 	CUDA_TRY(cudaStreamWaitEvent(cx->side, cx->ev_main, 0));
@@ -846,7 +860,7 @@ static int enqueue_align(bt_context *cx, const bt_policy_t *pol, const bt_read_b
 		bt_search_kernel_q<<<ix->sms, BT_Q_THREADS, bt_q_smem(BT_HEAVY_NCTX), cx->side>>>(P, cx->ctl + 1, BT_HEAVY_NCTX);
 		P.budget = 0;
 	} else {
-		bt_search_kernel<<<ix->sms * BT_HEAVY_BLOCKS_PER_SM, 32, 32 * BT_SMEM_STRIDE, cx->side>>>(P, cx->ctl + 1);
+		bt_search_kernel<<<ix->sms * heavy_bps, 32, 32 * BT_SMEM_STRIDE, cx->side>>>(P, cx->ctl + 1);
 	}
 	bt_collect_kernel<<<cblocks, 256, 0, cx->side>>>(out->flags, cx->heavy_sel, nwork, cx->ctl + 1, BT_FLAG_RETRY, cx->retry_sel, cx->ctl + 2);
 	P.sel = cx->retry_sel;

@@ -1,0 +1,90 @@
+"""Parity at BASELINE scale: the workloads bench.py times — 100-bp reads / 2x100-bp pairs sampled from the
+synthetic repeat-bearing genomes, `-n 2 -k 1`, `-n 2 --best`, paired `-n 3` — compared record by record (strand, reference, offset,
+other-matches count, mismatch list) with the unmodified reference binary on the same reads and index:
+
+* a 256-Mbp / 24-sequence genome of the same family (the size round 1 measured on);
+* the hg19-sized (3.0-Gbp) index bench.py measures on (joined offsets beyond 2^31, nFrag > nPat, reads that straddle fragment
+  boundaries; ebwt.h:2569-2629).
+Both indexes are built once per box by bt_index_build_text into bench.py's cache directory (seconds on a B200; the files are
+byte-identical to bowtie-build's, tests/test_index_build.py).
+
+The comparison code is bench.py's own `parity_sample` machinery, so the bench line's parity claim is the one tested here.
+"""
+import os
+import tempfile
+from pathlib import Path
+
+import numpy as np
+import pytest
+
+from helpers import ROOT, ensure_oracle_built, have_reference
+
+pytestmark = pytest.mark.gpu
+
+
+
+def _check(base: Path, policy: str, n: int, seed: int):
+    import bench
+    import bowtie_b200
+    ensure_oracle_built()
+    if not have_reference():
+        pytest.skip("reference binary not available")
+    bowtie_b200.build_library()
+    pd = bench.POLICIES[policy]
+    paired = pd["paired"]
+    R = 2 if paired else 1
+    genome = bench.load_genome(base)
+    h = (bench.make_pairs if paired else bench.make_reads)(genome, n, seed=seed)
+    del genome
+    ix = bowtie_b200.Index(str(base), need_mirror=True, device=0)
+    pol = bench.lib_policy(policy)
+    found, flags, hits = ix.align(h[0], h[1], h[2], h[3], pol, slots=R, mm_cap=7)
+    assert not (flags[: n] != 0).any(), "overflow flags on the bench workload"
+    got = bench.gpu_records(found, hits, n, paired)
+    with tempfile.TemporaryDirectory() as tdn:
+        td = Path(tdn)
+        fq = bench.write_sample(td, h, n, paired)
+        err: list = []
+        bench.run_reference(base, fq, min(32, bench.host_cores()), pd["flags"], td / "ref.out", stderr_to=err)
+        # ChunkPool exhaustion (pool.h:146-165) is the one documented deviation of the best-first path: the BASELINE
+        # configurations must not reach it, otherwise "identical to the reference" would be a claim about a different program
+        assert "Exhausted best-first chunk memory" not in err[0], "the reference ran out of --chunkmbs on a BASELINE configuration"
+        ref = bench.parse_reference_output(td / "ref.out", [x.decode() if isinstance(x, bytes) else x for x in ix.refnames])
+    res = bench.compare_parity(ref, got)
+    ix.close()
+    assert res["mismatching"] == 0, res
+    assert res["records_reference"] > 0.5 * n * R
+    return ref
+
+
+def _index(mbp):
+    import bench
+    try:
+        return bench.ensure_index(mbp, 0)[0]
+    except Exception as ex:          # no room / no time on this box: the bench reports the same failure loudly
+        pytest.skip(f"{mbp}-Mbp index unavailable: {ex}")
+
+
+@pytest.fixture(scope="module")
+def idx256():
+    return _index(256)
+
+
+@pytest.mark.parametrize("policy,n", [("n2k1", 200_000), ("best", 100_000), ("paired", 100_000)])
+def test_bench_workload_matches_reference_256mbp(idx256, policy, n):
+    _check(idx256, policy, n, seed=4242)
+
+
+@pytest.fixture(scope="module")
+def hg19_index():
+    return _index(int(os.environ.get("BT_TEST_HG19_MBP", 3000)))
+
+
+@pytest.mark.parametrize("policy,n", [("n2k1", 100_000), ("best", 100_000), ("paired", 100_000)])
+def test_bench_workload_matches_reference_hg19_sized(hg19_index, policy, n):
+    ref = _check(hg19_index, policy, n, seed=777)
+    # the hits must cover the far end of the joined text: sequences whose joined offset lies beyond 2^31 (chr13.. at 3 Gbp)
+    import bench
+    if bench.index_len(hg19_index) > (1 << 31):
+        tidx = np.array([v[1] for v in ref.values()])
+        assert (tidx >= 20).any() and (tidx <= 2).any()
