@@ -465,6 +465,39 @@ BT_FN void bt_position(BtLane &L, const BtKParams &P, const BtScratch &S,
 		}
 		if (L.stackDepth == 0 && L.bot > L.top && !L.reportExacts) { L.f_invExact = 1; L.f_bdm = 1; }
 	}
+#ifndef BT_MULTI_EXIT
+	/* one exit: every outcome sets `npc`, the lane state is written once at the end (the form with a `return` per outcome made the
+	 * compiler merge ~15 differently allocated copies of the lane into the loop header, a third of the fast path's instructions) */
+	uint32_t npc = PC_LF;
+	if (L.halfAndHalf) {
+		if ((d == (L.depth5 - 1)) && L.top < L.bot) {
+			L.f_invHH = (L.stackDepth == 0);
+			if (L.stackDepth == 0 && L.altNum > 0) { L.f_bdm = 1; L.f_must = 1; }
+			else if (L.stackDepth == 0) npc = PC_FRAME_RET;
+		} else if ((d == (L.depth3 - 1)) && L.top < L.bot) {
+			const uint32_t lh = bt_half_counts(S.frames, L.stackDepth, L.qlen, L.depth5, L.depth3);
+			L.f_invHH = ((lh & 0xffffu) == 0 || (lh >> 16) == 0);
+			if ((L.stackDepth < 2 || L.f_invHH) && L.altNum > 0) { L.f_must = 1; L.f_bdm = 1; }
+			else if (L.stackDepth < 2) npc = PC_FRAME_RET;
+		}
+	}
+	if (npc == PC_LF) {
+		if (cur == 0 && L.bot > L.top && !L.f_invHH && !L.f_invExact && !reportedPartial) {
+			/* reportAlignment(stackDepth, top, bot, ham) */
+			L.rep_sd = L.stackDepth; L.rep_top = L.top; L.rep_bot = L.bot; L.rep_cost = L.ham; L.rep_site = SITE_MAIN;
+			npc = PC_REPORT;
+		} else if ((L.top == L.bot || L.f_bdm) && L.altNum > 0) npc = PC_BTLOOP;          /* mismatch with alternatives */
+		else if (L.f_must || L.f_invHH || L.f_invExact || L.top == L.bot) npc = PC_FRAME_RET;
+		else {
+			L.d = d + 1;
+			if (L.d >= L.qlen) npc = PC_POS;
+			else if (L.halfAndHalf && !bt_hh_check_top(L, S)) npc = PC_FRAME_RET;
+		}
+	}
+	if (npc == PC_FRAME_RET) L.ret = 0;
+	L.pc = npc;
+	if (npc == PC_LF) bt_prologue(L, nc, nq);
+#else
 	if (L.halfAndHalf) {
 		if ((d == (L.depth5 - 1)) && L.top < L.bot) {
 			L.f_invHH = (L.stackDepth == 0);
@@ -490,6 +523,7 @@ BT_FN void bt_position(BtLane &L, const BtKParams &P, const BtScratch &S,
 	if (L.d >= L.qlen) { L.pc = PC_POS; return; }
 	if (L.halfAndHalf && !bt_hh_check_top(L, S)) { L.ret = 0; L.pc = PC_FRAME_RET; return; }
 	bt_prologue(L, nc, nq);
+#endif
 }
 
 /* The rare transitions, one block each.  Every block exists once; call sites communicate through lane fields.  A block leaves

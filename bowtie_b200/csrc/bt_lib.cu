@@ -100,6 +100,20 @@ bt_search_kernel(BtKParams P, BtWorkCtl *ctl) {
 	L.nmuts = 0; L.mut0 = L.mut1 = L.mut2 = 0; L.ebwtSel = 0; L.lfk = 0; L.ltop = L.lbot = L.crow = 0; L.flags = 0; L.d = 0; L.qlen = 0;
 	L.rlen = 0; L.rseq = my_stage; L.rqual = my_stage + BT_SMEM_LEN; L.hasN = 1; L.step = 0;
 	const unsigned long long nwork = ctl->nwork;
+#ifndef BT_INNER_FAST
+#define BT_INNER_FAST 1
+#endif
+#if BT_INNER_FAST
+	/* Two nested loops: the outer one runs a rare pass, the inner one up to `rare_period` fast iterations — left early when no lane
+	 * has fast work or `rare_thresh` lanes wait.  The inner loop's body is the fast transition alone, so its back edge merges only
+	 * the fast path's register assignment (the single-loop form paid ~100 register moves per iteration at the merge with the rare code). */
+	for (;;) {
+		{
+			const bool rare0 = !BT_IS_FAST(L.pc) && L.pc != PC_EXIT;
+			if (__ballot_sync(0xffffffffu, BT_IS_FAST(L.pc) || rare0) == 0) break;         /* every lane has exited */
+		}
+		{
+#else
 	uint32_t it = 0;
 	for (;; it++) {
 		const bool fast = BT_IS_FAST(L.pc);
@@ -109,6 +123,7 @@ bt_search_kernel(BtKParams P, BtWorkCtl *ctl) {
 		if ((fmask | rmask) == 0) break;                                  /* every lane has exited */
 		const bool run_rare = (fmask == 0) || ((uint32_t)__popc(rmask) >= P.rare_thresh) || ((it % P.rare_period) == 0);
 		if (run_rare) {
+#endif
 			if (L.pc == PC_FINISH_READ) {
 				if (L.flags & BT_FLAG_RETRY) {
 					/* this read is re-run from scratch by a later pass: its operations so far are not part of the algorithm's
@@ -175,7 +190,18 @@ bt_search_kernel(BtKParams P, BtWorkCtl *ctl) {
 			}
 			if (BT_IS_RARE_STEP(L.pc)) bt_rare_iter(L, P, S);
 		}
+#if BT_INNER_FAST
+#pragma unroll 1
+		for (uint32_t k = 0; k < P.rare_period; k++) {
+			const bool fast = BT_IS_FAST(L.pc);
+			const unsigned fmask = __ballot_sync(0xffffffffu, fast);
+			const unsigned rmask = __ballot_sync(0xffffffffu, !fast && L.pc != PC_EXIT);
+			if (fmask == 0 || (uint32_t)__popc(rmask) >= P.rare_thresh) break;
+			if (fast) bt_fast_iter(L, P, S);
+		}
+#else
 		if (fast) bt_fast_iter(L, P, S);
+#endif
 	}
 	/* statistics: warp-reduce, one atomic per warp and counter */
 	unsigned long long v[8] = { L.s_lfex, L.s_lf, L.s_chase, L.s_ftab, L.s_offs, L.s_bt, L.s_iter, L.s_blk };
