@@ -183,7 +183,10 @@ struct BtLane {
 };
 
 /* ---- small helpers --------------------------------------------------------------------------- */
-BT_FN uint32_t bt_qual_round(uint32_t q) { return q < 5 ? 0u : q < 15 ? 10u : q < 25 ? 20u : 30u; }  /* qual.cpp:4-32 */
+BT_FN uint32_t bt_qual_round(uint32_t q) {                                                          /* qual.cpp:4-32: 0 / 10 / 20 / 30 by Phred bucket */
+	const uint32_t r = ((q + 5u) / 10u) * 10u;                     /* branch-free: < 5 -> 0, 5..14 -> 10, 15..24 -> 20, >= 25 -> 30 */
+	return r < 30u ? r : 30u;
+}
 BT_FN uint32_t bt_mm_penalty(uint32_t maq, uint32_t q) { return maq ? bt_qual_round(q) : q; }          /* qual.h:55-61 */
 BT_FN uint32_t bt_rand_next(uint32_t &last) {                                                          /* random_source.h:45-54 */
 	last = 1664525u * last + 1013904223u;

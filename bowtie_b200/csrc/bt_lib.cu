@@ -58,10 +58,10 @@ __global__ void bt_debug_lf_kernel(BtDevIndex ix, const uint32_t *rows, uint32_t
 #define BT_MIN_BLOCKS 3            /* register cap = 65536 / (128 * BT_MIN_BLOCKS) */
 #endif
 #ifndef BT_RARE_PERIOD
-#define BT_RARE_PERIOD 16          /* rare transitions run at least every BT_RARE_PERIOD-th iteration ... */
+#define BT_RARE_PERIOD 8           /* rare transitions run at least every BT_RARE_PERIOD-th iteration ... */
 #endif
 #ifndef BT_RARE_THRESH
-#define BT_RARE_THRESH 24          /* ... or as soon as this many lanes of the warp wait for one          */
+#define BT_RARE_THRESH 16          /* ... or as soon as this many lanes of the warp wait for one (8 / 16: sweep on the hg19-sized index, profiles/) */
 #endif
 #ifndef BT_Q_NCTX
 #define BT_Q_NCTX 1024              /* read contexts per block of the queue-driven kernel                    */
@@ -472,7 +472,7 @@ struct bt_context {
 	Workspace ws1, wsh, ws2;     /* main pass / heavy-read pass / scratch-overflow pass */
 	uint32_t *arena[4] = { nullptr, nullptr, nullptr, nullptr }; size_t arena_words[4] = { 0, 0, 0, 0 };   /* best-first path: four arena tiers */
 	BtWorkCtl *ctl = nullptr;    /* [4] */
-	uint32_t *heavy_sel = nullptr, *retry_sel = nullptr; uint32_t retry_cap = 0;
+	uint32_t *heavy_sel = nullptr, *ultra_sel = nullptr, *retry_sel = nullptr; uint32_t retry_cap = 0;
 	cudaStream_t side = nullptr; /* the heavy and overflow passes run here, overlapping the next batch's main pass */
 	cudaEvent_t ev_main = nullptr, ev_tail = nullptr;
 	uint8_t *d_seq = nullptr, *d_qual = nullptr; uint64_t *d_offs = nullptr; uint32_t *d_seeds = nullptr, *d_sel = nullptr;
@@ -584,7 +584,7 @@ extern "C" void bt_context_free(bt_context_t *cx) {
 	if (cx->ev_tail) cudaEventDestroy(cx->ev_tail);
 	cx->ws1.release(); cx->wsh.release(); cx->ws2.release();
 	for (int k = 0; k < 4; k++) cudaFree(cx->arena[k]);
-	cudaFree(cx->ctl); cudaFree(cx->retry_sel); cudaFree(cx->heavy_sel);
+	cudaFree(cx->ctl); cudaFree(cx->retry_sel); cudaFree(cx->heavy_sel); cudaFree(cx->ultra_sel);
 	cudaFree(cx->d_seq); cudaFree(cx->d_qual); cudaFree(cx->d_offs); cudaFree(cx->d_seeds); cudaFree(cx->d_sel);
 	cudaFree(cx->d_found); cudaFree(cx->d_flags); cudaFree(cx->d_hits);
 	delete cx;
@@ -717,21 +717,11 @@ static int check_policy(const bt_index_t *ix, const bt_policy_t *pol) {
 #define BT_MAIN_BUDGET 8000u       /* transitions a read may take in the main pass before it is moved to the heavy pass */
 #endif
 /* Main / heavy pass kernels: thread-per-lane (default) or the experimental queue-driven kernel
- * (BT_MAIN_KERNEL=q / BT_HEAVY_KERNEL=q; see DESIGN.md §4.2 for the measurements that decided the default). */
+ * (BT_MAIN_KERNEL=q; see DESIGN.md §4.2 for the measurements that decided the default). */
 static uint32_t env_u32(const char *name, uint32_t dflt) { const char *e = getenv(name); return e ? (uint32_t)atol(e) : dflt; }
 static uint32_t main_budget() {
 	static long v = -1;
 	if (v < 0) { const char *e = getenv("BT_MAIN_BUDGET"); v = e ? atol(e) : (long)BT_MAIN_BUDGET; }
-	return (uint32_t)v;
-}
-static bool heavy_kernel_is_queue() {
-	static int v = -1;
-	if (v < 0) { const char *e = getenv("BT_HEAVY_KERNEL"); v = (e && e[0] == 'q') ? 1 : 0; }
-	return v == 1;
-}
-static uint32_t heavy_budget() {
-	static long v = -1;
-	if (v < 0) { const char *e = getenv("BT_HEAVY_BUDGET"); v = e ? atol(e) : 50000l; }
 	return (uint32_t)v;
 }
 static bool main_kernel_is_queue() {
@@ -740,8 +730,6 @@ static bool main_kernel_is_queue() {
 	return v == 1;
 }
 
-#define BT_HEAVY_NCTX 256           /* heavy pass, queue kernel: contexts per block (one block per SM)        */
-#define BT_HEAVY_BLOCKS_PER_SM 8   /* heavy pass: 32-thread blocks, so finished warps free their slots */
 
 /* The best-first path (bt_best.cuh).  Four passes with growing per-read arenas: every read with 64 KB on the caller's
  * stream (148 x 12 x 64 lanes); the reads that exhausted it with 1 MB (148 x 32 lanes), then 16 MB (148 lanes), then 256 MB
@@ -760,7 +748,8 @@ static int enqueue_best(bt_context *cx, const bt_policy_t *pol, const bt_read_ba
 	const uint32_t tierWords[NT] = { (pol->paired ? kw0 + kw0 / 2 : kw0) << 10, 256u << 10, 4096u << 10, 65536u << 10 };
 	const uint32_t tierLanes[NT] = { BF_THREADS, 32, 1, 1 };                                /* active threads per block */
 	/* first tier: 12 blocks of 64 lanes per SM = 768 resident threads (72 / 80 registers per thread: the register file allows 910 / 819) */
-	uint32_t tierBlocks[NT] = { (uint32_t)ix->sms * 12, (uint32_t)ix->sms, (uint32_t)ix->sms, 8 };
+	static const uint32_t bps0 = env_u32("BT_BEST_BLOCKS", 12);
+	uint32_t tierBlocks[NT] = { (uint32_t)ix->sms * bps0, (uint32_t)ix->sms, (uint32_t)ix->sms, 8 };
 	for (int k = 0; k < NT; k++) {
 		const uint32_t need_blocks = (nwork + tierLanes[k] - 1) / tierLanes[k];   /* small batches do not need a full machine of arenas */
 		if (tierBlocks[k] > need_blocks) tierBlocks[k] = need_blocks;
@@ -772,9 +761,10 @@ static int enqueue_best(bt_context *cx, const bt_policy_t *pol, const bt_read_ba
 		}
 	}
 	if (cx->retry_cap < nwork) {
-		cudaFree(cx->retry_sel); cudaFree(cx->heavy_sel); cx->retry_sel = cx->heavy_sel = nullptr; cx->retry_cap = 0;
+		cudaFree(cx->retry_sel); cudaFree(cx->heavy_sel); cudaFree(cx->ultra_sel); cx->retry_sel = cx->heavy_sel = cx->ultra_sel = nullptr; cx->retry_cap = 0;
 		CUDA_TRY(cudaMalloc((void **)&cx->retry_sel, (size_t)nwork * 4));
 		CUDA_TRY(cudaMalloc((void **)&cx->heavy_sel, (size_t)nwork * 4));
+		CUDA_TRY(cudaMalloc((void **)&cx->ultra_sel, (size_t)nwork * 4));
 		cx->retry_cap = nwork;
 	}
 	BfKParams P; memset(&P, 0, sizeof P);
@@ -812,9 +802,10 @@ static void set_ws(BtKParams &P, const Workspace &w) {
 
 /* Enqueues one batch.  All pointers are device pointers; `maxlen` bounds the read length.
  *   main pass      on `st`:        every read, with a per-read transition budget and first-tier scratch
- *   tail pass      on cx->side:    the few reads that exhausted the budget (long sequential searches) or the first-tier scratch
- *                                  (more seedlings than 64), no budget, 4096 seedlings
- *   overflow pass  on cx->side:    reads whose scratch overflowed in the tail pass too, with worst-case scratch (normally empty)
+ *   tail pass      on cx->side:    the reads that exhausted the budget or the first-tier scratch (more seedlings than 64): a second,
+ *                                  large budget, 4096 seedlings, full-size blocks
+ *   ultra pass     on cx->side:    the handful of reads beyond the second budget: no budget, single-warp blocks on a fraction of the SMs
+ *   overflow pass  on cx->side:    reads whose scratch overflowed in the tail / ultra pass too, worst-case scratch (normally empty)
  * The side stream lets the long tail of batch k overlap the main pass of batch k+1 (another context); the
  * batch is complete when cx->ev_tail has fired (bt_context_join / bt_context_sync). */
 static int enqueue_align(bt_context *cx, const bt_policy_t *pol, const bt_read_batch_t *in, bt_hit_batch_t *out, uint32_t maxlen, cudaStream_t st) {
@@ -831,17 +822,18 @@ static int enqueue_align(bt_context *cx, const bt_policy_t *pol, const bt_read_b
 	const uint32_t stage_len = (maxlen + 15) & ~15u;                     /* every context keeps a writable copy of its read */
 	if (ensure_ws(cx->ws1, nthreads, 6 * maxlen + 8, 8, 64, stage_len)) return 1;
 	/* the tail pass takes the heavy reads AND the reads whose first-tier scratch overflowed (seedling lists of repeat reads, mostly),
-	 * so it gets the seedling capacity of the worst case: one pass instead of two serialised ones for the slowest reads of a batch */
-	static const uint32_t heavy_bps = env_u32("BT_HEAVY_BLOCKS", BT_HEAVY_BLOCKS_PER_SM);
-	const uint32_t nthreads_h = (uint32_t)ix->sms * heavy_bps * 32;
+	 * so it gets the seedling capacity of the worst case; the ultra pass shares its scratch (they run one after the other) */
+	static const uint32_t tail_bps = env_u32("BT_TAIL_BLOCKS", 2);
+	const uint32_t nthreads_h = (uint32_t)ix->sms * tail_bps * BT_THREADS;
 	if (ensure_ws(cx->wsh, nthreads_h, 6 * maxlen + 8, 16, 4096, stage_len)) return 1;
 	const uint32_t nthreads2 = (uint32_t)ix->sms * 32;
 	uint32_t R2 = maxlen * maxlen + 8; if (R2 > 65000) R2 = 65000;   /* BtFrame::rowbase is 16 bits */
 	if (ensure_ws(cx->ws2, nthreads2, R2, maxlen + 2, 4096, stage_len)) return 1;
 	if (cx->retry_cap < nwork) {
-		cudaFree(cx->retry_sel); cudaFree(cx->heavy_sel); cx->retry_sel = cx->heavy_sel = nullptr; cx->retry_cap = 0;
+		cudaFree(cx->retry_sel); cudaFree(cx->heavy_sel); cudaFree(cx->ultra_sel); cx->retry_sel = cx->heavy_sel = cx->ultra_sel = nullptr; cx->retry_cap = 0;
 		CUDA_TRY(cudaMalloc((void **)&cx->retry_sel, (size_t)nwork * 4));
 		CUDA_TRY(cudaMalloc((void **)&cx->heavy_sel, (size_t)nwork * 4));
+		CUDA_TRY(cudaMalloc((void **)&cx->ultra_sel, (size_t)nwork * 4));
 		cx->retry_cap = nwork;
 	}
 	BtKParams P; memset(&P, 0, sizeof P);
@@ -861,6 +853,7 @@ static int enqueue_align(bt_context *cx, const bt_policy_t *pol, const bt_read_b
 	bt_ctl_set_kernel<<<1, 1, 0, st>>>(cx->ctl, nwork);
 	bt_ctl_set_kernel<<<1, 1, 0, st>>>(cx->ctl + 1, 0);
 	bt_ctl_set_kernel<<<1, 1, 0, st>>>(cx->ctl + 2, 0);
+	bt_ctl_set_kernel<<<1, 1, 0, st>>>(cx->ctl + 3, 0);
 	if (main_kernel_is_queue()) {
 		uint32_t grid = (uint32_t)ix->sms;
 		const uint32_t need = (nwork + BT_Q_NCTX - 1) / BT_Q_NCTX;
@@ -874,24 +867,26 @@ static int enqueue_align(bt_context *cx, const bt_policy_t *pol, const bt_read_b
 	}
 	bt_collect_kernel<<<cblocks, 256, 0, st>>>(out->flags, in->sel, nwork, nullptr, BT_FLAG_RETRY, cx->heavy_sel, cx->ctl + 1);
 	CUDA_TRY(cudaEventRecord(cx->ev_main, st));
-	/* heavy pass and overflow pass on the side stream */
+	/* tail, ultra and overflow passes on the side stream */
 	CUDA_TRY(cudaStreamWaitEvent(cx->side, cx->ev_main, 0));
-	P.sel = cx->heavy_sel; P.budget = 0;
-	set_ws(P, cx->wsh);
 	{ static uint32_t p = env_u32("BT_HEAVY_PERIOD", BT_RARE_PERIOD), t = env_u32("BT_HEAVY_THRESH", BT_RARE_THRESH); P.rare_period = p ? p : 1; P.rare_thresh = t; }
-	if (heavy_kernel_is_queue()) {
-		/* heavy reads are ~1 % of the reads but ~45 % of the work: run them SIMT-efficiently too; the handful that exceed
-		 * the second budget (sequential searches of 10^5..10^6 transitions) finish in the last pass, where latency matters */
-		P.budget = heavy_budget();
-		bt_search_kernel_q<<<ix->sms, BT_Q_THREADS, bt_q_smem(BT_HEAVY_NCTX), cx->side>>>(P, cx->ctl + 1, BT_HEAVY_NCTX);
-		P.budget = 0;
-	} else {
-		bt_search_kernel<<<ix->sms * heavy_bps, 32, 32 * BT_SMEM_STRIDE, cx->side>>>(P, cx->ctl + 1);
-	}
-	bt_collect_kernel<<<cblocks, 256, 0, cx->side>>>(out->flags, cx->heavy_sel, nwork, cx->ctl + 1, BT_FLAG_RETRY, cx->retry_sel, cx->ctl + 2);
+	set_ws(P, cx->wsh);
+	/* tail pass: full-size blocks, a second (large) budget, so that it ends when its bulk is done — its few stragglers move on */
+	static const uint32_t tail_budget = env_u32("BT_TAIL_BUDGET", 131072);
+	P.sel = cx->heavy_sel; P.budget = tail_budget;
+	bt_search_kernel<<<ix->sms * tail_bps, BT_THREADS, BT_THREADS * BT_SMEM_STRIDE, cx->side>>>(P, cx->ctl + 1);
+	bt_collect_kernel<<<cblocks, 256, 0, cx->side>>>(out->flags, cx->heavy_sel, nwork, cx->ctl + 1, BT_FLAG_BUDGET, cx->ultra_sel, cx->ctl + 2);
+	bt_collect_kernel<<<cblocks, 256, 0, cx->side>>>(out->flags, cx->heavy_sel, nwork, cx->ctl + 1, BT_FLAG_SCRATCH_OVF, cx->retry_sel, cx->ctl + 3);
+	/* ultra pass: the handful of searches of 10^5 .. 10^6 sequential transitions.  They take as long as they take (a GPU lane is a
+	 * slow serial processor); what matters is that they hold few resources while they do: single-warp blocks on a fraction of the
+	 * SMs, so that the main passes of the following batches keep (almost) the whole machine */
+	static const uint32_t ultra_blocks = env_u32("BT_ULTRA_BLOCKS", 74);
+	P.sel = cx->ultra_sel; P.budget = 0;
+	bt_search_kernel<<<ultra_blocks, 32, 32 * BT_SMEM_STRIDE, cx->side>>>(P, cx->ctl + 2);
+	bt_collect_kernel<<<cblocks, 256, 0, cx->side>>>(out->flags, cx->ultra_sel, nwork, cx->ctl + 2, BT_FLAG_RETRY, cx->retry_sel, cx->ctl + 3);
 	P.sel = cx->retry_sel;
 	set_ws(P, cx->ws2);
-	bt_search_kernel<<<ix->sms, 32, 32 * BT_SMEM_STRIDE, cx->side>>>(P, cx->ctl + 2);
+	bt_search_kernel<<<ix->sms, 32, 32 * BT_SMEM_STRIDE, cx->side>>>(P, cx->ctl + 3);
 	CUDA_TRY(cudaGetLastError());
 	return 0;
 }
