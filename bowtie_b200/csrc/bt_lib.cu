@@ -425,7 +425,7 @@ __global__ void bt_ctl_set_kernel(BtWorkCtl *ctl, unsigned long long nwork) { ct
 
 static thread_local std::string g_err;
 static int fail(const std::string &m) { g_err = m; return 1; }
-int bt_internal_fail(const std::string &m) { return fail(m); }       /* for bt_build.cu */
+int bt_internal_fail(const std::string &m) { return fail(m); }       /* for bt_build.cu, bt_io.cu */
 #define CUDA_TRY(x) do { cudaError_t e_ = (x); if (e_ != cudaSuccess) return fail(std::string(#x) + ": " + cudaGetErrorString(e_)); } while (0)
 
 struct HostEbwt {     /* the parsed contents of X.1.ebwt / X.2.ebwt */
@@ -480,6 +480,9 @@ struct bt_context {
 	size_t cap_seq = 0, cap_qual = 0, cap_offs = 0, cap_seeds = 0, cap_found = 0, cap_flags = 0, cap_hitwords = 0, cap_sel = 0;
 	std::mutex mu;
 };
+
+int bt_internal_context_device(bt_context_t *cx) { return cx->ix->device; }
+bt_index_t *bt_internal_context_index(bt_context_t *cx) { return cx->ix; }
 
 static bool read_exact(FILE *f, void *p, size_t n) { return fread(p, 1, n, f) == n; }
 

@@ -1324,6 +1324,63 @@ int main(int argc, char **argv) {
 		numAligned += cnt[0]; numUnaligned += cnt[1]; numMaxed += cnt[2]; numReported += cnt[3]; numReportedPaired += cnt[4];
 	};
 
+	/* Device I/O path (bt_io_parse_fastq / bt_io_align_format): for the common case — one stream of plain
+	 * single-end FASTQ, default or SAM output — the file's text goes to the GPU as it is, reads are cut out of it, searched and
+	 * formatted there, and what comes back is the output text, in input order.  The host only reads and writes files.  The path
+	 * covers well-formed records and the options listed below; it stops at the first record it does not cover (and always before
+	 * the last record of the input), leaving the Reader exactly there: everything else — odd records, the end of the file, the
+	 * other options — is the host pipeline's, whose behaviour is the specification.  BT_CLI_HOST_IO=1 turns the device path off. */
+	double t_dev_io = 0; uint64_t n_dev_io = 0;
+	{
+		bool anySuppress = false;
+		for (size_t i = 0; i < op.suppress.size(); i++) anySuppress = anySuppress || op.suppress[i];
+		const bool dev_ok = !getenv("BT_CLI_HOST_IO") && !pairedInput && !tabbed && !interleaved && op.format == FASTQ && !op.allHits && !op.sampleMax &&
+			op.khits >= 1 && op.khits <= 16 && !op.refIdx && !op.printCost && !anySuppress && op.dumpAl.empty() && op.dumpUn.empty() && op.dumpMax.empty() &&
+			op.skipReads == 0 && op.qUpto == 0xffffffffu && op.trim5 == 0 && op.trim3 == 0 && !op.solexaQuals && !op.phred64Quals && !op.integerQuals;
+		if (dev_ok && (rd.f || rd.open_next())) {
+			if (rd.first) {                                                          /* as fq_gather does for the first record of a file */
+				int c = rd.peek_();
+				while (c == '\r' || c == '\n') { rd.getc_(); c = rd.peek_(); }
+				if (c == '@') rd.first = false;
+			}
+			if (!rd.first && rd.fast_ok()) {
+				const auto td0 = std::chrono::steady_clock::now();
+				bt_io_t *io[2] = { NULL, NULL };
+				for (int k = 0; k < 2; k++) if (bt_io_create(bt[k].cx, &io[k])) die(std::string("Error: ") + bt_last_error());
+				size_t chunk = 192u << 20;
+				if (const char *e = getenv("BT_CLI_CHUNK_MB")) chunk = (size_t)std::max(1l, atol(e)) << 20;
+				if (rd.buf.size() < chunk) rd.buf.resize(chunk);
+				bt_io_format_t fmt; memset(&fmt, 0, sizeof fmt);
+				fmt.sam = op.sam; fmt.no_unal = op.noUnal; fmt.no_qname_trunc = op.noQnameTrunc; fmt.full_ref = op.fullRef; fmt.off_base = op.offBase; fmt.mapq = (uint32_t)op.defaultMapq;
+				out.flush();
+				std::thread writer;
+				for (size_t k = 0;; k++) {
+					if (rd.pos > 0) { memmove(rd.buf.data(), rd.buf.data() + rd.pos, rd.len - rd.pos); rd.len -= rd.pos; rd.pos = 0; }
+					while (!rd.eof && rd.len < rd.buf.size()) {
+						const int got = gzread(rd.f, rd.buf.data() + rd.len, (unsigned)std::min<size_t>(rd.buf.size() - rd.len, (size_t)1 << 30));
+						if (got <= 0) { rd.eof = true; break; }
+						rd.len += (size_t)got;
+					}
+					if (rd.len == 0) break;
+					uint32_t n = 0; uint64_t used = 0; int irregular = 0;
+					if (bt_io_parse_fastq(io[k & 1], rd.buf.data(), rd.len, op.seed, 0xffffffffu, &n, &used, &irregular)) die(std::string("Error: ") + bt_last_error());
+					if (n == 0) break;
+					const char *text = NULL; uint64_t bytes = 0, cnt[4] = { 0, 0, 0, 0 };
+					if (bt_io_align_format(io[k & 1], &polU, &fmt, &text, &bytes, cnt)) die(std::string("Error: ") + bt_last_error());
+					if (writer.joinable()) writer.join();                              /* chunk k-1 is on disk: its buffer (the other io's) may be reused */
+					FILE *fp = out.fp;
+					writer = std::thread([fp, text, bytes]() { if (bytes) fwrite(text, 1, (size_t)bytes, fp); });
+					numAligned += cnt[0]; numUnaligned += cnt[1]; numMaxed += cnt[2]; numReported += cnt[3];
+					rd.pos = (size_t)used; rd.rdid += n; n_dev_io += n;
+					if (irregular) break;
+				}
+				if (writer.joinable()) writer.join();
+				for (int k = 0; k < 2; k++) bt_io_free(io[k]);
+				t_dev_io = std::chrono::duration<double>(std::chrono::steady_clock::now() - td0).count();
+			}
+		}
+	}
+
 	/* Three batches in a ring: a parser thread fills batch k+1 while the GPU searches batch k and this thread formats batch k-1
 	 * (the reference parses and formats inside its -p worker threads; here the search needs no host thread at all). */
 	std::mutex mu; std::condition_variable cv;
@@ -1361,6 +1418,7 @@ int main(int argc, char **argv) {
 	}
 	if (prev >= 0) { auto t1 = std::chrono::steady_clock::now(); finish(bt[prev]); t_finish += std::chrono::duration<double>(std::chrono::steady_clock::now() - t1).count(); }
 	parser.join();
+	if (getenv("BT_CLI_TIMING")) fprintf(stderr, "device I/O path: %llu reads in %.2f s\n", (unsigned long long)n_dev_io, t_dev_io);
 	if (getenv("BT_CLI_TIMING")) fprintf(stderr, "host pipeline: parse %.2f s (parser thread; fast path: scan %.2f s, records %.2f s), launch %.2f s, sync+format %.2f s\n", t_fill, rd.t_scan, rd.t_work, t_launch, t_finish);
 	out.flush();
 	if (out.fp != stdout) fclose(out.fp);

@@ -26,7 +26,7 @@
 extern "C" {
 #endif
 
-#define BT_ABI_VERSION 4
+#define BT_ABI_VERSION 5
 
 typedef struct bt_index bt_index_t;
 typedef struct bt_context bt_context_t;
@@ -167,6 +167,33 @@ int  bt_index_build(const char *const *fasta_paths, uint32_t n_paths, const char
 typedef struct bt_ref_record { uint32_t off, len, first; } bt_ref_record_t;
 int  bt_index_build_text(const uint8_t *text, uint64_t text_len, const bt_ref_record_t *recs, uint32_t n_recs, const char *const *names, uint32_t n_names,
                          const char *out_base, int off_rate, int ftab_chars, int device);
+
+/* Device I/O path: read ingest and hit formatting on the device, around the same search.
+ *   bt_io_parse_fastq    replaces FastqPatternSource::parse + genRandSeed (pat.cpp:858-975, 21-57; read.h:118-132) for well-formed
+ *                        4-line FASTQ (Phred+33): `text` (host memory) must start at a record; the complete, regular records at its
+ *                        start — at most max_reads, never the chunk's last complete one — become a device-resident read batch.
+ *                        *consumed = bytes of text they cover; *irregular != 0 if a record was met that the host parser must handle
+ *                        (the caller hands everything from text + *consumed on to it).
+ *   bt_io_align_format   runs the policy over that batch (bt_context_align_device on the io's context) and formats the hits on the
+ *                        device: the default format (VerboseHitSink::append, hit.cpp:176-240) or SAM records (SAMHitSink::append /
+ *                        reportUnOrMax, sam.cpp:57-257; no header), unpaired, with finishRead's -k / -m arithmetic (hit.h:741-786), in
+ *                        read order.  *out_text (host memory owned by the io, valid until its next call) holds *out_bytes bytes;
+ *                        counters = { aligned, unaligned, maxed, reported } of hit.h:169-175.  Not provided here (callers format those
+ *                        from hit records): paired-end, -a, -M, --suppress / --refidx / cost columns.
+ * One io per in-flight chunk; calls on one io are synchronous. */
+typedef struct bt_io bt_io_t;
+typedef struct bt_io_format {
+	int32_t  sam;             /* 0: default format, 1: SAM records               */
+	int32_t  no_unal;         /* --no-unal                                        */
+	int32_t  no_qname_trunc;  /* --sam-no-qname-trunc                             */
+	int32_t  full_ref;        /* --fullref                                        */
+	int32_t  off_base;        /* -B                                               */
+	uint32_t mapq;            /* --mapq (255)                                     */
+} bt_io_format_t;
+int  bt_io_create(bt_context_t *cx, bt_io_t **out);
+void bt_io_free(bt_io_t *io);
+int  bt_io_parse_fastq(bt_io_t *io, const char *text, uint64_t nbytes, uint32_t global_seed, uint32_t max_reads, uint32_t *nreads, uint64_t *consumed, int *irregular);
+int  bt_io_align_format(bt_io_t *io, const bt_policy_t *pol, const bt_io_format_t *fmt, const char **out_text, uint64_t *out_bytes, uint64_t counters[4]);
 
 /* LF primitives on the device layout, for parity tests: computes, for each row, mapLFEx-style
  * (fchr[c] + occ(c,row)) for c = 0..3 and rowL.  rows/out are host arrays; out has 5 words per row. */

@@ -17,6 +17,7 @@
 #include "../../bowtie_b200/csrc/bt_best_prog.h"
 #include "../../bowtie_b200/csrc/bt_ref_load.h"
 #include "bsa_host.h"
+#include "../../bowtie_b200/csrc/bt_io_run.h"
 #include "../../include/bowtie_b200.h"
 extern "C" {
 #include "../../oracle/bt_oracle.h"
@@ -172,6 +173,48 @@ int bt_index_build_text(const uint8_t *text, uint64_t text_len, const bt_ref_rec
 	BtBuildParams P; P.offRate = off_rate; P.ftabChars = ftab_chars;
 	BsaHost be;
 	if (!bt_build_check_ref(R, err) || !bt_build_all_on(be, R, out_base, P, err)) { g_err = err; return 1; }
+	return 0;
+}
+
+/* device I/O path (f1 / f2): the product's functors (bt_io.cuh) and driver (bt_io_run.h) over a host backend; "device" memory is
+ * host memory here, and the search in between is this shim's bt_align_batch */
+}
+struct BioHost {
+	bt_context_t *cx = nullptr;
+	void *alloc(size_t bytes) { return malloc(bytes ? bytes : 1); }
+	void release(void *p) { free(p); }
+	void h2d(void *d, const void *s, size_t bytes) { memcpy(d, s, bytes); }
+	void d2h(void *d, const void *s, size_t bytes) { memcpy(d, s, bytes); }
+	void zero(void *d, size_t bytes) { memset(d, 0, bytes); }
+	void sync() { }
+	template <class F> void each(uint64_t n, F f) { for (uint64_t i = 0; i < n; i++) f(i); }
+	uint64_t count_nl(const char *t, uint64_t n) { uint64_t m = 0; for (uint64_t i = 0; i < n; i++) m += t[i] == '\n'; return m; }
+	void positions_nl(const char *t, uint64_t n, uint32_t *out) { uint64_t m = 0; for (uint64_t i = 0; i < n; i++) if (t[i] == '\n') out[m++] = (uint32_t)i; }
+	void excl_scan(uint32_t *a, uint64_t n) { uint32_t acc = 0; for (uint64_t i = 0; i < n; i++) { const uint32_t v = a[i]; a[i] = acc; acc += v; } }
+	int align(const bt_policy_t *pol, const bt_read_batch_t *in, bt_hit_batch_t *out) { return bt_align_batch(cx->ix, pol, in, out, NULL); }
+	char *out_host(size_t bytes, std::vector<char> &v) { v.resize(bytes); return v.data(); }
+};
+struct bt_io { BioPipe<BioHost> pipe; };
+extern "C" {
+int bt_io_create(bt_context_t *cx, bt_io_t **out) { bt_io *io = new bt_io(); io->pipe.be.cx = cx; io->pipe.init(); *out = io; return 0; }
+void bt_io_free(bt_io_t *io) { if (!io) return; io->pipe.destroy(); delete io; }
+int bt_io_parse_fastq(bt_io_t *io, const char *text, uint64_t nbytes, uint32_t global_seed, uint32_t max_reads, uint32_t *nreads, uint64_t *consumed, int *irregular) {
+	if (!io->pipe.parse(text, nbytes, global_seed, max_reads, nreads, consumed, irregular)) { g_err = io->pipe.err; return 1; }
+	return 0;
+}
+int bt_io_align_format(bt_io_t *io, const bt_policy_t *pol, const bt_io_format_t *fmt, const char **out_text, uint64_t *out_bytes, uint64_t counters[4]) {
+	BioPipe<BioHost> &p = io->pipe;
+	if (pol->paired || pol->all_hits || pol->sample_max || pol->khits == 0 || pol->khits > 16) { g_err = "bt_io_align_format: not provided on the device output path"; return 1; }
+	if (!p.have_names || p.names_full != (fmt->full_ref != 0)) {
+		std::vector<std::string> names;
+		const bt_index *ix = p.be.cx->ix;
+		for (uint32_t i = 0; i < ix->e[0]->raw->nPat; i++) names.push_back(i < ix->names.size() ? ix->names[i] : std::to_string(i));
+		p.set_names(names, fmt->full_ref != 0);
+	}
+	BioFmt f;
+	f.sam = fmt->sam ? 1u : 0u; f.khits = pol->khits; f.mhits = pol->mhits; f.strata = pol->strata ? 1u : 0u; f.noUnal = fmt->no_unal ? 1u : 0u;
+	f.noQnameTrunc = fmt->no_qname_trunc ? 1u : 0u; f.offBase = (uint32_t)fmt->off_base; f.mapq = fmt->mapq; f.slots = pol->khits; f.recWords = 0;
+	if (!p.align_format(pol, f, out_text, out_bytes, counters)) { g_err = p.err; return 1; }
 	return 0;
 }
 }

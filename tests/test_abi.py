@@ -35,7 +35,7 @@ def test_library_exports_every_declared_symbol(lib):
 
 def test_abi_version_and_policy_defaults(lib):
     from bowtie_b200.api import _Policy
-    assert lib.bt_abi_version() == 4
+    assert lib.bt_abi_version() == 5
     p = _Policy()
     lib.bt_policy_init(C.byref(p))
     # resetOptions defaults (ebwt_search.cpp:181-219)
