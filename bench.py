@@ -419,6 +419,47 @@ class ReferenceRunner:
         return {"n": n, "wall_s": wall, "search_s": max(1e-3, wall - self.overhead), "time_searching_s": search, "gave_up": gave_up}
 
 
+def cli_e2e(base: Path, h, n: int, td: Path, rr: "ReferenceRunner") -> dict:
+    """FASTQ file in -> SAM file out through the drop-in program (`bowtie-b200-align`: device read ingest, search, device formatting)
+    against `bowtie-align-s -p <best>` on the same file; both on a search-time basis (wall clock minus a one-read run of the same
+    program = process start + index load), with the wall-clock figures beside them.  Files live in RAM-backed storage."""
+    exe = ROOT / "bowtie_b200" / "bowtie-b200-align"
+    (td / "cli").mkdir(exist_ok=True)
+    fq = write_sample(td / "cli", h, n, False)
+    one = td / "one" / "s.fq"
+    flags = ["-n", "2", "-k", "1", "-S"]
+
+    def run(cmd) -> float:
+        t0 = time.time()
+        p = subprocess.run(cmd, capture_output=True, text=True)
+        if p.returncode != 0:
+            raise RuntimeError("cli_e2e run failed: " + p.stderr[-300:])
+        return time.time() - t0
+    o1 = min(run([str(exe), *flags, "-x", str(base), str(one), str(td / "o1.sam")]) for _ in range(2))
+    w = run([str(exe), *flags, "-x", str(base), str(fq), str(td / "ours.sam")])
+    r1 = min(run([str(REF_DIR / "bowtie-align-s"), *flags, "-p", str(rr.threads), "-x", str(base), str(one), str(td / "r1.sam")]) for _ in range(2))
+    rw = run([str(REF_DIR / "bowtie-align-s"), *flags, "-p", str(rr.threads), "-x", str(base), str(fq), str(td / "ref.sam")])
+    same = None
+    try:
+        a = [l for l in (td / "ours.sam").read_bytes().split(b"\n") if not l.startswith(b"@PG")]
+        if rr.threads == 1:
+            b = [l for l in (td / "ref.sam").read_bytes().split(b"\n") if not l.startswith(b"@PG")]
+            same = a == b
+        else:                      # the reference's -p threads write in completion order: compare as multisets of lines
+            b = [l for l in (td / "ref.sam").read_bytes().split(b"\n") if not l.startswith(b"@PG")]
+            same = sorted(a) == sorted(b)
+    except Exception:
+        pass
+    for f in ("ours.sam", "ref.sam"):
+        try:
+            (td / f).unlink()
+        except Exception:
+            pass
+    return {"reads": n, "flags": " ".join(flags), "value": n / max(1e-3, w - o1), "unit": "reads/s", "wall_s": round(w, 2), "start_and_index_load_s": round(o1, 2),
+            "reference_value": n / max(1e-3, rw - r1), "reference_wall_s": round(rw, 2), "reference_start_and_index_load_s": round(r1, 2),
+            "reference_threads": rr.threads, "sam_identical": same}
+
+
 def parse_reference_output(path: Path, refnames: list[str]) -> dict:
     """Default-format hit lines (hit.cpp:176-240) -> {(unit, mate): (fw, tidx, toff, oms, ((pos, refc), ...))}."""
     tid = {n.split()[0] if n.split() else n: i for i, n in enumerate(refnames)}
@@ -489,7 +530,7 @@ def reference_arm(args, base: Path, idx_name: str, idx_info: dict) -> None:
     nmax = max(args.cpu_sample, 200_000)
     h0 = gen(genome, nmax, seed=12345)
     del genome
-    with tempfile.TemporaryDirectory() as tdn:
+    with tempfile.TemporaryDirectory(dir="/dev/shm" if os.path.isdir("/dev/shm") and os.access("/dev/shm", os.W_OK) else None) as tdn:
         td = Path(tdn)
         rr = ReferenceRunner(base, pd["flags"], R == 2, td, h0)
         rr.pick_threads(min(nmax, 200_000))
@@ -749,7 +790,7 @@ def main() -> None:
         # the reference on the host cores + parity of the same reads (rank 0 of a single-GPU run only)
         if world == 1 and not os.environ.get("BT_BENCH_NO_CPU"):
             try:
-                with tempfile.TemporaryDirectory() as tdn:
+                with tempfile.TemporaryDirectory(dir="/dev/shm" if os.path.isdir("/dev/shm") and os.access("/dev/shm", os.W_OK) else None) as tdn:
                     td = Path(tdn)
                     rr = ReferenceRunner(base, pd["flags"], R == 2, td, arm.host[0])
                     nmax = min(args.cpu_sample if headline else args.cpu_sample // 4, B)
@@ -772,6 +813,11 @@ def main() -> None:
                                             arm.pol, slots=arm.slots, mm_cap=arm.mm_cap)
                         got = gpu_records(f, hh, n, R == 2)
                     res["parity_sample"] = {"units": n, **compare_parity(ref, got, r["gave_up"])}
+                    if headline and name == "n2k1" and not os.environ.get("BT_BENCH_NO_CLI"):
+                        try:
+                            res["cli_e2e"] = cli_e2e(base, arm.host[0], min(B, 2_000_000), td, rr)
+                        except Exception as ex:
+                            res["cli_e2e"] = {"error": str(ex)[-300:]}
             except Exception as ex:  # the reference binary did not travel: report why instead of a number
                 res["cpu_baseline"] = {"value": None, "unit": unit, "cores": host_cores(), "kind": "reference", "sample": f"unavailable: {str(ex)[-300:]}"}
         arm.close()
@@ -816,7 +862,7 @@ def main() -> None:
             "clocks": head.get("clocks"), "e2e": head["e2e"], "gpu_launches": head["gpu_launches"], "roofline": head["roofline"],
             "cpu_baseline": head.get("cpu_baseline"),
         }
-        for k in ("parity_sample", "latency_ms_single_batch"):
+        for k in ("parity_sample", "latency_ms_single_batch", "cli_e2e"):
             if k in head:
                 line[k] = head[k]
         if others:

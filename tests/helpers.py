@@ -427,9 +427,17 @@ class HostEmu:
         so = d / "libbtemu.so"
         srcs = [d / "emu.cpp", ROOT / "bowtie_b200" / "csrc" / "bt_core.cuh", ROOT / "bowtie_b200" / "csrc" / "bt_native.cuh",
                 ORACLE_DIR / "bt_oracle.c"]
-        if not so.exists() or so.stat().st_mtime < max(s.stat().st_mtime for s in srcs):
-            subprocess.run(["g++", "-O2", "-g", "-std=c++17", "-fPIC", "-shared", "-o", str(so), str(d / "emu.cpp"),
-                            str(ORACLE_DIR / "bt_oracle.c")], check=True, capture_output=True)
+        def stale():
+            return not so.exists() or so.stat().st_mtime < max(s.stat().st_mtime for s in srcs)
+        if stale():                                          # several pytest workers may get here at once: one builds, the others wait
+            import fcntl
+            with open(d / ".emu.lock", "w") as lk:
+                fcntl.flock(lk, fcntl.LOCK_EX)
+                if stale():
+                    tmp = d / f".libbtemu.{os.getpid()}.so"
+                    subprocess.run(["g++", "-O2", "-g", "-std=c++17", "-fPIC", "-shared", "-o", str(tmp), str(d / "emu.cpp"),
+                                    str(ORACLE_DIR / "bt_oracle.c")], check=True, capture_output=True)
+                    os.replace(tmp, so)
         L = C.CDLL(str(so))
         L.emu_index_load.restype = C.c_void_p
         L.emu_index_load.argtypes = [C.c_char_p, C.c_int]

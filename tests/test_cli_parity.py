@@ -73,14 +73,25 @@ def cli():
 
 
 def build_shim():
+    """The emulation shim, rebuilt when a source changed; several pytest workers may get here at once: one builds (file lock,
+    atomic rename), the others wait."""
+    import fcntl
     so = SHIM_DIR / "libbowtie_b200.so"
     csrc = ROOT / "bowtie_b200" / "csrc"
     srcs = [ROOT / "tests" / "host_emu" / "abi_shim.cpp", csrc / "bt_core.cuh", ROOT / "oracle" / "bt_oracle.c", csrc / "bt_best.cuh", csrc / "bt_best_prog.h",
-            csrc / "bt_build.h", csrc / "bt_build_sa.cuh", ROOT / "tests" / "host_emu" / "bsa_host.h",
-            ROOT / "include" / "bowtie_b200.h"]
-    if not so.exists() or so.stat().st_mtime < max(s.stat().st_mtime for s in srcs):
+            csrc / "bt_build.h", csrc / "bt_build_sa.cuh", csrc / "bt_io.cuh", csrc / "bt_io_run.h", csrc / "bt_prog.h", csrc / "bt_native.cuh",
+            ROOT / "tests" / "host_emu" / "bsa_host.h", ROOT / "include" / "bowtie_b200.h"]
+
+    def stale():
+        return not so.exists() or so.stat().st_mtime < max(s.stat().st_mtime for s in srcs)
+    if stale():
         SHIM_DIR.mkdir(exist_ok=True)
-        subprocess.run(["g++", "-O2", "-std=c++17", "-fPIC", "-shared", "-o", str(so), str(srcs[0]), str(srcs[2]), "-lz"], check=True, capture_output=True)
+        with open(SHIM_DIR / ".lock", "w") as lk:
+            fcntl.flock(lk, fcntl.LOCK_EX)
+            if stale():
+                tmp = SHIM_DIR / f".libbowtie_b200.{os.getpid()}.so"
+                subprocess.run(["g++", "-O2", "-std=c++17", "-fPIC", "-shared", "-o", str(tmp), str(srcs[0]), str(srcs[2]), "-lz"], check=True, capture_output=True)
+                os.replace(tmp, so)
     return so
 
 
