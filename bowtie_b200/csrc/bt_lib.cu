@@ -752,7 +752,8 @@ static int enqueue_best(bt_context *cx, const bt_policy_t *pol, const bt_read_ba
 	const uint32_t tierLanes[NT] = { BF_THREADS, 32, 1, 1 };                                /* active threads per block */
 	/* first tier: 12 blocks of 64 lanes per SM = 768 resident threads (72 / 80 registers per thread: the register file allows 910 / 819) */
 	static const uint32_t bps0 = env_u32("BT_BEST_BLOCKS", 12);
-	uint32_t tierBlocks[NT] = { (uint32_t)ix->sms * bps0, (uint32_t)ix->sms, (uint32_t)ix->sms, 8 };
+	static const uint32_t t1b = env_u32("BT_BEST_T1_BLOCKS", 1);
+	uint32_t tierBlocks[NT] = { (uint32_t)ix->sms * bps0, (uint32_t)ix->sms * t1b, (uint32_t)ix->sms, 8 };
 	for (int k = 0; k < NT; k++) {
 		const uint32_t need_blocks = (nwork + tierLanes[k] - 1) / tierLanes[k];   /* small batches do not need a full machine of arenas */
 		if (tierBlocks[k] > need_blocks) tierBlocks[k] = need_blocks;
@@ -875,7 +876,10 @@ static int enqueue_align(bt_context *cx, const bt_policy_t *pol, const bt_read_b
 	{ static uint32_t p = env_u32("BT_HEAVY_PERIOD", BT_RARE_PERIOD), t = env_u32("BT_HEAVY_THRESH", BT_RARE_THRESH); P.rare_period = p ? p : 1; P.rare_thresh = t; }
 	set_ws(P, cx->wsh);
 	/* tail pass: full-size blocks, a second (large) budget, so that it ends when its bulk is done — its few stragglers move on */
-	static const uint32_t tail_budget = env_u32("BT_TAIL_BUDGET", 131072);
+	/* (a second budget + an "ultra" pass for what exceeds it was measured on the hg19-sized index: 3.0 M reads/s against 5.1 M reads/s
+	 * without — every restart repeats work and the few single-warp blocks serialise the longest searches; BT_TAIL_BUDGET keeps the
+	 * experiment available, 0 = the tail pass finishes every read) */
+	static const uint32_t tail_budget = env_u32("BT_TAIL_BUDGET", 0);
 	P.sel = cx->heavy_sel; P.budget = tail_budget;
 	bt_search_kernel<<<ix->sms * tail_bps, BT_THREADS, BT_THREADS * BT_SMEM_STRIDE, cx->side>>>(P, cx->ctl + 1);
 	bt_collect_kernel<<<cblocks, 256, 0, cx->side>>>(out->flags, cx->heavy_sel, nwork, cx->ctl + 1, BT_FLAG_BUDGET, cx->ultra_sel, cx->ctl + 2);

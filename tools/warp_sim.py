@@ -18,7 +18,7 @@ period = int(sys.argv[2]) if len(sys.argv) > 2 else 16
 thresh = int(sys.argv[3]) if len(sys.argv) > 3 else 24
 budget = int(sys.argv[4]) if len(sys.argv) > 4 else 8000
 nwarps = int(sys.argv[5]) if len(sys.argv) > 5 else 16
-base, _ = bench.pick_index()
+base = bench.Path(os.environ.get("BT_BENCH_INDEX", str(bench.REF_DIR / "cache" / "benchs_24_256000000_1_10_5_1")))
 genome = bench.load_genome(base)
 codes, quals, offs, seeds, _ = bench.make_reads(genome, n, seed=12345)
 emu = HostEmu()
