@@ -137,6 +137,7 @@ struct BtKParams {
 	uint8_t *stage;               /* 2 * stage_len bytes: writable copy of the read (long reads) */
 	uint32_t R, FCAP, PCAP, stage_len;
 	uint32_t budget;              /* per-read transition budget of this pass (0 = unlimited)  */
+	uint32_t drain_budget;        /* ... once the pass's work queue is empty (0 = the same)    */
 	uint32_t rare_period, rare_thresh;   /* deferral of rare transitions in the thread-per-lane kernel */
 	unsigned long long *stats;    /* [8]: lfex, lf, chase, ftab, offs, backtracks, iters, blockloads */
 };
@@ -1037,13 +1038,13 @@ BT_FN void bt_fast_iter(BtLane &L, const BtKParams &P, const BtScratch &S) {
 #ifndef BT_SWEEP_ROUNDS
 #define BT_SWEEP_ROUNDS 3
 #endif
-BT_FN void bt_rare_iter(BtLane &L, const BtKParams &P, const BtScratch &S) {
+BT_FN void bt_rare_iter(BtLane &L, const BtKParams &P, const BtScratch &S, const uint32_t budget) {
 #if BT_RARE_SWEEP
 #define BT_STEP(state, blk) if (L.pc == (state) && !(L.flags & BT_FLAG_SCRATCH_OVF)) { L.s_iter++; L.nit++; blk(L, P, S); }
 #pragma unroll 1
 	for (int r = 0; r < BT_SWEEP_ROUNDS && BT_IS_RARE_STEP(L.pc); r++) {
 		if (L.flags & BT_FLAG_SCRATCH_OVF) { L.pc = PC_FINISH_READ; break; }
-		if (P.budget && L.nit > P.budget) { L.flags |= BT_FLAG_BUDGET; L.pc = PC_FINISH_READ; break; }   /* heavy read */
+		if (budget && L.nit > budget) { L.flags |= BT_FLAG_BUDGET; L.pc = PC_FINISH_READ; break; }   /* heavy read */
 		BT_STEP(PC_REPORT, bt_blk_report)
 		BT_STEP(PC_REPORT_ROW, bt_blk_report_row)
 		BT_STEP(PC_RESOLVE, bt_blk_resolve)
@@ -1066,9 +1067,10 @@ BT_FN void bt_rare_iter(BtLane &L, const BtKParams &P, const BtScratch &S) {
 #pragma unroll 1
 	for (int k = 0; k < BT_RARE_CHAIN && BT_IS_RARE_STEP(L.pc); k++) {
 		if (L.flags & BT_FLAG_SCRATCH_OVF) { L.pc = PC_FINISH_READ; break; }
-		if (P.budget && L.nit > P.budget) { L.flags |= BT_FLAG_BUDGET; L.pc = PC_FINISH_READ; break; }   /* heavy read */
+		if (budget && L.nit > budget) { L.flags |= BT_FLAG_BUDGET; L.pc = PC_FINISH_READ; break; }   /* heavy read */
 		L.s_iter++; L.nit++;
 		bt_rare_step(L, P, S);
 	}
 #endif
 }
+BT_FN void bt_rare_iter(BtLane &L, const BtKParams &P, const BtScratch &S) { bt_rare_iter(L, P, S, P.budget); }

@@ -53,7 +53,9 @@ __global__ void bt_debug_lf_kernel(BtDevIndex ix, const uint32_t *rows, uint32_t
 	out[5 * (size_t)i + 4] = bt_row_l(b, row);
 }
 
+#ifndef BT_THREADS
 #define BT_THREADS 128
+#endif
 #ifndef BT_MIN_BLOCKS
 #define BT_MIN_BLOCKS 3            /* register cap = 65536 / (128 * BT_MIN_BLOCKS) */
 #endif
@@ -100,6 +102,11 @@ bt_search_kernel(BtKParams P, BtWorkCtl *ctl) {
 	L.nmuts = 0; L.mut0 = L.mut1 = L.mut2 = 0; L.ebwtSel = 0; L.lfk = 0; L.ltop = L.lbot = L.crow = 0; L.flags = 0; L.d = 0; L.qlen = 0;
 	L.rlen = 0; L.rseq = my_stage; L.rqual = my_stage + BT_SMEM_LEN; L.hasN = 1; L.step = 0;
 	const unsigned long long nwork = ctl->nwork;
+	/* Once the work queue is empty a pass only waits for its slowest reads while most lanes idle — with a per-read budget of 8000
+	 * transitions that drain is as long as everything a lane did before it at a million reads per pass.  From the moment a warp
+	 * finds the queue empty its lanes therefore run on the (smaller) drain budget: what exceeds it moves to the tail pass, where it
+	 * overlaps the next batch instead of holding this one's blocks. */
+	uint32_t budget = P.budget;
 #ifndef BT_INNER_FAST
 #define BT_INNER_FAST 1
 #endif
@@ -155,6 +162,7 @@ bt_search_kernel(BtKParams P, BtWorkCtl *ctl) {
 						snap[0] = L.s_lfex; snap[1] = L.s_lf; snap[2] = L.s_chase; snap[3] = L.s_ftab; snap[4] = L.s_offs; snap[5] = L.s_blk;
 					} else L.pc = PC_EXIT;
 				}
+				if (P.drain_budget && budget > P.drain_budget && __ballot_sync(0xffffffffu, want && !got)) budget = P.drain_budget;
 				unsigned gmask = __ballot_sync(0xffffffffu, got && L.rlen <= BT_SMEM_LEN);
 				while (gmask) {
 					const int j = __ffs(gmask) - 1;
@@ -188,7 +196,7 @@ bt_search_kernel(BtKParams P, BtWorkCtl *ctl) {
 				}
 				__syncwarp();
 			}
-			if (BT_IS_RARE_STEP(L.pc)) bt_rare_iter(L, P, S);
+			if (BT_IS_RARE_STEP(L.pc)) bt_rare_iter(L, P, S, budget);
 		}
 #if BT_INNER_FAST
 #pragma unroll 1
@@ -828,7 +836,7 @@ static int enqueue_align(bt_context *cx, const bt_policy_t *pol, const bt_read_b
 	/* the tail pass takes the heavy reads AND the reads whose first-tier scratch overflowed (seedling lists of repeat reads, mostly),
 	 * so it gets the seedling capacity of the worst case; the ultra pass shares its scratch (they run one after the other) */
 	static const uint32_t tail_bps = env_u32("BT_TAIL_BLOCKS", 2);
-	const uint32_t nthreads_h = (uint32_t)ix->sms * tail_bps * BT_THREADS;
+	const uint32_t nthreads_h = (uint32_t)ix->sms * tail_bps * 128;       /* BT_TAIL_BLOCKS counts 128 lanes */
 	if (ensure_ws(cx->wsh, nthreads_h, 6 * maxlen + 8, 16, 4096, stage_len)) return 1;
 	const uint32_t nthreads2 = (uint32_t)ix->sms * 32;
 	uint32_t R2 = maxlen * maxlen + 8; if (R2 > 65000) R2 = 65000;   /* BtFrame::rowbase is 16 bits */
@@ -853,6 +861,7 @@ static int enqueue_align(bt_context *cx, const bt_policy_t *pol, const bt_read_b
 	/* main pass */
 	set_ws(P, cx->ws1);
 	P.budget = main_budget();
+	{ static const uint32_t db = env_u32("BT_DRAIN_BUDGET", 1500); P.drain_budget = db; }
 	{ static uint32_t p = env_u32("BT_RARE_PERIOD", BT_RARE_PERIOD), t = env_u32("BT_RARE_THRESH", BT_RARE_THRESH); P.rare_period = p ? p : 1; P.rare_thresh = t; }
 	bt_ctl_set_kernel<<<1, 1, 0, st>>>(cx->ctl, nwork);
 	bt_ctl_set_kernel<<<1, 1, 0, st>>>(cx->ctl + 1, 0);
@@ -880,8 +889,8 @@ static int enqueue_align(bt_context *cx, const bt_policy_t *pol, const bt_read_b
 	 * without — every restart repeats work and the few single-warp blocks serialise the longest searches; BT_TAIL_BUDGET keeps the
 	 * experiment available, 0 = the tail pass finishes every read) */
 	static const uint32_t tail_budget = env_u32("BT_TAIL_BUDGET", 0);
-	P.sel = cx->heavy_sel; P.budget = tail_budget;
-	bt_search_kernel<<<ix->sms * tail_bps, BT_THREADS, BT_THREADS * BT_SMEM_STRIDE, cx->side>>>(P, cx->ctl + 1);
+	P.sel = cx->heavy_sel; P.budget = tail_budget; P.drain_budget = 0;
+	bt_search_kernel<<<nthreads_h / BT_THREADS, BT_THREADS, BT_THREADS * BT_SMEM_STRIDE, cx->side>>>(P, cx->ctl + 1);
 	bt_collect_kernel<<<cblocks, 256, 0, cx->side>>>(out->flags, cx->heavy_sel, nwork, cx->ctl + 1, BT_FLAG_BUDGET, cx->ultra_sel, cx->ctl + 2);
 	bt_collect_kernel<<<cblocks, 256, 0, cx->side>>>(out->flags, cx->heavy_sel, nwork, cx->ctl + 1, BT_FLAG_SCRATCH_OVF, cx->retry_sel, cx->ctl + 3);
 	/* ultra pass: the handful of searches of 10^5 .. 10^6 sequential transitions.  They take as long as they take (a GPU lane is a
