@@ -742,6 +742,43 @@ def main() -> None:
         dist.all_gather(out, t)
         return sorted(float(o.item()) for o in out)
 
+    lib_comm = {"comm": None, "tried": False}
+
+    def allreduce_counters(c: list[int]):
+        """bt_counters_allreduce (the library's one collective) on a communicator made for it — the unique id travels through
+        torch.distributed; falls back to dist.all_reduce if NCCL cannot be bound that way."""
+        if world == 1:
+            return c, "single rank"
+        import ctypes as C
+        if not lib_comm["tried"]:
+            lib_comm["tried"] = True
+            try:
+                nccl = C.CDLL("libnccl.so.2")
+
+                class UID(C.Structure):
+                    _fields_ = [("internal", C.c_char * 128)]
+                uid = UID()
+                if rank == 0:
+                    assert nccl.ncclGetUniqueId(C.byref(uid)) == 0
+                t = torch.frombuffer(bytearray(bytes(uid)), dtype=torch.uint8).cuda()
+                dist.broadcast(t, 0)
+                C.memmove(C.byref(uid), bytes(t.cpu().numpy()), 128)
+                comm = C.c_void_p()
+                nccl.ncclCommInitRank.argtypes = [C.POINTER(C.c_void_p), C.c_int, UID, C.c_int]
+                assert nccl.ncclCommInitRank(C.byref(comm), world, uid, rank) == 0
+                lib_comm["comm"] = comm
+            except Exception as ex:
+                lib_comm["err"] = str(ex)[-200:]
+        if lib_comm["comm"] is not None:
+            L = bowtie_b200.load_library()
+            arr = (C.c_uint64 * 5)(*c)
+            L.bt_counters_allreduce.argtypes = [C.c_void_p, C.POINTER(C.c_uint64), C.c_void_p]
+            if L.bt_counters_allreduce(lib_comm["comm"], arr, None) == 0:
+                return [int(x) for x in arr], "bt_counters_allreduce (ncclAllReduce over 5 x u64)"
+        t = torch.tensor(c, dtype=torch.int64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.SUM)
+        return [int(x) for x in t.tolist()], "torch.distributed all_reduce (fallback: " + lib_comm.get("err", "library call failed") + ")"
+
     peaks = {}
     try:
         peaks = json.loads((ROOT / "MEASURED_PEAKS.json").read_text())
@@ -760,9 +797,8 @@ def main() -> None:
         st = m["stats"]
         alg = st.algorithmic_bytes / steps
         achieved = alg / (m["ms"] / steps / 1e3) / 1e9
-        ctr = torch.tensor([m["aligned"], B - m["aligned"], 0, m["aligned"] * R, m["aligned"] * R if R == 2 else 0], dtype=torch.int64, device="cuda")   # counters of the last step (hit.h:169-175)
-        if world > 1:
-            dist.all_reduce(ctr, op=dist.ReduceOp.SUM)                                                  # the path's only collective
+        ctr = [m["aligned"], B - m["aligned"], 0, m["aligned"] * R if R == 1 else 0, m["aligned"] * R if R == 2 else 0]   # counters of the last step (hit.h:169-175)
+        ctr, ctr_how = allreduce_counters(ctr)                                                          # the path's only collective
         res = {"metric": pd["metric"], "value": value, "unit": unit, "ms_per_step": ms_max / steps, "steps": steps, "warmup": warmup,
                "workload": workload_name(pd, idx_name), "units_per_step_per_gpu": B, "batches_in_flight": NS,
                "e2e": {"value": B * steps * world / e2e_max, "unit": unit, "h2d_bytes_per_step": arm.h2d, "d2h_bytes_per_step": arm.d2h},
@@ -771,7 +807,7 @@ def main() -> None:
                             "side_fetches_per_unit": st.side_fetches / (B * steps), "block_loads_per_unit": st.block_loads / (B * steps),
                             "algorithmic_bytes_per_unit": alg / B},
                "aligned_frac_last_step": m["aligned"] / B, "aligned_frac_last_e2e_step": m["e2e_aligned"] / B, "overflow_flags": m["flags_bad"],
-               "counters_allreduced": [int(x) for x in ctr.tolist()],
+               "counters_allreduced": [int(x) for x in ctr], "counters_collective": ctr_how,
                "rank_ms_per_step": {"min": m["ms_ranks"][0] / steps, "median": m["ms_ranks"][len(m["ms_ranks"]) // 2] / steps, "max": ms_max / steps},
                # per step: ctl_set x4, main search, collect, tail search, collect x2, ultra search, collect, overflow search
                # (best-first / paired: ctl_set x4, 4 arena tiers, 3 collects)

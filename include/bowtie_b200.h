@@ -195,6 +195,11 @@ void bt_io_free(bt_io_t *io);
 int  bt_io_parse_fastq(bt_io_t *io, const char *text, uint64_t nbytes, uint32_t global_seed, uint32_t max_reads, uint32_t *nreads, uint64_t *consumed, int *irregular);
 int  bt_io_align_format(bt_io_t *io, const bt_policy_t *pol, const bt_io_format_t *fmt, const char **out_text, uint64_t *out_bytes, uint64_t counters[4]);
 
+/* The path's only collective (reads shard across GPUs with no data-path exchange): sums the five summary counters of hit.h:169-175
+ * { aligned, unaligned, maxed, reported, reportedPaired } over the ranks of `nccl_comm` (an ncclComm_t; NCCL is bound at call
+ * time) on the calling thread's current device.  In place; returns when `counters` holds the sums. */
+int  bt_counters_allreduce(void *nccl_comm, uint64_t counters[5], void *stream);
+
 /* LF primitives on the device layout, for parity tests: computes, for each row, mapLFEx-style
  * (fchr[c] + occ(c,row)) for c = 0..3 and rowL.  rows/out are host arrays; out has 5 words per row. */
 int  bt_debug_lf(bt_index_t *ix, int mirror, const uint32_t *rows, uint32_t n, uint32_t *out);

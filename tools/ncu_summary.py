@@ -26,7 +26,8 @@ for i, h in enumerate(hdr):
 json.dump(m, open(outp + ".metrics.json", "w"), indent=1)
 print(json.dumps(m, indent=1))
 if len(sys.argv) > 5:
-    so, sym, regions = sys.argv[3], sys.argv[4], eval(open(sys.argv[5]).read())
+    import os
+    so, sym, regions = os.path.abspath(sys.argv[3]), sys.argv[4], eval(open(sys.argv[5]).read())
     td = tempfile.mkdtemp()
     subprocess.run(f"cd {td} && cuobjdump -xelf all {so} >/dev/null && for f in *.cubin; do nvdisasm -g -c $f > $f.txt 2>/dev/null; done", shell=True, check=True)
     lines = None
