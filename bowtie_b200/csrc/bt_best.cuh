@@ -107,6 +107,10 @@ struct BfKParams {
 	const uint8_t *seq, *qual; const uint64_t *roff; const uint32_t *seeds; const uint32_t *sel; uint32_t nwork;
 	uint32_t *found, *flags, *hits; uint32_t slots, mm_cap, rec_words;
 	uint32_t *arena; uint32_t arenaWords;     /* per lane */
+	/* The arenas of a tier are a pool shared by every context of the index: a block claims one pool entry (`lanes` arenas) for its
+	 * lifetime by setting a bit of poolMask, so the memory is sized by how many blocks can be resident, not by how many batches are
+	 * in flight. */
+	unsigned *poolMask; uint32_t poolBlocks;
 	unsigned long long *stats;
 };
 

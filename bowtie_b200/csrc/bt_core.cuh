@@ -92,6 +92,7 @@ struct BtPolicy {
 #define BT_FLAG_HITS_OVF  8u   /* more reportable hits than slots      */
 #define BT_FLAG_MM_OVF   16u   /* more mismatches than the record holds */
 #define BT_FLAG_BUDGET  32u   /* (internal) iteration budget of the main pass exceeded: moved to the heavy pass */
+#define BT_FLAG_PREEMPT 64u   /* (internal, transient) the read leaves this pass with its state: checkpointed into a slot, resumed by the next slice */
 #define BT_FLAG_SCRATCH_OVF 7u
 #define BT_FLAG_RETRY (BT_FLAG_SCRATCH_OVF | BT_FLAG_BUDGET)
 
@@ -139,6 +140,16 @@ struct BtKParams {
 	uint32_t budget;              /* per-read transition budget of this pass (0 = unlimited)  */
 	uint32_t drain_budget;        /* ... once the pass's work queue is empty (0 = the same)    */
 	uint32_t rare_period, rare_thresh;   /* deferral of rare transitions in the thread-per-lane kernel */
+	/* Checkpoint slots (bt_ctxq.cuh): a read that exceeds its pass's budget (or fills its seedling list) is not re-run, it is
+	 * suspended — packed lane state, its copy of the read and its live scratch move into a slot — and the next, denser pass resumes
+	 * it.  slot_ctx == NULL: no slots, such reads are flagged and re-run from scratch by a later pass. */
+	uint32_t *slot_ctx;           /* BT_CTX_WORDS x nslot (word-major)                        */
+	uint4 *slot_rows; uint8_t *slot_elims; BtFrame *slot_frames; uint64_t *slot_partials; uint8_t *slot_stage;
+	uint32_t nslot, slot_R, slot_FCAP, slot_PCAP, slot_stage_len;
+	uint32_t resume;              /* 1: the work items are slot ids to resume; 0: read ids     */
+	unsigned long long *slice_count;   /* main pass: slots handed out so far (may run past nslot: those reads are flagged for a re-run);
+	                                    * a slice: length of slice_out                             */
+	uint32_t *slice_out;          /* a slice: the slots it suspended again = the next slice's work list */
 	unsigned long long *stats;    /* [8]: lfex, lf, chase, ftab, offs, backtracks, iters, blockloads */
 };
 
@@ -1044,7 +1055,11 @@ BT_FN void bt_rare_iter(BtLane &L, const BtKParams &P, const BtScratch &S, const
 #pragma unroll 1
 	for (int r = 0; r < BT_SWEEP_ROUNDS && BT_IS_RARE_STEP(L.pc); r++) {
 		if (L.flags & BT_FLAG_SCRATCH_OVF) { L.pc = PC_FINISH_READ; break; }
-		if (budget && L.nit > budget) { L.flags |= BT_FLAG_BUDGET; L.pc = PC_FINISH_READ; break; }   /* heavy read */
+		if ((budget && L.nit > budget) || (P.slot_ctx && !P.resume && L.npart >= P.PCAP)) {                  /* heavy read, or its seedling list is full */
+			if (P.slot_ctx) L.flags |= BT_FLAG_PREEMPT;                                                    /* suspended as it is: the state stays put */
+			else { L.flags |= BT_FLAG_BUDGET; L.pc = PC_FINISH_READ; }
+			break;
+		}
 		BT_STEP(PC_REPORT, bt_blk_report)
 		BT_STEP(PC_REPORT_ROW, bt_blk_report_row)
 		BT_STEP(PC_RESOLVE, bt_blk_resolve)
@@ -1063,14 +1078,21 @@ BT_FN void bt_rare_iter(BtLane &L, const BtKParams &P, const BtScratch &S, const
 		BT_STEP(PC_POS, bt_blk_pos)
 	}
 #undef BT_STEP
+	/* a report in the last round may have filled the seedling list and the lane left for a fast state: the next position could report again */
+	if (P.slot_ctx && !P.resume && L.npart >= P.PCAP && L.pc != PC_FINISH_READ) L.flags |= BT_FLAG_PREEMPT;
 #else
 #pragma unroll 1
 	for (int k = 0; k < BT_RARE_CHAIN && BT_IS_RARE_STEP(L.pc); k++) {
 		if (L.flags & BT_FLAG_SCRATCH_OVF) { L.pc = PC_FINISH_READ; break; }
-		if (budget && L.nit > budget) { L.flags |= BT_FLAG_BUDGET; L.pc = PC_FINISH_READ; break; }   /* heavy read */
+		if ((budget && L.nit > budget) || (P.slot_ctx && !P.resume && L.npart >= P.PCAP)) {
+			if (P.slot_ctx) L.flags |= BT_FLAG_PREEMPT;
+			else { L.flags |= BT_FLAG_BUDGET; L.pc = PC_FINISH_READ; }
+			break;
+		}
 		L.s_iter++; L.nit++;
 		bt_rare_step(L, P, S);
 	}
+	if (P.slot_ctx && !P.resume && L.npart >= P.PCAP && L.pc != PC_FINISH_READ) L.flags |= BT_FLAG_PREEMPT;
 #endif
 }
 BT_FN void bt_rare_iter(BtLane &L, const BtKParams &P, const BtScratch &S) { bt_rare_iter(L, P, S, P.budget); }

@@ -69,3 +69,44 @@ BT_FN void bt_ctx_load(BtLane &L, const uint32_t *ctx, uint32_t nctx, uint32_t i
 	L.viewComp = !L.fw;
 }
 #undef CW
+
+/* ---- checkpoint slots ---------------------------------------------------------------------------------------------------------
+ * A slot is everything a suspended read owns: the packed lane state above (word-major in P.slot_ctx), its writable copy of the read
+ * (mutated by seedlings) and a private scratch set (rows / elims / frames / seedlings) with the capacities of the later passes.
+ * The main pass suspends a read by copying what is live of its per-thread scratch into a fresh slot; the slices that follow work in
+ * the slot's own scratch, so suspending again costs only the 39 state words. */
+BT_FN void bt_slot_scratch(const BtKParams &P, uint32_t slot, BtScratch &S) {
+	S.rows = P.slot_rows + (size_t)slot * P.slot_R * 2;
+	S.elims = P.slot_elims + (size_t)slot * P.slot_R;
+	S.frames = P.slot_frames + (size_t)slot * P.slot_FCAP;
+	S.partials = P.slot_partials + (size_t)slot * P.slot_PCAP;
+}
+
+/* First suspension (main pass): per-thread scratch S -> slot.  Live rows are [0, rowbase + qlen - rowd0) of the current frame's
+ * allocation (bt_blk_frame_enter reserved them), live frames [0, stackDepth] (BTLOOP writes mm_pos / mm_refc of the frame it is
+ * about to push before reporting through it), live seedlings [0, npart). */
+BT_FN void bt_slot_save_new(const BtLane &L, const BtKParams &P, const BtScratch &S, uint32_t slot) {
+	BtScratch D; bt_slot_scratch(P, slot, D);
+	uint32_t nrows = L.rowbase + (L.qlen > L.rowd0 ? L.qlen - L.rowd0 : 0u);
+	if (nrows > P.R) nrows = P.R;
+	if (nrows > P.slot_R) nrows = P.slot_R;
+	for (uint32_t i = 0; i < 2 * nrows; i++) D.rows[i] = S.rows[i];
+	for (uint32_t i = 0; i < nrows; i++) D.elims[i] = S.elims[i];
+	uint32_t nfr = L.stackDepth + 1; if (nfr > P.FCAP) nfr = P.FCAP; if (nfr > P.slot_FCAP) nfr = P.slot_FCAP;
+	for (uint32_t i = 0; i < nfr; i++) D.frames[i] = S.frames[i];
+	uint32_t np = L.npart; if (np > P.PCAP) np = P.PCAP; if (np > P.slot_PCAP) np = P.slot_PCAP;
+	for (uint32_t i = 0; i < np; i++) D.partials[i] = S.partials[i];
+	uint8_t *st = P.slot_stage + (size_t)slot * 2 * P.slot_stage_len;
+	for (uint32_t i = 0; i < L.rlen; i++) { st[i] = L.rseq[i]; st[P.slot_stage_len + i] = L.rqual[i]; }
+	bt_ctx_store(L, P.slot_ctx, P.nslot, slot);
+}
+
+/* Resume: the lane continues the slot's read in the slot's scratch. */
+BT_FN void bt_slot_resume(BtLane &L, const BtKParams &P, BtScratch &S, uint32_t slot) {
+	bt_ctx_load(L, P.slot_ctx, P.nslot, slot);
+	bt_slot_scratch(P, slot, S);
+	L.rseq = P.slot_stage + (size_t)slot * 2 * P.slot_stage_len; L.rqual = L.rseq + P.slot_stage_len;
+	L.qualThresh = P.pol.mode == 0 ? 0xffffffffu : P.pol.qualThresh;
+	L.maxBts = P.pol.mode == 0 ? 0xffffffffu : P.pol.maxBts;
+	L.maqPenalty = P.pol.mode == 0 ? 1u : (uint32_t)P.pol.maqRound;
+}

@@ -92,16 +92,20 @@ bt_search_kernel(BtKParams P, BtWorkCtl *ctl) {
 	const uint32_t lane = threadIdx.x & 31;
 	uint8_t *const my_stage = bt_smem + (size_t)threadIdx.x * BT_SMEM_STRIDE;
 	BtScratch S;
-	S.rows = P.rows + (size_t)tid * P.R * 2;
-	S.elims = P.elims + (size_t)tid * P.R;
-	S.frames = P.frames + (size_t)tid * P.FCAP;
-	S.partials = P.partials + (size_t)tid * P.PCAP;
+	if (!P.resume) {
+		S.rows = P.rows + (size_t)tid * P.R * 2;
+		S.elims = P.elims + (size_t)tid * P.R;
+		S.frames = P.frames + (size_t)tid * P.FCAP;
+		S.partials = P.partials + (size_t)tid * P.PCAP;
+	} else S.rows = nullptr, S.elims = nullptr, S.frames = nullptr, S.partials = nullptr;      /* a slice works in the slot's scratch */
+	uint32_t my_slot = 0;
 	BtLane L;
 	L.pc = PC_NEXT_READ;
 	L.s_lfex = L.s_lf = L.s_chase = L.s_ftab = L.s_offs = L.s_bt = L.s_iter = L.s_blk = 0;
 	L.nmuts = 0; L.mut0 = L.mut1 = L.mut2 = 0; L.ebwtSel = 0; L.lfk = 0; L.ltop = L.lbot = L.crow = 0; L.flags = 0; L.d = 0; L.qlen = 0;
 	L.rlen = 0; L.rseq = my_stage; L.rqual = my_stage + BT_SMEM_LEN; L.hasN = 1; L.step = 0;
-	const unsigned long long nwork = ctl->nwork;
+	unsigned long long nwork = ctl->nwork;
+	if (P.resume && nwork > P.nslot) nwork = P.nslot;                 /* the main pass counts past the last slot (those reads are re-run) */
 	/* Once the work queue is empty a pass only waits for its slowest reads while most lanes idle — with a per-read budget of 8000
 	 * transitions that drain is as long as everything a lane did before it at a million reads per pass.  From the moment a warp
 	 * finds the queue empty its lanes therefore run on the (smaller) drain budget: what exceeds it moves to the tail pass, where it
@@ -149,20 +153,24 @@ bt_search_kernel(BtKParams P, BtWorkCtl *ctl) {
 				unsigned long long base = 0;
 				if ((int)lane == leader) base = atomicAdd(&ctl->next, (unsigned long long)__popc(wmask));
 				base = __shfl_sync(0xffffffffu, base, leader);
-				bool got = false;
+				bool got = false, took = false;
 				unsigned long long ro = 0;
 				if (want) {
 					unsigned long long w = base + (unsigned long long)__popc(wmask & ((1u << lane) - 1u));
 					if (w < nwork) {
 						const uint32_t rid = P.sel ? P.sel[w] : (uint32_t)w;
-						bt_begin_read(L, P, rid);
-						ro = P.roff[rid];
-						got = true;
+						took = true;
+						if (P.resume) { my_slot = rid; bt_slot_resume(L, P, S, my_slot); }     /* the item is a slot: continue its read where it stopped */
+						else {
+							bt_begin_read(L, P, rid);
+							ro = P.roff[rid];
+							got = true;
+						}
 						uint32_t *snap = reinterpret_cast<uint32_t *>(my_stage + BT_SMEM_SNAP);
 						snap[0] = L.s_lfex; snap[1] = L.s_lf; snap[2] = L.s_chase; snap[3] = L.s_ftab; snap[4] = L.s_offs; snap[5] = L.s_blk;
 					} else L.pc = PC_EXIT;
 				}
-				if (P.drain_budget && budget > P.drain_budget && __ballot_sync(0xffffffffu, want && !got)) budget = P.drain_budget;
+				if (P.drain_budget && budget > P.drain_budget && __ballot_sync(0xffffffffu, want && !took)) budget = P.drain_budget;
 				unsigned gmask = __ballot_sync(0xffffffffu, got && L.rlen <= BT_SMEM_LEN);
 				while (gmask) {
 					const int j = __ffs(gmask) - 1;
@@ -197,6 +205,21 @@ bt_search_kernel(BtKParams P, BtWorkCtl *ctl) {
 				__syncwarp();
 			}
 			if (BT_IS_RARE_STEP(L.pc)) bt_rare_iter(L, P, S, budget);
+			if (L.flags & BT_FLAG_PREEMPT) {
+				/* over this pass's budget (or out of seedling space): suspend the read into a checkpoint slot; the next slice resumes it */
+				L.flags &= ~BT_FLAG_PREEMPT;
+				bool kept = true;
+				if (P.resume) {
+					bt_ctx_store(L, P.slot_ctx, P.nslot, my_slot);              /* its scratch and its read are in the slot already */
+					P.slice_out[atomicAdd(P.slice_count, 1ull)] = my_slot;
+				} else {
+					const unsigned long long p = atomicAdd(P.slice_count, 1ull);
+					if (p < P.nslot) { bt_slot_save_new(L, P, S, (uint32_t)p); P.flags[L.rid] = 0; P.found[L.rid] = 0; }
+					else kept = false;
+				}
+				if (kept) L.pc = PC_NEXT_READ;
+				else { L.flags |= BT_FLAG_BUDGET; L.pc = PC_FINISH_READ; }      /* no slot left: re-run from scratch by the overflow pass */
+			}
 		}
 #if BT_INNER_FAST
 #pragma unroll 1
@@ -377,13 +400,37 @@ static size_t bt_q_smem(uint32_t nctx) { return sizeof(BtQueues) + (size_t)nctx 
 template <bool PAIRED>
 __global__ void __launch_bounds__(BF_THREADS)
 bt_best_kernel(const __grid_constant__ BfKParams P, BtWorkCtl *ctl, uint32_t lanes) {
-	if (threadIdx.x >= lanes) return;
-	const uint32_t tid = blockIdx.x * lanes + threadIdx.x;
+	const unsigned long long nwork = ctl->nwork;
+	/* claim one entry of the tier's arena pool for this block: first clear bit of the mask, starting at a block-dependent word */
+	__shared__ uint32_t s_blk;
+	if (threadIdx.x == 0) {
+		const uint32_t nw = (P.poolBlocks + 31) / 32;
+		uint32_t w = blockIdx.x % nw, got = 0xffffffffu, sweeps = 0, seen = 0;
+		if (*(volatile unsigned long long *)&ctl->next >= nwork) got = 0xfffffffeu;    /* nothing left (the later tiers are usually empty): no arena needed */
+		while (got == 0xffffffffu) {
+			const unsigned valid = (w == nw - 1 && (P.poolBlocks & 31)) ? ((1u << (P.poolBlocks & 31)) - 1u) : 0xffffffffu;
+			const unsigned fr = ~atomicOr(P.poolMask + w, 0u) & valid;
+			if (fr) {
+				const unsigned b = (unsigned)__ffs(fr) - 1u;
+				if (!(atomicOr(P.poolMask + w, 1u << b) & (1u << b))) got = w * 32 + b;
+			} else {
+				w = (w + 1) % nw;
+				if (++seen == nw) {                                                 /* every entry is held by a resident block: wait for one to finish */
+					seen = 0; __nanosleep(20000);
+					if (++sweeps > 3000000u) __trap();                                 /* a minute: something is wrong — fail loudly rather than hang */
+				}
+			}
+		}
+		s_blk = got;
+	}
+	__syncthreads();
+	const uint32_t blk = s_blk;
+	if (blk == 0xfffffffeu) return;
+	if (threadIdx.x < lanes) {
 	BfCtx X;
 	X.P = &P;
-	X.A = P.arena + (size_t)tid * P.arenaWords; X.acap = P.arenaWords;
+	X.A = P.arena + ((size_t)blk * lanes + threadIdx.x) * P.arenaWords; X.acap = P.arenaWords;
 	X.s_lfex = X.s_lf = X.s_chase = X.s_ftab = X.s_offs = X.s_bt = 0;
-	const unsigned long long nwork = ctl->nwork;
 	for (;;) {
 		const unsigned long long w = atomicAdd(&ctl->next, 1ull);
 		if (w >= nwork) break;
@@ -411,6 +458,9 @@ bt_best_kernel(const __grid_constant__ BfKParams P, BtWorkCtl *ctl, uint32_t lan
 	if (X.s_ftab) atomicAdd(&P.stats[3], (unsigned long long)X.s_ftab);
 	if (X.s_offs) atomicAdd(&P.stats[4], (unsigned long long)X.s_offs);
 	if (X.s_bt) atomicAdd(&P.stats[5], (unsigned long long)X.s_bt);
+	}
+	__syncthreads();                                                         /* every lane is done with its arena */
+	if (threadIdx.x == 0) atomicAnd(P.poolMask + (blk >> 5), ~(1u << (blk & 31)));
 }
 
 /* Appends to sel_out the reads (of the first n work items of sel_in / the identity) whose flags intersect `mask`;
@@ -426,6 +476,11 @@ __global__ void bt_collect_kernel(const uint32_t *flags, const uint32_t *sel_in,
 	}
 }
 __global__ void bt_ctl_set_kernel(BtWorkCtl *ctl, unsigned long long nwork) { ctl->next = 0; ctl->nwork = nwork; }
+/* resets a context's whole array of work lists: list 0 holds `nwork` items, the others are empty */
+#define BT_CTL_WORDS 12
+__global__ void bt_ctl_set_all_kernel(BtWorkCtl *ctl, uint32_t n, unsigned long long nwork) {
+	if (threadIdx.x < n) { ctl[threadIdx.x].next = 0; ctl[threadIdx.x].nwork = threadIdx.x == 0 ? nwork : 0; }
+}
 
 /* ------------------------------------------------------------------------------------------- */
 /* host side                                                                                    */
@@ -458,6 +513,7 @@ struct Workspace {
 	void release() { cudaFree(rows); cudaFree(elims); cudaFree(frames); cudaFree(partials); cudaFree(stage); rows = nullptr; elims = nullptr; frames = nullptr; partials = nullptr; stage = nullptr; nthreads = 0; }
 };
 
+struct ArenaPool { uint32_t *mem = nullptr; unsigned *mask = nullptr; uint32_t blocks = 0, lanes = 0, words = 0; };
 struct bt_context;
 struct bt_index {
 	int device = 0;
@@ -468,6 +524,7 @@ struct bt_index {
 	int sms = 0, blocks_per_sm = 0;
 	bt_context *def = nullptr;   /* context behind bt_align_batch / bt_align_batch_device */
 	std::string base;            /* index basename: the bit-pair reference (X.3.ebwt / X.4.ebwt) is loaded on the first paired-end call */
+	ArenaPool bf_pool[4];        /* best-first path: the arena tiers, shared by all contexts (entries are claimed per resident block) */
 	bool ref_loaded = false; BtDevRef dref; uint32_t *d_refwords[4] = { nullptr, nullptr, nullptr, nullptr }; uint8_t *d_refbuf = nullptr;
 	std::mutex mu;
 };
@@ -478,8 +535,8 @@ struct bt_index {
 struct bt_context {
 	bt_index *ix = nullptr;
 	Workspace ws1, wsh, ws2;     /* main pass / heavy-read pass / scratch-overflow pass */
-	uint32_t *arena[4] = { nullptr, nullptr, nullptr, nullptr }; size_t arena_words[4] = { 0, 0, 0, 0 };   /* best-first path: four arena tiers */
-	BtWorkCtl *ctl = nullptr;    /* [4] */
+	BtWorkCtl *ctl = nullptr;    /* [BT_CTL_WORDS]: main pass, slices, overflow pass (best-first path: its four tiers) */
+	Workspace wsl; uint32_t *slot_ctx = nullptr, *slice_list[2] = { nullptr, nullptr }; uint32_t slot_cap = 0;   /* checkpoint slots (bt_ctxq.cuh) */
 	uint32_t *heavy_sel = nullptr, *ultra_sel = nullptr, *retry_sel = nullptr; uint32_t retry_cap = 0;
 	cudaStream_t side = nullptr; /* the heavy and overflow passes run here, overlapping the next batch's main pass */
 	cudaEvent_t ev_main = nullptr, ev_tail = nullptr;
@@ -593,8 +650,8 @@ extern "C" void bt_context_free(bt_context_t *cx) {
 	if (cx->side) { cudaStreamSynchronize(cx->side); cudaStreamDestroy(cx->side); }
 	if (cx->ev_main) cudaEventDestroy(cx->ev_main);
 	if (cx->ev_tail) cudaEventDestroy(cx->ev_tail);
-	cx->ws1.release(); cx->wsh.release(); cx->ws2.release();
-	for (int k = 0; k < 4; k++) cudaFree(cx->arena[k]);
+	cx->ws1.release(); cx->wsh.release(); cx->ws2.release(); cx->wsl.release();
+	cudaFree(cx->slot_ctx); cudaFree(cx->slice_list[0]); cudaFree(cx->slice_list[1]);
 	cudaFree(cx->ctl); cudaFree(cx->retry_sel); cudaFree(cx->heavy_sel); cudaFree(cx->ultra_sel);
 	cudaFree(cx->d_seq); cudaFree(cx->d_qual); cudaFree(cx->d_offs); cudaFree(cx->d_seeds); cudaFree(cx->d_sel);
 	cudaFree(cx->d_found); cudaFree(cx->d_flags); cudaFree(cx->d_hits);
@@ -607,7 +664,7 @@ extern "C" int bt_context_create(bt_index_t *ix, bt_context_t **out) {
 	CUDA_TRY(cudaSetDevice(ix->device));
 	bt_context *cx = new bt_context();
 	cx->ix = ix;
-	if (cudaMalloc((void **)&cx->ctl, 4 * sizeof(BtWorkCtl)) != cudaSuccess || cudaStreamCreateWithFlags(&cx->side, cudaStreamNonBlocking) != cudaSuccess ||
+	if (cudaMalloc((void **)&cx->ctl, BT_CTL_WORDS * sizeof(BtWorkCtl)) != cudaSuccess || cudaStreamCreateWithFlags(&cx->side, cudaStreamNonBlocking) != cudaSuccess ||
 	    cudaEventCreateWithFlags(&cx->ev_main, cudaEventDisableTiming) != cudaSuccess || cudaEventCreateWithFlags(&cx->ev_tail, cudaEventDisableTiming) != cudaSuccess) {
 		bt_context_free(cx); return fail("bt_context_create: CUDA resource allocation failed");
 	}
@@ -630,6 +687,7 @@ extern "C" void bt_index_free(bt_index_t *ix) {
 	}
 	if (ix->def) bt_context_free(ix->def);
 	for (int k = 0; k < 4; k++) cudaFree(ix->d_refwords[k]);
+	for (int k = 0; k < 4; k++) { cudaFree(ix->bf_pool[k].mem); cudaFree(ix->bf_pool[k].mask); }
 	cudaFree(ix->d_refbuf);
 	cudaFree(ix->stats);
 	delete ix;
@@ -742,35 +800,55 @@ static bool main_kernel_is_queue() {
 }
 
 
-/* The best-first path (bt_best.cuh).  Four passes with growing per-read arenas: every read with 64 KB on the caller's
- * stream (148 x 12 x 64 lanes); the reads that exhausted it with 1 MB (148 x 32 lanes), then 16 MB (148 lanes), then 256 MB
- * (8 lanes; the reference's own ceiling is 64 MB of chunked pools per thread) on the side stream.
- * About 7.5 (pairs: 11) + 5 + 2.5 + 2 GB per context for full batches. */
+/* Grows tier k's arena pool of the index to `blocks` entries of `lanes` x `words` (caller holds ix->mu).  Entries are claimed by resident
+ * blocks (bt_best_kernel), so a pool may be smaller than what is in flight — blocks then wait for an entry — but it must not be
+ * freed while any kernel may hold one: growing synchronises the device first. */
+static int ensure_pool(bt_index *ix, int k, uint32_t blocks, uint32_t lanes, uint32_t words) {
+	ArenaPool &p = ix->bf_pool[k];
+	if (p.mem && p.blocks >= blocks && p.lanes == lanes && p.words == words) return 0;
+	if (p.mem) { CUDA_TRY(cudaDeviceSynchronize()); if (blocks < p.blocks) blocks = p.blocks; }
+	cudaFree(p.mem); cudaFree(p.mask); p.mem = nullptr; p.mask = nullptr; p.blocks = 0;
+	CUDA_TRY(cudaMalloc((void **)&p.mem, (size_t)blocks * lanes * words * 4));
+	const size_t mw = (blocks + 31) / 32;
+	CUDA_TRY(cudaMalloc((void **)&p.mask, mw * 4));
+	CUDA_TRY(cudaMemset(p.mask, 0, mw * 4));
+	p.blocks = blocks; p.lanes = lanes; p.words = words;
+	return 0;
+}
+
+/* The best-first path (bt_best.cuh).  Four passes with growing per-read arenas: every read with 128 KB (pairs: 192 KB) on the caller's
+ * stream; the reads that exhausted it with 1 MB (32 lanes per block), then 16 MB (one lane per block), then 256 MB (8 blocks; the
+ * reference's own ceiling is 64 MB of chunked pools per thread) on the side stream.  The arenas of a tier are ONE pool per index, sized
+ * by the number of blocks that can be resident (occupancy x SMs for the first tier), whatever the number of batches in flight:
+ * about 25 + 19 + 2.5 + 2 GB for full-size batches, a few MB for small ones. */
 static int enqueue_best(bt_context *cx, const bt_policy_t *pol, const bt_read_batch_t *in, bt_hit_batch_t *out, uint32_t maxlen, cudaStream_t st) {
 	bt_index_t *ix = cx->ix;
 	if (pol->paired && (in->nreads & 1)) return fail("bt_align (paired-end): nreads must be even (mates are adjacent reads)");
 	const uint32_t nwork = in->sel ? in->nsel : (pol->paired ? in->nreads / 2 : in->nreads);
 	if (nwork == 0) return 0;
 	if (pol->paired && ensure_ref(ix)) return 1;
-	static const uint32_t kw0 = env_u32("BT_BEST_ARENA_KW", 16);
+	static const uint32_t kw0 = env_u32("BT_BEST_ARENA_KW", 32);
 	enum { NT = 4 };
-	/* 64 KB (pairs: 96 KB), 1 MB, 16 MB, 256 MB per read.  Measured high-water marks on the bench workloads (host emulation,
-	 * profiles/README.md): -n 2 --best p99 35 KB, p99.9 282 KB; paired -n 3 p95 60 KB, p99 113 KB, p99.9 326 KB */
-	const uint32_t tierWords[NT] = { (pol->paired ? kw0 + kw0 / 2 : kw0) << 10, 256u << 10, 4096u << 10, 65536u << 10 };
+	/* 192 KB (sized for pairs; unpaired reads use the same pool), 1 MB, 16 MB, 256 MB per read.  Measured high-water marks on the bench
+	 * workloads (host emulation, profiles/README.md): -n 2 --best p99 35 KB, p99.9 282 KB; paired -n 3 p95 60 KB, p99 113 KB, p99.9 326 KB */
+	const uint32_t tierWords[NT] = { (kw0 + kw0 / 2) << 10, 256u << 10, 4096u << 10, 65536u << 10 };
 	const uint32_t tierLanes[NT] = { BF_THREADS, 32, 1, 1 };                                /* active threads per block */
 	/* first tier: 12 blocks of 64 lanes per SM = 768 resident threads (72 / 80 registers per thread: the register file allows 910 / 819) */
 	static const uint32_t bps0 = env_u32("BT_BEST_BLOCKS", 12);
-	static const uint32_t t1b = env_u32("BT_BEST_T1_BLOCKS", 1);
+	static const uint32_t t1b = env_u32("BT_BEST_T1_BLOCKS", 4);
+	static int occ = 0;
+	if (!occ) {
+		int a = 0, b = 0;
+		CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&a, bt_best_kernel<false>, BF_THREADS, 0));
+		CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&b, bt_best_kernel<true>, BF_THREADS, 0));
+		occ = a > b ? a : b; if (occ < 1) occ = 1;
+	}
 	uint32_t tierBlocks[NT] = { (uint32_t)ix->sms * bps0, (uint32_t)ix->sms * t1b, (uint32_t)ix->sms, 8 };
+	uint32_t poolBlocks[NT] = { (uint32_t)ix->sms * (uint32_t)occ, (uint32_t)ix->sms * t1b, (uint32_t)ix->sms, 8 };
 	for (int k = 0; k < NT; k++) {
 		const uint32_t need_blocks = (nwork + tierLanes[k] - 1) / tierLanes[k];   /* small batches do not need a full machine of arenas */
 		if (tierBlocks[k] > need_blocks) tierBlocks[k] = need_blocks;
-		const size_t need = (size_t)tierBlocks[k] * tierLanes[k] * tierWords[k];
-		if (cx->arena_words[k] < need) {
-			cudaFree(cx->arena[k]); cx->arena[k] = nullptr; cx->arena_words[k] = 0;
-			CUDA_TRY(cudaMalloc((void **)&cx->arena[k], need * 4));
-			cx->arena_words[k] = need;
-		}
+		if (poolBlocks[k] > need_blocks) poolBlocks[k] = need_blocks;
 	}
 	if (cx->retry_cap < nwork) {
 		cudaFree(cx->retry_sel); cudaFree(cx->heavy_sel); cudaFree(cx->ultra_sel); cx->retry_sel = cx->heavy_sel = cx->ultra_sel = nullptr; cx->retry_cap = 0;
@@ -790,15 +868,17 @@ static int enqueue_best(bt_context *cx, const bt_policy_t *pol, const bt_read_ba
 	P.stats = ix->stats;
 	(void)maxlen;
 	const uint32_t cblocks = (nwork + 255) / 256;
+	/* pools and launches under the index lock: a pool that another thread grows must not be handed to a kernel here meanwhile */
+	std::lock_guard<std::mutex> g(ix->mu);
+	for (int k = 0; k < NT; k++) if (ensure_pool(ix, k, poolBlocks[k], tierLanes[k], tierWords[k])) return 1;
 	CUDA_TRY(cudaStreamWaitEvent(st, cx->ev_tail, 0));
-	bt_ctl_set_kernel<<<1, 1, 0, st>>>(cx->ctl, nwork);
-	for (int k = 1; k < NT; k++) bt_ctl_set_kernel<<<1, 1, 0, st>>>(cx->ctl + k, 0);
+	bt_ctl_set_all_kernel<<<1, 32, 0, st>>>(cx->ctl, BT_CTL_WORDS, nwork);
 	auto kernel = pol->paired ? bt_best_kernel<true> : bt_best_kernel<false>;
 	uint32_t *sels[2] = { cx->heavy_sel, cx->retry_sel };                 /* tier k reads the list tier k-1 wrote; two buffers alternate */
 	for (int k = 0; k < NT; k++) {
 		cudaStream_t s = k == 0 ? st : cx->side;
 		const uint32_t *sel_in = k == 0 ? in->sel : sels[(k - 1) & 1];
-		P.sel = sel_in; P.arena = cx->arena[k]; P.arenaWords = tierWords[k];
+		P.sel = sel_in; P.arena = ix->bf_pool[k].mem; P.arenaWords = tierWords[k]; P.poolMask = ix->bf_pool[k].mask; P.poolBlocks = ix->bf_pool[k].blocks;
 		kernel<<<tierBlocks[k], BF_THREADS, 0, s>>>(P, cx->ctl + k, tierLanes[k]);
 		if (k + 1 < NT) bt_collect_kernel<<<cblocks, 256, 0, s>>>(out->flags, sel_in, nwork, k == 0 ? nullptr : cx->ctl + k, BT_FLAG_STACK_OVF, sels[k & 1], cx->ctl + k + 1);
 		if (k == 0) { CUDA_TRY(cudaEventRecord(cx->ev_main, st)); CUDA_TRY(cudaStreamWaitEvent(cx->side, cx->ev_main, 0)); }
@@ -813,13 +893,18 @@ static void set_ws(BtKParams &P, const Workspace &w) {
 }
 
 /* Enqueues one batch.  All pointers are device pointers; `maxlen` bounds the read length.
- *   main pass      on `st`:        every read, with a per-read transition budget and first-tier scratch
- *   tail pass      on cx->side:    the reads that exhausted the budget or the first-tier scratch (more seedlings than 64): a second,
- *                                  large budget, 4096 seedlings, full-size blocks
- *   ultra pass     on cx->side:    the handful of reads beyond the second budget: no budget, single-warp blocks on a fraction of the SMs
- *   overflow pass  on cx->side:    reads whose scratch overflowed in the tail / ultra pass too, worst-case scratch (normally empty)
+ *   main pass      on `st`:        every read, with a per-read transition budget and first-tier scratch (64 seedlings).  A read that
+ *                                  exceeds the budget or fills its seedling list is SUSPENDED into a checkpoint slot (bt_ctxq.cuh).
+ *   slices         on cx->side:    BT_SLICES passes over the suspended reads, each resuming every read still unfinished for a
+ *                                  (geometrically growing) quantum of transitions and suspending it again; the last one runs to the end.
+ *                                  Search cost is heavy-tailed (1 % of the reads = half of all transitions, the longest 10^6 sequential
+ *                                  steps): re-packing the survivors after every quantum keeps the warps of the long tail full instead
+ *                                  of one straggler holding 127 idle lanes and their registers.
+ *   overflow pass  on cx->side:    reads whose scratch overflowed even in a slot (or that found no free slot): re-run from scratch with
+ *                                  worst-case scratch (normally empty)
  * The side stream lets the long tail of batch k overlap the main pass of batch k+1 (another context); the
  * batch is complete when cx->ev_tail has fired (bt_context_join / bt_context_sync). */
+#define BT_SLICES_MAX 8
 static int enqueue_align(bt_context *cx, const bt_policy_t *pol, const bt_read_batch_t *in, bt_hit_batch_t *out, uint32_t maxlen, cudaStream_t st) {
 	bt_index_t *ix = cx->ix;
 	const uint32_t nwork = in->sel ? in->nsel : in->nreads;
@@ -833,11 +918,27 @@ static int enqueue_align(bt_context *cx, const bt_policy_t *pol, const bt_read_b
 	const uint32_t nthreads = main_kernel_is_queue() ? (uint32_t)ix->sms * BT_Q_NCTX : (uint32_t)ix->sms * (uint32_t)ix->blocks_per_sm * BT_THREADS;
 	const uint32_t stage_len = (maxlen + 15) & ~15u;                     /* every context keeps a writable copy of its read */
 	if (ensure_ws(cx->ws1, nthreads, 6 * maxlen + 8, 8, 64, stage_len)) return 1;
-	/* the tail pass takes the heavy reads AND the reads whose first-tier scratch overflowed (seedling lists of repeat reads, mostly),
-	 * so it gets the seedling capacity of the worst case; the ultra pass shares its scratch (they run one after the other) */
-	static const uint32_t tail_bps = env_u32("BT_TAIL_BLOCKS", 2);
-	const uint32_t nthreads_h = (uint32_t)ix->sms * tail_bps * 128;       /* BT_TAIL_BLOCKS counts 128 lanes */
-	if (ensure_ws(cx->wsh, nthreads_h, 6 * maxlen + 8, 16, 4096, stage_len)) return 1;
+	/* checkpoint slots: one per suspended read.  On the bench workload 0.7 % of the reads exceed the main budget and 0.3 % fill the
+	 * 64-seedling list; slots for 1/32 of the batch (BT_SLOT_DIV), at least 4096.  A read that finds none is re-run by the overflow pass. */
+	static const uint32_t slot_div = env_u32("BT_SLOT_DIV", 32), slot_pcap = env_u32("BT_SLOT_PCAP", 1024);
+	static const bool use_slots = env_u32("BT_SLICES", 6) > 0 && !main_kernel_is_queue();
+	static const uint32_t nslices = env_u32("BT_SLICES", 6) > BT_SLICES_MAX ? BT_SLICES_MAX : env_u32("BT_SLICES", 6);
+	uint32_t nslot = nwork / (slot_div ? slot_div : 32); if (nslot < 4096) nslot = 4096; if (nslot > nwork) nslot = nwork;
+	if (use_slots) {
+		if (ensure_ws(cx->wsl, nslot, 6 * maxlen + 8, 16, slot_pcap, stage_len)) return 1;
+		if (cx->slot_cap < nslot) {
+			cudaFree(cx->slot_ctx); cudaFree(cx->slice_list[0]); cudaFree(cx->slice_list[1]); cx->slot_ctx = cx->slice_list[0] = cx->slice_list[1] = nullptr; cx->slot_cap = 0;
+			CUDA_TRY(cudaMalloc((void **)&cx->slot_ctx, (size_t)cx->wsl.nthreads * BT_CTX_WORDS * 4));
+			CUDA_TRY(cudaMalloc((void **)&cx->slice_list[0], (size_t)cx->wsl.nthreads * 4));
+			CUDA_TRY(cudaMalloc((void **)&cx->slice_list[1], (size_t)cx->wsl.nthreads * 4));
+			cx->slot_cap = cx->wsl.nthreads;
+		}
+		nslot = cx->wsl.nthreads >= nslot ? nslot : cx->wsl.nthreads;
+	} else {
+		/* no slots (BT_SLICES=0, or the queue kernel): the tail pass re-runs heavy reads from scratch on full-size scratch */
+		static const uint32_t tail_bps = env_u32("BT_TAIL_BLOCKS", 2);
+		if (ensure_ws(cx->wsh, (uint32_t)ix->sms * tail_bps * 128, 6 * maxlen + 8, 16, 4096, stage_len)) return 1;
+	}
 	const uint32_t nthreads2 = (uint32_t)ix->sms * 32;
 	uint32_t R2 = maxlen * maxlen + 8; if (R2 > 65000) R2 = 65000;   /* BtFrame::rowbase is 16 bits */
 	if (ensure_ws(cx->ws2, nthreads2, R2, maxlen + 2, 4096, stage_len)) return 1;
@@ -856,6 +957,7 @@ static int enqueue_align(bt_context *cx, const bt_policy_t *pol, const bt_read_b
 	P.found = out->found; P.flags = out->flags; P.hits = out->hits; P.slots = out->slots; P.mm_cap = out->mm_cap; P.rec_words = BT_HIT_HDR + out->mm_cap;
 	P.stats = ix->stats;
 	const uint32_t cblocks = (nwork + 255) / 256;
+	BtWorkCtl *const ctl_main = cx->ctl, *const ctl_slice = cx->ctl + 1, *const ctl_ovf = cx->ctl + 1 + BT_SLICES_MAX + 1;   /* ctl_slice[k]: work list of slice k */
 	/* this context's previous batch must have finished with the scratch and the lists */
 	CUDA_TRY(cudaStreamWaitEvent(st, cx->ev_tail, 0));
 	/* main pass */
@@ -863,46 +965,57 @@ static int enqueue_align(bt_context *cx, const bt_policy_t *pol, const bt_read_b
 	P.budget = main_budget();
 	{ static const uint32_t db = env_u32("BT_DRAIN_BUDGET", 1500); P.drain_budget = db; }
 	{ static uint32_t p = env_u32("BT_RARE_PERIOD", BT_RARE_PERIOD), t = env_u32("BT_RARE_THRESH", BT_RARE_THRESH); P.rare_period = p ? p : 1; P.rare_thresh = t; }
-	bt_ctl_set_kernel<<<1, 1, 0, st>>>(cx->ctl, nwork);
-	bt_ctl_set_kernel<<<1, 1, 0, st>>>(cx->ctl + 1, 0);
-	bt_ctl_set_kernel<<<1, 1, 0, st>>>(cx->ctl + 2, 0);
-	bt_ctl_set_kernel<<<1, 1, 0, st>>>(cx->ctl + 3, 0);
+	bt_ctl_set_all_kernel<<<1, 32, 0, st>>>(cx->ctl, BT_CTL_WORDS, nwork);
+	if (use_slots) {
+		P.slot_ctx = cx->slot_ctx; P.slot_rows = cx->wsl.rows; P.slot_elims = cx->wsl.elims; P.slot_frames = cx->wsl.frames; P.slot_partials = cx->wsl.partials;
+		P.slot_stage = cx->wsl.stage; P.nslot = nslot; P.slot_R = cx->wsl.R; P.slot_FCAP = cx->wsl.FCAP; P.slot_PCAP = cx->wsl.PCAP; P.slot_stage_len = cx->wsl.stage_len;
+		P.resume = 0; P.slice_count = &ctl_slice[0].nwork; P.slice_out = nullptr;
+	}
 	if (main_kernel_is_queue()) {
 		uint32_t grid = (uint32_t)ix->sms;
 		const uint32_t need = (nwork + BT_Q_NCTX - 1) / BT_Q_NCTX;
 		if (grid > need) grid = need;
-		bt_search_kernel_q<<<grid, BT_Q_THREADS, bt_q_smem(BT_Q_NCTX), st>>>(P, cx->ctl, BT_Q_NCTX);
+		bt_search_kernel_q<<<grid, BT_Q_THREADS, bt_q_smem(BT_Q_NCTX), st>>>(P, ctl_main, BT_Q_NCTX);
 	} else {
 		uint32_t grid = (uint32_t)ix->sms * (uint32_t)ix->blocks_per_sm;
 		const uint32_t need = (nwork + BT_THREADS - 1) / BT_THREADS;
 		if (grid > need) grid = need;
-		bt_search_kernel<<<grid, BT_THREADS, BT_THREADS * BT_SMEM_STRIDE, st>>>(P, cx->ctl);
+		bt_search_kernel<<<grid, BT_THREADS, BT_THREADS * BT_SMEM_STRIDE, st>>>(P, ctl_main);
 	}
-	bt_collect_kernel<<<cblocks, 256, 0, st>>>(out->flags, in->sel, nwork, nullptr, BT_FLAG_RETRY, cx->heavy_sel, cx->ctl + 1);
 	CUDA_TRY(cudaEventRecord(cx->ev_main, st));
-	/* tail, ultra and overflow passes on the side stream */
 	CUDA_TRY(cudaStreamWaitEvent(cx->side, cx->ev_main, 0));
 	{ static uint32_t p = env_u32("BT_HEAVY_PERIOD", BT_RARE_PERIOD), t = env_u32("BT_HEAVY_THRESH", BT_RARE_THRESH); P.rare_period = p ? p : 1; P.rare_thresh = t; }
-	set_ws(P, cx->wsh);
-	/* tail pass: full-size blocks, a second (large) budget, so that it ends when its bulk is done — its few stragglers move on */
-	/* (a second budget + an "ultra" pass for what exceeds it was measured on the hg19-sized index: 3.0 M reads/s against 5.1 M reads/s
-	 * without — every restart repeats work and the few single-warp blocks serialise the longest searches; BT_TAIL_BUDGET keeps the
-	 * experiment available, 0 = the tail pass finishes every read) */
-	static const uint32_t tail_budget = env_u32("BT_TAIL_BUDGET", 0);
-	P.sel = cx->heavy_sel; P.budget = tail_budget; P.drain_budget = 0;
-	bt_search_kernel<<<nthreads_h / BT_THREADS, BT_THREADS, BT_THREADS * BT_SMEM_STRIDE, cx->side>>>(P, cx->ctl + 1);
-	bt_collect_kernel<<<cblocks, 256, 0, cx->side>>>(out->flags, cx->heavy_sel, nwork, cx->ctl + 1, BT_FLAG_BUDGET, cx->ultra_sel, cx->ctl + 2);
-	bt_collect_kernel<<<cblocks, 256, 0, cx->side>>>(out->flags, cx->heavy_sel, nwork, cx->ctl + 1, BT_FLAG_SCRATCH_OVF, cx->retry_sel, cx->ctl + 3);
-	/* ultra pass: the handful of searches of 10^5 .. 10^6 sequential transitions.  They take as long as they take (a GPU lane is a
-	 * slow serial processor); what matters is that they hold few resources while they do: single-warp blocks on a fraction of the
-	 * SMs, so that the main passes of the following batches keep (almost) the whole machine */
-	static const uint32_t ultra_blocks = env_u32("BT_ULTRA_BLOCKS", 74);
-	P.sel = cx->ultra_sel; P.budget = 0;
-	bt_search_kernel<<<ultra_blocks, 32, 32 * BT_SMEM_STRIDE, cx->side>>>(P, cx->ctl + 2);
-	bt_collect_kernel<<<cblocks, 256, 0, cx->side>>>(out->flags, cx->ultra_sel, nwork, cx->ctl + 2, BT_FLAG_RETRY, cx->retry_sel, cx->ctl + 3);
-	P.sel = cx->retry_sel;
+	if (use_slots) {
+		/* slices: slice k resumes the slots of its list (slice 0: all of them, in order) and runs each read up to a cumulative budget of
+		 * main budget x BT_SLICE_GROWTH^(k+1) transitions; what is still unfinished is suspended again into the next slice's list */
+		static const uint32_t growth = env_u32("BT_SLICE_GROWTH", 3), sl_threads = env_u32("BT_SLICE_THREADS", BT_THREADS), sl_bps = env_u32("BT_SLICE_BLOCKS", 2);
+		const uint32_t threads = (sl_threads >= 32 && sl_threads <= BT_THREADS && sl_threads % 32 == 0) ? sl_threads : BT_THREADS;
+		uint32_t grid = (uint32_t)ix->sms * sl_bps * (BT_THREADS / threads);
+		{ const uint32_t need = (nslot + threads - 1) / threads; if (grid > need) grid = need; }
+		P.resume = 1; P.drain_budget = 0;
+		P.R = cx->wsl.R; P.FCAP = cx->wsl.FCAP; P.PCAP = cx->wsl.PCAP; P.stage = nullptr; P.stage_len = cx->wsl.stage_len;
+		P.rows = nullptr; P.elims = nullptr; P.frames = nullptr; P.partials = nullptr;
+		unsigned long long b = P.budget ? P.budget : 8000;
+		for (uint32_t k = 0; k < nslices; k++) {
+			b *= growth > 1 ? growth : 2;
+			P.budget = (k + 1 == nslices || b > 0x7fffffffull) ? 0u : (uint32_t)b;           /* the last slice finishes every read */
+			P.sel = k == 0 ? nullptr : cx->slice_list[(k - 1) & 1];
+			P.slice_count = &ctl_slice[k + 1].nwork; P.slice_out = cx->slice_list[k & 1];
+			bt_search_kernel<<<grid, threads, threads * BT_SMEM_STRIDE, cx->side>>>(P, ctl_slice + k);
+		}
+		P.resume = 0; P.slot_ctx = nullptr;
+		/* what is flagged now: scratch overflow in a slot, or no free slot */
+		bt_collect_kernel<<<cblocks, 256, 0, cx->side>>>(out->flags, in->sel, nwork, nullptr, BT_FLAG_RETRY, cx->retry_sel, ctl_ovf);
+	} else {
+		bt_collect_kernel<<<cblocks, 256, 0, cx->side>>>(out->flags, in->sel, nwork, nullptr, BT_FLAG_RETRY, cx->heavy_sel, ctl_slice);
+		set_ws(P, cx->wsh);
+		P.sel = cx->heavy_sel; P.budget = 0; P.drain_budget = 0;
+		bt_search_kernel<<<cx->wsh.nthreads / BT_THREADS, BT_THREADS, BT_THREADS * BT_SMEM_STRIDE, cx->side>>>(P, ctl_slice);
+		bt_collect_kernel<<<cblocks, 256, 0, cx->side>>>(out->flags, cx->heavy_sel, nwork, ctl_slice, BT_FLAG_SCRATCH_OVF, cx->retry_sel, ctl_ovf);
+	}
+	P.sel = cx->retry_sel; P.budget = 0; P.drain_budget = 0;
 	set_ws(P, cx->ws2);
-	bt_search_kernel<<<ix->sms, 32, 32 * BT_SMEM_STRIDE, cx->side>>>(P, cx->ctl + 3);
+	bt_search_kernel<<<ix->sms, 32, 32 * BT_SMEM_STRIDE, cx->side>>>(P, ctl_ovf);
 	CUDA_TRY(cudaGetLastError());
 	return 0;
 }

@@ -425,7 +425,7 @@ class HostEmu:
         ensure_oracle_built()
         d = ROOT / "tests" / "host_emu"
         so = d / "libbtemu.so"
-        srcs = [d / "emu.cpp", ROOT / "bowtie_b200" / "csrc" / "bt_core.cuh", ROOT / "bowtie_b200" / "csrc" / "bt_native.cuh",
+        srcs = [d / "emu.cpp", ROOT / "bowtie_b200" / "csrc" / "bt_core.cuh", ROOT / "bowtie_b200" / "csrc" / "bt_native.cuh", ROOT / "bowtie_b200" / "csrc" / "bt_ctxq.cuh",
                 ORACLE_DIR / "bt_oracle.c"]
         def stale():
             return not so.exists() or so.stat().st_mtime < max(s.stat().st_mtime for s in srcs)
@@ -451,6 +451,10 @@ class HostEmu:
         L.emu_align.argtypes = [C.c_void_p, C.c_void_p, C.POINTER(_DevPolicy), C.c_uint32, C.c_void_p, C.c_void_p, C.c_void_p,
                                 C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint32, C.c_uint32, C.c_uint32,
                                 C.c_uint32, C.c_uint32, C.c_void_p, C.c_void_p]
+        L.emu_align_sliced.restype = C.c_int
+        L.emu_align_sliced.argtypes = [C.c_void_p, C.c_void_p, C.POINTER(_DevPolicy), C.c_uint32, C.c_void_p, C.c_void_p, C.c_void_p,
+                                       C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint32, C.c_uint32, C.c_uint32,
+                                       C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32, C.c_void_p, C.c_void_p]
         self.L = L
         self._idx = {}
 
@@ -462,6 +466,35 @@ class HostEmu:
                 raise RuntimeError("emu index load failed")
             self._idx[key] = h
         return self._idx[key]
+
+    def align_sliced(self, base, batch: ReadBatch, pol: Policy, budget0: int, growth: int, slots=None, mm_cap=8, R=None, FCAP=8, PCAP=64,
+                     slot_FCAP=16, slot_PCAP=1024):
+        """The batch under the kernels' time slicing: reads beyond `budget0` transitions (or with a full seedling list) are suspended into a
+        checkpoint slot and resumed with `growth` x the budget (0: unlimited), with a poisoned lane in between.  Returns (result, flags, suspensions)."""
+        fw = self.index(base, False)
+        bw = self.index(base, True) if (pol.mode == 1 or pol.mms > 0) else None
+        n = len(batch)
+        if slots is None:
+            slots = 64 if pol.all_hits else pol.khits
+        maxlen = int((batch.offs[1:] - batch.offs[:-1]).max()) if n else 1
+        if R is None:
+            R = 8 * maxlen
+        found = np.zeros(n, np.uint32)
+        flags = np.zeros(n, np.uint32)
+        hits = np.zeros(n * slots * (BT_HIT_HDR + mm_cap), np.uint32)
+        stats = np.zeros(8, np.uint64)
+        nsusp = np.zeros(1, np.uint64)
+        cp = dev_policy(pol)
+        rc = self.L.emu_align_sliced(fw, bw, C.byref(cp), n, batch.seq_codes.ctypes.data, batch.qual_cat.ctypes.data,
+                                     batch.offs.ctypes.data, batch.seeds.ctypes.data, found.ctypes.data, flags.ctypes.data,
+                                     hits.ctypes.data, slots, mm_cap, R, FCAP, PCAP, slot_FCAP, slot_PCAP, budget0, growth,
+                                     stats.ctypes.data, nsusp.ctypes.data)
+        if rc:
+            raise RuntimeError(f"emu_align_sliced rc={rc}")
+        res = decode_device_result(found, hits, slots, mm_cap, pol)
+        res.stats = dict(zip(["lfex", "lf", "chase", "ftab", "offs", "backtracks", "iters", "blockloads"], stats.tolist()))
+        self.raw = (found, hits)
+        return res, flags, int(nsusp[0])
 
     def align(self, base, batch: ReadBatch, pol: Policy, slots=None, mm_cap=8, R=None, FCAP=16, PCAP=256):
         fw = self.index(base, False)

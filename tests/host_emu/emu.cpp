@@ -12,6 +12,7 @@
 #include <stdio.h>
 #include <vector>
 #include "../../bowtie_b200/csrc/bt_native.cuh"
+#include "../../bowtie_b200/csrc/bt_ctxq.cuh"
 extern "C" {
 #include "../../oracle/bt_oracle.h"
 }
@@ -96,6 +97,67 @@ int emu_align(void *fwp, void *bwp, const BtPolicy *pol, uint32_t nreads, const 
 	return 0;
 }
 
+/* The same batch under the kernels' time slicing (bt_ctxq.cuh, checkpoint slots): a read that exceeds `budget0` transitions — or fills
+ * the main pass's seedling list — is suspended into a slot (bt_slot_save_new), the lane and its scratch are poisoned, and the read is
+ * resumed from the slot (bt_slot_resume) with the slot's capacities and `growth` times the budget, again and again until it ends.
+ * Results must equal emu_align's; *nsusp counts the suspensions. */
+int emu_align_sliced(void *fwp, void *bwp, const BtPolicy *pol, uint32_t nreads, const uint8_t *seq, const uint8_t *qual,
+                     const uint64_t *roff, const uint32_t *seeds, uint32_t *found, uint32_t *flags, uint32_t *hits,
+                     uint32_t slots, uint32_t mm_cap, uint32_t R, uint32_t FCAP, uint32_t PCAP, uint32_t slotFCAP, uint32_t slotPCAP,
+                     uint32_t budget0, uint32_t growth, unsigned long long *stats, unsigned long long *nsusp) {
+	BtKParams P; memset(&P, 0, sizeof P);
+	P.ix[0] = ((EmuIndex *)fwp)->dev;
+	if (bwp) P.ix[1] = ((EmuIndex *)bwp)->dev;
+	P.pol = *pol;
+	P.seq = seq; P.qual = qual; P.roff = roff; P.seeds = seeds; P.nwork = nreads;
+	P.found = found; P.flags = flags; P.hits = hits; P.slots = slots; P.mm_cap = mm_cap; P.rec_words = BT_HIT_HDR + mm_cap;
+	std::vector<uint4> rows(2 * (size_t)R), srows(2 * (size_t)R); std::vector<uint8_t> elims(R), selims(R);
+	std::vector<BtFrame> frames(FCAP), sframes(slotFCAP); std::vector<uint64_t> parts(PCAP), sparts(slotPCAP);
+	std::vector<uint32_t> sctx(BT_CTX_WORDS);
+	uint32_t maxlen = 1;
+	for (uint32_t r = 0; r < nreads; r++) { const uint32_t l = (uint32_t)(roff[r + 1] - roff[r]); if (l > maxlen) maxlen = l; }
+	std::vector<uint8_t> sstage(2 * (size_t)maxlen + 2);
+	P.slot_ctx = sctx.data(); P.slot_rows = srows.data(); P.slot_elims = selims.data(); P.slot_frames = sframes.data(); P.slot_partials = sparts.data();
+	P.slot_stage = sstage.data(); P.nslot = 1; P.slot_R = R; P.slot_FCAP = slotFCAP; P.slot_PCAP = slotPCAP; P.slot_stage_len = maxlen;
+	bt_build_prog(pol->mode, pol->mms, pol->nofw, pol->norc, P.prog);
+	BtLane L; memset(&L, 0, sizeof L);
+	std::vector<uint8_t> stage;
+	*nsusp = 0;
+	for (uint32_t r = 0; r < nreads; r++) {
+		P.R = R; P.FCAP = FCAP; P.PCAP = PCAP; P.resume = 0;
+		BtScratch S = { rows.data(), elims.data(), frames.data(), parts.data() };
+		uint32_t budget = budget0;
+		bt_begin_read(L, P, r);
+		stage.assign(2 * (size_t)L.rlen + 2, 0);
+		memcpy(stage.data(), seq + roff[r], L.rlen);
+		memcpy(stage.data() + L.rlen, qual + roff[r], L.rlen);
+		L.rseq = stage.data(); L.rqual = stage.data() + L.rlen;
+		L.hasN = memchr(stage.data(), 4, L.rlen) != NULL;
+		unsigned long long guard = 0;
+		while (L.pc != PC_FINISH_READ) {
+			if (BT_IS_FAST(L.pc)) bt_fast_iter(L, P, S); else bt_rare_iter(L, P, S, budget);
+			if (L.flags & BT_FLAG_PREEMPT) {
+				L.flags &= ~BT_FLAG_PREEMPT;
+				if (!P.resume) bt_slot_save_new(L, P, S, 0); else bt_ctx_store(L, P.slot_ctx, 1, 0);
+				(*nsusp)++;
+				/* nothing of the lane or of the main pass's scratch survives, except the lane's operation counters */
+				uint32_t keep[8] = { L.s_lfex, L.s_lf, L.s_chase, L.s_ftab, L.s_offs, L.s_bt, L.s_iter, L.s_blk };
+				memset(&L, 0xCD, sizeof L);
+				L.s_lfex = keep[0]; L.s_lf = keep[1]; L.s_chase = keep[2]; L.s_ftab = keep[3]; L.s_offs = keep[4]; L.s_bt = keep[5]; L.s_iter = keep[6]; L.s_blk = keep[7];
+				memset(rows.data(), 0xCD, rows.size() * sizeof(uint4)); memset(elims.data(), 0xCD, elims.size());
+				memset(frames.data(), 0xCD, frames.size() * sizeof(BtFrame)); memset(parts.data(), 0xCD, parts.size() * 8);
+				memset(stage.data(), 0xCD, stage.size());
+				P.resume = 1; P.R = P.slot_R; P.FCAP = slotFCAP; P.PCAP = slotPCAP;
+				budget = growth ? (budget > 0x7fffffffu / growth ? 0u : budget * growth) : 0u;
+				bt_slot_resume(L, P, S, 0);
+			}
+			if (++guard > (1ull << 34)) return 1;
+		}
+		bt_finish_read(L, P);
+	}
+	stats[0] = L.s_lfex; stats[1] = L.s_lf; stats[2] = L.s_chase; stats[3] = L.s_ftab; stats[4] = L.s_offs; stats[5] = L.s_bt; stats[6] = L.s_iter; stats[7] = L.s_blk;
+	return 0;
+}
 
 /* Warp-level replay of bt_search_kernel's scheduling (development aid, tools/warp_sim.py): `nwarps` x 32 lanes pull reads from one
  * cursor and take fast / deferred-rare transitions under the kernel's rule; what comes out is how full the warps are when they

@@ -78,3 +78,34 @@ def test_scratch_overflow_is_flagged_not_silent(emu, oracle, synth_index):
     clean = flags == 0
     # reads that were not flagged are exact
     assert np.array_equal(a.nhits_per_read[clean], b.nhits_per_read[clean])
+
+
+@pytest.mark.parametrize("pol", POLICIES, ids=lambda p: " ".join(p.ref_args()))
+def test_time_sliced_search_equals_oracle(pol, emu, oracle, ecoli_base, ecoli_reads):
+    """Checkpoint slots (bt_ctxq.cuh): every read is suspended after a few transitions — packed lane state, read copy and live scratch
+    into a slot, the lane poisoned — and resumed from the slot, over and over with a growing budget.  Output and operation counters
+    equal the oracle's, i.e. a suspended read loses nothing."""
+    a = oracle.align(ecoli_base, ecoli_reads, pol)
+    for budget0, growth in ((7, 2), (150, 3)):
+        b, flags, nsusp = emu.align_sliced(ecoli_base, ecoli_reads, pol, budget0, growth)
+        assert budget0 > 7 or nsusp > 0          # (the budget is tested between rare transitions: exact-match searches have few)
+        assert not flags.any()
+        ok, why = results_equal(a, b)
+        assert ok, (budget0, growth, why)
+        for k in ("lfex", "lf", "chase", "ftab", "offs", "backtracks"):
+            assert a.stats[k] == b.stats[k], k
+
+
+@pytest.mark.parametrize("pol", POLICIES[::2], ids=lambda p: " ".join(p.ref_args()))
+def test_time_sliced_search_synthetic(pol, emu, oracle, synth_index):
+    """Ragged reads, Ns, deep recursion and long seedling lists: the main pass's small scratch (8 frames, 16 seedlings here) fills up, the
+    read moves to a slot with the later passes' capacities and finishes there."""
+    from synth import synth_reads
+    base, genome = synth_index
+    batch = synth_reads(genome, 600, (18, 120), seed=3, sub_rate=0.03, n_rate=0.005, qual_profile="low")
+    a = oracle.align(base, batch, pol)
+    b, flags, nsusp = emu.align_sliced(base, batch, pol, 40, 2, mm_cap=64, R=120 * 121, FCAP=128, PCAP=16, slot_FCAP=128, slot_PCAP=4096)
+    assert nsusp > 100
+    assert not flags.any()
+    ok, why = results_equal(a, b)
+    assert ok, why
