@@ -40,11 +40,13 @@
 #define BT_NOINLINE __device__ __noinline__
 #define BT_LDG(p) __ldg(p)
 #define BT_POPC64(x) __popcll(x)
+#define BT_POPC32(x) ((uint32_t)__popc(x))
 #else
 #define BT_FN static inline
 #define BT_NOINLINE static
 #define BT_LDG(p) (*(p))
 #define BT_POPC64(x) __builtin_popcountll(x)
+#define BT_POPC32(x) ((uint32_t)__builtin_popcount(x))
 #ifndef BT_HOST_EMU
 #error "bt_core.cuh is device code; the host build exists only for tests/host_emu (define BT_HOST_EMU)"
 #endif
@@ -52,6 +54,17 @@ struct uint4 { uint32_t x, y, z, w; };
 #endif
 
 #define BT_OFF_MASK 0xffffffffu
+#ifndef BT_ALT_FLAT
+#define BT_ALT_FLAT 1              /* branch-free bookkeeping of a position's alternatives (bt_position) */
+#endif
+
+/* development aid (tools/pc_hist.py): trip counts of the per-lane loops inside the rare blocks, host emulation only */
+#if defined(BT_HOST_EMU) && defined(BT_EMU_PROFILE)
+extern unsigned long long bt_emu_prof[16];
+#define BT_PROF(i, n) (bt_emu_prof[i] += (n))
+#else
+#define BT_PROF(i, n) ((void)0)
+#endif
 
 /* ---- device-resident index (one per orientation) -------------------------------------------- */
 struct BtDevIndex {
@@ -447,6 +460,30 @@ BT_FN void bt_position(BtLane &L, const BtKParams &P, const BtScratch &S,
 	if (d >= L.rowd0) {
 		const uint32_t ri = bt_row_idx(L, d);
 		uint32_t el = (c < 4) ? (1u << c) : 0u;                   /* eliminate() */
+#if BT_ALT_FLAT
+		if (L.curIsAlt) {
+			/* the per-character loop of ebwt_search_backtrack.h:603-653 without its branches: the live alternatives as a bit mask, their
+			 * number and total width; the first live one becomes the recorded eligible edit when this position overrides */
+			uint4 tv = { tops[0], tops[1], tops[2], tops[3] }, bv = { bots[0], bots[1], bots[2], bots[3] };
+			S.rows[2 * (size_t)ri] = tv; S.rows[2 * (size_t)ri + 1] = bv;
+			const uint32_t s0 = bots[0] - tops[0], s1 = bots[1] - tops[1], s2 = bots[2] - tops[2], s3 = bots[3] - tops[3];
+			const uint32_t nz = ((uint32_t)(s0 != 0) | ((uint32_t)(s1 != 0) << 1) | ((uint32_t)(s2 != 0) << 2) | ((uint32_t)(s3 != 0) << 3)) & ~el;
+			el = ~nz & 15u;
+			const uint32_t n = BT_POPC32(nz);
+			L.altNum += n;
+			if (L.curIsElig && n) {
+				if (L.curOverrides) {
+					const uint32_t f = (nz & 1u) ? 0u : (nz & 2u) ? 1u : (nz & 4u) ? 2u : 3u;
+					L.lowAltQual = q; L.eligibleNum = 0; L.eligibleSz = 0; L.curOverrides = 0;
+					L.eli = d; L.eltop = f == 0 ? tops[0] : f == 1 ? tops[1] : f == 2 ? tops[2] : tops[3];
+					L.elbot = f == 0 ? bots[0] : f == 1 ? bots[1] : f == 2 ? bots[2] : bots[3];
+					L.elham = bt_mm_penalty(L.maqPenalty, q); L.elcint = f; L.elignore = 0;
+				}
+				L.eligibleSz += ((nz & 1u) ? s0 : 0u) + ((nz & 2u) ? s1 : 0u) + ((nz & 4u) ? s2 : 0u) + ((nz & 8u) ? s3 : 0u);
+				L.eligibleNum += n;
+			}
+		}
+#else
 		if (L.curIsAlt) {
 			uint4 tv = { tops[0], tops[1], tops[2], tops[3] }, bv = { bots[0], bots[1], bots[2], bots[3] };
 			S.rows[2 * (size_t)ri] = tv; S.rows[2 * (size_t)ri + 1] = bv;
@@ -469,6 +506,7 @@ BT_FN void bt_position(BtLane &L, const BtKParams &P, const BtScratch &S,
 				}
 			}
 		}
+#endif
 		S.elims[ri] = (uint8_t)el;
 	}
 	L.f_bdm = 0; L.f_must = 0; L.f_invHH = 0; L.f_invExact = 0;
@@ -641,9 +679,12 @@ BT_FN void bt_blk_btloop(BtLane &L, const BtKParams &P, const BtScratch &S) {
 		/* while((top == bot || backtrackDespiteMatch) && altNum > 0) (ebwt_search_backtrack.h:743-971) */
 		if (!((L.top == L.bot || L.f_bdm) && L.altNum > 0)) { L.pc = PC_POS_END; break; }
 		uint32_t i = L.d, j = 0, bttop = 0, btbot = 0, btham = L.ham, btcint = 0;
+		BT_PROF(0, 1);
 		if (L.eligibleNum > 1 || L.elignore) {
+			BT_PROF(1, 1);
 #pragma unroll 1
 			for (;; i--) {
+				BT_PROF(2, 1);
 				const uint32_t qi = bt_qual_at(L, L.qlen - i - 1);
 				const uint32_t ri = bt_row_idx(L, i);
 				const uint32_t el = (i >= L.rowd0) ? S.elims[ri] : 15u;
@@ -744,12 +785,15 @@ BT_FN void bt_blk_child_ret(BtLane &L, const BtKParams &P, const BtScratch &S) {
 		L.elignore = 1;
 		L.altNum--;
 		if (L.altNum == 0) { L.ret = 0; L.pc = PC_FRAME_RET; break; }
+		BT_PROF(3, 1);
 		if (L.eligibleNum == 0 && L.considerQuals) {
 			/* re-scan the frame for the next-lowest quality (1004-1058) */
 			L.lowAltQual = 0xff;
+			BT_PROF(4, 1);
 #pragma unroll 1
 			for (uint32_t k = L.d;; k--) {
 				if (k < L.unrevOff) break;
+				BT_PROF(5, 1);
 				const uint32_t kq = bt_qual_at(L, L.qlen - k - 1);
 				const bool kAlt = (L.ham + bt_mm_penalty(L.maqPenalty, kq) <= L.qualThresh);
 				bool kOverrides = false;

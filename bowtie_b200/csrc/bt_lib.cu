@@ -718,6 +718,7 @@ extern "C" int bt_index_load(const char *basename, int need_mirror, int device, 
 			ix->sms = prop.multiProcessorCount;
 			int bps = 0;
 			if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bps, bt_search_kernel, BT_THREADS, BT_THREADS * BT_SMEM_STRIDE) != cudaSuccess || bps < 1) bps = 1;
+			{ const char *e = getenv("BT_MAIN_BLOCKS"); if (e && atoi(e) >= 1 && atoi(e) < bps) bps = atoi(e); }   /* occupancy experiments (profiles/) */
 			ix->blocks_per_sm = bps;
 			if (cudaFuncSetAttribute(bt_search_kernel_q, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bt_q_smem(BT_Q_NCTX)) != cudaSuccess) rc = fail("cudaFuncSetAttribute(shared memory) failed");
 		}

@@ -424,7 +424,8 @@ class HostEmu:
     def __init__(self) -> None:
         ensure_oracle_built()
         d = ROOT / "tests" / "host_emu"
-        so = d / "libbtemu.so"
+        prof = bool(os.environ.get("BT_EMU_PROFILE"))         # tools/pc_hist.py: loop trip counts of the rare blocks
+        so = d / ("libbtemu_prof.so" if prof else "libbtemu.so")
         srcs = [d / "emu.cpp", ROOT / "bowtie_b200" / "csrc" / "bt_core.cuh", ROOT / "bowtie_b200" / "csrc" / "bt_native.cuh", ROOT / "bowtie_b200" / "csrc" / "bt_ctxq.cuh",
                 ORACLE_DIR / "bt_oracle.c"]
         def stale():
@@ -435,7 +436,7 @@ class HostEmu:
                 fcntl.flock(lk, fcntl.LOCK_EX)
                 if stale():
                     tmp = d / f".libbtemu.{os.getpid()}.so"
-                    subprocess.run(["g++", "-O2", "-g", "-std=c++17", "-fPIC", "-shared", "-o", str(tmp), str(d / "emu.cpp"),
+                    subprocess.run(["g++", "-O2", "-g", "-std=c++17", "-fPIC", "-shared"] + (["-DBT_EMU_PROFILE"] if prof else []) + ["-o", str(tmp), str(d / "emu.cpp"),
                                     str(ORACLE_DIR / "bt_oracle.c")], check=True, capture_output=True)
                     os.replace(tmp, so)
         L = C.CDLL(str(so))

@@ -11,6 +11,10 @@
 #include <string.h>
 #include <stdio.h>
 #include <vector>
+#ifdef BT_EMU_PROFILE
+unsigned long long bt_emu_prof[16];          /* trip counts of the rare blocks' loops (tools/pc_hist.py builds with -DBT_EMU_PROFILE) */
+extern "C" unsigned long long *emu_prof(void) { return bt_emu_prof; }
+#endif
 #include "../../bowtie_b200/csrc/bt_native.cuh"
 #include "../../bowtie_b200/csrc/bt_ctxq.cuh"
 extern "C" {

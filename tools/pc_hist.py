@@ -3,11 +3,11 @@ bench workload (-n 2 -k 1, 100-bp synthetic reads, the bench index) and prints t
 per-read distribution.  Development aid for the kernel work; not a measurement.  Usage: python tools/pc_hist.py [n_reads=20000]"""
 import sys, os, types
 sys.path.insert(0, '/root/repo/tests'); sys.path.insert(0, '/root/repo')
-os.environ['BT_EMU_PC_HIST'] = '1'
+os.environ['BT_EMU_PC_HIST'] = '1'; os.environ['BT_EMU_PROFILE'] = '1'
 import numpy as np
 from helpers import HostEmu, Policy
 import bench
-base, name = bench.pick_index()
+base, name = bench.fallback_index()
 genome = bench.load_genome(base)
 n = int(sys.argv[1]) if len(sys.argv) > 1 else 20000
 codes, quals, offs, seeds, names = bench.make_reads(genome, n, seed=12345)
@@ -21,3 +21,7 @@ res, flags = emu.align(base, batch, pol)
 print("aligned", int((res.nhits_per_read > 0).sum()) if hasattr(res, 'nhits_per_read') else '?', "of", n)
 ipr = emu.iters_per_read
 print("iters/read: mean %.1f p50 %d p90 %d p99 %d max %d" % (ipr.mean(), np.percentile(ipr, 50), np.percentile(ipr, 90), np.percentile(ipr, 99), ipr.max()))
+import ctypes
+emu.L.emu_prof.restype = ctypes.POINTER(ctypes.c_ulonglong)
+pr = emu.L.emu_prof()
+print("per read: BTLOOP %.2f (scans %.2f, scan positions %.2f) CHILD_RET %.2f (rescans %.2f, rescan positions %.2f)" % tuple(pr[i] / n for i in range(6)))
