@@ -178,33 +178,47 @@ enum {
 enum { SITE_MAIN = 0, SITE_BT, SITE_END, SITE_FTABFULL };
 enum { LFK_EX = 0, LFK_ONE, LFK_PAIR, LFK_FCHR, LFK_NONE };
 
+/* The part of a lane's state that only the rare transitions touch (phase program, frame push / pop, reporting, seedlings).  It is
+ * reached through BtLane::K so that the kernel can keep it out of the register file: bt_search_kernel points K into the lane's
+ * shared-memory area (BT_COLD_SMEM), which takes the lane from 168 to <= 128 registers — one more resident block per SM — while the
+ * fast transition (bt_fast_iter) never dereferences it on its common path.  Elsewhere K points at an ordinary local object. */
+struct BtLaneCold {
+	uint32_t rid, seed, found, hasN;                  /* read */
+	uint32_t ph, done, step;                          /* control */
+	uint32_t fw, reportExacts, maxBts, unrev0, rev1_0, iham;   /* backtracker object state */
+	uint32_t nmuts, mut0, mut1, mut2;                 /* pos | newBase << 16 | oldBase << 24                 */
+	uint32_t rnd, numBts, bailed;
+	uint32_t depth, oneRevOff, twoRevOff, threeRevOff, disableFtab;   /* current frame */
+	uint32_t bt_i, bt_j, bttop, btbot, btham;
+	uint32_t rep_site, rep_sd, rep_cost, rep_stratum, rep_top, rep_bot, rep_r, rep_i;   /* report */
+	uint32_t npart, pal_i;                            /* seedlings */
+	uint32_t s_ftab, s_offs, s_bt;                    /* statistics */
+};
+#define BT_COLD_WORDS ((uint32_t)(sizeof(BtLaneCold) / 4))
+
 struct BtLane {
+	BtLaneCold *K;
 	/* read */
-	uint32_t rid, rlen, seed, found, flags, hasN;
-	uint8_t *rseq, *rqual;         /* writable per-lane copy of the read (shared memory, or scratch for long reads) */
+	uint32_t rlen, flags;
+	uint8_t *rseq, *rqual;         /* the lane's writable copy of the read (shared memory, or scratch for long reads); qualities are never written */
 	/* control */
-	uint32_t pc, ph, done, ret, lfk, step, nit;   /* nit: transitions taken by the current read */
+	uint32_t pc, ret, lfk, nit;    /* nit: transitions taken by the current read */
 	/* backtracker object state */
-	uint32_t ebwtSel, fw, considerQuals, halfAndHalf, reportPartials, reportExacts, maqPenalty;
-	uint32_t qualThresh, maxBts;
-	uint32_t qlen, depth5, depth3, unrev0, rev1_0, rev2_0, rev3_0, iham;
-	uint32_t nmuts, mut0, mut1, mut2;   /* pos | newBase << 16 | oldBase << 24                 */
-	uint32_t rnd, numBts, bailed, viewRev, viewComp;
+	uint32_t ebwtSel, considerQuals, halfAndHalf, reportPartials, maqPenalty;
+	uint32_t qualThresh;
+	uint32_t qlen, depth5, depth3, rev2_0, rev3_0;
+	uint32_t viewRev, viewComp;
 	/* current frame */
-	uint32_t stackDepth, depth, d, unrevOff, oneRevOff, twoRevOff, threeRevOff, ham;
+	uint32_t stackDepth, d, unrevOff, ham;
 	uint32_t altNum, eligibleNum, eligibleSz, eli, elignore, eltop, elbot, elham, elcint, lowAltQual;
-	uint32_t rowbase, rowd0, disableFtab;
+	uint32_t rowbase, rowd0;
 	uint32_t top, bot, ltop, lbot;   /* ltop/lbot: rows of the SideLocus pair (ebwt_search_backtrack.h:419-426,569-574) */
 	uint32_t c, q, curIsAlt, curIsElig, curOverrides;
 	uint32_t f_bdm, f_must, f_invHH, f_invExact;
-	uint32_t bt_i, bt_j, bttop, btbot, btham;
-	/* report / chase */
-	uint32_t rep_site, rep_sd, rep_cost, rep_stratum, rep_top, rep_bot, rep_r, rep_i;
+	/* chase */
 	uint32_t crow, cjumps;
-	/* seedlings */
-	uint32_t npart, pal_i;
 	/* statistics */
-	uint32_t s_lfex, s_lf, s_chase, s_ftab, s_offs, s_bt, s_iter, s_blk;
+	uint32_t s_lfex, s_lf, s_chase, s_iter, s_blk;
 };
 
 /* ---- small helpers --------------------------------------------------------------------------- */
@@ -240,9 +254,9 @@ BT_FN void bt_put_base(BtLane &L, uint32_t cur, uint32_t base) {
 	L.rseq[bt_view_idx(L, cur)] = (uint8_t)base;
 }
 BT_FN void bt_apply_muts(BtLane &L, bool undo) {
-	if (L.nmuts > 0) bt_put_base(L, L.mut0 & 0xffffu, undo ? (L.mut0 >> 24) : ((L.mut0 >> 16) & 0xff));
-	if (L.nmuts > 1) bt_put_base(L, L.mut1 & 0xffffu, undo ? (L.mut1 >> 24) : ((L.mut1 >> 16) & 0xff));
-	if (L.nmuts > 2) bt_put_base(L, L.mut2 & 0xffffu, undo ? (L.mut2 >> 24) : ((L.mut2 >> 16) & 0xff));
+	if (L.K->nmuts > 0) bt_put_base(L, L.K->mut0 & 0xffffu, undo ? (L.K->mut0 >> 24) : ((L.K->mut0 >> 16) & 0xff));
+	if (L.K->nmuts > 1) bt_put_base(L, L.K->mut1 & 0xffffu, undo ? (L.K->mut1 >> 24) : ((L.K->mut1 >> 16) & 0xff));
+	if (L.K->nmuts > 2) bt_put_base(L, L.K->mut2 & 0xffffu, undo ? (L.K->mut2 >> 24) : ((L.K->mut2 >> 16) & 0xff));
 }
 
 /* ---- rank blocks ----------------------------------------------------------------------------- */
@@ -328,15 +342,15 @@ BT_FN void bt_phase(BtLane &L, const BtKParams &P, const BtScratch &S) {
 	const uint32_t s = P.pol.mode == 0 ? len : (uint32_t)P.pol.seedLen;
 	const uint32_t SS = len < s ? len : s, S3 = SS >> 1, S5 = S3 + (SS & 1);
 	for (;;) {
-		if (L.done) { L.pc = PC_FINISH_READ; return; }
-		const uint32_t st = P.prog[L.ph];
+		if (L.K->done) { L.pc = PC_FINISH_READ; return; }
+		const uint32_t st = P.prog[L.K->ph];
 		const uint32_t kind = BTS_KIND(st);
 		if (kind == BTK_END) { L.pc = PC_FINISH_READ; return; }
 		if (kind == BTK_FILTER) {
 			/* search_seeded_phase1.c:17-43: too short, or more Ns in the seed than seedMms */
-			L.ph++;
+			L.K->ph++;
 			bool skip = len < 4;
-			if (!skip && L.hasN) {
+			if (!skip && L.K->hasN) {
 				uint32_t ns = 0;
 #pragma unroll 1
 				for (uint32_t i = 0; i < SS; i++) if (L.rseq[i] == 4) { if (++ns > (uint32_t)P.pol.mms) { skip = true; break; } }
@@ -348,26 +362,26 @@ BT_FN void bt_phase(BtLane &L, const BtKParams &P, const BtScratch &S) {
 		if (kind == BTK_SEEDLOOP) {
 			/* search_seeded_phase3.c:25-55 / phase4.c:24-52: extend each seedling; setQuery() is called once
 			 * before the loop, so the RNG state carries over from one seedling to the next */
-			if (L.pal_i >= L.npart) { L.npart = 0; L.pal_i = 0; L.nmuts = 0; L.ph++; continue; }
-			first = (L.pal_i == 0);
-		} else L.ph++;
+			if (L.K->pal_i >= L.K->npart) { L.K->npart = 0; L.K->pal_i = 0; L.K->nmuts = 0; L.K->ph++; continue; }
+			first = (L.K->pal_i == 0);
+		} else L.K->ph++;
 		/* constructor arguments + setQuery + setOffs + setQlen + setReportExacts of one GreedyDFSRangeSource */
-		L.step = st;
-		L.ebwtSel = BTS_EBWT(st); L.fw = BTS_FW(st); L.considerQuals = BTS_CQ(st); L.halfAndHalf = BTS_HH(st);
-		L.reportPartials = BTS_RP(st) ? (uint32_t)P.pol.mms : 0u; L.reportExacts = BTS_RE(st);
+		L.K->step = st;
+		L.ebwtSel = BTS_EBWT(st); L.K->fw = BTS_FW(st); L.considerQuals = BTS_CQ(st); L.halfAndHalf = BTS_HH(st);
+		L.reportPartials = BTS_RP(st) ? (uint32_t)P.pol.mms : 0u; L.K->reportExacts = BTS_RE(st);
 		L.qlen = BTS_SEEDQ(st) ? SS : len;
 		uint32_t v[6];
 #pragma unroll
 		for (int k = 0; k < 6; k++) { uint32_t sel = BTS_SEL(st, k); v[k] = sel == BTV_0 ? 0u : sel == BTV_LEN ? len : sel == BTV_S ? SS : sel == BTV_S3 ? S3 : S5; }
-		L.depth5 = v[0]; L.depth3 = v[1]; L.unrev0 = v[2]; L.rev1_0 = v[3]; L.rev2_0 = v[4]; L.rev3_0 = v[5];
-		L.iham = 0; L.nmuts = 0;
-		if (first) L.rnd = L.seed;                         /* setQuery: _rand.init(r.seed) */
-		L.viewRev = (L.ebwtSel == 0) ? !L.fw : L.fw;
-		L.viewComp = !L.fw;
-		if (BTS_CLEARP(st)) L.npart = 0;
+		L.depth5 = v[0]; L.depth3 = v[1]; L.K->unrev0 = v[2]; L.K->rev1_0 = v[3]; L.rev2_0 = v[4]; L.rev3_0 = v[5];
+		L.K->iham = 0; L.K->nmuts = 0;
+		if (first) L.K->rnd = L.K->seed;                         /* setQuery: _rand.init(r.seed) */
+		L.viewRev = (L.ebwtSel == 0) ? !L.K->fw : L.K->fw;
+		L.viewComp = !L.K->fw;
+		if (BTS_CLEARP(st)) L.K->npart = 0;
 		if (kind == BTK_SEEDLOOP) {
 			/* PartialAlignmentManager::toMutsString (ebwt_search_util.h:299-357) */
-			const uint64_t pal = S.partials[L.pal_i++];
+			const uint64_t pal = S.partials[L.K->pal_i++];
 			uint32_t oldQuals = 0;
 #pragma unroll 1
 			for (uint32_t k = 0; k < 3; k++) {
@@ -377,10 +391,10 @@ BT_FN void bt_phase(BtLane &L, const BtKParams &P, const BtScratch &S) {
 				uint32_t tpos = (L.rlen - 1 - pos) & 0xffffu;
 				oldQuals = (oldQuals + bt_mm_penalty(L.maqPenalty, bt_qual_at(L, tpos))) & 0xff;
 				uint32_t mv = tpos | (chr << 16) | (bt_qry(L, tpos) << 24);
-				if (k == 0) L.mut0 = mv; else if (k == 1) L.mut1 = mv; else L.mut2 = mv;
-				L.nmuts = k + 1;
+				if (k == 0) L.K->mut0 = mv; else if (k == 1) L.K->mut1 = mv; else L.K->mut2 = mv;
+				L.K->nmuts = k + 1;
 			}
-			L.iham = oldQuals;
+			L.K->iham = oldQuals;
 			bt_apply_muts(L, false);                       /* setMuts(&muts) */
 		}
 		L.pc = PC_BT_BEGIN;
@@ -425,8 +439,8 @@ BT_NOINLINE uint32_t bt_store_partial(const BtFrame *frames, uint64_t *partials,
 	return BT_FLAG_PART_OVF;
 }
 BT_FN void bt_report_partial(BtLane &L, const BtKParams &P, const BtScratch &S, uint32_t sd) {
-	L.flags |= bt_store_partial(S.frames, S.partials, L.npart, P.PCAP, sd);
-	L.npart++;
+	L.flags |= bt_store_partial(S.frames, S.partials, L.K->npart, P.PCAP, sd);
+	L.K->npart++;
 }
 
 /* Position prologue: the part of the while-loop body before the LF step (ebwt_search_backtrack.h:472-529),
@@ -516,7 +530,7 @@ BT_FN void bt_position(BtLane &L, const BtKParams &P, const BtScratch &S,
 			if (L.altNum > 0) L.f_bdm = 1;
 			if (L.stackDepth > 0) { bt_report_partial(L, P, S, L.stackDepth); reportedPartial = 1; }
 		}
-		if (L.stackDepth == 0 && L.bot > L.top && !L.reportExacts) { L.f_invExact = 1; L.f_bdm = 1; }
+		if (L.stackDepth == 0 && L.bot > L.top && !L.K->reportExacts) { L.f_invExact = 1; L.f_bdm = 1; }
 	}
 #ifndef BT_MULTI_EXIT
 	/* one exit: every outcome sets `npc`, the lane state is written once at the end (the form with a `return` per outcome made the
@@ -537,7 +551,7 @@ BT_FN void bt_position(BtLane &L, const BtKParams &P, const BtScratch &S,
 	if (npc == PC_LF) {
 		if (cur == 0 && L.bot > L.top && !L.f_invHH && !L.f_invExact && !reportedPartial) {
 			/* reportAlignment(stackDepth, top, bot, ham) */
-			L.rep_sd = L.stackDepth; L.rep_top = L.top; L.rep_bot = L.bot; L.rep_cost = L.ham; L.rep_site = SITE_MAIN;
+			L.K->rep_sd = L.stackDepth; L.K->rep_top = L.top; L.K->rep_bot = L.bot; L.K->rep_cost = L.ham; L.K->rep_site = SITE_MAIN;
 			npc = PC_REPORT;
 		} else if ((L.top == L.bot || L.f_bdm) && L.altNum > 0) npc = PC_BTLOOP;          /* mismatch with alternatives */
 		else if (L.f_must || L.f_invHH || L.f_invExact || L.top == L.bot) npc = PC_FRAME_RET;
@@ -565,7 +579,7 @@ BT_FN void bt_position(BtLane &L, const BtKParams &P, const BtScratch &S,
 	}
 	if (cur == 0 && L.bot > L.top && !L.f_invHH && !L.f_invExact && !reportedPartial) {
 		/* reportAlignment(stackDepth, top, bot, ham) */
-		L.rep_sd = L.stackDepth; L.rep_top = L.top; L.rep_bot = L.bot; L.rep_cost = L.ham; L.rep_site = SITE_MAIN;
+		L.K->rep_sd = L.stackDepth; L.K->rep_top = L.top; L.K->rep_bot = L.bot; L.K->rep_cost = L.ham; L.K->rep_site = SITE_MAIN;
 		L.pc = PC_REPORT;
 		return;
 	}
@@ -594,16 +608,16 @@ BT_FN void bt_blk_bt_begin(BtLane &L, const BtKParams &P, const BtScratch &S) {
 	do { {
 		/* backtrack(ham) (ebwt_search_backtrack.h:237-297) */
 		const uint32_t ftabChars = (uint32_t)ix.ftabChars;
-		L.numBts = 0; L.bailed = 0;
+		L.K->numBts = 0; L.K->bailed = 0;
 		/* tallyNs (1308-1341) */
 		uint32_t nsInSeed = 0, nsInFtab = 0; bool ok = true;
-		if (L.hasN) {
+		if (L.K->hasN) {
 #pragma unroll 1
 			for (uint32_t i = 0; i < L.rev3_0 && ok; i++) {
 				if (bt_qry(L, L.qlen - i - 1) == 4) {
 					nsInSeed++;
-					if (nsInSeed == 1) { if (i < L.unrev0) ok = false; }
-					else if (nsInSeed == 2) { if (i < L.rev1_0) ok = false; }
+					if (nsInSeed == 1) { if (i < L.K->unrev0) ok = false; }
+					else if (nsInSeed == 2) { if (i < L.K->rev1_0) ok = false; }
 					else if (nsInSeed == 3) { if (i < L.rev2_0) ok = false; }
 					else ok = false;
 				}
@@ -613,22 +627,22 @@ BT_FN void bt_blk_bt_begin(BtLane &L, const BtKParams &P, const BtScratch &S) {
 		}
 		if (!ok) { L.ret = 0; L.pc = PC_BT_END; break; }
 		/* the new root frame: backtrack(0, depth, _unrevOff, _1revOff, _2revOff, _3revOff, top, bot, iham, iham, ...) */
-		L.stackDepth = 0; L.depth = 0; L.unrevOff = L.unrev0; L.oneRevOff = L.rev1_0; L.twoRevOff = L.rev2_0; L.threeRevOff = L.rev3_0;
-		L.top = 0; L.bot = 0; L.ham = L.iham; L.rowbase = 0; L.disableFtab = nsInFtab > 0;
+		L.stackDepth = 0; L.K->depth = 0; L.unrevOff = L.K->unrev0; L.K->oneRevOff = L.K->rev1_0; L.K->twoRevOff = L.rev2_0; L.K->threeRevOff = L.rev3_0;
+		L.top = 0; L.bot = 0; L.ham = L.K->iham; L.rowbase = 0; L.K->disableFtab = nsInFtab > 0;
 		L.pc = PC_FRAME_ENTER;
-		const uint32_t mlim = L.unrev0 < L.qlen ? L.unrev0 : L.qlen;
+		const uint32_t mlim = L.K->unrev0 < L.qlen ? L.K->unrev0 : L.qlen;
 		if (nsInFtab == 0 && mlim >= ftabChars) {
 			uint32_t ftabOff = 0;                                             /* calcFtabOff (1348-1362) */
 #pragma unroll 1
 			for (uint32_t i = ftabChars; i > 0; i--) ftabOff = (ftabOff << 2) | bt_qry(L, L.qlen - i);
 			const uint32_t top = bt_ftab_hi(ix, ftabOff), bot = bt_ftab_lo(ix, ftabOff + 1);
-			L.s_ftab++;
+			L.K->s_ftab++;
 			if (L.qlen == ftabChars && bot > top) {
 				if (L.reportPartials == 0) {
-					L.rep_sd = 0; L.rep_top = top; L.rep_bot = bot; L.rep_cost = L.iham; L.rep_site = SITE_FTABFULL;
+					L.K->rep_sd = 0; L.K->rep_top = top; L.K->rep_bot = bot; L.K->rep_cost = L.K->iham; L.K->rep_site = SITE_FTABFULL;
 					L.pc = PC_REPORT;
 				}
-			} else if (bot > top) { L.depth = ftabChars; L.top = top; L.bot = bot; }
+			} else if (bot > top) { L.K->depth = ftabChars; L.top = top; L.bot = bot; }
 			else { L.ret = 0; L.pc = PC_BT_END; }
 		}
 		break; }
@@ -640,16 +654,16 @@ BT_FN void bt_blk_frame_enter(BtLane &L, const BtKParams &P, const BtScratch &S)
 	do { {
 		/* the head of backtrack(stackDepth, depth, ...) up to the while loop (ebwt_search_backtrack.h:363-455);
 		 * the caller has filled stackDepth, depth, the rev offsets, top, bot, ham, rowbase, disableFtab */
-		L.rowd0 = L.depth > L.unrevOff ? L.depth : L.unrevOff;
+		L.rowd0 = L.K->depth > L.unrevOff ? L.K->depth : L.unrevOff;
 		if (L.top != 0 || L.bot != 0) { L.ltop = L.top; L.lbot = L.bot; }
-		if (L.stackDepth > 0) L.s_bt++;
+		if (L.stackDepth > 0) L.K->s_bt++;
 		if (L.rowd0 < L.qlen && L.rowbase + (L.qlen - L.rowd0) > P.R) { L.flags |= BT_FLAG_STACK_OVF; break; }
 		if (L.halfAndHalf) {
-			if (L.maxBts > 0 && L.numBts == L.maxBts) { L.bailed = 1; L.ret = 0; L.pc = PC_FRAME_RET; break; }
-			L.numBts++;
+			if (L.K->maxBts > 0 && L.K->numBts == L.K->maxBts) { L.K->bailed = 1; L.ret = 0; L.pc = PC_FRAME_RET; break; }
+			L.K->numBts++;
 		}
 		L.altNum = 0; L.eligibleNum = 0; L.eligibleSz = 0; L.eli = 0; L.elignore = 1; L.eltop = 0; L.elbot = 0;
-		L.elham = L.ham; L.elcint = 0; L.lowAltQual = 0xff; L.d = L.depth;
+		L.elham = L.ham; L.elcint = 0; L.lowAltQual = 0xff; L.d = L.K->depth;
 		L.pc = PC_POS;
 	}
 	} while (0);
@@ -661,7 +675,7 @@ BT_FN void bt_blk_pos(BtLane &L, const BtKParams &P, const BtScratch &S) {
 		/* top of while(cur < _qlen) (ebwt_search_backtrack.h:456-529) with its own query loads */
 		if (L.d >= L.qlen) {
 			if (L.stackDepth >= L.reportPartials) {
-				L.rep_sd = L.stackDepth; L.rep_top = L.top; L.rep_bot = L.bot; L.rep_cost = L.ham; L.rep_site = SITE_END;
+				L.K->rep_sd = L.stackDepth; L.K->rep_top = L.top; L.K->rep_bot = L.bot; L.K->rep_cost = L.ham; L.K->rep_site = SITE_END;
 				L.pc = PC_REPORT;
 			} else { L.ret = 0; L.pc = PC_FRAME_RET; }
 			break;
@@ -688,10 +702,11 @@ BT_FN void bt_blk_btloop(BtLane &L, const BtKParams &P, const BtScratch &S) {
 				const uint32_t qi = bt_qual_at(L, L.qlen - i - 1);
 				const uint32_t ri = bt_row_idx(L, i);
 				const uint32_t el = (i >= L.rowd0) ? S.elims[ri] : 15u;
+				if (el != 15) BT_PROF(6, 1);
 				if ((qi == L.lowAltQual || !L.considerQuals) && el != 15) {
 					uint32_t posSz = 0;
 					for (j = 0; j < 4; j++) if ((el & (1u << j)) == 0) posSz += bt_pair_bot(S, ri, j) - bt_pair_top(S, ri, j);
-					uint32_t r = bt_rand_next(L.rnd) % posSz;
+					uint32_t r = bt_rand_next(L.K->rnd) % posSz;
 					for (j = 0; j < 4; j++) {
 						if ((el & (1u << j)) == 0) {
 							const uint32_t ptop = bt_pair_top(S, ri, j), pbot = bt_pair_bot(S, ri, j);
@@ -702,27 +717,27 @@ BT_FN void bt_blk_btloop(BtLane &L, const BtKParams &P, const BtScratch &S) {
 					}
 					break;
 				}
-				if (i == L.depth) break;   /* cannot happen while eligibleNum > 0 */
+				if (i == L.K->depth) break;   /* cannot happen while eligibleNum > 0 */
 			}
 		} else {
 			i = L.eli; bttop = L.eltop; btbot = L.elbot; btham += L.elham; j = L.elcint; btcint = L.elcint;
 		}
 		const uint32_t icur = L.qlen - i - 1;
-		uint32_t btUnrevOff = L.unrevOff, btOneRevOff = L.oneRevOff, btTwoRevOff = L.twoRevOff;
-		const uint32_t btThreeRevOff = L.threeRevOff;
-		if (i < L.oneRevOff) { btUnrevOff = L.oneRevOff; btOneRevOff = L.twoRevOff; btTwoRevOff = L.threeRevOff; }
-		else if (i < L.twoRevOff) { btOneRevOff = L.twoRevOff; btTwoRevOff = L.threeRevOff; }
-		else if (i < L.threeRevOff) { btTwoRevOff = L.threeRevOff; }
+		uint32_t btUnrevOff = L.unrevOff, btOneRevOff = L.K->oneRevOff, btTwoRevOff = L.K->twoRevOff;
+		const uint32_t btThreeRevOff = L.K->threeRevOff;
+		if (i < L.K->oneRevOff) { btUnrevOff = L.K->oneRevOff; btOneRevOff = L.K->twoRevOff; btTwoRevOff = L.K->threeRevOff; }
+		else if (i < L.K->twoRevOff) { btOneRevOff = L.K->twoRevOff; btTwoRevOff = L.K->threeRevOff; }
+		else if (i < L.K->threeRevOff) { btTwoRevOff = L.K->threeRevOff; }
 		if (L.stackDepth >= P.FCAP) { L.flags |= BT_FLAG_FRAME_OVF; break; }
 		BtFrame &F = S.frames[L.stackDepth];
 		F.mm_pos = (uint16_t)icur; F.mm_refc = (uint8_t)btcint;       /* _mms[stackDepth], _refcs[stackDepth] */
-		L.bt_i = i; L.bt_j = j; L.bttop = bttop; L.btbot = btbot; L.btham = btham;
+		L.K->bt_i = i; L.K->bt_j = j; L.K->bttop = bttop; L.K->btbot = btbot; L.K->btham = btham;
 		if (i + 1 == L.qlen) {
-			L.rep_sd = L.stackDepth + 1; L.rep_top = bttop; L.rep_bot = btbot; L.rep_cost = btham; L.rep_site = SITE_BT;
+			L.K->rep_sd = L.stackDepth + 1; L.K->rep_top = bttop; L.K->rep_bot = btbot; L.K->rep_cost = btham; L.K->rep_site = SITE_BT;
 			L.pc = PC_REPORT;
 			break;
 		}
-		const bool rejump = L.halfAndHalf && !L.disableFtab && L.rev2_0 == L.rev3_0 && i + 1 < (uint32_t)ix.ftabChars && (uint32_t)ix.ftabChars <= L.depth5;
+		const bool rejump = L.halfAndHalf && !L.K->disableFtab && L.rev2_0 == L.rev3_0 && i + 1 < (uint32_t)ix.ftabChars && (uint32_t)ix.ftabChars <= L.depth5;
 		uint32_t ndepth = i + 1, ntop = bttop, nbot = btbot;
 		if (rejump) {
 			/* ftab re-jump with the substituted character (ebwt_search_backtrack.h:908-952) */
@@ -731,21 +746,21 @@ BT_FN void bt_blk_btloop(BtLane &L, const BtKParams &P, const BtScratch &S) {
 #pragma unroll 1
 			for (uint32_t jj = ftabChars; jj > 0; jj--) ftabOff = (ftabOff << 2) | ((L.qlen - jj == icur) ? btcint : bt_qry(L, L.qlen - jj));
 			ntop = bt_ftab_hi(ix, ftabOff); nbot = bt_ftab_lo(ix, ftabOff + 1);
-			L.s_ftab++;
+			L.K->s_ftab++;
 			ndepth = ftabChars;
 			if (ntop == nbot) { L.ret = 0; L.pc = PC_CHILD_RET; break; }
 		}
 		/* PUSH: suspend this frame, then set up the callee */
 		F.top = L.top; F.bot = L.bot; F.eligibleSz = L.eligibleSz; F.eltop = L.eltop; F.elbot = L.elbot; F.btspread = btbot - bttop;
-		F.depth = (uint16_t)L.depth; F.d = (uint16_t)L.d; F.unrevOff = (uint16_t)L.unrevOff; F.oneRevOff = (uint16_t)L.oneRevOff;
-		F.twoRevOff = (uint16_t)L.twoRevOff; F.threeRevOff = (uint16_t)L.threeRevOff; F.ham = (uint16_t)L.ham; F.altNum = (uint16_t)L.altNum;
+		F.depth = (uint16_t)L.K->depth; F.d = (uint16_t)L.d; F.unrevOff = (uint16_t)L.unrevOff; F.oneRevOff = (uint16_t)L.K->oneRevOff;
+		F.twoRevOff = (uint16_t)L.K->twoRevOff; F.threeRevOff = (uint16_t)L.K->threeRevOff; F.ham = (uint16_t)L.ham; F.altNum = (uint16_t)L.altNum;
 		F.eligibleNum = (uint16_t)L.eligibleNum; F.eli = (uint16_t)L.eli; F.rowbase = (uint16_t)L.rowbase; F.rowd0 = (uint16_t)L.rowd0;
 		F.bt_i = (uint16_t)i; F.lowAltQual = (uint8_t)L.lowAltQual; F.elham = (uint8_t)L.elham; F.elcint = (uint8_t)L.elcint; F.bt_j = (uint8_t)j;
 		F.flags = (uint8_t)((L.elignore ? FF_ELIGNORE : 0) | (L.f_bdm ? FF_BDM : 0) | (L.f_must ? FF_MUST : 0) | (L.f_invHH ? FF_INVHH : 0) |
-		                    (L.f_invExact ? FF_INVEXACT : 0) | (L.disableFtab ? FF_DISABLEFTAB : 0));
+		                    (L.f_invExact ? FF_INVEXACT : 0) | (L.K->disableFtab ? FF_DISABLEFTAB : 0));
 		L.rowbase = L.rowbase + ((L.d >= L.rowd0) ? (L.d - L.rowd0 + 1) : 0);
-		L.stackDepth++; L.depth = ndepth; L.unrevOff = btUnrevOff; L.oneRevOff = btOneRevOff; L.twoRevOff = btTwoRevOff; L.threeRevOff = btThreeRevOff;
-		L.top = ntop; L.bot = nbot; L.ham = btham; L.disableFtab = 0;
+		L.stackDepth++; L.K->depth = ndepth; L.unrevOff = btUnrevOff; L.K->oneRevOff = btOneRevOff; L.K->twoRevOff = btTwoRevOff; L.K->threeRevOff = btThreeRevOff;
+		L.top = ntop; L.bot = nbot; L.ham = btham; L.K->disableFtab = 0;
 		L.pc = PC_FRAME_ENTER;
 		break; }
 	} while (0);
@@ -759,12 +774,12 @@ BT_FN void bt_blk_frame_ret(BtLane &L, const BtKParams &P, const BtScratch &S) {
 		const BtFrame &F = S.frames[L.stackDepth - 1];
 		L.stackDepth--;
 		L.top = F.top; L.bot = F.bot; L.eligibleSz = F.eligibleSz; L.eltop = F.eltop; L.elbot = F.elbot;
-		L.depth = F.depth; L.d = F.d; L.unrevOff = F.unrevOff; L.oneRevOff = F.oneRevOff; L.twoRevOff = F.twoRevOff; L.threeRevOff = F.threeRevOff;
+		L.K->depth = F.depth; L.d = F.d; L.unrevOff = F.unrevOff; L.K->oneRevOff = F.oneRevOff; L.K->twoRevOff = F.twoRevOff; L.K->threeRevOff = F.threeRevOff;
 		L.ham = F.ham; L.altNum = F.altNum; L.eligibleNum = F.eligibleNum; L.eli = F.eli; L.rowbase = F.rowbase; L.rowd0 = F.rowd0;
-		L.bt_i = F.bt_i; L.bt_j = F.bt_j; L.lowAltQual = F.lowAltQual; L.elham = F.elham; L.elcint = F.elcint;
+		L.K->bt_i = F.bt_i; L.K->bt_j = F.bt_j; L.lowAltQual = F.lowAltQual; L.elham = F.elham; L.elcint = F.elcint;
 		L.elignore = (F.flags & FF_ELIGNORE) != 0; L.f_bdm = (F.flags & FF_BDM) != 0; L.f_must = (F.flags & FF_MUST) != 0;
-		L.f_invHH = (F.flags & FF_INVHH) != 0; L.f_invExact = (F.flags & FF_INVEXACT) != 0; L.disableFtab = (F.flags & FF_DISABLEFTAB) != 0;
-		L.bttop = 0; L.btbot = F.btspread;
+		L.f_invHH = (F.flags & FF_INVHH) != 0; L.f_invExact = (F.flags & FF_INVEXACT) != 0; L.K->disableFtab = (F.flags & FF_DISABLEFTAB) != 0;
+		L.K->bttop = 0; L.K->btbot = F.btspread;
 		L.pc = PC_CHILD_RET;
 	}
 	} while (0);
@@ -775,12 +790,12 @@ BT_FN void bt_blk_child_ret(BtLane &L, const BtKParams &P, const BtScratch &S) {
 	do { {
 		/* after the recursive call (ebwt_search_backtrack.h:972-1064) */
 		if (L.ret) { L.pc = PC_FRAME_RET; break; }
-		if (L.bailed || (L.halfAndHalf && L.maxBts > 0 && L.numBts >= L.maxBts)) { L.bailed = 1; L.ret = 0; L.pc = PC_FRAME_RET; break; }
+		if (L.K->bailed || (L.halfAndHalf && L.K->maxBts > 0 && L.K->numBts >= L.K->maxBts)) { L.K->bailed = 1; L.ret = 0; L.pc = PC_FRAME_RET; break; }
 		{
-			const uint32_t ri = bt_row_idx(L, L.bt_i);
-			S.elims[ri] = (uint8_t)(S.elims[ri] | (1u << L.bt_j));
+			const uint32_t ri = bt_row_idx(L, L.K->bt_i);
+			S.elims[ri] = (uint8_t)(S.elims[ri] | (1u << L.K->bt_j));
 		}
-		L.eligibleSz -= (L.btbot - L.bttop);
+		L.eligibleSz -= (L.K->btbot - L.K->bttop);
 		L.eligibleNum--;
 		L.elignore = 1;
 		L.altNum--;
@@ -802,6 +817,7 @@ BT_FN void bt_blk_child_ret(BtLane &L, const BtKParams &P, const BtScratch &S) {
 					if (kq <= L.lowAltQual) {
 						const uint32_t ri = bt_row_idx(L, k);
 						const uint32_t el = S.elims[ri];
+						BT_PROF(7, 1); if (el != 15) BT_PROF(8, 1);
 						for (uint32_t l = 0; l < 4; l++) {
 							if ((el & (1u << l)) == 0) {
 								const uint32_t ptop = bt_pair_top(S, ri, l), pbot = bt_pair_bot(S, ri, l);
@@ -815,7 +831,7 @@ BT_FN void bt_blk_child_ret(BtLane &L, const BtKParams &P, const BtScratch &S) {
 						}
 					}
 				}
-				if (k == L.depth || k == 0) break;
+				if (k == L.K->depth || k == 0) break;
 			}
 		}
 		L.pc = PC_BTLOOP;
@@ -840,7 +856,7 @@ BT_FN void bt_blk_report(BtLane &L, const BtKParams &P, const BtScratch &S) {
 	do { {
 		/* reportAlignment(rep_sd, rep_top, rep_bot, rep_cost) (ebwt_search_backtrack.h:1455-1513) and the
 		 * prologue of reportFullAlignment (1522-1538) */
-		uint32_t sd = L.rep_sd;
+		uint32_t sd = L.K->rep_sd;
 		if (L.reportPartials) {
 			if (sd > 0) bt_report_partial(L, P, S, sd);
 			L.ret = 0; L.pc = PC_REPORT_RET; break;
@@ -848,12 +864,12 @@ BT_FN void bt_blk_report(BtLane &L, const BtKParams &P, const BtScratch &S) {
 		uint32_t stratum = 0;
 #pragma unroll 1
 		for (uint32_t i = 0; i < sd; i++) if (bt_mm_pos(S, i) >= (L.qlen - L.rev3_0)) stratum++;    /* calcStratum */
-		stratum += L.nmuts;
-		sd += L.nmuts;
-		if (sd == 0 && !L.reportExacts) { L.ret = 0; L.pc = PC_REPORT_RET; break; }
-		L.rep_sd = sd; L.rep_cost = (L.rep_cost & 0xffffu) | ((stratum << 14) & 0xffffu); L.rep_stratum = stratum;
-		L.rep_r = L.rep_top + (bt_rand_next(L.rnd) % (L.rep_bot - L.rep_top));
-		L.rep_i = 0;
+		stratum += L.K->nmuts;
+		sd += L.K->nmuts;
+		if (sd == 0 && !L.K->reportExacts) { L.ret = 0; L.pc = PC_REPORT_RET; break; }
+		L.K->rep_sd = sd; L.K->rep_cost = (L.K->rep_cost & 0xffffu) | ((stratum << 14) & 0xffffu); L.K->rep_stratum = stratum;
+		L.K->rep_r = L.K->rep_top + (bt_rand_next(L.K->rnd) % (L.K->rep_bot - L.K->rep_top));
+		L.K->rep_i = 0;
 		L.pc = PC_REPORT_ROW;
 	}
 	} while (0);
@@ -863,10 +879,10 @@ BT_FN void bt_blk_report_row(BtLane &L, const BtKParams &P, const BtScratch &S) 
 	const BtDevIndex &ix = P.ix[L.ebwtSel]; (void)ix;
 	do { {
 		/* loop of reportFullAlignment (ebwt_search_backtrack.h:1539-1564) */
-		const uint32_t spread = L.rep_bot - L.rep_top;
-		if (L.rep_i >= spread) { L.ret = 0; L.pc = PC_REPORT_RET; break; }
-		uint32_t ri = L.rep_r + L.rep_i;
-		if (ri >= L.rep_bot) ri -= spread;
+		const uint32_t spread = L.K->rep_bot - L.K->rep_top;
+		if (L.K->rep_i >= spread) { L.ret = 0; L.pc = PC_REPORT_RET; break; }
+		uint32_t ri = L.K->rep_r + L.K->rep_i;
+		if (ri >= L.K->rep_bot) ri -= spread;
 		L.crow = ri; L.cjumps = 0;
 		if (((ri & ix.offMask) != ri) && ri != ix.zOff) { L.pc = PC_CHASE; break; }
 		L.pc = PC_RESOLVE;
@@ -882,38 +898,38 @@ BT_FN void bt_blk_resolve(BtLane &L, const BtKParams &P, const BtScratch &S) {
 		 * fused with the Hit construction of EbwtSearchParams::reportHit (ebwt.h:1288-1405) */
 		uint32_t off;
 		if (L.crow == ix.zOff) off = L.cjumps;
-		else { off = BT_LDG(ix.offs + (L.crow >> ix.offRate)) + L.cjumps; L.s_offs++; }
+		else { off = BT_LDG(ix.offs + (L.crow >> ix.offRate)) + L.cjumps; L.K->s_offs++; }
 		uint32_t tidx = 0, toff = 0;
 		bool stop = false;
 		if (bt_joined_to_text(ix, L.qlen, off, tidx, toff)) {
 			const BtPolicy &pol = P.pol;
 			const uint32_t n = pol.allHits ? 0xffffffffu : pol.khits;
-			L.found++;
-			if (L.found > pol.mhits) stop = true;
+			L.K->found++;
+			if (L.K->found > pol.mhits) stop = true;
 			else {
-				if (L.found <= n) {
-					if (L.found <= P.slots) {
-						uint32_t *rec = P.hits + ((size_t)L.rid * P.slots + (L.found - 1)) * P.rec_words;
-						const uint32_t nmm = L.rep_sd, nsearch = nmm - L.nmuts;      /* frame-stack mismatches, then promoted seedling muts */
-						rec[0] = tidx; rec[1] = toff; rec[2] = L.rep_bot - L.rep_top - 1;
-						rec[3] = (L.rep_cost & 0xffffu) | (L.rep_stratum << 16) | (L.fw << 24);
+				if (L.K->found <= n) {
+					if (L.K->found <= P.slots) {
+						uint32_t *rec = P.hits + ((size_t)L.K->rid * P.slots + (L.K->found - 1)) * P.rec_words;
+						const uint32_t nmm = L.K->rep_sd, nsearch = nmm - L.K->nmuts;      /* frame-stack mismatches, then promoted seedling muts */
+						rec[0] = tidx; rec[1] = toff; rec[2] = L.K->rep_bot - L.K->rep_top - 1;
+						rec[3] = (L.K->rep_cost & 0xffffu) | (L.K->rep_stratum << 16) | (L.K->fw << 24);
 						rec[4] = nmm;
-						const bool flip = (ix.fw != L.fw);                          /* ebwt.h:1339-1350 */
+						const bool flip = (ix.fw != L.K->fw);                          /* ebwt.h:1339-1350 */
 #pragma unroll 1
 						for (uint32_t i = 0; i < nmm; i++) {
 							uint32_t pos, refc;
 							if (i < nsearch) { pos = S.frames[i].mm_pos; refc = S.frames[i].mm_refc; }
-							else { const uint32_t km = i - nsearch; const uint32_t mu = km == 0 ? L.mut0 : km == 1 ? L.mut1 : L.mut2; pos = mu & 0xffffu; refc = (mu >> 16) & 0xff; }
+							else { const uint32_t km = i - nsearch; const uint32_t mu = km == 0 ? L.K->mut0 : km == 1 ? L.K->mut1 : L.K->mut2; pos = mu & 0xffffu; refc = (mu >> 16) & 0xff; }
 							if (flip) pos = L.qlen - pos - 1;
 							if (i < P.mm_cap) rec[BT_HIT_HDR + i] = pos | (refc << 16); else L.flags |= BT_FLAG_MM_OVF;
 						}
 					} else L.flags |= BT_FLAG_HITS_OVF;
 				}
-				if (!pol.allHits && L.found == n && (pol.mhits == 0xffffffffu || pol.mhits < n)) stop = true;
+				if (!pol.allHits && L.K->found == n && (pol.mhits == 0xffffffffu || pol.mhits < n)) stop = true;
 			}
 		}
 		if (stop) { L.ret = 1; L.pc = PC_REPORT_RET; }
-		else { L.rep_i++; L.pc = PC_REPORT_ROW; }
+		else { L.K->rep_i++; L.pc = PC_REPORT_ROW; }
 		break; }
 	} while (0);
 }
@@ -921,7 +937,7 @@ BT_FN void bt_blk_resolve(BtLane &L, const BtKParams &P, const BtScratch &S) {
 BT_FN void bt_blk_report_ret(BtLane &L, const BtKParams &P, const BtScratch &S) {
 	const BtDevIndex &ix = P.ix[L.ebwtSel]; (void)ix;
 	do { {
-		switch (L.rep_site) {
+		switch (L.K->rep_site) {
 		case SITE_MAIN:
 			if (!L.ret) { L.top = L.bot; L.pc = PC_BTLOOP; }
 			else L.pc = PC_FRAME_RET;
@@ -939,10 +955,10 @@ BT_FN void bt_blk_bt_end(BtLane &L, const BtKParams &P, const BtScratch &S) {
 	do { {
 		/* tail of backtrack(depth, top, bot, ...) and finalize() (ebwt_search_backtrack.h:348-352, 303-324);
 		 * setMuts(NULL) of the seedling loops */
-		L.numBts = 0; L.bailed = 0;
-		if (L.nmuts > 0) bt_apply_muts(L, true);
-		if (L.reportPartials > 0 && L.npart > 0) L.ret = 1;
-		L.done = BTS_IGNORE(L.step) ? 0u : L.ret;
+		L.K->numBts = 0; L.K->bailed = 0;
+		if (L.K->nmuts > 0) bt_apply_muts(L, true);
+		if (L.reportPartials > 0 && L.K->npart > 0) L.ret = 1;
+		L.K->done = BTS_IGNORE(L.K->step) ? 0u : L.ret;
 		L.pc = PC_PHASE;
 		break; }
 	} while (0);
@@ -971,12 +987,12 @@ BT_FN void bt_rare_step(BtLane &L, const BtKParams &P, const BtScratch &S) {
 
 /* Begin a read: GET_READ (ebwt_search.cpp:923-961).  The caller points rseq/rqual at a writable copy. */
 BT_FN void bt_begin_read(BtLane &L, const BtKParams &P, uint32_t rid) {
-	L.rid = rid;
+	L.K->rid = rid;
 	L.rlen = (uint32_t)(P.roff[rid + 1] - P.roff[rid]);
-	L.seed = P.seeds[rid];
-	L.found = 0; L.flags = 0; L.ph = 0; L.done = 0; L.npart = 0; L.nmuts = 0; L.pal_i = 0; L.step = 0; L.nit = 0;
+	L.K->seed = P.seeds[rid];
+	L.K->found = 0; L.flags = 0; L.K->ph = 0; L.K->done = 0; L.K->npart = 0; L.K->nmuts = 0; L.K->pal_i = 0; L.K->step = 0; L.nit = 0;
 	L.qualThresh = P.pol.mode == 0 ? 0xffffffffu : P.pol.qualThresh;
-	L.maxBts = P.pol.mode == 0 ? 0xffffffffu : P.pol.maxBts;
+	L.K->maxBts = P.pol.mode == 0 ? 0xffffffffu : P.pol.maxBts;
 	L.maqPenalty = P.pol.mode == 0 ? 1u : (uint32_t)P.pol.maqRound;
 	L.pc = L.rlen > 0 ? PC_PHASE : PC_FINISH_READ;
 }
@@ -984,9 +1000,9 @@ BT_FN void bt_begin_read(BtLane &L, const BtKParams &P, uint32_t rid) {
 /* HitSinkPerThread::finishRead (hit.h:741-786): the host applies -m suppression / -k truncation
  * from `found`; the kernel stored the first min(found, n, slots) hits. */
 BT_FN void bt_finish_read(BtLane &L, const BtKParams &P) {
-	if (L.flags & BT_FLAG_RETRY) L.found = 0;          /* re-run by a later pass */
-	P.found[L.rid] = L.found;
-	P.flags[L.rid] = L.flags;
+	if (L.flags & BT_FLAG_RETRY) L.K->found = 0;          /* re-run by a later pass */
+	P.found[L.K->rid] = L.K->found;
+	P.flags[L.K->rid] = L.flags;
 }
 
 /* A fast transition with its fetch stage: the rank block(s) of the pending LF / chase step plus the
@@ -1099,7 +1115,7 @@ BT_FN void bt_rare_iter(BtLane &L, const BtKParams &P, const BtScratch &S, const
 #pragma unroll 1
 	for (int r = 0; r < BT_SWEEP_ROUNDS && BT_IS_RARE_STEP(L.pc); r++) {
 		if (L.flags & BT_FLAG_SCRATCH_OVF) { L.pc = PC_FINISH_READ; break; }
-		if ((budget && L.nit > budget) || (P.slot_ctx && !P.resume && L.npart >= P.PCAP)) {                  /* heavy read, or its seedling list is full */
+		if ((budget && L.nit > budget) || (P.slot_ctx && !P.resume && L.K->npart >= P.PCAP)) {                  /* heavy read, or its seedling list is full */
 			if (P.slot_ctx) L.flags |= BT_FLAG_PREEMPT;                                                    /* suspended as it is: the state stays put */
 			else { L.flags |= BT_FLAG_BUDGET; L.pc = PC_FINISH_READ; }
 			break;
@@ -1123,12 +1139,12 @@ BT_FN void bt_rare_iter(BtLane &L, const BtKParams &P, const BtScratch &S, const
 	}
 #undef BT_STEP
 	/* a report in the last round may have filled the seedling list and the lane left for a fast state: the next position could report again */
-	if (P.slot_ctx && !P.resume && L.npart >= P.PCAP && L.pc != PC_FINISH_READ) L.flags |= BT_FLAG_PREEMPT;
+	if (P.slot_ctx && !P.resume && L.K->npart >= P.PCAP && L.pc != PC_FINISH_READ) L.flags |= BT_FLAG_PREEMPT;
 #else
 #pragma unroll 1
 	for (int k = 0; k < BT_RARE_CHAIN && BT_IS_RARE_STEP(L.pc); k++) {
 		if (L.flags & BT_FLAG_SCRATCH_OVF) { L.pc = PC_FINISH_READ; break; }
-		if ((budget && L.nit > budget) || (P.slot_ctx && !P.resume && L.npart >= P.PCAP)) {
+		if ((budget && L.nit > budget) || (P.slot_ctx && !P.resume && L.K->npart >= P.PCAP)) {
 			if (P.slot_ctx) L.flags |= BT_FLAG_PREEMPT;
 			else { L.flags |= BT_FLAG_BUDGET; L.pc = PC_FINISH_READ; }
 			break;
@@ -1136,7 +1152,7 @@ BT_FN void bt_rare_iter(BtLane &L, const BtKParams &P, const BtScratch &S, const
 		L.s_iter++; L.nit++;
 		bt_rare_step(L, P, S);
 	}
-	if (P.slot_ctx && !P.resume && L.npart >= P.PCAP && L.pc != PC_FINISH_READ) L.flags |= BT_FLAG_PREEMPT;
+	if (P.slot_ctx && !P.resume && L.K->npart >= P.PCAP && L.pc != PC_FINISH_READ) L.flags |= BT_FLAG_PREEMPT;
 #endif
 }
 BT_FN void bt_rare_iter(BtLane &L, const BtKParams &P, const BtScratch &S) { bt_rare_iter(L, P, S, P.budget); }

@@ -57,7 +57,7 @@ __global__ void bt_debug_lf_kernel(BtDevIndex ix, const uint32_t *rows, uint32_t
 #define BT_THREADS 128
 #endif
 #ifndef BT_MIN_BLOCKS
-#define BT_MIN_BLOCKS 3            /* register cap = 65536 / (128 * BT_MIN_BLOCKS) */
+#define BT_MIN_BLOCKS 4            /* register cap = 65536 / (128 * BT_MIN_BLOCKS): 128 registers with the cold lane state in shared memory */
 #endif
 #ifndef BT_RARE_PERIOD
 #define BT_RARE_PERIOD 8           /* rare transitions run at least every BT_RARE_PERIOD-th iteration ... */
@@ -72,8 +72,21 @@ __global__ void bt_debug_lf_kernel(BtDevIndex ix, const uint32_t *rows, uint32_t
 #define BT_Q_THREADS 384            /* worker threads per block                                               */
 #endif
 #define BT_SMEM_LEN 128            /* reads up to this length are staged in shared memory                   */
-#define BT_SMEM_SNAP (2 * BT_SMEM_LEN)          /* 6 words: the lane's operation counters when its current read began    */
-#define BT_SMEM_STRIDE (2 * BT_SMEM_LEN + 28)  /* 71 words per lane (odd): lanes' equal offsets fall in different banks */
+#ifndef BT_COLD_SMEM
+#define BT_COLD_SMEM 1             /* the rare transitions' part of the lane state (BtLaneCold) lives in shared memory, not in registers */
+#endif
+/* A lane's shared-memory area: its writable copy of the read's bases (seedling mutations are applied to it), the 6 operation counters
+ * snapped when its current read began, and — BT_COLD_SMEM — its BtLaneCold.  Qualities are never written, so they are read in place
+ * from the batch (L1-resident: 100 bytes per read, fetched a position ahead of their use).  The stride is an odd number of words:
+ * lanes' equal offsets fall in different banks. */
+#define BT_SMEM_SNAP BT_SMEM_LEN
+#define BT_SMEM_COLD (BT_SMEM_LEN + 24)
+#if BT_COLD_SMEM
+#define BT_SMEM_STRIDE ((BT_SMEM_LEN + 24 + (uint32_t)sizeof(BtLaneCold) + 4) | 4u)
+#else
+#define BT_SMEM_STRIDE (BT_SMEM_LEN + 28)
+#endif
+static_assert((BT_SMEM_STRIDE / 4) % 2 == 1 && BT_SMEM_STRIDE % 4 == 0, "odd word stride");
 
 struct BtWorkCtl { unsigned long long next; unsigned long long nwork; };
 
@@ -100,10 +113,15 @@ bt_search_kernel(BtKParams P, BtWorkCtl *ctl) {
 	} else S.rows = nullptr, S.elims = nullptr, S.frames = nullptr, S.partials = nullptr;      /* a slice works in the slot's scratch */
 	uint32_t my_slot = 0;
 	BtLane L;
+#if BT_COLD_SMEM
+	L.K = reinterpret_cast<BtLaneCold *>(my_stage + BT_SMEM_COLD);
+#else
+	BtLaneCold cold_regs; L.K = &cold_regs;
+#endif
 	L.pc = PC_NEXT_READ;
-	L.s_lfex = L.s_lf = L.s_chase = L.s_ftab = L.s_offs = L.s_bt = L.s_iter = L.s_blk = 0;
-	L.nmuts = 0; L.mut0 = L.mut1 = L.mut2 = 0; L.ebwtSel = 0; L.lfk = 0; L.ltop = L.lbot = L.crow = 0; L.flags = 0; L.d = 0; L.qlen = 0;
-	L.rlen = 0; L.rseq = my_stage; L.rqual = my_stage + BT_SMEM_LEN; L.hasN = 1; L.step = 0;
+	L.s_lfex = L.s_lf = L.s_chase = L.K->s_ftab = L.K->s_offs = L.K->s_bt = L.s_iter = L.s_blk = 0;
+	L.K->nmuts = 0; L.K->mut0 = L.K->mut1 = L.K->mut2 = 0; L.ebwtSel = 0; L.lfk = 0; L.ltop = L.lbot = L.crow = 0; L.flags = 0; L.d = 0; L.qlen = 0;
+	L.rlen = 0; L.rseq = my_stage; L.rqual = my_stage; L.K->hasN = 1; L.K->step = 0;
 	unsigned long long nwork = ctl->nwork;
 	if (P.resume && nwork > P.nslot) nwork = P.nslot;                 /* the main pass counts past the last slot (those reads are re-run) */
 	/* Once the work queue is empty a pass only waits for its slowest reads while most lanes idle — with a per-read budget of 8000
@@ -140,7 +158,7 @@ bt_search_kernel(BtKParams P, BtWorkCtl *ctl) {
 					/* this read is re-run from scratch by a later pass: its operations so far are not part of the algorithm's
 					 * count (SURVEY.md §8d counts each read's side fetches once) */
 					const uint32_t *snap = reinterpret_cast<const uint32_t *>(my_stage + BT_SMEM_SNAP);
-					L.s_lfex = snap[0]; L.s_lf = snap[1]; L.s_chase = snap[2]; L.s_ftab = snap[3]; L.s_offs = snap[4]; L.s_blk = snap[5];
+					L.s_lfex = snap[0]; L.s_lf = snap[1]; L.s_chase = snap[2]; L.K->s_ftab = snap[3]; L.K->s_offs = snap[4]; L.s_blk = snap[5];
 				}
 				bt_finish_read(L, P); L.pc = PC_NEXT_READ;
 			}
@@ -167,7 +185,7 @@ bt_search_kernel(BtKParams P, BtWorkCtl *ctl) {
 							got = true;
 						}
 						uint32_t *snap = reinterpret_cast<uint32_t *>(my_stage + BT_SMEM_SNAP);
-						snap[0] = L.s_lfex; snap[1] = L.s_lf; snap[2] = L.s_chase; snap[3] = L.s_ftab; snap[4] = L.s_offs; snap[5] = L.s_blk;
+						snap[0] = L.s_lfex; snap[1] = L.s_lf; snap[2] = L.s_chase; snap[3] = L.K->s_ftab; snap[4] = L.K->s_offs; snap[5] = L.s_blk;
 					} else L.pc = PC_EXIT;
 				}
 				if (P.drain_budget && budget > P.drain_budget && __ballot_sync(0xffffffffu, want && !took)) budget = P.drain_budget;
@@ -184,12 +202,11 @@ bt_search_kernel(BtKParams P, BtWorkCtl *ctl) {
 						if (idx < rl) {
 							const uint8_t b = __ldg(P.seq + rj + idx);
 							dst[idx] = b;
-							dst[BT_SMEM_LEN + idx] = __ldg(P.qual + rj + idx);
 							sawN |= (b == 4);
 						}
 					}
 					const unsigned nm = __ballot_sync(0xffffffffu, sawN);
-					if ((int)lane == j) { L.rseq = my_stage; L.rqual = my_stage + BT_SMEM_LEN; L.hasN = (nm != 0); }
+					if ((int)lane == j) { L.rseq = my_stage; L.rqual = const_cast<uint8_t *>(P.qual + rj); L.K->hasN = (nm != 0); }
 				}
 				if (got && L.rlen > BT_SMEM_LEN) {
 					/* long read: private copy in global scratch */
@@ -200,7 +217,7 @@ bt_search_kernel(BtKParams P, BtWorkCtl *ctl) {
 						dst[k] = b; dst[P.stage_len + k] = __ldg(P.qual + ro + k);
 						sawN |= (b == 4);
 					}
-					L.rseq = dst; L.rqual = dst + P.stage_len; L.hasN = sawN;
+					L.rseq = dst; L.rqual = dst + P.stage_len; L.K->hasN = sawN;
 				}
 				__syncwarp();
 			}
@@ -214,7 +231,7 @@ bt_search_kernel(BtKParams P, BtWorkCtl *ctl) {
 					P.slice_out[atomicAdd(P.slice_count, 1ull)] = my_slot;
 				} else {
 					const unsigned long long p = atomicAdd(P.slice_count, 1ull);
-					if (p < P.nslot) { bt_slot_save_new(L, P, S, (uint32_t)p); P.flags[L.rid] = 0; P.found[L.rid] = 0; }
+					if (p < P.nslot) { bt_slot_save_new(L, P, S, (uint32_t)p); P.flags[L.K->rid] = 0; P.found[L.K->rid] = 0; }
 					else kept = false;
 				}
 				if (kept) L.pc = PC_NEXT_READ;
@@ -235,7 +252,7 @@ bt_search_kernel(BtKParams P, BtWorkCtl *ctl) {
 #endif
 	}
 	/* statistics: warp-reduce, one atomic per warp and counter */
-	unsigned long long v[8] = { L.s_lfex, L.s_lf, L.s_chase, L.s_ftab, L.s_offs, L.s_bt, L.s_iter, L.s_blk };
+	unsigned long long v[8] = { L.s_lfex, L.s_lf, L.s_chase, L.K->s_ftab, L.K->s_offs, L.K->s_bt, L.s_iter, L.s_blk };
 #pragma unroll
 	for (int k = 0; k < 8; k++) {
 		unsigned long long x = v[k];
@@ -295,10 +312,11 @@ bt_search_kernel_q(BtKParams P, BtWorkCtl *ctl, uint32_t nctx) {
 		ctx[(size_t)25 * nctx + i] = 0;
 	}
 	__syncthreads();
-	BtLane L;
-	memset(&L, 0, sizeof L);
+	BtLane L; BtLaneCold cold;
+	memset(&L, 0, sizeof L); memset(&cold, 0, sizeof cold);
+	L.K = &cold;
 	L.qualThresh = P.pol.mode == 0 ? 0xffffffffu : P.pol.qualThresh;
-	L.maxBts = P.pol.mode == 0 ? 0xffffffffu : P.pol.maxBts;
+	L.K->maxBts = P.pol.mode == 0 ? 0xffffffffu : P.pol.maxBts;
 	L.maqPenalty = P.pol.mode == 0 ? 1u : (uint32_t)P.pol.maqRound;
 	volatile uint32_t *vhead = Q->head, *vtail = Q->tail;
 	volatile uint32_t *vlive = &Q->live;
@@ -353,7 +371,7 @@ bt_search_kernel_q(BtKParams P, BtWorkCtl *ctl, uint32_t nctx) {
 							dst[i] = b; dst[qoff + i] = __ldg(P.qual + ro + i);
 							sawN |= (b == 4);
 						}
-						L.rseq = dst; L.rqual = dst + qoff; L.hasN = sawN;
+						L.rseq = dst; L.rqual = dst + qoff; L.K->hasN = sawN;
 					} else L.pc = PC_EXIT;
 				}
 			} else {
@@ -383,7 +401,7 @@ bt_search_kernel_q(BtKParams P, BtWorkCtl *ctl, uint32_t nctx) {
 		}
 	}
 	/* statistics: warp-reduce, one atomic per warp and counter */
-	unsigned long long v[8] = { L.s_lfex, L.s_lf, L.s_chase, L.s_ftab, L.s_offs, L.s_bt, L.s_iter, L.s_blk };
+	unsigned long long v[8] = { L.s_lfex, L.s_lf, L.s_chase, L.K->s_ftab, L.K->s_offs, L.K->s_bt, L.s_iter, L.s_blk };
 #pragma unroll
 	for (int kk = 0; kk < 8; kk++) {
 		unsigned long long x = v[kk];
@@ -922,8 +940,11 @@ static int enqueue_align(bt_context *cx, const bt_policy_t *pol, const bt_read_b
 	/* checkpoint slots: one per suspended read.  On the bench workload 0.7 % of the reads exceed the main budget and 0.3 % fill the
 	 * 64-seedling list; slots for 1/32 of the batch (BT_SLOT_DIV), at least 4096.  A read that finds none is re-run by the overflow pass. */
 	static const uint32_t slot_div = env_u32("BT_SLOT_DIV", 32), slot_pcap = env_u32("BT_SLOT_PCAP", 1024);
-	static const bool use_slots = env_u32("BT_SLICES", 6) > 0 && !main_kernel_is_queue();
-	static const uint32_t nslices = env_u32("BT_SLICES", 6) > BT_SLICES_MAX ? BT_SLICES_MAX : env_u32("BT_SLICES", 6);
+	/* BT_SLICES=n (default 0: off) turns the slices on.  Measured on the hg19-sized index (profiles/README.md, call 6): a read is sequential,
+	 * so every slice lasts as long as its longest resumed read runs, the slices of a batch are serialised behind each other, and their
+	 * 128-thread blocks stay resident around single surviving lanes — 3.3 M reads/s against 5.1 M for the restart tail below. */
+	static const bool use_slots = env_u32("BT_SLICES", 0) > 0 && !main_kernel_is_queue();
+	static const uint32_t nslices = env_u32("BT_SLICES", 0) > BT_SLICES_MAX ? BT_SLICES_MAX : env_u32("BT_SLICES", 0);
 	uint32_t nslot = nwork / (slot_div ? slot_div : 32); if (nslot < 4096) nslot = 4096; if (nslot > nwork) nslot = nwork;
 	if (use_slots) {
 		if (ensure_ws(cx->wsl, nslot, 6 * maxlen + 8, 16, slot_pcap, stage_len)) return 1;
@@ -938,7 +959,7 @@ static int enqueue_align(bt_context *cx, const bt_policy_t *pol, const bt_read_b
 	} else {
 		/* no slots (BT_SLICES=0, or the queue kernel): the tail pass re-runs heavy reads from scratch on full-size scratch */
 		static const uint32_t tail_bps = env_u32("BT_TAIL_BLOCKS", 2);
-		if (ensure_ws(cx->wsh, (uint32_t)ix->sms * tail_bps * 128, 6 * maxlen + 8, 16, 4096, stage_len)) return 1;
+		if (ensure_ws(cx->wsh, (uint32_t)ix->sms * tail_bps * BT_THREADS, 6 * maxlen + 8, 16, 4096, stage_len)) return 1;
 	}
 	const uint32_t nthreads2 = (uint32_t)ix->sms * 32;
 	uint32_t R2 = maxlen * maxlen + 8; if (R2 > 65000) R2 = 65000;   /* BtFrame::rowbase is 16 bits */
@@ -1011,7 +1032,13 @@ static int enqueue_align(bt_context *cx, const bt_policy_t *pol, const bt_read_b
 		bt_collect_kernel<<<cblocks, 256, 0, cx->side>>>(out->flags, in->sel, nwork, nullptr, BT_FLAG_RETRY, cx->heavy_sel, ctl_slice);
 		set_ws(P, cx->wsh);
 		P.sel = cx->heavy_sel; P.budget = 0; P.drain_budget = 0;
-		bt_search_kernel<<<cx->wsh.nthreads / BT_THREADS, BT_THREADS, BT_THREADS * BT_SMEM_STRIDE, cx->side>>>(P, ctl_slice);
+		{
+			/* the tail's blocks may be smaller than the main pass's: a block lives as long as its slowest read, and what a straggler pins
+			 * (registers and shared memory of its whole block) is what the other batches' main passes cannot use meanwhile */
+			static const uint32_t tt = env_u32("BT_TAIL_THREADS", BT_THREADS);
+			const uint32_t threads = (tt >= 32 && tt <= BT_THREADS && tt % 32 == 0) ? tt : BT_THREADS;
+			bt_search_kernel<<<cx->wsh.nthreads / threads, threads, threads * BT_SMEM_STRIDE, cx->side>>>(P, ctl_slice);
+		}
 		bt_collect_kernel<<<cblocks, 256, 0, cx->side>>>(out->flags, cx->heavy_sel, nwork, ctl_slice, BT_FLAG_SCRATCH_OVF, cx->retry_sel, ctl_ovf);
 	}
 	P.sel = cx->retry_sel; P.budget = 0; P.drain_budget = 0;

@@ -78,14 +78,14 @@ static int run(bt_index *ix, const bt_policy_t *pol, const bt_read_batch_t *in, 
 	std::vector<uint4> rows(2 * (size_t)R); std::vector<uint8_t> elims(R), stage; std::vector<BtFrame> frames(maxlen + 2); std::vector<uint64_t> parts(1 << 16);
 	P.R = R; P.FCAP = maxlen + 2; P.PCAP = 1 << 16;
 	BtScratch S = { rows.data(), elims.data(), frames.data(), parts.data() };
-	BtLane L; memset(&L, 0, sizeof L);
+	BtLane L; BtLaneCold LK; memset(&L, 0, sizeof L); memset(&LK, 0, sizeof LK); L.K = &LK;
 	const uint32_t nwork = in->sel ? in->nsel : in->nreads;
 	for (uint32_t w = 0; w < nwork; w++) {
 		uint32_t r = in->sel ? in->sel[w] : w;
 		bt_begin_read(L, P, r);
 		stage.assign(2 * (size_t)L.rlen + 2, 0);
 		memcpy(stage.data(), in->seq + in->offs[r], L.rlen); memcpy(stage.data() + L.rlen, in->qual + in->offs[r], L.rlen);
-		L.rseq = stage.data(); L.rqual = stage.data() + L.rlen; L.hasN = memchr(stage.data(), 4, L.rlen) != NULL;
+		L.rseq = stage.data(); L.rqual = stage.data() + L.rlen; L.K->hasN = memchr(stage.data(), 4, L.rlen) != NULL;
 		while (L.pc != PC_FINISH_READ) { if (BT_IS_FAST(L.pc)) bt_fast_iter(L, P, S); else bt_rare_iter(L, P, S); }
 		bt_finish_read(L, P);
 	}

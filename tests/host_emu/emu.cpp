@@ -65,7 +65,7 @@ int emu_align(void *fwp, void *bwp, const BtPolicy *pol, uint32_t nreads, const 
 	P.R = R; P.FCAP = FCAP; P.PCAP = PCAP;
 	BtScratch S = { rows.data(), elims.data(), frames.data(), parts.data() };
 	bt_build_prog(pol->mode, pol->mms, pol->nofw, pol->norc, P.prog);
-	BtLane L; memset(&L, 0, sizeof L);
+	BtLane L; BtLaneCold LK; memset(&L, 0, sizeof L); memset(&LK, 0, sizeof LK); L.K = &LK;
 	std::vector<uint8_t> stage;
 	/* BT_EMU_PC_HIST=1: how many transitions of each kind the batch took (where a lane's iterations go; development aid) */
 	static unsigned long long hist_store[40];
@@ -78,7 +78,7 @@ int emu_align(void *fwp, void *bwp, const BtPolicy *pol, uint32_t nreads, const 
 		memcpy(stage.data(), seq + roff[r], L.rlen);
 		memcpy(stage.data() + L.rlen, qual + roff[r], L.rlen);
 		L.rseq = stage.data(); L.rqual = stage.data() + L.rlen;
-		L.hasN = memchr(stage.data(), 4, L.rlen) != NULL;
+		L.K->hasN = memchr(stage.data(), 4, L.rlen) != NULL;
 		unsigned long long guard = 0; uint32_t it0 = L.s_iter;
 		while (L.pc != PC_FINISH_READ) {
 			if (pc_hist) { pc_hist[L.pc < 32 ? L.pc : 31]++; if (L.pc == PC_LF) lfk_hist[L.lfk & 7]++; }
@@ -97,7 +97,7 @@ int emu_align(void *fwp, void *bwp, const BtPolicy *pol, uint32_t nreads, const 
 		static const char *lk[] = { "EX", "ONE", "PAIR", "FCHR", "NONE" };
 		for (int i = 0; i < 5; i++) fprintf(stderr, "  LF kind %-5s %8.2f per read\n", lk[i], (double)lfk_hist[i] / nreads);
 	}
-	stats[0] = L.s_lfex; stats[1] = L.s_lf; stats[2] = L.s_chase; stats[3] = L.s_ftab; stats[4] = L.s_offs; stats[5] = L.s_bt; stats[6] = L.s_iter; stats[7] = L.s_blk;
+	stats[0] = L.s_lfex; stats[1] = L.s_lf; stats[2] = L.s_chase; stats[3] = L.K->s_ftab; stats[4] = L.K->s_offs; stats[5] = L.K->s_bt; stats[6] = L.s_iter; stats[7] = L.s_blk;
 	return 0;
 }
 
@@ -124,7 +124,7 @@ int emu_align_sliced(void *fwp, void *bwp, const BtPolicy *pol, uint32_t nreads,
 	P.slot_ctx = sctx.data(); P.slot_rows = srows.data(); P.slot_elims = selims.data(); P.slot_frames = sframes.data(); P.slot_partials = sparts.data();
 	P.slot_stage = sstage.data(); P.nslot = 1; P.slot_R = R; P.slot_FCAP = slotFCAP; P.slot_PCAP = slotPCAP; P.slot_stage_len = maxlen;
 	bt_build_prog(pol->mode, pol->mms, pol->nofw, pol->norc, P.prog);
-	BtLane L; memset(&L, 0, sizeof L);
+	BtLane L; BtLaneCold LK; memset(&L, 0, sizeof L); memset(&LK, 0, sizeof LK); L.K = &LK;
 	std::vector<uint8_t> stage;
 	*nsusp = 0;
 	for (uint32_t r = 0; r < nreads; r++) {
@@ -136,7 +136,7 @@ int emu_align_sliced(void *fwp, void *bwp, const BtPolicy *pol, uint32_t nreads,
 		memcpy(stage.data(), seq + roff[r], L.rlen);
 		memcpy(stage.data() + L.rlen, qual + roff[r], L.rlen);
 		L.rseq = stage.data(); L.rqual = stage.data() + L.rlen;
-		L.hasN = memchr(stage.data(), 4, L.rlen) != NULL;
+		L.K->hasN = memchr(stage.data(), 4, L.rlen) != NULL;
 		unsigned long long guard = 0;
 		while (L.pc != PC_FINISH_READ) {
 			if (BT_IS_FAST(L.pc)) bt_fast_iter(L, P, S); else bt_rare_iter(L, P, S, budget);
@@ -145,9 +145,9 @@ int emu_align_sliced(void *fwp, void *bwp, const BtPolicy *pol, uint32_t nreads,
 				if (!P.resume) bt_slot_save_new(L, P, S, 0); else bt_ctx_store(L, P.slot_ctx, 1, 0);
 				(*nsusp)++;
 				/* nothing of the lane or of the main pass's scratch survives, except the lane's operation counters */
-				uint32_t keep[8] = { L.s_lfex, L.s_lf, L.s_chase, L.s_ftab, L.s_offs, L.s_bt, L.s_iter, L.s_blk };
-				memset(&L, 0xCD, sizeof L);
-				L.s_lfex = keep[0]; L.s_lf = keep[1]; L.s_chase = keep[2]; L.s_ftab = keep[3]; L.s_offs = keep[4]; L.s_bt = keep[5]; L.s_iter = keep[6]; L.s_blk = keep[7];
+				uint32_t keep[8] = { L.s_lfex, L.s_lf, L.s_chase, L.K->s_ftab, L.K->s_offs, L.K->s_bt, L.s_iter, L.s_blk };
+				memset(&L, 0xCD, sizeof L); memset(&LK, 0xCD, sizeof LK); L.K = &LK;
+				L.s_lfex = keep[0]; L.s_lf = keep[1]; L.s_chase = keep[2]; L.K->s_ftab = keep[3]; L.K->s_offs = keep[4]; L.K->s_bt = keep[5]; L.s_iter = keep[6]; L.s_blk = keep[7];
 				memset(rows.data(), 0xCD, rows.size() * sizeof(uint4)); memset(elims.data(), 0xCD, elims.size());
 				memset(frames.data(), 0xCD, frames.size() * sizeof(BtFrame)); memset(parts.data(), 0xCD, parts.size() * 8);
 				memset(stage.data(), 0xCD, stage.size());
@@ -159,7 +159,7 @@ int emu_align_sliced(void *fwp, void *bwp, const BtPolicy *pol, uint32_t nreads,
 		}
 		bt_finish_read(L, P);
 	}
-	stats[0] = L.s_lfex; stats[1] = L.s_lf; stats[2] = L.s_chase; stats[3] = L.s_ftab; stats[4] = L.s_offs; stats[5] = L.s_bt; stats[6] = L.s_iter; stats[7] = L.s_blk;
+	stats[0] = L.s_lfex; stats[1] = L.s_lf; stats[2] = L.s_chase; stats[3] = L.K->s_ftab; stats[4] = L.K->s_offs; stats[5] = L.K->s_bt; stats[6] = L.s_iter; stats[7] = L.s_blk;
 	return 0;
 }
 
@@ -182,13 +182,13 @@ int emu_warp_sim(void *fwp, void *bwp, const BtPolicy *pol, uint32_t nreads, con
 	P.R = R; P.FCAP = FCAP; P.PCAP = PCAP; P.rare_period = rare_period ? rare_period : 1; P.rare_thresh = rare_thresh; P.budget = budget;
 	bt_build_prog(pol->mode, pol->mms, pol->nofw, pol->norc, P.prog);
 	const uint32_t nl = nwarps * 32;
-	std::vector<BtLane> lanes(nl);
+	std::vector<BtLane> lanes(nl); std::vector<BtLaneCold> colds(nl);
 	std::vector<std::vector<uint4>> rows(nl); std::vector<std::vector<uint8_t>> elims(nl), stage(nl); std::vector<std::vector<BtFrame>> frames(nl); std::vector<std::vector<uint64_t>> parts(nl);
 	std::vector<BtScratch> S(nl);
 	for (uint32_t i = 0; i < nl; i++) {
 		rows[i].resize(2 * (size_t)R); elims[i].resize(R); frames[i].resize(FCAP); parts[i].resize(PCAP);
 		S[i] = BtScratch{ rows[i].data(), elims[i].data(), frames[i].data(), parts[i].data() };
-		memset(&lanes[i], 0, sizeof(BtLane)); lanes[i].pc = PC_NEXT_READ; lanes[i].hasN = 1;
+		memset(&lanes[i], 0, sizeof(BtLane)); memset(&colds[i], 0, sizeof(BtLaneCold)); lanes[i].K = &colds[i]; lanes[i].pc = PC_NEXT_READ; lanes[i].K->hasN = 1;
 	}
 	const int rule = getenv("BT_SIM_RULE") ? atoi(getenv("BT_SIM_RULE")) : 0;
 	const int unify = getenv("BT_SIM_UNIFIED") ? atoi(getenv("BT_SIM_UNIFIED")) : 0;   /* 1: one code path for the three LF kinds; 2: the chase step shares it too */
@@ -223,7 +223,7 @@ int emu_warp_sim(void *fwp, void *bwp, const BtPolicy *pol, uint32_t nreads, con
 							std::vector<uint8_t> &st = stage[w * 32 + l];
 							st.assign(2 * (size_t)X.rlen + 2, 0);
 							memcpy(st.data(), seq + roff[rid], X.rlen); memcpy(st.data() + X.rlen, qual + roff[rid], X.rlen);
-							X.rseq = st.data(); X.rqual = st.data() + X.rlen; X.hasN = memchr(st.data(), 4, X.rlen) != NULL;
+							X.rseq = st.data(); X.rqual = st.data() + X.rlen; X.K->hasN = memchr(st.data(), 4, X.rlen) != NULL;
 						} else X.pc = PC_EXIT;
 						pcs |= 1u << 31;
 					}

@@ -25,3 +25,4 @@ import ctypes
 emu.L.emu_prof.restype = ctypes.POINTER(ctypes.c_ulonglong)
 pr = emu.L.emu_prof()
 print("per read: BTLOOP %.2f (scans %.2f, scan positions %.2f) CHILD_RET %.2f (rescans %.2f, rescan positions %.2f)" % tuple(pr[i] / n for i in range(6)))
+print("per read: scan positions with live alternatives %.2f; rescan positions at <= lowest quality %.2f, of which live %.2f" % tuple(pr[i] / n for i in (6, 7, 8)))
