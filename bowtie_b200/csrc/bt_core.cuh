@@ -37,7 +37,7 @@
 
 #if defined(__CUDACC__)
 #define BT_FN __device__ __forceinline__
-#define BT_NOINLINE __device__ __noinline__
+#define BT_NOINLINE static __device__ __noinline__
 #define BT_LDG(p) __ldg(p)
 #define BT_POPC64(x) __popcll(x)
 #define BT_POPC32(x) ((uint32_t)__popc(x))
@@ -150,6 +150,7 @@ struct BtKParams {
 	uint64_t *partials;           /* PCAP                                                     */
 	uint8_t *stage;               /* 2 * stage_len bytes: writable copy of the read (long reads) */
 	uint32_t R, FCAP, PCAP, stage_len;
+	uint32_t mask_rows;           /* rows (of 256 bits) that every frame reserves below its rowbase for its live-position mask (bt_live_mask) */
 	uint32_t budget;              /* per-read transition budget of this pass (0 = unlimited)  */
 	uint32_t drain_budget;        /* ... once the pass's work queue is empty (0 = the same)    */
 	uint32_t rare_period, rare_thresh;   /* deferral of rare transitions in the thread-per-lane kernel */
@@ -334,6 +335,18 @@ BT_FN uint32_t bt_row_idx(const BtLane &L, uint32_t d) { return L.rowbase + (d -
 BT_FN uint32_t bt_pair_top(const BtScratch &S, uint32_t ri, uint32_t c) { const uint32_t *p = (const uint32_t *)(S.rows + 2 * (size_t)ri); return p[c]; }
 BT_FN uint32_t bt_pair_bot(const BtScratch &S, uint32_t ri, uint32_t c) { const uint32_t *p = (const uint32_t *)(S.rows + 2 * (size_t)ri); return p[4 + c]; }
 BT_FN uint32_t bt_mm_pos(const BtScratch &S, uint32_t k) { return S.frames[k].mm_pos; }
+/* The frame's live-position mask: bit (k - rowd0) is set for the positions k of the current frame that were recorded with at least one
+ * alternative of non-zero width (the only positions the backtrack-target scan and the next-lowest-quality re-scan can ever select —
+ * ebwt_search_backtrack.h:760-800, 1004-1058 walk ALL positions of the frame and skip the others one by one).  It lives in the
+ * P.mask_rows rows below the frame's rowbase, so pushing / popping a frame, suspending a read and the lane state need nothing new. */
+BT_FN uint32_t *bt_live_mask(const BtLane &L, const BtKParams &P, const BtScratch &S) { return (uint32_t *)(S.rows + 2 * (size_t)(L.rowbase - P.mask_rows)); }
+BT_FN uint32_t bt_clz32(uint32_t x) {
+#if defined(__CUDA_ARCH__)
+	return (uint32_t)__clz((int)x);
+#else
+	return x ? (uint32_t)__builtin_clz(x) : 32u;
+#endif
+}
 
 /* ---- the phase interpreter (program built by bt_build_prog): GET_READ .. search_*.c .. ----------
  * Leaves L.pc = PC_BT_BEGIN with a configured backtracker, or PC_FINISH_READ. */
@@ -485,6 +498,7 @@ BT_FN void bt_position(BtLane &L, const BtKParams &P, const BtScratch &S,
 			el = ~nz & 15u;
 			const uint32_t n = BT_POPC32(nz);
 			L.altNum += n;
+			if (n) { uint32_t *lm = bt_live_mask(L, P, S) + ((d - L.rowd0) >> 5); *lm |= 1u << ((d - L.rowd0) & 31u); }
 			if (L.curIsElig && n) {
 				if (L.curOverrides) {
 					const uint32_t f = (nz & 1u) ? 0u : (nz & 2u) ? 1u : (nz & 4u) ? 2u : 3u;
@@ -519,6 +533,7 @@ BT_FN void bt_position(BtLane &L, const BtKParams &P, const BtScratch &S,
 					L.altNum++;
 				}
 			}
+			if (el != 15u) { uint32_t *lm = bt_live_mask(L, P, S) + ((d - L.rowd0) >> 5); *lm |= 1u << ((d - L.rowd0) & 31u); }
 		}
 #endif
 		S.elims[ri] = (uint8_t)el;
@@ -628,7 +643,7 @@ BT_FN void bt_blk_bt_begin(BtLane &L, const BtKParams &P, const BtScratch &S) {
 		if (!ok) { L.ret = 0; L.pc = PC_BT_END; break; }
 		/* the new root frame: backtrack(0, depth, _unrevOff, _1revOff, _2revOff, _3revOff, top, bot, iham, iham, ...) */
 		L.stackDepth = 0; L.K->depth = 0; L.unrevOff = L.K->unrev0; L.K->oneRevOff = L.K->rev1_0; L.K->twoRevOff = L.rev2_0; L.K->threeRevOff = L.rev3_0;
-		L.top = 0; L.bot = 0; L.ham = L.K->iham; L.rowbase = 0; L.K->disableFtab = nsInFtab > 0;
+		L.top = 0; L.bot = 0; L.ham = L.K->iham; L.rowbase = P.mask_rows; L.K->disableFtab = nsInFtab > 0;
 		L.pc = PC_FRAME_ENTER;
 		const uint32_t mlim = L.K->unrev0 < L.qlen ? L.K->unrev0 : L.qlen;
 		if (nsInFtab == 0 && mlim >= ftabChars) {
@@ -658,6 +673,11 @@ BT_FN void bt_blk_frame_enter(BtLane &L, const BtKParams &P, const BtScratch &S)
 		if (L.top != 0 || L.bot != 0) { L.ltop = L.top; L.lbot = L.bot; }
 		if (L.stackDepth > 0) L.K->s_bt++;
 		if (L.rowd0 < L.qlen && L.rowbase + (L.qlen - L.rowd0) > P.R) { L.flags |= BT_FLAG_STACK_OVF; break; }
+		if (L.rowd0 < L.qlen) {
+			const uint4 z = { 0, 0, 0, 0 };
+			uint4 *m = S.rows + 2 * (size_t)(L.rowbase - P.mask_rows);
+			for (uint32_t k = 0; k < 2 * P.mask_rows; k++) m[k] = z;
+		}
 		if (L.halfAndHalf) {
 			if (L.K->maxBts > 0 && L.K->numBts == L.K->maxBts) { L.K->bailed = 1; L.ret = 0; L.pc = PC_FRAME_RET; break; }
 			L.K->numBts++;
@@ -696,12 +716,22 @@ BT_FN void bt_blk_btloop(BtLane &L, const BtKParams &P, const BtScratch &S) {
 		BT_PROF(0, 1);
 		if (L.eligibleNum > 1 || L.elignore) {
 			BT_PROF(1, 1);
+			/* the highest position <= d of this frame whose quality is the lowest eligible one and that still has an alternative: the reference
+			 * steps down from d one position at a time (760-800); here only the positions of the live mask are visited, highest first */
+			const uint32_t *lm = bt_live_mask(L, P, S);
+			int32_t w = (int32_t)((L.d - L.rowd0) >> 5);
+			uint32_t mw = lm[w];
 #pragma unroll 1
-			for (;; i--) {
+			for (;;) {
+				while (mw == 0 && w > 0) mw = lm[--w];
+				if (mw == 0) break;                     /* cannot happen while eligibleNum > 0 */
+				const uint32_t b = 31u - bt_clz32(mw);
+				mw &= ~(1u << b);
+				i = L.rowd0 + ((uint32_t)w << 5) + b;
 				BT_PROF(2, 1);
 				const uint32_t qi = bt_qual_at(L, L.qlen - i - 1);
 				const uint32_t ri = bt_row_idx(L, i);
-				const uint32_t el = (i >= L.rowd0) ? S.elims[ri] : 15u;
+				const uint32_t el = S.elims[ri];
 				if (el != 15) BT_PROF(6, 1);
 				if ((qi == L.lowAltQual || !L.considerQuals) && el != 15) {
 					uint32_t posSz = 0;
@@ -717,7 +747,6 @@ BT_FN void bt_blk_btloop(BtLane &L, const BtKParams &P, const BtScratch &S) {
 					}
 					break;
 				}
-				if (i == L.K->depth) break;   /* cannot happen while eligibleNum > 0 */
 			}
 		} else {
 			i = L.eli; bttop = L.eltop; btbot = L.elbot; btham += L.elham; j = L.elcint; btcint = L.elcint;
@@ -758,7 +787,7 @@ BT_FN void bt_blk_btloop(BtLane &L, const BtKParams &P, const BtScratch &S) {
 		F.bt_i = (uint16_t)i; F.lowAltQual = (uint8_t)L.lowAltQual; F.elham = (uint8_t)L.elham; F.elcint = (uint8_t)L.elcint; F.bt_j = (uint8_t)j;
 		F.flags = (uint8_t)((L.elignore ? FF_ELIGNORE : 0) | (L.f_bdm ? FF_BDM : 0) | (L.f_must ? FF_MUST : 0) | (L.f_invHH ? FF_INVHH : 0) |
 		                    (L.f_invExact ? FF_INVEXACT : 0) | (L.K->disableFtab ? FF_DISABLEFTAB : 0));
-		L.rowbase = L.rowbase + ((L.d >= L.rowd0) ? (L.d - L.rowd0 + 1) : 0);
+		L.rowbase = L.rowbase + ((L.d >= L.rowd0) ? (L.d - L.rowd0 + 1) : 0) + P.mask_rows;
 		L.stackDepth++; L.K->depth = ndepth; L.unrevOff = btUnrevOff; L.K->oneRevOff = btOneRevOff; L.K->twoRevOff = btTwoRevOff; L.K->threeRevOff = btThreeRevOff;
 		L.top = ntop; L.bot = nbot; L.ham = btham; L.K->disableFtab = 0;
 		L.pc = PC_FRAME_ENTER;
@@ -793,7 +822,9 @@ BT_FN void bt_blk_child_ret(BtLane &L, const BtKParams &P, const BtScratch &S) {
 		if (L.K->bailed || (L.halfAndHalf && L.K->maxBts > 0 && L.K->numBts >= L.K->maxBts)) { L.K->bailed = 1; L.ret = 0; L.pc = PC_FRAME_RET; break; }
 		{
 			const uint32_t ri = bt_row_idx(L, L.K->bt_i);
-			S.elims[ri] = (uint8_t)(S.elims[ri] | (1u << L.K->bt_j));
+			const uint32_t el = S.elims[ri] | (1u << L.K->bt_j);
+			S.elims[ri] = (uint8_t)el;
+			if (el == 15u) { uint32_t *lm = bt_live_mask(L, P, S) + ((L.K->bt_i - L.rowd0) >> 5); *lm &= ~(1u << ((L.K->bt_i - L.rowd0) & 31u)); }   /* no alternative left at that position */
 		}
 		L.eligibleSz -= (L.K->btbot - L.K->bttop);
 		L.eligibleNum--;
@@ -805,9 +836,17 @@ BT_FN void bt_blk_child_ret(BtLane &L, const BtKParams &P, const BtScratch &S) {
 			/* re-scan the frame for the next-lowest quality (1004-1058) */
 			L.lowAltQual = 0xff;
 			BT_PROF(4, 1);
+			/* (the reference walks every position of the frame from d down; only those of the live mask can contribute) */
+			const uint32_t *lm = bt_live_mask(L, P, S);
+			int32_t w = (int32_t)((L.d - L.rowd0) >> 5);
+			uint32_t mw = lm[w];
 #pragma unroll 1
-			for (uint32_t k = L.d;; k--) {
-				if (k < L.unrevOff) break;
+			for (;;) {
+				while (mw == 0 && w > 0) mw = lm[--w];
+				if (mw == 0) break;
+				const uint32_t b = 31u - bt_clz32(mw);
+				mw &= ~(1u << b);
+				const uint32_t k = L.rowd0 + ((uint32_t)w << 5) + b;
 				BT_PROF(5, 1);
 				const uint32_t kq = bt_qual_at(L, L.qlen - k - 1);
 				const bool kAlt = (L.ham + bt_mm_penalty(L.maqPenalty, kq) <= L.qualThresh);
@@ -831,7 +870,6 @@ BT_FN void bt_blk_child_ret(BtLane &L, const BtKParams &P, const BtScratch &S) {
 						}
 					}
 				}
-				if (k == L.K->depth || k == 0) break;
 			}
 		}
 		L.pc = PC_BTLOOP;

@@ -149,6 +149,10 @@ extern "C" int bt_io_align_format(bt_io_t *io, const bt_policy_t *pol, const bt_
 	BioFmt f;
 	f.sam = fmt->sam ? 1u : 0u; f.khits = pol->khits; f.mhits = pol->mhits; f.strata = pol->strata ? 1u : 0u; f.noUnal = fmt->no_unal ? 1u : 0u;
 	f.noQnameTrunc = fmt->no_qname_trunc ? 1u : 0u; f.offBase = (uint32_t)fmt->off_base; f.mapq = fmt->mapq; f.slots = pol->khits; f.recWords = 0;
-	if (!p.align_format(pol, f, out_text, out_bytes, counters) || p.be.e != cudaSuccess) return io_fail(io, "bt_io_align_format");
+	if (!p.align_format(pol, f, out_text, out_bytes, counters) || p.be.e != cudaSuccess) {
+		const bool nc = p.not_covered && p.be.e == cudaSuccess;
+		io_fail(io, "bt_io_align_format");
+		return nc ? 2 : 1;                                            /* 2: nothing produced, the caller formats this batch itself */
+	}
 	return 0;
 }

@@ -108,7 +108,9 @@ struct BioPipe {
 		return true;
 	}
 	/* search + f2; returns the formatted text (host memory owned by the pipe) and the four sink counters */
+	bool not_covered = false;        /* set when align_format gave up on a batch the device formatter does not cover (nothing was produced) */
 	bool align_format(const bt_policy_t *pol, const BioFmt &fmt_in, const char **out_text, uint64_t *out_bytes, uint64_t counters[4]) {
+		not_covered = false;
 		const uint32_t max_read_len = maxlen ? maxlen : 1;
 		*out_text = nullptr; *out_bytes = 0;
 		for (int k = 0; k < 4; k++) counters[k] = 0;
@@ -135,7 +137,7 @@ struct BioPipe {
 			if (any & ~(uint32_t)(BT_OVF_MM | BT_OVF_HITS)) { err = "bt_io: search scratch exhausted for a read"; return false; }
 			if (!any) break;
 			const uint32_t full = max_read_len < BIO_MM_MAX ? max_read_len : BIO_MM_MAX;
-			if ((any & BT_OVF_HITS) || cap >= full) { err = "bt_io: a read has more mismatches than the device formatter handles (use the host output path)"; return false; }
+			if ((any & BT_OVF_HITS) || cap >= full) { not_covered = true; err = "bt_io: a read has more mismatches (or hits) than the device formatter handles: the host output path formats this batch"; return false; }
 			cap = full;
 		}
 		be.zero(d_cnt, 4 * sizeof(unsigned long long));

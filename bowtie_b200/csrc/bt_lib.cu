@@ -53,42 +53,7 @@ __global__ void bt_debug_lf_kernel(BtDevIndex ix, const uint32_t *rows, uint32_t
 	out[5 * (size_t)i + 4] = bt_row_l(b, row);
 }
 
-#ifndef BT_THREADS
-#define BT_THREADS 128
-#endif
-#ifndef BT_MIN_BLOCKS
-#define BT_MIN_BLOCKS 4            /* register cap = 65536 / (128 * BT_MIN_BLOCKS): 128 registers with the cold lane state in shared memory */
-#endif
-#ifndef BT_RARE_PERIOD
-#define BT_RARE_PERIOD 8           /* rare transitions run at least every BT_RARE_PERIOD-th iteration ... */
-#endif
-#ifndef BT_RARE_THRESH
-#define BT_RARE_THRESH 16          /* ... or as soon as this many lanes of the warp wait for one (8 / 16: sweep on the hg19-sized index, profiles/) */
-#endif
-#ifndef BT_Q_NCTX
-#define BT_Q_NCTX 1024              /* read contexts per block of the queue-driven kernel                    */
-#endif
-#ifndef BT_Q_THREADS
-#define BT_Q_THREADS 384            /* worker threads per block                                               */
-#endif
-#define BT_SMEM_LEN 128            /* reads up to this length are staged in shared memory                   */
-#ifndef BT_COLD_SMEM
-#define BT_COLD_SMEM 1             /* the rare transitions' part of the lane state (BtLaneCold) lives in shared memory, not in registers */
-#endif
-/* A lane's shared-memory area: its writable copy of the read's bases (seedling mutations are applied to it), the 6 operation counters
- * snapped when its current read began, and — BT_COLD_SMEM — its BtLaneCold.  Qualities are never written, so they are read in place
- * from the batch (L1-resident: 100 bytes per read, fetched a position ahead of their use).  The stride is an odd number of words:
- * lanes' equal offsets fall in different banks. */
-#define BT_SMEM_SNAP BT_SMEM_LEN
-#define BT_SMEM_COLD (BT_SMEM_LEN + 24)
-#if BT_COLD_SMEM
-#define BT_SMEM_STRIDE ((BT_SMEM_LEN + 24 + (uint32_t)sizeof(BtLaneCold) + 4) | 4u)
-#else
-#define BT_SMEM_STRIDE (BT_SMEM_LEN + 28)
-#endif
-static_assert((BT_SMEM_STRIDE / 4) % 2 == 1 && BT_SMEM_STRIDE % 4 == 0, "odd word stride");
-
-struct BtWorkCtl { unsigned long long next; unsigned long long nwork; };
+#include "bt_kernel_cfg.cuh"
 
 /* Persistent search kernel: every thread is a lane that pulls read ids from a global cursor until
  * the batch is exhausted.  `ctl->nwork` is read from device memory so that the retry pass can be
@@ -105,13 +70,10 @@ bt_search_kernel(BtKParams P, BtWorkCtl *ctl) {
 	const uint32_t lane = threadIdx.x & 31;
 	uint8_t *const my_stage = bt_smem + (size_t)threadIdx.x * BT_SMEM_STRIDE;
 	BtScratch S;
-	if (!P.resume) {
-		S.rows = P.rows + (size_t)tid * P.R * 2;
-		S.elims = P.elims + (size_t)tid * P.R;
-		S.frames = P.frames + (size_t)tid * P.FCAP;
-		S.partials = P.partials + (size_t)tid * P.PCAP;
-	} else S.rows = nullptr, S.elims = nullptr, S.frames = nullptr, S.partials = nullptr;      /* a slice works in the slot's scratch */
-	uint32_t my_slot = 0;
+	S.rows = P.rows + (size_t)tid * P.R * 2;
+	S.elims = P.elims + (size_t)tid * P.R;
+	S.frames = P.frames + (size_t)tid * P.FCAP;
+	S.partials = P.partials + (size_t)tid * P.PCAP;
 	BtLane L;
 #if BT_COLD_SMEM
 	L.K = reinterpret_cast<BtLaneCold *>(my_stage + BT_SMEM_COLD);
@@ -122,8 +84,7 @@ bt_search_kernel(BtKParams P, BtWorkCtl *ctl) {
 	L.s_lfex = L.s_lf = L.s_chase = L.K->s_ftab = L.K->s_offs = L.K->s_bt = L.s_iter = L.s_blk = 0;
 	L.K->nmuts = 0; L.K->mut0 = L.K->mut1 = L.K->mut2 = 0; L.ebwtSel = 0; L.lfk = 0; L.ltop = L.lbot = L.crow = 0; L.flags = 0; L.d = 0; L.qlen = 0;
 	L.rlen = 0; L.rseq = my_stage; L.rqual = my_stage; L.K->hasN = 1; L.K->step = 0;
-	unsigned long long nwork = ctl->nwork;
-	if (P.resume && nwork > P.nslot) nwork = P.nslot;                 /* the main pass counts past the last slot (those reads are re-run) */
+	const unsigned long long nwork = ctl->nwork;
 	/* Once the work queue is empty a pass only waits for its slowest reads while most lanes idle — with a per-read budget of 8000
 	 * transitions that drain is as long as everything a lane did before it at a million reads per pass.  From the moment a warp
 	 * finds the queue empty its lanes therefore run on the (smaller) drain budget: what exceeds it moves to the tail pass, where it
@@ -178,12 +139,9 @@ bt_search_kernel(BtKParams P, BtWorkCtl *ctl) {
 					if (w < nwork) {
 						const uint32_t rid = P.sel ? P.sel[w] : (uint32_t)w;
 						took = true;
-						if (P.resume) { my_slot = rid; bt_slot_resume(L, P, S, my_slot); }     /* the item is a slot: continue its read where it stopped */
-						else {
-							bt_begin_read(L, P, rid);
-							ro = P.roff[rid];
-							got = true;
-						}
+						bt_begin_read(L, P, rid);
+						ro = P.roff[rid];
+						got = true;
 						uint32_t *snap = reinterpret_cast<uint32_t *>(my_stage + BT_SMEM_SNAP);
 						snap[0] = L.s_lfex; snap[1] = L.s_lf; snap[2] = L.s_chase; snap[3] = L.K->s_ftab; snap[4] = L.K->s_offs; snap[5] = L.s_blk;
 					} else L.pc = PC_EXIT;
@@ -225,16 +183,8 @@ bt_search_kernel(BtKParams P, BtWorkCtl *ctl) {
 			if (L.flags & BT_FLAG_PREEMPT) {
 				/* over this pass's budget (or out of seedling space): suspend the read into a checkpoint slot; the next slice resumes it */
 				L.flags &= ~BT_FLAG_PREEMPT;
-				bool kept = true;
-				if (P.resume) {
-					bt_ctx_store(L, P.slot_ctx, P.nslot, my_slot);              /* its scratch and its read are in the slot already */
-					P.slice_out[atomicAdd(P.slice_count, 1ull)] = my_slot;
-				} else {
-					const unsigned long long p = atomicAdd(P.slice_count, 1ull);
-					if (p < P.nslot) { bt_slot_save_new(L, P, S, (uint32_t)p); P.flags[L.K->rid] = 0; P.found[L.K->rid] = 0; }
-					else kept = false;
-				}
-				if (kept) L.pc = PC_NEXT_READ;
+				const unsigned long long p = atomicAdd(P.slice_count, 1ull);
+				if (p < P.nslot) { bt_slot_save_new(L, P, S, (uint32_t)p); P.flags[L.K->rid] = 0; P.found[L.K->rid] = 0; L.pc = PC_NEXT_READ; }
 				else { L.flags |= BT_FLAG_BUDGET; L.pc = PC_FINISH_READ; }      /* no slot left: re-run from scratch by the overflow pass */
 			}
 		}
@@ -554,7 +504,7 @@ struct bt_context {
 	bt_index *ix = nullptr;
 	Workspace ws1, wsh, ws2;     /* main pass / heavy-read pass / scratch-overflow pass */
 	BtWorkCtl *ctl = nullptr;    /* [BT_CTL_WORDS]: main pass, slices, overflow pass (best-first path: its four tiers) */
-	Workspace wsl; uint32_t *slot_ctx = nullptr, *slice_list[2] = { nullptr, nullptr }; uint32_t slot_cap = 0;   /* checkpoint slots (bt_ctxq.cuh) */
+	Workspace wsl; uint32_t *slot_ctx = nullptr, *tailq_items = nullptr; BtTailQ *tailq = nullptr; uint32_t slot_cap = 0, tailq_cap = 0;   /* checkpoint slots (bt_ctxq.cuh) and the tail's ring (bt_tail.cu) */
 	uint32_t *heavy_sel = nullptr, *ultra_sel = nullptr, *retry_sel = nullptr; uint32_t retry_cap = 0;
 	cudaStream_t side = nullptr; /* the heavy and overflow passes run here, overlapping the next batch's main pass */
 	cudaEvent_t ev_main = nullptr, ev_tail = nullptr;
@@ -669,7 +619,7 @@ extern "C" void bt_context_free(bt_context_t *cx) {
 	if (cx->ev_main) cudaEventDestroy(cx->ev_main);
 	if (cx->ev_tail) cudaEventDestroy(cx->ev_tail);
 	cx->ws1.release(); cx->wsh.release(); cx->ws2.release(); cx->wsl.release();
-	cudaFree(cx->slot_ctx); cudaFree(cx->slice_list[0]); cudaFree(cx->slice_list[1]);
+	cudaFree(cx->slot_ctx); cudaFree(cx->tailq_items); cudaFree(cx->tailq);
 	cudaFree(cx->ctl); cudaFree(cx->retry_sel); cudaFree(cx->heavy_sel); cudaFree(cx->ultra_sel);
 	cudaFree(cx->d_seq); cudaFree(cx->d_qual); cudaFree(cx->d_offs); cudaFree(cx->d_seeds); cudaFree(cx->d_sel);
 	cudaFree(cx->d_found); cudaFree(cx->d_flags); cudaFree(cx->d_hits);
@@ -914,16 +864,13 @@ static void set_ws(BtKParams &P, const Workspace &w) {
 /* Enqueues one batch.  All pointers are device pointers; `maxlen` bounds the read length.
  *   main pass      on `st`:        every read, with a per-read transition budget and first-tier scratch (64 seedlings).  A read that
  *                                  exceeds the budget or fills its seedling list is SUSPENDED into a checkpoint slot (bt_ctxq.cuh).
- *   slices         on cx->side:    BT_SLICES passes over the suspended reads, each resuming every read still unfinished for a
- *                                  (geometrically growing) quantum of transitions and suspending it again; the last one runs to the end.
- *                                  Search cost is heavy-tailed (1 % of the reads = half of all transitions, the longest 10^6 sequential
- *                                  steps): re-packing the survivors after every quantum keeps the warps of the long tail full instead
- *                                  of one straggler holding 127 idle lanes and their registers.
+ *   tail           on cx->side:    bt_tail_kernel (bt_tail.cu): the suspended reads circulate through a ring, a quantum of transitions
+ *                                  per turn, always packed into as few single-warp blocks as there are reads left.  (BT_TAIL=restart:
+ *                                  instead, over-budget reads are flagged and re-run from scratch by one unbudgeted pass.)
  *   overflow pass  on cx->side:    reads whose scratch overflowed even in a slot (or that found no free slot): re-run from scratch with
  *                                  worst-case scratch (normally empty)
  * The side stream lets the long tail of batch k overlap the main pass of batch k+1 (another context); the
  * batch is complete when cx->ev_tail has fired (bt_context_join / bt_context_sync). */
-#define BT_SLICES_MAX 8
 static int enqueue_align(bt_context *cx, const bt_policy_t *pol, const bt_read_batch_t *in, bt_hit_batch_t *out, uint32_t maxlen, cudaStream_t st) {
 	bt_index_t *ix = cx->ix;
 	const uint32_t nwork = in->sel ? in->nsel : in->nreads;
@@ -936,33 +883,34 @@ static int enqueue_align(bt_context *cx, const bt_policy_t *pol, const bt_read_b
 	if (maxlen > 1023) return fail("bt_align: reads longer than 1023 bases are not supported (the reference's Hit::mms is a FixedBitset<1024>)");
 	const uint32_t nthreads = main_kernel_is_queue() ? (uint32_t)ix->sms * BT_Q_NCTX : (uint32_t)ix->sms * (uint32_t)ix->blocks_per_sm * BT_THREADS;
 	const uint32_t stage_len = (maxlen + 15) & ~15u;                     /* every context keeps a writable copy of its read */
-	if (ensure_ws(cx->ws1, nthreads, 6 * maxlen + 8, 8, 64, stage_len)) return 1;
+	const uint32_t mask_rows = (maxlen + 255) >> 8;                      /* per-frame live-position mask (bt_live_mask): 256 positions per row */
+	if (ensure_ws(cx->ws1, nthreads, 6 * maxlen + 8 + 9 * mask_rows, 8, 64, stage_len)) return 1;
 	/* checkpoint slots: one per suspended read.  On the bench workload 0.7 % of the reads exceed the main budget and 0.3 % fill the
 	 * 64-seedling list; slots for 1/32 of the batch (BT_SLOT_DIV), at least 4096.  A read that finds none is re-run by the overflow pass. */
 	static const uint32_t slot_div = env_u32("BT_SLOT_DIV", 32), slot_pcap = env_u32("BT_SLOT_PCAP", 1024);
-	/* BT_SLICES=n (default 0: off) turns the slices on.  Measured on the hg19-sized index (profiles/README.md, call 6): a read is sequential,
-	 * so every slice lasts as long as its longest resumed read runs, the slices of a batch are serialised behind each other, and their
-	 * 128-thread blocks stay resident around single surviving lanes — 3.3 M reads/s against 5.1 M for the restart tail below. */
-	static const bool use_slots = env_u32("BT_SLICES", 0) > 0 && !main_kernel_is_queue();
-	static const uint32_t nslices = env_u32("BT_SLICES", 0) > BT_SLICES_MAX ? BT_SLICES_MAX : env_u32("BT_SLICES", 0);
+	/* BT_TAIL=rr (default): reads over the main budget are suspended into checkpoint slots and finished by the round-robin tail
+	 * (bt_tail.cu); BT_TAIL=restart: they are flagged and re-run from scratch by one unbudgeted pass, one read per lane until it ends. */
+	static const bool use_slots = !(getenv("BT_TAIL") && getenv("BT_TAIL")[0] == 'r' && getenv("BT_TAIL")[1] == 'e') && !main_kernel_is_queue();
 	uint32_t nslot = nwork / (slot_div ? slot_div : 32); if (nslot < 4096) nslot = 4096; if (nslot > nwork) nslot = nwork;
 	if (use_slots) {
-		if (ensure_ws(cx->wsl, nslot, 6 * maxlen + 8, 16, slot_pcap, stage_len)) return 1;
+		if (ensure_ws(cx->wsl, nslot, 6 * maxlen + 8 + 17 * mask_rows, 16, slot_pcap, stage_len)) return 1;
 		if (cx->slot_cap < nslot) {
-			cudaFree(cx->slot_ctx); cudaFree(cx->slice_list[0]); cudaFree(cx->slice_list[1]); cx->slot_ctx = cx->slice_list[0] = cx->slice_list[1] = nullptr; cx->slot_cap = 0;
+			cudaFree(cx->slot_ctx); cudaFree(cx->tailq_items); cudaFree(cx->tailq); cx->slot_ctx = cx->tailq_items = nullptr; cx->tailq = nullptr; cx->slot_cap = 0;
+			uint32_t cap = 8192; while (cap < 2 * cx->wsl.nthreads) cap <<= 1;                 /* ring: a power of two >= 2 x slots */
 			CUDA_TRY(cudaMalloc((void **)&cx->slot_ctx, (size_t)cx->wsl.nthreads * BT_CTX_WORDS * 4));
-			CUDA_TRY(cudaMalloc((void **)&cx->slice_list[0], (size_t)cx->wsl.nthreads * 4));
-			CUDA_TRY(cudaMalloc((void **)&cx->slice_list[1], (size_t)cx->wsl.nthreads * 4));
+			CUDA_TRY(cudaMalloc((void **)&cx->tailq_items, (size_t)cap * 4));
+			CUDA_TRY(cudaMalloc((void **)&cx->tailq, sizeof(BtTailQ)));
+			cx->tailq_cap = cap;
 			cx->slot_cap = cx->wsl.nthreads;
 		}
 		nslot = cx->wsl.nthreads >= nslot ? nslot : cx->wsl.nthreads;
 	} else {
 		/* no slots (BT_SLICES=0, or the queue kernel): the tail pass re-runs heavy reads from scratch on full-size scratch */
 		static const uint32_t tail_bps = env_u32("BT_TAIL_BLOCKS", 2);
-		if (ensure_ws(cx->wsh, (uint32_t)ix->sms * tail_bps * BT_THREADS, 6 * maxlen + 8, 16, 4096, stage_len)) return 1;
+		if (ensure_ws(cx->wsh, (uint32_t)ix->sms * tail_bps * BT_THREADS, 6 * maxlen + 8 + 17 * mask_rows, 16, 4096, stage_len)) return 1;
 	}
 	const uint32_t nthreads2 = (uint32_t)ix->sms * 32;
-	uint32_t R2 = maxlen * maxlen + 8; if (R2 > 65000) R2 = 65000;   /* BtFrame::rowbase is 16 bits */
+	uint32_t R2 = maxlen * maxlen + 8 + (maxlen + 3) * mask_rows; if (R2 > 65000) R2 = 65000;   /* BtFrame::rowbase is 16 bits */
 	if (ensure_ws(cx->ws2, nthreads2, R2, maxlen + 2, 4096, stage_len)) return 1;
 	if (cx->retry_cap < nwork) {
 		cudaFree(cx->retry_sel); cudaFree(cx->heavy_sel); cudaFree(cx->ultra_sel); cx->retry_sel = cx->heavy_sel = cx->ultra_sel = nullptr; cx->retry_cap = 0;
@@ -977,9 +925,9 @@ static int enqueue_align(bt_context *cx, const bt_policy_t *pol, const bt_read_b
 	bt_build_prog(pol->mode, pol->mms, pol->nofw, pol->norc, P.prog);
 	P.seq = in->seq; P.qual = in->qual; P.roff = in->offs; P.seeds = in->seeds; P.sel = in->sel; P.nwork = nwork;
 	P.found = out->found; P.flags = out->flags; P.hits = out->hits; P.slots = out->slots; P.mm_cap = out->mm_cap; P.rec_words = BT_HIT_HDR + out->mm_cap;
-	P.stats = ix->stats;
+	P.stats = ix->stats; P.mask_rows = mask_rows;
 	const uint32_t cblocks = (nwork + 255) / 256;
-	BtWorkCtl *const ctl_main = cx->ctl, *const ctl_slice = cx->ctl + 1, *const ctl_ovf = cx->ctl + 1 + BT_SLICES_MAX + 1;   /* ctl_slice[k]: work list of slice k */
+	BtWorkCtl *const ctl_main = cx->ctl, *const ctl_slice = cx->ctl + 1, *const ctl_ovf = cx->ctl + 2;   /* ctl_slice: the suspended reads' slot count (round-robin tail), or the restart pass's work list */
 	/* this context's previous batch must have finished with the scratch and the lists */
 	CUDA_TRY(cudaStreamWaitEvent(st, cx->ev_tail, 0));
 	/* main pass */
@@ -1008,23 +956,14 @@ static int enqueue_align(bt_context *cx, const bt_policy_t *pol, const bt_read_b
 	CUDA_TRY(cudaStreamWaitEvent(cx->side, cx->ev_main, 0));
 	{ static uint32_t p = env_u32("BT_HEAVY_PERIOD", BT_RARE_PERIOD), t = env_u32("BT_HEAVY_THRESH", BT_RARE_THRESH); P.rare_period = p ? p : 1; P.rare_thresh = t; }
 	if (use_slots) {
-		/* slices: slice k resumes the slots of its list (slice 0: all of them, in order) and runs each read up to a cumulative budget of
-		 * main budget x BT_SLICE_GROWTH^(k+1) transitions; what is still unfinished is suspended again into the next slice's list */
-		static const uint32_t growth = env_u32("BT_SLICE_GROWTH", 3), sl_threads = env_u32("BT_SLICE_THREADS", BT_THREADS), sl_bps = env_u32("BT_SLICE_BLOCKS", 2);
-		const uint32_t threads = (sl_threads >= 32 && sl_threads <= BT_THREADS && sl_threads % 32 == 0) ? sl_threads : BT_THREADS;
-		uint32_t grid = (uint32_t)ix->sms * sl_bps * (BT_THREADS / threads);
-		{ const uint32_t need = (nslot + threads - 1) / threads; if (grid > need) grid = need; }
-		P.resume = 1; P.drain_budget = 0;
+		/* the round-robin tail: single-warp blocks, as many as the suspended reads can fill (bt_tail.cu) */
+		static const uint32_t quantum = env_u32("BT_TAIL_QUANTUM", 4096), wps = env_u32("BT_TAIL_WARPS", 16);
+		uint32_t blocks = (uint32_t)ix->sms * (wps ? wps : 16);
+		{ const uint32_t need = (nslot + 31) / 32; if (blocks > need) blocks = need; }
+		P.resume = 1; P.drain_budget = 0; P.budget = 0; P.sel = nullptr;
 		P.R = cx->wsl.R; P.FCAP = cx->wsl.FCAP; P.PCAP = cx->wsl.PCAP; P.stage = nullptr; P.stage_len = cx->wsl.stage_len;
 		P.rows = nullptr; P.elims = nullptr; P.frames = nullptr; P.partials = nullptr;
-		unsigned long long b = P.budget ? P.budget : 8000;
-		for (uint32_t k = 0; k < nslices; k++) {
-			b *= growth > 1 ? growth : 2;
-			P.budget = (k + 1 == nslices || b > 0x7fffffffull) ? 0u : (uint32_t)b;           /* the last slice finishes every read */
-			P.sel = k == 0 ? nullptr : cx->slice_list[(k - 1) & 1];
-			P.slice_count = &ctl_slice[k + 1].nwork; P.slice_out = cx->slice_list[k & 1];
-			bt_search_kernel<<<grid, threads, threads * BT_SMEM_STRIDE, cx->side>>>(P, ctl_slice + k);
-		}
+		if (bt_tail_launch(P, cx->tailq, &ctl_slice[0].nwork, nslot, cx->tailq_cap, cx->tailq_items, quantum ? quantum : 4096, blocks, cx->side) != 0) return fail("bt_tail_launch failed");
 		P.resume = 0; P.slot_ctx = nullptr;
 		/* what is flagged now: scratch overflow in a slot, or no free slot */
 		bt_collect_kernel<<<cblocks, 256, 0, cx->side>>>(out->flags, in->sel, nwork, nullptr, BT_FLAG_RETRY, cx->retry_sel, ctl_ovf);

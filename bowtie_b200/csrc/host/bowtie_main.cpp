@@ -1366,7 +1366,9 @@ int main(int argc, char **argv) {
 					if (bt_io_parse_fastq(io[k & 1], rd.buf.data(), rd.len, op.seed, 0xffffffffu, &n, &used, &irregular)) die(std::string("Error: ") + bt_last_error());
 					if (n == 0) break;
 					const char *text = NULL; uint64_t bytes = 0, cnt[4] = { 0, 0, 0, 0 };
-					if (bt_io_align_format(io[k & 1], &polU, &fmt, &text, &bytes, cnt)) die(std::string("Error: ") + bt_last_error());
+					const int frc = bt_io_align_format(io[k & 1], &polU, &fmt, &text, &bytes, cnt);
+					if (frc == 2) break;                                               /* a batch the device formatter does not cover: the host pipeline takes over from this record on */
+					if (frc) die(std::string("Error: ") + bt_last_error());
 					if (writer.joinable()) writer.join();                              /* chunk k-1 is on disk: its buffer (the other io's) may be reused */
 					FILE *fp = out.fp;
 					writer = std::thread([fp, text, bytes]() { if (bytes) fwrite(text, 1, (size_t)bytes, fp); });

@@ -179,7 +179,9 @@ int  bt_index_build_text(const uint8_t *text, uint64_t text_len, const bt_ref_re
  *                        reportUnOrMax, sam.cpp:57-257; no header), unpaired, with finishRead's -k / -m arithmetic (hit.h:741-786), in
  *                        read order.  *out_text (host memory owned by the io, valid until its next call) holds *out_bytes bytes;
  *                        counters = { aligned, unaligned, maxed, reported } of hit.h:169-175.  Not provided here (callers format those
- *                        from hit records): paired-end, -a, -M, --suppress / --refidx / cost columns.
+ *                        from hit records): paired-end, -a, -M, --suppress / --refidx / cost columns.  Returns 2 (and produces nothing)
+ *                        when a read of the batch has more than 32 mismatches or more hits than -k records: the caller formats that
+ *                        batch from hit records (the host parser re-reads the same text).
  * One io per in-flight chunk; calls on one io are synchronous. */
 typedef struct bt_io bt_io_t;
 typedef struct bt_io_format {

@@ -74,7 +74,8 @@ static int run(bt_index *ix, const bt_policy_t *pol, const bt_read_batch_t *in, 
 	P.seq = in->seq; P.qual = in->qual; P.roff = in->offs; P.seeds = in->seeds;
 	P.found = out->found; P.flags = out->flags; P.hits = out->hits; P.slots = out->slots; P.mm_cap = out->mm_cap; P.rec_words = BT_HIT_HDR + out->mm_cap;
 	uint32_t maxlen = 1; for (uint32_t i = 0; i < in->nreads; i++) { uint64_t l = in->offs[i + 1] - in->offs[i]; if (l > maxlen) maxlen = (uint32_t)l; }
-	uint32_t R = maxlen * maxlen + 8; if (R > 65000) R = 65000;
+	P.mask_rows = (maxlen + 255) >> 8;
+	uint32_t R = maxlen * maxlen + 8 + (maxlen + 3) * P.mask_rows; if (R > 65000) R = 65000;
 	std::vector<uint4> rows(2 * (size_t)R); std::vector<uint8_t> elims(R), stage; std::vector<BtFrame> frames(maxlen + 2); std::vector<uint64_t> parts(1 << 16);
 	P.R = R; P.FCAP = maxlen + 2; P.PCAP = 1 << 16;
 	BtScratch S = { rows.data(), elims.data(), frames.data(), parts.data() };
@@ -214,7 +215,7 @@ int bt_io_align_format(bt_io_t *io, const bt_policy_t *pol, const bt_io_format_t
 	BioFmt f;
 	f.sam = fmt->sam ? 1u : 0u; f.khits = pol->khits; f.mhits = pol->mhits; f.strata = pol->strata ? 1u : 0u; f.noUnal = fmt->no_unal ? 1u : 0u;
 	f.noQnameTrunc = fmt->no_qname_trunc ? 1u : 0u; f.offBase = (uint32_t)fmt->off_base; f.mapq = fmt->mapq; f.slots = pol->khits; f.recWords = 0;
-	if (!p.align_format(pol, f, out_text, out_bytes, counters)) { g_err = p.err; return 1; }
+	if (!p.align_format(pol, f, out_text, out_bytes, counters)) { g_err = p.err; return p.not_covered ? 2 : 1; }
 	return 0;
 }
 int bt_counters_allreduce(void *, uint64_t *, void *) { g_err = "emulation shim has no collective"; return 1; }

@@ -61,6 +61,8 @@ int emu_align(void *fwp, void *bwp, const BtPolicy *pol, uint32_t nreads, const 
 	P.pol = *pol;
 	P.seq = seq; P.qual = qual; P.roff = roff; P.seeds = seeds; P.nwork = nreads;
 	P.found = found; P.flags = flags; P.hits = hits; P.slots = slots; P.mm_cap = mm_cap; P.rec_words = BT_HIT_HDR + mm_cap;
+	{ uint32_t ml = 1; for (uint32_t r = 0; r < nreads; r++) { const uint32_t l = (uint32_t)(roff[r + 1] - roff[r]); if (l > ml) ml = l; } P.mask_rows = (ml + 255) >> 8; }
+	R += (FCAP + 1) * P.mask_rows;                            /* every frame also holds its live-position mask (as enqueue_align sizes it) */
 	std::vector<uint4> rows(2 * (size_t)R); std::vector<uint8_t> elims(R); std::vector<BtFrame> frames(FCAP); std::vector<uint64_t> parts(PCAP);
 	P.R = R; P.FCAP = FCAP; P.PCAP = PCAP;
 	BtScratch S = { rows.data(), elims.data(), frames.data(), parts.data() };
@@ -115,6 +117,8 @@ int emu_align_sliced(void *fwp, void *bwp, const BtPolicy *pol, uint32_t nreads,
 	P.pol = *pol;
 	P.seq = seq; P.qual = qual; P.roff = roff; P.seeds = seeds; P.nwork = nreads;
 	P.found = found; P.flags = flags; P.hits = hits; P.slots = slots; P.mm_cap = mm_cap; P.rec_words = BT_HIT_HDR + mm_cap;
+	{ uint32_t ml = 1; for (uint32_t r = 0; r < nreads; r++) { const uint32_t l = (uint32_t)(roff[r + 1] - roff[r]); if (l > ml) ml = l; } P.mask_rows = (ml + 255) >> 8; }
+	R += ((FCAP > slotFCAP ? FCAP : slotFCAP) + 1) * P.mask_rows;
 	std::vector<uint4> rows(2 * (size_t)R), srows(2 * (size_t)R); std::vector<uint8_t> elims(R), selims(R);
 	std::vector<BtFrame> frames(FCAP), sframes(slotFCAP); std::vector<uint64_t> parts(PCAP), sparts(slotPCAP);
 	std::vector<uint32_t> sctx(BT_CTX_WORDS);
@@ -179,6 +183,8 @@ int emu_warp_sim(void *fwp, void *bwp, const BtPolicy *pol, uint32_t nreads, con
 	const uint32_t slots = 1, mm_cap = 8;
 	std::vector<uint32_t> found(nreads), flags(nreads), hits((size_t)nreads * slots * (BT_HIT_HDR + mm_cap));
 	P.found = found.data(); P.flags = flags.data(); P.hits = hits.data(); P.slots = slots; P.mm_cap = mm_cap; P.rec_words = BT_HIT_HDR + mm_cap;
+	{ uint32_t ml = 1; for (uint32_t r = 0; r < nreads; r++) { const uint32_t l = (uint32_t)(roff[r + 1] - roff[r]); if (l > ml) ml = l; } P.mask_rows = (ml + 255) >> 8; }
+	R += (FCAP + 1) * P.mask_rows;
 	P.R = R; P.FCAP = FCAP; P.PCAP = PCAP; P.rare_period = rare_period ? rare_period : 1; P.rare_thresh = rare_thresh; P.budget = budget;
 	bt_build_prog(pol->mode, pol->mms, pol->nofw, pol->norc, P.prog);
 	const uint32_t nl = nwarps * 32;
