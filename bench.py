@@ -189,31 +189,64 @@ def _seeds(codes2d, quals2d, name2d):
     """Read::seed per pat.cpp:21-57 with global seed 0, vectorised."""
     n, L = codes2d.shape
     seeds = np.full(n, ((0 + 101) * 59 * 61 * 67 * 71 * 73 * 79 * 83) & 0xFFFFFFFF, np.uint32)
-    i = np.arange(L)
-    seeds ^= np.bitwise_xor.reduce(codes2d.astype(np.uint32) << ((i & 15) << 1).astype(np.uint32), axis=1)
-    seeds ^= np.bitwise_xor.reduce(quals2d.astype(np.uint32) << ((i & 3) << 3).astype(np.uint32), axis=1)
-    j = np.arange(name2d.shape[1])
-    seeds ^= np.bitwise_xor.reduce(name2d.astype(np.uint32) << ((j & 3) << 3).astype(np.uint32), axis=1)
+
+    def fold(a, period, shift):
+        """XOR over i of a[:, i] << (shift * (i % period)): columns with the same shift are XORed as bytes first."""
+        w = a.shape[1]
+        acc = np.zeros((n, period), np.uint8)
+        for k in range(0, w, period):
+            blk = a[:, k:k + period]
+            acc[:, :blk.shape[1]] ^= blk
+        return np.bitwise_xor.reduce(acc.astype(np.uint32) << (np.arange(period, dtype=np.uint32) * np.uint32(shift)), axis=1)
+    seeds ^= fold(codes2d, 16, 2)
+    seeds ^= fold(quals2d, 4, 8)
+    seeds ^= fold(name2d, 4, 8)
     return seeds.astype(np.uint32)
+
+
+_QUAL_LUT = (np.array([40, 40, 40, 35, 30, 20, 10], np.uint8)[(np.arange(256) * 7) >> 8] + 33).astype(np.uint8)   # random byte -> Phred+33 character
+GEN_CHUNK = 1 << 20            # reads generated per numpy pass: bounds the temporaries (a (n, 100) int64 index array) whatever the batch size
+
+
+def _chunked(gen, genome: np.ndarray, n: int, seed: int, per_unit: int):
+    """Runs a generator over [0, n) in chunks of GEN_CHUNK units (chunk k: seed (seed, k), read ids continuing) and concatenates."""
+    if n <= GEN_CHUNK:
+        return gen(genome, n, seed, 0)
+    parts = [gen(genome, min(GEN_CHUNK, n - a), (seed, a // GEN_CHUNK), a) for a in range(0, n, GEN_CHUNK)]
+    offs = (np.arange(per_unit * n + 1, dtype=np.uint64) * READ_LEN)
+    return (np.concatenate([p[0] for p in parts]), np.concatenate([p[1] for p in parts]), offs, np.concatenate([p[3] for p in parts]),
+            np.concatenate([p[4] for p in parts]))
 
 
 def make_reads(genome: np.ndarray, n: int, seed: int):
     """n x 100 bp: uniform positions, both strands, 1 % substitutions, 0.1 % random reads, Phred33 quals from
     {40,40,40,35,30,20,10}.  Returns (codes[n*100], quals[n*100], offs[n+1], seeds[n], names)."""
+    return _chunked(_make_reads, genome, n, seed, 1)
+
+
+def make_pairs(genome: np.ndarray, n: int, seed: int):
+    """n pairs of 2 x 100 bp in --fr geometry (SURVEY.md §8d config 5): fragment length N(200, 20) clipped to [101, 250], mate 1 the
+    fragment's first 100 bases, mate 2 the reverse complement of its last 100, the whole fragment flipped half of the time,
+    1 % substitutions.  Reads are interleaved (mate 1, mate 2, mate 1, ...); names "r%09d/1", "r%09d/2"."""
+    return _chunked(_make_pairs, genome, n, seed, 2)
+
+
+def _make_reads(genome: np.ndarray, n: int, seed, id0: int):
     rng = np.random.default_rng(seed)
     L = READ_LEN
     pos = rng.integers(0, len(genome) - L, n)
-    codes = genome[pos[:, None] + np.arange(L)[None, :]]
-    mut = rng.random((n, L), dtype=np.float32) < 0.01
-    codes[mut] = (codes[mut] + rng.integers(1, 4, int(mut.sum()))) & 3
+    codes = np.lib.stride_tricks.sliding_window_view(genome, L)[pos]        # (n, L) gather of windows, no index matrix
+    mi = rng.integers(0, n * L, int(rng.binomial(n * L, 0.01)))              # 1 % substitutions (positions drawn directly)
+    cf = codes.reshape(-1)
+    cf[mi] = (cf[mi] + rng.integers(1, 4, mi.size, dtype=np.uint8)) & 3
     rnd = rng.random(n) < 0.001
-    codes[rnd] = rng.integers(0, 4, (int(rnd.sum()), L))
+    codes[rnd] = rng.integers(0, 4, (int(rnd.sum()), L), dtype=np.uint8)
     rc = rng.random(n) < 0.5
     flipped = codes[rc, ::-1]
     codes[rc] = np.where(flipped < 4, 3 - flipped, 4)
     codes = np.ascontiguousarray(codes, np.uint8)
-    quals = (rng.choice(np.array([40, 40, 40, 35, 30, 20, 10], np.uint8), (n, L)) + 33).astype(np.uint8)
-    ids = np.arange(n, dtype=np.uint32)
+    quals = _QUAL_LUT[np.frombuffer(rng.bytes(n * L), np.uint8)].reshape(n, L)
+    ids = np.arange(id0, id0 + n, dtype=np.uint32)
     name = np.zeros((n, 10), np.uint8)                           # "r%09d": fixed width so genRandSeed vectorises
     name[:, 0] = ord("r")
     for d in range(9):
@@ -222,26 +255,25 @@ def make_reads(genome: np.ndarray, n: int, seed: int):
     return codes.reshape(-1), quals.reshape(-1), offs, _seeds(codes, quals, name), name
 
 
-def make_pairs(genome: np.ndarray, n: int, seed: int):
-    """n pairs of 2 x 100 bp in --fr geometry (SURVEY.md §8d config 5): fragment length N(200, 20) clipped to [101, 250], mate 1 the
-    fragment's first 100 bases, mate 2 the reverse complement of its last 100, the whole fragment flipped half of the time,
-    1 % substitutions.  Reads are interleaved (mate 1, mate 2, mate 1, ...); names "r%09d/1", "r%09d/2"."""
+def _make_pairs(genome: np.ndarray, n: int, seed, id0: int):
     rng = np.random.default_rng(seed)
     L = READ_LEN
     F = np.clip(rng.normal(200.0, 20.0, n).round().astype(np.int64), L + 1, 250)
     pos = rng.integers(0, len(genome) - 251, n)
-    left = genome[pos[:, None] + np.arange(L)[None, :]]
-    right = genome[(pos + F - L)[:, None] + np.arange(L)[None, :]]
+    win = np.lib.stride_tricks.sliding_window_view(genome, L)
+    left = win[pos]
+    right = win[pos + F - L]
     rcomp = lambda a: np.where(a[:, ::-1] < 4, 3 - a[:, ::-1], 4)
     flip = rng.random(n) < 0.5
     m1 = np.where(flip[:, None], rcomp(right), left)
     m2 = np.where(flip[:, None], left, rcomp(right))
     codes = np.empty((2 * n, L), np.uint8)
     codes[0::2] = m1; codes[1::2] = m2
-    mut = rng.random((2 * n, L), dtype=np.float32) < 0.01
-    codes[mut] = (codes[mut] + rng.integers(1, 4, int(mut.sum()))) & 3
-    quals = (rng.choice(np.array([40, 40, 40, 35, 30, 20, 10], np.uint8), (2 * n, L)) + 33).astype(np.uint8)
-    ids = np.repeat(np.arange(n, dtype=np.uint32), 2)
+    mi = rng.integers(0, 2 * n * L, int(rng.binomial(2 * n * L, 0.01)))
+    cf = codes.reshape(-1)
+    cf[mi] = (cf[mi] + rng.integers(1, 4, mi.size, dtype=np.uint8)) & 3
+    quals = _QUAL_LUT[np.frombuffer(rng.bytes(2 * n * L), np.uint8)].reshape(2 * n, L)
+    ids = np.repeat(np.arange(id0, id0 + n, dtype=np.uint32), 2)
     name = np.zeros((2 * n, 12), np.uint8)
     name[:, 0] = ord("r")
     for d in range(9):
@@ -681,8 +713,8 @@ def main() -> None:
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--reads-per-step", type=int, default=int(os.environ.get("BT_BENCH_READS", 4_000_000)))
-    ap.add_argument("--streams", type=int, default=int(os.environ.get("BT_BENCH_STREAMS", 8)),
+    ap.add_argument("--reads-per-step", type=int, default=int(os.environ.get("BT_BENCH_READS", 8_000_000)))
+    ap.add_argument("--streams", type=int, default=int(os.environ.get("BT_BENCH_STREAMS", 6)),
                     help="batches kept in flight (one bt_context_t + CUDA stream each), like the reference's -p worker threads")
     ap.add_argument("--policy", default=os.environ.get("BT_BENCH_POLICY", "n2k1"), choices=list(POLICIES),
                     help="headline policy; n2k1 also measures best and paired afterwards (other_policies) unless --no-others")
@@ -864,7 +896,7 @@ def main() -> None:
     head = run_policy(args.policy, B, NS, args.steps, args.warmup, True)
     others = {}
     if args.policy == "n2k1" and not args.no_others:
-        for name, b, ns in (("best", 1_000_000, 3), ("paired", 500_000, 3)):      # every context of the best-first path owns several GB of arenas
+        for name, b, ns in (("best", 1_000_000, 6), ("paired", 500_000, 6)):      # every context of the best-first path owns several GB of arenas
             try:
                 others[name] = run_policy(name, min(b, B), min(ns, args.steps), min(args.steps, 6), min(args.warmup, 3), False)
             except Exception as ex:

@@ -49,7 +49,8 @@ struct BtTailQ {
 	unsigned long long head, tail;     /* items [head, tail) are queued                                          */
 	long long live;                    /* unfinished reads: queued, or held by a lane                            */
 	uint32_t cap_mask, quantum;        /* ring capacity - 1 (power of two >= 2 x slots); transitions per turn    */
+	uint32_t wtarget, mincap;          /* warps the live reads are spread over; fewest reads a warp is filled to  */
 	uint32_t *items;
 };
 int bt_tail_launch(const BtKParams &P, BtTailQ *q, const unsigned long long *count, uint32_t nslot, uint32_t cap, uint32_t *items, uint32_t quantum,
-                   uint32_t blocks, cudaStream_t st);
+                   uint32_t wtarget, uint32_t mincap, uint32_t blocks, cudaStream_t st);

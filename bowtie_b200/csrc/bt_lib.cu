@@ -886,12 +886,16 @@ static int enqueue_align(bt_context *cx, const bt_policy_t *pol, const bt_read_b
 	const uint32_t mask_rows = (maxlen + 255) >> 8;                      /* per-frame live-position mask (bt_live_mask): 256 positions per row */
 	if (ensure_ws(cx->ws1, nthreads, 6 * maxlen + 8 + 9 * mask_rows, 8, 64, stage_len)) return 1;
 	/* checkpoint slots: one per suspended read.  On the bench workload 0.7 % of the reads exceed the main budget and 0.3 % fill the
-	 * 64-seedling list; slots for 1/32 of the batch (BT_SLOT_DIV), at least 4096.  A read that finds none is re-run by the overflow pass. */
-	static const uint32_t slot_div = env_u32("BT_SLOT_DIV", 32), slot_pcap = env_u32("BT_SLOT_PCAP", 1024);
-	/* BT_TAIL=rr (default): reads over the main budget are suspended into checkpoint slots and finished by the round-robin tail
-	 * (bt_tail.cu); BT_TAIL=restart: they are flagged and re-run from scratch by one unbudgeted pass, one read per lane until it ends. */
-	static const bool use_slots = !(getenv("BT_TAIL") && getenv("BT_TAIL")[0] == 'r' && getenv("BT_TAIL")[1] == 'e') && !main_kernel_is_queue();
-	uint32_t nslot = nwork / (slot_div ? slot_div : 32); if (nslot < 4096) nslot = 4096; if (nslot > nwork) nslot = nwork;
+	 * 64-seedling list; slots for 1/64 of the batch (BT_SLOT_DIV), at least 4096, each with room for 4096 seedlings.  A read that finds none is re-run by the overflow pass. */
+	static const uint32_t slot_div = env_u32("BT_SLOT_DIV", 64), slot_pcap = env_u32("BT_SLOT_PCAP", 4096);
+	/* The tail — the reads over the main budget.  Default ("restart"): they are flagged and re-run from scratch by one unbudgeted pass, one
+	 * read per lane until it ends.  BT_TAIL=rr: they are suspended into checkpoint slots and finished by the round-robin tail (bt_tail.cu).
+	 * Measured on the hg19-sized index (profiles/README.md, call 8): the round-robin tail executes 4.8 x fewer warp instructions (9.9 G
+	 * against 47 G per million reads, 8.9 against 3.6 active threads per instruction) but a packed warp advances each of its reads ~3.5 x
+	 * more slowly than a lone lane does, and a read is sequential: 2.4 s against 0.7 s for the tail of a batch, and with the contexts that
+	 * fit in flight 2-4 M reads/s against 5.7-9.3 M. */
+	static const bool use_slots = getenv("BT_TAIL") && getenv("BT_TAIL")[0] == 'r' && getenv("BT_TAIL")[1] == 'r' && !main_kernel_is_queue();
+	uint32_t nslot = nwork / (slot_div ? slot_div : 64); if (nslot < 4096) nslot = 4096; if (nslot > nwork) nslot = nwork;
 	if (use_slots) {
 		if (ensure_ws(cx->wsl, nslot, 6 * maxlen + 8 + 17 * mask_rows, 16, slot_pcap, stage_len)) return 1;
 		if (cx->slot_cap < nslot) {
@@ -957,13 +961,13 @@ static int enqueue_align(bt_context *cx, const bt_policy_t *pol, const bt_read_b
 	{ static uint32_t p = env_u32("BT_HEAVY_PERIOD", BT_RARE_PERIOD), t = env_u32("BT_HEAVY_THRESH", BT_RARE_THRESH); P.rare_period = p ? p : 1; P.rare_thresh = t; }
 	if (use_slots) {
 		/* the round-robin tail: single-warp blocks, as many as the suspended reads can fill (bt_tail.cu) */
-		static const uint32_t quantum = env_u32("BT_TAIL_QUANTUM", 4096), wps = env_u32("BT_TAIL_WARPS", 16);
+		static const uint32_t quantum = env_u32("BT_TAIL_QUANTUM", 4096), wps = env_u32("BT_TAIL_WARPS", 16), wtarget = env_u32("BT_TAIL_WTARGET", 256), mincap = env_u32("BT_TAIL_MINCAP", 4);
 		uint32_t blocks = (uint32_t)ix->sms * (wps ? wps : 16);
 		{ const uint32_t need = (nslot + 31) / 32; if (blocks > need) blocks = need; }
 		P.resume = 1; P.drain_budget = 0; P.budget = 0; P.sel = nullptr;
 		P.R = cx->wsl.R; P.FCAP = cx->wsl.FCAP; P.PCAP = cx->wsl.PCAP; P.stage = nullptr; P.stage_len = cx->wsl.stage_len;
 		P.rows = nullptr; P.elims = nullptr; P.frames = nullptr; P.partials = nullptr;
-		if (bt_tail_launch(P, cx->tailq, &ctl_slice[0].nwork, nslot, cx->tailq_cap, cx->tailq_items, quantum ? quantum : 4096, blocks, cx->side) != 0) return fail("bt_tail_launch failed");
+		if (bt_tail_launch(P, cx->tailq, &ctl_slice[0].nwork, nslot, cx->tailq_cap, cx->tailq_items, quantum ? quantum : 4096, wtarget, mincap, blocks, cx->side) != 0) return fail("bt_tail_launch failed");
 		P.resume = 0; P.slot_ctx = nullptr;
 		/* what is flagged now: scratch overflow in a slot, or no free slot */
 		bt_collect_kernel<<<cblocks, 256, 0, cx->side>>>(out->flags, in->sel, nwork, nullptr, BT_FLAG_RETRY, cx->retry_sel, ctl_ovf);

@@ -9,9 +9,10 @@
  *   - the suspended reads circulate through ONE ring of slot ids (BtTailQ).  A lane pops a slot, resumes the read, runs it for a
  *     quantum of transitions, and — if it is still unfinished — stores its 39 words and pushes the slot back: round robin, so a
  *     warp's lanes always hold reads as long as the ring has any, whatever the individual reads' lengths;
- *   - a warp may hold at most (live - 32 x its index) reads, where `live` counts the unfinished ones: as the reads run out the
- *     warps with the highest indices hand their reads back and exit, and what is left is always packed into ceil(live / 32)
- *     warps.  Blocks are single warps so that an exiting warp returns its registers and shared memory at once.
+ *   - a warp may hold at most min(cap, live - cap x its index) reads, where `live` counts the unfinished ones and cap = live / wtarget
+ *     clamped to [mincap, 32]: as the reads run out the warps with the highest indices hand their reads back and exit, and what is
+ *     left always sits in about min(wtarget, live / mincap) warps.  Blocks are single warps so that an exiting warp returns its
+ *     registers and shared memory at once.
  *
  * The straggler problem this replaces (one kernel for the whole tail, one read per lane until it ends): the last reads of a
  * batch run alone in their warps for ~0.7 s — measured 47 G warp instructions at 3.6 active threads for the tail of a
@@ -29,12 +30,12 @@
 #define BT_TAIL_MIN_BLOCKS 16      /* single-warp blocks per SM: 128 registers per thread */
 #endif
 
-__global__ void bt_tail_init_kernel(BtTailQ *q, const unsigned long long *count, uint32_t nslot, uint32_t cap, uint32_t *items, uint32_t quantum) {
+__global__ void bt_tail_init_kernel(BtTailQ *q, const unsigned long long *count, uint32_t nslot, uint32_t cap, uint32_t *items, uint32_t quantum, uint32_t wtarget, uint32_t mincap) {
 	unsigned long long n = *count;                                  /* the main pass counts past the last slot (those reads are re-run) */
 	if (n > nslot) n = nslot;
 	const uint32_t stride = gridDim.x * blockDim.x;
 	for (uint32_t k = blockIdx.x * blockDim.x + threadIdx.x; k < cap; k += stride) items[k] = k < n ? k : BT_TAILQ_EMPTY;
-	if (blockIdx.x == 0 && threadIdx.x == 0) { q->head = 0; q->tail = n; q->live = (long long)n; q->cap_mask = cap - 1; q->quantum = quantum; q->items = items; }
+	if (blockIdx.x == 0 && threadIdx.x == 0) { q->head = 0; q->tail = n; q->live = (long long)n; q->cap_mask = cap - 1; q->quantum = quantum; q->wtarget = wtarget; q->mincap = mincap; q->items = items; }
 }
 
 __global__ void __launch_bounds__(32, BT_TAIL_MIN_BLOCKS)
@@ -56,7 +57,7 @@ bt_tail_kernel(BtKParams P, BtTailQ *Q) {
 	L.K->nmuts = 0; L.K->mut0 = L.K->mut1 = L.K->mut2 = 0; L.ebwtSel = 0; L.lfk = 0; L.ltop = L.lbot = L.crow = 0; L.flags = 0; L.d = 0; L.qlen = 0;
 	L.rlen = 0; L.rseq = my_stage; L.rqual = my_stage; L.K->hasN = 1; L.K->step = 0; L.nit = 0;
 	volatile uint32_t *const items = Q->items;
-	const uint32_t cap_mask = Q->cap_mask, quantum = Q->quantum;
+	const uint32_t cap_mask = Q->cap_mask, quantum = Q->quantum, wtarget = Q->wtarget ? Q->wtarget : 1u, mincap = Q->mincap ? Q->mincap : 1u;
 	uint32_t *const snap = reinterpret_cast<uint32_t *>(my_stage + BT_SMEM_SNAP);
 	for (;;) {
 		if (__ballot_sync(0xffffffffu, L.pc != PC_EXIT) == 0) break;
@@ -89,8 +90,13 @@ bt_tail_kernel(BtKParams P, BtTailQ *Q) {
 			if (lane == 0) live = *reinterpret_cast<volatile long long *>(&Q->live);
 			live = __shfl_sync(0xffffffffu, live, 0);
 			const uint32_t hold = (uint32_t)__popc(__ballot_sync(0xffffffffu, L.pc != PC_NEXT_READ && L.pc != PC_EXIT));
-			const long long al = live - 32ll * (long long)wid;
-			const uint32_t allowed = al <= 0 ? 0u : (al > 32 ? 32u : (uint32_t)al);
+			/* reads per warp: as many as spread the live reads over `wtarget` warps, between `mincap` and 32 — packed while there are many
+			 * (throughput), thinning out towards the end, where the longest reads set the batch's latency and a full warp advances
+			 * each of its reads several times more slowly than a nearly empty one */
+			long long cap = (live + (long long)wtarget - 1) / (long long)wtarget;
+			cap = cap < (long long)mincap ? (long long)mincap : (cap > 32 ? 32 : cap);
+			const long long al = live - cap * (long long)wid;
+			const uint32_t allowed = al <= 0 ? 0u : (al > cap ? (uint32_t)cap : (uint32_t)al);
 			uint32_t take = 0;
 			unsigned long long h = 0;
 			if (live <= 0 || (allowed == 0 && hold == 0)) { if (want) L.pc = PC_EXIT; }        /* nothing left, or this warp's share is gone: leave */
@@ -142,8 +148,8 @@ bt_tail_kernel(BtKParams P, BtTailQ *Q) {
 
 /* Enqueues the tail of one batch on `st`: ring set-up from the main pass's slot count, then the kernel.  Returns the CUDA error code. */
 int bt_tail_launch(const BtKParams &P, BtTailQ *q, const unsigned long long *count, uint32_t nslot, uint32_t cap, uint32_t *items, uint32_t quantum,
-                   uint32_t blocks, cudaStream_t st) {
-	bt_tail_init_kernel<<<64, 256, 0, st>>>(q, count, nslot, cap, items, quantum);
+                   uint32_t wtarget, uint32_t mincap, uint32_t blocks, cudaStream_t st) {
+	bt_tail_init_kernel<<<64, 256, 0, st>>>(q, count, nslot, cap, items, quantum, wtarget, mincap);
 	bt_tail_kernel<<<blocks, 32, 32 * BT_SMEM_STRIDE, st>>>(P, q);
 	return (int)cudaGetLastError();
 }

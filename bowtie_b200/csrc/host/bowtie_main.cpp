@@ -1345,39 +1345,76 @@ int main(int argc, char **argv) {
 			}
 			if (!rd.first && rd.fast_ok()) {
 				const auto td0 = std::chrono::steady_clock::now();
-				bt_io_t *io[2] = { NULL, NULL };
-				for (int k = 0; k < 2; k++) if (bt_io_create(bt[k].cx, &io[k])) die(std::string("Error: ") + bt_last_error());
-				size_t chunk = 192u << 20;
+				/* NIO chunks in flight: the main thread reads the file and cuts records (bt_io_parse_fastq: the cut decides where the next
+				 * chunk starts), one thread per chunk searches and formats (bt_io_align_format, synchronous), outputs are written in chunk
+				 * order.  A batch's search ends with its slowest reads (~0.8 s per million on an hg19-sized index), so chunks must overlap. */
+				enum { NIO_MAX = 8 };
+				int NIO = 4;
+				if (const char *e = getenv("BT_CLI_IOS")) NIO = std::max(1, std::min<int>(NIO_MAX, atoi(e)));
+				struct Job { bt_io_t *io = NULL; bt_context_t *cx = NULL; std::thread th; bool busy = false; int rc = 0; std::string err; const char *text = NULL; uint64_t bytes = 0, cnt[4] = { 0, 0, 0, 0 }, foff = 0; uint64_t rdid0 = 0; uint32_t n = 0; };
+				Job jobs[NIO_MAX];
+				for (int k = 0; k < NIO; k++) {
+					if (k < NB) jobs[k].cx = bt[k].cx;
+					else if (bt_context_create(ix, &jobs[k].cx)) die(std::string("Error: ") + bt_last_error());
+					if (bt_io_create(jobs[k].cx, &jobs[k].io)) die(std::string("Error: ") + bt_last_error());
+				}
+				size_t chunk = 64u << 20;
 				if (const char *e = getenv("BT_CLI_CHUNK_MB")) chunk = (size_t)std::max(1l, atol(e)) << 20;
 				if (rd.buf.size() < chunk) rd.buf.resize(chunk);
 				bt_io_format_t fmt; memset(&fmt, 0, sizeof fmt);
 				fmt.sam = op.sam; fmt.no_unal = op.noUnal; fmt.no_qname_trunc = op.noQnameTrunc; fmt.full_ref = op.fullRef; fmt.off_base = op.offBase; fmt.mapq = (uint32_t)op.defaultMapq;
 				out.flush();
-				std::thread writer;
-				for (size_t k = 0;; k++) {
-					if (rd.pos > 0) { memmove(rd.buf.data(), rd.buf.data() + rd.pos, rd.len - rd.pos); rd.len -= rd.pos; rd.pos = 0; }
-					while (!rd.eof && rd.len < rd.buf.size()) {
-						const int got = gzread(rd.f, rd.buf.data() + rd.len, (unsigned)std::min<size_t>(rd.buf.size() - rd.len, (size_t)1 << 30));
-						if (got <= 0) { rd.eof = true; break; }
-						rd.len += (size_t)got;
+				uint64_t foff = (uint64_t)gztell(rd.f) - (uint64_t)(rd.len - rd.pos);      /* file offset (uncompressed) of the next unconsumed byte */
+				bool fallback = false;                                                      /* a chunk the device formatter does not cover: the host pipeline resumes at its first record */
+				/* finishes the oldest outstanding chunk: its text goes out, its counters count; returns false if it was not covered */
+				auto finish = [&](Job &j) -> bool {
+					j.th.join(); j.busy = false;
+					if (j.rc == 2) return false;
+					if (j.rc) die(std::string("Error: ") + j.err);
+					if (j.bytes) fwrite(j.text, 1, (size_t)j.bytes, out.fp);
+					numAligned += j.cnt[0]; numUnaligned += j.cnt[1]; numMaxed += j.cnt[2]; numReported += j.cnt[3];
+					n_dev_io += j.n;
+					return true;
+				};
+				size_t k = 0, done = 0;                                                      /* chunks started / finished */
+				bool more = true;
+				while (more || done < k) {
+					if (more && k - done < (size_t)NIO) {
+						if (rd.pos > 0) { memmove(rd.buf.data(), rd.buf.data() + rd.pos, rd.len - rd.pos); rd.len -= rd.pos; rd.pos = 0; }
+						while (!rd.eof && rd.len < rd.buf.size()) {
+							const int got = gzread(rd.f, rd.buf.data() + rd.len, (unsigned)std::min<size_t>(rd.buf.size() - rd.len, (size_t)1 << 30));
+							if (got <= 0) { rd.eof = true; break; }
+							rd.len += (size_t)got;
+						}
+						if (rd.len == 0) { more = false; continue; }
+						Job &j = jobs[k % NIO];
+						uint32_t n = 0; uint64_t used = 0; int irregular = 0;
+						if (bt_io_parse_fastq(j.io, rd.buf.data(), rd.len, op.seed, 0xffffffffu, &n, &used, &irregular)) die(std::string("Error: ") + bt_last_error());
+						if (n == 0) { more = false; continue; }
+						j.foff = foff; j.rdid0 = rd.rdid; j.n = n; j.rc = 0; j.busy = true;
+						const bt_policy_t *pp = &polU; const bt_io_format_t *pf = &fmt;
+						j.th = std::thread([&j, pp, pf]() {
+							j.rc = bt_io_align_format(j.io, pp, pf, &j.text, &j.bytes, j.cnt);
+							if (j.rc) j.err = bt_last_error();
+						});
+						rd.pos = (size_t)used; rd.rdid += n; foff += used;
+						k++;
+						if (irregular) more = false;
+						continue;
 					}
-					if (rd.len == 0) break;
-					uint32_t n = 0; uint64_t used = 0; int irregular = 0;
-					if (bt_io_parse_fastq(io[k & 1], rd.buf.data(), rd.len, op.seed, 0xffffffffu, &n, &used, &irregular)) die(std::string("Error: ") + bt_last_error());
-					if (n == 0) break;
-					const char *text = NULL; uint64_t bytes = 0, cnt[4] = { 0, 0, 0, 0 };
-					const int frc = bt_io_align_format(io[k & 1], &polU, &fmt, &text, &bytes, cnt);
-					if (frc == 2) break;                                               /* a batch the device formatter does not cover: the host pipeline takes over from this record on */
-					if (frc) die(std::string("Error: ") + bt_last_error());
-					if (writer.joinable()) writer.join();                              /* chunk k-1 is on disk: its buffer (the other io's) may be reused */
-					FILE *fp = out.fp;
-					writer = std::thread([fp, text, bytes]() { if (bytes) fwrite(text, 1, (size_t)bytes, fp); });
-					numAligned += cnt[0]; numUnaligned += cnt[1]; numMaxed += cnt[2]; numReported += cnt[3];
-					rd.pos = (size_t)used; rd.rdid += n; n_dev_io += n;
-					if (irregular) break;
+					Job &j = jobs[done % NIO];
+					if (!finish(j)) {
+						/* not covered: drop the chunks behind it and rewind the input to this chunk's first record */
+						for (size_t q = done + 1; q < k; q++) { jobs[q % NIO].th.join(); jobs[q % NIO].busy = false; }
+						if (gzseek(rd.f, (z_off_t)j.foff, SEEK_SET) < 0) die("Error: could not rewind the read file for the host output path");
+						rd.len = 0; rd.pos = 0; rd.eof = false; rd.rdid = j.rdid0;
+						fallback = true; k = done; more = false;
+						break;
+					}
+					done++;
 				}
-				if (writer.joinable()) writer.join();
-				for (int k = 0; k < 2; k++) bt_io_free(io[k]);
+				(void)fallback;
+				for (int q = 0; q < NIO; q++) { bt_io_free(jobs[q].io); if (q >= NB) bt_context_free(jobs[q].cx); }
 				t_dev_io = std::chrono::duration<double>(std::chrono::steady_clock::now() - td0).count();
 			}
 		}
