@@ -27,6 +27,7 @@ import argparse
 import fcntl
 import json
 import os
+import re
 import shutil
 import subprocess
 import sys
@@ -461,14 +462,23 @@ def cli_e2e(base: Path, h, n: int, td: Path, rr: "ReferenceRunner") -> dict:
     one = td / "one" / "s.fq"
     flags = ["-n", "2", "-k", "1", "-S"]
 
-    def run(cmd) -> float:
+    own: dict = {}
+
+    def run(cmd, timing: bool = False) -> float:
         t0 = time.time()
-        p = subprocess.run(cmd, capture_output=True, text=True)
+        p = subprocess.run(cmd, capture_output=True, text=True, env=dict(os.environ, BT_CLI_TIMING="1") if timing else None)
         if p.returncode != 0:
             raise RuntimeError("cli_e2e run failed: " + p.stderr[-300:])
+        if timing:                     # the program's own clock: "timing: index load X s, reads to output Y s"
+            m = re.search(r"timing: index load ([0-9.]+) s, reads to output ([0-9.]+) s", p.stderr)
+            if m:
+                own["index_load_s"], own["reads_to_output_s"] = float(m.group(1)), float(m.group(2))
+            m = re.search(r"device I/O chunks: [^\n]*", p.stderr)
+            if m:
+                own["device_io"] = m.group(0)
         return time.time() - t0
     o1 = min(run([str(exe), *flags, "-x", str(base), str(one), str(td / "o1.sam")]) for _ in range(2))
-    w = run([str(exe), *flags, "-x", str(base), str(fq), str(td / "ours.sam")])
+    w = run([str(exe), *flags, "-x", str(base), str(fq), str(td / "ours.sam")], timing=True)
     r1 = min(run([str(REF_DIR / "bowtie-align-s"), *flags, "-p", str(rr.threads), "-x", str(base), str(one), str(td / "r1.sam")]) for _ in range(2))
     rw = run([str(REF_DIR / "bowtie-align-s"), *flags, "-p", str(rr.threads), "-x", str(base), str(fq), str(td / "ref.sam")])
     same = None
@@ -487,7 +497,9 @@ def cli_e2e(base: Path, h, n: int, td: Path, rr: "ReferenceRunner") -> dict:
             (td / f).unlink()
         except Exception:
             pass
-    return {"reads": n, "flags": " ".join(flags), "value": n / max(1e-3, w - o1), "unit": "reads/s", "wall_s": round(w, 2), "start_and_index_load_s": round(o1, 2),
+    if "reads_to_output_s" in own:
+        own["value_by_own_clock"] = n / max(1e-3, own["reads_to_output_s"])       # index load varies by seconds between two runs on one box: the program's own split is the steadier basis
+    return {"reads": n, "flags": " ".join(flags), "value": n / max(1e-3, w - o1), "unit": "reads/s", "wall_s": round(w, 2), "start_and_index_load_s": round(o1, 2), "own_clock": own,
             "reference_value": n / max(1e-3, rw - r1), "reference_wall_s": round(rw, 2), "reference_start_and_index_load_s": round(r1, 2),
             "reference_threads": rr.threads, "sam_identical": same}
 
@@ -831,10 +843,19 @@ def main() -> None:
         achieved = alg / (m["ms"] / steps / 1e3) / 1e9
         ctr = [m["aligned"], B - m["aligned"], 0, m["aligned"] * R if R == 1 else 0, m["aligned"] * R if R == 2 else 0]   # counters of the last step (hit.h:169-175)
         ctr, ctr_how = allreduce_counters(ctr)                                                          # the path's only collective
+        # DRAM bytes per unit of the dominant kernel's launches, from the committed `ncu --set full` captures (profiles/): per step like `achieved`
+        traffic, traffic_src = None, None
+        try:
+            tj = json.loads((ROOT / "profiles" / "r2_traffic_per_unit.json").read_text()).get(name)
+            if tj:
+                traffic, traffic_src = float(tj["dram_bytes_per_unit"]) * B, tj["source"]
+        except Exception:
+            pass
         res = {"metric": pd["metric"], "value": value, "unit": unit, "ms_per_step": ms_max / steps, "steps": steps, "warmup": warmup,
                "workload": workload_name(pd, idx_name), "units_per_step_per_gpu": B, "batches_in_flight": NS,
                "e2e": {"value": B * steps * world / e2e_max, "unit": unit, "h2d_bytes_per_step": arm.h2d, "d2h_bytes_per_step": arm.d2h},
-               "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": None,
+               "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic, "traffic_source": traffic_src,
+                            "algorithmic_bytes_per_step": alg,
                             "peak_source": "MEASURED_PEAKS.json hbm_gbs" if peaks else "fallback 6650 GB/s",
                             "side_fetches_per_unit": st.side_fetches / (B * steps), "block_loads_per_unit": st.block_loads / (B * steps),
                             "algorithmic_bytes_per_unit": alg / B},

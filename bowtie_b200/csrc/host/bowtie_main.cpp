@@ -1353,11 +1353,12 @@ int main(int argc, char **argv) {
 				if (const char *e = getenv("BT_CLI_IOS")) NIO = std::max(1, std::min<int>(NIO_MAX, atoi(e)));
 				struct Job { bt_io_t *io = NULL; bt_context_t *cx = NULL; std::thread th; bool busy = false; int rc = 0; std::string err; const char *text = NULL; uint64_t bytes = 0, cnt[4] = { 0, 0, 0, 0 }, foff = 0; uint64_t rdid0 = 0; uint32_t n = 0; };
 				Job jobs[NIO_MAX];
-				for (int k = 0; k < NIO; k++) {
+				auto ensure_io = [&](int k) {                                                /* contexts own GBs of scratch: made only for the chunks that exist */
+					if (jobs[k].io) return;
 					if (k < NB) jobs[k].cx = bt[k].cx;
 					else if (bt_context_create(ix, &jobs[k].cx)) die(std::string("Error: ") + bt_last_error());
 					if (bt_io_create(jobs[k].cx, &jobs[k].io)) die(std::string("Error: ") + bt_last_error());
-				}
+				};
 				size_t chunk = 64u << 20;
 				if (const char *e = getenv("BT_CLI_CHUNK_MB")) chunk = (size_t)std::max(1l, atol(e)) << 20;
 				if (rd.buf.size() < chunk) rd.buf.resize(chunk);
@@ -1378,18 +1379,26 @@ int main(int argc, char **argv) {
 				};
 				size_t k = 0, done = 0;                                                      /* chunks started / finished */
 				bool more = true;
+				double t_rd = 0, t_parse = 0, t_wait = 0; const bool timing = getenv("BT_CLI_TIMING") != NULL;
+				auto now = []() { return std::chrono::steady_clock::now(); };
+				auto since = [&](std::chrono::steady_clock::time_point t0) { return std::chrono::duration<double>(now() - t0).count(); };
 				while (more || done < k) {
 					if (more && k - done < (size_t)NIO) {
+						auto t0 = now();
 						if (rd.pos > 0) { memmove(rd.buf.data(), rd.buf.data() + rd.pos, rd.len - rd.pos); rd.len -= rd.pos; rd.pos = 0; }
 						while (!rd.eof && rd.len < rd.buf.size()) {
 							const int got = gzread(rd.f, rd.buf.data() + rd.len, (unsigned)std::min<size_t>(rd.buf.size() - rd.len, (size_t)1 << 30));
 							if (got <= 0) { rd.eof = true; break; }
 							rd.len += (size_t)got;
 						}
+						t_rd += since(t0);
 						if (rd.len == 0) { more = false; continue; }
+						ensure_io((int)(k % NIO));
 						Job &j = jobs[k % NIO];
 						uint32_t n = 0; uint64_t used = 0; int irregular = 0;
+						t0 = now();
 						if (bt_io_parse_fastq(j.io, rd.buf.data(), rd.len, op.seed, 0xffffffffu, &n, &used, &irregular)) die(std::string("Error: ") + bt_last_error());
+						t_parse += since(t0);
 						if (n == 0) { more = false; continue; }
 						j.foff = foff; j.rdid0 = rd.rdid; j.n = n; j.rc = 0; j.busy = true;
 						const bt_policy_t *pp = &polU; const bt_io_format_t *pf = &fmt;
@@ -1403,7 +1412,10 @@ int main(int argc, char **argv) {
 						continue;
 					}
 					Job &j = jobs[done % NIO];
-					if (!finish(j)) {
+					auto t0 = now();
+					const bool okj = finish(j);
+					t_wait += since(t0);
+					if (!okj) {
 						/* not covered: drop the chunks behind it and rewind the input to this chunk's first record */
 						for (size_t q = done + 1; q < k; q++) { jobs[q % NIO].th.join(); jobs[q % NIO].busy = false; }
 						if (gzseek(rd.f, (z_off_t)j.foff, SEEK_SET) < 0) die("Error: could not rewind the read file for the host output path");
@@ -1414,7 +1426,8 @@ int main(int argc, char **argv) {
 					done++;
 				}
 				(void)fallback;
-				for (int q = 0; q < NIO; q++) { bt_io_free(jobs[q].io); if (q >= NB) bt_context_free(jobs[q].cx); }
+				if (timing) fprintf(stderr, "device I/O chunks: %d of <= %zu MB in flight, %zu chunks; reading %.2f s, cutting records %.2f s, waiting for search+format and writing %.2f s\n", NIO, chunk >> 20, k, t_rd, t_parse, t_wait);
+				for (int q = 0; q < NIO; q++) { if (jobs[q].io) bt_io_free(jobs[q].io); if (q >= NB && jobs[q].cx) bt_context_free(jobs[q].cx); }
 				t_dev_io = std::chrono::duration<double>(std::chrono::steady_clock::now() - td0).count();
 			}
 		}
@@ -1480,6 +1493,8 @@ int main(int argc, char **argv) {
 		else if (numReported > 0 && numReportedPaired == 0) fprintf(stderr, "Reported %llu alignments\n", (unsigned long long)numReported);
 		else fprintf(stderr, "Reported %llu paired-end alignments and %llu singleton alignments\n", (unsigned long long)(numReportedPaired >> 1), (unsigned long long)numReported);
 	}
+	if (getenv("BT_CLI_TIMING"))
+		fprintf(stderr, "timing: index load %.3f s, reads to output %.3f s\n", std::chrono::duration<double>(t_loaded - t_start).count(), std::chrono::duration<double>(t_end - t_loaded).count());
 	if (op.timing) {
 		auto secs = [](std::chrono::steady_clock::duration d) { return (long)std::chrono::duration_cast<std::chrono::seconds>(d).count(); };
 		long a = secs(t_loaded - t_start), s = secs(t_end - t_loaded), t = secs(t_end - t_start);

@@ -96,3 +96,31 @@ def test_bench_workload_matches_reference_hg19_sized(hg19_index, policy, n):
     if bench.index_len(hg19_index) > (1 << 31):
         tidx = np.array([v[1] for v in ref.values()])
         assert (tidx >= 20).any() and (tidx <= 2).any()
+
+
+def test_tail_modes_agree(idx256):
+    """The two ways of finishing the reads over the main pass's budget — re-run from scratch by one pass (default) and the round-robin
+    tail over checkpoint slots (BT_TAIL=rr, bt_tail.cu: suspension, ring, resumption on another SM) — must produce the same records.
+    A small main budget sends a few per cent of the reads through the tail (BT_MAIN_BUDGET=600; the default 8000 sends 0.7 %)."""
+    import subprocess
+    import sys
+    outs = {}
+    with tempfile.TemporaryDirectory() as td:
+        for mode, env_extra in (("restart", {"BT_TAIL": "restart"}), ("rr", {"BT_TAIL": "rr", "BT_TAIL_QUANTUM": "512"}), ("rr_dense", {"BT_TAIL": "rr", "BT_TAIL_WTARGET": "16", "BT_TAIL_MINCAP": "32"})):
+            env = {k: v for k, v in os.environ.items() if k != "LD_LIBRARY_PATH"}
+            env.update(env_extra); env["BT_MAIN_BUDGET"] = "600"
+            out = str(Path(td) / f"{mode}.npz")
+            p = subprocess.run([sys.executable, str(ROOT / "tests" / "tail_mode_child.py"), str(idx256), "150000", "99", out], env=env, capture_output=True, text=True, timeout=900)
+            assert p.returncode == 0, p.stderr[-2000:]
+            outs[mode] = dict(np.load(out))
+    a = outs["restart"]
+    assert (a["found"] > 0).mean() > 0.5 and not a["flags"].any()
+    for mode in ("rr", "rr_dense"):
+        b = outs[mode]
+        assert not b["flags"].any()
+        assert np.array_equal(a["found"], b["found"]), mode
+        rw = a["hits"].size // a["found"].size
+        ha, hb = a["hits"].reshape(-1, rw), b["hits"].reshape(-1, rw)
+        sel = a["found"] > 0
+        assert np.array_equal(ha[sel], hb[sel]), mode
+        assert int(b["side"][0]) <= int(a["side"][0])       # nothing is re-run: the round-robin tail never fetches more sides than the restart tail counts
