@@ -105,7 +105,7 @@ struct BtPolicy {
 #define BT_FLAG_HITS_OVF  8u   /* more reportable hits than slots      */
 #define BT_FLAG_MM_OVF   16u   /* more mismatches than the record holds */
 #define BT_FLAG_BUDGET  32u   /* (internal) iteration budget of the main pass exceeded: moved to the heavy pass */
-#define BT_FLAG_PREEMPT 64u   /* (internal, transient) the read leaves this pass with its state: checkpointed into a slot, resumed by the next slice */
+#define BT_FLAG_PREEMPT 64u   /* (internal, transient) the read leaves this pass with its state: checkpointed into a slot (or back into the tail's ring), resumed later */
 #define BT_FLAG_SCRATCH_OVF 7u
 #define BT_FLAG_RETRY (BT_FLAG_SCRATCH_OVF | BT_FLAG_BUDGET)
 
@@ -154,16 +154,14 @@ struct BtKParams {
 	uint32_t budget;              /* per-read transition budget of this pass (0 = unlimited)  */
 	uint32_t drain_budget;        /* ... once the pass's work queue is empty (0 = the same)    */
 	uint32_t rare_period, rare_thresh;   /* deferral of rare transitions in the thread-per-lane kernel */
-	/* Checkpoint slots (bt_ctxq.cuh): a read that exceeds its pass's budget (or fills its seedling list) is not re-run, it is
-	 * suspended — packed lane state, its copy of the read and its live scratch move into a slot — and the next, denser pass resumes
-	 * it.  slot_ctx == NULL: no slots, such reads are flagged and re-run from scratch by a later pass. */
+	/* Checkpoint slots (bt_ctxq.cuh; BT_TAIL=rr): a read that exceeds the main pass's budget (or fills its seedling list) is not
+	 * re-run, it is suspended — packed lane state, its copy of the read and its live scratch move into a slot — and the round-robin
+	 * tail (bt_tail.cu) resumes it.  slot_ctx == NULL (the default): no slots, such reads are flagged and re-run from scratch by the tail pass. */
 	uint32_t *slot_ctx;           /* BT_CTX_WORDS x nslot (word-major)                        */
 	uint4 *slot_rows; uint8_t *slot_elims; BtFrame *slot_frames; uint64_t *slot_partials; uint8_t *slot_stage;
 	uint32_t nslot, slot_R, slot_FCAP, slot_PCAP, slot_stage_len;
 	uint32_t resume;              /* 1: the work items are slot ids to resume; 0: read ids     */
-	unsigned long long *slice_count;   /* main pass: slots handed out so far (may run past nslot: those reads are flagged for a re-run);
-	                                    * a slice: length of slice_out                             */
-	uint32_t *slice_out;          /* a slice: the slots it suspended again = the next slice's work list */
+	unsigned long long *slot_count;    /* main pass: slots handed out so far (may run past nslot: those reads are flagged for a re-run) */
 	unsigned long long *stats;    /* [8]: lfex, lf, chase, ftab, offs, backtracks, iters, blockloads */
 };
 

@@ -73,7 +73,7 @@ BT_FN void bt_ctx_load(BtLane &L, const uint32_t *ctx, uint32_t nctx, uint32_t i
 /* ---- checkpoint slots ---------------------------------------------------------------------------------------------------------
  * A slot is everything a suspended read owns: the packed lane state above (word-major in P.slot_ctx), its writable copy of the read
  * (mutated by seedlings) and a private scratch set (rows / elims / frames / seedlings) with the capacities of the later passes.
- * The main pass suspends a read by copying what is live of its per-thread scratch into a fresh slot; the slices that follow work in
+ * The main pass suspends a read by copying what is live of its per-thread scratch into a fresh slot; the tail's turns that follow work in
  * the slot's own scratch, so suspending again costs only the 39 state words. */
 BT_FN void bt_slot_scratch(const BtKParams &P, uint32_t slot, BtScratch &S) {
 	S.rows = P.slot_rows + (size_t)slot * P.slot_R * 2;

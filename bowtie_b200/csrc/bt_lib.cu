@@ -181,9 +181,9 @@ bt_search_kernel(BtKParams P, BtWorkCtl *ctl) {
 			}
 			if (BT_IS_RARE_STEP(L.pc)) bt_rare_iter(L, P, S, budget);
 			if (L.flags & BT_FLAG_PREEMPT) {
-				/* over this pass's budget (or out of seedling space): suspend the read into a checkpoint slot; the next slice resumes it */
+				/* over this pass's budget (or out of seedling space): suspend the read into a checkpoint slot; the round-robin tail resumes it */
 				L.flags &= ~BT_FLAG_PREEMPT;
-				const unsigned long long p = atomicAdd(P.slice_count, 1ull);
+				const unsigned long long p = atomicAdd(P.slot_count, 1ull);
 				if (p < P.nslot) { bt_slot_save_new(L, P, S, (uint32_t)p); P.flags[L.K->rid] = 0; P.found[L.K->rid] = 0; L.pc = PC_NEXT_READ; }
 				else { L.flags |= BT_FLAG_BUDGET; L.pc = PC_FINISH_READ; }      /* no slot left: re-run from scratch by the overflow pass */
 			}
@@ -503,7 +503,7 @@ struct bt_index {
 struct bt_context {
 	bt_index *ix = nullptr;
 	Workspace ws1, wsh, ws2;     /* main pass / heavy-read pass / scratch-overflow pass */
-	BtWorkCtl *ctl = nullptr;    /* [BT_CTL_WORDS]: main pass, slices, overflow pass (best-first path: its four tiers) */
+	BtWorkCtl *ctl = nullptr;    /* [BT_CTL_WORDS]: main pass, tail, overflow pass (best-first path: its four tiers) */
 	Workspace wsl; uint32_t *slot_ctx = nullptr, *tailq_items = nullptr; BtTailQ *tailq = nullptr; uint32_t slot_cap = 0, tailq_cap = 0;   /* checkpoint slots (bt_ctxq.cuh) and the tail's ring (bt_tail.cu) */
 	uint32_t *heavy_sel = nullptr, *ultra_sel = nullptr, *retry_sel = nullptr; uint32_t retry_cap = 0;
 	cudaStream_t side = nullptr; /* the heavy and overflow passes run here, overlapping the next batch's main pass */
@@ -909,7 +909,7 @@ static int enqueue_align(bt_context *cx, const bt_policy_t *pol, const bt_read_b
 		}
 		nslot = cx->wsl.nthreads >= nslot ? nslot : cx->wsl.nthreads;
 	} else {
-		/* no slots (BT_SLICES=0, or the queue kernel): the tail pass re-runs heavy reads from scratch on full-size scratch */
+		/* no slots (the default, or the queue kernel): the tail pass re-runs heavy reads from scratch on full-size scratch */
 		static const uint32_t tail_bps = env_u32("BT_TAIL_BLOCKS", 2);
 		if (ensure_ws(cx->wsh, (uint32_t)ix->sms * tail_bps * BT_THREADS, 6 * maxlen + 8 + 17 * mask_rows, 16, 4096, stage_len)) return 1;
 	}
@@ -931,7 +931,7 @@ static int enqueue_align(bt_context *cx, const bt_policy_t *pol, const bt_read_b
 	P.found = out->found; P.flags = out->flags; P.hits = out->hits; P.slots = out->slots; P.mm_cap = out->mm_cap; P.rec_words = BT_HIT_HDR + out->mm_cap;
 	P.stats = ix->stats; P.mask_rows = mask_rows;
 	const uint32_t cblocks = (nwork + 255) / 256;
-	BtWorkCtl *const ctl_main = cx->ctl, *const ctl_slice = cx->ctl + 1, *const ctl_ovf = cx->ctl + 2;   /* ctl_slice: the suspended reads' slot count (round-robin tail), or the restart pass's work list */
+	BtWorkCtl *const ctl_main = cx->ctl, *const ctl_tail = cx->ctl + 1, *const ctl_ovf = cx->ctl + 2;   /* ctl_tail: the suspended reads' slot count (round-robin tail), or the restart pass's work list */
 	/* this context's previous batch must have finished with the scratch and the lists */
 	CUDA_TRY(cudaStreamWaitEvent(st, cx->ev_tail, 0));
 	/* main pass */
@@ -943,7 +943,7 @@ static int enqueue_align(bt_context *cx, const bt_policy_t *pol, const bt_read_b
 	if (use_slots) {
 		P.slot_ctx = cx->slot_ctx; P.slot_rows = cx->wsl.rows; P.slot_elims = cx->wsl.elims; P.slot_frames = cx->wsl.frames; P.slot_partials = cx->wsl.partials;
 		P.slot_stage = cx->wsl.stage; P.nslot = nslot; P.slot_R = cx->wsl.R; P.slot_FCAP = cx->wsl.FCAP; P.slot_PCAP = cx->wsl.PCAP; P.slot_stage_len = cx->wsl.stage_len;
-		P.resume = 0; P.slice_count = &ctl_slice[0].nwork; P.slice_out = nullptr;
+		P.resume = 0; P.slot_count = &ctl_tail[0].nwork;
 	}
 	if (main_kernel_is_queue()) {
 		uint32_t grid = (uint32_t)ix->sms;
@@ -967,12 +967,12 @@ static int enqueue_align(bt_context *cx, const bt_policy_t *pol, const bt_read_b
 		P.resume = 1; P.drain_budget = 0; P.budget = 0; P.sel = nullptr;
 		P.R = cx->wsl.R; P.FCAP = cx->wsl.FCAP; P.PCAP = cx->wsl.PCAP; P.stage = nullptr; P.stage_len = cx->wsl.stage_len;
 		P.rows = nullptr; P.elims = nullptr; P.frames = nullptr; P.partials = nullptr;
-		if (bt_tail_launch(P, cx->tailq, &ctl_slice[0].nwork, nslot, cx->tailq_cap, cx->tailq_items, quantum ? quantum : 4096, wtarget, mincap, blocks, cx->side) != 0) return fail("bt_tail_launch failed");
+		if (bt_tail_launch(P, cx->tailq, &ctl_tail[0].nwork, nslot, cx->tailq_cap, cx->tailq_items, quantum ? quantum : 4096, wtarget, mincap, blocks, cx->side) != 0) return fail("bt_tail_launch failed");
 		P.resume = 0; P.slot_ctx = nullptr;
 		/* what is flagged now: scratch overflow in a slot, or no free slot */
 		bt_collect_kernel<<<cblocks, 256, 0, cx->side>>>(out->flags, in->sel, nwork, nullptr, BT_FLAG_RETRY, cx->retry_sel, ctl_ovf);
 	} else {
-		bt_collect_kernel<<<cblocks, 256, 0, cx->side>>>(out->flags, in->sel, nwork, nullptr, BT_FLAG_RETRY, cx->heavy_sel, ctl_slice);
+		bt_collect_kernel<<<cblocks, 256, 0, cx->side>>>(out->flags, in->sel, nwork, nullptr, BT_FLAG_RETRY, cx->heavy_sel, ctl_tail);
 		set_ws(P, cx->wsh);
 		P.sel = cx->heavy_sel; P.budget = 0; P.drain_budget = 0;
 		{
@@ -980,9 +980,9 @@ static int enqueue_align(bt_context *cx, const bt_policy_t *pol, const bt_read_b
 			 * (registers and shared memory of its whole block) is what the other batches' main passes cannot use meanwhile */
 			static const uint32_t tt = env_u32("BT_TAIL_THREADS", BT_THREADS);
 			const uint32_t threads = (tt >= 32 && tt <= BT_THREADS && tt % 32 == 0) ? tt : BT_THREADS;
-			bt_search_kernel<<<cx->wsh.nthreads / threads, threads, threads * BT_SMEM_STRIDE, cx->side>>>(P, ctl_slice);
+			bt_search_kernel<<<cx->wsh.nthreads / threads, threads, threads * BT_SMEM_STRIDE, cx->side>>>(P, ctl_tail);
 		}
-		bt_collect_kernel<<<cblocks, 256, 0, cx->side>>>(out->flags, cx->heavy_sel, nwork, ctl_slice, BT_FLAG_SCRATCH_OVF, cx->retry_sel, ctl_ovf);
+		bt_collect_kernel<<<cblocks, 256, 0, cx->side>>>(out->flags, cx->heavy_sel, nwork, ctl_tail, BT_FLAG_SCRATCH_OVF, cx->retry_sel, ctl_ovf);
 	}
 	P.sel = cx->retry_sel; P.budget = 0; P.drain_budget = 0;
 	set_ws(P, cx->ws2);

@@ -109,3 +109,20 @@ def test_time_sliced_search_synthetic(pol, emu, oracle, synth_index):
     assert not flags.any()
     ok, why = results_equal(a, b)
     assert ok, why
+
+
+@pytest.mark.parametrize("pol", [Policy(mode=1, mms=2), Policy(mode=0, mms=2), Policy(mode=1, mms=3, khits=2, maq_round=False, qual_thresh=120)], ids=lambda p: " ".join(p.ref_args()))
+def test_long_reads_live_mask_rows(pol, emu, oracle, synth_index):
+    """Reads of 200-600 bases: every frame's live-position mask (bt_live_mask, one row per 256 positions below the frame's rowbase) spans
+    several rows, and the backtrack-target scan / next-lowest-quality re-scan walk its words from the top — output and operation
+    counters equal the oracle's position-by-position loops."""
+    from synth import synth_reads
+    base, genome = synth_index
+    batch = synth_reads(genome, 120, (200, 600), seed=21, sub_rate=0.02, n_rate=0.002, qual_profile="low")
+    a = oracle.align(base, batch, pol)
+    b, flags = emu.align(base, batch, pol, mm_cap=96, FCAP=64, PCAP=4096, R=60000)
+    assert not flags.any()
+    ok, why = results_equal(a, b)
+    assert ok, why
+    for k in ("lfex", "lf", "chase", "ftab", "offs", "backtracks"):
+        assert a.stats[k] == b.stats[k], k
