@@ -4,6 +4,7 @@
  * (CUB reduce / select / scan: library code off the search path) and the entry points.
  */
 #include <cuda_runtime.h>
+#include <utility>
 #include <cub/cub.cuh>
 #include <thrust/iterator/counting_iterator.h>
 #include <thrust/iterator/transform_iterator.h>
@@ -27,6 +28,7 @@ struct BioIsNlPred { const char *t; __host__ __device__ __forceinline__ bool ope
 
 struct BioCuda {
 	cudaStream_t st = nullptr; bt_context_t *cx = nullptr;
+	cudaStream_t st_hi = nullptr;        /* highest priority: record cutting (small kernels) must not queue behind other chunks' search kernels, which fill the machine */
 	void *tmp = nullptr; size_t tmp_bytes = 0;
 	unsigned long long *d_num = nullptr;
 	char *pinned = nullptr; size_t pinned_cap = 0;
@@ -91,7 +93,7 @@ struct BioCuda {
 		}
 		return pinned;
 	}
-	void destroy() { cudaFree(tmp); cudaFree(d_num); if (pinned) cudaFreeHost(pinned); if (st) cudaStreamDestroy(st); }
+	void destroy() { cudaFree(tmp); cudaFree(d_num); if (pinned) cudaFreeHost(pinned); if (st) cudaStreamDestroy(st); if (st_hi) cudaStreamDestroy(st_hi); }
 };
 
 struct bt_io { BioPipe<BioCuda> pipe; int device = 0; };
@@ -111,7 +113,10 @@ extern "C" int bt_io_create(bt_context_t *cx, bt_io_t **out) {
 	bt_io *io = new bt_io();
 	io->device = dev; io->pipe.be.cx = cx;
 	cudaDeviceGetAttribute(&io->pipe.be.sms, cudaDevAttrMultiProcessorCount, dev);
-	if (cudaStreamCreateWithFlags(&io->pipe.be.st, cudaStreamNonBlocking) != cudaSuccess || !io->pipe.init()) { io->pipe.destroy(); io->pipe.be.destroy(); delete io; return bt_internal_fail("bt_io_create: CUDA resource allocation failed"); }
+	int prLo = 0, prHi = 0;
+	cudaDeviceGetStreamPriorityRange(&prLo, &prHi);                          /* numerically lower = higher priority */
+	if (cudaStreamCreateWithFlags(&io->pipe.be.st, cudaStreamNonBlocking) != cudaSuccess ||
+	    cudaStreamCreateWithPriority(&io->pipe.be.st_hi, cudaStreamNonBlocking, prHi) != cudaSuccess || !io->pipe.init()) { io->pipe.destroy(); io->pipe.be.destroy(); delete io; return bt_internal_fail("bt_io_create: CUDA resource allocation failed"); }
 	bt_index_t *ix = bt_internal_context_index(cx);
 	bt_index_info_t info;
 	bt_index_info(ix, &info);
@@ -129,7 +134,13 @@ extern "C" void bt_io_free(bt_io_t *io) {
 extern "C" int bt_io_parse_fastq(bt_io_t *io, const char *text, uint64_t nbytes, uint32_t global_seed, uint32_t max_reads, uint32_t *nreads, uint64_t *consumed, int *irregular) {
 	if (!io || (!text && nbytes) || !nreads || !consumed || !irregular) return bt_internal_fail("bt_io_parse_fastq: null argument");
 	if (cudaSetDevice(io->device) != cudaSuccess) return bt_internal_fail("bt_io_parse_fastq: cudaSetDevice failed");
-	if (!io->pipe.parse(text, nbytes, global_seed, max_reads, nreads, consumed, irregular) || io->pipe.be.e != cudaSuccess) return io_fail(io, "bt_io_parse_fastq");
+	/* the whole parse runs on the high-priority stream and ends with a synchronising read-back, so the search (on the io's ordinary
+	 * stream) always starts after it */
+	std::swap(io->pipe.be.st, io->pipe.be.st_hi);
+	const bool ok = io->pipe.parse(text, nbytes, global_seed, max_reads, nreads, consumed, irregular);
+	io->pipe.be.sync();
+	std::swap(io->pipe.be.st, io->pipe.be.st_hi);
+	if (!ok || io->pipe.be.e != cudaSuccess) return io_fail(io, "bt_io_parse_fastq");
 	return 0;
 }
 extern "C" int bt_io_align_format(bt_io_t *io, const bt_policy_t *pol, const bt_io_format_t *fmt, const char **out_text, uint64_t *out_bytes, uint64_t counters[4]) {
