@@ -722,7 +722,7 @@ def measure(arm: Arm, steps: int, warmup: int, barrier, allmax, clock_gpus=None)
 def main() -> None:
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--steps", type=int, default=6)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--reads-per-step", type=int, default=int(os.environ.get("BT_BENCH_READS", 8_000_000)))
