@@ -917,7 +917,7 @@ def main() -> None:
     head = run_policy(args.policy, B, NS, args.steps, args.warmup, True)
     others = {}
     if args.policy == "n2k1" and not args.no_others:
-        for name, b, ns in (("best", 2_000_000, 6), ("paired", 1_000_000, 6)):      # batch sizes from profiles/r2_kbench_call10.jsonl      # every context of the best-first path owns several GB of arenas
+        for name, b, ns in (("best", 2_000_000, 6), ("paired", 1_000_000, 6)):      # batch sizes from profiles/r2_kbench_call10.jsonl (the arenas are one pool per index)
             try:
                 others[name] = run_policy(name, min(b, B), min(ns, args.steps), min(args.steps, 6), min(args.warmup, 3), False)
             except Exception as ex:
