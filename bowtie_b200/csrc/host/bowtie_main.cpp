@@ -1386,8 +1386,8 @@ int main(int argc, char **argv) {
 					if (more && k - done < (size_t)NIO) {
 						auto t0 = now();
 						if (rd.pos > 0) { memmove(rd.buf.data(), rd.buf.data() + rd.pos, rd.len - rd.pos); rd.len -= rd.pos; rd.pos = 0; }
-						while (!rd.eof && rd.len < rd.buf.size()) {
-							const int got = gzread(rd.f, rd.buf.data() + rd.len, (unsigned)std::min<size_t>(rd.buf.size() - rd.len, (size_t)1 << 30));
+						while (!rd.eof && rd.len < chunk) {                                  /* (the buffer may be larger than a chunk: the chunk size is what is in flight per io) */
+							const int got = gzread(rd.f, rd.buf.data() + rd.len, (unsigned)std::min<size_t>(chunk - rd.len, (size_t)1 << 30));
 							if (got <= 0) { rd.eof = true; break; }
 							rd.len += (size_t)got;
 						}
@@ -1397,7 +1397,7 @@ int main(int argc, char **argv) {
 						Job &j = jobs[k % NIO];
 						uint32_t n = 0; uint64_t used = 0; int irregular = 0;
 						t0 = now();
-						if (bt_io_parse_fastq(j.io, rd.buf.data(), rd.len, op.seed, 0xffffffffu, &n, &used, &irregular)) die(std::string("Error: ") + bt_last_error());
+						if (bt_io_parse_fastq(j.io, rd.buf.data(), std::min(rd.len, chunk), op.seed, 0xffffffffu, &n, &used, &irregular)) die(std::string("Error: ") + bt_last_error());
 						t_parse += since(t0);
 						if (n == 0) { more = false; continue; }
 						j.foff = foff; j.rdid0 = rd.rdid; j.n = n; j.rc = 0; j.busy = true;

@@ -145,3 +145,25 @@ def test_device_io_chunks_and_gzip_host_emulation(tools, tmp_path):
 def test_device_io_matches_reference_gpu(tools, tmp_path, idx):
     env = {k: v for k, v in os.environ.items() if k not in ("LD_LIBRARY_PATH", "BOWTIE_B200_LIB")}
     _run_case(env, tmp_path, idx, dict(CASES[idx][0]), CASES[idx][1], chunk_mb=1)
+
+
+FUZZ_R2 = [("c1", ["-n", "3", "-l", "5", "-e", "400", "--norc"]), ("c2", ["-n", "0", "-l", "5", "-e", "400", "-m", "2", "-k", "3", "--best", "-y"])]
+
+
+@pytest.mark.parametrize("case,flags", FUZZ_R2, ids=[c for c, _ in FUZZ_R2])
+def test_batches_beyond_the_device_formatter_fall_back_to_the_host_path(tools, tmp_path, case, flags):
+    """Two finds of the round-2 differential fuzzer (tests/golden/fuzz_r2: tiny genomes, reads with zero-penalty qualities): with `-e 400`
+    a read can align with more mismatches than the device formatter's records hold (32).  bt_io_align_format then returns 2 and
+    produces nothing; the driver rewinds the input to that chunk's first record and the host pipeline formats it — the output must
+    still be the reference's, byte for byte (the driver used to stop with an error here)."""
+    build_shim()
+    d = ROOT / "tests" / "golden" / "fuzz_r2"
+    base = tmp_path / "g"
+    subprocess.run([str(ROOT / "oracle" / "_ref" / "bowtie-build-s"), "-q", str(d / f"{case}.fa"), str(base)], check=True, capture_output=True)
+    outs = []
+    for exe, ev in ((CLI, dict(os.environ, LD_LIBRARY_PATH=str(SHIM_DIR))), (REF, os.environ)):
+        o = tmp_path / f"o{len(outs)}.out"
+        p = subprocess.run([str(exe), *flags, "-x", str(base), str(d / f"{case}.fq"), str(o)], capture_output=True, text=True, env=ev)
+        assert p.returncode == 0, p.stderr[-300:]
+        outs.append((o.read_bytes(), [l for l in p.stderr.splitlines() if l.startswith("#") or l.startswith("Reported")]))
+    assert outs[0] == outs[1]
