@@ -1123,6 +1123,13 @@ extern "C" int bt_stats_get(bt_index_t *ix, bt_stats_t *out, int reset) {
 	return 0;
 }
 
+extern "C" void *bt_host_alloc(size_t bytes) {
+	void *p = nullptr;
+	if (cudaHostAlloc(&p, bytes ? bytes : 1, cudaHostAllocPortable) != cudaSuccess) { cudaGetLastError(); fail("bt_host_alloc: cudaHostAlloc failed"); return nullptr; }
+	return p;
+}
+extern "C" void bt_host_free(void *p) { if (p) cudaFreeHost(p); }
+
 extern "C" int bt_debug_lf(bt_index_t *ix, int mirror, const uint32_t *rows, uint32_t n, uint32_t *out) {
 	if (!ix || !rows || !out) return fail("bt_debug_lf: null argument");
 	if (mirror && !ix->has_mirror) return fail("bt_debug_lf: mirror index not loaded");

@@ -407,7 +407,8 @@ struct Reader {
 	std::vector<FqSpan> spans_;
 	double t_scan = 0, t_work = 0;      /* BT_CLI_TIMING */
 	bool fast_ok() const { return o.format == FASTQ && f && !first && !keepOrig && pending.empty() && o.trim5 == 0 && o.trim3 == 0 && !o.solexaQuals && !o.phred64Quals && !o.integerQuals; }
-	size_t fast_batch(std::vector<ReadRec> &recs, std::vector<uint32_t> &seeds, std::vector<uint8_t> &bseq, std::vector<uint8_t> &bqual, std::vector<uint64_t> &boffs,
+	template <class V32, class V8, class V64>          /* (the batch's arrays: vectors over page-locked memory) */
+	size_t fast_batch(std::vector<ReadRec> &recs, V32 &seeds, V8 &bseq, V8 &bqual, V64 &boffs,
 	                  size_t maxRecs, size_t nth, uint32_t gseed) {
 		std::vector<FqSpan> &spans = spans_;        /* (a member: worker threads must see this thread's list) */
 		spans.clear();
@@ -992,11 +993,24 @@ static void sam_headers(std::string &o, const Opts &op, const bt_index_t *ix, ui
 /* ---------------------------------------------------------------------------------------------- */
 /* batches                                                                                         */
 /* ---------------------------------------------------------------------------------------------- */
+/* The arrays that travel to and from the device live in page-locked memory (bt_host_alloc): bt_context_align_async's copies are
+ * asynchronous only then, which is what lets the search of batch k+1 overlap the formatting of batch k. */
+template <class T> struct PinAlloc {
+	typedef T value_type;
+	PinAlloc() {}
+	template <class U> PinAlloc(const PinAlloc<U> &) {}
+	T *allocate(size_t n) { void *p = bt_host_alloc(n * sizeof(T)); if (!p) throw std::bad_alloc(); return (T *)p; }
+	void deallocate(T *p, size_t) { bt_host_free(p); }
+	template <class U> bool operator==(const PinAlloc<U> &) const { return true; }
+	template <class U> bool operator!=(const PinAlloc<U> &) const { return false; }
+};
+template <class T> using PinVec = std::vector<T, PinAlloc<T>>;
+
 struct Batch {
 	bool paired = false;           /* every unit of the batch is a pair (mates adjacent) */
 	std::vector<ReadRec> reads;
-	std::vector<uint8_t> seq, qual; std::vector<uint64_t> offs; std::vector<uint32_t> seeds;
-	std::vector<uint32_t> found, flags, hits;
+	PinVec<uint8_t> seq, qual; PinVec<uint64_t> offs; PinVec<uint32_t> seeds;
+	PinVec<uint32_t> found, flags, hits;
 	uint32_t slots = 1, mm_cap = 8;
 	bt_context_t *cx = NULL;
 	bool inflight = false;

@@ -206,6 +206,11 @@ int  bt_counters_allreduce(void *nccl_comm, uint64_t counters[5], void *stream);
  * (fchr[c] + occ(c,row)) for c = 0..3 and rowL.  rows/out are host arrays; out has 5 words per row. */
 int  bt_debug_lf(bt_index_t *ix, int mirror, const uint32_t *rows, uint32_t n, uint32_t *out);
 
+/* Page-locked host memory for the buffers of bt_context_align_async (whose copies are asynchronous only from / to pinned memory;
+ * with pageable buffers the call is correct but returns only when its last copy has completed).  NULL when the allocation fails. */
+void *bt_host_alloc(size_t bytes);
+void  bt_host_free(void *p);
+
 #ifdef __cplusplus
 }
 #endif

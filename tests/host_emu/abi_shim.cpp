@@ -151,6 +151,8 @@ int bt_context_sync(bt_context_t *, void *) { return 0; }
 int bt_context_join(bt_context_t *, void *) { return 0; }
 int bt_stats_get(bt_index_t *ix, bt_stats_t *out, int) { *out = ix->st; return 0; }
 int bt_debug_lf(bt_index_t *, int, const uint32_t *, uint32_t, uint32_t *) { g_err = "not in the shim"; return 1; }
+void *bt_host_alloc(size_t bytes) { return malloc(bytes ? bytes : 1); }
+void bt_host_free(void *p) { free(p); }
 /* index construction: the product's host code (bt_build.h) and per-element device code (bt_build_sa.cuh) over the host backend */
 int bt_index_build(const char *const *fasta_paths, uint32_t n_paths, const char *out_base, int off_rate, int ftab_chars, int) {
 	std::vector<std::string> files;
