@@ -864,7 +864,10 @@ def main() -> None:
                "rank_ms_per_step": {"min": m["ms_ranks"][0] / steps, "median": m["ms_ranks"][len(m["ms_ranks"]) // 2] / steps, "max": ms_max / steps},
                # per step: ctl_set x4, main search, collect, tail search, collect x2, ultra search, collect, overflow search
                # (best-first / paired: ctl_set x4, 4 arena tiers, 3 collects)
-               "gpu_launches": (12 if name in ("n2k1", "v0") else 11) * steps}
+               # kernels of this repository inside the timed region, per step (one batch): DFS path = bt_ctl_set_all_kernel, bt_search_kernel (main),
+               # bt_collect_kernel, bt_search_kernel (tail), bt_collect_kernel, bt_search_kernel (overflow); best-first / paired path =
+               # bt_ctl_set_all_kernel, 4 x bt_best_kernel (arena tiers), 3 x bt_collect_kernel (profiles/r2_launches_*.csv)
+               "gpu_launches": (6 if name in ("n2k1", "v0") else 8) * steps}
         if m["clocks"] is not None:
             res["clocks"] = m["clocks"]
         # latency of ONE synchronous batch through bt_align_batch (the INTEGRATION.md stub's call): host buffers in, host buffers out
